@@ -1,0 +1,129 @@
+/* dbslmm_b200.h -- C ABI of the B200-native DBSLMM per-LD-block fit.
+ *
+ * This is the drop-in boundary for ONE path of fboehm/DBSLMM: the block estimation
+ * DBSLMMFIT::est -> calcBlock -> estBlock -> PCG (scr/dbslmmfit.cpp:56-770) fed by
+ * IO::readSNPIm + SNPPROC::nomalizeVec (scr/dtpr.cpp:285-380).  Every entry point
+ * takes plain host pointers and sizes (caller-owned), returns an int status and never
+ * throws.  One handle drives one GPU; LD blocks are independent, so multi-GPU use is
+ * "one handle per GPU, each given its own shard of blocks" (dbslmm_b200_plan_shards).
+ * There is no CPU fallback: without a CUDA device every call fails with
+ * DBSLMM_B200_ERR_CUDA.
+ *
+ * Reference interface each entry point replaces (paths relative to the reference):
+ *   dbslmm_b200_load_bed     the per-block `ifstream bed_in(bed_str)` opens and per-byte
+ *                            reads of IO::readSNPIm          scr/dbslmmfit.cpp:384, scr/dtpr.cpp:302-315
+ *   dbslmm_b200_snp_stats    the MAF pre-pass of IO::readBim  scr/dtpr.cpp:93-102
+ *   dbslmm_b200_plan_shards  the batch-of-60 OpenMP scheduler scr/dbslmmfit.cpp:92-96,189-193
+ *   dbslmm_b200_fit          both DBSLMMFIT::est overloads    scr/dbslmmfit.hpp:38-67
+ *                            (calcBlock/estBlock/PCGv/PCGm inside)
+ */
+#ifndef DBSLMM_B200_H
+#define DBSLMM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DBSLMM_B200_ABI_VERSION 1
+
+/* status codes: 0 ok; <0 failure; >0 (fit only) number of blocks whose status != 0 */
+#define DBSLMM_B200_OK            0
+#define DBSLMM_B200_ERR_CUDA     (-1)   /* no device / CUDA runtime error (see last_error) */
+#define DBSLMM_B200_ERR_ARG      (-2)   /* bad argument                                    */
+#define DBSLMM_B200_ERR_STATE    (-3)   /* call order (e.g. fit before load_bed)           */
+#define DBSLMM_B200_ERR_NOMEM    (-4)   /* device or host allocation failed                */
+
+/* per-block status bits written to block_status_out */
+#define DBSLMM_B200_BLK_OK          0
+#define DBSLMM_B200_BLK_NOT_SPD     1   /* Cholesky pivot <= 0 or NaN (monomorphic SNP => NaN column,
+                                           the reference poisons the whole block the same way)      */
+#define DBSLMM_B200_BLK_PCG_MAXITER 2   /* PCG hit maxiter ("Matrix is Singular", dbslmmfit.cpp:664) */
+
+/* solver selection */
+#define DBSLMM_B200_SOLVER_CHOLESKY 0   /* exact: batched FP64 Cholesky of the bordered block system  */
+#define DBSLMM_B200_SOLVER_PCG      1   /* reference-faithful Jacobi-PCG, tol 1e-7, maxiter 1000       */
+
+typedef struct dbslmm_b200_handle dbslmm_b200_handle;
+
+/* Device-side phase times of the last fit, CUDA events on the library's own stream (ms). */
+typedef struct dbslmm_b200_timing {
+    float h2d_ms;        /* plan + z upload                                   */
+    float decode_ms;     /* genotype decoder kernel(s)                        */
+    float gram_ms;       /* correlation builder kernel(s)                     */
+    float solve_ms;      /* block solver (all folds): factor + substitutions  */
+    float d2h_ms;        /* beta download                                     */
+    float total_ms;      /* first event to last event                         */
+    int32_t n_launches;  /* kernels launched by this library in the fit       */
+    int32_t n_chol_launches;
+    double gram_ops;     /* algorithmic int8 ops  (2*n_pad*m*(m+1)/2 per plain block, x4 planes if missing) */
+    double solve_flops;  /* algorithmic FP64 flop (m^3/3 + 2 m^2 per block and fold)                       */
+    double decode_bytes; /* algorithmic bytes read + written by the decoder                                */
+    double chol_ms;      /* factorisation kernels only (subset of solve_ms), summed over folds             */
+} dbslmm_b200_timing;
+
+typedef struct dbslmm_b200_fit_args {
+    int32_t  n_blocks;        /* blocks in this call (an m==0 block is a legal no-op)               */
+    const int32_t* s_off;     /* [n_blocks+1] CSR offsets of small-effect SNPs                       */
+    const int32_t* s_pos;     /* [s_off[n_blocks]] .bed row (INFO::pos) of each small SNP            */
+    const double*  s_z;       /* [..] z-score (INFO::z)                                              */
+    const int32_t* l_off;     /* NULL => small-only overload (LMM mode) for every block              */
+    const int32_t* l_pos;
+    const double*  l_z;
+    int32_t  n_folds;         /* >=1: heritability folds sharing one Gram per block                  */
+    const double* sigma_s;    /* [n_folds] h2/nsnp per fold (dbslmm.cpp:332)                          */
+    int64_t  n_obs;           /* GWAS sample size (-n)                                               */
+    double   tau;             /* LD shrinkage, 0.8 in the reference (dbslmmfit.cpp:697)              */
+    int32_t  solver;          /* DBSLMM_B200_SOLVER_*                                                */
+    int32_t  flags;           /* DBSLMM_B200_FLAG_*                                                  */
+    double*  beta_s_out;      /* [n_folds][s_off[n_blocks]]                                          */
+    double*  beta_l_out;      /* [n_folds][l_off[n_blocks]] or NULL                                  */
+    int32_t* block_status_out;/* [n_blocks] or NULL                                                  */
+    dbslmm_b200_timing* timing; /* or NULL                                                           */
+} dbslmm_b200_fit_args;
+
+#define DBSLMM_B200_FLAG_KEEP_INT_GRAM 1  /* also keep raw int32 Gram planes for dbslmm_b200_get_block_gram */
+#define DBSLMM_B200_FLAG_FULL_SIGMA    2  /* write both triangles of Sigma (implied by the PCG solver)       */
+#define DBSLMM_B200_FLAG_PLAN_CACHED   4  /* reuse the device plan of the previous fit (same CSR arrays)     */
+
+int  dbslmm_b200_abi_version(void);
+int  dbslmm_b200_device_count(void);
+
+int  dbslmm_b200_create(int device, dbslmm_b200_handle** out);
+void dbslmm_b200_destroy(dbslmm_b200_handle* h);
+const char* dbslmm_b200_last_error(const dbslmm_b200_handle* h);
+
+/* Reference panel.  `bed` points just after the 3 magic bytes of a SNP-major PLINK .bed
+ * (pitch = ceil(n_ref/4) bytes per SNP).  Copies to the device and runs the statistics
+ * kernel (per-SNP allele sum, sum of squares, non-missing count). */
+int  dbslmm_b200_load_bed(dbslmm_b200_handle* h, const uint8_t* bed, int64_t n_snp, int32_t n_ref);
+
+/* MAF pre-pass product (dtpr.cpp:93-102, 361-362): maf after mean imputation; optional
+ * non-missing counts.  Both arrays have n_snp entries. */
+int  dbslmm_b200_snp_stats(dbslmm_b200_handle* h, double* maf_out, int32_t* n_nonmiss_out);
+
+/* Block scheduler: O(n m^2 + m^3) cost model, longest-processing-time-first onto n_ranks.
+ * m_s/m_l are per-block SNP counts (m_l may be NULL).  owner_out[b] in [0, n_ranks). */
+int  dbslmm_b200_plan_shards(int32_t n_blocks, const int32_t* m_s, const int32_t* m_l,
+                             int32_t n_ref, int32_t n_ranks, int32_t* owner_out, double* rank_cost_out);
+
+int  dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* args);
+
+/* ---- inspection hooks used by the parity tests (operate on the state of the last fit) ---- */
+/* int8 codes of one decoded row of the last fit (row = global row index in block order:
+ * block b's rows are its small SNPs then its large SNPs); n_pad bytes. */
+int  dbslmm_b200_get_row_codes(dbslmm_b200_handle* h, int64_t row, int8_t* codes_out, int32_t n_out);
+/* Sigma of block b as dense row-major m x m (m = m_s + m_l, small SNPs first).  Lower triangle is
+ * always valid; the upper one only with FLAG_FULL_SIGMA / PCG solver (else mirrored on the host). */
+int  dbslmm_b200_get_block_sigma(dbslmm_b200_handle* h, int32_t block, double* sigma_out);
+/* raw integer Gram planes (needs FLAG_KEEP_INT_GRAM): Q = G G^T, A_ij = sum g_i M_j, N = M M^T;
+ * A and N may be NULL; for blocks without missing calls A_ij = S_i and N = n_ref. */
+int  dbslmm_b200_get_block_gram(dbslmm_b200_handle* h, int32_t block, int32_t* q_out, int32_t* a_out, int32_t* n_out);
+/* PCG iteration count of block b in the last PCG-solver fit (max over its right-hand sides). */
+int  dbslmm_b200_get_block_iters(dbslmm_b200_handle* h, int32_t block);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DBSLMM_B200_H */

@@ -1,0 +1,151 @@
+"""ctypes binding of the CPU oracle (oracle/liboracle.so).
+
+TEST INFRASTRUCTURE ONLY: importable from tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py.  The product package (dbslmm_b200)
+never imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+MODE_REF = 0    # PCG exactly as dbslmmfit.cpp:629-668 + the reference's beta_s form
+MODE_EXACT = 1  # Cholesky + direct form
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liboracle.so")
+    src = os.path.join(_HERE, "dbslmm_oracle.cpp")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(so):
+            build()
+        _LIB = C.CDLL(so)
+        _LIB.orc_read_snp_im.restype = C.c_int
+        _LIB.orc_est_block.restype = C.c_int
+        _LIB.orc_est.restype = C.c_int
+        _LIB.orc_pcgv.restype = C.c_int
+        _LIB.orc_num_threads.restype = C.c_int
+    return _LIB
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _bed(bed):
+    bed = np.ascontiguousarray(bed, dtype=np.uint8)
+    return bed
+
+
+def read_snp_im(bed, pos, n_total, indicator=None):
+    """IO::readSNPIm: returns (geno[kept], maf)."""
+    bed = _bed(bed)
+    ind = None if indicator is None else np.ascontiguousarray(indicator, dtype=np.int32)
+    n_keep = n_total if ind is None else int(ind.sum())
+    g = np.zeros(n_keep, dtype=np.float64)
+    maf = C.c_double(0.0)
+    lib().orc_read_snp_im(_p(bed), C.c_int64(pos), C.c_int(n_total), _p(ind), _p(g), C.byref(maf))
+    return g, maf.value
+
+
+def normalize(x):
+    x = np.array(x, dtype=np.float64, copy=True)
+    lib().orc_normalize(_p(x), C.c_int(x.size))
+    return x
+
+
+def gram_int(bed, n_ref, pos):
+    bed = _bed(bed)
+    pos = np.ascontiguousarray(pos, dtype=np.int32)
+    m = pos.size
+    Q = np.zeros((m, m), np.int32)
+    A = np.zeros((m, m), np.int32)
+    N = np.zeros((m, m), np.int32)
+    lib().orc_gram_int(_p(bed), C.c_int(n_ref), _p(pos), C.c_int(m), _p(Q), _p(A), _p(N))
+    return Q, A, N
+
+
+def snp_maf(bed, n_snp, n_ref):
+    bed = _bed(bed)
+    maf = np.zeros(n_snp, np.float64)
+    lib().orc_snp_maf(_p(bed), C.c_int64(n_snp), C.c_int(n_ref), _p(maf))
+    return maf
+
+
+def sigma(bed, n_ref, pos, tau=0.8):
+    bed = _bed(bed)
+    pos = np.ascontiguousarray(pos, dtype=np.int32)
+    m = pos.size
+    S = np.zeros((m, m), np.float64)
+    lib().orc_sigma(_p(bed), C.c_int(n_ref), _p(pos), C.c_int(m), C.c_double(tau), _p(S))
+    return S
+
+
+def pcgv(A, b, maxiter=1000, tol=1e-7):
+    A = np.asfortranarray(A, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    x = np.zeros_like(b)
+    it = lib().orc_pcgv(_p(A), _p(b), C.c_int(b.size), C.c_int(maxiter), C.c_double(tol), _p(x))
+    return x, it
+
+
+def est_block(bed, n_ref, n_obs, sigma_s, pos_s, z_s, pos_l=None, z_l=None, mode=MODE_REF, tau=0.8):
+    bed = _bed(bed)
+    pos_s = np.ascontiguousarray(pos_s, dtype=np.int32)
+    z_s = np.ascontiguousarray(z_s, dtype=np.float64)
+    ms = pos_s.size
+    ml = 0 if pos_l is None else len(pos_l)
+    if ml:
+        pos_l = np.ascontiguousarray(pos_l, dtype=np.int32)
+        z_l = np.ascontiguousarray(z_l, dtype=np.float64)
+    else:
+        pos_l = z_l = None
+    bs = np.zeros(ms, np.float64)
+    bl = np.zeros(max(ml, 1), np.float64)
+    sing = C.c_int(0)
+    it = lib().orc_est_block(_p(bed), C.c_int(n_ref), C.c_int(n_obs), C.c_double(sigma_s), C.c_double(tau),
+                             _p(pos_s), _p(z_s), C.c_int(ms), _p(pos_l), _p(z_l), C.c_int(ml), C.c_int(mode),
+                             _p(bs), _p(bl), C.byref(sing))
+    return bs, bl[:ml], it, sing.value
+
+
+def est(bed, n_ref, n_obs, sigma_s, s_off, s_pos, s_z, l_off=None, l_pos=None, l_z=None,
+        threads=1, mode=MODE_REF, tau=0.8):
+    """DBSLMMFIT::est over CSR blocks. Returns (beta_s, beta_l, n_singular, max_iters)."""
+    bed = _bed(bed)
+    s_off = np.ascontiguousarray(s_off, dtype=np.int32)
+    s_pos = np.ascontiguousarray(s_pos, dtype=np.int32)
+    s_z = np.ascontiguousarray(s_z, dtype=np.float64)
+    nb = s_off.size - 1
+    bs = np.zeros(s_pos.size, np.float64)
+    if l_off is not None:
+        l_off = np.ascontiguousarray(l_off, dtype=np.int32)
+        l_pos = np.ascontiguousarray(l_pos, dtype=np.int32)
+        l_z = np.ascontiguousarray(l_z, dtype=np.float64)
+        bl = np.zeros(max(l_pos.size, 1), np.float64)
+        nl = l_pos.size
+    else:
+        l_pos = l_z = None
+        bl = np.zeros(1, np.float64)
+        nl = 0
+    mi = C.c_int(0)
+    sing = lib().orc_est(_p(bed), C.c_int(n_ref), C.c_int(n_obs), C.c_double(sigma_s), C.c_double(tau),
+                         C.c_int(nb), _p(s_off), _p(s_pos), _p(s_z), _p(l_off), _p(l_pos), _p(l_z),
+                         C.c_int(threads), C.c_int(mode), _p(bs), _p(bl), C.byref(mi))
+    return bs, bl[:nl], sing, mi.value
+
+
+def num_threads():
+    return lib().orc_num_threads()
