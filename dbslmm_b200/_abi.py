@@ -1,0 +1,188 @@
+"""ctypes binding of libdbslmm_b200.so (the C ABI in include/dbslmm_b200.h).
+
+The product path has no CPU fallback: if the shared library is missing or no B200 is
+visible, constructing an Engine raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libdbslmm_b200.so")
+
+SOLVER_CHOLESKY = 0
+SOLVER_PCG = 1
+FLAG_KEEP_INT_GRAM = 1
+FLAG_FULL_SIGMA = 2
+FLAG_PLAN_CACHED = 4
+
+EXPORTS = [
+    "dbslmm_b200_abi_version", "dbslmm_b200_device_count", "dbslmm_b200_create", "dbslmm_b200_destroy",
+    "dbslmm_b200_last_error", "dbslmm_b200_load_bed", "dbslmm_b200_snp_stats", "dbslmm_b200_plan_shards",
+    "dbslmm_b200_fit", "dbslmm_b200_get_row_codes", "dbslmm_b200_get_block_sigma",
+    "dbslmm_b200_get_block_gram", "dbslmm_b200_get_block_iters",
+]
+
+
+class Timing(C.Structure):
+    _fields_ = [("h2d_ms", C.c_float), ("decode_ms", C.c_float), ("gram_ms", C.c_float),
+                ("solve_ms", C.c_float), ("d2h_ms", C.c_float), ("total_ms", C.c_float),
+                ("n_launches", C.c_int32), ("n_chol_launches", C.c_int32),
+                ("gram_ops", C.c_double), ("solve_flops", C.c_double), ("decode_bytes", C.c_double),
+                ("chol_ms", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class FitArgs(C.Structure):
+    _fields_ = [("n_blocks", C.c_int32), ("s_off", C.c_void_p), ("s_pos", C.c_void_p), ("s_z", C.c_void_p),
+                ("l_off", C.c_void_p), ("l_pos", C.c_void_p), ("l_z", C.c_void_p),
+                ("n_folds", C.c_int32), ("sigma_s", C.c_void_p), ("n_obs", C.c_int64), ("tau", C.c_double),
+                ("solver", C.c_int32), ("flags", C.c_int32),
+                ("beta_s_out", C.c_void_p), ("beta_l_out", C.c_void_p), ("block_status_out", C.c_void_p),
+                ("timing", C.POINTER(Timing))]
+
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: run `python -m dbslmm_b200.build` "
+                               "(the B200 path has no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        lib.dbslmm_b200_last_error.restype = C.c_char_p
+        lib.dbslmm_b200_last_error.argtypes = [C.c_void_p]
+        lib.dbslmm_b200_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        lib.dbslmm_b200_destroy.argtypes = [C.c_void_p]
+        lib.dbslmm_b200_destroy.restype = None
+        lib.dbslmm_b200_load_bed.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32]
+        lib.dbslmm_b200_snp_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.dbslmm_b200_plan_shards.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                                C.c_void_p, C.c_void_p]
+        lib.dbslmm_b200_fit.argtypes = [C.c_void_p, C.POINTER(FitArgs)]
+        lib.dbslmm_b200_get_row_codes.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32]
+        lib.dbslmm_b200_get_block_sigma.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        lib.dbslmm_b200_get_block_gram.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.dbslmm_b200_get_block_iters.argtypes = [C.c_void_p, C.c_int32]
+        _lib = lib
+    return _lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class Engine:
+    """One handle = one GPU."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        h = C.c_void_p()
+        rc = self.lib.dbslmm_b200_create(int(device), C.byref(h))
+        if rc != 0:
+            raise EngineError(f"dbslmm_b200_create(device={device}) failed with {rc}: no usable sm_100 GPU "
+                              "(there is no CPU fallback)")
+        self.h = h
+        self.n_snp = 0
+        self.n_ref = 0
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.dbslmm_b200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc < 0:
+            raise EngineError(f"{what} failed ({rc}): {self.lib.dbslmm_b200_last_error(self.h).decode()}")
+        return rc
+
+    def load_bed(self, bed, n_ref):
+        """bed: uint8[n_snp, ceil(n_ref/4)] -- payload after the 3 magic bytes (numpy or pinned torch-backed)."""
+        bed = np.ascontiguousarray(bed, dtype=np.uint8)
+        pitch = (n_ref + 3) // 4
+        n_snp = bed.size // pitch
+        self._check(self.lib.dbslmm_b200_load_bed(self.h, bed.ctypes.data, n_snp, n_ref), "load_bed")
+        self.n_snp, self.n_ref = n_snp, n_ref
+
+    def snp_stats(self):
+        maf = np.zeros(self.n_snp, np.float64)
+        nn = np.zeros(self.n_snp, np.int32)
+        self._check(self.lib.dbslmm_b200_snp_stats(self.h, maf.ctypes.data, nn.ctypes.data), "snp_stats")
+        return maf, nn
+
+    def plan_shards(self, m_s, m_l, n_ref, n_ranks):
+        m_s = np.ascontiguousarray(m_s, np.int32)
+        m_l = None if m_l is None else np.ascontiguousarray(m_l, np.int32)
+        owner = np.zeros(m_s.size, np.int32)
+        cost = np.zeros(n_ranks, np.float64)
+        rc = self.lib.dbslmm_b200_plan_shards(m_s.size, m_s.ctypes.data, _ptr(m_l), n_ref, n_ranks,
+                                              owner.ctypes.data, cost.ctypes.data)
+        if rc != 0:
+            raise EngineError(f"plan_shards failed ({rc})")
+        return owner, cost
+
+    def fit(self, s_off, s_pos, s_z, l_off=None, l_pos=None, l_z=None, *, sigma_s, n_obs, tau=0.8,
+            solver=SOLVER_CHOLESKY, flags=0):
+        """Returns dict(beta_s[n_folds, S], beta_l[n_folds, L], status[n_blocks], n_bad, timing)."""
+        s_off = np.ascontiguousarray(s_off, np.int32)
+        s_pos = np.ascontiguousarray(s_pos, np.int32)
+        s_z = np.ascontiguousarray(s_z, np.float64)
+        nb = s_off.size - 1
+        sig = np.atleast_1d(np.asarray(sigma_s, np.float64)).copy()
+        nf = sig.size
+        beta_s = np.zeros((nf, s_pos.size), np.float64)
+        if l_off is not None:
+            l_off = np.ascontiguousarray(l_off, np.int32)
+            l_pos = np.ascontiguousarray(l_pos, np.int32)
+            l_z = np.ascontiguousarray(l_z, np.float64)
+            beta_l = np.zeros((nf, max(l_pos.size, 1)), np.float64)
+            nl = l_pos.size
+        else:
+            beta_l = None
+            nl = 0
+        status = np.zeros(max(nb, 1), np.int32)
+        tm = Timing()
+        a = FitArgs(nb, s_off.ctypes.data, _ptr(s_pos), _ptr(s_z), _ptr(l_off), _ptr(l_pos), _ptr(l_z),
+                    nf, sig.ctypes.data, int(n_obs), float(tau), int(solver), int(flags),
+                    beta_s.ctypes.data, _ptr(beta_l), status.ctypes.data, C.pointer(tm))
+        rc = self._check(self.lib.dbslmm_b200_fit(self.h, C.byref(a)), "fit")
+        return {"beta_s": beta_s, "beta_l": None if beta_l is None else beta_l[:, :nl], "status": status[:nb],
+                "n_bad": rc, "timing": tm.as_dict()}
+
+    # ---- inspection hooks (parity tests)
+    def row_codes(self, row, n):
+        out = np.zeros(n, np.int8)
+        self._check(self.lib.dbslmm_b200_get_row_codes(self.h, int(row), out.ctypes.data, n), "get_row_codes")
+        return out
+
+    def block_sigma(self, block, m):
+        out = np.zeros((m, m), np.float64)
+        self._check(self.lib.dbslmm_b200_get_block_sigma(self.h, int(block), out.ctypes.data), "get_block_sigma")
+        return out
+
+    def block_gram(self, block, m):
+        q = np.zeros((m, m), np.int32)
+        a = np.zeros((m, m), np.int32)
+        n = np.zeros((m, m), np.int32)
+        self._check(self.lib.dbslmm_b200_get_block_gram(self.h, int(block), q.ctypes.data, a.ctypes.data,
+                                                        n.ctypes.data), "get_block_gram")
+        return q, a, n
+
+    def block_iters(self, block):
+        return self._check(self.lib.dbslmm_b200_get_block_iters(self.h, int(block)), "get_block_iters")

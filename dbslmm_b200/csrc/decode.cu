@@ -1,0 +1,228 @@
+// decode.cu -- genotype decoder (K1) and per-SNP statistics (the MAF pre-pass, a3).
+//
+// Replaces IO::readSNPIm + SNPPROC::nomalizeVec (reference scr/dtpr.cpp:285-380): instead
+// of one ifstream::read per byte and an FP64 column per SNP, each warp stages one .bed row
+// into shared memory with a 1-D TMA bulk copy (cp.async.bulk, double buffered on
+// mbarriers), unpacks sixteen 2-bit codes per lane with bit arithmetic and writes int8
+// allele counts with coalesced 16-byte stores.  Standardisation is NOT applied here: it is
+// folded into the Gram epilogue as exact integer arithmetic (gram.cu); the decoder only
+// emits the per-row scale factor.
+//
+// Code map (dtpr.cpp:329-350): 2-bit v = b0 + 2*b1, low bits first within a byte:
+//   v=0 -> 2, v=2 -> 1, v=3 -> 0, v=1 -> missing (genotype plane 0, mask plane 0).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace dbslmm {
+
+static constexpr int kWarpsPerCta = 8;
+
+struct RowStage {
+    // returns byte offset of the row inside the staged buffer
+    __device__ static __forceinline__ uint32_t issue(const uint8_t* bed, int64_t row, int32_t pitch,
+                                                     uint8_t* buf, uint64_t* bar, int lane) {
+        const int64_t s = row * (int64_t)pitch;
+        const int64_t a0 = s & ~(int64_t)15;
+        const uint32_t nbytes = (uint32_t)(((s + pitch + 15) & ~(int64_t)15) - a0);
+        if (lane == 0) {
+            mbar_expect_tx(bar, nbytes);
+            bulk_g2s(buf, bed + a0, nbytes, bar);
+        }
+        return (uint32_t)(s - a0);
+    }
+};
+
+// 32-bit word `i` of a row that starts `off` bytes into the 16-byte aligned staging buffer
+__device__ __forceinline__ uint32_t row_word(const uint32_t* w32, uint32_t off, int i) {
+    const uint32_t idx = (off >> 2) + i;
+    const uint32_t lo = w32[idx], hi = w32[idx + 1];
+    return __funnelshift_r(lo, hi, (off & 3u) * 8u);
+}
+
+// mask with the low 2*k bits set, k = number of valid samples in word i (0..16)
+__device__ __forceinline__ uint32_t valid_bits(int n_ref, int i) {
+    int k = n_ref - 16 * i;
+    k = k < 0 ? 0 : (k > 16 ? 16 : k);
+    return k == 16 ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u);
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-SNP statistics over the whole .bed: non-missing count, allele sum, sum of squares.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+snp_stats_kernel(const uint8_t* __restrict__ bed, int64_t n_snp, int32_t n_ref, int32_t pitch,
+                 int32_t buf_bytes, SnpStat* __restrict__ stats) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bars[kWarpsPerCta][2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* buf0 = smem + (size_t)warp * 2 * buf_bytes;
+    uint8_t* bufs[2] = {buf0, buf0 + buf_bytes};
+    if (lane == 0) { mbar_init(&bars[warp][0], 1); mbar_init(&bars[warp][1], 1); }
+    mbar_fence_init();
+    __syncwarp();
+
+    const int64_t gw = (int64_t)blockIdx.x * kWarpsPerCta + warp;
+    const int64_t stride = (int64_t)gridDim.x * kWarpsPerCta;
+    const int nwords = (pitch + 3) >> 2;
+    uint32_t phase[2] = {0, 0};
+    uint32_t off[2] = {0, 0};
+    int cur = 0;
+    int64_t row = gw;
+    if (row < n_snp) off[0] = RowStage::issue(bed, row, pitch, bufs[0], &bars[warp][0], lane);
+    for (; row < n_snp; row += stride) {
+        const int64_t nxt = row + stride;
+        if (nxt < n_snp) off[cur ^ 1] = RowStage::issue(bed, nxt, pitch, bufs[cur ^ 1], &bars[warp][cur ^ 1], lane);
+        mbar_wait(&bars[warp][cur], phase[cur]);
+        phase[cur] ^= 1;
+        const uint32_t* w32 = reinterpret_cast<const uint32_t*>(bufs[cur]);
+        int c0 = 0, c1 = 0, c2 = 0;
+        for (int i = lane; i < nwords; i += 32) {
+            uint32_t w = row_word(w32, off[cur], i);
+            w |= ~valid_bits(n_ref, i);                // samples past n_ref -> code 3 (counts nothing)
+            const uint32_t lo = w & 0x55555555u, hi = (w >> 1) & 0x55555555u;
+            c0 += __popc(~(lo | hi) & 0x55555555u);    // code 0 -> allele count 2
+            c1 += __popc(lo & ~hi);                    // code 1 -> missing
+            c2 += __popc(hi & ~lo);                    // code 2 -> allele count 1
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+            c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+            c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+        }
+        if (lane == 0) {
+            SnpStat s;
+            s.n_nonmiss = n_ref - c1;
+            s.sum = 2 * c0 + c2;
+            s.sumsq = 4 * c0 + c2;
+            s.pad = 0;
+            stats[row] = s;
+        }
+        __syncwarp();
+        cur ^= 1;
+    }
+}
+
+// four 2-bit codes of byte x -> allele-count bytes / mask bytes
+__device__ __forceinline__ void expand4(uint32_t x, uint32_t& g, uint32_t& m) {
+    const uint32_t t = (x | (x << 6) | (x << 12) | (x << 18)) & 0x03030303u;
+    const uint32_t b0 = t & 0x01010101u, b1 = (t >> 1) & 0x01010101u;
+    const uint32_t nb0 = b0 ^ 0x01010101u;
+    g = (nb0 << 1) - (nb0 & b1);   // (1-b0)*(2-b1): 0->2, 2->1, 1/3->0
+    m = nb0 | b1;                  // 0 only for code 1 (missing)
+}
+
+// ------------------------------------------------------------------------------------------
+// Decoder: one warp per output code row.  row_src[r] = bed row | (mask plane ? 1<<31 : 0);
+// row_g[r] = SNP-row index that receives the scale factors (or -1 for mask rows).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+decode_rows_kernel(const uint8_t* __restrict__ bed, int32_t n_ref, int32_t pitch, int32_t n_pad,
+                   int32_t buf_bytes, const uint32_t* __restrict__ row_src, const int32_t* __restrict__ row_g,
+                   int64_t n_rows, const SnpStat* __restrict__ stats, double tau,
+                   int8_t* __restrict__ codes, int32_t* __restrict__ rowN, int32_t* __restrict__ rowS,
+                   double* __restrict__ rowR) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bars[kWarpsPerCta][2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* buf0 = smem + (size_t)warp * 2 * buf_bytes;
+    uint8_t* bufs[2] = {buf0, buf0 + buf_bytes};
+    if (lane == 0) { mbar_init(&bars[warp][0], 1); mbar_init(&bars[warp][1], 1); }
+    mbar_fence_init();
+    __syncwarp();
+
+    const int64_t gw = (int64_t)blockIdx.x * kWarpsPerCta + warp;
+    const int64_t stride = (int64_t)gridDim.x * kWarpsPerCta;
+    const int nwords = (pitch + 3) >> 2;     // input words holding real samples
+    const int nout = n_pad >> 4;             // 16-byte output chunks per row
+    uint32_t phase[2] = {0, 0};
+    uint32_t off[2] = {0, 0};
+    int cur = 0;
+    int64_t row = gw;
+    if (row < n_rows)
+        off[0] = RowStage::issue(bed, (int64_t)(row_src[row] & 0x7FFFFFFFu), pitch, bufs[0], &bars[warp][0], lane);
+    for (; row < n_rows; row += stride) {
+        const int64_t nxt = row + stride;
+        if (nxt < n_rows)
+            off[cur ^ 1] = RowStage::issue(bed, (int64_t)(row_src[nxt] & 0x7FFFFFFFu), pitch, bufs[cur ^ 1],
+                                           &bars[warp][cur ^ 1], lane);
+        const uint32_t src = row_src[row];
+        const bool mask_plane = (src >> 31) != 0;
+        mbar_wait(&bars[warp][cur], phase[cur]);
+        phase[cur] ^= 1;
+        const uint32_t* w32 = reinterpret_cast<const uint32_t*>(bufs[cur]);
+        uint4* out = reinterpret_cast<uint4*>(codes + (size_t)row * n_pad);
+        for (int i = lane; i < nout; i += 32) {
+            uint4 o = make_uint4(0u, 0u, 0u, 0u);
+            if (i < nwords) {
+                uint32_t w = row_word(w32, off[cur], i);
+                const uint32_t vb = valid_bits(n_ref, i);
+                w = (w & vb) | (0x55555555u & ~vb);    // samples past n_ref -> "missing": 0 in both planes
+                uint32_t g0, g1, g2, g3, m0, m1, m2, m3;
+                expand4(w & 0xFFu, g0, m0);
+                expand4((w >> 8) & 0xFFu, g1, m1);
+                expand4((w >> 16) & 0xFFu, g2, m2);
+                expand4(w >> 24, g3, m3);
+                o = mask_plane ? make_uint4(m0, m1, m2, m3) : make_uint4(g0, g1, g2, g3);
+            }
+            out[i] = o;
+        }
+        if (lane == 0) {
+            const int32_t g = row_g[row];
+            if (g >= 0) {
+                const SnpStat s = stats[src & 0x7FFFFFFFu];
+                const double ni = (double)s.n_nonmiss;
+                // d = n_i * sum g^2 - (sum g)^2  (exact integer), r = sqrt(tau (n-1) / (n n_i d))
+                const double d = ni * (double)s.sumsq - (double)s.sum * (double)s.sum;
+                const double n = (double)n_ref;
+                rowN[g] = s.n_nonmiss;
+                rowS[g] = s.sum;
+                rowR[g] = sqrt(tau * (n - 1.0) / (n * ni * d));
+            }
+        }
+        __syncwarp();
+        cur ^= 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------
+static int stage_bytes(int32_t pitch) { return ((pitch + 15 + 16 + 15) / 16) * 16 + 16; }
+
+cudaError_t launch_snp_stats(const uint8_t* bed, int64_t n_snp, int32_t n_ref, SnpStat* stats, int n_sm,
+                             cudaStream_t st) {
+    const int32_t pitch = (n_ref + 3) / 4;
+    const int buf = stage_bytes(pitch);
+    const size_t smem = (size_t)kWarpsPerCta * 2 * buf;
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(snp_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int64_t ctas = (n_snp + kWarpsPerCta - 1) / kWarpsPerCta;
+    const int64_t cap = (int64_t)n_sm * 8;
+    if (ctas > cap) ctas = cap;
+    if (ctas < 1) ctas = 1;
+    snp_stats_kernel<<<(unsigned)ctas, kWarpsPerCta * 32, smem, st>>>(bed, n_snp, n_ref, pitch, buf, stats);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_decode_rows(const uint8_t* bed, int32_t n_ref, int32_t n_pad, const uint32_t* row_src,
+                               const int32_t* row_g, int64_t n_rows, const SnpStat* stats, double tau,
+                               int8_t* codes, int32_t* rowN, int32_t* rowS, double* rowR, int n_sm,
+                               cudaStream_t st) {
+    if (n_rows == 0) return cudaSuccess;
+    const int32_t pitch = (n_ref + 3) / 4;
+    const int buf = stage_bytes(pitch);
+    const size_t smem = (size_t)kWarpsPerCta * 2 * buf;
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(decode_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int64_t ctas = (n_rows + kWarpsPerCta - 1) / kWarpsPerCta;
+    const int64_t cap = (int64_t)n_sm * 8;
+    if (ctas > cap) ctas = cap;
+    decode_rows_kernel<<<(unsigned)ctas, kWarpsPerCta * 32, smem, st>>>(bed, n_ref, pitch, n_pad, buf, row_src, row_g,
+                                                                      n_rows, stats, tau, codes, rowN, rowS, rowR);
+    return cudaGetLastError();
+}
+
+}  // namespace dbslmm

@@ -1,0 +1,707 @@
+// engine.cu -- C-ABI implementation: handle, device workspace, block plan (the scheduler side of
+// DBSLMMFIT::est, reference scr/dbslmmfit.cpp:56-244) and the launch sequence of one fit.
+//
+// Host work per fit: walk the CSR block lists once, lay the blocks out in device memory
+// (int8 code rows, one row-major FP64 matrix per block), build the tile / panel work lists,
+// ship everything in ONE pinned blob, launch decode -> gram -> (per fold) cholesky steps ->
+// back substitution, and read the betas back.  No CPU arithmetic on the data path: without a
+// CUDA device every entry point fails.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include <cudaTypedefs.h>
+#include "../../include/dbslmm_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace dbslmm;
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        const size_t want = bytes + bytes / 16 + 4096;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        const size_t want = bytes + bytes / 8 + 4096;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+constexpr int kNumClasses = 4;                 // size classes of the Cholesky step loop (by #panels)
+constexpr int kClassMaxPanels[kNumClasses] = {8, 16, 32, 1 << 30};
+
+struct StepList { int32_t diag_off, n_diag, panel_off, n_panel; };
+
+struct Plan {
+    int32_t n_blocks = 0;
+    int64_t n_snp_rows = 0;       // total SNP rows (sum m)
+    int64_t n_code_rows = 0;      // genotype + mask rows
+    int64_t mat_doubles = 0;      // total doubles of all block matrices
+    int64_t tot_s = 0, tot_l = 0;
+    int32_t max_mp = 0;
+    std::vector<BlockDesc> blocks;
+    std::vector<int32_t> order;                       // blocks by descending size
+    int32_t n_tiles_plain = 0, n_tiles_miss = 0;
+    std::vector<StepList> steps[kNumClasses];         // per class, per panel step
+    // blob layout (byte offsets inside the plan blob, identical on host and device)
+    size_t o_blocks = 0, o_rowsrc = 0, o_rowg = 0, o_z = 0, o_tiles_plain = 0, o_tiles_miss = 0, o_order = 0,
+           o_diag = 0, o_panel = 0, blob_bytes = 0;
+    double gram_ops = 0, solve_flops = 0, decode_bytes = 0;
+    bool valid = false;
+};
+
+}  // namespace
+
+struct dbslmm_b200_handle {
+    int device = 0;
+    int n_sm = 148;
+    cudaStream_t stream = nullptr;
+    cudaStream_t cls_stream[kNumClasses] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[8] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[kNumClasses] = {};
+    std::string err;
+    // reference panel
+    DevBuf bed, stats;
+    std::vector<SnpStat> h_stats;
+    int64_t n_snp = 0;
+    int32_t n_ref = 0, pitch = 0, n_pad = 0;
+    // workspace
+    DevBuf codes, sigma, lbuf, rowN, rowS, rowR, planblob, beta, status, intQ, intA, intN, scratch;
+    PinBuf h_blob, h_out;
+    Plan plan;
+    int32_t last_flags = 0, last_solver = 0, last_nfolds = 0;
+    PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+};
+
+namespace {
+
+int fail(dbslmm_b200_handle* h, int code, const std::string& msg) {
+    if (h) h->err = msg;
+    return code;
+}
+#define CU_TRY(h, expr)                                                                             \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            return fail(h, (_e == cudaErrorMemoryAllocation) ? DBSLMM_B200_ERR_NOMEM : DBSLMM_B200_ERR_CUDA, \
+                        std::string(#expr) + ": " + cudaGetErrorString(_e));                        \
+    } while (0)
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ------------------------------------------------------------------------------------------
+// Plan construction (host): the block scheduler's bookkeeping
+// ------------------------------------------------------------------------------------------
+int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, std::vector<uint8_t>& blob) {
+    const int nb = a->n_blocks;
+    P = Plan();
+    P.n_blocks = nb;
+    P.blocks.resize(nb);
+    P.tot_s = a->s_off[nb];
+    P.tot_l = a->l_off ? a->l_off[nb] : 0;
+    const int64_t n_snp = h->n_snp;
+    int64_t goff = 0, croff = 0, moff = 0;
+    for (int b = 0; b < nb; ++b) {
+        const int ms = a->s_off[b + 1] - a->s_off[b];
+        const int ml = a->l_off ? a->l_off[b + 1] - a->l_off[b] : 0;
+        if (ms < 0 || ml < 0) return fail(h, DBSLMM_B200_ERR_ARG, "CSR offsets must be non-decreasing");
+        BlockDesc& d = P.blocks[b];
+        d.m = ms + ml;
+        d.ms = ms;
+        d.mp = (d.m + 7) / 8 * 8;
+        d.ld = d.mp;
+        d.goff = (int32_t)goff;
+        d.croff = (int32_t)croff;
+        d.moff = moff;
+        d.out_s = a->s_off[b];
+        d.out_l = a->l_off ? a->l_off[b] : 0;
+        d.pad = 0;
+        int miss = 0;
+        for (int j = 0; j < ms; ++j) {
+            const int32_t p = a->s_pos[a->s_off[b] + j];
+            if (p < 0 || p >= n_snp) return fail(h, DBSLMM_B200_ERR_ARG, "s_pos out of range of the loaded .bed");
+            miss |= (h->h_stats[p].n_nonmiss != h->n_ref);
+        }
+        for (int j = 0; j < ml; ++j) {
+            const int32_t p = a->l_pos[a->l_off[b] + j];
+            if (p < 0 || p >= n_snp) return fail(h, DBSLMM_B200_ERR_ARG, "l_pos out of range of the loaded .bed");
+            miss |= (h->h_stats[p].n_nonmiss != h->n_ref);
+        }
+        d.has_missing = miss;
+        goff += d.m;
+        croff += (int64_t)d.m * (miss ? 2 : 1);
+        if (d.m > 0) moff += align_up((size_t)(d.mp + 8) * d.ld, 16);
+        P.max_mp = std::max(P.max_mp, d.mp);
+        const double m = d.m;
+        P.gram_ops += (miss ? 4.0 : 1.0) * (double)h->n_pad * m * (m + 1.0);   // 2 ops per MAC, lower triangle
+        P.solve_flops += m * m * m / 3.0 + 2.0 * m * m;
+    }
+    if (goff > INT32_MAX || croff > INT32_MAX) return fail(h, DBSLMM_B200_ERR_ARG, "too many SNP rows for one call");
+    P.n_snp_rows = goff;
+    P.n_code_rows = croff;
+    P.mat_doubles = moff;
+    P.decode_bytes = (double)croff * ((double)h->pitch + (double)h->n_pad);
+
+    P.order.resize(nb);
+    std::iota(P.order.begin(), P.order.end(), 0);
+    std::stable_sort(P.order.begin(), P.order.end(),
+                     [&](int x, int y) { return P.blocks[x].m > P.blocks[y].m; });
+
+    // Gram tiles (lower triangle of 128x128 tiles), big blocks first
+    std::vector<GramTile> tiles_plain, tiles_miss;
+    for (int b : P.order) {
+        const BlockDesc& d = P.blocks[b];
+        const int nt = (d.mp + 127) / 128;
+        for (int ti = 0; ti < nt; ++ti)
+            for (int tj = 0; tj <= ti; ++tj) (d.has_missing ? tiles_miss : tiles_plain).push_back({b, ti, tj, 0});
+    }
+    P.n_tiles_plain = (int32_t)tiles_plain.size();
+    P.n_tiles_miss = (int32_t)tiles_miss.size();
+
+    // Cholesky step lists per size class
+    std::vector<int32_t> diag_items;
+    std::vector<int2> panel_items;
+    for (int c = 0; c < kNumClasses; ++c) {
+        const int lo = (c == 0) ? 0 : kClassMaxPanels[c - 1];
+        const int hi = kClassMaxPanels[c];
+        std::vector<int> members;
+        int kmax = 0;
+        for (int b : P.order) {
+            const int K = (P.blocks[b].mp + 63) / 64;
+            if (K > lo && K <= hi) { members.push_back(b); kmax = std::max(kmax, K); }
+        }
+        P.steps[c].resize(kmax);
+        for (int k = 0; k < kmax; ++k) {
+            StepList& s = P.steps[c][k];
+            s.diag_off = (int32_t)diag_items.size();
+            s.panel_off = (int32_t)panel_items.size();
+            for (int b : members) {
+                const BlockDesc& d = P.blocks[b];
+                const int K = (d.mp + 63) / 64;
+                if (K <= k) continue;
+                diag_items.push_back(b);
+                const int wk = std::min(64, d.mp - 64 * k);
+                const int below = 64 * k + wk;
+                const int nt = (d.mp + 8 - below + 127) / 128;
+                for (int t = 0; t < nt; ++t) panel_items.push_back(make_int2(b, t));
+            }
+            s.n_diag = (int32_t)diag_items.size() - s.diag_off;
+            s.n_panel = (int32_t)panel_items.size() - s.panel_off;
+        }
+    }
+
+    // ---- pack the blob
+    size_t o = 0;
+    auto place = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
+    P.o_blocks = place(sizeof(BlockDesc) * (size_t)nb);
+    P.o_rowsrc = place(sizeof(uint32_t) * (size_t)croff);
+    P.o_rowg = place(sizeof(int32_t) * (size_t)croff);
+    P.o_z = place(sizeof(double) * (size_t)goff);
+    P.o_tiles_plain = place(sizeof(GramTile) * tiles_plain.size());
+    P.o_tiles_miss = place(sizeof(GramTile) * tiles_miss.size());
+    P.o_order = place(sizeof(int32_t) * (size_t)nb);
+    P.o_diag = place(sizeof(int32_t) * diag_items.size());
+    P.o_panel = place(sizeof(int2) * panel_items.size());
+    P.blob_bytes = o;
+    blob.assign(o, 0);
+    std::memcpy(blob.data() + P.o_blocks, P.blocks.data(), sizeof(BlockDesc) * (size_t)nb);
+    uint32_t* rs = reinterpret_cast<uint32_t*>(blob.data() + P.o_rowsrc);
+    int32_t* rg = reinterpret_cast<int32_t*>(blob.data() + P.o_rowg);
+    double* z = reinterpret_cast<double*>(blob.data() + P.o_z);
+    for (int b = 0; b < nb; ++b) {
+        const BlockDesc& d = P.blocks[b];
+        const int ml = d.m - d.ms;
+        for (int j = 0; j < d.m; ++j) {
+            const bool small = j < d.ms;
+            const int32_t p = small ? a->s_pos[a->s_off[b] + j] : a->l_pos[a->l_off[b] + (j - d.ms)];
+            const double zz = small ? a->s_z[a->s_off[b] + j] : a->l_z[a->l_off[b] + (j - d.ms)];
+            rs[d.croff + j] = (uint32_t)p;
+            rg[d.croff + j] = d.goff + j;
+            z[d.goff + j] = zz;
+            if (d.has_missing) {
+                rs[d.croff + d.m + j] = (uint32_t)p | 0x80000000u;
+                rg[d.croff + d.m + j] = -1;
+            }
+        }
+        (void)ml;
+    }
+    if (!tiles_plain.empty()) std::memcpy(blob.data() + P.o_tiles_plain, tiles_plain.data(), sizeof(GramTile) * tiles_plain.size());
+    if (!tiles_miss.empty()) std::memcpy(blob.data() + P.o_tiles_miss, tiles_miss.data(), sizeof(GramTile) * tiles_miss.size());
+    std::memcpy(blob.data() + P.o_order, P.order.data(), sizeof(int32_t) * (size_t)nb);
+    if (!diag_items.empty()) std::memcpy(blob.data() + P.o_diag, diag_items.data(), sizeof(int32_t) * diag_items.size());
+    if (!panel_items.empty()) std::memcpy(blob.data() + P.o_panel, panel_items.data(), sizeof(int2) * panel_items.size());
+    P.valid = true;
+    return DBSLMM_B200_OK;
+}
+
+int make_tensor_map(dbslmm_b200_handle* h, CUtensorMap* tm, void* base, int64_t n_rows, int32_t n_pad) {
+    if (!h->encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+            return fail(h, DBSLMM_B200_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+        h->encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)n_pad, (cuuint64_t)n_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)n_pad};
+    cuuint32_t box[2] = {128, 128};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = h->encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(h, DBSLMM_B200_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
+    return DBSLMM_B200_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int dbslmm_b200_abi_version(void) { return DBSLMM_B200_ABI_VERSION; }
+
+int dbslmm_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int dbslmm_b200_create(int device, dbslmm_b200_handle** out) {
+    if (!out) return DBSLMM_B200_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) {
+        cudaGetLastError();
+        return DBSLMM_B200_ERR_CUDA;   // no CPU fallback: the product path needs a GPU
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return DBSLMM_B200_ERR_CUDA;
+    if (prop.major != 10) return DBSLMM_B200_ERR_CUDA;   // kernels are sm_100a only
+    if (cudaSetDevice(device) != cudaSuccess) return DBSLMM_B200_ERR_CUDA;
+    dbslmm_b200_handle* h = new (std::nothrow) dbslmm_b200_handle();
+    if (!h) return DBSLMM_B200_ERR_NOMEM;
+    h->device = device;
+    h->n_sm = prop.multiProcessorCount;
+    bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int c = 0; c < kNumClasses && ok; ++c) {
+        ok = cudaStreamCreateWithFlags(&h->cls_stream[c], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&h->ev_join[c], cudaEventDisableTiming) == cudaSuccess;
+    }
+    for (int i = 0; i < 8 && ok; ++i) ok = cudaEventCreate(&h->ev[i]) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && chol_configure() == cudaSuccess;
+    if (!ok) { dbslmm_b200_destroy(h); return DBSLMM_B200_ERR_CUDA; }
+    *out = h;
+    return DBSLMM_B200_OK;
+}
+
+void dbslmm_b200_destroy(dbslmm_b200_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    DevBuf* bufs[] = {&h->bed, &h->stats, &h->codes, &h->sigma, &h->lbuf, &h->rowN, &h->rowS, &h->rowR,
+                      &h->planblob, &h->beta, &h->status, &h->intQ, &h->intA, &h->intN, &h->scratch};
+    for (DevBuf* b : bufs) b->release();
+    h->h_blob.release();
+    h->h_out.release();
+    for (int i = 0; i < 8; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    for (int c = 0; c < kNumClasses; ++c) {
+        if (h->ev_join[c]) cudaEventDestroy(h->ev_join[c]);
+        if (h->cls_stream[c]) cudaStreamDestroy(h->cls_stream[c]);
+    }
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+const char* dbslmm_b200_last_error(const dbslmm_b200_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int dbslmm_b200_load_bed(dbslmm_b200_handle* h, const uint8_t* bed, int64_t n_snp, int32_t n_ref) {
+    if (!h) return DBSLMM_B200_ERR_ARG;
+    if (!bed || n_snp <= 0 || n_ref <= 1) return fail(h, DBSLMM_B200_ERR_ARG, "load_bed: bad arguments");
+    CU_TRY(h, cudaSetDevice(h->device));
+    const int32_t pitch = (n_ref + 3) / 4;
+    const size_t bytes = (size_t)n_snp * pitch;
+    CU_TRY(h, h->bed.ensure(bytes + 64));
+    CU_TRY(h, h->stats.ensure(sizeof(SnpStat) * (size_t)n_snp));
+    CU_TRY(h, cudaMemcpyAsync(h->bed.p, bed, bytes, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaMemsetAsync((uint8_t*)h->bed.p + bytes, 0xFF, 64, h->stream));
+    CU_TRY(h, launch_snp_stats((const uint8_t*)h->bed.p, n_snp, n_ref, (SnpStat*)h->stats.p, h->n_sm, h->stream));
+    h->h_stats.resize((size_t)n_snp);
+    CU_TRY(h, cudaMemcpyAsync(h->h_stats.data(), h->stats.p, sizeof(SnpStat) * (size_t)n_snp, cudaMemcpyDeviceToHost,
+                              h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    h->n_snp = n_snp;
+    h->n_ref = n_ref;
+    h->pitch = pitch;
+    h->n_pad = (n_ref + 127) / 128 * 128;
+    h->plan.valid = false;
+    return DBSLMM_B200_OK;
+}
+
+int dbslmm_b200_snp_stats(dbslmm_b200_handle* h, double* maf_out, int32_t* n_nonmiss_out) {
+    if (!h) return DBSLMM_B200_ERR_ARG;
+    if (h->n_snp == 0) return fail(h, DBSLMM_B200_ERR_STATE, "snp_stats before load_bed");
+    for (int64_t i = 0; i < h->n_snp; ++i) {
+        const SnpStat& s = h->h_stats[(size_t)i];
+        if (maf_out) {
+            // readSNPIm (dtpr.cpp:358-362): mean-impute, af = sum(geno) / (2 n) = S / (2 n_i)
+            const double af = 0.5 * (double)s.sum / (double)s.n_nonmiss;
+            maf_out[i] = std::min(af, 1.0 - af);
+        }
+        if (n_nonmiss_out) n_nonmiss_out[i] = s.n_nonmiss;
+    }
+    return DBSLMM_B200_OK;
+}
+
+int dbslmm_b200_plan_shards(int32_t n_blocks, const int32_t* m_s, const int32_t* m_l, int32_t n_ref,
+                            int32_t n_ranks, int32_t* owner_out, double* rank_cost_out) {
+    if (n_blocks < 0 || n_ranks <= 0 || !m_s || !owner_out) return DBSLMM_B200_ERR_ARG;
+    const double n_pad = (double)((n_ref + 127) / 128 * 128);
+    std::vector<double> cost(n_blocks);
+    for (int b = 0; b < n_blocks; ++b) {
+        const double m = (double)m_s[b] + (m_l ? (double)m_l[b] : 0.0);
+        // seconds-like units: int8 Gram at ~1 Pop/s effective, FP64 factorisation at ~15 TF/s effective,
+        // plus a per-block latency floor (panel steps are serial inside a block)
+        cost[b] = n_pad * m * (m + 1.0) / 1.0e15 + (m * m * m / 3.0 + 2.0 * m * m) / 1.5e13 + 2.0e-6 * std::ceil(m / 64.0);
+    }
+    std::vector<int> idx(n_blocks);
+    std::iota(idx.begin(), idx.end(), 0);
+    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+    std::vector<double> load(n_ranks, 0.0);
+    for (int b : idx) {
+        int r = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+        owner_out[b] = r;
+        load[r] += cost[b];
+    }
+    if (rank_cost_out) for (int r = 0; r < n_ranks; ++r) rank_cost_out[r] = load[r];
+    return DBSLMM_B200_OK;
+}
+
+int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
+    if (!h || !a) return DBSLMM_B200_ERR_ARG;
+    if (h->n_snp == 0) return fail(h, DBSLMM_B200_ERR_STATE, "fit before load_bed");
+    if (a->n_blocks < 0 || !a->s_off || a->n_folds < 1 || !a->sigma_s || a->n_obs <= 0 || !a->beta_s_out)
+        return fail(h, DBSLMM_B200_ERR_ARG, "fit: bad arguments");
+    if (a->n_blocks > 0 && a->s_off[a->n_blocks] > 0 && (!a->s_pos || !a->s_z))
+        return fail(h, DBSLMM_B200_ERR_ARG, "fit: s_pos/s_z missing");
+    if (a->l_off && a->l_off[a->n_blocks] > 0 && (!a->l_pos || !a->l_z || !a->beta_l_out))
+        return fail(h, DBSLMM_B200_ERR_ARG, "fit: l_pos/l_z/beta_l_out missing");
+    if (!(a->tau > 0.0 && a->tau <= 1.0)) return fail(h, DBSLMM_B200_ERR_ARG, "fit: tau must be in (0,1]");
+    if (a->solver != DBSLMM_B200_SOLVER_CHOLESKY && a->solver != DBSLMM_B200_SOLVER_PCG)
+        return fail(h, DBSLMM_B200_ERR_ARG, "fit: unknown solver");
+    for (int f = 0; f < a->n_folds; ++f)
+        if (!(a->sigma_s[f] > 0.0)) return fail(h, DBSLMM_B200_ERR_ARG, "fit: sigma_s must be > 0");
+    CU_TRY(h, cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const bool pcg = (a->solver == DBSLMM_B200_SOLVER_PCG);
+    const bool full = pcg || (a->flags & DBSLMM_B200_FLAG_FULL_SIGMA);
+    const bool keep_int = (a->flags & DBSLMM_B200_FLAG_KEEP_INT_GRAM) != 0;
+
+    // ---- plan
+    Plan& P = h->plan;
+    const bool reuse = (a->flags & DBSLMM_B200_FLAG_PLAN_CACHED) && P.valid && P.n_blocks == a->n_blocks &&
+                       P.tot_s == a->s_off[a->n_blocks] && P.tot_l == (a->l_off ? a->l_off[a->n_blocks] : 0);
+    std::vector<uint8_t> blob;
+    if (!reuse) {
+        int rc = build_plan(h, a, P, blob);
+        if (rc != DBSLMM_B200_OK) { P.valid = false; return rc; }
+    }
+    const int nb = P.n_blocks;
+    const size_t nfold = (size_t)a->n_folds;
+
+    // ---- workspace
+    CU_TRY(h, h->planblob.ensure(P.blob_bytes + 256));
+    CU_TRY(h, h->codes.ensure((size_t)std::max<int64_t>(P.n_code_rows, 1) * h->n_pad));
+    CU_TRY(h, h->sigma.ensure(sizeof(double) * (size_t)std::max<int64_t>(P.mat_doubles, 1)));
+    if (!pcg) CU_TRY(h, h->lbuf.ensure(sizeof(double) * (size_t)std::max<int64_t>(P.mat_doubles, 1)));
+    CU_TRY(h, h->rowN.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(P.n_snp_rows, 1)));
+    CU_TRY(h, h->rowS.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(P.n_snp_rows, 1)));
+    CU_TRY(h, h->rowR.ensure(sizeof(double) * (size_t)std::max<int64_t>(P.n_snp_rows, 1)));
+    const size_t n_out = (size_t)(P.tot_s + P.tot_l);
+    CU_TRY(h, h->beta.ensure(sizeof(double) * std::max<size_t>(n_out * nfold, 1)));
+    CU_TRY(h, h->status.ensure(sizeof(int32_t) * (size_t)std::max(2 * nb, 1)));
+    if (keep_int) {
+        CU_TRY(h, h->intQ.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(P.mat_doubles, 1)));
+        CU_TRY(h, h->intA.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(P.mat_doubles, 1)));
+        CU_TRY(h, h->intN.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(P.mat_doubles, 1)));
+    }
+    const size_t out_bytes = sizeof(double) * n_out * nfold + sizeof(int32_t) * (size_t)(2 * nb);
+    CU_TRY(h, h->h_out.ensure(out_bytes + 64));
+
+    uint8_t* dblob = (uint8_t*)h->planblob.p;
+    const BlockDesc* d_blocks = (const BlockDesc*)(dblob + P.o_blocks);
+    const uint32_t* d_rowsrc = (const uint32_t*)(dblob + P.o_rowsrc);
+    const int32_t* d_rowg = (const int32_t*)(dblob + P.o_rowg);
+    const double* d_z = (const double*)(dblob + P.o_z);
+    const GramTile* d_tiles_plain = (const GramTile*)(dblob + P.o_tiles_plain);
+    const GramTile* d_tiles_miss = (const GramTile*)(dblob + P.o_tiles_miss);
+    const int32_t* d_order = (const int32_t*)(dblob + P.o_order);
+    const int32_t* d_diag = (const int32_t*)(dblob + P.o_diag);
+    const int2* d_panel = (const int2*)(dblob + P.o_panel);
+    double* d_beta = (double*)h->beta.p;
+    int32_t* d_status = (int32_t*)h->status.p;
+    int32_t* d_iters = d_status + nb;
+
+    int n_launch = 0, n_chol_launch = 0;
+    CU_TRY(h, cudaEventRecord(h->ev[0], st));
+    // ---- upload
+    if (!reuse) {
+        CU_TRY(h, h->h_blob.ensure(P.blob_bytes));
+        std::memcpy(h->h_blob.p, blob.data(), P.blob_bytes);
+        if (P.blob_bytes) CU_TRY(h, cudaMemcpyAsync(dblob, h->h_blob.p, P.blob_bytes, cudaMemcpyHostToDevice, st));
+    } else if (P.n_snp_rows > 0) {
+        // same CSR layout, new z-scores
+        double* z = reinterpret_cast<double*>((uint8_t*)h->h_blob.p + P.o_z);
+        for (int b = 0; b < nb; ++b) {
+            const BlockDesc& d = P.blocks[b];
+            for (int j = 0; j < d.m; ++j)
+                z[d.goff + j] = (j < d.ms) ? a->s_z[a->s_off[b] + j] : a->l_z[a->l_off[b] + (j - d.ms)];
+        }
+        CU_TRY(h, cudaMemcpyAsync(dblob + P.o_z, z, sizeof(double) * (size_t)P.n_snp_rows, cudaMemcpyHostToDevice, st));
+    }
+    CU_TRY(h, cudaMemsetAsync(d_status, 0, sizeof(int32_t) * (size_t)std::max(2 * nb, 1), st));
+    CU_TRY(h, cudaEventRecord(h->ev[1], st));
+
+    // ---- decode
+    if (P.n_code_rows > 0) {
+        CU_TRY(h, launch_decode_rows((const uint8_t*)h->bed.p, h->n_ref, h->n_pad, d_rowsrc, d_rowg, P.n_code_rows,
+                                     (const SnpStat*)h->stats.p, a->tau, (int8_t*)h->codes.p, (int32_t*)h->rowN.p,
+                                     (int32_t*)h->rowS.p, (double*)h->rowR.p, h->n_sm, st));
+        ++n_launch;
+    }
+    CU_TRY(h, cudaEventRecord(h->ev[2], st));
+
+    // ---- gram
+    if (P.n_code_rows > 0) {
+        CUtensorMap tmap;
+        int rc = make_tensor_map(h, &tmap, h->codes.p, P.n_code_rows, h->n_pad);
+        if (rc != DBSLMM_B200_OK) return rc;
+        GramArgs g;
+        g.blocks = d_blocks;
+        g.nk = h->n_pad / 128;
+        g.n_ref = h->n_ref;
+        g.one_minus_tau = 1.0 - a->tau;
+        g.rowN = (const int32_t*)h->rowN.p;
+        g.rowS = (const int32_t*)h->rowS.p;
+        g.rowR = (const double*)h->rowR.p;
+        g.sigma = (double*)h->sigma.p;
+        g.intQ = keep_int ? (int32_t*)h->intQ.p : nullptr;
+        g.intA = keep_int ? (int32_t*)h->intA.p : nullptr;
+        g.intN = keep_int ? (int32_t*)h->intN.p : nullptr;
+        g.full = full ? 1 : 0;
+        if (P.n_tiles_plain) {
+            g.tiles = d_tiles_plain;
+            g.n_tiles = P.n_tiles_plain;
+            CU_TRY(h, launch_gram(tmap, g, false, st));
+            ++n_launch;
+        }
+        if (P.n_tiles_miss) {
+            g.tiles = d_tiles_miss;
+            g.n_tiles = P.n_tiles_miss;
+            CU_TRY(h, launch_gram(tmap, g, true, st));
+            ++n_launch;
+        }
+        CU_TRY(h, launch_fill_z(d_blocks, nb, d_z, (double*)h->sigma.p, st));
+        ++n_launch;
+    }
+    CU_TRY(h, cudaEventRecord(h->ev[3], st));
+
+    // ---- solve, once per heritability fold (Sigma is shared: only the ridge changes)
+    float chol_ms_total = 0.f;
+    const double inv_sqrt_n = 1.0 / std::sqrt((double)a->n_obs);
+    for (int f = 0; f < a->n_folds; ++f) {
+        const double ridge = 1.0 / (a->sigma_s[f] * (double)a->n_obs);    // dbslmmfit.cpp:712 / :759
+        double* bs = d_beta + (size_t)f * n_out;
+        double* bl = bs + P.tot_s;
+        if (!pcg) {
+            CU_TRY(h, cudaEventRecord(h->ev_fork, st));
+            for (int c = 0; c < kNumClasses; ++c) {
+                if (P.steps[c].empty()) continue;
+                cudaStream_t cs = h->cls_stream[c];
+                CU_TRY(h, cudaStreamWaitEvent(cs, h->ev_fork, 0));
+                for (size_t k = 0; k < P.steps[c].size(); ++k) {
+                    const StepList& s = P.steps[c][k];
+                    CU_TRY(h, launch_chol_diag(d_blocks, d_diag + s.diag_off, s.n_diag, (int32_t)k,
+                                               (const double*)h->sigma.p, (double*)h->lbuf.p, ridge, d_status, cs));
+                    CU_TRY(h, launch_chol_panel(d_blocks, d_panel + s.panel_off, s.n_panel, (int32_t)k,
+                                                (const double*)h->sigma.p, (double*)h->lbuf.p, cs));
+                    n_launch += 2;
+                    n_chol_launch += 2;
+                }
+                CU_TRY(h, cudaEventRecord(h->ev_join[c], cs));
+                CU_TRY(h, cudaStreamWaitEvent(st, h->ev_join[c], 0));
+            }
+            CU_TRY(h, cudaEventRecord(h->ev[6], st));
+            CU_TRY(h, launch_backsolve(d_blocks, d_order, nb, (const double*)h->lbuf.p, inv_sqrt_n, bs, bl, P.max_mp, st));
+            ++n_launch;
+            if (a->timing && a->n_folds > 1) {
+                // per-fold factorisation time needs a sync; only paid when timing is requested
+                CU_TRY(h, cudaEventRecord(h->ev[7], st));
+                CU_TRY(h, cudaEventSynchronize(h->ev[7]));
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, (f == 0) ? h->ev[3] : h->ev[5], h->ev[6]);
+                chol_ms_total += ms;
+                CU_TRY(h, cudaEventRecord(h->ev[5], st));
+            }
+        } else {
+            return fail(h, DBSLMM_B200_ERR_ARG, "PCG solver not built yet");
+        }
+    }
+    CU_TRY(h, cudaEventRecord(h->ev[4], st));
+
+    // ---- download
+    uint8_t* hout = (uint8_t*)h->h_out.p;
+    if (n_out) CU_TRY(h, cudaMemcpyAsync(hout, d_beta, sizeof(double) * n_out * nfold, cudaMemcpyDeviceToHost, st));
+    CU_TRY(h, cudaMemcpyAsync(hout + sizeof(double) * n_out * nfold, d_status, sizeof(int32_t) * (size_t)(2 * nb),
+                              cudaMemcpyDeviceToHost, st));
+    CU_TRY(h, cudaEventRecord(h->ev[5], st));
+    CU_TRY(h, cudaStreamSynchronize(st));
+    {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(h, DBSLMM_B200_ERR_CUDA, std::string("fit: ") + cudaGetErrorString(e));
+    }
+    const double* hb = (const double*)hout;
+    for (int f = 0; f < a->n_folds; ++f) {
+        std::memcpy(a->beta_s_out + (size_t)f * P.tot_s, hb + (size_t)f * n_out, sizeof(double) * (size_t)P.tot_s);
+        if (P.tot_l) std::memcpy(a->beta_l_out + (size_t)f * P.tot_l, hb + (size_t)f * n_out + P.tot_s, sizeof(double) * (size_t)P.tot_l);
+    }
+    const int32_t* hs = (const int32_t*)(hout + sizeof(double) * n_out * nfold);
+    int n_bad = 0;
+    for (int b = 0; b < nb; ++b) {
+        if (a->block_status_out) a->block_status_out[b] = hs[b];
+        n_bad += (hs[b] != 0);
+    }
+    h->last_flags = a->flags | (full ? DBSLMM_B200_FLAG_FULL_SIGMA : 0);
+    h->last_solver = a->solver;
+    h->last_nfolds = a->n_folds;
+    if (a->timing) {
+        dbslmm_b200_timing* t = a->timing;
+        cudaEventElapsedTime(&t->h2d_ms, h->ev[0], h->ev[1]);
+        cudaEventElapsedTime(&t->decode_ms, h->ev[1], h->ev[2]);
+        cudaEventElapsedTime(&t->gram_ms, h->ev[2], h->ev[3]);
+        cudaEventElapsedTime(&t->solve_ms, h->ev[3], h->ev[4]);
+        cudaEventElapsedTime(&t->d2h_ms, h->ev[4], h->ev[5]);
+        cudaEventElapsedTime(&t->total_ms, h->ev[0], h->ev[5]);
+        if (!pcg && a->n_folds == 1) { float ms = 0.f; cudaEventElapsedTime(&ms, h->ev[3], h->ev[6]); chol_ms_total = ms; }
+        t->chol_ms = chol_ms_total;
+        t->n_launches = n_launch;
+        t->n_chol_launches = n_chol_launch;
+        t->gram_ops = P.gram_ops;
+        t->solve_flops = P.solve_flops * (double)a->n_folds;
+        t->decode_bytes = P.decode_bytes;
+    }
+    return n_bad;
+}
+
+// ---------------------------------------------------------------------------------------------
+// inspection hooks
+// ---------------------------------------------------------------------------------------------
+int dbslmm_b200_get_row_codes(dbslmm_b200_handle* h, int64_t row, int8_t* codes_out, int32_t n_out) {
+    if (!h || !codes_out) return DBSLMM_B200_ERR_ARG;
+    if (!h->plan.valid) return fail(h, DBSLMM_B200_ERR_STATE, "no fit yet");
+    if (row < 0 || row >= h->plan.n_code_rows || n_out > h->n_pad || n_out < 0) return fail(h, DBSLMM_B200_ERR_ARG, "row out of range");
+    CU_TRY(h, cudaSetDevice(h->device));
+    CU_TRY(h, cudaMemcpy(codes_out, (const int8_t*)h->codes.p + (size_t)row * h->n_pad, (size_t)n_out, cudaMemcpyDeviceToHost));
+    return DBSLMM_B200_OK;
+}
+
+static int fetch_block(dbslmm_b200_handle* h, int32_t block, const void* dev, size_t esz, std::vector<uint8_t>& tmp,
+                       const BlockDesc** bd_out) {
+    if (!h->plan.valid) return fail(h, DBSLMM_B200_ERR_STATE, "no fit yet");
+    if (block < 0 || block >= h->plan.n_blocks) return fail(h, DBSLMM_B200_ERR_ARG, "block out of range");
+    const BlockDesc& bd = h->plan.blocks[block];
+    *bd_out = &bd;
+    if (bd.m == 0) return DBSLMM_B200_OK;
+    tmp.resize((size_t)bd.mp * bd.ld * esz);
+    CU_TRY(h, cudaSetDevice(h->device));
+    CU_TRY(h, cudaMemcpy(tmp.data(), (const uint8_t*)dev + (size_t)bd.moff * esz, tmp.size(), cudaMemcpyDeviceToHost));
+    return DBSLMM_B200_OK;
+}
+
+int dbslmm_b200_get_block_sigma(dbslmm_b200_handle* h, int32_t block, double* sigma_out) {
+    if (!h || !sigma_out) return DBSLMM_B200_ERR_ARG;
+    std::vector<uint8_t> tmp;
+    const BlockDesc* bd = nullptr;
+    int rc = fetch_block(h, block, h->sigma.p, sizeof(double), tmp, &bd);
+    if (rc != DBSLMM_B200_OK) return rc;
+    const double* s = (const double*)tmp.data();
+    const bool full = (h->last_flags & DBSLMM_B200_FLAG_FULL_SIGMA) != 0;
+    for (int i = 0; i < bd->m; ++i)
+        for (int j = 0; j < bd->m; ++j) {
+            const double v = (j <= i || full) ? s[(size_t)i * bd->ld + j] : s[(size_t)j * bd->ld + i];
+            sigma_out[(size_t)i * bd->m + j] = v;
+        }
+    return DBSLMM_B200_OK;
+}
+
+int dbslmm_b200_get_block_gram(dbslmm_b200_handle* h, int32_t block, int32_t* q_out, int32_t* a_out, int32_t* n_out) {
+    if (!h || !q_out) return DBSLMM_B200_ERR_ARG;
+    if (!(h->last_flags & DBSLMM_B200_FLAG_KEEP_INT_GRAM)) return fail(h, DBSLMM_B200_ERR_STATE, "last fit did not keep the integer Gram");
+    std::vector<uint8_t> tmp;
+    const BlockDesc* bd = nullptr;
+    int rc = fetch_block(h, block, h->intQ.p, sizeof(int32_t), tmp, &bd);
+    if (rc != DBSLMM_B200_OK) return rc;
+    const int m = bd->m;
+    auto copy_plane = [&](int32_t* out) {
+        const int32_t* s = (const int32_t*)tmp.data();
+        for (int i = 0; i < m; ++i)
+            for (int j = 0; j < m; ++j) out[(size_t)i * m + j] = s[(size_t)i * bd->ld + j];
+    };
+    copy_plane(q_out);
+    if (bd->has_missing) {
+        if (a_out) { rc = fetch_block(h, block, h->intA.p, sizeof(int32_t), tmp, &bd); if (rc) return rc; copy_plane(a_out); }
+        if (n_out) { rc = fetch_block(h, block, h->intN.p, sizeof(int32_t), tmp, &bd); if (rc) return rc; copy_plane(n_out); }
+    } else {
+        // no missing calls: A_ij = S_i, N_ij = n_ref (the fast path never forms them)
+        std::vector<int32_t> S(std::max(m, 1));
+        if (m) CU_TRY(h, cudaMemcpy(S.data(), (const int32_t*)h->rowS.p + bd->goff, sizeof(int32_t) * (size_t)m, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < m; ++i)
+            for (int j = 0; j < m; ++j) {
+                if (a_out) a_out[(size_t)i * m + j] = S[i];
+                if (n_out) n_out[(size_t)i * m + j] = h->n_ref;
+            }
+    }
+    return DBSLMM_B200_OK;
+}
+
+int dbslmm_b200_get_block_iters(dbslmm_b200_handle* h, int32_t block) {
+    if (!h) return DBSLMM_B200_ERR_ARG;
+    if (!h->plan.valid || block < 0 || block >= h->plan.n_blocks) return fail(h, DBSLMM_B200_ERR_ARG, "block out of range");
+    if (h->last_solver != DBSLMM_B200_SOLVER_PCG) return fail(h, DBSLMM_B200_ERR_STATE, "last fit was not a PCG fit");
+    const int32_t* hs = (const int32_t*)((const uint8_t*)h->h_out.p +
+                                         sizeof(double) * (size_t)(h->plan.tot_s + h->plan.tot_l) * (size_t)h->last_nfolds);
+    return hs[h->plan.n_blocks + block];
+}
+
+}  // extern "C"

@@ -1,0 +1,272 @@
+// gram.cu -- correlation builder (K3): exact int8 tensor-core Gram + FP64 centre/scale epilogue.
+//
+// Replaces the FP64 dsyrk/dgemm call sites of DBSLMMFIT::estBlock (reference
+// scr/dbslmmfit.cpp:698-709, 752-756) and the per-column z-scoring of nomalizeVec
+// (scr/dtpr.cpp:375-380).  For one LD block with SNP rows i, j (small SNPs first, then
+// large ones), raw allele counts g in {0,1,2} (missing -> 0) and call mask M:
+//     Q_ij = sum g_i g_j,  A_ij = sum g_i M_j,  N_ij = sum M_i M_j          (exact, s32)
+//     num_ij = n_i n_j Q_ij - n_i S_j A_ij - n_j S_i A_ji + S_i S_j N_ij      (exact integer < 2^53)
+//     Sigma_ij = num_ij * r_i * r_j + (1 - tau) [i == j],   r_i = sqrt(tau (n-1) / (n n_i d_i)),
+//     d_i = n_i Q_ii - S_i^2
+// which equals tau * X^T X / n + (1 - tau) I for the mean-imputed, (N-1)-standardised X of
+// the reference.  Blocks without missing calls need only Q
+// (A_ij = S_i, N_ij = n): one accumulator plane; blocks with missing calls use four.
+//
+// Kernel shape: one CTA per 128 x 128 tile of the block's lower triangle, 192 threads:
+//   warp 0   TMA producer: int8 code tiles [128 rows x 128 B], SWIZZLE_128B, 3-stage ring
+//   warp 1   TMEM allocator + single-thread tcgen05.mma.kind::i8 issuer (M=128, N=128, K=32)
+//   warps 2-5 epilogue: tcgen05.ld -> FP64 transform -> coalesced stores of the LOWER tile.
+// The A operand is the J (column) side and the B operand the I (row) side, so a TMEM lane
+// holds one Sigma column and consecutive lanes store consecutive addresses of one Sigma row.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace dbslmm {
+
+static constexpr int kTile = 128;            // output tile edge and UMMA M = N
+static constexpr int kTileBytes = kTile * 128;   // one operand stage: 128 rows x 128 B (K chunk = 128 samples)
+static constexpr int kStages = 3;
+static constexpr int kGramThreads = 192;
+
+template <int NPROD>
+struct GramCfg {
+    static constexpr int kOper = (NPROD == 1) ? 2 : 4;           // operand tiles per stage
+    static constexpr int kStageBytes = kOper * kTileBytes;
+    static constexpr int kSmem = kStages * kStageBytes + 1024;   // + alignment slack
+    static constexpr uint32_t kTmemCols = (NPROD == 1) ? 128 : 512;
+    static constexpr int kChunk = (NPROD == 1) ? 32 : 16;        // TMEM columns per epilogue step
+};
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+
+template <int NPROD>
+__global__ void __launch_bounds__(kGramThreads, (NPROD == 1) ? 2 : 1)
+gram_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs a) {
+    using Cfg = GramCfg<NPROD>;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], accum_bar;
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+
+    const GramTile tile = a.tiles[blockIdx.x];
+    const BlockDesc bd = a.blocks[tile.blk];
+    const bool diag = (tile.ti == tile.tj);
+    const int nk = a.nk;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&accum_bar, 1);
+        mbar_fence_init();
+        tma_prefetch_desc(&tmap);
+    }
+    if (warp == 1) tmem_alloc<Cfg::kTmemCols>(&tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    // operand rows in the global code array: genotype rows then (missing blocks) mask rows
+    const int32_t rowJ = bd.croff + tile.tj * kTile;
+    const int32_t rowI = bd.croff + tile.ti * kTile;
+    const int32_t rowJm = rowJ + bd.m, rowIm = rowI + bd.m;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---------------- TMA producer ----------------
+            const uint32_t bytes = (uint32_t)((diag ? Cfg::kOper / 2 : Cfg::kOper) * kTileBytes);
+            for (int ks = 0; ks < nk; ++ks) {
+                const int s = ks % kStages;
+                const uint32_t ph = (uint32_t)((ks / kStages) & 1);
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                uint8_t* st = smem + (size_t)s * Cfg::kStageBytes;
+                mbar_expect_tx(&full_bar[s], bytes);
+                const int32_t x = ks * 128;
+                tma_load_2d(st + 0 * kTileBytes, &tmap, x, rowJ, &full_bar[s]);
+                if (!diag) tma_load_2d(st + 1 * kTileBytes, &tmap, x, rowI, &full_bar[s]);
+                if (NPROD == 4) {
+                    tma_load_2d(st + 2 * kTileBytes, &tmap, x, rowJm, &full_bar[s]);
+                    if (!diag) tma_load_2d(st + 3 * kTileBytes, &tmap, x, rowIm, &full_bar[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ---------------- MMA issuer ----------------
+            constexpr uint32_t idesc = make_i8_idesc(kTile, kTile);
+            for (int ks = 0; ks < nk; ++ks) {
+                const int s = ks % kStages;
+                const uint32_t ph = (uint32_t)((ks / kStages) & 1);
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t st = smem_u32(smem + (size_t)s * Cfg::kStageBytes);
+                const uint32_t gJ = st, gI = diag ? st : st + kTileBytes;
+                const uint64_t dgJ = make_sw128_kmajor_desc(gJ), dgI = make_sw128_kmajor_desc(gI);
+                uint64_t dmJ = 0, dmI = 0;
+                if (NPROD == 4) {
+                    const uint32_t mJ = st + 2 * kTileBytes, mI = diag ? mJ : st + 3 * kTileBytes;
+                    dmJ = make_sw128_kmajor_desc(mJ);
+                    dmI = make_sw128_kmajor_desc(mI);
+                }
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const uint32_t acc = (ks > 0 || kk > 0) ? 1u : 0u;
+                    const uint64_t adv = (uint64_t)(kk * 2);   // +32 bytes inside the 128 B swizzle atom
+                    umma_i8(tmem_base + 0 * kTile, dgJ + adv, dgI + adv, idesc, acc);       // Q  : g_j . g_i
+                    if (NPROD == 4) {
+                        umma_i8(tmem_base + 1 * kTile, dgJ + adv, dmI + adv, idesc, acc);   // P1 : g_j . M_i
+                        umma_i8(tmem_base + 2 * kTile, dmJ + adv, dgI + adv, idesc, acc);   // P2 : M_j . g_i
+                        umma_i8(tmem_base + 3 * kTile, dmJ + adv, dmI + adv, idesc, acc);   // N  : M_j . M_i
+                    }
+                }
+                umma_commit(&empty_bar[s]);        // frees the smem stage when these MMAs retire
+            }
+            umma_commit(&accum_bar);               // accumulators complete
+        }
+    } else {
+        // ---------------- epilogue: 4 warps, TMEM lane quarter = warp % 4 ----------------
+        const int q = warp & 3;
+        const int jl = tile.tj * kTile + q * 32 + lane;          // Sigma column (block local)
+        const bool jvalid = jl < bd.m;
+        int32_t Sj = 0, Nj = 1;
+        double rj = 0.0;
+        if (jvalid) { Sj = a.rowS[bd.goff + jl]; Nj = a.rowN[bd.goff + jl]; rj = a.rowR[bd.goff + jl]; }
+        const double dn = (double)a.n_ref;
+        mbar_wait(&accum_bar, 0);
+        tc_fence_after();
+        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+        double* sig = a.sigma + bd.moff;
+        constexpr int CH = Cfg::kChunk;
+#pragma unroll 1
+        for (int c0 = 0; c0 < kTile; c0 += CH) {
+            const int ibase = tile.ti * kTile + c0;
+            if (ibase >= bd.mp) break;                            // warp-uniform
+            uint32_t v0[CH], v1[NPROD == 4 ? CH : 1], v2[NPROD == 4 ? CH : 1], v3[NPROD == 4 ? CH : 1];
+            if constexpr (CH == 32) {
+                tmem_ld32(tlane + c0, v0);
+            } else {
+                tmem_ld16(tlane + 0 * kTile + c0, v0);
+                tmem_ld16(tlane + 1 * kTile + c0, v1);
+                tmem_ld16(tlane + 2 * kTile + c0, v2);
+                tmem_ld16(tlane + 3 * kTile + c0, v3);
+            }
+            // per-row constants for the CH rows of this chunk, one per lane, broadcast by shuffle
+            int32_t Si_l = 0, Ni_l = 1;
+            double ri_l = 0.0;
+            {
+                const int il = ibase + (lane % CH);
+                if (il < bd.m) { Si_l = a.rowS[bd.goff + il]; Ni_l = a.rowN[bd.goff + il]; ri_l = a.rowR[bd.goff + il]; }
+            }
+            tmem_ld_wait();
+#pragma unroll
+            for (int r = 0; r < CH; ++r) {
+                const int il = ibase + r;
+                const int32_t Si = __shfl_sync(0xffffffffu, Si_l, r);
+                const int32_t Ni = __shfl_sync(0xffffffffu, Ni_l, r);
+                const double ri = __shfl_sync(0xffffffffu, ri_l, r);
+                if (il >= bd.mp || jl > il) continue;
+                double val;
+                if (il < bd.m) {
+                    double num;
+                    if constexpr (NPROD == 1) {
+                        const long long t = (long long)a.n_ref * (long long)(int32_t)v0[r] - (long long)Si * (long long)Sj;
+                        num = dn * (double)t;
+                    } else {
+                        const double Q = (double)(int32_t)v0[r], P1 = (double)(int32_t)v1[r];
+                        const double P2 = (double)(int32_t)v2[r], Nn = (double)(int32_t)v3[r];
+                        // A_ij = sum g_i M_j = P2,  A_ji = sum g_j M_i = P1
+                        num = (double)Ni * (double)Nj * Q - (double)Ni * (double)Sj * P2 -
+                              (double)Nj * (double)Si * P1 + (double)Si * (double)Sj * Nn;
+                    }
+                    val = num * ri * rj;
+                    if (il == jl) val += a.one_minus_tau;
+                } else {
+                    val = (il == jl) ? 1.0 : 0.0;                 // identity padding rows m..mp-1
+                }
+                sig[(size_t)il * bd.ld + jl] = val;
+                if (a.full && jl < il) sig[(size_t)jl * bd.ld + il] = val;
+                if (a.intQ != nullptr && il < bd.m) {
+                    const size_t o = (size_t)bd.moff + (size_t)il * bd.ld + jl, ot = (size_t)bd.moff + (size_t)jl * bd.ld + il;
+                    a.intQ[o] = (int32_t)v0[r];
+                    a.intQ[ot] = (int32_t)v0[r];
+                    if constexpr (NPROD == 4) {
+                        a.intA[o] = (int32_t)v2[r];
+                        a.intA[ot] = (int32_t)v1[r];
+                        a.intN[o] = (int32_t)v3[r];
+                        a.intN[ot] = (int32_t)v3[r];
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+}
+
+cudaError_t launch_gram(const CUtensorMap& tmap, const GramArgs& a, bool missing, cudaStream_t st) {
+    if (a.n_tiles == 0) return cudaSuccess;
+    cudaError_t e;
+    if (!missing) {
+        e = cudaFuncSetAttribute(gram_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GramCfg<1>::kSmem);
+        if (e != cudaSuccess) return e;
+        gram_kernel<1><<<a.n_tiles, kGramThreads, GramCfg<1>::kSmem, st>>>(tmap, a);
+    } else {
+        e = cudaFuncSetAttribute(gram_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GramCfg<4>::kSmem);
+        if (e != cudaSuccess) return e;
+        gram_kernel<4><<<a.n_tiles, kGramThreads, GramCfg<4>::kSmem, st>>>(tmap, a);
+    }
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// Plain dp4a Gram of consecutive code rows: a cross-check for the tcgen05 path used by the
+// test-suite only (dbslmm_b200_debug_gram_simt); never part of a fit.
+// ------------------------------------------------------------------------------------------
+__global__ void gram_simt_kernel(const int8_t* __restrict__ codes, int32_t n_pad, int64_t row0, int32_t m,
+                                 int32_t* __restrict__ q) {
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m || j >= m) return;
+    const int* a = reinterpret_cast<const int*>(codes + (size_t)(row0 + i) * n_pad);
+    const int* b = reinterpret_cast<const int*>(codes + (size_t)(row0 + j) * n_pad);
+    int acc = 0;
+    for (int k = 0; k < n_pad / 4; ++k) acc = __dp4a(a[k], b[k], acc);
+    q[(size_t)i * m + j] = acc;
+}
+cudaError_t launch_gram_simt(const int8_t* codes, int32_t n_pad, int64_t row0, int32_t m, int32_t* q_out,
+                             cudaStream_t st) {
+    dim3 blk(16, 16), grd((m + 15) / 16, (m + 15) / 16);
+    gram_simt_kernel<<<grd, blk, 0, st>>>(codes, n_pad, row0, m, q_out);
+    return cudaGetLastError();
+}
+
+// z-score row of every block matrix: row mp <- [z_s ; z_l ; 0...], rows mp+1..mp+7 <- 0.
+// Appending z as one more row makes the left-looking factorisation produce y = L^-1 z
+// in that row, i.e. the forward substitution comes for free (chol.cu).
+__global__ void fill_z_kernel(const BlockDesc* __restrict__ blocks, const double* __restrict__ z,
+                              double* __restrict__ sigma) {
+    const BlockDesc bd = blocks[blockIdx.x];
+    double* base = sigma + bd.moff + (size_t)bd.mp * bd.ld;
+    for (int t = threadIdx.x; t < 8 * bd.ld; t += blockDim.x) {
+        const int r = t / bd.ld, c = t - r * bd.ld;
+        base[t] = (r == 0 && c < bd.m) ? z[bd.goff + c] : 0.0;
+    }
+}
+cudaError_t launch_fill_z(const BlockDesc* blocks, int32_t n_blocks, const double* z, double* sigma,
+                          cudaStream_t st) {
+    if (n_blocks == 0) return cudaSuccess;
+    fill_z_kernel<<<n_blocks, 256, 0, st>>>(blocks, z, sigma);
+    return cudaGetLastError();
+}
+
+}  // namespace dbslmm

@@ -1,0 +1,74 @@
+// kernels.h -- host-callable launchers of the sm_100a kernels (internal to the library).
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include "common.cuh"
+
+namespace dbslmm {
+
+// decode.cu
+cudaError_t launch_snp_stats(const uint8_t* bed, int64_t n_snp, int32_t n_ref, SnpStat* stats, int n_sm,
+                             cudaStream_t st);
+cudaError_t launch_decode_rows(const uint8_t* bed, int32_t n_ref, int32_t n_pad, const uint32_t* row_src,
+                               const int32_t* row_g, int64_t n_rows, const SnpStat* stats, double tau,
+                               int8_t* codes, int32_t* rowN, int32_t* rowS, double* rowR, int n_sm,
+                               cudaStream_t st);
+
+// gram.cu
+struct GramArgs {
+    const GramTile* tiles;      // device
+    int32_t n_tiles;
+    const BlockDesc* blocks;    // device
+    int32_t nk;                 // n_pad / 128
+    int32_t n_ref;
+    double one_minus_tau;
+    const int32_t* rowN;
+    const int32_t* rowS;
+    const double* rowR;
+    double* sigma;
+    int32_t* intQ;              // optional raw planes (same offsets/ld as sigma)
+    int32_t* intA;
+    int32_t* intN;
+    int32_t full;               // also write the upper triangle
+};
+cudaError_t launch_gram(const CUtensorMap& tmap, const GramArgs& a, bool missing, cudaStream_t st);
+cudaError_t launch_gram_simt(const int8_t* codes, int32_t n_pad, int64_t row0, int32_t m, int32_t* q_out,
+                             cudaStream_t st);
+cudaError_t launch_fill_z(const BlockDesc* blocks, int32_t n_blocks, const double* z, double* sigma,
+                          cudaStream_t st);
+
+// chol.cu
+struct CholStep {               // work lists of one panel step (device pointers)
+    const int32_t* diag_blk;    // blocks active at this step
+    int32_t n_diag;
+    const int2* panel_items;    // (block, row macro-tile) below the diagonal tile
+    int32_t n_panel;
+};
+cudaError_t launch_chol_diag(const BlockDesc* blocks, const int32_t* items, int32_t n_items, int32_t k,
+                             const double* sigma, double* L, double ridge, int32_t* status, cudaStream_t st);
+cudaError_t launch_chol_panel(const BlockDesc* blocks, const int2* items, int32_t n_items, int32_t k,
+                              const double* sigma, double* L, cudaStream_t st);
+cudaError_t launch_backsolve(const BlockDesc* blocks, const int32_t* order, int32_t n_blocks, const double* L,
+                             double inv_sqrt_n, double* beta_s, double* beta_l, int32_t max_mp, cudaStream_t st);
+cudaError_t chol_configure();
+
+// pcg.cu
+struct PcgArgs {
+    const BlockDesc* blocks;
+    const int32_t* order;       // blocks sorted by descending size
+    int32_t n_blocks;
+    const double* sigma;        // full symmetric
+    double* work;               // per-block scratch (see pcg.cu)
+    const int64_t* work_off;
+    double ridge;               // 1 / (sigma_s * n_obs)
+    double sigma_s;
+    double n_obs;
+    double* beta_s;
+    double* beta_l;
+    int32_t* status;
+    int32_t* iters;
+};
+cudaError_t launch_pcg(const PcgArgs& a, cudaStream_t st);
+
+}  // namespace dbslmm

@@ -28,6 +28,12 @@ extern "C" {
 
 #define DBSLMM_B200_ABI_VERSION 1
 
+#if defined(__GNUC__)
+#define DBSLMM_B200_API __attribute__((visibility("default")))
+#else
+#define DBSLMM_B200_API
+#endif
+
 /* status codes: 0 ok; <0 failure; >0 (fit only) number of blocks whose status != 0 */
 #define DBSLMM_B200_OK            0
 #define DBSLMM_B200_ERR_CUDA     (-1)   /* no device / CUDA runtime error (see last_error) */
@@ -87,41 +93,41 @@ typedef struct dbslmm_b200_fit_args {
 #define DBSLMM_B200_FLAG_FULL_SIGMA    2  /* write both triangles of Sigma (implied by the PCG solver)       */
 #define DBSLMM_B200_FLAG_PLAN_CACHED   4  /* reuse the device plan of the previous fit (same CSR arrays)     */
 
-int  dbslmm_b200_abi_version(void);
-int  dbslmm_b200_device_count(void);
+DBSLMM_B200_API int  dbslmm_b200_abi_version(void);
+DBSLMM_B200_API int  dbslmm_b200_device_count(void);
 
-int  dbslmm_b200_create(int device, dbslmm_b200_handle** out);
-void dbslmm_b200_destroy(dbslmm_b200_handle* h);
-const char* dbslmm_b200_last_error(const dbslmm_b200_handle* h);
+DBSLMM_B200_API int  dbslmm_b200_create(int device, dbslmm_b200_handle** out);
+DBSLMM_B200_API void dbslmm_b200_destroy(dbslmm_b200_handle* h);
+DBSLMM_B200_API const char* dbslmm_b200_last_error(const dbslmm_b200_handle* h);
 
 /* Reference panel.  `bed` points just after the 3 magic bytes of a SNP-major PLINK .bed
  * (pitch = ceil(n_ref/4) bytes per SNP).  Copies to the device and runs the statistics
  * kernel (per-SNP allele sum, sum of squares, non-missing count). */
-int  dbslmm_b200_load_bed(dbslmm_b200_handle* h, const uint8_t* bed, int64_t n_snp, int32_t n_ref);
+DBSLMM_B200_API int  dbslmm_b200_load_bed(dbslmm_b200_handle* h, const uint8_t* bed, int64_t n_snp, int32_t n_ref);
 
 /* MAF pre-pass product (dtpr.cpp:93-102, 361-362): maf after mean imputation; optional
  * non-missing counts.  Both arrays have n_snp entries. */
-int  dbslmm_b200_snp_stats(dbslmm_b200_handle* h, double* maf_out, int32_t* n_nonmiss_out);
+DBSLMM_B200_API int  dbslmm_b200_snp_stats(dbslmm_b200_handle* h, double* maf_out, int32_t* n_nonmiss_out);
 
 /* Block scheduler: O(n m^2 + m^3) cost model, longest-processing-time-first onto n_ranks.
  * m_s/m_l are per-block SNP counts (m_l may be NULL).  owner_out[b] in [0, n_ranks). */
-int  dbslmm_b200_plan_shards(int32_t n_blocks, const int32_t* m_s, const int32_t* m_l,
+DBSLMM_B200_API int  dbslmm_b200_plan_shards(int32_t n_blocks, const int32_t* m_s, const int32_t* m_l,
                              int32_t n_ref, int32_t n_ranks, int32_t* owner_out, double* rank_cost_out);
 
-int  dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* args);
+DBSLMM_B200_API int  dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* args);
 
 /* ---- inspection hooks used by the parity tests (operate on the state of the last fit) ---- */
 /* int8 codes of one decoded row of the last fit (row = global row index in block order:
  * block b's rows are its small SNPs then its large SNPs); n_pad bytes. */
-int  dbslmm_b200_get_row_codes(dbslmm_b200_handle* h, int64_t row, int8_t* codes_out, int32_t n_out);
+DBSLMM_B200_API int  dbslmm_b200_get_row_codes(dbslmm_b200_handle* h, int64_t row, int8_t* codes_out, int32_t n_out);
 /* Sigma of block b as dense row-major m x m (m = m_s + m_l, small SNPs first).  Lower triangle is
  * always valid; the upper one only with FLAG_FULL_SIGMA / PCG solver (else mirrored on the host). */
-int  dbslmm_b200_get_block_sigma(dbslmm_b200_handle* h, int32_t block, double* sigma_out);
+DBSLMM_B200_API int  dbslmm_b200_get_block_sigma(dbslmm_b200_handle* h, int32_t block, double* sigma_out);
 /* raw integer Gram planes (needs FLAG_KEEP_INT_GRAM): Q = G G^T, A_ij = sum g_i M_j, N = M M^T;
  * A and N may be NULL; for blocks without missing calls A_ij = S_i and N = n_ref. */
-int  dbslmm_b200_get_block_gram(dbslmm_b200_handle* h, int32_t block, int32_t* q_out, int32_t* a_out, int32_t* n_out);
+DBSLMM_B200_API int  dbslmm_b200_get_block_gram(dbslmm_b200_handle* h, int32_t block, int32_t* q_out, int32_t* a_out, int32_t* n_out);
 /* PCG iteration count of block b in the last PCG-solver fit (max over its right-hand sides). */
-int  dbslmm_b200_get_block_iters(dbslmm_b200_handle* h, int32_t block);
+DBSLMM_B200_API int  dbslmm_b200_get_block_iters(dbslmm_b200_handle* h, int32_t block);
 
 #ifdef __cplusplus
 }
