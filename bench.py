@@ -113,30 +113,20 @@ def build_workload(args, torch, dev, rank_seed):
 
 
 def shard_workload(w, owner, rank, torch):
-    """Compact per-rank problem: only this rank's blocks and their .bed rows (pinned)."""
-    sizes = w["sizes"]
-    starts = np.concatenate([[0], np.cumsum(sizes)])[:-1]
-    mine = np.where(owner == rank)[0]
-    rows = np.concatenate([np.arange(starts[b], starts[b] + sizes[b]) for b in mine]) if mine.size else np.zeros(0, np.int64)
-    remap = np.full(w["n_snp"], -1, np.int64)
-    remap[rows] = np.arange(rows.size)
-    bed_t = torch.empty((max(rows.size, 1), w["bed"].shape[1]), dtype=torch.uint8, pin_memory=True)
-    if rows.size:
-        bed_t[:rows.size].copy_(torch.from_numpy(w["bed"][rows]))
-    s_off = np.zeros(mine.size + 1, np.int32)
-    l_off = np.zeros(mine.size + 1, np.int32)
-    s_pos, l_pos, s_z, l_z = [], [], [], []
-    for i, b in enumerate(mine):
-        sp = w["s_pos"][w["s_off"][b]:w["s_off"][b + 1]]
-        lp = w["l_pos"][w["l_off"][b]:w["l_off"][b + 1]]
-        s_pos.append(remap[sp]); l_pos.append(remap[lp])
-        s_z.append(w["z"][sp]); l_z.append(w["z"][lp])
-        s_off[i + 1] = s_off[i] + sp.size
-        l_off[i + 1] = l_off[i] + lp.size
-    cat = lambda xs, dt: (np.concatenate(xs).astype(dt) if xs else np.zeros(0, dt))
-    return {"blocks": mine, "n_rows": rows.size, "bed_t": bed_t, "bed": bed_t.numpy()[:max(rows.size, 1)],
-            "s_off": s_off, "s_pos": cat(s_pos, np.int32), "s_z": cat(s_z, np.float64),
-            "l_off": l_off, "l_pos": cat(l_pos, np.int32), "l_z": cat(l_z, np.float64)}
+    """Compact per-rank problem (dbslmm_b200.multigpu.shard) with the .bed shard in pinned host memory."""
+    from dbslmm_b200 import multigpu
+    keep = []
+
+    def pinned(shape):
+        t = torch.empty(shape, dtype=torch.uint8, pin_memory=True)
+        keep.append(t)
+        return t.numpy()
+    ww = dict(w)
+    ww["s_z"] = w["z"][w["s_pos"]]
+    ww["l_z"] = w["z"][w["l_pos"]]
+    sh = multigpu.shard(ww, owner, rank, pinned_alloc=pinned)
+    sh["_pin"] = keep
+    return sh
 
 
 class ClockSampler:

@@ -1,0 +1,197 @@
+"""GPU parity tests: every call goes through the C ABI (ctypes) of libdbslmm_b200.so.
+
+Bars (DESIGN.md "Parity"):
+  decoder codes, per-SNP counts, integer Gram planes ......... bit-exact
+  maf ........................................................ <= 1e-15 abs (one FP64 division)
+  Sigma ...................................................... <= 1e-13 abs vs the reference float path
+  beta, Cholesky solver vs `exact` oracle .................... <= 1e-10 of max|beta| per call
+  beta vs the UNMODIFIED reference's golden vectors .......... <= 2e-7 of max|beta|: the reference stops PCG at an
+       absolute residual of 1e-7, so ITS answer carries a few 1e-8 of truncation error (tests/test_oracle.py)
+"""
+import os
+
+import numpy as np
+import pytest
+
+from dbslmm_b200 import _abi, synth
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def relmax(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def block_pos(w, b):
+    return np.concatenate([w["s_pos"][w["s_off"][b]:w["s_off"][b + 1]], w["l_pos"][w["l_off"][b]:w["l_off"][b + 1]]]).astype(np.int32)
+
+
+CASES = {
+    # name: (block sizes, n_ref, missing rate)
+    "ragged_plain": ([300, 0, 1, 7, 8, 63, 64, 65, 127, 128, 129, 200], 400, 0.0),
+    "ragged_missing": ([150, 70, 5, 130, 0, 257], 403, 0.02),
+    "odd_pitch": ([90, 33], 125 * 4 - 3, 0.0),        # pitch 125 B: unaligned rows, 3 padding samples
+    "wide_n": ([260, 140], 2000, 0.005),
+}
+
+
+@pytest.fixture(scope="module", params=list(CASES))
+def case(request, engine):
+    sizes, n_ref, miss = CASES[request.param]
+    w = synth.make_workload(1234 + len(sizes), sizes, n_ref, missing_rate=miss, frac_large=0.02)
+    engine.load_bed(w["bed"], n_ref)
+    return request.param, w
+
+
+def test_snp_stats(case, engine):
+    _, w = case
+    maf, nn = engine.snp_stats()
+    assert np.array_equal(nn, (w["G"] >= 0).sum(axis=1))
+    assert np.abs(maf - O.snp_maf(w["bed"], w["bed"].shape[0], w["n_ref"])).max() <= 1e-15
+
+
+def test_decode_gram_sigma(case, engine):
+    name, w = case
+    n_ref = w["n_ref"]
+    r = engine.fit(w["s_off"], w["s_pos"], w["s_z"], w["l_off"], w["l_pos"], w["l_z"], sigma_s=[1e-4], n_obs=10_000,
+                   flags=_abi.FLAG_KEEP_INT_GRAM)
+    assert r["n_bad"] == 0
+    Gz = np.where(w["G"] < 0, 0, w["G"]).astype(np.int8)
+    n_pad = (n_ref + 127) // 128 * 128
+    row = 0
+    for b, m in enumerate(w["block_sizes"]):
+        if m == 0:
+            continue
+        pos = block_pos(w, b)
+        miss = bool((w["G"][pos] < 0).any())
+        for j in sorted({0, m // 2, m - 1}):
+            codes = engine.row_codes(row + j, n_pad)
+            assert np.array_equal(codes[:n_ref], Gz[pos[j]]) and not codes[n_ref:].any()
+            if miss:
+                mk = engine.row_codes(row + m + j, n_pad)
+                assert np.array_equal(mk[:n_ref], (w["G"][pos[j]] >= 0).astype(np.int8)) and not mk[n_ref:].any()
+        Q, A, N = engine.block_gram(b, m)
+        Qo, Ao, No = O.gram_int(w["bed"], n_ref, pos)
+        assert np.array_equal(Q, Qo), (name, b)
+        assert np.array_equal(A, Ao) and np.array_equal(N, No), (name, b)
+        S = engine.block_sigma(b, m)
+        assert np.abs(S - O.sigma(w["bed"], n_ref, pos)).max() <= 1e-13, (name, b)
+        assert np.array_equal(S, S.T)
+        row += m * (2 if miss else 1)
+
+
+@pytest.mark.parametrize("mode", ["dbslmm", "lmm"])
+def test_beta_vs_exact_oracle(case, engine, mode):
+    _, w = case
+    n_ref = w["n_ref"]
+    sig, n_obs = 0.5 / 3000.0, 30_000
+    if mode == "dbslmm":
+        csr = (w["s_off"], w["s_pos"], w["s_z"], w["l_off"], w["l_pos"], w["l_z"])
+    else:
+        sizes = w["block_sizes"]
+        off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+        z = np.zeros(off[-1]); z[w["s_pos"]] = w["s_z"]; z[w["l_pos"]] = w["l_z"]
+        csr = (off, np.arange(off[-1], dtype=np.int32), z)
+    r = engine.fit(*csr, sigma_s=[sig], n_obs=n_obs)
+    assert r["n_bad"] == 0 and not r["status"].any()
+    bs, bl, sing, _ = O.est(w["bed"], n_ref, n_obs, sig, *csr, threads=4, mode=O.MODE_EXACT)
+    assert sing == 0
+    assert relmax(r["beta_s"][0], bs) <= 1e-10
+    if mode == "dbslmm" and bl.size:
+        assert relmax(r["beta_l"][0], bl) <= 1e-10
+    assert r["timing"]["n_launches"] > 0
+
+
+def test_h2_folds_share_one_gram(engine):
+    w = synth.make_workload(77, [180, 90, 40], 500, frac_large=0.02)
+    engine.load_bed(w["bed"], 500)
+    csr = (w["s_off"], w["s_pos"], w["s_z"], w["l_off"], w["l_pos"], w["l_z"])
+    sig = np.array([0.8, 1.0, 1.2]) * 0.4 / 2000.0
+    r = engine.fit(*csr, sigma_s=sig, n_obs=20_000)
+    assert r["beta_s"].shape == (3, w["s_pos"].size)
+    for f in range(3):
+        bs, bl, _, _ = O.est(w["bed"], 500, 20_000, float(sig[f]), *csr, threads=4, mode=O.MODE_EXACT)
+        assert relmax(r["beta_s"][f], bs) <= 1e-10 and relmax(r["beta_l"][f], bl) <= 1e-10
+    assert relmax(r["beta_s"][0], r["beta_s"][2]) > 1e-3          # the folds really differ
+
+
+def test_plan_cache_reuses_layout_with_new_z(engine):
+    w = synth.make_workload(5, [120, 300], 400, frac_large=0.0)
+    engine.load_bed(w["bed"], 400)
+    r1 = engine.fit(w["s_off"], w["s_pos"], w["s_z"], sigma_s=[1e-4], n_obs=5000)
+    z2 = w["s_z"][::-1].copy()
+    r2 = engine.fit(w["s_off"], w["s_pos"], z2, sigma_s=[1e-4], n_obs=5000, flags=_abi.FLAG_PLAN_CACHED)
+    b2, _, _, _ = O.est(w["bed"], 400, 5000, 1e-4, w["s_off"], w["s_pos"], z2, threads=4, mode=O.MODE_EXACT)
+    assert relmax(r2["beta_s"][0], b2) <= 1e-10 and relmax(r1["beta_s"][0], b2) > 1e-3
+
+
+def test_golden_c1_testdat(engine):
+    """BASELINE.json configs[0] against the unmodified reference's FP64 betas."""
+    d = np.load(os.path.join(GOLD, "c1_testdat.npz"))
+    n_ref, n_obs, sig = int(d["n_ref"]), int(d["n_obs"]), float(d["sigma_s"])
+    engine.load_bed(d["bed"], n_ref)
+    maf, _ = engine.snp_stats()
+    assert np.abs(maf - d["ref_maf"]).max() <= 1e-15
+    r = engine.fit(d["lmm_off"], d["lmm_pos"], d["lmm_z"], sigma_s=[sig], n_obs=n_obs)
+    assert r["n_bad"] == 0
+    assert relmax(r["beta_s"][0], d["lmm_beta"]) <= 2e-8            # measured reference truncation gap: 3e-9
+    r = engine.fit(d["s_off"], d["s_pos"], d["s_z"], d["l_off"], d["l_pos"], d["l_z"], sigma_s=[sig], n_obs=n_obs)
+    assert relmax(r["beta_s"][0], d["beta_s"]) <= 2e-7 and relmax(r["beta_l"][0], d["beta_l"]) <= 2e-7
+    bs, bl, _, _ = O.est(d["bed"], n_ref, n_obs, sig, d["s_off"], d["s_pos"], d["s_z"], d["l_off"], d["l_pos"], d["l_z"],
+                         mode=O.MODE_EXACT)
+    assert relmax(r["beta_s"][0], bs) <= 1e-10 and relmax(r["beta_l"][0], bl) <= 1e-10
+
+
+def test_golden_synth_ragged(engine):
+    d = np.load(os.path.join(GOLD, "synth_ragged.npz"))
+    n_ref, n_obs, sig = int(d["n_ref"]), int(d["n_obs"]), float(d["sigma_s"])
+    engine.load_bed(d["bed"], n_ref)
+    r = engine.fit(d["s_off"], d["s_pos"], d["s_z"], d["l_off"], d["l_pos"], d["l_z"], sigma_s=[sig], n_obs=n_obs)
+    assert r["n_bad"] == 0
+    assert relmax(r["beta_s"][0], d["beta_s"]) <= 2e-7 and relmax(r["beta_l"][0], d["beta_l"]) <= 2e-7
+
+
+def test_monomorphic_snp_poisons_only_its_block(engine):
+    """stddev = 0 => NaN column in the reference (dtpr.cpp:378); we flag the block and leave the others intact."""
+    w = synth.make_workload(9, [40, 50], 400, frac_large=0.0)
+    G = w["G"].copy()
+    G[3, :] = 1
+    bed = synth.pack_bed(G)
+    engine.load_bed(bed, 400)
+    r = engine.fit(w["s_off"], w["s_pos"], w["s_z"], sigma_s=[1e-4], n_obs=5000)
+    assert r["n_bad"] == 1 and r["status"][0] == 1 and r["status"][1] == 0
+    assert not np.isfinite(r["beta_s"][0][:40]).all() and np.isfinite(r["beta_s"][0][40:]).all()
+
+
+def test_argument_errors(engine):
+    w = synth.make_workload(5, [20], 400, frac_large=0.0)
+    engine.load_bed(w["bed"], 400)
+    with pytest.raises(_abi.EngineError):
+        engine.fit(w["s_off"], w["s_pos"] + 10_000, w["s_z"], sigma_s=[1e-4], n_obs=5000)
+    with pytest.raises(_abi.EngineError):
+        engine.fit(w["s_off"], w["s_pos"], w["s_z"], sigma_s=[-1.0], n_obs=5000)
+
+
+def test_full_size_properties(engine):
+    """At a BASELINE-sized block (m = 3000, n_ref = 2000) the oracle is too slow for a per-call check:
+    use size-independent properties: K x = z residual from Sigma itself, symmetry, unit diagonal structure."""
+    sizes = [3000, 646]
+    rng = np.random.default_rng(3)
+    G = synth.make_genotypes(rng, sizes, 2000)
+    bed = synth.pack_bed(G)
+    engine.load_bed(bed, 2000)
+    off = np.array([0, 3000, 3646], np.int32)
+    z = rng.standard_normal(3646)
+    sig, n_obs = 0.5 / 1.1e6, 300_000
+    r = engine.fit(off, np.arange(3646, dtype=np.int32), z, sigma_s=[sig], n_obs=n_obs, flags=_abi.FLAG_FULL_SIGMA)
+    assert r["n_bad"] == 0
+    for b, (lo, hi) in enumerate(((0, 3000), (3000, 3646))):
+        S = engine.block_sigma(b, hi - lo)
+        assert np.array_equal(S, S.T)
+        assert np.abs(np.diag(S) - (0.8 * 1999 / 2000 + 0.2)).max() < 1e-12
+        K = S + np.eye(hi - lo) / (sig * n_obs)
+        x = r["beta_s"][0][lo:hi] * np.sqrt(n_obs)
+        res = np.abs(K @ x - z[lo:hi]).max() / np.abs(z[lo:hi]).max()
+        assert res < 1e-11, res

@@ -1,0 +1,131 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (oracle/_ref, built by
+oracle/build_ref.sh from /root/reference/scr over oracle/shim) in this container.
+
+  c1_testdat.npz  BASELINE.json configs[0]: test_dat chr1 (summary_gemma_chr1.assoc.txt + ref_chr1),
+                  h2 = 0.5, nsnp = 996, n = 2400, mafMax 0.2, -t 1.  Holds the input files as byte
+                  strings (so the CLI test can re-create them on the GPU box), the matched CSR
+                  problem, the reference's FP64 betas (harness: readSNPIm + nomalizeVec + estBlock)
+                  for LMM and DBSLMM mode and the `dbslmm` CLI's text output.
+  synth_ragged.npz  seeded synthetic panel with ragged blocks and 2 % missing calls + reference betas.
+The large/small split restates `plink --clump` (r2 0.2, 1000 kb, p1 1e-6) as software/DBSLMM.R:140-145
+calls it; plink itself is not in this image.
+"""
+import os, subprocess, sys, tempfile
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from dbslmm_b200 import hostio as H, synth
+from oracle import oracle as O, refharness as R
+
+REF = "/root/reference"
+TD = REF + "/test_dat/"
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def clump(summ, lines, bim, bed, n_ref):
+    p = np.array([float(l.split("\t")[10]) for l in lines])
+    order = np.argsort(p, kind="stable")
+    chosen, cache = [], {}
+    def g(i):
+        if i not in cache:
+            x, _ = O.read_snp_im(bed, bim[summ.snp[i]][0], n_ref)
+            cache[i] = O.normalize(x)
+        return cache[i]
+    for i in order:
+        if p[i] >= 1e-6:
+            break
+        if summ.snp[i] not in bim:
+            continue
+        ok = True
+        for c in chosen:
+            if abs(summ.ps[i] - summ.ps[c]) <= 1_000_000:
+                r = float(np.dot(g(i), g(c))) / (n_ref - 1)
+                if r * r >= 0.2:
+                    ok = False
+                    break
+        if ok:
+            chosen.append(i)
+    return sorted(chosen)
+
+
+def c1():
+    n_ref = H.read_fam_count(TD + "ref_chr1.fam")
+    bim, nsnp = H.read_bim(TD + "ref_chr1.bim")
+    bed = H.read_bed(TD + "ref_chr1.bed", nsnp, n_ref)
+    lines = [l for l in open(TD + "summary_gemma_chr1.assoc.txt").read().split("\n") if l]
+    summ = H.read_summ(TD + "summary_gemma_chr1.assoc.txt")
+    large = clump(summ, lines, bim, bed, n_ref)
+    ls = set(large)
+    l_txt = "\n".join(lines[i] for i in large) + "\n"
+    s_txt = "\n".join(lines[i] for i in range(len(lines)) if i not in ls) + "\n"
+    blk_txt = open(REF + "/block_data/EUR/chr1.bed").read()
+    bs, be = H.read_block(REF + "/block_data/EUR/chr1.bed")
+    maf = O.snp_maf(bed, nsnp, n_ref)
+    n_obs, sigma_s = 2400, 0.5 / 996
+    out = {}
+    with tempfile.TemporaryDirectory() as td:
+        open(td + "/l.txt", "w").write(l_txt)
+        open(td + "/s.txt", "w").write(s_txt)
+        open(td + "/ind.txt", "w").write("\n".join(["1"] * 20 + ["0"] * 83) + "\n")
+        # ---- the unmodified CLI (DBSLMM mode, then LMM mode = no -l)
+        for mode, extra in (("dbslmm", ["-l", td + "/l.txt", "-s", td + "/s.txt"]), ("lmm", ["-s", TD + "summary_gemma_chr1.assoc.txt"])):
+            cmd = [R.CLI] + extra + ["-r", TD + "ref_chr1", "-n", "2400", "-nsnp", "996", "-mafMax", "0.2", "-b",
+                   REF + "/block_data/EUR/chr1.bed", "-h", "0.5", "-t", "1", "-eff", td + "/out_" + mode,
+                   "-test_indicator_file", td + "/ind.txt", "-dat_str", TD + "test_chr1"]
+            rc = subprocess.run(cmd, cwd=td, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL).returncode
+            if rc != 0:
+                # the fork's small-only calcBlock sizes `gg` with n_obs (dbslmmfit.cpp:585) and assigns it
+                # into an n_test-row column (:593): it aborts unless n_obs == n_test, so the unmodified
+                # CLI has no LMM-mode output on this fixture; LMM betas come from the harness below.
+                print("reference CLI failed in mode", mode, "rc", rc)
+                continue
+            out["cli_" + mode + "_txt"] = open(td + "/out_" + mode + ".txt").read()
+            out["cli_" + mode + "_badsnps"] = open(td + "/out_" + mode + ".badsnps").read()
+    # ---- matched CSR problems + FP64 reference betas through the harness
+    def problem(summ_subset_idx):
+        sub = H.Summ([summ.snp[i] for i in summ_subset_idx], summ.ps[summ_subset_idx], [summ.a1[i] for i in summ_subset_idx],
+                     [summ.a2[i] for i in summ_subset_idx], summ.maf[summ_subset_idx], summ.z[summ_subset_idx])
+        keep, pos = H.match_ref(sub, bim, maf, 0.2)
+        blk = H.add_block(sub.ps[keep], bs, be)
+        ok = blk >= 0
+        return H.to_csr(blk, len(bs)), pos[ok], sub.z[keep][ok]
+    all_idx = np.arange(len(lines))
+    small_idx = np.array([i for i in all_idx if i not in ls])
+    large_idx = np.array(large)
+    with R.BedFile(bed) as bf:
+        off, pos, z = problem(all_idx)
+        b_lmm, _ = R.est_path(bf.path, n_ref, n_obs, sigma_s, off, pos, z, threads=1)
+        s_off, s_pos, s_z = problem(small_idx)
+        l_off, l_pos, l_z = problem(large_idx)
+        b_s, b_l = R.est_path(bf.path, n_ref, n_obs, sigma_s, s_off, s_pos, s_z, l_off, l_pos, l_z, threads=1)
+    out.update(dict(bed=bed, n_ref=n_ref, n_obs=n_obs, sigma_s=sigma_s, ref_maf=maf,
+                    bim_txt=open(TD + "ref_chr1.bim").read(), fam_lines=n_ref, summary_txt="\n".join(lines) + "\n",
+                    l_txt=l_txt, s_txt=s_txt, block_txt=blk_txt,
+                    lmm_off=off, lmm_pos=pos, lmm_z=z, lmm_beta=b_lmm,
+                    s_off=s_off, s_pos=s_pos, s_z=s_z, l_off=l_off, l_pos=l_pos, l_z=l_z, beta_s=b_s, beta_l=b_l))
+    np.savez_compressed(os.path.join(GOLD, "c1_testdat.npz"), **out)
+    print("c1: LMM m=%d, DBSLMM m_s=%d m_l=%d" % (pos.size, s_pos.size, l_pos.size))
+
+
+def ragged():
+    sizes = [150, 0, 1, 9, 64, 70, 131]
+    w = synth.make_workload(20240001, sizes, 403, missing_rate=0.02, frac_large=0.03)
+    n_obs, sigma_s = 50_000, 0.4 / 20_000
+    with R.BedFile(w["bed"]) as bf:
+        b_s, b_l = R.est_path(bf.path, 403, n_obs, sigma_s, w["s_off"], w["s_pos"], w["s_z"], w["l_off"], w["l_pos"], w["l_z"], threads=4)
+        off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+        zz = np.zeros(off[-1]); zz[w["s_pos"]] = w["s_z"]; zz[w["l_pos"]] = w["l_z"]
+        b_lmm, _ = R.est_path(bf.path, 403, n_obs, sigma_s, off, np.arange(off[-1], dtype=np.int32), zz, threads=4)
+        maf = np.array([R.read_snp_im(bf.path, i, 403)[1] for i in range(off[-1])])
+    np.savez_compressed(os.path.join(GOLD, "synth_ragged.npz"), bed=w["bed"], G=w["G"], n_ref=403, n_obs=n_obs, sigma_s=sigma_s,
+                        sizes=np.asarray(sizes), s_off=w["s_off"], s_pos=w["s_pos"], s_z=w["s_z"], l_off=w["l_off"],
+                        l_pos=w["l_pos"], l_z=w["l_z"], beta_s=b_s, beta_l=b_l, lmm_off=off, lmm_z=zz, lmm_beta=b_lmm, ref_maf=maf)
+    print("ragged: large per block", np.diff(w["l_off"]))
+
+
+if __name__ == "__main__":
+    if not R.available():
+        raise SystemExit("oracle/_ref missing: run oracle/build_ref.sh first")
+    os.makedirs(GOLD, exist_ok=True)
+    c1()
+    ragged()
