@@ -377,7 +377,8 @@ def main():
              "gram": {"bound": "hbm (Sigma write) / int8 tensor", "int8_Pops": gram_pops,
                       "sigma_write_GBs": sigma_bytes / (avg("gram_ms") * 1e-3) / 1e9 if world == 1 and avg("gram_ms") > 0 else None,
                       "ms": avg("gram_ms")},
-             "solve_total_ms": avg("solve_ms"), "h2d_ms": avg("h2d_ms"), "d2h_ms": avg("d2h_ms")}
+             "solve_total_ms": avg("solve_ms"), "h2d_ms": avg("h2d_ms"), "d2h_ms": avg("d2h_ms"),
+             "chol_class_ms": [float(np.mean([t["class_ms"][c] for t in tms])) for c in range(4)]}
     h2d = int(sh["bed"].nbytes + 8 * my_snps + 24 * my_snps)     # bed + z + plan rows (rank 0's share)
     d2h = int(8 * my_snps + 8 * my_blocks)
     line = {"metric": "LD blocks fitted/sec genome-wide", "value": value, "unit": "blocks/s", "n_gpus": world,

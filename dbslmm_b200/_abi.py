@@ -30,10 +30,12 @@ class Timing(C.Structure):
                 ("solve_ms", C.c_float), ("d2h_ms", C.c_float), ("total_ms", C.c_float),
                 ("n_launches", C.c_int32), ("n_chol_launches", C.c_int32),
                 ("gram_ops", C.c_double), ("solve_flops", C.c_double), ("decode_bytes", C.c_double),
-                ("chol_ms", C.c_double)]
+                ("chol_ms", C.c_double), ("class_ms", C.c_float * 4)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        d = {k: getattr(self, k) for k, _ in self._fields_}
+        d["class_ms"] = list(self.class_ms)
+        return d
 
 
 class FitArgs(C.Structure):

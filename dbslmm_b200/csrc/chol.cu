@@ -13,10 +13,11 @@
 //
 // Algorithm: left-looking tile Cholesky, panel width 64, batched over ALL blocks of a size
 // class per panel step k (two launches per step):
-//   chol_diag_kernel  : T_kk = K_kk - L_k,0:k L_k,0:k^T (DMMA), potrf(T_kk) in shared memory,
-//                       W_kk = L_kk^-1; L_kk -> lower, W_kk^T -> upper triangle of the tile.
+//   chol_diag_kernel  : potrf of the (already updated) 64x64 diagonal tile T_kk and W_kk = L_kk^-1;
+//                       L_kk -> lower, W_kk^T -> upper triangle of the tile.
 //   chol_panel_kernel : for each 128-row macro tile below: C = K_ik - L_i,0:k L_k,0:k^T (DMMA,
-//                       cp.async 3-stage ring), then L_ik = C W_kk^T (DMMA) -- TRSM as a GEMM.
+//                       cp.async 3-stage ring), L_ik = C W_kk^T (DMMA) -- TRSM as a GEMM -- and the
+//                       look-ahead T_ii -= L_ik L_ik^T on the macro tile's own diagonal tiles.
 // The z-scores ride along as matrix row `mp`, so that row of L ends up holding y = L^-1 z;
 // backsolve_kernel then solves L^T x = y per block and writes beta = x / sqrt(N).
 // Matrices are row-major, lower triangle, ld = mp (m padded to 8 with identity rows).
@@ -104,98 +105,177 @@ __device__ __forceinline__ void gemm_nt_core(const double* __restrict__ Pg, cons
 }
 
 // ------------------------------------------------------------------------------------------
-// Diagonal tile of panel k for every active block: update, factor, invert.
+// Diagonal tile of panel k for every active block: factor + invert (no GEMM: the tile arrives
+// fully updated, see chol_panel_kernel's look-ahead SYRK).
+//   potrf: 4 sub-blocks of 16; each 16x16 diagonal sub-block is factored and inverted by ONE
+//   warp in registers (shuffles), the sub-panel below and the trailing part by all 8 warps.
+//   W = L^-1 is then assembled block-wise from the four 16x16 inverses.
+// Tiles narrower than 64 (last panel) are padded with identity, so the code path is uniform.
 // ------------------------------------------------------------------------------------------
+static constexpr int DT = NB + 1;   // odd stride: conflict-free row and column walks in FP64
+static constexpr int SMEM_DIAG = (2 * NB * DT + 16 * 17) * 8;
+
 __global__ void __launch_bounds__(CHOL_THREADS, 2)
 chol_diag_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict__ items, int32_t k,
                  const double* __restrict__ sigma, double* __restrict__ Lbuf, double ridge,
                  int32_t* __restrict__ status) {
     extern __shared__ __align__(16) double smem[];
+    double* T = smem;                        // [64][DT] tile, becomes L (lower)
+    double* Wf = T + NB * DT;                // [64][DT] W = L^-1 (lower)
+    double* tmp = Wf + NB * DT;              // [16][17]
     const int blk = items[blockIdx.x];
     const BlockDesc bd = blocks[blk];
     const int pc0 = k * NB;
     const int wk = min(NB, bd.mp - pc0);
     const int ld = bd.ld;
     double* Lb = Lbuf + bd.moff;
-    const double* Sb = sigma + bd.moff;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const double* src = (k == 0 ? sigma : Lbuf) + bd.moff;     // step 0 reads Sigma, later steps the accumulated tile
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    double acc[2][8][2];
-#pragma unroll
-    for (int f = 0; f < 2; ++f)
-#pragma unroll
-        for (int c = 0; c < 8; ++c) acc[f][c][0] = acc[f][c][1] = 0.0;
-    const double* Qg = Lb + (size_t)pc0 * ld;
-    gemm_nt_core(Qg, Qg, ld, wk, wk, pc0, smem, acc);
+    for (int idx = tid; idx < NB * NB; idx += CHOL_THREADS) {
+        const int a = idx >> 6, b = idx & 63;
+        double v = (a == b) ? 1.0 : 0.0;
+        if (a < wk && b < wk) {
+            v = 0.0;
+            if (b <= a) {
+                v = src[(size_t)(pc0 + a) * ld + pc0 + b];
+                if (k == 0 && a == b && a < bd.ms) v += ridge;
+            }
+        }
+        T[a * DT + b] = v;
+        Wf[a * DT + b] = 0.0;
+    }
+    __syncthreads();
 
-    double* T = smem;                 // [64][LDT]
-    double* W = smem + NB * LDT;      // [64][LDT]
-    for (int i = tid; i < NB * LDT; i += CHOL_THREADS) W[i] = 0.0;
-    if (16 * warp < wk) {
+    bool bad = false;
+#pragma unroll 1
+    for (int jb = 0; jb < 4; ++jb) {
+        const int o = 16 * jb;
+        if (warp == 0) {
+            // ---- 16x16 potrf + inverse in registers; lane r (and r+16) holds row r
+            const int r = lane & 15;
+            double row[16];
 #pragma unroll
-        for (int f = 0; f < 2; ++f)
+            for (int c = 0; c < 16; ++c) row[c] = T[(o + r) * DT + o + c];
+            double dinv[16];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const int r = 16 * warp + 8 * f + g, cc = 8 * c + 2 * t;
-                if (r < wk && cc <= r) {                       // lower triangle (+ the pair partner)
-                    const double2 a = *reinterpret_cast<const double2*>(Sb + (size_t)(pc0 + r) * ld + pc0 + cc);
-                    double v0 = a.x - acc[f][c][0], v1 = a.y - acc[f][c][1];
-                    const int gr = pc0 + r;
-                    if (cc == r && gr < bd.ms) v0 += ridge;
-                    if (cc + 1 == r && gr < bd.ms) v1 += ridge;
-                    T[r * LDT + cc] = v0;
-                    T[r * LDT + cc + 1] = v1;                  // (r, cc+1) may be above the diagonal: unused
+            for (int j = 0; j < 16; ++j) {
+                const double d = __shfl_sync(0xffffffffu, row[j], j);
+                if (!(d > 0.0)) bad = true;
+                const double inv = rsqrt(d);
+                const double sq = d * inv;
+                dinv[j] = 1.0 / sq;
+                double lrj = row[j] * inv;
+                if (r == j) lrj = sq;
+                if (r < j) lrj = 0.0;
+                row[j] = lrj;
+#pragma unroll
+                for (int c = j + 1; c < 16; ++c) {
+                    const double lcj = __shfl_sync(0xffffffffu, lrj, c);
+                    row[c] -= lrj * lcj;
                 }
             }
-    }
-    // ---- potrf (right-looking, in shared memory)
-    bool bad = false;
-    const int ty = tid >> 4, tx = tid & 15;
-    for (int j = 0; j < wk; ++j) {
-        __syncthreads();
-        const double d = T[j * LDT + j];
-        if (!(d > 0.0)) bad = true;
-        const double s = sqrt(d), inv = 1.0 / s;
-        if (tid > j && tid < wk) T[tid * LDT + j] *= inv;
-        __syncthreads();
-        if (tid == 0) T[j * LDT + j] = s;
-        for (int i = j + 1 + ty; i < wk; i += 16) {
-            const double lij = T[i * LDT + j];
-            for (int c = j + 1 + tx; c <= i; c += 16) T[i * LDT + c] -= lij * T[c * LDT + j];
-        }
-    }
-    __syncthreads();
-    if (bad && tid == 0) atomicOr(&status[blk], 1);
-    // ---- W = L^-1 (lower), four lanes per column
-    {
-        const int c = tid >> 2, q = tid & 3;
-        const int cw0 = (warp * 8);                            // first column handled by this warp
-        if (q == 0 && c < wk) W[c * LDT + c] = 1.0 / T[c * LDT + c];
-        __syncwarp();
-        for (int i = cw0 + 1; i < wk; ++i) {
-            double p = 0.0;
-            if (c < wk && i > c)
-                for (int kk = c + q; kk < i; kk += 4) p += T[i * LDT + kk] * W[kk * LDT + c];
-            p += __shfl_xor_sync(0xffffffffu, p, 1);
-            p += __shfl_xor_sync(0xffffffffu, p, 2);
-            if (q == 0 && c < wk && i > c) W[i * LDT + c] = -p / T[i * LDT + i];
+            if (lane < 16) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) T[(o + r) * DT + o + c] = (c <= r) ? row[c] : 0.0;
+            }
             __syncwarp();
+            // inverse: lane c owns column c of W16; w[i] = -(sum_{k<i} l_ik w[k]) / l_ii
+            const int c = r;
+            double w[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+                for (int kk = 0; kk + 1 < i; kk += 2) {
+                    acc0 += T[(o + i) * DT + o + kk] * w[kk];
+                    acc1 += T[(o + i) * DT + o + kk + 1] * w[kk + 1];
+                }
+                if (i & 1) acc0 += T[(o + i) * DT + o + i - 1] * w[i - 1];
+                double wi = -(acc0 + acc1) * dinv[i];
+                if (i == c) wi = dinv[i];
+                if (i < c) wi = 0.0;
+                w[i] = wi;
+            }
+            if (lane < 16) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) Wf[(o + i) * DT + o + c] = w[i];
+            }
+        }
+        __syncthreads();
+        if (jb == 3) break;
+        // ---- sub-panel below: X = T[rows, o:o+16] * W16^T  (rows o+16 .. 63)
+        const int nrem = 48 - o;
+        double x[3];
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const int oi = tid + u * CHOL_THREADS;
+            x[u] = 0.0;
+            if (oi < nrem * 16) {
+                const int i = o + 16 + (oi >> 4), c = oi & 15;
+                double a = 0.0;
+                for (int cp = 0; cp <= c; ++cp) a += T[i * DT + o + cp] * Wf[(o + c) * DT + o + cp];
+                x[u] = a;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const int oi = tid + u * CHOL_THREADS;
+            if (oi < nrem * 16) T[(o + 16 + (oi >> 4)) * DT + o + (oi & 15)] = x[u];
+        }
+        __syncthreads();
+        // ---- trailing update of the remaining lower triangle
+        for (int oi = tid; oi < nrem * nrem; oi += CHOL_THREADS) {
+            const int i = oi / nrem, c = oi - i * nrem;
+            if (c <= i) {
+                const double* xi = T + (o + 16 + i) * DT + o;
+                const double* xc = T + (o + 16 + c) * DT + o;
+                double a = 0.0;
+#pragma unroll
+                for (int kk = 0; kk < 16; ++kk) a += xi[kk] * xc[kk];
+                T[(o + 16 + i) * DT + o + 16 + c] -= a;
+            }
+        }
+        __syncthreads();
+    }
+    if (warp == 0 && __any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&status[blk], 1);
+    // ---- off-diagonal 16x16 blocks of W:  W_ij = -W_ii * sum_{kb=j}^{i-1} L_i,kb W_kb,j
+    {
+        const int r = tid >> 4, c = tid & 15;
+#pragma unroll 1
+        for (int d = 1; d < 4; ++d) {
+#pragma unroll 1
+            for (int i = d; i < 4; ++i) {
+                const int j = i - d;
+                double a = 0.0;
+                for (int kk = 16 * j; kk < 16 * i; ++kk) a += T[(16 * i + r) * DT + kk] * Wf[kk * DT + 16 * j + c];
+                tmp[r * 17 + c] = a;
+                __syncthreads();
+                double wv = 0.0;
+                for (int kk = 0; kk <= r; ++kk) wv += Wf[(16 * i + r) * DT + 16 * i + kk] * tmp[kk * 17 + c];
+                Wf[(16 * i + r) * DT + 16 * j + c] = -wv;
+                __syncthreads();
+            }
         }
     }
-    __syncthreads();
     // ---- write back: lower = L_kk, strict upper = W_kk^T
     for (int idx = tid; idx < wk * wk; idx += CHOL_THREADS) {
         const int a = idx / wk, b = idx - a * wk;
-        Lb[(size_t)(pc0 + a) * ld + pc0 + b] = (b <= a) ? T[a * LDT + b] : W[b * LDT + a];
+        Lb[(size_t)(pc0 + a) * ld + pc0 + b] = (b <= a) ? T[a * DT + b] : Wf[b * DT + a];
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// Rows below the diagonal tile of panel k: update + triangular solve (as GEMM with W_kk^T).
+// Rows below the diagonal tile of panel k:
+//   C = K_ik - L_i,0:k L_k,0:k^T (DMMA, cp.async ring), L_ik = C W_kk^T (DMMA), then the
+//   look-ahead: each of the (up to two) 64-row tiles of this macro tile immediately applies
+//   its contribution  T_ii -= L_ik L_ik^T  to ITS OWN diagonal tile (one writer per tile and
+//   step, so no atomics), so the diagonal kernel never runs a GEMM.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(CHOL_THREADS, 2)
 chol_panel_kernel(const BlockDesc* __restrict__ blocks, const int2* __restrict__ items, int32_t k,
-                  const double* __restrict__ sigma, double* __restrict__ Lbuf) {
+                  const double* __restrict__ sigma, double* __restrict__ Lbuf, double ridge) {
     extern __shared__ __align__(16) double smem[];
     const int2 item = items[blockIdx.x];
     const BlockDesc bd = blocks[item.x];
@@ -216,7 +296,8 @@ chol_panel_kernel(const BlockDesc* __restrict__ blocks, const int2* __restrict__
         for (int c = 0; c < 8; ++c) acc[f][c][0] = acc[f][c][1] = 0.0;
     gemm_nt_core(Lb + (size_t)r0 * ld, Lb + (size_t)pc0 * ld, ld, prow, wk, pc0, smem, acc);
 
-    double* Cw = smem + warp * 16 * LDT;          // warp-private [16][LDT]
+    double* Ct = smem;                            // [128][LDT] macro tile, 16 rows per warp
+    double* Cw = Ct + warp * 16 * LDT;
     double* W = smem + 8 * 16 * LDT;              // [64][LDT], W[c][c'] = (L_kk^-1)[c][c'], zero above diagonal
     for (int i = tid; i < NB * LDT; i += CHOL_THREADS) W[i] = 0.0;
     __syncthreads();
@@ -227,36 +308,37 @@ chol_panel_kernel(const BlockDesc* __restrict__ blocks, const int2* __restrict__
         else if (b == a) W[a * LDT + a] = 1.0 / v;
     }
     const bool active = (16 * warp < prow);
-    if (active) {
 #pragma unroll
-        for (int f = 0; f < 2; ++f)
+    for (int f = 0; f < 2; ++f)
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const int rl = 16 * warp + 8 * f + g, cc = 8 * c + 2 * t;
-                double2 a = make_double2(0.0, 0.0);
-                if (rl < prow && cc < wk) a = *reinterpret_cast<const double2*>(Sb + (size_t)(r0 + rl) * ld + pc0 + cc);
-                Cw[(8 * f + g) * LDT + cc] = a.x - acc[f][c][0];
-                Cw[(8 * f + g) * LDT + cc + 1] = a.y - acc[f][c][1];
-                acc[f][c][0] = acc[f][c][1] = 0.0;
-            }
-    }
+        for (int c = 0; c < 8; ++c) {
+            const int rl = 16 * warp + 8 * f + g, cc = 8 * c + 2 * t;
+            double2 a = make_double2(0.0, 0.0);
+            if (rl < prow && cc < wk) a = *reinterpret_cast<const double2*>(Sb + (size_t)(r0 + rl) * ld + pc0 + cc);
+            Cw[(8 * f + g) * LDT + cc] = a.x - acc[f][c][0];
+            Cw[(8 * f + g) * LDT + cc + 1] = a.y - acc[f][c][1];
+            acc[f][c][0] = acc[f][c][1] = 0.0;
+        }
     __syncthreads();
-    if (!active) return;
     const double* Ca = Cw + g * LDT + t;
     const double* Wb = W + g * LDT + t;
     const int ns4 = wk / 4;
+    if (active) {
 #pragma unroll 4
-    for (int s4 = 0; s4 < ns4; ++s4) {
-        const double a0 = Ca[s4 * 4], a1 = Ca[8 * LDT + s4 * 4];
+        for (int s4 = 0; s4 < ns4; ++s4) {
+            const double a0 = Ca[s4 * 4], a1 = Ca[8 * LDT + s4 * 4];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            if (4 * s4 <= 8 * c + 7 && 8 * c < wk) {          // W is lower triangular
-                const double b = Wb[c * 8 * LDT + s4 * 4];
-                dmma884(acc[0][c][0], acc[0][c][1], a0, b);
-                dmma884(acc[1][c][0], acc[1][c][1], a1, b);
+            for (int c = 0; c < 8; ++c) {
+                if (4 * s4 <= 8 * c + 7 && 8 * c < wk) {          // W is lower triangular
+                    const double b = Wb[c * 8 * LDT + s4 * 4];
+                    dmma884(acc[0][c][0], acc[0][c][1], a0, b);
+                    dmma884(acc[1][c][0], acc[1][c][1], a1, b);
+                }
             }
         }
     }
+    __syncwarp();
+    // L tile: to global and back into shared memory (operand of the look-ahead SYRK)
 #pragma unroll
     for (int f = 0; f < 2; ++f)
 #pragma unroll
@@ -265,7 +347,51 @@ chol_panel_kernel(const BlockDesc* __restrict__ blocks, const int2* __restrict__
             if (rl < prow && cc < wk)
                 *reinterpret_cast<double2*>(Lb + (size_t)(r0 + rl) * ld + pc0 + cc) =
                     make_double2(acc[f][c][0], acc[f][c][1]);
+            Cw[(8 * f + g) * LDT + cc] = acc[f][c][0];
+            Cw[(8 * f + g) * LDT + cc + 1] = acc[f][c][1];
+            acc[f][c][0] = acc[f][c][1] = 0.0;
         }
+    __syncthreads();
+    // ---- look-ahead: T_ii -= L_ik L_ik^T for the 64-row tile this warp belongs to
+    const int grp = warp >> 2, wl = warp & 3;
+    const int trow0 = r0 + 64 * grp;              // first global row of the 64-row tile
+    if (trow0 >= bd.mp || wk < NB) return;        // z rows / last (narrow) panel: no diagonal tile below
+    const int tw = min(NB, bd.mp - trow0);        // tile extent
+    if (16 * wl >= tw) return;
+    {
+        const double* A = Ct + (64 * grp + 16 * wl + g) * LDT + t;
+        const double* B = Ct + (64 * grp + g) * LDT + t;
+#pragma unroll 4
+        for (int s4 = 0; s4 < NB / 4; ++s4) {
+            const double a0 = A[s4 * 4], a1 = A[8 * LDT + s4 * 4];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                if (c <= 2 * wl + 1) {                             // lower triangle of the tile only
+                    const double b = B[c * 8 * LDT + s4 * 4];
+                    dmma884(acc[0][c][0], acc[0][c][1], a0, b);
+                    dmma884(acc[1][c][0], acc[1][c][1], a1, b);
+                }
+            }
+        }
+        const double* src = (k == 0 ? sigma : Lbuf) + bd.moff;    // first touch reads Sigma (+ ridge)
+#pragma unroll
+        for (int f = 0; f < 2; ++f)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int rl = 16 * wl + 8 * f + g, cc = 8 * c + 2 * t;   // within the tile
+                if (c <= 2 * wl + 1 && rl < tw && cc <= rl) {
+                    const size_t o = (size_t)(trow0 + rl) * ld + trow0 + cc;
+                    double2 v = *reinterpret_cast<const double2*>(src + o);
+                    if (k == 0) {
+                        if (cc == rl && trow0 + rl < bd.ms) v.x += ridge;
+                        if (cc + 1 == rl && trow0 + rl < bd.ms) v.y += ridge;   // odd rows: the diagonal is the pair's second element
+                    }
+                    v.x -= acc[f][c][0];
+                    v.y -= acc[f][c][1];
+                    *reinterpret_cast<double2*>(Lb + o) = v;
+                }
+            }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -325,7 +451,7 @@ backsolve_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict
 }
 
 cudaError_t chol_configure() {
-    cudaError_t e = cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CHOL);
+    cudaError_t e = cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DIAG);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CHOL);
 }
@@ -333,13 +459,13 @@ cudaError_t chol_configure() {
 cudaError_t launch_chol_diag(const BlockDesc* blocks, const int32_t* items, int32_t n_items, int32_t k,
                              const double* sigma, double* L, double ridge, int32_t* status, cudaStream_t st) {
     if (n_items == 0) return cudaSuccess;
-    chol_diag_kernel<<<n_items, CHOL_THREADS, SMEM_CHOL, st>>>(blocks, items, k, sigma, L, ridge, status);
+    chol_diag_kernel<<<n_items, CHOL_THREADS, SMEM_DIAG, st>>>(blocks, items, k, sigma, L, ridge, status);
     return cudaGetLastError();
 }
 cudaError_t launch_chol_panel(const BlockDesc* blocks, const int2* items, int32_t n_items, int32_t k,
-                              const double* sigma, double* L, cudaStream_t st) {
+                              const double* sigma, double* L, double ridge, cudaStream_t st) {
     if (n_items == 0) return cudaSuccess;
-    chol_panel_kernel<<<n_items, CHOL_THREADS, SMEM_CHOL, st>>>(blocks, items, k, sigma, L);
+    chol_panel_kernel<<<n_items, CHOL_THREADS, SMEM_CHOL, st>>>(blocks, items, k, sigma, L, ridge);
     return cudaGetLastError();
 }
 cudaError_t launch_backsolve(const BlockDesc* blocks, const int32_t* order, int32_t n_blocks, const double* L,

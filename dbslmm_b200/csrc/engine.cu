@@ -313,12 +313,16 @@ int dbslmm_b200_create(int device, dbslmm_b200_handle** out) {
     h->device = device;
     h->n_sm = prop.multiProcessorCount;
     bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);     // numerically lower = higher priority
     for (int c = 0; c < kNumClasses && ok; ++c) {
-        ok = cudaStreamCreateWithFlags(&h->cls_stream[c], cudaStreamNonBlocking) == cudaSuccess &&
-             cudaEventCreateWithFlags(&h->ev_join[c], cudaEventDisableTiming) == cudaSuccess;
+        // the classes with the most panel steps have the longest dependency chains: schedule them first
+        const int prio = std::max(prio_hi, prio_lo - c);
+        ok = cudaStreamCreateWithPriority(&h->cls_stream[c], cudaStreamNonBlocking, prio) == cudaSuccess &&
+             cudaEventCreate(&h->ev_join[c]) == cudaSuccess;
     }
     for (int i = 0; i < 8 && ok; ++i) ok = cudaEventCreate(&h->ev[i]) == cudaSuccess;
-    ok = ok && cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreate(&h->ev_fork) == cudaSuccess;
     ok = ok && chol_configure() == cudaSuccess;
     if (!ok) { dbslmm_b200_destroy(h); return DBSLMM_B200_ERR_CUDA; }
     *out = h;
@@ -555,7 +559,7 @@ int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
                     CU_TRY(h, launch_chol_diag(d_blocks, d_diag + s.diag_off, s.n_diag, (int32_t)k,
                                                (const double*)h->sigma.p, (double*)h->lbuf.p, ridge, d_status, cs));
                     CU_TRY(h, launch_chol_panel(d_blocks, d_panel + s.panel_off, s.n_panel, (int32_t)k,
-                                                (const double*)h->sigma.p, (double*)h->lbuf.p, cs));
+                                                (const double*)h->sigma.p, (double*)h->lbuf.p, ridge, cs));
                     n_launch += 2;
                     n_chol_launch += 2;
                 }
@@ -615,6 +619,10 @@ int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
         cudaEventElapsedTime(&t->total_ms, h->ev[0], h->ev[5]);
         if (!pcg && a->n_folds == 1) { float ms = 0.f; cudaEventElapsedTime(&ms, h->ev[3], h->ev[6]); chol_ms_total = ms; }
         t->chol_ms = chol_ms_total;
+        for (int c = 0; c < kNumClasses; ++c) {
+            t->class_ms[c] = 0.f;
+            if (!pcg && !P.steps[c].empty()) cudaEventElapsedTime(&t->class_ms[c], h->ev_fork, h->ev_join[c]);
+        }
         t->n_launches = n_launch;
         t->n_chol_launches = n_chol_launch;
         t->gram_ops = P.gram_ops;

@@ -48,7 +48,7 @@ struct CholStep {               // work lists of one panel step (device pointers
 cudaError_t launch_chol_diag(const BlockDesc* blocks, const int32_t* items, int32_t n_items, int32_t k,
                              const double* sigma, double* L, double ridge, int32_t* status, cudaStream_t st);
 cudaError_t launch_chol_panel(const BlockDesc* blocks, const int2* items, int32_t n_items, int32_t k,
-                              const double* sigma, double* L, cudaStream_t st);
+                              const double* sigma, double* L, double ridge, cudaStream_t st);
 cudaError_t launch_backsolve(const BlockDesc* blocks, const int32_t* order, int32_t n_blocks, const double* L,
                              double inv_sqrt_n, double* beta_s, double* beta_l, int32_t max_mp, cudaStream_t st);
 cudaError_t chol_configure();

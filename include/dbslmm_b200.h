@@ -67,6 +67,7 @@ typedef struct dbslmm_b200_timing {
     double solve_flops;  /* algorithmic FP64 flop (m^3/3 + 2 m^2 per block and fold)                       */
     double decode_bytes; /* algorithmic bytes read + written by the decoder                                */
     double chol_ms;      /* factorisation kernels only (subset of solve_ms), summed over folds             */
+    float class_ms[4];   /* last fold: fork -> end of each Cholesky size class (streams run concurrently)  */
 } dbslmm_b200_timing;
 
 typedef struct dbslmm_b200_fit_args {

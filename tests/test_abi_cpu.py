@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 def test_fit_args_struct_layout_matches_header():
     # 17 fields, natural alignment on LP64: the ctypes mirror must be 128 bytes like the C struct
     assert C.sizeof(_abi.FitArgs) == 128
-    assert C.sizeof(_abi.Timing) == 64
+    assert C.sizeof(_abi.Timing) == 80
 
 
 def test_no_cpu_fallback():
