@@ -1,0 +1,357 @@
+// dbslmm_main.cpp -- the `dbslmm` command line on top of the B200 C ABI.
+//
+// Drop-in for the reference's CLI (scr/main_dbslmm.cpp:31-48, DBSLMM::Assign scr/dbslmm.cpp:67-172,
+// DBSLMM::BatchRun :174-398): same options and aliases, same input formats, same `<eff>.txt`
+// and `<eff>.badsnps` outputs.  The block fit itself (DBSLMMFIT::est) runs on the GPU(s)
+// through include/dbslmm_b200.h; there is no CPU path.
+//
+// Differences on purpose:
+//   * -test_indicator_file / -dat_str are accepted and ignored: the fork's asymptotic-variance
+//     side channel (variance.txt) is outside this path; nothing else depends on them.
+//   * hidden additions: --solver chol|pcg, --gpus N, --tau T, --h2-folds a,b,c (one Gram, several
+//     ridge folds, outputs <eff>_f<k>.txt), --dump-beta-bin FILE (FP64 betas; the text output
+//     only has 6 significant digits), --verbose.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+#include <string>
+#include <sys/time.h>
+#include <thread>
+#include <vector>
+
+#include "dbslmm_b200.h"
+#include "ingest.hpp"
+
+using namespace std;
+using namespace dbslmm_host;
+
+struct Param {                                   // PARAM, scr/dbslmm.hpp:29-45 (+ explicit defaults)
+    string s, l, r, b, eff, test_indicator_file, dat_str;
+    int n = 0, nsnp = 0, t = 1;
+    double mafMax = 1.0, h = 0.0;
+    // additions
+    string solver = "chol", dump_bin;
+    int gpus = 1;
+    double tau = 0.8;
+    vector<double> folds;
+    bool verbose = false;
+};
+
+static void print_header() {
+    cout << endl;
+    cout << "*************************************************************" << endl;
+    cout << "  Deterministic Bayesian Sparse Linear Mixed Model (DBSLMM)  " << endl;
+    cout << "  B200-native block fit (dbslmm_b200), CLI-compatible with   " << endl;
+    cout << "  DBSLMM 0.3                                                 " << endl;
+    cout << "  GNU General Public License                                 " << endl;
+    cout << "  For Help, Type ./dbslmm -h                                 " << endl;
+    cout << "*************************************************************" << endl;
+    cout << endl;
+}
+
+static void print_help() {
+    cout << " FILE I/O RELATED OPTIONS" << endl;
+    cout << " -s        [filename]  " << " specify input the summary data for the small effect SNPs." << endl;
+    cout << " -l        [filename]  " << " specify input the summary data for the large effect SNPs." << endl;
+    cout << " -r        [filename]  " << " specify input the bfile of reference data." << endl;
+    cout << " -n        [num]       " << " specify input the sample size of the summary data." << endl;
+    cout << " -mafMax   [num]       " << " specify input the maximium of the difference between reference panel and summary data." << endl;
+    cout << " -nsnp     [num]  " << " specify input the number of snp." << endl;
+    cout << " -b        [num]       " << " specify input the block information." << endl;
+    cout << " -h        [num]       " << " specify input the heritability." << endl;
+    cout << " -t        [filename]  " << " specify input thread." << endl;
+    cout << " -eff      [filename]  " << " specify output the estimate effect SNPs." << endl;
+}
+
+static bool opt(const char* a, const char* lng, const char* sht) { return strcmp(a, lng) == 0 || strcmp(a, sht) == 0; }
+
+static void assign(int argc, char** argv, Param& p) {       // scr/dbslmm.cpp:67-172
+    for (int i = 0; i < argc; i++) {
+        auto val = [&](string& dst) -> bool {
+            if (argv[i + 1] == NULL || argv[i + 1][0] == '-') return false;   // :74 values starting with '-' are skipped
+            ++i;
+            dst.assign(argv[i]);
+            return true;
+        };
+        string v;
+        if (opt(argv[i], "--smallEff", "-s")) { if (val(v)) p.s = v; }
+        else if (opt(argv[i], "--largeEff", "-l")) { if (val(v)) p.l = v; }
+        else if (opt(argv[i], "--reference", "-r")) { if (val(v)) p.r = v; }
+        else if (opt(argv[i], "--N", "-n")) { if (val(v)) p.n = atoi(v.c_str()); }
+        else if (opt(argv[i], "--mafMax", "-mafMax")) { if (val(v)) p.mafMax = atof(v.c_str()); }
+        else if (opt(argv[i], "--numSNP", "-nsnp")) { if (val(v)) p.nsnp = atoi(v.c_str()); }
+        else if (opt(argv[i], "--block", "-b")) { if (val(v)) p.b = v; }
+        else if (opt(argv[i], "--Heritability", "-h")) { if (val(v)) p.h = atof(v.c_str()); }
+        else if (opt(argv[i], "--Thread", "-t")) { if (val(v)) p.t = atoi(v.c_str()); }
+        else if (opt(argv[i], "--EFF", "-eff")) { if (val(v)) p.eff = v; }
+        else if (opt(argv[i], "--test_indicator_file", "-test_indicator_file")) { if (val(v)) p.test_indicator_file = v; }
+        else if (opt(argv[i], "--dat_str", "-dat_str")) { if (val(v)) p.dat_str = v; }
+        else if (opt(argv[i], "--solver", "-solver")) { if (val(v)) p.solver = v; }
+        else if (opt(argv[i], "--gpus", "-gpus")) { if (val(v)) p.gpus = atoi(v.c_str()); }
+        else if (opt(argv[i], "--tau", "-tau")) { if (val(v)) p.tau = atof(v.c_str()); }
+        else if (opt(argv[i], "--dump-beta-bin", "-dump-beta-bin")) { if (val(v)) p.dump_bin = v; }
+        else if (opt(argv[i], "--h2-folds", "-h2-folds")) {
+            if (val(v)) { stringstream ss(v); string e; while (getline(ss, e, ',')) p.folds.push_back(atof(e.c_str())); }
+        }
+        else if (opt(argv[i], "--verbose", "-verbose")) p.verbose = true;
+    }
+}
+
+static double walltime() { struct timeval t; gettimeofday(&t, NULL); return (double)t.tv_sec + (double)t.tv_usec * 1e-6; }
+
+struct Shard {                                   // what one GPU fits
+    vector<int> blocks;                          // global block ids, ascending
+    vector<int32_t> s_off, s_pos, l_off, l_pos;
+    vector<double> s_z, l_z, beta_s, beta_l;
+    vector<int32_t> status;
+    vector<uint8_t> bed;                         // compact .bed (only when gpus > 1)
+    int64_t n_rows = 0;
+    int rc = 0;
+    string err;
+    dbslmm_b200_timing timing{};
+};
+
+int main(int argc, char* argv[]) {
+    if (argc <= 1) { print_header(); return EXIT_SUCCESS; }                                   // main_dbslmm.cpp:37-40
+    if (argc == 2 && argv[1][0] == '-' && argv[1][1] == 'h') { print_help(); return EXIT_SUCCESS; }   // :41-44
+    Param cPar;
+    assign(argc, argv, cPar);
+
+    cout << "Options: " << endl;                                                              // dbslmm.cpp:181-192
+    cout << "-s:      " << cPar.s << endl;
+    cout << "-l:      " << cPar.l << endl;
+    cout << "-r:      " << cPar.r << endl;
+    cout << "-nsnp:   " << cPar.nsnp << endl;
+    cout << "-n:      " << cPar.n << endl;
+    cout << "-mafMax: " << cPar.mafMax << endl;
+    cout << "-b:      " << cPar.b << endl;
+    cout << "-h:      " << cPar.h << endl;
+    cout << "-t:      " << cPar.t << endl;
+    cout << "-eff:    " << cPar.eff << endl;
+    cout << "-test_indicator_file:  " << cPar.test_indicator_file << endl;
+
+    const string ref_fam = cPar.r + ".fam";
+    ifstream seff(cPar.s.c_str()), leff(cPar.l.c_str()), reff(ref_fam.c_str()), beff(cPar.b.c_str());
+    if (cPar.s.size() == 0) { cerr << "ERROR: -s is no parameter!" << endl; exit(1); }        // :196-227
+    if (!beff) { cerr << "ERROR: " << cPar.b << " dose not exist!" << endl; exit(1); }
+    if (!seff) { cerr << "ERROR: " << cPar.s << " dose not exist!" << endl; exit(1); }
+    if (!reff) { cerr << "ERROR: " << cPar.r << " dose not exist!" << endl; exit(1); }
+    if (cPar.b.size() == 0) { cerr << "ERROR: -b is no parameter!" << endl; exit(1); }
+    if (cPar.r.size() == 0) { cerr << "ERROR: " << cPar.r << " dose not exist!" << endl; exit(1); }
+    if (cPar.h > 1 || cPar.h < 0) { cerr << "ERROR: -h is not correct (0, 1)!" << endl; exit(1); }
+    if (cPar.t > 100 || cPar.t < 1) { cerr << "ERROR: -t is not correct (1, 100)!" << endl; exit(1); }
+    if (cPar.n <= 0 || cPar.nsnp <= 0) { cerr << "ERROR: -n and -nsnp must be positive!" << endl; exit(1); }
+    const int solver = (cPar.solver == "pcg") ? DBSLMM_B200_SOLVER_PCG : DBSLMM_B200_SOLVER_CHOLESKY;
+    if (!cPar.test_indicator_file.empty() || !cPar.dat_str.empty())
+        cout << "[NOTE] -test_indicator_file/-dat_str: the asymptotic-variance side channel is not part of this build; no variance.txt is written." << endl;
+
+    const int n_dev = dbslmm_b200_device_count();
+    if (n_dev <= 0) { cerr << "ERROR: no CUDA device: dbslmm_b200 has no CPU fallback." << endl; exit(2); }
+    const int n_gpus = std::max(1, std::min(cPar.gpus, n_dev));
+
+    cout << "Reading reference PLINK FAM file from [" << cPar.r << ".fam]" << endl;
+    const int n_ref = get_row(ref_fam);                                                       // :232
+    cout << n_ref << " individuals to be included from reference FAM file." << endl;
+    cout << "Reading reference PLINK BIM file from [" << cPar.r << ".bim]" << endl;
+    BimMap ref_bim;
+    const bool constr = !(fabs(cPar.mafMax - 1.0) < 1e-10);                                   // :238-241
+    const int64_t n_snp_ref = read_bim(cPar.r + ".bim", ref_bim);
+    cout << ref_bim.size() << " SNPs to be included from reference BIM file." << endl;
+
+    vector<uint8_t> bed;
+    if (!read_bed(cPar.r + ".bed", n_snp_ref, n_ref, bed)) { cerr << "ERROR: cannot read SNP-major " << cPar.r << ".bed" << endl; exit(1); }
+    vector<dbslmm_b200_handle*> hs(n_gpus, nullptr);
+    for (int g = 0; g < n_gpus; ++g)
+        if (dbslmm_b200_create(g, &hs[g]) != DBSLMM_B200_OK) { cerr << "ERROR: cannot initialise GPU " << g << endl; exit(2); }
+    // GPU 0 holds the whole panel: its statistics kernel IS the MAF pre-pass (dtpr.cpp:93-102)
+    if (dbslmm_b200_load_bed(hs[0], bed.data(), n_snp_ref, n_ref) != DBSLMM_B200_OK) {
+        cerr << "ERROR: load_bed: " << dbslmm_b200_last_error(hs[0]) << endl; exit(2);
+    }
+    vector<double> ref_maf;
+    if (constr) {
+        cout << "Calculating MAF of reference panel ..." << endl;
+        ref_maf.resize((size_t)n_snp_ref);
+        dbslmm_b200_snp_stats(hs[0], ref_maf.data(), nullptr);
+    } else {
+        cout << "[WARNING] Do not consider the difference between reference panel and summary data ..." << endl;
+    }
+
+    vector<Block> block_dat;
+    read_block(cPar.b, block_dat);                                                            // :248
+    const int num_block = (int)block_dat.size();
+
+    cout << "Reading summary data of small effect SNPs from [" << cPar.s << "]" << endl;
+    Summ summ_s;
+    read_summ(cPar.s, summ_s);
+    Info inter_s, info_s;
+    vector<char> matched_s;
+    int dis = 0, mafc = 0;
+    match_ref(summ_s, ref_bim, constr ? ref_maf.data() : nullptr, cPar.mafMax, inter_s, matched_s, dis, mafc);
+    cout << "Number of allele discrepency: " << dis << endl;
+    cout << "Number of maf discrepency:    " << mafc << endl;
+    cout << "After filtering, " << inter_s.size() << " small effect SNPs are selected." << endl;
+    add_block(inter_s, block_dat, info_s);
+    const string badsnps_str = cPar.eff + ".badsnps";
+    ofstream badsnpsFout(badsnps_str.c_str());
+    for (size_t i = 0; i < summ_s.size(); ++i)
+        if (!matched_s[i]) badsnpsFout << summ_s.snp[i] << " " << 0 << endl;                 // :282-285
+
+    Info inter_l, info_l;
+    if (leff) {                                                                               // :292-317
+        cout << "Reading summary data of large effect SNPs from [" << cPar.l << "]" << endl;
+        Summ summ_l;
+        read_summ(cPar.l, summ_l);
+        vector<char> matched_l;
+        match_ref(summ_l, ref_bim, constr ? ref_maf.data() : nullptr, cPar.mafMax, inter_l, matched_l, dis, mafc);
+        cout << "Number of allele discrepency: " << dis << endl;
+        cout << "Number of maf discrepency:    " << mafc << endl;
+        if (inter_l.size() != 0) {
+            add_block(inter_l, block_dat, info_l);
+            cout << "After filtering, " << inter_l.size() << " large effect SNPs are selected." << endl;
+        } else {
+            cout << "After filtering, no large effect SNP is selected." << endl;
+        }
+        for (size_t i = 0; i < summ_l.size(); ++i)
+            if (!matched_l[i]) badsnpsFout << summ_l.snp[i] << " " << 1 << endl;
+    }
+    badsnpsFout.close();
+    const bool with_large = inter_l.size() != 0;                                              // :325 / :366
+
+    // ---- block plan: CSR offsets, shard over GPUs
+    const vector<int32_t> s_off = block_offsets(info_s, num_block);
+    const vector<int32_t> l_off = with_large ? block_offsets(info_l, num_block) : vector<int32_t>();
+    vector<int32_t> m_s(num_block), m_l(num_block, 0), owner(num_block, 0);
+    for (int b = 0; b < num_block; ++b) {
+        m_s[b] = s_off[b + 1] - s_off[b];
+        if (with_large) m_l[b] = l_off[b + 1] - l_off[b];
+    }
+    if (n_gpus > 1) dbslmm_b200_plan_shards(num_block, m_s.data(), m_l.data(), n_ref, n_gpus, owner.data(), nullptr);
+
+    vector<double> folds = cPar.folds;
+    if (folds.empty()) folds.push_back(1.0);
+    vector<double> sigma_s(folds.size());
+    for (size_t f = 0; f < folds.size(); ++f) sigma_s[f] = folds[f] * cPar.h / (double)cPar.nsnp;   // :332 (x fold)
+    const int n_folds = (int)folds.size();
+
+    vector<Shard> shards(n_gpus);
+    for (int g = 0; g < n_gpus; ++g) {
+        Shard& sh = shards[g];
+        sh.s_off.push_back(0);
+        if (with_large) sh.l_off.push_back(0);
+        vector<int64_t> remap;
+        if (n_gpus > 1) remap.assign((size_t)n_snp_ref, -1);
+        const size_t pitch = (size_t)((n_ref + 3) / 4);
+        auto map_row = [&](int32_t p) -> int32_t {
+            if (n_gpus == 1) return p;
+            if (remap[p] < 0) {
+                remap[p] = sh.n_rows++;
+                sh.bed.insert(sh.bed.end(), bed.begin() + (size_t)p * pitch, bed.begin() + (size_t)(p + 1) * pitch);
+            }
+            return (int32_t)remap[p];
+        };
+        for (int b = 0; b < num_block; ++b) {
+            if (owner[b] != g) continue;
+            sh.blocks.push_back(b);
+            for (int j = s_off[b]; j < s_off[b + 1]; ++j) { sh.s_pos.push_back(map_row(info_s.pos[j])); sh.s_z.push_back(info_s.z[j]); }
+            sh.s_off.push_back((int32_t)sh.s_pos.size());
+            if (with_large) {
+                for (int j = l_off[b]; j < l_off[b + 1]; ++j) { sh.l_pos.push_back(map_row(info_l.pos[j])); sh.l_z.push_back(info_l.z[j]); }
+                sh.l_off.push_back((int32_t)sh.l_pos.size());
+            }
+        }
+        sh.beta_s.assign(sh.s_pos.size() * n_folds + 1, 0.0);
+        sh.beta_l.assign(sh.l_pos.size() * n_folds + 1, 0.0);
+        sh.status.assign(sh.blocks.size() + 1, 0);
+    }
+
+    // ---- fit (the reference's "Fitting time" window, dbslmm.cpp:331-350 / 372-388)
+    const double t_fitting = walltime();
+    cout << "Fitting model..." << endl;
+    auto run = [&](int g) {
+        Shard& sh = shards[g];
+        if (n_gpus > 1 && sh.n_rows > 0) {
+            sh.rc = dbslmm_b200_load_bed(hs[g], sh.bed.data(), sh.n_rows, n_ref);
+            if (sh.rc < 0) { sh.err = dbslmm_b200_last_error(hs[g]); return; }
+        } else if (n_gpus > 1) {
+            return;
+        }
+        dbslmm_b200_fit_args a{};
+        a.n_blocks = (int32_t)sh.blocks.size();
+        a.s_off = sh.s_off.data(); a.s_pos = sh.s_pos.data(); a.s_z = sh.s_z.data();
+        if (with_large) { a.l_off = sh.l_off.data(); a.l_pos = sh.l_pos.data(); a.l_z = sh.l_z.data(); }
+        a.n_folds = n_folds; a.sigma_s = sigma_s.data(); a.n_obs = cPar.n; a.tau = cPar.tau;
+        a.solver = solver; a.flags = 0;
+        a.beta_s_out = sh.beta_s.data(); a.beta_l_out = with_large ? sh.beta_l.data() : nullptr;
+        a.block_status_out = sh.status.data(); a.timing = &sh.timing;
+        sh.rc = dbslmm_b200_fit(hs[g], &a);
+        if (sh.rc < 0) sh.err = dbslmm_b200_last_error(hs[g]);
+    };
+    {
+        vector<thread> th;
+        for (int g = 1; g < n_gpus; ++g) th.emplace_back(run, g);
+        run(0);
+        for (auto& t : th) t.join();
+    }
+    for (int g = 0; g < n_gpus; ++g) {
+        if (shards[g].rc < 0) { cerr << "ERROR: GPU " << g << ": " << shards[g].err << endl; exit(2); }
+        if (shards[g].rc > 0) cerr << "ERROR: Matrix is Singular! (" << shards[g].rc << " block(s) on GPU " << g << ")" << endl;   // dbslmmfit.cpp:665
+    }
+    const double time_fitting = walltime() - t_fitting;
+    cout << "Fitting time: " << time_fitting << " seconds." << endl;
+    if (cPar.verbose)
+        for (int g = 0; g < n_gpus; ++g) {
+            const dbslmm_b200_timing& t = shards[g].timing;
+            cout << "[gpu " << g << "] blocks " << shards[g].blocks.size() << " h2d " << t.h2d_ms << " decode " << t.decode_ms << " gram "
+                 << t.gram_ms << " solve " << t.solve_ms << " d2h " << t.d2h_ms << " ms, " << t.n_launches << " launches" << endl;
+        }
+
+    // ---- gather to block-major global order
+    const size_t tot_s = info_s.size(), tot_l = info_l.size();
+    vector<double> beta_s(tot_s * n_folds), beta_l(tot_l * n_folds + 1);
+    for (int g = 0; g < n_gpus; ++g) {
+        const Shard& sh = shards[g];
+        const size_t ns = sh.s_pos.size(), nl = sh.l_pos.size();
+        for (size_t i = 0; i < sh.blocks.size(); ++i) {
+            const int b = sh.blocks[i];
+            for (int f = 0; f < n_folds; ++f) {
+                for (int j = 0; j < m_s[b]; ++j) beta_s[f * tot_s + s_off[b] + j] = sh.beta_s[f * ns + sh.s_off[i] + j];
+                if (with_large)
+                    for (int j = 0; j < m_l[b]; ++j) beta_l[f * tot_l + l_off[b] + j] = sh.beta_l[f * nl + sh.l_off[i] + j];
+            }
+        }
+    }
+
+    // ---- output effect (dbslmm.cpp:353-364 / 391-395): large first (flag 1), then small (flag 0)
+    for (int f = 0; f < n_folds; ++f) {
+        string eff_str = cPar.eff + ".txt";
+        if (n_folds > 1) { ostringstream o; o << cPar.eff << "_f" << f << ".txt"; eff_str = o.str(); }
+        ofstream effFout(eff_str.c_str());
+        for (size_t i = 0; i < tot_l; ++i) {
+            const double b = beta_l[f * tot_l + i];
+            const double noscl = b / sqrt(2 * info_l.maf[i] * (1 - info_l.maf[i]));
+            if (isinf(noscl) == false) effFout << info_l.snp[i] << " " << info_l.a1[i] << " " << b << " " << noscl << " " << 1 << endl;
+        }
+        for (size_t i = 0; i < tot_s; ++i) {
+            const double b = beta_s[f * tot_s + i];
+            const double noscl = b / sqrt(2 * info_s.maf[i] * (1 - info_s.maf[i]));
+            if (info_s.snp[i].size() != 0 && isinf(noscl) == false)
+                effFout << info_s.snp[i] << " " << info_s.a1[i] << " " << b << " " << noscl << " " << 0 << endl;
+        }
+        effFout.close();
+    }
+    if (!cPar.dump_bin.empty()) {
+        // int64 n_folds, tot_l, tot_s, then FP64 beta_l[n_folds][tot_l], beta_s[n_folds][tot_s]
+        ofstream o(cPar.dump_bin.c_str(), ios::binary);
+        const int64_t hdr[3] = {n_folds, (int64_t)tot_l, (int64_t)tot_s};
+        o.write((const char*)hdr, sizeof(hdr));
+        o.write((const char*)beta_l.data(), sizeof(double) * tot_l * n_folds);
+        o.write((const char*)beta_s.data(), sizeof(double) * tot_s * n_folds);
+    }
+    for (auto* h : hs) dbslmm_b200_destroy(h);
+    return EXIT_SUCCESS;
+}

@@ -1,0 +1,88 @@
+"""The drop-in `dbslmm` command line: option handling on CPU, file-level parity against the
+UNMODIFIED reference CLI's golden output on the GPU."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "build", "dbslmm")
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _write_fixture(tmp_path):
+    d = np.load(os.path.join(GOLD, "c1_testdat.npz"))
+    (tmp_path / "ref.bim").write_text(str(d["bim_txt"]))
+    (tmp_path / "ref.fam").write_text("f i 0 0 0 -9\n" * int(d["fam_lines"]))
+    with open(tmp_path / "ref.bed", "wb") as f:
+        f.write(bytes([0x6C, 0x1B, 0x01]) + d["bed"].tobytes())
+    (tmp_path / "summ.txt").write_text(str(d["summary_txt"]))
+    (tmp_path / "l.txt").write_text(str(d["l_txt"]))
+    (tmp_path / "s.txt").write_text(str(d["s_txt"]))
+    (tmp_path / "blocks.bed").write_text(str(d["block_txt"]))
+    return d
+
+
+@pytest.mark.skipif(not os.path.exists(CLI), reason="CLI not built")
+def test_banner_help_and_checks(tmp_path):
+    out = subprocess.run([CLI], capture_output=True, text=True)
+    assert out.returncode == 0 and "Deterministic Bayesian Sparse Linear Mixed Model" in out.stdout
+    out = subprocess.run([CLI, "-h"], capture_output=True, text=True)
+    assert out.returncode == 0 and "-mafMax" in out.stdout and "-eff" in out.stdout
+    _write_fixture(tmp_path)
+    base = ["-r", str(tmp_path / "ref"), "-b", str(tmp_path / "blocks.bed"), "-n", "2400", "-nsnp", "996", "-eff", str(tmp_path / "o")]
+    r = subprocess.run([CLI, "-s", str(tmp_path / "nope.txt"), "-h", "0.5", "-t", "1"] + base, capture_output=True, text=True)
+    assert r.returncode == 1 and "dose not exist" in r.stderr
+    r = subprocess.run([CLI, "-s", str(tmp_path / "summ.txt"), "-h", "1.5", "-t", "1"] + base, capture_output=True, text=True)
+    assert r.returncode == 1 and "-h is not correct" in r.stderr
+    r = subprocess.run([CLI, "-s", str(tmp_path / "summ.txt"), "-h", "0.5", "-t", "101"] + base, capture_output=True, text=True)
+    assert r.returncode == 1 and "-t is not correct" in r.stderr
+
+
+def _parse(txt):
+    rows = [ln.split(" ") for ln in txt.strip().split("\n")]
+    return [(r[0], r[1], float(r[2]), float(r[3]), int(r[4])) for r in rows]
+
+
+@pytest.mark.gpu
+def test_cli_matches_reference_cli_output(tmp_path):
+    d = _write_fixture(tmp_path)
+    cmd = [CLI, "-s", str(tmp_path / "s.txt"), "-l", str(tmp_path / "l.txt"), "-r", str(tmp_path / "ref"), "-n", "2400",
+           "-nsnp", "996", "-mafMax", "0.2", "-b", str(tmp_path / "blocks.bed"), "-h", "0.5", "-t", "1",
+           "-eff", str(tmp_path / "out"), "--dump-beta-bin", str(tmp_path / "beta.bin")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "Fitting time:" in r.stdout
+    got = _parse((tmp_path / "out.txt").read_text())
+    ref = _parse(str(d["cli_dbslmm_txt"]))
+    assert [(g[0], g[1], g[4]) for g in got] == [(x[0], x[1], x[4]) for x in ref]       # same SNPs, alleles, flags, order
+    gb, rb = np.array([g[2] for g in got]), np.array([x[2] for x in ref])
+    gn, rn = np.array([g[3] for g in got]), np.array([x[3] for x in ref])
+    # 6 significant digits in the text format; the reference's own PCG truncation is ~3e-8
+    assert np.abs(gb - rb).max() / np.abs(rb).max() < 5e-6 and np.abs(gn - rn).max() / np.abs(rn).max() < 5e-6
+    assert (tmp_path / "out.badsnps").read_text() == str(d["cli_dbslmm_badsnps"])
+    raw = (tmp_path / "beta.bin").read_bytes()
+    nf, nl, ns = struct.unpack("qqq", raw[:24])
+    beta = np.frombuffer(raw[24:], dtype=np.float64)
+    assert (nf, nl, ns) == (1, d["beta_l"].size, d["beta_s"].size)
+    assert np.abs(beta[:nl] - d["beta_l"]).max() / np.abs(d["beta_l"]).max() < 2e-7
+    assert np.abs(beta[nl:] - d["beta_s"]).max() / np.abs(d["beta_s"]).max() < 2e-7
+
+
+@pytest.mark.gpu
+def test_cli_lmm_mode_and_folds(tmp_path):
+    d = _write_fixture(tmp_path)
+    cmd = [CLI, "-s", str(tmp_path / "summ.txt"), "-r", str(tmp_path / "ref"), "-n", "2400", "-nsnp", "996", "-mafMax", "0.2",
+           "-b", str(tmp_path / "blocks.bed"), "-h", "0.5", "-t", "1", "-eff", str(tmp_path / "lmm"),
+           "--dump-beta-bin", str(tmp_path / "b.bin"), "--h2-folds", "0.8,1.0,1.2"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    raw = (tmp_path / "b.bin").read_bytes()
+    nf, nl, ns = struct.unpack("qqq", raw[:24])
+    assert (nf, nl, ns) == (3, 0, 716)
+    beta = np.frombuffer(raw[24:], dtype=np.float64).reshape(3, 716)
+    assert np.abs(beta[1] - d["lmm_beta"]).max() / np.abs(d["lmm_beta"]).max() < 2e-8
+    for f in range(3):
+        assert len((tmp_path / f"lmm_f{f}.txt").read_text().strip().split("\n")) == 716
