@@ -43,12 +43,14 @@ static constexpr int SMEM_CHOL = (SMEM_PIPE > SMEM_EPI ? SMEM_PIPE : SMEM_EPI);
 // acc (16 rows x 64 cols per warp) += P[r0.., 0:K] * Q[q0.., 0:K]^T, both row-major with K contiguous.
 // prow/qrow = number of valid rows (others are zero-filled).  All 256 threads must call.
 __device__ __forceinline__ void gemm_nt_core(const double* __restrict__ Pg, const double* __restrict__ Qg, int ld,
-                                             int prow, int qrow, int Kdim, double* smem,
+                                             int prow, int qrow, int kbeg, int kend, double* smem,
                                              double (&acc)[2][8][2]) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
-    const int nchunk = Kdim / KC;
+    const int nchunk = (kend - kbeg) / KC;     // K range [kbeg, kend), both multiples of KC
     const bool active = (16 * warp < prow);
+    Pg += kbeg;
+    Qg += kbeg;
 
     auto load_stage = [&](int kc, int s) {
         double* Ps = smem + s * STAGE;
@@ -274,10 +276,12 @@ chol_diag_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict
 //   step, so no atomics), so the diagonal kernel never runs a GEMM.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(CHOL_THREADS, 2)
-chol_panel_kernel(const BlockDesc* __restrict__ blocks, const int2* __restrict__ items, int32_t k,
-                  const double* __restrict__ sigma, double* __restrict__ Lbuf, double ridge) {
+chol_panel_kernel(const BlockDesc* __restrict__ blocks, const int4* __restrict__ items, int32_t k,
+                  const double* __restrict__ sigma, double* __restrict__ Lbuf, double ridge,
+                  double* __restrict__ scratch, int32_t* __restrict__ counters, int32_t group_base) {
     extern __shared__ __align__(16) double smem[];
-    const int2 item = items[blockIdx.x];
+    __shared__ int s_last;
+    const int4 item = items[blockIdx.x];     // x = block, y = macro tile, z = slice | nslices << 8, w = split group id
     const BlockDesc bd = blocks[item.x];
     const int pc0 = k * NB;
     const int wk = min(NB, bd.mp - pc0);
@@ -294,7 +298,42 @@ chol_panel_kernel(const BlockDesc* __restrict__ blocks, const int2* __restrict__
     for (int f = 0; f < 2; ++f)
 #pragma unroll
         for (int c = 0; c < 8; ++c) acc[f][c][0] = acc[f][c][1] = 0.0;
-    gemm_nt_core(Lb + (size_t)r0 * ld, Lb + (size_t)pc0 * ld, ld, prow, wk, pc0, smem, acc);
+    const int slice = item.z & 0xFF, nsl = item.z >> 8;
+    {
+        // split-K: slice s of nsl owns 64-wide K blocks [k*s/nsl, k*(s+1)/nsl)
+        const int kb = (k * slice) / nsl * NB, ke = (k * (slice + 1)) / nsl * NB;
+        gemm_nt_core(Lb + (size_t)r0 * ld, Lb + (size_t)pc0 * ld, ld, prow, wk, kb, ke, smem, acc);
+    }
+    if (nsl > 1) {
+        // partial sums go to scratch; the CTA that arrives last adds them up IN SLICE ORDER (deterministic)
+        double* part = scratch + ((size_t)(item.w - group_base) * nsl) * (TM * NB);
+        double2* mine = reinterpret_cast<double2*>(part + (size_t)slice * (TM * NB)) + tid;
+#pragma unroll
+        for (int f = 0; f < 2; ++f)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) mine[(f * 8 + c) * CHOL_THREADS] = make_double2(acc[f][c][0], acc[f][c][1]);
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_last = (atomicAdd(&counters[item.w], 1) == nsl - 1);
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+#pragma unroll
+        for (int f = 0; f < 2; ++f)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[f][c][0] = acc[f][c][1] = 0.0;
+        for (int sl = 0; sl < nsl; ++sl) {
+            const double2* src2 = reinterpret_cast<const double2*>(part + (size_t)sl * (TM * NB)) + tid;
+#pragma unroll
+            for (int f = 0; f < 2; ++f)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const double2 v = __ldcg(src2 + (f * 8 + c) * CHOL_THREADS);
+                    acc[f][c][0] += v.x;
+                    acc[f][c][1] += v.y;
+                }
+        }
+    }
 
     double* Ct = smem;                            // [128][LDT] macro tile, 16 rows per warp
     double* Cw = Ct + warp * 16 * LDT;
@@ -397,7 +436,8 @@ chol_panel_kernel(const BlockDesc* __restrict__ blocks, const int2* __restrict__
 // ------------------------------------------------------------------------------------------
 // Back substitution L^T x = y (y = matrix row mp), beta = x / sqrt(N).  One CTA per block.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CHOL_THREADS)
+template <int NT>
+__global__ void __launch_bounds__(NT)
 backsolve_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict__ order,
                  const double* __restrict__ Lbuf, double inv_sqrt_n, double* __restrict__ beta_s,
                  double* __restrict__ beta_l) {
@@ -408,29 +448,48 @@ backsolve_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict
     const double* Lb = Lbuf + bd.moff;
     const double* y = Lb + (size_t)mp * ld;
     double* x = smem;               // [mp]
-    double* red = smem + mp;        // [4][64]
-    double* v = red + 4 * NB;       // [64]
+    constexpr int NRG = NT / 32;    // row groups
+    double* red = smem + mp;        // [NRG][64]
+    double* v = red + NRG * NB;     // [64]
     const int tid = threadIdx.x;
     const int K = (mp + NB - 1) / NB;
     for (int k = K - 1; k >= 0; --k) {
         const int pc0 = k * NB, wk = min(NB, mp - pc0), below = pc0 + wk;
         {
-            const int rg = tid >> 6, c = tid & 63;
-            double p0 = 0.0, p1 = 0.0;
-            if (c < wk) {
+            // 32 lanes x double2 cover the 64 panel columns of one row; 8 row groups, 4 rows in flight each
+            const int rg = tid >> 5, c2 = (tid & 31) * 2;
+            double2 p0 = make_double2(0.0, 0.0), p1 = p0, p2 = p0, p3 = p0;
+            if (c2 < wk) {
+                const double* col = Lb + pc0 + c2;
                 int i = below + rg;
-                for (; i + 4 < mp; i += 8) {
-                    p0 += Lb[(size_t)i * ld + pc0 + c] * x[i];
-                    p1 += Lb[(size_t)(i + 4) * ld + pc0 + c] * x[i + 4];
+                for (; i + 3 * NRG < mp; i += 4 * NRG) {
+                    const double2 a0 = *reinterpret_cast<const double2*>(col + (size_t)i * ld);
+                    const double2 a1 = *reinterpret_cast<const double2*>(col + (size_t)(i + NRG) * ld);
+                    const double2 a2 = *reinterpret_cast<const double2*>(col + (size_t)(i + 2 * NRG) * ld);
+                    const double2 a3 = *reinterpret_cast<const double2*>(col + (size_t)(i + 3 * NRG) * ld);
+                    const double x0 = x[i], x1 = x[i + NRG], x2 = x[i + 2 * NRG], x3 = x[i + 3 * NRG];
+                    p0.x += a0.x * x0; p0.y += a0.y * x0;
+                    p1.x += a1.x * x1; p1.y += a1.y * x1;
+                    p2.x += a2.x * x2; p2.y += a2.y * x2;
+                    p3.x += a3.x * x3; p3.y += a3.y * x3;
                 }
-                if (i < mp) p0 += Lb[(size_t)i * ld + pc0 + c] * x[i];
+                for (; i < mp; i += NRG) {
+                    const double2 a0 = *reinterpret_cast<const double2*>(col + (size_t)i * ld);
+                    p0.x += a0.x * x[i]; p0.y += a0.y * x[i];
+                }
             }
-            red[rg * NB + c] = p0 + p1;
+            red[rg * NB + c2] = (p0.x + p1.x) + (p2.x + p3.x);
+            red[rg * NB + c2 + 1] = (p0.y + p1.y) + (p2.y + p3.y);
         }
         __syncthreads();
-        if (tid < NB) v[tid] = (tid < wk) ? y[pc0 + tid] - (red[tid] + red[NB + tid] + red[2 * NB + tid] + red[3 * NB + tid]) : 0.0;
+        if (tid < NB) {
+            double sacc = 0.0;
+#pragma unroll
+            for (int q = 0; q < NRG; ++q) sacc += red[q * NB + tid];
+            v[tid] = (tid < wk) ? y[pc0 + tid] - sacc : 0.0;
+        }
         __syncthreads();
-        {
+        if (tid < 256) {
             const int c = tid >> 2, q = tid & 3;
             double p = 0.0;
             if (c < wk) {
@@ -443,7 +502,7 @@ backsolve_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict
         }
         __syncthreads();
     }
-    for (int j = tid; j < bd.m; j += CHOL_THREADS) {
+    for (int j = tid; j < bd.m; j += NT) {
         const double b = x[j] * inv_sqrt_n;
         if (j < bd.ms) beta_s[bd.out_s + j] = b;
         else beta_l[bd.out_l + (j - bd.ms)] = b;
@@ -462,21 +521,31 @@ cudaError_t launch_chol_diag(const BlockDesc* blocks, const int32_t* items, int3
     chol_diag_kernel<<<n_items, CHOL_THREADS, SMEM_DIAG, st>>>(blocks, items, k, sigma, L, ridge, status);
     return cudaGetLastError();
 }
-cudaError_t launch_chol_panel(const BlockDesc* blocks, const int2* items, int32_t n_items, int32_t k,
-                              const double* sigma, double* L, double ridge, cudaStream_t st) {
+cudaError_t launch_chol_panel(const BlockDesc* blocks, const int4* items, int32_t n_items, int32_t k,
+                              const double* sigma, double* L, double ridge, double* scratch, int32_t* counters,
+                              int32_t group_base, cudaStream_t st) {
     if (n_items == 0) return cudaSuccess;
-    chol_panel_kernel<<<n_items, CHOL_THREADS, SMEM_CHOL, st>>>(blocks, items, k, sigma, L, ridge);
+    chol_panel_kernel<<<n_items, CHOL_THREADS, SMEM_CHOL, st>>>(blocks, items, k, sigma, L, ridge, scratch, counters,
+                                                                 group_base);
     return cudaGetLastError();
 }
-cudaError_t launch_backsolve(const BlockDesc* blocks, const int32_t* order, int32_t n_blocks, const double* L,
-                             double inv_sqrt_n, double* beta_s, double* beta_l, int32_t max_mp, cudaStream_t st) {
+// `order` lists blocks by descending size; the first n_big (mp > 1024) get 1024-thread CTAs so that
+// one CTA keeps enough loads in flight to stream a multi-MB factor (a single 256-thread CTA is
+// latency-bound at ~16 GB/s and was the critical path of the whole solve).
+cudaError_t launch_backsolve(const BlockDesc* blocks, const int32_t* order, int32_t n_blocks, int32_t n_big,
+                             const double* L, double inv_sqrt_n, double* beta_s, double* beta_l, int32_t max_mp,
+                             cudaStream_t st) {
     if (n_blocks == 0) return cudaSuccess;
-    const size_t smem = (size_t)(max_mp + 5 * NB) * sizeof(double);
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(backsolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (n_big > 0) {
+        const size_t smem = (size_t)(max_mp + 33 * NB) * sizeof(double);
+        cudaError_t e = cudaFuncSetAttribute(backsolve_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
+        backsolve_kernel<1024><<<n_big, 1024, smem, st>>>(blocks, order, L, inv_sqrt_n, beta_s, beta_l);
     }
-    backsolve_kernel<<<n_blocks, CHOL_THREADS, smem, st>>>(blocks, order, L, inv_sqrt_n, beta_s, beta_l);
+    if (n_blocks > n_big) {
+        const size_t smem = (size_t)(1024 + 9 * NB) * sizeof(double);
+        backsolve_kernel<256><<<n_blocks - n_big, 256, smem, st>>>(blocks, order + n_big, L, inv_sqrt_n, beta_s, beta_l);
+    }
     return cudaGetLastError();
 }
 

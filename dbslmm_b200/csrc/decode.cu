@@ -103,13 +103,19 @@ snp_stats_kernel(const uint8_t* __restrict__ bed, int64_t n_snp, int32_t n_ref, 
     }
 }
 
-// four 2-bit codes of byte x -> allele-count bytes / mask bytes
-__device__ __forceinline__ void expand4(uint32_t x, uint32_t& g, uint32_t& m) {
+// four 2-bit codes of byte x -> allele-count bytes (MASK = false) or call-mask bytes (MASK = true)
+template <bool MASK>
+__device__ __forceinline__ uint32_t expand4(uint32_t x) {
     const uint32_t t = (x | (x << 6) | (x << 12) | (x << 18)) & 0x03030303u;
     const uint32_t b0 = t & 0x01010101u, b1 = (t >> 1) & 0x01010101u;
     const uint32_t nb0 = b0 ^ 0x01010101u;
-    g = (nb0 << 1) - (nb0 & b1);   // (1-b0)*(2-b1): 0->2, 2->1, 1/3->0
-    m = nb0 | b1;                  // 0 only for code 1 (missing)
+    if (MASK) return nb0 | b1;              // 0 only for code 1 (missing)
+    return (nb0 << 1) - (nb0 & b1);         // (1-b0)*(2-b1): 0->2, 2->1, 1/3->0
+}
+template <bool MASK>
+__device__ __forceinline__ uint4 expand16(uint32_t w) {
+    return make_uint4(expand4<MASK>(w & 0xFFu), expand4<MASK>((w >> 8) & 0xFFu), expand4<MASK>((w >> 16) & 0xFFu),
+                      expand4<MASK>(w >> 24));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -152,18 +158,16 @@ decode_rows_kernel(const uint8_t* __restrict__ bed, int32_t n_ref, int32_t pitch
         phase[cur] ^= 1;
         const uint32_t* w32 = reinterpret_cast<const uint32_t*>(bufs[cur]);
         uint4* out = reinterpret_cast<uint4*>(codes + (size_t)row * n_pad);
+        const int nfull = n_ref >> 4;             // words whose 16 samples are all real
         for (int i = lane; i < nout; i += 32) {
             uint4 o = make_uint4(0u, 0u, 0u, 0u);
             if (i < nwords) {
                 uint32_t w = row_word(w32, off[cur], i);
-                const uint32_t vb = valid_bits(n_ref, i);
-                w = (w & vb) | (0x55555555u & ~vb);    // samples past n_ref -> "missing": 0 in both planes
-                uint32_t g0, g1, g2, g3, m0, m1, m2, m3;
-                expand4(w & 0xFFu, g0, m0);
-                expand4((w >> 8) & 0xFFu, g1, m1);
-                expand4((w >> 16) & 0xFFu, g2, m2);
-                expand4(w >> 24, g3, m3);
-                o = mask_plane ? make_uint4(m0, m1, m2, m3) : make_uint4(g0, g1, g2, g3);
+                if (i >= nfull) {
+                    const uint32_t vb = valid_bits(n_ref, i);
+                    w = (w & vb) | (0x55555555u & ~vb);   // samples past n_ref -> "missing": 0 in both planes
+                }
+                o = mask_plane ? expand16<true>(w) : expand16<false>(w);
             }
             out[i] = o;
         }

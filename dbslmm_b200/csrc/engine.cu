@@ -57,7 +57,7 @@ struct PinBuf {
 constexpr int kNumClasses = 4;                 // size classes of the Cholesky step loop (by #panels)
 constexpr int kClassMaxPanels[kNumClasses] = {8, 16, 32, 1 << 30};
 
-struct StepList { int32_t diag_off, n_diag, panel_off, n_panel; };
+struct StepList { int32_t diag_off, n_diag, panel_off, n_panel, group_base, n_groups, nsl; };
 
 struct Plan {
     int32_t n_blocks = 0;
@@ -70,6 +70,10 @@ struct Plan {
     std::vector<int32_t> order;                       // blocks by descending size
     int32_t n_tiles_plain = 0, n_tiles_miss = 0;
     std::vector<StepList> steps[kNumClasses];         // per class, per panel step
+    int64_t scratch_off[kNumClasses] = {0, 0, 0, 0};  // split-K scratch region of each class (doubles)
+    int64_t scratch_doubles = 0;
+    int32_t n_groups = 0;                             // split-K groups (one arrival counter each)
+    int32_t n_big = 0;                                // blocks with mp > 1024 (head of `order`)
     // blob layout (byte offsets inside the plan blob, identical on host and device)
     size_t o_blocks = 0, o_rowsrc = 0, o_rowg = 0, o_z = 0, o_tiles_plain = 0, o_tiles_miss = 0, o_order = 0,
            o_diag = 0, o_panel = 0, blob_bytes = 0;
@@ -93,7 +97,7 @@ struct dbslmm_b200_handle {
     int64_t n_snp = 0;
     int32_t n_ref = 0, pitch = 0, n_pad = 0;
     // workspace
-    DevBuf codes, sigma, lbuf, rowN, rowS, rowR, planblob, beta, status, intQ, intA, intN, scratch;
+    DevBuf codes, sigma, lbuf, rowN, rowS, rowR, planblob, beta, status, intQ, intA, intN, scratch, counters;
     PinBuf h_blob, h_out;
     Plan plan;
     int32_t last_flags = 0, last_solver = 0, last_nfolds = 0;
@@ -187,7 +191,9 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, st
 
     // Cholesky step lists per size class
     std::vector<int32_t> diag_items;
-    std::vector<int2> panel_items;
+    std::vector<int4> panel_items;
+    int32_t n_groups = 0;
+    constexpr int kTargetCtas = 296;                  // 2 CTAs per SM on a 148-SM part
     for (int c = 0; c < kNumClasses; ++c) {
         const int lo = (c == 0) ? 0 : kClassMaxPanels[c - 1];
         const int hi = kClassMaxPanels[c];
@@ -198,10 +204,24 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, st
             if (K > lo && K <= hi) { members.push_back(b); kmax = std::max(kmax, K); }
         }
         P.steps[c].resize(kmax);
+        int64_t class_scratch = 0;
         for (int k = 0; k < kmax; ++k) {
             StepList& s = P.steps[c][k];
             s.diag_off = (int32_t)diag_items.size();
             s.panel_off = (int32_t)panel_items.size();
+            // macro tiles of this step, then the split-K factor: when a step has few tiles but a long K
+            // loop (late panels of big blocks), slice K so the step still fills the GPU
+            int ntiles = 0;
+            for (int b : members) {
+                const BlockDesc& d = P.blocks[b];
+                if ((d.mp + 63) / 64 <= k) continue;
+                const int wk = std::min(64, d.mp - 64 * k);
+                ntiles += (d.mp + 8 - (64 * k + wk) + 127) / 128;
+            }
+            int nsl = 1;
+            if (ntiles > 0) nsl = std::max(1, std::min({8, k / 4, kTargetCtas / ntiles}));
+            s.nsl = nsl;
+            s.group_base = n_groups;
             for (int b : members) {
                 const BlockDesc& d = P.blocks[b];
                 const int K = (d.mp + 63) / 64;
@@ -210,11 +230,18 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, st
                 const int wk = std::min(64, d.mp - 64 * k);
                 const int below = 64 * k + wk;
                 const int nt = (d.mp + 8 - below + 127) / 128;
-                for (int t = 0; t < nt; ++t) panel_items.push_back(make_int2(b, t));
+                for (int t = 0; t < nt; ++t) {
+                    const int gid = (nsl > 1) ? n_groups++ : 0;
+                    for (int sl = 0; sl < nsl; ++sl) panel_items.push_back(make_int4(b, t, sl | (nsl << 8), gid));
+                }
             }
+            s.n_groups = n_groups - s.group_base;
             s.n_diag = (int32_t)diag_items.size() - s.diag_off;
             s.n_panel = (int32_t)panel_items.size() - s.panel_off;
+            class_scratch = std::max<int64_t>(class_scratch, (int64_t)s.n_groups * nsl * 128 * 64);
         }
+        P.scratch_off[c] = P.scratch_doubles;
+        P.scratch_doubles += class_scratch;
     }
 
     // ---- pack the blob
@@ -228,7 +255,10 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, st
     P.o_tiles_miss = place(sizeof(GramTile) * tiles_miss.size());
     P.o_order = place(sizeof(int32_t) * (size_t)nb);
     P.o_diag = place(sizeof(int32_t) * diag_items.size());
-    P.o_panel = place(sizeof(int2) * panel_items.size());
+    P.o_panel = place(sizeof(int4) * panel_items.size());
+    P.n_groups = n_groups;
+    P.n_big = 0;
+    for (int b : P.order) { if (P.blocks[b].mp > 1024) P.n_big++; else break; }
     P.blob_bytes = o;
     blob.assign(o, 0);
     std::memcpy(blob.data() + P.o_blocks, P.blocks.data(), sizeof(BlockDesc) * (size_t)nb);
@@ -256,7 +286,7 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, st
     if (!tiles_miss.empty()) std::memcpy(blob.data() + P.o_tiles_miss, tiles_miss.data(), sizeof(GramTile) * tiles_miss.size());
     std::memcpy(blob.data() + P.o_order, P.order.data(), sizeof(int32_t) * (size_t)nb);
     if (!diag_items.empty()) std::memcpy(blob.data() + P.o_diag, diag_items.data(), sizeof(int32_t) * diag_items.size());
-    if (!panel_items.empty()) std::memcpy(blob.data() + P.o_panel, panel_items.data(), sizeof(int2) * panel_items.size());
+    if (!panel_items.empty()) std::memcpy(blob.data() + P.o_panel, panel_items.data(), sizeof(int4) * panel_items.size());
     P.valid = true;
     return DBSLMM_B200_OK;
 }
@@ -334,7 +364,7 @@ void dbslmm_b200_destroy(dbslmm_b200_handle* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     DevBuf* bufs[] = {&h->bed, &h->stats, &h->codes, &h->sigma, &h->lbuf, &h->rowN, &h->rowS, &h->rowR,
-                      &h->planblob, &h->beta, &h->status, &h->intQ, &h->intA, &h->intN, &h->scratch};
+                      &h->planblob, &h->beta, &h->status, &h->intQ, &h->intA, &h->intN, &h->scratch, &h->counters};
     for (DevBuf* b : bufs) b->release();
     h->h_blob.release();
     h->h_out.release();
@@ -455,6 +485,10 @@ int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
     const size_t n_out = (size_t)(P.tot_s + P.tot_l);
     CU_TRY(h, h->beta.ensure(sizeof(double) * std::max<size_t>(n_out * nfold, 1)));
     CU_TRY(h, h->status.ensure(sizeof(int32_t) * (size_t)std::max(2 * nb, 1)));
+    if (!pcg) {
+        CU_TRY(h, h->scratch.ensure(sizeof(double) * (size_t)std::max<int64_t>(P.scratch_doubles, 1)));
+        CU_TRY(h, h->counters.ensure(sizeof(int32_t) * (size_t)std::max(P.n_groups, 1)));
+    }
     if (keep_int) {
         CU_TRY(h, h->intQ.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(P.mat_doubles, 1)));
         CU_TRY(h, h->intA.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(P.mat_doubles, 1)));
@@ -472,7 +506,7 @@ int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
     const GramTile* d_tiles_miss = (const GramTile*)(dblob + P.o_tiles_miss);
     const int32_t* d_order = (const int32_t*)(dblob + P.o_order);
     const int32_t* d_diag = (const int32_t*)(dblob + P.o_diag);
-    const int2* d_panel = (const int2*)(dblob + P.o_panel);
+    const int4* d_panel = (const int4*)(dblob + P.o_panel);
     double* d_beta = (double*)h->beta.p;
     int32_t* d_status = (int32_t*)h->status.p;
     int32_t* d_iters = d_status + nb;
@@ -549,6 +583,7 @@ int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
         double* bs = d_beta + (size_t)f * n_out;
         double* bl = bs + P.tot_s;
         if (!pcg) {
+            if (P.n_groups > 0) CU_TRY(h, cudaMemsetAsync(h->counters.p, 0, sizeof(int32_t) * (size_t)P.n_groups, st));
             CU_TRY(h, cudaEventRecord(h->ev_fork, st));
             for (int c = 0; c < kNumClasses; ++c) {
                 if (P.steps[c].empty()) continue;
@@ -559,7 +594,9 @@ int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
                     CU_TRY(h, launch_chol_diag(d_blocks, d_diag + s.diag_off, s.n_diag, (int32_t)k,
                                                (const double*)h->sigma.p, (double*)h->lbuf.p, ridge, d_status, cs));
                     CU_TRY(h, launch_chol_panel(d_blocks, d_panel + s.panel_off, s.n_panel, (int32_t)k,
-                                                (const double*)h->sigma.p, (double*)h->lbuf.p, ridge, cs));
+                                                (const double*)h->sigma.p, (double*)h->lbuf.p, ridge,
+                                                (double*)h->scratch.p + P.scratch_off[c], (int32_t*)h->counters.p,
+                                                s.group_base, cs));
                     n_launch += 2;
                     n_chol_launch += 2;
                 }
@@ -567,7 +604,7 @@ int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
                 CU_TRY(h, cudaStreamWaitEvent(st, h->ev_join[c], 0));
             }
             CU_TRY(h, cudaEventRecord(h->ev[6], st));
-            CU_TRY(h, launch_backsolve(d_blocks, d_order, nb, (const double*)h->lbuf.p, inv_sqrt_n, bs, bl, P.max_mp, st));
+            CU_TRY(h, launch_backsolve(d_blocks, d_order, nb, P.n_big, (const double*)h->lbuf.p, inv_sqrt_n, bs, bl, P.max_mp, st));
             ++n_launch;
             if (a->timing && a->n_folds > 1) {
                 // per-fold factorisation time needs a sync; only paid when timing is requested
