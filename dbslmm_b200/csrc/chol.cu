@@ -21,6 +21,7 @@
 // The z-scores ride along as matrix row `mp`, so that row of L ends up holding y = L^-1 z;
 // backsolve_kernel then solves L^T x = y per block and writes beta = x / sqrt(N).
 // Matrices are row-major, lower triangle, ld = mp (m padded to 8 with identity rows).
+#include <algorithm>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -29,7 +30,7 @@ namespace dbslmm {
 static constexpr int NB = 64;          // panel width
 static constexpr int TM = 128;         // rows per macro tile
 static constexpr int KC = 16;          // K chunk per pipeline stage
-static constexpr int LDS = KC + 4;     // padded smem row stride (doubles): conflict-free 8x4 fragment loads
+static constexpr int LDS = KC + 8;     // padded smem row stride (doubles): conflict-free 128-bit fragment loads
 static constexpr int NST = 3;          // cp.async stages
 static constexpr int P_STAGE = TM * LDS;
 static constexpr int Q_STAGE = NB * LDS;
@@ -84,19 +85,24 @@ __device__ __forceinline__ void gemm_nt_core(const double* __restrict__ Pg, cons
         if (nx < nchunk) load_stage(nx, nx % NST);
         cp_async_commit();
         if (active) {
-            const double* Ps = smem + (kc % NST) * STAGE + (16 * warp + g) * LDS + t;
-            const double* Qs = smem + (kc % NST) * STAGE + P_STAGE + g * LDS + t;
+            // One 128-bit load feeds two DMMAs: within each 8-wide K group lane t owns k = 2t (.x) and
+            // k = 2t+1 (.y); A and B use the same assignment, so every product pairs the same k.
+            const double* Ps = smem + (kc % NST) * STAGE + (16 * warp + g) * LDS + 2 * t;
+            const double* Qs = smem + (kc % NST) * STAGE + P_STAGE + g * LDS + 2 * t;
 #pragma unroll
-            for (int s4 = 0; s4 < KC / 4; ++s4) {
-                const double a0 = Ps[s4 * 4], a1 = Ps[8 * LDS + s4 * 4];
-                double b[8];
+            for (int s8 = 0; s8 < KC / 8; ++s8) {
+                const double2 a0 = *reinterpret_cast<const double2*>(Ps + s8 * 8);
+                const double2 a1 = *reinterpret_cast<const double2*>(Ps + 8 * LDS + s8 * 8);
+                double2 b[8];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) b[c] = Qs[c * 8 * LDS + s4 * 4];
+                for (int c = 0; c < 8; ++c) b[c] = *reinterpret_cast<const double2*>(Qs + c * 8 * LDS + s8 * 8);
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     if (8 * c < qrow) {
-                        dmma884(acc[0][c][0], acc[0][c][1], a0, b[c]);
-                        dmma884(acc[1][c][0], acc[1][c][1], a1, b[c]);
+                        dmma884(acc[0][c][0], acc[0][c][1], a0.x, b[c].x);
+                        dmma884(acc[1][c][0], acc[1][c][1], a1.x, b[c].x);
+                        dmma884(acc[0][c][0], acc[0][c][1], a0.y, b[c].y);
+                        dmma884(acc[1][c][0], acc[1][c][1], a1.y, b[c].y);
                     }
                 }
             }
@@ -117,16 +123,12 @@ __device__ __forceinline__ void gemm_nt_core(const double* __restrict__ Pg, cons
 static constexpr int DT = NB + 1;   // odd stride: conflict-free row and column walks in FP64
 static constexpr int SMEM_DIAG = (2 * NB * DT + 16 * 17) * 8;
 
-__global__ void __launch_bounds__(CHOL_THREADS, 2)
-chol_diag_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict__ items, int32_t k,
-                 const double* __restrict__ sigma, double* __restrict__ Lbuf, double ridge,
-                 int32_t* __restrict__ status) {
-    extern __shared__ __align__(16) double smem[];
+__device__ __forceinline__ void diag_body(const BlockDesc& bd, int blk, int k, const double* __restrict__ sigma,
+                                          double* __restrict__ Lbuf, double ridge, int32_t* __restrict__ status,
+                                          double* smem) {
     double* T = smem;                        // [64][DT] tile, becomes L (lower)
     double* Wf = T + NB * DT;                // [64][DT] W = L^-1 (lower)
     double* tmp = Wf + NB * DT;              // [16][17]
-    const int blk = items[blockIdx.x];
-    const BlockDesc bd = blocks[blk];
     const int pc0 = k * NB;
     const int wk = min(NB, bd.mp - pc0);
     const int ld = bd.ld;
@@ -134,18 +136,28 @@ chol_diag_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict
     const double* src = (k == 0 ? sigma : Lbuf) + bd.moff;     // step 0 reads Sigma, later steps the accumulated tile
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    for (int idx = tid; idx < NB * NB; idx += CHOL_THREADS) {
-        const int a = idx >> 6, b = idx & 63;
-        double v = (a == b) ? 1.0 : 0.0;
-        if (a < wk && b < wk) {
-            v = 0.0;
-            if (b <= a) {
-                v = src[(size_t)(pc0 + a) * ld + pc0 + b];
-                if (k == 0 && a == b && a < bd.ms) v += ridge;
-            }
+    {
+        // all 16 loads of a thread are issued back to back (independent), then consumed
+        double tv[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int idx = tid + u * CHOL_THREADS;
+            const int a = idx >> 6, b = idx & 63;
+            const bool ld_it = (a < wk) && (b <= a);
+            tv[u] = ld_it ? __ldcg(src + (size_t)(pc0 + a) * ld + pc0 + b) : 0.0;
         }
-        T[a * DT + b] = v;
-        Wf[a * DT + b] = 0.0;
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int idx = tid + u * CHOL_THREADS;
+            const int a = idx >> 6, b = idx & 63;
+            double v = tv[u];
+            if (a == b) {
+                if (a >= wk) v = 1.0;                                   // identity padding
+                else if (k == 0 && pc0 + a < bd.ms) v += ridge;
+            }
+            T[a * DT + b] = v;
+            Wf[a * DT + b] = 0.0;
+        }
     }
     __syncthreads();
 
@@ -166,7 +178,7 @@ chol_diag_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict
                 if (!(d > 0.0)) bad = true;
                 const double inv = rsqrt(d);
                 const double sq = d * inv;
-                dinv[j] = 1.0 / sq;
+                dinv[j] = inv;
                 double lrj = row[j] * inv;
                 if (r == j) lrj = sq;
                 if (r < j) lrj = 0.0;
@@ -268,6 +280,16 @@ chol_diag_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict
     }
 }
 
+__global__ void __launch_bounds__(CHOL_THREADS, 2)
+chol_diag_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict__ items, int32_t k,
+                 const double* __restrict__ sigma, double* __restrict__ Lbuf, double ridge,
+                 int32_t* __restrict__ status) {
+    extern __shared__ __align__(16) double smem[];
+    const int blk = items[blockIdx.x];
+    const BlockDesc bd = blocks[blk];
+    diag_body(bd, blk, k, sigma, Lbuf, ridge, status, smem);
+}
+
 // ------------------------------------------------------------------------------------------
 // Rows below the diagonal tile of panel k:
 //   C = K_ik - L_i,0:k L_k,0:k^T (DMMA, cp.async ring), L_ik = C W_kk^T (DMMA), then the
@@ -275,14 +297,13 @@ chol_diag_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict
 //   its contribution  T_ii -= L_ik L_ik^T  to ITS OWN diagonal tile (one writer per tile and
 //   step, so no atomics), so the diagonal kernel never runs a GEMM.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CHOL_THREADS, 2)
-chol_panel_kernel(const BlockDesc* __restrict__ blocks, const int4* __restrict__ items, int32_t k,
-                  const double* __restrict__ sigma, double* __restrict__ Lbuf, double ridge,
-                  double* __restrict__ scratch, int32_t* __restrict__ counters, int32_t group_base) {
-    extern __shared__ __align__(16) double smem[];
-    __shared__ int s_last;
-    const int4 item = items[blockIdx.x];     // x = block, y = macro tile, z = slice | nslices << 8, w = split group id
-    const BlockDesc bd = blocks[item.x];
+// item: x = block, y = macro tile, z = slice | nslices << 8, w = split group id.
+// Returns false when this CTA was a non-final split-K slice (nothing more to do).
+__device__ __forceinline__ bool panel_body(const BlockDesc& bd, const int4 item, int k, const double* __restrict__ sigma,
+                                           double* __restrict__ Lbuf, double ridge, double* __restrict__ scratch,
+                                           int32_t* __restrict__ counters, int32_t group_base, double* smem,
+                                           int* s_last_p) {
+    int& s_last = *s_last_p;
     const int pc0 = k * NB;
     const int wk = min(NB, bd.mp - pc0);
     const int ld = bd.ld;
@@ -316,7 +337,7 @@ chol_panel_kernel(const BlockDesc* __restrict__ blocks, const int4* __restrict__
         __syncthreads();
         if (tid == 0) s_last = (atomicAdd(&counters[item.w], 1) == nsl - 1);
         __syncthreads();
-        if (!s_last) return;
+        if (!s_last) return false;
         __threadfence();
 #pragma unroll
         for (int f = 0; f < 2; ++f)
@@ -338,13 +359,23 @@ chol_panel_kernel(const BlockDesc* __restrict__ blocks, const int4* __restrict__
     double* Ct = smem;                            // [128][LDT] macro tile, 16 rows per warp
     double* Cw = Ct + warp * 16 * LDT;
     double* W = smem + 8 * 16 * LDT;              // [64][LDT], W[c][c'] = (L_kk^-1)[c][c'], zero above diagonal
-    for (int i = tid; i < NB * LDT; i += CHOL_THREADS) W[i] = 0.0;
-    __syncthreads();
-    for (int idx = tid; idx < wk * wk; idx += CHOL_THREADS) {
-        const int a = idx / wk, b = idx - a * wk;
-        const double v = Lb[(size_t)(pc0 + a) * ld + pc0 + b];
-        if (b > a) W[b * LDT + a] = v;            // upper triangle stores W^T
-        else if (b == a) W[a * LDT + a] = 1.0 / v;
+    {
+        // W tile: 16 independent loads per thread, every W entry written exactly once
+        double wv[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int idx = tid + u * CHOL_THREADS;
+            const int a = idx >> 6, b = idx & 63;
+            const bool ld_it = (b >= a) && (b < wk);
+            wv[u] = ld_it ? __ldcg(Lb + (size_t)(pc0 + a) * ld + pc0 + b) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int idx = tid + u * CHOL_THREADS;
+            const int a = idx >> 6, b = idx & 63;
+            if (b > a) { W[b * LDT + a] = wv[u]; W[a * LDT + b] = 0.0; }      // upper triangle stores W^T
+            else if (b == a) W[a * LDT + a] = (a < wk) ? 1.0 / wv[u] : 0.0;
+        }
     }
     const bool active = (16 * warp < prow);
 #pragma unroll
@@ -394,10 +425,8 @@ chol_panel_kernel(const BlockDesc* __restrict__ blocks, const int4* __restrict__
     // ---- look-ahead: T_ii -= L_ik L_ik^T for the 64-row tile this warp belongs to
     const int grp = warp >> 2, wl = warp & 3;
     const int trow0 = r0 + 64 * grp;              // first global row of the 64-row tile
-    if (trow0 >= bd.mp || wk < NB) return;        // z rows / last (narrow) panel: no diagonal tile below
-    const int tw = min(NB, bd.mp - trow0);        // tile extent
-    if (16 * wl >= tw) return;
-    {
+    const int tw = min(NB, bd.mp - trow0);        // tile extent (<= 0: z rows, no diagonal tile)
+    if (trow0 < bd.mp && wk == NB && 16 * wl < tw) {   // (a narrow last panel has no diagonal tile below either)
         const double* A = Ct + (64 * grp + 16 * wl + g) * LDT + t;
         const double* B = Ct + (64 * grp + g) * LDT + t;
 #pragma unroll 4
@@ -420,7 +449,7 @@ chol_panel_kernel(const BlockDesc* __restrict__ blocks, const int4* __restrict__
                 const int rl = 16 * wl + 8 * f + g, cc = 8 * c + 2 * t;   // within the tile
                 if (c <= 2 * wl + 1 && rl < tw && cc <= rl) {
                     const size_t o = (size_t)(trow0 + rl) * ld + trow0 + cc;
-                    double2 v = *reinterpret_cast<const double2*>(src + o);
+                    double2 v = __ldcg(reinterpret_cast<const double2*>(src + o));
                     if (k == 0) {
                         if (cc == rl && trow0 + rl < bd.ms) v.x += ridge;
                         if (cc + 1 == rl && trow0 + rl < bd.ms) v.y += ridge;   // odd rows: the diagonal is the pair's second element
@@ -431,6 +460,18 @@ chol_panel_kernel(const BlockDesc* __restrict__ blocks, const int4* __restrict__
                 }
             }
     }
+    return true;
+}
+
+__global__ void __launch_bounds__(CHOL_THREADS, 2)
+chol_panel_kernel(const BlockDesc* __restrict__ blocks, const int4* __restrict__ items, int32_t k,
+                  const double* __restrict__ sigma, double* __restrict__ Lbuf, double ridge,
+                  double* __restrict__ scratch, int32_t* __restrict__ counters, int32_t group_base) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ int s_last;
+    const int4 item = items[blockIdx.x];
+    const BlockDesc bd = blocks[item.x];
+    panel_body(bd, item, k, sigma, Lbuf, ridge, scratch, counters, group_base, smem, &s_last);
 }
 
 // ------------------------------------------------------------------------------------------

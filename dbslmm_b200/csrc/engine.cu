@@ -123,7 +123,7 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // ------------------------------------------------------------------------------------------
 // Plan construction (host): the block scheduler's bookkeeping
 // ------------------------------------------------------------------------------------------
-int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, std::vector<uint8_t>& blob) {
+int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P) {
     const int nb = a->n_blocks;
     P = Plan();
     P.n_blocks = nb;
@@ -260,7 +260,9 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, st
     P.n_big = 0;
     for (int b : P.order) { if (P.blocks[b].mp > 1024) P.n_big++; else break; }
     P.blob_bytes = o;
-    blob.assign(o, 0);
+    // fill the pinned staging buffer in place (no intermediate copy; alignment gaps are never read)
+    if (h->h_blob.ensure(o + 256) != cudaSuccess) return fail(h, DBSLMM_B200_ERR_NOMEM, "pinned plan buffer");
+    struct { uint8_t* p; uint8_t* data() const { return p; } } blob{(uint8_t*)h->h_blob.p};
     std::memcpy(blob.data() + P.o_blocks, P.blocks.data(), sizeof(BlockDesc) * (size_t)nb);
     uint32_t* rs = reinterpret_cast<uint32_t*>(blob.data() + P.o_rowsrc);
     int32_t* rg = reinterpret_cast<int32_t*>(blob.data() + P.o_rowg);
@@ -466,9 +468,8 @@ int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
     Plan& P = h->plan;
     const bool reuse = (a->flags & DBSLMM_B200_FLAG_PLAN_CACHED) && P.valid && P.n_blocks == a->n_blocks &&
                        P.tot_s == a->s_off[a->n_blocks] && P.tot_l == (a->l_off ? a->l_off[a->n_blocks] : 0);
-    std::vector<uint8_t> blob;
     if (!reuse) {
-        int rc = build_plan(h, a, P, blob);
+        int rc = build_plan(h, a, P);
         if (rc != DBSLMM_B200_OK) { P.valid = false; return rc; }
     }
     const int nb = P.n_blocks;
@@ -515,8 +516,6 @@ int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
     CU_TRY(h, cudaEventRecord(h->ev[0], st));
     // ---- upload
     if (!reuse) {
-        CU_TRY(h, h->h_blob.ensure(P.blob_bytes));
-        std::memcpy(h->h_blob.p, blob.data(), P.blob_bytes);
         if (P.blob_bytes) CU_TRY(h, cudaMemcpyAsync(dblob, h->h_blob.p, P.blob_bytes, cudaMemcpyHostToDevice, st));
     } else if (P.n_snp_rows > 0) {
         // same CSR layout, new z-scores
