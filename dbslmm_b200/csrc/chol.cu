@@ -38,7 +38,9 @@ static constexpr int STAGE = P_STAGE + Q_STAGE;
 static constexpr int LDT = NB + 4;     // stride of 64-wide epilogue tiles
 static constexpr int CHOL_THREADS = 256;
 static constexpr int SMEM_PIPE = NST * STAGE * 8;
-static constexpr int SMEM_EPI = (8 * 16 * LDT + NB * LDT) * 8;
+static constexpr int SMEM_CT = 8 * 16 * LDT * 8;                           // macro tile C / L, aliases the pipeline
+static constexpr int W_OFF = SMEM_CT / 8;                                  // W tile follows the macro tile (doubles)
+static constexpr int SMEM_EPI = SMEM_CT + NB * LDT * 8;
 static constexpr int SMEM_CHOL = (SMEM_PIPE > SMEM_EPI ? SMEM_PIPE : SMEM_EPI);
 
 // acc (16 rows x 64 cols per warp) += P[r0.., 0:K] * Q[q0.., 0:K]^T, both row-major with K contiguous.
@@ -121,11 +123,11 @@ __device__ __forceinline__ void gemm_nt_core(const double* __restrict__ Pg, cons
 // Tiles narrower than 64 (last panel) are padded with identity, so the code path is uniform.
 // ------------------------------------------------------------------------------------------
 static constexpr int DT = NB + 1;   // odd stride: conflict-free row and column walks in FP64
-static constexpr int SMEM_DIAG = (2 * NB * DT + 16 * 17) * 8;
+static constexpr int SMEM_DIAG = (2 * NB * DT + 3 * 16 * 17) * 8;
 
 __device__ __forceinline__ void diag_body(const BlockDesc& bd, int blk, int k, const double* __restrict__ sigma,
-                                          double* __restrict__ Lbuf, double ridge, int32_t* __restrict__ status,
-                                          double* smem) {
+                                          double* __restrict__ Lbuf, double* __restrict__ wbuf, double ridge,
+                                          int32_t* __restrict__ status, double* smem) {
     double* T = smem;                        // [64][DT] tile, becomes L (lower)
     double* Wf = T + NB * DT;                // [64][DT] W = L^-1 (lower)
     double* tmp = Wf + NB * DT;              // [16][17]
@@ -254,40 +256,51 @@ __device__ __forceinline__ void diag_body(const BlockDesc& bd, int blk, int k, c
         __syncthreads();
     }
     if (warp == 0 && __any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&status[blk], 1);
-    // ---- off-diagonal 16x16 blocks of W:  W_ij = -W_ii * sum_{kb=j}^{i-1} L_i,kb W_kb,j
+    // ---- off-diagonal 16x16 blocks of W:  W_ij = -W_ii * sum_{kb=j}^{i-1} L_i,kb W_kb,j, level by level in
+    // the block distance d = i - j (all blocks of a level at once; tmp holds up to three 16x16 products)
     {
         const int r = tid >> 4, c = tid & 15;
 #pragma unroll 1
         for (int d = 1; d < 4; ++d) {
-#pragma unroll 1
-            for (int i = d; i < 4; ++i) {
-                const int j = i - d;
+            const int nblk = 4 - d;
+            for (int q = 0; q < nblk; ++q) {
+                const int i = d + q, j = q;
                 double a = 0.0;
                 for (int kk = 16 * j; kk < 16 * i; ++kk) a += T[(16 * i + r) * DT + kk] * Wf[kk * DT + 16 * j + c];
-                tmp[r * 17 + c] = a;
-                __syncthreads();
-                double wv = 0.0;
-                for (int kk = 0; kk <= r; ++kk) wv += Wf[(16 * i + r) * DT + 16 * i + kk] * tmp[kk * 17 + c];
-                Wf[(16 * i + r) * DT + 16 * j + c] = -wv;
-                __syncthreads();
+                tmp[q * 272 + r * 17 + c] = a;
             }
+            __syncthreads();
+            for (int q = 0; q < nblk; ++q) {
+                const int i = d + q, j = q;
+                double wv = 0.0;
+                for (int kk = 0; kk <= r; ++kk) wv += Wf[(16 * i + r) * DT + 16 * i + kk] * tmp[q * 272 + kk * 17 + c];
+                Wf[(16 * i + r) * DT + 16 * j + c] = -wv;
+            }
+            __syncthreads();
         }
     }
-    // ---- write back: lower = L_kk, strict upper = W_kk^T
+    // ---- write back: lower = L_kk, strict upper = W_kk^T (used by the back substitution) ...
     for (int idx = tid; idx < wk * wk; idx += CHOL_THREADS) {
         const int a = idx / wk, b = idx - a * wk;
         Lb[(size_t)(pc0 + a) * ld + pc0 + b] = (b <= a) ? T[a * DT + b] : Wf[b * DT + a];
     }
+    // ... and W_kk as a dense 64x64 lower-triangular tile for the panel kernel of this step, which
+    // streams it into shared memory with cp.async while its GEMM loop runs
+    double* wb = wbuf + (size_t)blk * (NB * NB);
+    for (int idx = tid; idx < NB * NB; idx += CHOL_THREADS) {
+        const int a = idx >> 6, b = idx & 63;
+        wb[idx] = (b <= a) ? Wf[a * DT + b] : 0.0;
+    }
 }
 
-__global__ void __launch_bounds__(CHOL_THREADS, 2)
+__global__ void __launch_bounds__(CHOL_THREADS, 3)
 chol_diag_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict__ items, int32_t k,
-                 const double* __restrict__ sigma, double* __restrict__ Lbuf, double ridge,
-                 int32_t* __restrict__ status) {
+                 const double* __restrict__ sigma, double* __restrict__ Lbuf, double* __restrict__ wbuf,
+                 double ridge, int32_t* __restrict__ status) {
     extern __shared__ __align__(16) double smem[];
     const int blk = items[blockIdx.x];
     const BlockDesc bd = blocks[blk];
-    diag_body(bd, blk, k, sigma, Lbuf, ridge, status, smem);
+    diag_body(bd, blk, k, sigma, Lbuf, wbuf, ridge, status, smem);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -300,9 +313,9 @@ chol_diag_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict
 // item: x = block, y = macro tile, z = slice | nslices << 8, w = split group id.
 // Returns false when this CTA was a non-final split-K slice (nothing more to do).
 __device__ __forceinline__ bool panel_body(const BlockDesc& bd, const int4 item, int k, const double* __restrict__ sigma,
-                                           double* __restrict__ Lbuf, double ridge, double* __restrict__ scratch,
-                                           int32_t* __restrict__ counters, int32_t group_base, double* smem,
-                                           int* s_last_p) {
+                                           double* __restrict__ Lbuf, const double* __restrict__ wbuf, double ridge,
+                                           double* __restrict__ scratch, int32_t* __restrict__ counters,
+                                           int32_t group_base, double* smem, int* s_last_p) {
     int& s_last = *s_last_p;
     const int pc0 = k * NB;
     const int wk = min(NB, bd.mp - pc0);
@@ -314,12 +327,21 @@ __device__ __forceinline__ bool panel_body(const BlockDesc& bd, const int4 item,
     const double* Sb = sigma + bd.moff;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
 
+    const int slice = item.z & 0xFF, nsl = item.z >> 8;
+    double* Wsm = smem + W_OFF;                   // [64][LDT], W[c][c'] = (L_kk^-1)[c][c'], zero above the diagonal
+    // accumulators start at -K_ik (slice 0 only), so the Sigma tile's HBM latency hides behind the pipeline
+    // prologue: after the loop acc = L_i,0:k L_k,0:k^T - K_ik = -C
     double acc[2][8][2];
 #pragma unroll
     for (int f = 0; f < 2; ++f)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc[f][c][0] = acc[f][c][1] = 0.0;
-    const int slice = item.z & 0xFF, nsl = item.z >> 8;
+        for (int c = 0; c < 8; ++c) {
+            const int rl = 16 * warp + 8 * f + g, cc = 8 * c + 2 * t;
+            double2 a = make_double2(0.0, 0.0);
+            if (slice == 0 && rl < prow && cc < wk) a = *reinterpret_cast<const double2*>(Sb + (size_t)(r0 + rl) * ld + pc0 + cc);
+            acc[f][c][0] = -a.x;
+            acc[f][c][1] = -a.y;
+        }
     {
         // split-K: slice s of nsl owns 64-wide K blocks [k*s/nsl, k*(s+1)/nsl)
         const int kb = (k * slice) / nsl * NB, ke = (k * (slice + 1)) / nsl * NB;
@@ -356,39 +378,31 @@ __device__ __forceinline__ bool panel_body(const BlockDesc& bd, const int4 item,
         }
     }
 
+    {
+        // W tile of this step (written dense by the diagonal kernel): its L2 latency overlaps the C write-out
+        const double* wsrc = wbuf + (size_t)item.x * (NB * NB);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int idx = tid + u * CHOL_THREADS;
+            const int row = idx >> 5, ch = (idx & 31) * 2;
+            cp_async16(Wsm + row * LDT + ch, wsrc + row * NB + ch, true);
+        }
+        cp_async_commit();
+    }
     double* Ct = smem;                            // [128][LDT] macro tile, 16 rows per warp
     double* Cw = Ct + warp * 16 * LDT;
-    double* W = smem + 8 * 16 * LDT;              // [64][LDT], W[c][c'] = (L_kk^-1)[c][c'], zero above diagonal
-    {
-        // W tile: 16 independent loads per thread, every W entry written exactly once
-        double wv[16];
-#pragma unroll
-        for (int u = 0; u < 16; ++u) {
-            const int idx = tid + u * CHOL_THREADS;
-            const int a = idx >> 6, b = idx & 63;
-            const bool ld_it = (b >= a) && (b < wk);
-            wv[u] = ld_it ? __ldcg(Lb + (size_t)(pc0 + a) * ld + pc0 + b) : 0.0;
-        }
-#pragma unroll
-        for (int u = 0; u < 16; ++u) {
-            const int idx = tid + u * CHOL_THREADS;
-            const int a = idx >> 6, b = idx & 63;
-            if (b > a) { W[b * LDT + a] = wv[u]; W[a * LDT + b] = 0.0; }      // upper triangle stores W^T
-            else if (b == a) W[a * LDT + a] = (a < wk) ? 1.0 / wv[u] : 0.0;
-        }
-    }
+    const double* W = Wsm;
     const bool active = (16 * warp < prow);
 #pragma unroll
     for (int f = 0; f < 2; ++f)
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-            const int rl = 16 * warp + 8 * f + g, cc = 8 * c + 2 * t;
-            double2 a = make_double2(0.0, 0.0);
-            if (rl < prow && cc < wk) a = *reinterpret_cast<const double2*>(Sb + (size_t)(r0 + rl) * ld + pc0 + cc);
-            Cw[(8 * f + g) * LDT + cc] = a.x - acc[f][c][0];
-            Cw[(8 * f + g) * LDT + cc + 1] = a.y - acc[f][c][1];
+            const int cc = 8 * c + 2 * t;
+            Cw[(8 * f + g) * LDT + cc] = -acc[f][c][0];
+            Cw[(8 * f + g) * LDT + cc + 1] = -acc[f][c][1];
             acc[f][c][0] = acc[f][c][1] = 0.0;
         }
+    cp_async_wait<0>();
     __syncthreads();
     const double* Ca = Cw + g * LDT + t;
     const double* Wb = W + g * LDT + t;
@@ -421,12 +435,32 @@ __device__ __forceinline__ bool panel_body(const BlockDesc& bd, const int4 item,
             Cw[(8 * f + g) * LDT + cc + 1] = acc[f][c][1];
             acc[f][c][0] = acc[f][c][1] = 0.0;
         }
-    __syncthreads();
     // ---- look-ahead: T_ii -= L_ik L_ik^T for the 64-row tile this warp belongs to
     const int grp = warp >> 2, wl = warp & 3;
     const int trow0 = r0 + 64 * grp;              // first global row of the 64-row tile
     const int tw = min(NB, bd.mp - trow0);        // tile extent (<= 0: z rows, no diagonal tile)
-    if (trow0 < bd.mp && wk == NB && 16 * wl < tw) {   // (a narrow last panel has no diagonal tile below either)
+    const bool look = (trow0 < bd.mp && wk == NB && 16 * wl < tw);   // (a narrow last panel has no diagonal tile below)
+    if (look) {
+        // the old tile values go straight into the accumulators (negated): their latency overlaps the barrier
+        const double* src = (k == 0 ? sigma : Lbuf) + bd.moff;    // first touch reads Sigma (+ ridge)
+#pragma unroll
+        for (int f = 0; f < 2; ++f)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int rl = 16 * wl + 8 * f + g, cc = 8 * c + 2 * t;   // within the tile
+                if (c <= 2 * wl + 1 && rl < tw && cc <= rl) {
+                    double2 v = __ldcg(reinterpret_cast<const double2*>(src + (size_t)(trow0 + rl) * ld + trow0 + cc));
+                    if (k == 0) {
+                        if (cc == rl && trow0 + rl < bd.ms) v.x += ridge;
+                        if (cc + 1 == rl && trow0 + rl < bd.ms) v.y += ridge;   // odd rows: the diagonal is the pair's second element
+                    }
+                    acc[f][c][0] = -v.x;
+                    acc[f][c][1] = -v.y;
+                }
+            }
+    }
+    __syncthreads();
+    if (look) {
         const double* A = Ct + (64 * grp + 16 * wl + g) * LDT + t;
         const double* B = Ct + (64 * grp + g) * LDT + t;
 #pragma unroll 4
@@ -441,23 +475,15 @@ __device__ __forceinline__ bool panel_body(const BlockDesc& bd, const int4 item,
                 }
             }
         }
-        const double* src = (k == 0 ? sigma : Lbuf) + bd.moff;    // first touch reads Sigma (+ ridge)
+        // acc = L L^T - T_old  =>  T_new = -acc
 #pragma unroll
         for (int f = 0; f < 2; ++f)
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 const int rl = 16 * wl + 8 * f + g, cc = 8 * c + 2 * t;   // within the tile
-                if (c <= 2 * wl + 1 && rl < tw && cc <= rl) {
-                    const size_t o = (size_t)(trow0 + rl) * ld + trow0 + cc;
-                    double2 v = __ldcg(reinterpret_cast<const double2*>(src + o));
-                    if (k == 0) {
-                        if (cc == rl && trow0 + rl < bd.ms) v.x += ridge;
-                        if (cc + 1 == rl && trow0 + rl < bd.ms) v.y += ridge;   // odd rows: the diagonal is the pair's second element
-                    }
-                    v.x -= acc[f][c][0];
-                    v.y -= acc[f][c][1];
-                    *reinterpret_cast<double2*>(Lb + o) = v;
-                }
+                if (c <= 2 * wl + 1 && rl < tw && cc <= rl)
+                    *reinterpret_cast<double2*>(Lb + (size_t)(trow0 + rl) * ld + trow0 + cc) =
+                        make_double2(-acc[f][c][0], -acc[f][c][1]);
             }
     }
     return true;
@@ -465,13 +491,13 @@ __device__ __forceinline__ bool panel_body(const BlockDesc& bd, const int4 item,
 
 __global__ void __launch_bounds__(CHOL_THREADS, 2)
 chol_panel_kernel(const BlockDesc* __restrict__ blocks, const int4* __restrict__ items, int32_t k,
-                  const double* __restrict__ sigma, double* __restrict__ Lbuf, double ridge,
-                  double* __restrict__ scratch, int32_t* __restrict__ counters, int32_t group_base) {
+                  const double* __restrict__ sigma, double* __restrict__ Lbuf, const double* __restrict__ wbuf,
+                  double ridge, double* __restrict__ scratch, int32_t* __restrict__ counters, int32_t group_base) {
     extern __shared__ __align__(16) double smem[];
     __shared__ int s_last;
     const int4 item = items[blockIdx.x];
     const BlockDesc bd = blocks[item.x];
-    panel_body(bd, item, k, sigma, Lbuf, ridge, scratch, counters, group_base, smem, &s_last);
+    panel_body(bd, item, k, sigma, Lbuf, wbuf, ridge, scratch, counters, group_base, smem, &s_last);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -557,17 +583,18 @@ cudaError_t chol_configure() {
 }
 
 cudaError_t launch_chol_diag(const BlockDesc* blocks, const int32_t* items, int32_t n_items, int32_t k,
-                             const double* sigma, double* L, double ridge, int32_t* status, cudaStream_t st) {
+                             const double* sigma, double* L, double* wbuf, double ridge, int32_t* status,
+                             cudaStream_t st) {
     if (n_items == 0) return cudaSuccess;
-    chol_diag_kernel<<<n_items, CHOL_THREADS, SMEM_DIAG, st>>>(blocks, items, k, sigma, L, ridge, status);
+    chol_diag_kernel<<<n_items, CHOL_THREADS, SMEM_DIAG, st>>>(blocks, items, k, sigma, L, wbuf, ridge, status);
     return cudaGetLastError();
 }
 cudaError_t launch_chol_panel(const BlockDesc* blocks, const int4* items, int32_t n_items, int32_t k,
-                              const double* sigma, double* L, double ridge, double* scratch, int32_t* counters,
-                              int32_t group_base, cudaStream_t st) {
+                              const double* sigma, double* L, const double* wbuf, double ridge, double* scratch,
+                              int32_t* counters, int32_t group_base, cudaStream_t st) {
     if (n_items == 0) return cudaSuccess;
-    chol_panel_kernel<<<n_items, CHOL_THREADS, SMEM_CHOL, st>>>(blocks, items, k, sigma, L, ridge, scratch, counters,
-                                                                 group_base);
+    chol_panel_kernel<<<n_items, CHOL_THREADS, SMEM_CHOL, st>>>(blocks, items, k, sigma, L, wbuf, ridge, scratch,
+                                                                 counters, group_base);
     return cudaGetLastError();
 }
 // `order` lists blocks by descending size; the first n_big (mp > 1024) get 1024-thread CTAs so that

@@ -97,7 +97,7 @@ struct dbslmm_b200_handle {
     int64_t n_snp = 0;
     int32_t n_ref = 0, pitch = 0, n_pad = 0;
     // workspace
-    DevBuf codes, sigma, lbuf, rowN, rowS, rowR, planblob, beta, status, intQ, intA, intN, scratch, counters;
+    DevBuf codes, sigma, lbuf, rowN, rowS, rowR, planblob, beta, status, intQ, intA, intN, scratch, counters, wbuf;
     PinBuf h_blob, h_out;
     Plan plan;
     int32_t last_flags = 0, last_solver = 0, last_nfolds = 0;
@@ -366,7 +366,7 @@ void dbslmm_b200_destroy(dbslmm_b200_handle* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     DevBuf* bufs[] = {&h->bed, &h->stats, &h->codes, &h->sigma, &h->lbuf, &h->rowN, &h->rowS, &h->rowR,
-                      &h->planblob, &h->beta, &h->status, &h->intQ, &h->intA, &h->intN, &h->scratch, &h->counters};
+                      &h->planblob, &h->beta, &h->status, &h->intQ, &h->intA, &h->intN, &h->scratch, &h->counters, &h->wbuf};
     for (DevBuf* b : bufs) b->release();
     h->h_blob.release();
     h->h_out.release();
@@ -488,6 +488,7 @@ int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
     CU_TRY(h, h->status.ensure(sizeof(int32_t) * (size_t)std::max(2 * nb, 1)));
     if (!pcg) {
         CU_TRY(h, h->scratch.ensure(sizeof(double) * (size_t)std::max<int64_t>(P.scratch_doubles, 1)));
+        CU_TRY(h, h->wbuf.ensure(sizeof(double) * 64 * 64 * (size_t)std::max(nb, 1)));
         CU_TRY(h, h->counters.ensure(sizeof(int32_t) * (size_t)std::max(P.n_groups, 1)));
     }
     if (keep_int) {
@@ -591,10 +592,11 @@ int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
                 for (size_t k = 0; k < P.steps[c].size(); ++k) {
                     const StepList& s = P.steps[c][k];
                     CU_TRY(h, launch_chol_diag(d_blocks, d_diag + s.diag_off, s.n_diag, (int32_t)k,
-                                               (const double*)h->sigma.p, (double*)h->lbuf.p, ridge, d_status, cs));
+                                               (const double*)h->sigma.p, (double*)h->lbuf.p, (double*)h->wbuf.p, ridge,
+                                               d_status, cs));
                     CU_TRY(h, launch_chol_panel(d_blocks, d_panel + s.panel_off, s.n_panel, (int32_t)k,
-                                                (const double*)h->sigma.p, (double*)h->lbuf.p, ridge,
-                                                (double*)h->scratch.p + P.scratch_off[c], (int32_t*)h->counters.p,
+                                                (const double*)h->sigma.p, (double*)h->lbuf.p, (const double*)h->wbuf.p,
+                                                ridge, (double*)h->scratch.p + P.scratch_off[c], (int32_t*)h->counters.p,
                                                 s.group_base, cs));
                     n_launch += 2;
                     n_chol_launch += 2;
