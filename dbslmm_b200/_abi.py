@@ -20,7 +20,7 @@ FLAG_PLAN_CACHED = 4
 EXPORTS = [
     "dbslmm_b200_abi_version", "dbslmm_b200_device_count", "dbslmm_b200_create", "dbslmm_b200_destroy",
     "dbslmm_b200_last_error", "dbslmm_b200_load_bed", "dbslmm_b200_snp_stats", "dbslmm_b200_plan_shards",
-    "dbslmm_b200_fit", "dbslmm_b200_get_row_codes", "dbslmm_b200_get_block_sigma",
+    "dbslmm_b200_fit", "dbslmm_b200_score", "dbslmm_b200_get_row_codes", "dbslmm_b200_get_block_sigma",
     "dbslmm_b200_get_block_gram", "dbslmm_b200_get_block_iters",
 ]
 
@@ -67,6 +67,8 @@ def load():
         lib.dbslmm_b200_plan_shards.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                                 C.c_void_p, C.c_void_p]
         lib.dbslmm_b200_fit.argtypes = [C.c_void_p, C.POINTER(FitArgs)]
+        lib.dbslmm_b200_score.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,
+                                          C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_float)]
         lib.dbslmm_b200_get_row_codes.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32]
         lib.dbslmm_b200_get_block_sigma.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         lib.dbslmm_b200_get_block_gram.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -166,6 +168,20 @@ class Engine:
         rc = self._check(self.lib.dbslmm_b200_fit(self.h, C.byref(a)), "fit")
         return {"beta_s": beta_s, "beta_l": None if beta_l is None else beta_l[:, :nl], "status": status[:nb],
                 "n_bad": rc, "timing": tm.as_dict()}
+
+    def score(self, bed_val, n_val, pos, beta, flip=None):
+        """PRS over a validation panel: returns (scores[n_folds, n_val], kernel_ms)."""
+        bed_val = np.ascontiguousarray(bed_val, np.uint8)
+        pitch = (n_val + 3) // 4
+        n_snp_val = bed_val.size // pitch
+        pos = np.ascontiguousarray(pos, np.int32)
+        beta = np.ascontiguousarray(np.atleast_2d(beta), np.float64)
+        fl = None if flip is None else np.ascontiguousarray(flip, np.uint8)
+        out = np.zeros((beta.shape[0], n_val), np.float64)
+        ms = C.c_float(0)
+        self._check(self.lib.dbslmm_b200_score(self.h, bed_val.ctypes.data, n_snp_val, n_val, pos.ctypes.data, _ptr(fl),
+                                               pos.size, beta.ctypes.data, beta.shape[0], out.ctypes.data, C.byref(ms)), "score")
+        return out, ms.value
 
     # ---- inspection hooks (parity tests)
     def row_codes(self, row, n):

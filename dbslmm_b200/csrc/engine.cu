@@ -97,7 +97,7 @@ struct dbslmm_b200_handle {
     int64_t n_snp = 0;
     int32_t n_ref = 0, pitch = 0, n_pad = 0;
     // workspace
-    DevBuf codes, sigma, lbuf, rowN, rowS, rowR, planblob, beta, status, intQ, intA, intN, scratch, counters, wbuf;
+    DevBuf codes, sigma, lbuf, rowN, rowS, rowR, planblob, beta, status, intQ, intA, intN, scratch, counters, wbuf, vbed, vstats, vwork;
     PinBuf h_blob, h_out;
     Plan plan;
     int32_t last_flags = 0, last_solver = 0, last_nfolds = 0;
@@ -366,7 +366,7 @@ void dbslmm_b200_destroy(dbslmm_b200_handle* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     DevBuf* bufs[] = {&h->bed, &h->stats, &h->codes, &h->sigma, &h->lbuf, &h->rowN, &h->rowS, &h->rowR,
-                      &h->planblob, &h->beta, &h->status, &h->intQ, &h->intA, &h->intN, &h->scratch, &h->counters, &h->wbuf};
+                      &h->planblob, &h->beta, &h->status, &h->intQ, &h->intA, &h->intN, &h->scratch, &h->counters, &h->wbuf, &h->vbed, &h->vstats, &h->vwork};
     for (DevBuf* b : bufs) b->release();
     h->h_blob.release();
     h->h_out.release();
@@ -668,6 +668,56 @@ int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
         t->decode_bytes = P.decode_bytes;
     }
     return n_bad;
+}
+
+int dbslmm_b200_score(dbslmm_b200_handle* h, const uint8_t* bed_val, int64_t n_snp_val, int32_t n_val,
+                      const int32_t* pos, const uint8_t* flip, int64_t n_scored, const double* beta,
+                      int32_t n_folds, double* scores_out, float* kernel_ms_out) {
+    if (!h) return DBSLMM_B200_ERR_ARG;
+    if (!bed_val || n_snp_val <= 0 || n_val <= 0 || n_scored < 0 || n_folds < 1 || !scores_out || (n_scored > 0 && (!pos || !beta)))
+        return fail(h, DBSLMM_B200_ERR_ARG, "score: bad arguments");
+    if (n_scored > INT32_MAX) return fail(h, DBSLMM_B200_ERR_ARG, "score: too many SNPs");
+    for (int64_t j = 0; j < n_scored; ++j)
+        if (pos[j] < 0 || pos[j] >= n_snp_val) return fail(h, DBSLMM_B200_ERR_ARG, "score: pos out of range of the validation .bed");
+    CU_TRY(h, cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const int32_t pitch = (n_val + 3) / 4;
+    const size_t bytes = (size_t)n_snp_val * pitch;
+    const int n_chunks = std::max(1, std::min<int>(4 * h->n_sm / std::max(1, (pitch + 255) / 256), (int)((n_scored + 63) / 64)));
+    const int nf_pass = std::min(n_folds, 4);
+    // work buffer: pos | flip | beta | partial | scores
+    size_t o = 0;
+    auto place = [&](size_t b) { size_t r = o; o = align_up(o + b, 256); return r; };
+    const size_t o_pos = place(sizeof(int32_t) * (size_t)n_scored), o_flip = place((size_t)n_scored),
+                 o_beta = place(sizeof(double) * (size_t)n_scored * n_folds),
+                 o_part = place(sizeof(double) * (size_t)n_chunks * nf_pass * n_val),
+                 o_sc = place(sizeof(double) * (size_t)n_folds * n_val);
+    CU_TRY(h, h->vbed.ensure(bytes + 64));
+    CU_TRY(h, h->vstats.ensure(sizeof(SnpStat) * (size_t)n_snp_val));
+    CU_TRY(h, h->vwork.ensure(o));
+    uint8_t* w = (uint8_t*)h->vwork.p;
+    CU_TRY(h, cudaMemcpyAsync(h->vbed.p, bed_val, bytes, cudaMemcpyHostToDevice, st));
+    CU_TRY(h, cudaMemsetAsync((uint8_t*)h->vbed.p + bytes, 0xFF, 64, st));
+    if (n_scored) {
+        CU_TRY(h, cudaMemcpyAsync(w + o_pos, pos, sizeof(int32_t) * (size_t)n_scored, cudaMemcpyHostToDevice, st));
+        if (flip) CU_TRY(h, cudaMemcpyAsync(w + o_flip, flip, (size_t)n_scored, cudaMemcpyHostToDevice, st));
+        CU_TRY(h, cudaMemcpyAsync(w + o_beta, beta, sizeof(double) * (size_t)n_scored * n_folds, cudaMemcpyHostToDevice, st));
+    }
+    CU_TRY(h, launch_snp_stats((const uint8_t*)h->vbed.p, n_snp_val, n_val, (SnpStat*)h->vstats.p, h->n_sm, st));
+    CU_TRY(h, cudaMemsetAsync(w + o_sc, 0, sizeof(double) * (size_t)n_folds * n_val, st));
+    CU_TRY(h, cudaEventRecord(h->ev[0], st));
+    for (int f0 = 0; f0 < n_folds; f0 += 4) {
+        const int nf = std::min(4, n_folds - f0);
+        CU_TRY(h, launch_prs((const uint8_t*)h->vbed.p, n_val, (const SnpStat*)h->vstats.p, (const int32_t*)(w + o_pos),
+                             flip ? (const uint8_t*)(w + o_flip) : nullptr, (const double*)(w + o_beta) + (size_t)f0 * n_scored,
+                             n_scored, (int32_t)n_scored, nf, n_chunks, (double*)(w + o_part),
+                             (double*)(w + o_sc) + (size_t)f0 * n_val, st));
+    }
+    CU_TRY(h, cudaEventRecord(h->ev[1], st));
+    CU_TRY(h, cudaMemcpyAsync(scores_out, w + o_sc, sizeof(double) * (size_t)n_folds * n_val, cudaMemcpyDeviceToHost, st));
+    CU_TRY(h, cudaStreamSynchronize(st));
+    if (kernel_ms_out) cudaEventElapsedTime(kernel_ms_out, h->ev[0], h->ev[1]);
+    return DBSLMM_B200_OK;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -56,6 +56,11 @@ cudaError_t launch_backsolve(const BlockDesc* blocks, const int32_t* order, int3
                              cudaStream_t st);
 cudaError_t chol_configure();
 
+// score.cu
+cudaError_t launch_prs(const uint8_t* bed, int32_t n_val, const SnpStat* stats, const int32_t* pos, const uint8_t* flip,
+                       const double* beta, int64_t beta_stride, int32_t n_scored, int32_t nf, int32_t n_chunks,
+                       double* partial, double* scores, cudaStream_t st);
+
 // pcg.cu
 struct PcgArgs {
     const BlockDesc* blocks;

@@ -1,0 +1,120 @@
+// score.cu -- polygenic-score accumulation over a validation panel (BASELINE config 4).
+//
+// Replaces the `plink --bfile val --score <eff>.txt 1 2 4 sum` step that the reference's driver runs
+// once per heritability fold (DBSLMM_script.sh:87, scored column 4 = beta / sqrt(2 maf (1-maf)) written
+// by scr/dbslmm.cpp:354-362): score_i = sum_j beta_j * dosage_ij, dosage = copies of the scored
+// allele, missing calls mean-imputed (PLINK's default), all folds in ONE pass over the 2-bit .bed.
+// PLINK is external to the reference, so this path's parity is pinned only against a numpy
+// restatement of those documented semantics (tests/test_gpu_score.py).
+//
+// HBM-bound by design: every .bed byte is read once (coalesced, 1 byte = 4 individuals per thread),
+// per-chunk partial sums are written to a scratch buffer and reduced in a fixed order (deterministic).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace dbslmm {
+
+static constexpr int kScoreThreads = 256;
+static constexpr int kMaxFolds = 4;          // folds per pass (more folds => several passes)
+
+template <int NF>
+__global__ void __launch_bounds__(kScoreThreads)
+prs_partial_kernel(const uint8_t* __restrict__ bed, int32_t pitch, int32_t n_val, const SnpStat* __restrict__ stats,
+                   const int32_t* __restrict__ pos, const uint8_t* __restrict__ flip, const double* __restrict__ beta,
+                   int64_t beta_stride, int32_t n_scored, int32_t rows_per_chunk, double* __restrict__ partial) {
+    __shared__ double s_beta[64][NF];
+    __shared__ double s_mu[64];
+    __shared__ int32_t s_row[64];
+    __shared__ uint8_t s_flip[64];
+    const int tid = threadIdx.x;
+    const int byte_col = blockIdx.x * kScoreThreads + tid;
+    const bool in_range = byte_col < pitch;
+    const int s_begin = blockIdx.y * rows_per_chunk;
+    const int s_end = min(n_scored, s_begin + rows_per_chunk);
+    double acc[4][NF];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int f = 0; f < NF; ++f) acc[q][f] = 0.0;
+    for (int s0 = s_begin; s0 < s_end; s0 += 64) {
+        const int nb = min(64, s_end - s0);
+        __syncthreads();
+        if (tid < nb) {
+            const int row = pos[s0 + tid];
+            const SnpStat st = stats[row];
+            const bool fl = flip != nullptr && flip[s0 + tid] != 0;
+            const double mu = (double)st.sum / (double)st.n_nonmiss;        // mean A1 dosage of called genotypes
+            s_row[tid] = row;
+            s_flip[tid] = fl ? 1 : 0;
+            s_mu[tid] = fl ? 2.0 - mu : mu;
+#pragma unroll
+            for (int f = 0; f < NF; ++f) s_beta[tid][f] = beta[(int64_t)f * beta_stride + s0 + tid];
+        }
+        __syncthreads();
+        if (!in_range) continue;
+        uint8_t bytes[8];
+        for (int j0 = 0; j0 < nb; j0 += 8) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                bytes[u] = (j0 + u < nb) ? bed[(size_t)s_row[j0 + u] * pitch + byte_col] : (uint8_t)0xFF;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (j0 + u >= nb) break;
+                const unsigned b = bytes[u];
+                const bool fl = s_flip[j0 + u] != 0;
+                const double mu = s_mu[j0 + u];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const unsigned c = (b >> (2 * q)) & 3u;
+                    // A1 copies: code 0 -> 2, 2 -> 1, 3 -> 0, 1 -> missing (dtpr.cpp:329-350)
+                    double d = (c == 0u) ? 2.0 : (c == 2u) ? 1.0 : 0.0;
+                    if (fl) d = 2.0 - d;
+                    if (c == 1u) d = mu;
+#pragma unroll
+                    for (int f = 0; f < NF; ++f) acc[q][f] += s_beta[j0 + u][f] * d;
+                }
+            }
+        }
+    }
+    if (!in_range) return;
+#pragma unroll
+    for (int f = 0; f < NF; ++f)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int ind = byte_col * 4 + q;
+            if (ind < n_val) partial[((size_t)blockIdx.y * NF + f) * n_val + ind] = acc[q][f];
+        }
+}
+
+__global__ void prs_reduce_kernel(const double* __restrict__ partial, int32_t n_chunks, int32_t nf, int32_t n_val,
+                                  double* __restrict__ scores) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = blockIdx.y;
+    if (i >= n_val) return;
+    double s = 0.0;
+    for (int c = 0; c < n_chunks; ++c) s += partial[((size_t)c * nf + f) * n_val + i];
+    scores[(size_t)f * n_val + i] = s;
+}
+
+cudaError_t launch_prs(const uint8_t* bed, int32_t n_val, const SnpStat* stats, const int32_t* pos, const uint8_t* flip,
+                       const double* beta, int64_t beta_stride, int32_t n_scored, int32_t nf, int32_t n_chunks,
+                       double* partial, double* scores, cudaStream_t st) {
+    if (n_scored == 0 || nf == 0) return cudaSuccess;
+    const int32_t pitch = (n_val + 3) / 4;
+    const int rows_per_chunk = (n_scored + n_chunks - 1) / n_chunks;
+    dim3 grid((pitch + kScoreThreads - 1) / kScoreThreads, n_chunks);
+    switch (nf) {
+        case 1: prs_partial_kernel<1><<<grid, kScoreThreads, 0, st>>>(bed, pitch, n_val, stats, pos, flip, beta, beta_stride, n_scored, rows_per_chunk, partial); break;
+        case 2: prs_partial_kernel<2><<<grid, kScoreThreads, 0, st>>>(bed, pitch, n_val, stats, pos, flip, beta, beta_stride, n_scored, rows_per_chunk, partial); break;
+        case 3: prs_partial_kernel<3><<<grid, kScoreThreads, 0, st>>>(bed, pitch, n_val, stats, pos, flip, beta, beta_stride, n_scored, rows_per_chunk, partial); break;
+        case 4: prs_partial_kernel<4><<<grid, kScoreThreads, 0, st>>>(bed, pitch, n_val, stats, pos, flip, beta, beta_stride, n_scored, rows_per_chunk, partial); break;
+        default: return cudaErrorInvalidValue;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    dim3 rgrid((n_val + 255) / 256, nf);
+    prs_reduce_kernel<<<rgrid, 256, 0, st>>>(partial, n_chunks, nf, n_val, scores);
+    return cudaGetLastError();
+}
+
+}  // namespace dbslmm

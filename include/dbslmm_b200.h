@@ -117,6 +117,16 @@ DBSLMM_B200_API int  dbslmm_b200_plan_shards(int32_t n_blocks, const int32_t* m_
 
 DBSLMM_B200_API int  dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* args);
 
+/* Polygenic scores over a validation panel (BASELINE config 4; replaces the per-fold
+ * `plink --score <eff>.txt 1 2 4 sum` of DBSLMM_script.sh:87): score[f][i] = sum_j beta[f][j] * dosage_ij,
+ * dosage = copies of A1 (or of A2 where flip[j] != 0) of validation .bed row pos[j], missing calls
+ * mean-imputed.  `bed_val` is a host SNP-major .bed payload (after the magic bytes) of n_snp_val rows and
+ * n_val individuals; it is uploaded, scored for all n_folds in one pass and left resident until the next
+ * call.  flip may be NULL.  scores_out is [n_folds][n_val]. */
+DBSLMM_B200_API int  dbslmm_b200_score(dbslmm_b200_handle* h, const uint8_t* bed_val, int64_t n_snp_val, int32_t n_val,
+                       const int32_t* pos, const uint8_t* flip, int64_t n_scored,
+                       const double* beta, int32_t n_folds, double* scores_out, float* kernel_ms_out);
+
 /* ---- inspection hooks used by the parity tests (operate on the state of the last fit) ---- */
 /* int8 codes of one decoded row of the last fit (row = global row index in block order:
  * block b's rows are its small SNPs then its large SNPs); n_pad bytes. */

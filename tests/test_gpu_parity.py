@@ -195,3 +195,63 @@ def test_full_size_properties(engine):
         x = r["beta_s"][0][lo:hi] * np.sqrt(n_obs)
         res = np.abs(K @ x - z[lo:hi]).max() / np.abs(z[lo:hi]).max()
         assert res < 1e-11, res
+
+
+def test_config5_large_reference_panel(engine):
+    """BASELINE config 5 (n_ref = 20,000): pitch 5,000 B rows, n_pad 20,096, Gram entries up to 4 n = 80,000."""
+    n_ref = 20000
+    w = synth.make_workload(55, [260, 70], n_ref, missing_rate=0.0, frac_large=0.0)
+    engine.load_bed(w["bed"], n_ref)
+    maf, nn = engine.snp_stats()
+    assert np.array_equal(nn, np.full(330, n_ref))
+    r = engine.fit(w["s_off"], w["s_pos"], w["s_z"], sigma_s=[0.5 / 1e5], n_obs=300_000, flags=_abi.FLAG_KEEP_INT_GRAM)
+    assert r["n_bad"] == 0
+    pos = np.arange(260, dtype=np.int32)
+    Q, A, N = engine.block_gram(0, 260)
+    Qo, Ao, No = O.gram_int(w["bed"], n_ref, pos)
+    assert np.array_equal(Q, Qo) and np.array_equal(A, Ao) and np.array_equal(N, No)
+    # the reference float path sums 20,000 rounded products per entry: ITS rounding error grows like sqrt(n) eps, so
+    # the bar is 1e-12 here (the kernel's integer numerator is exact at any n)
+    dS = np.abs(engine.block_sigma(0, 260) - O.sigma(w["bed"], n_ref, pos)).max()
+    assert dS <= 1e-12, dS
+    bs, _, _, _ = O.est(w["bed"], n_ref, 300_000, 0.5 / 1e5, w["s_off"], w["s_pos"], w["s_z"], threads=4, mode=O.MODE_EXACT)
+    assert relmax(r["beta_s"][0], bs) <= 1e-10
+
+
+def test_config5_large_block(engine):
+    """A 5,000-SNP block (79 panels, split-K steps, 1024-thread back substitution): residual of K x = z."""
+    m, n_ref = 5000, 800
+    rng = np.random.default_rng(50)
+    G = synth.make_genotypes(rng, [m], n_ref)
+    engine.load_bed(synth.pack_bed(G), n_ref)
+    z = rng.standard_normal(m)
+    sig, n_obs = 0.5 / 1e5, 200_000
+    r = engine.fit(np.array([0, m], np.int32), np.arange(m, dtype=np.int32), z, sigma_s=[sig], n_obs=n_obs, flags=_abi.FLAG_FULL_SIGMA)
+    assert r["n_bad"] == 0
+    S = engine.block_sigma(0, m)
+    assert np.array_equal(S, S.T)
+    K = S + np.eye(m) / (sig * n_obs)
+    x = r["beta_s"][0] * np.sqrt(n_obs)
+    assert np.abs(K @ x - z).max() / np.abs(z).max() < 1e-10
+
+
+def test_config2_lmm_chr1(engine):
+    """BASELINE config 2: LMM mode on chr1-sized data (133 EUR LD blocks, ~90k SNPs, n_ref = 500)."""
+    sizes = synth.eur_block_sizes(90_000, 3000, chroms=[1])
+    assert sizes.size == 133
+    n_ref = 500
+    rng = np.random.default_rng(2)
+    G = synth.make_genotypes(rng, sizes, n_ref)
+    bed = synth.pack_bed(G)
+    engine.load_bed(bed, n_ref)
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    pos = np.arange(off[-1], dtype=np.int32)
+    z = rng.standard_normal(off[-1]) * 1.5
+    sig, n_obs = 0.5 / off[-1], 300_000
+    r = engine.fit(off, pos, z, sigma_s=[sig], n_obs=n_obs)
+    assert r["n_bad"] == 0 and np.isfinite(r["beta_s"]).all()
+    sample = list(range(0, 133, 12))
+    s_off = np.concatenate([[0], np.cumsum(sizes[sample])]).astype(np.int32)
+    s_pos = np.concatenate([pos[off[b]:off[b + 1]] for b in sample])
+    bs, _, _, _ = O.est(bed, n_ref, n_obs, sig, s_off, s_pos, z[s_pos], threads=8, mode=O.MODE_EXACT)
+    assert relmax(r["beta_s"][0][s_pos], bs) <= 1e-10
