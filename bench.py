@@ -351,7 +351,8 @@ def main():
     clocks = sampler.stop()
     n_bad = int(r["n_bad"])
 
-    # ---- end to end from host buffers (e2e): load_bed + fit, every step
+    # ---- end to end from host buffers (e2e): every step uploads the .bed shard (load_bed is asynchronous: the
+    # host builds the block plan while the panel crosses PCIe), runs the kernels and reads the betas back
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -415,7 +416,8 @@ def main():
                        "l2": "inputs larger than L2 (codes 2.2 GB, Sigma 8+ GB per step)"},
             "snps_per_s": snps_all * K / (dev_total * 1e-3),
             "e2e": {"value": e2e_v, "unit": "blocks/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": wall_e2e / K * 1e3},
+                    "ms_per_step": wall_e2e / K * 1e3,
+                    "how": "dbslmm_b200_load_bed (async H2D + stats) + dbslmm_b200_fit from host buffers, wall clock"},
             "resident_wall_ms_per_step": wall_resident / K * 1e3,
             "gpu_launches": int(sum(t["n_launches"] for t in tms)),
             "clocks": clocks, "roofline": roofline, "rooflines_other": other, "blocks_not_spd": n_bad}

@@ -190,8 +190,32 @@ decode_rows_kernel(const uint8_t* __restrict__ bed, int32_t n_ref, int32_t pitch
 }
 
 // ------------------------------------------------------------------------------------------
+// Per-block "has missing calls" flag from the per-SNP statistics: one warp per block over the block's
+// genotype rows.  Lets the host plan a fit without ever reading the panel or its statistics.
+// ------------------------------------------------------------------------------------------
+__global__ void block_missing_kernel(const BlockDesc* __restrict__ blocks, int32_t n_blocks,
+                                     const uint32_t* __restrict__ row_src, const SnpStat* __restrict__ stats,
+                                     int32_t n_ref, int32_t* __restrict__ flags) {
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= n_blocks) return;
+    const int lane = threadIdx.x & 31;
+    const BlockDesc bd = blocks[b];
+    int miss = 0;
+    for (int j = lane; j < bd.m; j += 32) miss |= (stats[row_src[bd.croff + j] & 0x7FFFFFFFu].n_nonmiss != n_ref);
+    miss = __any_sync(0xffffffffu, miss);
+    if (lane == 0) flags[b] = miss ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------
+cudaError_t launch_block_missing(const BlockDesc* blocks, int32_t n_blocks, const uint32_t* row_src,
+                                 const SnpStat* stats, int32_t n_ref, int32_t* flags, cudaStream_t st) {
+    if (n_blocks == 0) return cudaSuccess;
+    block_missing_kernel<<<(n_blocks + 7) / 8, 256, 0, st>>>(blocks, n_blocks, row_src, stats, n_ref, flags);
+    return cudaGetLastError();
+}
+
 static int stage_bytes(int32_t pitch) { return ((pitch + 15 + 16 + 15) / 16) * 16 + 16; }
 
 cudaError_t launch_snp_stats(const uint8_t* bed, int64_t n_snp, int32_t n_ref, SnpStat* stats, int n_sm,

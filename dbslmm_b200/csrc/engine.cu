@@ -93,7 +93,10 @@ struct dbslmm_b200_handle {
     std::string err;
     // reference panel
     DevBuf bed, stats;
-    std::vector<SnpStat> h_stats;
+    PinBuf h_stats;                      // per-SNP statistics, filled asynchronously by load_bed
+    cudaEvent_t ev_bed = nullptr;        // completes when the panel, its statistics and their host copy have landed
+    bool bed_pending = false;
+    std::vector<int32_t> miss_flags;     // per-block "has missing calls" of the current plan
     int64_t n_snp = 0;
     int32_t n_ref = 0, pitch = 0, n_pad = 0;
     // workspace
@@ -123,7 +126,8 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // ------------------------------------------------------------------------------------------
 // Plan construction (host): the block scheduler's bookkeeping
 // ------------------------------------------------------------------------------------------
-int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P) {
+// `miss` = per-block missing-call flags (nullptr: assume none; verified on the device, see fit)
+int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, const int32_t* miss_in) {
     const int nb = a->n_blocks;
     P = Plan();
     P.n_blocks = nb;
@@ -147,16 +151,14 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P) {
         d.out_s = a->s_off[b];
         d.out_l = a->l_off ? a->l_off[b] : 0;
         d.pad = 0;
-        int miss = 0;
+        const int miss = miss_in ? (miss_in[b] != 0) : 0;
         for (int j = 0; j < ms; ++j) {
             const int32_t p = a->s_pos[a->s_off[b] + j];
             if (p < 0 || p >= n_snp) return fail(h, DBSLMM_B200_ERR_ARG, "s_pos out of range of the loaded .bed");
-            miss |= (h->h_stats[p].n_nonmiss != h->n_ref);
         }
         for (int j = 0; j < ml; ++j) {
             const int32_t p = a->l_pos[a->l_off[b] + j];
             if (p < 0 || p >= n_snp) return fail(h, DBSLMM_B200_ERR_ARG, "l_pos out of range of the loaded .bed");
-            miss |= (h->h_stats[p].n_nonmiss != h->n_ref);
         }
         d.has_missing = miss;
         goff += d.m;
@@ -355,6 +357,7 @@ int dbslmm_b200_create(int device, dbslmm_b200_handle** out) {
     }
     for (int i = 0; i < 8 && ok; ++i) ok = cudaEventCreate(&h->ev[i]) == cudaSuccess;
     ok = ok && cudaEventCreate(&h->ev_fork) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->ev_bed, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && chol_configure() == cudaSuccess;
     if (!ok) { dbslmm_b200_destroy(h); return DBSLMM_B200_ERR_CUDA; }
     *out = h;
@@ -370,6 +373,8 @@ void dbslmm_b200_destroy(dbslmm_b200_handle* h) {
     for (DevBuf* b : bufs) b->release();
     h->h_blob.release();
     h->h_out.release();
+    h->h_stats.release();
+    if (h->ev_bed) cudaEventDestroy(h->ev_bed);
     for (int i = 0; i < 8; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     for (int c = 0; c < kNumClasses; ++c) {
@@ -386,6 +391,7 @@ int dbslmm_b200_load_bed(dbslmm_b200_handle* h, const uint8_t* bed, int64_t n_sn
     if (!h) return DBSLMM_B200_ERR_ARG;
     if (!bed || n_snp <= 0 || n_ref <= 1) return fail(h, DBSLMM_B200_ERR_ARG, "load_bed: bad arguments");
     CU_TRY(h, cudaSetDevice(h->device));
+    if (h->bed_pending) { CU_TRY(h, cudaEventSynchronize(h->ev_bed)); h->bed_pending = false; }   // buffers may be re-allocated
     const int32_t pitch = (n_ref + 3) / 4;
     const size_t bytes = (size_t)n_snp * pitch;
     CU_TRY(h, h->bed.ensure(bytes + 64));
@@ -393,10 +399,13 @@ int dbslmm_b200_load_bed(dbslmm_b200_handle* h, const uint8_t* bed, int64_t n_sn
     CU_TRY(h, cudaMemcpyAsync(h->bed.p, bed, bytes, cudaMemcpyHostToDevice, h->stream));
     CU_TRY(h, cudaMemsetAsync((uint8_t*)h->bed.p + bytes, 0xFF, 64, h->stream));
     CU_TRY(h, launch_snp_stats((const uint8_t*)h->bed.p, n_snp, n_ref, (SnpStat*)h->stats.p, h->n_sm, h->stream));
-    h->h_stats.resize((size_t)n_snp);
-    CU_TRY(h, cudaMemcpyAsync(h->h_stats.data(), h->stats.p, sizeof(SnpStat) * (size_t)n_snp, cudaMemcpyDeviceToHost,
-                              h->stream));
-    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    // Asynchronous from here on: the call returns while the panel is still crossing PCIe, so the caller's
+    // next step (dbslmm_b200_fit builds its block plan on the host) overlaps the upload.  The per-SNP
+    // statistics follow the panel back to pinned host memory; snp_stats() waits for them.
+    CU_TRY(h, h->h_stats.ensure(sizeof(SnpStat) * (size_t)n_snp));
+    CU_TRY(h, cudaMemcpyAsync(h->h_stats.p, h->stats.p, sizeof(SnpStat) * (size_t)n_snp, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaEventRecord(h->ev_bed, h->stream));
+    h->bed_pending = true;
     h->n_snp = n_snp;
     h->n_ref = n_ref;
     h->pitch = pitch;
@@ -408,8 +417,11 @@ int dbslmm_b200_load_bed(dbslmm_b200_handle* h, const uint8_t* bed, int64_t n_sn
 int dbslmm_b200_snp_stats(dbslmm_b200_handle* h, double* maf_out, int32_t* n_nonmiss_out) {
     if (!h) return DBSLMM_B200_ERR_ARG;
     if (h->n_snp == 0) return fail(h, DBSLMM_B200_ERR_STATE, "snp_stats before load_bed");
+    CU_TRY(h, cudaSetDevice(h->device));
+    if (h->bed_pending) { CU_TRY(h, cudaEventSynchronize(h->ev_bed)); h->bed_pending = false; }
+    const SnpStat* hs = (const SnpStat*)h->h_stats.p;
     for (int64_t i = 0; i < h->n_snp; ++i) {
-        const SnpStat& s = h->h_stats[(size_t)i];
+        const SnpStat& s = hs[(size_t)i];
         if (maf_out) {
             // readSNPIm (dtpr.cpp:358-362): mean-impute, af = sum(geno) / (2 n) = S / (2 n_i)
             const double af = 0.5 * (double)s.sum / (double)s.n_nonmiss;
@@ -469,7 +481,11 @@ int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
     const bool reuse = (a->flags & DBSLMM_B200_FLAG_PLAN_CACHED) && P.valid && P.n_blocks == a->n_blocks &&
                        P.tot_s == a->s_off[a->n_blocks] && P.tot_l == (a->l_off ? a->l_off[a->n_blocks] : 0);
     if (!reuse) {
-        int rc = build_plan(h, a, P);
+        // The plan is built while load_bed's upload may still be in flight, so it cannot look at the panel:
+        // it assumes no block has missing calls; block_missing_kernel checks that on the device (below) and
+        // the plan is rebuilt with the true flags in the rare case the assumption fails.
+        h->miss_flags.assign((size_t)std::max(a->n_blocks, 1), 0);
+        int rc = build_plan(h, a, P, nullptr);
         if (rc != DBSLMM_B200_OK) { P.valid = false; return rc; }
     }
     const int nb = P.n_blocks;
@@ -499,7 +515,7 @@ int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
     const size_t out_bytes = sizeof(double) * n_out * nfold + sizeof(int32_t) * (size_t)(2 * nb);
     CU_TRY(h, h->h_out.ensure(out_bytes + 64));
 
-    uint8_t* dblob = (uint8_t*)h->planblob.p;
+    uint8_t* dblob = (uint8_t*)h->planblob.p;   // (re-pointed below if the plan has to be rebuilt)
     const BlockDesc* d_blocks = (const BlockDesc*)(dblob + P.o_blocks);
     const uint32_t* d_rowsrc = (const uint32_t*)(dblob + P.o_rowsrc);
     const int32_t* d_rowg = (const int32_t*)(dblob + P.o_rowg);
@@ -529,6 +545,36 @@ int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
         CU_TRY(h, cudaMemcpyAsync(dblob + P.o_z, z, sizeof(double) * (size_t)P.n_snp_rows, cudaMemcpyHostToDevice, st));
     }
     CU_TRY(h, cudaMemsetAsync(d_status, 0, sizeof(int32_t) * (size_t)std::max(2 * nb, 1), st));
+    if (!reuse && nb > 0 && P.n_code_rows > 0) {
+        // verify the no-missing assumption: per-block flags from the device statistics (1 int per block)
+        int32_t* hflags = (int32_t*)h->h_out.p;
+        CU_TRY(h, launch_block_missing(d_blocks, nb, d_rowsrc, (const SnpStat*)h->stats.p, h->n_ref, d_iters, st));
+        CU_TRY(h, cudaMemcpyAsync(hflags, d_iters, sizeof(int32_t) * (size_t)nb, cudaMemcpyDeviceToHost, st));
+        CU_TRY(h, cudaStreamSynchronize(st));
+        h->bed_pending = false;
+        bool any = false;
+        for (int b = 0; b < nb; ++b) any = any || (hflags[b] != 0);
+        if (any) {
+            h->miss_flags.assign(hflags, hflags + nb);
+            int rc = build_plan(h, a, P, h->miss_flags.data());
+            if (rc != DBSLMM_B200_OK) { P.valid = false; return rc; }
+            // buffers sized from the speculative plan may be too small now: re-run the sizing + upload
+            CU_TRY(h, h->planblob.ensure(P.blob_bytes + 256));
+            CU_TRY(h, h->codes.ensure((size_t)std::max<int64_t>(P.n_code_rows, 1) * h->n_pad));
+            dblob = (uint8_t*)h->planblob.p;
+            d_blocks = (const BlockDesc*)(dblob + P.o_blocks);
+            d_rowsrc = (const uint32_t*)(dblob + P.o_rowsrc);
+            d_rowg = (const int32_t*)(dblob + P.o_rowg);
+            d_z = (const double*)(dblob + P.o_z);
+            d_tiles_plain = (const GramTile*)(dblob + P.o_tiles_plain);
+            d_tiles_miss = (const GramTile*)(dblob + P.o_tiles_miss);
+            d_order = (const int32_t*)(dblob + P.o_order);
+            d_diag = (const int32_t*)(dblob + P.o_diag);
+            d_panel = (const int4*)(dblob + P.o_panel);
+            CU_TRY(h, cudaMemcpyAsync(dblob, h->h_blob.p, P.blob_bytes, cudaMemcpyHostToDevice, st));
+            CU_TRY(h, cudaMemsetAsync(d_status, 0, sizeof(int32_t) * (size_t)std::max(2 * nb, 1), st));
+        }
+    }
     CU_TRY(h, cudaEventRecord(h->ev[1], st));
 
     // ---- decode
