@@ -18,6 +18,7 @@
 //   warps 2-5 epilogue: tcgen05.ld -> FP64 transform -> coalesced stores of the LOWER tile.
 // The A operand is the J (column) side and the B operand the I (row) side, so a TMEM lane
 // holds one Sigma column and consecutive lanes store consecutive addresses of one Sigma row.
+#include <algorithm>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -213,13 +214,156 @@ gram_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs a) {
     if (warp == 1) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
 }
 
+// ------------------------------------------------------------------------------------------
+// Persistent variant for blocks WITHOUT missing calls (one accumulator plane): one CTA per SM walks
+// the tile list; the s32 accumulator is double-buffered in TMEM (2 x 128 columns) so the FP64
+// epilogue of tile i (8 warps) overlaps the TMA/MMA main loop of tile i+1, and a 5-stage smem
+// ring keeps more TMA requests in flight.  Same arithmetic as gram_kernel<1>.
+//   warp 0: TMA producer   warp 1: TMEM alloc + MMA issuer   warps 2-9: epilogue
+//   (TMEM lane quarter = warp % 4, column half = (warp - 2) / 4)
+// ------------------------------------------------------------------------------------------
+static constexpr int kPStages = 5;
+static constexpr int kPThreads = 320;
+static constexpr int kPSmem = kPStages * 2 * kTileBytes + 1024;
+
+__global__ void __launch_bounds__(kPThreads, 1)
+gram_persistent_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[kPStages], empty_bar[kPStages], acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int nk = a.nk;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kPStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
+        mbar_fence_init();
+        tma_prefetch_desc(&tmap);
+    }
+    if (warp == 1) tmem_alloc<256>(&tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile_i = blockIdx.x; tile_i < a.n_tiles; tile_i += gridDim.x) {
+                const GramTile tile = a.tiles[tile_i];
+                const BlockDesc bd = a.blocks[tile.blk];
+                const bool diag = (tile.ti == tile.tj);
+                const int32_t rowJ = bd.croff + tile.tj * kTile, rowI = bd.croff + tile.ti * kTile;
+                const uint32_t bytes = (uint32_t)((diag ? 1 : 2) * kTileBytes);
+                for (int ks = 0; ks < nk; ++ks, ++it) {
+                    const int s = it % kPStages;
+                    const uint32_t ph = (it / kPStages) & 1u;
+                    mbar_wait(&empty_bar[s], ph ^ 1u);
+                    uint8_t* st = smem + (size_t)s * 2 * kTileBytes;
+                    mbar_expect_tx(&full_bar[s], bytes);
+                    tma_load_2d(st, &tmap, ks * 128, rowJ, &full_bar[s]);
+                    if (!diag) tma_load_2d(st + kTileBytes, &tmap, ks * 128, rowI, &full_bar[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_i8_idesc(kTile, kTile);
+            uint32_t it = 0, lt = 0;
+            for (int tile_i = blockIdx.x; tile_i < a.n_tiles; tile_i += gridDim.x, ++lt) {
+                const GramTile tile = a.tiles[tile_i];
+                const bool diag = (tile.ti == tile.tj);
+                const uint32_t as = lt & 1u;
+                mbar_wait(&acc_empty[as], ((lt >> 1) & 1u) ^ 1u);      // epilogue has drained this accumulator
+                tc_fence_after();
+                for (int ks = 0; ks < nk; ++ks, ++it) {
+                    const int s = it % kPStages;
+                    const uint32_t ph = (it / kPStages) & 1u;
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t st = smem_u32(smem + (size_t)s * 2 * kTileBytes);
+                    const uint64_t dJ = make_sw128_kmajor_desc(st), dI = make_sw128_kmajor_desc(diag ? st : st + kTileBytes);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        umma_i8(tmem_base + as * kTile, dJ + (uint64_t)(kk * 2), dI + (uint64_t)(kk * 2), idesc,
+                                (ks > 0 || kk > 0) ? 1u : 0u);
+                    umma_commit(&empty_bar[s]);
+                }
+                umma_commit(&acc_full[as]);
+            }
+        }
+    } else {
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        const double dn = (double)a.n_ref;
+        uint32_t lt = 0;
+        for (int tile_i = blockIdx.x; tile_i < a.n_tiles; tile_i += gridDim.x, ++lt) {
+            const GramTile tile = a.tiles[tile_i];
+            const BlockDesc bd = a.blocks[tile.blk];
+            const uint32_t as = lt & 1u;
+            const int jl = tile.tj * kTile + q * 32 + lane;
+            double Sj = 0.0, rj = 0.0;
+            if (jl < bd.m) { Sj = (double)a.rowS[bd.goff + jl]; rj = a.rowR[bd.goff + jl] * dn; }
+            mbar_wait(&acc_full[as], (lt >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t tlane = tmem_base + as * kTile + ((uint32_t)(q * 32) << 16);
+            double* sig = a.sigma + bd.moff;
+            uint32_t v[2][32];
+            tmem_ld32(tlane + half * 64, v[0]);
+            tmem_ld32(tlane + half * 64 + 32, v[1]);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[as]);               // accumulator copied out: MMA may reuse it
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                const int ibase = tile.ti * kTile + half * 64 + ch * 32;
+                if (ibase >= bd.mp) break;
+                double Si_l = 0.0, ri_l = 0.0;
+                {
+                    const int il = ibase + lane;
+                    if (il < bd.m) { Si_l = (double)a.rowS[bd.goff + il]; ri_l = a.rowR[bd.goff + il]; }
+                }
+#pragma unroll
+                for (int r = 0; r < 32; ++r) {
+                    const int il = ibase + r;
+                    const double Si = __shfl_sync(0xffffffffu, Si_l, r);
+                    const double ri = __shfl_sync(0xffffffffu, ri_l, r);
+                    if (il >= bd.mp || jl > il) continue;
+                    double val;
+                    if (il < bd.m) {
+                        // n Q - S_i S_j is an exact integer below 2^53: one FMA, no rounding
+                        const double t = fma(-Si, Sj, dn * (double)(int32_t)v[ch][r]);
+                        val = t * ri * rj;
+                        if (il == jl) val += a.one_minus_tau;
+                    } else {
+                        val = (il == jl) ? 1.0 : 0.0;
+                    }
+                    sig[(size_t)il * bd.ld + jl] = val;
+                    if (a.full && jl < il) sig[(size_t)jl * bd.ld + il] = val;
+                    if (a.intQ != nullptr && il < bd.m) {
+                        a.intQ[(size_t)bd.moff + (size_t)il * bd.ld + jl] = (int32_t)v[ch][r];
+                        a.intQ[(size_t)bd.moff + (size_t)jl * bd.ld + il] = (int32_t)v[ch][r];
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<256>(tmem_base);
+}
+
 cudaError_t launch_gram(const CUtensorMap& tmap, const GramArgs& a, bool missing, cudaStream_t st) {
     if (a.n_tiles == 0) return cudaSuccess;
     cudaError_t e;
     if (!missing) {
-        e = cudaFuncSetAttribute(gram_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GramCfg<1>::kSmem);
+        e = cudaFuncSetAttribute(gram_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmem);
         if (e != cudaSuccess) return e;
-        gram_kernel<1><<<a.n_tiles, kGramThreads, GramCfg<1>::kSmem, st>>>(tmap, a);
+        int dev = 0, n_sm = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        gram_persistent_kernel<<<std::min(a.n_tiles, n_sm), kPThreads, kPSmem, st>>>(tmap, a);
     } else {
         e = cudaFuncSetAttribute(gram_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GramCfg<4>::kSmem);
         if (e != cudaSuccess) return e;
