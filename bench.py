@@ -203,7 +203,8 @@ def cpu_sample(w, cpu_seconds, threads):
     """Every k-th block (keeps the size distribution), sized for ~cpu_seconds of host work."""
     sizes = w["sizes"].astype(np.float64)
     n = w["n_ref"]
-    est = (2.0 * n * sizes ** 2 / 6e9 + 60 * 2 * sizes ** 2 / 2e9 + 1e-4).sum() / max(threads, 1)   # crude seconds
+    # calibrated on the GPU boxes' hosts: ~1.9 GFLOP/s per thread for the X'X loops, ~1 GFLOP/s for PCG mat-vecs
+    est = (2.0 * n * sizes ** 2 / 1.9e9 + 60 * 2 * sizes ** 2 / 1.0e9 + 1e-4).sum() / max(threads, 1)   # seconds
     stride = max(1, int(np.ceil(est / cpu_seconds)))
     return np.arange(0, sizes.size, stride), stride
 

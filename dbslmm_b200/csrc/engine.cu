@@ -663,7 +663,36 @@ int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
                 CU_TRY(h, cudaEventRecord(h->ev[5], st));
             }
         } else {
-            return fail(h, DBSLMM_B200_ERR_ARG, "PCG solver not built yet");
+            // reference-faithful Jacobi-PCG (pcg.cu): per-block scratch vectors live in `scratch`
+            std::vector<int64_t> woff((size_t)std::max(nb, 1), 0);
+            int64_t wtot = 0;
+            int32_t max_ms = 8;
+            for (int b = 0; b < nb; ++b) {
+                const int64_t ms = P.blocks[b].ms, ml = P.blocks[b].m - P.blocks[b].ms;
+                woff[b] = wtot;
+                wtot += 7 * ms + ms * ml + ml * ml + 7 * ml + 8;
+                max_ms = std::max<int32_t>(max_ms, (int32_t)std::max(ms, ml));
+            }
+            const size_t off_bytes = align_up(sizeof(int64_t) * (size_t)std::max(nb, 1), 256);
+            CU_TRY(h, h->scratch.ensure(off_bytes + sizeof(double) * (size_t)std::max<int64_t>(wtot, 1)));
+            CU_TRY(h, cudaMemcpyAsync(h->scratch.p, woff.data(), sizeof(int64_t) * (size_t)std::max(nb, 1), cudaMemcpyHostToDevice, st));
+            CU_TRY(h, cudaStreamSynchronize(st));          // woff is a stack-lifetime host vector
+            PcgArgs pa;
+            pa.blocks = d_blocks;
+            pa.order = d_order;
+            pa.n_blocks = nb;
+            pa.sigma = (const double*)h->sigma.p;
+            pa.work = (double*)((uint8_t*)h->scratch.p + off_bytes);
+            pa.work_off = (const int64_t*)h->scratch.p;
+            pa.ridge = ridge;
+            pa.sigma_s = a->sigma_s[f];
+            pa.n_obs = (double)a->n_obs;
+            pa.beta_s = bs;
+            pa.beta_l = bl;
+            pa.status = d_status;
+            pa.iters = d_iters;
+            CU_TRY(h, launch_pcg(pa, max_ms, st));
+            ++n_launch;
         }
     }
     CU_TRY(h, cudaEventRecord(h->ev[4], st));

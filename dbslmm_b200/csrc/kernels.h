@@ -80,6 +80,6 @@ struct PcgArgs {
     int32_t* status;
     int32_t* iters;
 };
-cudaError_t launch_pcg(const PcgArgs& a, cudaStream_t st);
+cudaError_t launch_pcg(const PcgArgs& a, int32_t max_ms, cudaStream_t st);
 
 }  // namespace dbslmm

@@ -255,3 +255,37 @@ def test_config2_lmm_chr1(engine):
     s_pos = np.concatenate([pos[off[b]:off[b + 1]] for b in sample])
     bs, _, _, _ = O.est(bed, n_ref, n_obs, sig, s_off, s_pos, z[s_pos], threads=8, mode=O.MODE_EXACT)
     assert relmax(r["beta_s"][0][s_pos], bs) <= 1e-10
+
+
+# ------------------------------------------------------------------------------------------
+# reference-faithful PCG solver (csrc/pcg.cu): same stopping rule as DBSLMMFIT::PCGv, so it lands on the
+# reference's truncated answers; agreement is limited by CG's sensitivity to summation order near the 1e-7
+# threshold (tests/test_oracle.py), never by the integer Gram.
+# ------------------------------------------------------------------------------------------
+def test_pcg_solver_matches_ref_mode_oracle(engine):
+    w = synth.make_workload(321, [210, 0, 1, 33, 140], 400, missing_rate=0.01, frac_large=0.03)
+    engine.load_bed(w["bed"], 400)
+    csr = (w["s_off"], w["s_pos"], w["s_z"], w["l_off"], w["l_pos"], w["l_z"])
+    sig, n_obs = 0.5 / 3000.0, 30_000
+    r = engine.fit(*csr, sigma_s=[sig], n_obs=n_obs, solver=_abi.SOLVER_PCG)
+    assert r["n_bad"] == 0
+    bs, bl, sing, it = O.est(w["bed"], 400, n_obs, sig, *csr, threads=4, mode=O.MODE_REF)
+    assert sing == 0
+    assert relmax(r["beta_s"][0], bs) <= 2e-7 and relmax(r["beta_l"][0], bl) <= 2e-7
+    its = [engine.block_iters(b) for b in range(5)]
+    assert abs(max(its) - it) <= 1 and its[1] == 0
+    # and it differs from the exact solve by the reference's own truncation error, not by more
+    be, ble, _, _ = O.est(w["bed"], 400, n_obs, sig, *csr, threads=4, mode=O.MODE_EXACT)
+    assert relmax(r["beta_s"][0], be) <= 5e-6
+
+
+def test_pcg_solver_golden_c1(engine):
+    d = np.load(os.path.join(GOLD, "c1_testdat.npz"))
+    n_ref, n_obs, sig = int(d["n_ref"]), int(d["n_obs"]), float(d["sigma_s"])
+    engine.load_bed(d["bed"], n_ref)
+    r = engine.fit(d["lmm_off"], d["lmm_pos"], d["lmm_z"], sigma_s=[sig], n_obs=n_obs, solver=_abi.SOLVER_PCG)
+    assert relmax(r["beta_s"][0], d["lmm_beta"]) <= 2e-8           # same iteration count as the reference: ~1e-10
+    assert 40 <= engine.block_iters(0) <= 50                        # the reference takes 45-46 iterations here
+    r = engine.fit(d["s_off"], d["s_pos"], d["s_z"], d["l_off"], d["l_pos"], d["l_z"], sigma_s=[sig], n_obs=n_obs,
+                   solver=_abi.SOLVER_PCG)
+    assert relmax(r["beta_s"][0], d["beta_s"]) <= 2e-7 and relmax(r["beta_l"][0], d["beta_l"]) <= 2e-7
