@@ -37,7 +37,7 @@ CONFIGS = {
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="c3", choices=list(CONFIGS))
@@ -142,7 +142,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -390,9 +390,18 @@ def main():
     chol_ms = avg("chol_ms")
     chol_flops = float(tms[-1]["solve_flops"])
     ach = chol_flops / (chol_ms * 1e-3) / 1e12 if chol_ms > 0 else 0.0
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "chol_traffic.json")))
+        if world == 1 and args.config == "c3" and args.missing == 0.0:
+            traffic = tj["dram_bytes_per_fit"]
+    except Exception:
+        pass
     roofline = {"bound": "tensor", "kernel": "chol_panel_kernel + chol_diag_kernel (all panel steps of one fit)",
                 "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak if fp64_peak else None,
-                "traffic": None,
+                "traffic": traffic,
+                "traffic_note": "dram__bytes_read+write summed over all chol_* launches of one fit (ncu, profiles/chol_traffic.json); "
+                                "algorithmic flops / traffic = arithmetic intensity of the factorisation",
                 "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
                 "flops_per_step": chol_flops, "ms_per_step": chol_ms}
     dec_gbs = float(tms[-1]["decode_bytes"]) / (avg("decode_ms") * 1e-3) / 1e9 if avg("decode_ms") > 0 else 0.0
