@@ -11,6 +11,11 @@
 //   * hidden additions: --solver chol|pcg, --gpus N, --tau T, --h2-folds a,b,c (one Gram, several
 //     ridge folds, outputs <eff>_f<k>.txt), --dump-beta-bin FILE (FP64 betas; the text output
 //     only has 6 significant digits), --verbose.
+//   * --manifest FILE: genome-wide in one process.  The reference is run once per chromosome
+//     by a bash loop (DBSLMM_script.sh:69,118); here each manifest line `s<TAB>l<TAB>r<TAB>b<TAB>eff` (l may be
+//     `-`) is one chromosome, all panels are concatenated into one GPU plan and every chromosome gets its own
+//     `<eff>.txt` / `<eff>.badsnps` with the same rows as a separate run (values agree to FP64 rounding: the
+//     split-K slicing of the Cholesky depends on how many blocks share a panel step).
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -40,6 +45,7 @@ struct Param {                                   // PARAM, scr/dbslmm.hpp:29-45 
     double tau = 0.8;
     vector<double> folds;
     bool verbose = false;
+    string manifest;                             // --manifest: several chromosomes (s l r b eff per line) in ONE run / GPU plan
 };
 
 static void print_header() {
@@ -98,6 +104,7 @@ static void assign(int argc, char** argv, Param& p) {       // scr/dbslmm.cpp:67
         else if (opt(argv[i], "--h2-folds", "-h2-folds")) {
             if (val(v)) { stringstream ss(v); string e; while (getline(ss, e, ',')) p.folds.push_back(atof(e.c_str())); }
         }
+        else if (opt(argv[i], "--manifest", "-manifest")) { if (val(v)) p.manifest = v; }
         else if (opt(argv[i], "--verbose", "-verbose")) p.verbose = true;
     }
 }
@@ -116,34 +123,66 @@ struct Shard {                                   // what one GPU fits
     dbslmm_b200_timing timing{};
 };
 
+// one chromosome's worth of inputs (the reference processes exactly one per process)
+struct Job {
+    string s, l, r, b, eff;
+    int64_t n_snp_ref = 0, row0 = 0;             // rows of this panel inside the concatenated .bed
+    int num_block = 0, block0 = 0;
+    BimMap bim;
+    Info info_s, info_l;
+    bool with_large = false;
+};
+
 int main(int argc, char* argv[]) {
     if (argc <= 1) { print_header(); return EXIT_SUCCESS; }                                   // main_dbslmm.cpp:37-40
     if (argc == 2 && argv[1][0] == '-' && argv[1][1] == 'h') { print_help(); return EXIT_SUCCESS; }   // :41-44
     Param cPar;
     assign(argc, argv, cPar);
 
+    vector<Job> jobs;
+    if (cPar.manifest.empty()) {
+        Job j; j.s = cPar.s; j.l = cPar.l; j.r = cPar.r; j.b = cPar.b; j.eff = cPar.eff;
+        jobs.push_back(j);
+    } else {
+        ifstream mf(cPar.manifest.c_str());
+        if (!mf) { cerr << "ERROR: " << cPar.manifest << " dose not exist!" << endl; exit(1); }
+        string line;
+        while (getline(mf, line)) {
+            if (line.empty() || line[0] == '#') continue;
+            vector<string> t; stringstream ss(line); string e;
+            while (getline(ss, e, '\t')) t.push_back(e);
+            if (t.size() < 5) { cerr << "ERROR: manifest line needs s, l, r, b, eff (tab separated)" << endl; exit(1); }
+            Job j; j.s = t[0]; j.l = (t[1] == "-" ? string() : t[1]); j.r = t[2]; j.b = t[3]; j.eff = t[4];
+            jobs.push_back(j);
+        }
+        if (jobs.empty()) { cerr << "ERROR: empty manifest" << endl; exit(1); }
+    }
+
     cout << "Options: " << endl;                                                              // dbslmm.cpp:181-192
-    cout << "-s:      " << cPar.s << endl;
-    cout << "-l:      " << cPar.l << endl;
-    cout << "-r:      " << cPar.r << endl;
+    cout << "-s:      " << jobs[0].s << endl;
+    cout << "-l:      " << jobs[0].l << endl;
+    cout << "-r:      " << jobs[0].r << endl;
     cout << "-nsnp:   " << cPar.nsnp << endl;
     cout << "-n:      " << cPar.n << endl;
     cout << "-mafMax: " << cPar.mafMax << endl;
-    cout << "-b:      " << cPar.b << endl;
+    cout << "-b:      " << jobs[0].b << endl;
     cout << "-h:      " << cPar.h << endl;
     cout << "-t:      " << cPar.t << endl;
-    cout << "-eff:    " << cPar.eff << endl;
+    cout << "-eff:    " << jobs[0].eff << endl;
     cout << "-test_indicator_file:  " << cPar.test_indicator_file << endl;
+    if (jobs.size() > 1) cout << "--manifest: " << jobs.size() << " chromosomes in one run" << endl;
 
-    const string ref_fam = cPar.r + ".fam";
-    ifstream seff(cPar.s.c_str()), leff(cPar.l.c_str()), reff(ref_fam.c_str()), beff(cPar.b.c_str());
-    if (cPar.s.size() == 0) { cerr << "ERROR: -s is no parameter!" << endl; exit(1); }        // :196-227
-    if (!beff) { cerr << "ERROR: " << cPar.b << " dose not exist!" << endl; exit(1); }
-    if (!seff) { cerr << "ERROR: " << cPar.s << " dose not exist!" << endl; exit(1); }
-    if (!reff) { cerr << "ERROR: " << cPar.r << " dose not exist!" << endl; exit(1); }
-    if (cPar.b.size() == 0) { cerr << "ERROR: -b is no parameter!" << endl; exit(1); }
-    if (cPar.r.size() == 0) { cerr << "ERROR: " << cPar.r << " dose not exist!" << endl; exit(1); }
-    if (cPar.h > 1 || cPar.h < 0) { cerr << "ERROR: -h is not correct (0, 1)!" << endl; exit(1); }
+    for (const Job& j : jobs) {                                                               // :194-219
+        const string ref_fam = j.r + ".fam";
+        ifstream seff(j.s.c_str()), reff(ref_fam.c_str()), beff(j.b.c_str());
+        if (j.s.size() == 0) { cerr << "ERROR: -s is no parameter!" << endl; exit(1); }
+        if (!beff) { cerr << "ERROR: " << j.b << " dose not exist!" << endl; exit(1); }
+        if (!seff) { cerr << "ERROR: " << j.s << " dose not exist!" << endl; exit(1); }
+        if (!reff) { cerr << "ERROR: " << j.r << " dose not exist!" << endl; exit(1); }
+        if (j.b.size() == 0) { cerr << "ERROR: -b is no parameter!" << endl; exit(1); }
+        if (j.r.size() == 0) { cerr << "ERROR: " << j.r << " dose not exist!" << endl; exit(1); }
+    }
+    if (cPar.h > 1 || cPar.h < 0) { cerr << "ERROR: -h is not correct (0, 1)!" << endl; exit(1); }   // :220-227
     if (cPar.t > 100 || cPar.t < 1) { cerr << "ERROR: -t is not correct (1, 100)!" << endl; exit(1); }
     if (cPar.n <= 0 || cPar.nsnp <= 0) { cerr << "ERROR: -n and -nsnp must be positive!" << endl; exit(1); }
     const int solver = (cPar.solver == "pcg") ? DBSLMM_B200_SOLVER_PCG : DBSLMM_B200_SOLVER_CHOLESKY;
@@ -154,81 +193,107 @@ int main(int argc, char* argv[]) {
     if (n_dev <= 0) { cerr << "ERROR: no CUDA device: dbslmm_b200 has no CPU fallback." << endl; exit(2); }
     const int n_gpus = std::max(1, std::min(cPar.gpus, n_dev));
 
-    cout << "Reading reference PLINK FAM file from [" << cPar.r << ".fam]" << endl;
-    const int n_ref = get_row(ref_fam);                                                       // :232
-    cout << n_ref << " individuals to be included from reference FAM file." << endl;
-    cout << "Reading reference PLINK BIM file from [" << cPar.r << ".bim]" << endl;
-    BimMap ref_bim;
-    const bool constr = !(fabs(cPar.mafMax - 1.0) < 1e-10);                                   // :238-241
-    const int64_t n_snp_ref = read_bim(cPar.r + ".bim", ref_bim);
-    cout << ref_bim.size() << " SNPs to be included from reference BIM file." << endl;
-
+    // ---- reference panels: .fam / .bim / .bed of every chromosome, concatenated row-wise
+    int n_ref = -1;
     vector<uint8_t> bed;
-    if (!read_bed(cPar.r + ".bed", n_snp_ref, n_ref, bed)) { cerr << "ERROR: cannot read SNP-major " << cPar.r << ".bed" << endl; exit(1); }
+    int64_t n_snp_all = 0;
+    for (Job& j : jobs) {
+        cout << "Reading reference PLINK FAM file from [" << j.r << ".fam]" << endl;
+        const int nr = get_row(j.r + ".fam");                                                 // :232
+        cout << nr << " individuals to be included from reference FAM file." << endl;
+        if (n_ref >= 0 && nr != n_ref) { cerr << "ERROR: all panels of a manifest must hold the same individuals" << endl; exit(1); }
+        n_ref = nr;
+        cout << "Reading reference PLINK BIM file from [" << j.r << ".bim]" << endl;
+        j.n_snp_ref = read_bim(j.r + ".bim", j.bim);
+        cout << j.bim.size() << " SNPs to be included from reference BIM file." << endl;
+        j.row0 = n_snp_all;
+        vector<uint8_t> part;
+        if (!read_bed(j.r + ".bed", j.n_snp_ref, n_ref, part)) { cerr << "ERROR: cannot read SNP-major " << j.r << ".bed" << endl; exit(1); }
+        bed.insert(bed.end(), part.begin(), part.end());
+        n_snp_all += j.n_snp_ref;
+    }
+    const bool constr = !(fabs(cPar.mafMax - 1.0) < 1e-10);                                   // :238-241
     vector<dbslmm_b200_handle*> hs(n_gpus, nullptr);
     for (int g = 0; g < n_gpus; ++g)
         if (dbslmm_b200_create(g, &hs[g]) != DBSLMM_B200_OK) { cerr << "ERROR: cannot initialise GPU " << g << endl; exit(2); }
     // GPU 0 holds the whole panel: its statistics kernel IS the MAF pre-pass (dtpr.cpp:93-102)
-    if (dbslmm_b200_load_bed(hs[0], bed.data(), n_snp_ref, n_ref) != DBSLMM_B200_OK) {
+    if (dbslmm_b200_load_bed(hs[0], bed.data(), n_snp_all, n_ref) != DBSLMM_B200_OK) {
         cerr << "ERROR: load_bed: " << dbslmm_b200_last_error(hs[0]) << endl; exit(2);
     }
     vector<double> ref_maf;
     if (constr) {
         cout << "Calculating MAF of reference panel ..." << endl;
-        ref_maf.resize((size_t)n_snp_ref);
+        ref_maf.resize((size_t)n_snp_all);
         dbslmm_b200_snp_stats(hs[0], ref_maf.data(), nullptr);
     } else {
         cout << "[WARNING] Do not consider the difference between reference panel and summary data ..." << endl;
     }
 
-    vector<Block> block_dat;
-    read_block(cPar.b, block_dat);                                                            // :248
-    const int num_block = (int)block_dat.size();
-
-    cout << "Reading summary data of small effect SNPs from [" << cPar.s << "]" << endl;
-    Summ summ_s;
-    read_summ(cPar.s, summ_s);
-    Info inter_s, info_s;
-    vector<char> matched_s;
-    int dis = 0, mafc = 0;
-    match_ref(summ_s, ref_bim, constr ? ref_maf.data() : nullptr, cPar.mafMax, inter_s, matched_s, dis, mafc);
-    cout << "Number of allele discrepency: " << dis << endl;
-    cout << "Number of maf discrepency:    " << mafc << endl;
-    cout << "After filtering, " << inter_s.size() << " small effect SNPs are selected." << endl;
-    add_block(inter_s, block_dat, info_s);
-    const string badsnps_str = cPar.eff + ".badsnps";
-    ofstream badsnpsFout(badsnps_str.c_str());
-    for (size_t i = 0; i < summ_s.size(); ++i)
-        if (!matched_s[i]) badsnpsFout << summ_s.snp[i] << " " << 0 << endl;                 // :282-285
-
-    Info inter_l, info_l;
-    if (leff) {                                                                               // :292-317
-        cout << "Reading summary data of large effect SNPs from [" << cPar.l << "]" << endl;
-        Summ summ_l;
-        read_summ(cPar.l, summ_l);
-        vector<char> matched_l;
-        match_ref(summ_l, ref_bim, constr ? ref_maf.data() : nullptr, cPar.mafMax, inter_l, matched_l, dis, mafc);
+    // ---- per chromosome: blocks, summary statistics, matching, block assignment, badsnps
+    int num_block = 0;
+    for (Job& j : jobs) {
+        vector<Block> block_dat;
+        read_block(j.b, block_dat);                                                           // :248
+        j.num_block = (int)block_dat.size();
+        j.block0 = num_block;
+        num_block += j.num_block;
+        const double* maf = constr ? ref_maf.data() + j.row0 : nullptr;
+        cout << "Reading summary data of small effect SNPs from [" << j.s << "]" << endl;
+        Summ summ_s;
+        read_summ(j.s, summ_s);
+        Info inter_s;
+        vector<char> matched_s;
+        int dis = 0, mafc = 0;
+        match_ref(summ_s, j.bim, maf, cPar.mafMax, inter_s, matched_s, dis, mafc);
         cout << "Number of allele discrepency: " << dis << endl;
         cout << "Number of maf discrepency:    " << mafc << endl;
-        if (inter_l.size() != 0) {
-            add_block(inter_l, block_dat, info_l);
-            cout << "After filtering, " << inter_l.size() << " large effect SNPs are selected." << endl;
-        } else {
-            cout << "After filtering, no large effect SNP is selected." << endl;
+        cout << "After filtering, " << inter_s.size() << " small effect SNPs are selected." << endl;
+        add_block(inter_s, block_dat, j.info_s);
+        const string badsnps_str = j.eff + ".badsnps";
+        ofstream badsnpsFout(badsnps_str.c_str());
+        for (size_t i = 0; i < summ_s.size(); ++i)
+            if (!matched_s[i]) badsnpsFout << summ_s.snp[i] << " " << 0 << endl;             // :282-285
+        ifstream leff(j.l.c_str());
+        Info inter_l;
+        if (!j.l.empty() && leff) {                                                           // :292-317
+            cout << "Reading summary data of large effect SNPs from [" << j.l << "]" << endl;
+            Summ summ_l;
+            read_summ(j.l, summ_l);
+            vector<char> matched_l;
+            match_ref(summ_l, j.bim, maf, cPar.mafMax, inter_l, matched_l, dis, mafc);
+            cout << "Number of allele discrepency: " << dis << endl;
+            cout << "Number of maf discrepency:    " << mafc << endl;
+            if (inter_l.size() != 0) {
+                add_block(inter_l, block_dat, j.info_l);
+                cout << "After filtering, " << inter_l.size() << " large effect SNPs are selected." << endl;
+            } else {
+                cout << "After filtering, no large effect SNP is selected." << endl;
+            }
+            for (size_t i = 0; i < summ_l.size(); ++i)
+                if (!matched_l[i]) badsnpsFout << summ_l.snp[i] << " " << 1 << endl;
         }
-        for (size_t i = 0; i < summ_l.size(); ++i)
-            if (!matched_l[i]) badsnpsFout << summ_l.snp[i] << " " << 1 << endl;
+        badsnpsFout.close();
+        j.with_large = inter_l.size() != 0;                                                   // :325 / :366
     }
-    badsnpsFout.close();
-    const bool with_large = inter_l.size() != 0;                                              // :325 / :366
+    bool with_large = false;
+    for (const Job& j : jobs) with_large = with_large || j.with_large;
 
-    // ---- block plan: CSR offsets, shard over GPUs
-    const vector<int32_t> s_off = block_offsets(info_s, num_block);
-    const vector<int32_t> l_off = with_large ? block_offsets(info_l, num_block) : vector<int32_t>();
+    // ---- ONE block plan over all chromosomes: CSR offsets (global block ids), shard over GPUs
+    vector<int32_t> s_off(1, 0), l_off(1, 0), s_pos_all, l_pos_all;
+    vector<double> s_z_all, l_z_all;
+    for (const Job& j : jobs) {
+        const vector<int32_t> so = block_offsets(j.info_s, j.num_block);
+        const vector<int32_t> lo = j.with_large ? block_offsets(j.info_l, j.num_block) : vector<int32_t>((size_t)j.num_block + 1, 0);
+        const int32_t sb = s_off.back(), lb = l_off.back();
+        for (int b = 1; b <= j.num_block; ++b) { s_off.push_back(sb + so[b]); l_off.push_back(lb + lo[b]); }
+        for (size_t i = 0; i < j.info_s.size(); ++i) { s_pos_all.push_back((int32_t)(j.info_s.pos[i] + j.row0)); s_z_all.push_back(j.info_s.z[i]); }
+        if (j.with_large)
+            for (size_t i = 0; i < j.info_l.size(); ++i) { l_pos_all.push_back((int32_t)(j.info_l.pos[i] + j.row0)); l_z_all.push_back(j.info_l.z[i]); }
+    }
     vector<int32_t> m_s(num_block), m_l(num_block, 0), owner(num_block, 0);
     for (int b = 0; b < num_block; ++b) {
         m_s[b] = s_off[b + 1] - s_off[b];
-        if (with_large) m_l[b] = l_off[b + 1] - l_off[b];
+        m_l[b] = l_off[b + 1] - l_off[b];
     }
     if (n_gpus > 1) dbslmm_b200_plan_shards(num_block, m_s.data(), m_l.data(), n_ref, n_gpus, owner.data(), nullptr);
 
@@ -244,7 +309,7 @@ int main(int argc, char* argv[]) {
         sh.s_off.push_back(0);
         if (with_large) sh.l_off.push_back(0);
         vector<int64_t> remap;
-        if (n_gpus > 1) remap.assign((size_t)n_snp_ref, -1);
+        if (n_gpus > 1) remap.assign((size_t)n_snp_all, -1);
         const size_t pitch = (size_t)((n_ref + 3) / 4);
         auto map_row = [&](int32_t p) -> int32_t {
             if (n_gpus == 1) return p;
@@ -257,10 +322,10 @@ int main(int argc, char* argv[]) {
         for (int b = 0; b < num_block; ++b) {
             if (owner[b] != g) continue;
             sh.blocks.push_back(b);
-            for (int j = s_off[b]; j < s_off[b + 1]; ++j) { sh.s_pos.push_back(map_row(info_s.pos[j])); sh.s_z.push_back(info_s.z[j]); }
+            for (int j = s_off[b]; j < s_off[b + 1]; ++j) { sh.s_pos.push_back(map_row(s_pos_all[j])); sh.s_z.push_back(s_z_all[j]); }
             sh.s_off.push_back((int32_t)sh.s_pos.size());
             if (with_large) {
-                for (int j = l_off[b]; j < l_off[b + 1]; ++j) { sh.l_pos.push_back(map_row(info_l.pos[j])); sh.l_z.push_back(info_l.z[j]); }
+                for (int j = l_off[b]; j < l_off[b + 1]; ++j) { sh.l_pos.push_back(map_row(l_pos_all[j])); sh.l_z.push_back(l_z_all[j]); }
                 sh.l_off.push_back((int32_t)sh.l_pos.size());
             }
         }
@@ -311,8 +376,8 @@ int main(int argc, char* argv[]) {
         }
 
     // ---- gather to block-major global order
-    const size_t tot_s = info_s.size(), tot_l = info_l.size();
-    vector<double> beta_s(tot_s * n_folds), beta_l(tot_l * n_folds + 1);
+    const size_t tot_s = s_pos_all.size(), tot_l = l_pos_all.size();
+    vector<double> beta_s(tot_s * n_folds + 1), beta_l(tot_l * n_folds + 1);
     for (int g = 0; g < n_gpus; ++g) {
         const Shard& sh = shards[g];
         const size_t ns = sh.s_pos.size(), nl = sh.l_pos.size();
@@ -326,26 +391,30 @@ int main(int argc, char* argv[]) {
         }
     }
 
-    // ---- output effect (dbslmm.cpp:353-364 / 391-395): large first (flag 1), then small (flag 0)
-    for (int f = 0; f < n_folds; ++f) {
-        string eff_str = cPar.eff + ".txt";
-        if (n_folds > 1) { ostringstream o; o << cPar.eff << "_f" << f << ".txt"; eff_str = o.str(); }
-        ofstream effFout(eff_str.c_str());
-        for (size_t i = 0; i < tot_l; ++i) {
-            const double b = beta_l[f * tot_l + i];
-            const double noscl = b / sqrt(2 * info_l.maf[i] * (1 - info_l.maf[i]));
-            if (isinf(noscl) == false) effFout << info_l.snp[i] << " " << info_l.a1[i] << " " << b << " " << noscl << " " << 1 << endl;
+    // ---- output effect per chromosome (dbslmm.cpp:353-364 / 391-395): large first (flag 1), then small (flag 0)
+    for (const Job& j : jobs) {
+        const size_t js = (size_t)s_off[j.block0], jl = (size_t)l_off[j.block0];   // this chromosome's slice of the global arrays
+        for (int f = 0; f < n_folds; ++f) {
+            string eff_str = j.eff + ".txt";
+            if (n_folds > 1) { ostringstream o; o << j.eff << "_f" << f << ".txt"; eff_str = o.str(); }
+            ofstream effFout(eff_str.c_str());
+            if (j.with_large)
+                for (size_t i = 0; i < j.info_l.size(); ++i) {
+                    const double b = beta_l[f * tot_l + jl + i];
+                    const double noscl = b / sqrt(2 * j.info_l.maf[i] * (1 - j.info_l.maf[i]));
+                    if (isinf(noscl) == false) effFout << j.info_l.snp[i] << " " << j.info_l.a1[i] << " " << b << " " << noscl << " " << 1 << endl;
+                }
+            for (size_t i = 0; i < j.info_s.size(); ++i) {
+                const double b = beta_s[f * tot_s + js + i];
+                const double noscl = b / sqrt(2 * j.info_s.maf[i] * (1 - j.info_s.maf[i]));
+                if (j.info_s.snp[i].size() != 0 && isinf(noscl) == false)
+                    effFout << j.info_s.snp[i] << " " << j.info_s.a1[i] << " " << b << " " << noscl << " " << 0 << endl;
+            }
+            effFout.close();
         }
-        for (size_t i = 0; i < tot_s; ++i) {
-            const double b = beta_s[f * tot_s + i];
-            const double noscl = b / sqrt(2 * info_s.maf[i] * (1 - info_s.maf[i]));
-            if (info_s.snp[i].size() != 0 && isinf(noscl) == false)
-                effFout << info_s.snp[i] << " " << info_s.a1[i] << " " << b << " " << noscl << " " << 0 << endl;
-        }
-        effFout.close();
     }
     if (!cPar.dump_bin.empty()) {
-        // int64 n_folds, tot_l, tot_s, then FP64 beta_l[n_folds][tot_l], beta_s[n_folds][tot_s]
+        // int64 n_folds, tot_l, tot_s, then FP64 beta_l[n_folds][tot_l], beta_s[n_folds][tot_s] (chromosomes in manifest order)
         ofstream o(cPar.dump_bin.c_str(), ios::binary);
         const int64_t hdr[3] = {n_folds, (int64_t)tot_l, (int64_t)tot_s};
         o.write((const char*)hdr, sizeof(hdr));

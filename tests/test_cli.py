@@ -86,3 +86,31 @@ def test_cli_lmm_mode_and_folds(tmp_path):
     assert np.abs(beta[1] - d["lmm_beta"]).max() / np.abs(d["lmm_beta"]).max() < 2e-8
     for f in range(3):
         assert len((tmp_path / f"lmm_f{f}.txt").read_text().strip().split("\n")) == 716
+
+
+@pytest.mark.gpu
+def test_cli_manifest_two_chromosomes(tmp_path):
+    """several chromosomes in one process / one GPU plan give the same per-chromosome files as separate runs."""
+    _write_fixture(tmp_path)
+    common = ["-n", "2400", "-nsnp", "996", "-mafMax", "0.2", "-h", "0.5", "-t", "1"]
+    ref, blk = str(tmp_path / "ref"), str(tmp_path / "blocks.bed")
+    # separate runs
+    r = subprocess.run([CLI, "-s", str(tmp_path / "s.txt"), "-l", str(tmp_path / "l.txt"), "-r", ref, "-b", blk, "-eff", str(tmp_path / "a")] + common,
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([CLI, "-s", str(tmp_path / "summ.txt"), "-r", ref, "-b", blk, "-eff", str(tmp_path / "b")] + common,
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    # one manifest run
+    (tmp_path / "manifest.tsv").write_text(
+        f"{tmp_path / 's.txt'}\t{tmp_path / 'l.txt'}\t{ref}\t{blk}\t{tmp_path / 'ma'}\n"
+        f"{tmp_path / 'summ.txt'}\t-\t{ref}\t{blk}\t{tmp_path / 'mb'}\n")
+    r = subprocess.run([CLI, "--manifest", str(tmp_path / "manifest.tsv")] + common, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "2 chromosomes in one run" in r.stdout
+    for single, multi in (("a", "ma"), ("b", "mb")):
+        x, y = _parse((tmp_path / f"{single}.txt").read_text()), _parse((tmp_path / f"{multi}.txt").read_text())
+        assert [(g[0], g[1], g[4]) for g in x] == [(g[0], g[1], g[4]) for g in y]
+        vx, vy = np.array([g[2] for g in x]), np.array([g[2] for g in y])
+        assert np.abs(vx - vy).max() <= 2e-6 * np.abs(vx).max()
+        assert (tmp_path / f"{single}.badsnps").read_text() == (tmp_path / f"{multi}.badsnps").read_text()
