@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="target CPU work of the baseline sample")
     ap.add_argument("--seed", type=int, default=20240003)
+    ap.add_argument("--emulate-shard", default="", help="R/N: time rank R's shard of an N-GPU run on one GPU (tuning aid)")
     return ap.parse_args()
 
 
@@ -314,11 +315,16 @@ def main():
     eng = _abi.Engine(local)
     ms_blk = (w["s_off"][1:] - w["s_off"][:-1]).astype(np.int32)
     ml_blk = (w["l_off"][1:] - w["l_off"][:-1]).astype(np.int32)
-    if args.scaling == "strong" and world > 1:
+    if args.emulate_shard:
+        er, en = (int(x) for x in args.emulate_shard.split("/"))
+        owner, _ = eng.plan_shards(ms_blk, ml_blk, n_ref, en)
+        sh = shard_workload(w, owner, er, torch)
+    elif args.scaling == "strong" and world > 1:
         owner, _ = eng.plan_shards(ms_blk, ml_blk, n_ref, world)
+        sh = shard_workload(w, owner, rank, torch)
     else:
         owner = np.zeros(nb_total, np.int32) + (0 if args.scaling == "strong" else rank)
-    sh = shard_workload(w, owner, rank if (args.scaling == "strong" and world > 1) else owner[0], torch)
+        sh = shard_workload(w, owner, owner[0], torch)
     my_blocks = int(sh["blocks"].size)
     my_snps = int(sh["s_pos"].size + sh["l_pos"].size)
     sigma_s = [0.5 / w["nsnp_total"]]

@@ -22,6 +22,7 @@
 // backsolve_kernel then solves L^T x = y per block and writes beta = x / sqrt(N).
 // Matrices are row-major, lower triangle, ld = mp (m padded to 8 with identity rows).
 #include <algorithm>
+#include <cooperative_groups.h>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -576,6 +577,100 @@ backsolve_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Back substitution for big blocks (mp > 1024): a thread-block CLUSTER of 8 CTAs per block.
+// Each CTA streams one eighth of the rows below the current panel, the eight 64-entry partial
+// sums are exchanged through distributed shared memory, and every CTA then forms x_k itself
+// (redundantly: cheaper than a broadcast).  Two cluster barriers per panel.  One CTA alone is
+// latency-bound at ~30 GB/s on a 36 MB factor and was the critical path of the 8-GPU shards.
+// ------------------------------------------------------------------------------------------
+static constexpr int kBsCluster = 8;
+static constexpr int kBsThreads = 512;
+
+__global__ void __cluster_dims__(kBsCluster, 1, 1) __launch_bounds__(kBsThreads)
+backsolve_cluster_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict__ order,
+                         const double* __restrict__ Lbuf, double inv_sqrt_n, double* __restrict__ beta_s,
+                         double* __restrict__ beta_l) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) double smem[];
+    const unsigned cr = cluster.block_rank();
+    const BlockDesc bd = blocks[order[blockIdx.x / kBsCluster]];
+    const int mp = bd.mp, ld = bd.ld;
+    const double* Lb = Lbuf + bd.moff;
+    const double* y = Lb + (size_t)mp * ld;
+    constexpr int NRG = kBsThreads / 32;          // row groups per CTA
+    constexpr int RS = NRG * kBsCluster;          // row stride of one (CTA, row group)
+    double* x = smem;                              // [mp]   full solution vector, kept by every CTA
+    double* part = smem + mp;                      // [64]   this CTA's partial sums (read by the others)
+    double* red = part + NB;                       // [NRG][64]
+    double* v = red + NRG * NB;                    // [64]
+    const int tid = threadIdx.x;
+    const int K = (mp + NB - 1) / NB;
+    for (int k = K - 1; k >= 0; --k) {
+        const int pc0 = k * NB, wk = min(NB, mp - pc0), below = pc0 + wk;
+        {
+            const int rg = tid >> 5, c2 = (tid & 31) * 2;
+            double2 p0 = make_double2(0.0, 0.0), p1 = p0, p2 = p0, p3 = p0;
+            if (c2 < wk) {
+                const double* col = Lb + pc0 + c2;
+                int i = below + (int)cr * NRG + rg;
+                for (; i + 3 * RS < mp; i += 4 * RS) {
+                    const double2 a0 = *reinterpret_cast<const double2*>(col + (size_t)i * ld);
+                    const double2 a1 = *reinterpret_cast<const double2*>(col + (size_t)(i + RS) * ld);
+                    const double2 a2 = *reinterpret_cast<const double2*>(col + (size_t)(i + 2 * RS) * ld);
+                    const double2 a3 = *reinterpret_cast<const double2*>(col + (size_t)(i + 3 * RS) * ld);
+                    const double x0 = x[i], x1 = x[i + RS], x2 = x[i + 2 * RS], x3 = x[i + 3 * RS];
+                    p0.x += a0.x * x0; p0.y += a0.y * x0;
+                    p1.x += a1.x * x1; p1.y += a1.y * x1;
+                    p2.x += a2.x * x2; p2.y += a2.y * x2;
+                    p3.x += a3.x * x3; p3.y += a3.y * x3;
+                }
+                for (; i < mp; i += RS) {
+                    const double2 a0 = *reinterpret_cast<const double2*>(col + (size_t)i * ld);
+                    p0.x += a0.x * x[i]; p0.y += a0.y * x[i];
+                }
+            }
+            red[rg * NB + c2] = (p0.x + p1.x) + (p2.x + p3.x);
+            red[rg * NB + c2 + 1] = (p0.y + p1.y) + (p2.y + p3.y);
+        }
+        __syncthreads();
+        if (tid < NB) {
+            double sacc = 0.0;
+#pragma unroll
+            for (int q = 0; q < NRG; ++q) sacc += red[q * NB + tid];
+            part[tid] = sacc;
+        }
+        cluster.sync();                            // all eight partial vectors are in place
+        if (tid < NB) {
+            double sacc = 0.0;
+#pragma unroll
+            for (unsigned r = 0; r < (unsigned)kBsCluster; ++r) sacc += cluster.map_shared_rank(part, r)[tid];   // fixed order
+            v[tid] = (tid < wk) ? y[pc0 + tid] - sacc : 0.0;
+        }
+        __syncthreads();
+        if (tid < 256) {
+            const int c = tid >> 2, q = tid & 3;
+            double p = 0.0;
+            if (c < wk) {
+                const double* row = Lb + (size_t)(pc0 + c) * ld + pc0;
+                for (int cp = c + q; cp < wk; cp += 4) p += ((cp == c) ? 1.0 / row[c] : row[cp]) * v[cp];
+            }
+            p += __shfl_xor_sync(0xffffffffu, p, 1);
+            p += __shfl_xor_sync(0xffffffffu, p, 2);
+            if (q == 0 && c < wk) x[pc0 + c] = p;
+        }
+        cluster.sync();                            // everyone has read the partials: they may be overwritten
+    }
+    if (cr == 0) {
+        for (int j = tid; j < bd.m; j += kBsThreads) {
+            const double b = x[j] * inv_sqrt_n;
+            if (j < bd.ms) beta_s[bd.out_s + j] = b;
+            else beta_l[bd.out_l + (j - bd.ms)] = b;
+        }
+    }
+}
+
 cudaError_t chol_configure() {
     cudaError_t e = cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DIAG);
     if (e != cudaSuccess) return e;
@@ -597,22 +692,20 @@ cudaError_t launch_chol_panel(const BlockDesc* blocks, const int4* items, int32_
                                                                  counters, group_base);
     return cudaGetLastError();
 }
-// `order` lists blocks by descending size; the first n_big (mp > 1024) get 1024-thread CTAs so that
-// one CTA keeps enough loads in flight to stream a multi-MB factor (a single 256-thread CTA is
-// latency-bound at ~16 GB/s and was the critical path of the whole solve).
-cudaError_t launch_backsolve(const BlockDesc* blocks, const int32_t* order, int32_t n_blocks, int32_t n_big,
+// Back substitution of `n_blocks` blocks listed in `order`: an 8-CTA cluster per block for the big size
+// classes (mp > 1024), one 256-thread CTA per block otherwise.
+cudaError_t launch_backsolve(const BlockDesc* blocks, const int32_t* order, int32_t n_blocks, bool big,
                              const double* L, double inv_sqrt_n, double* beta_s, double* beta_l, int32_t max_mp,
                              cudaStream_t st) {
     if (n_blocks == 0) return cudaSuccess;
-    if (n_big > 0) {
-        const size_t smem = (size_t)(max_mp + 33 * NB) * sizeof(double);
-        cudaError_t e = cudaFuncSetAttribute(backsolve_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (big) {
+        const size_t smem = (size_t)(max_mp + (kBsThreads / 32 + 2) * NB) * sizeof(double);
+        cudaError_t e = cudaFuncSetAttribute(backsolve_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        backsolve_kernel<1024><<<n_big, 1024, smem, st>>>(blocks, order, L, inv_sqrt_n, beta_s, beta_l);
-    }
-    if (n_blocks > n_big) {
+        backsolve_cluster_kernel<<<n_blocks * kBsCluster, kBsThreads, smem, st>>>(blocks, order, L, inv_sqrt_n, beta_s, beta_l);
+    } else {
         const size_t smem = (size_t)(1024 + 9 * NB) * sizeof(double);
-        backsolve_kernel<256><<<n_blocks - n_big, 256, smem, st>>>(blocks, order + n_big, L, inv_sqrt_n, beta_s, beta_l);
+        backsolve_kernel<256><<<n_blocks, 256, smem, st>>>(blocks, order, L, inv_sqrt_n, beta_s, beta_l);
     }
     return cudaGetLastError();
 }

@@ -74,6 +74,8 @@ struct Plan {
     int64_t scratch_doubles = 0;
     int32_t n_groups = 0;                             // split-K groups (one arrival counter each)
     int32_t n_big = 0;                                // blocks with mp > 1024 (head of `order`)
+    int32_t cls_off[kNumClasses] = {0, 0, 0, 0};      // each size class is a contiguous range of `order`
+    int32_t cls_n[kNumClasses] = {0, 0, 0, 0};
     // blob layout (byte offsets inside the plan blob, identical on host and device)
     size_t o_blocks = 0, o_rowsrc = 0, o_rowg = 0, o_z = 0, o_tiles_plain = 0, o_tiles_miss = 0, o_order = 0,
            o_diag = 0, o_panel = 0, blob_bytes = 0;
@@ -89,7 +91,7 @@ struct dbslmm_b200_handle {
     cudaStream_t stream = nullptr;
     cudaStream_t cls_stream[kNumClasses] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev[8] = {};
-    cudaEvent_t ev_fork = nullptr, ev_join[kNumClasses] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[kNumClasses] = {}, ev_cend[kNumClasses] = {};
     std::string err;
     // reference panel
     DevBuf bed, stats;
@@ -261,6 +263,15 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
     P.n_groups = n_groups;
     P.n_big = 0;
     for (int b : P.order) { if (P.blocks[b].mp > 1024) P.n_big++; else break; }
+    for (int c = 0; c < kNumClasses; ++c) { P.cls_off[c] = 0; P.cls_n[c] = 0; }
+    for (int i = 0; i < nb; ++i) {                    // `order` is by descending size => classes are contiguous
+        const int K = (P.blocks[P.order[i]].mp + 63) / 64;
+        if (K == 0) continue;
+        int c = 0;
+        while (K > kClassMaxPanels[c]) ++c;
+        if (P.cls_n[c] == 0) P.cls_off[c] = i;
+        P.cls_n[c]++;
+    }
     P.blob_bytes = o;
     // fill the pinned staging buffer in place (no intermediate copy; alignment gaps are never read)
     if (h->h_blob.ensure(o + 256) != cudaSuccess) return fail(h, DBSLMM_B200_ERR_NOMEM, "pinned plan buffer");
@@ -353,7 +364,7 @@ int dbslmm_b200_create(int device, dbslmm_b200_handle** out) {
         // the classes with the most panel steps have the longest dependency chains: schedule them first
         const int prio = std::max(prio_hi, prio_lo - c);
         ok = cudaStreamCreateWithPriority(&h->cls_stream[c], cudaStreamNonBlocking, prio) == cudaSuccess &&
-             cudaEventCreate(&h->ev_join[c]) == cudaSuccess;
+             cudaEventCreate(&h->ev_join[c]) == cudaSuccess && cudaEventCreate(&h->ev_cend[c]) == cudaSuccess;
     }
     for (int i = 0; i < 8 && ok; ++i) ok = cudaEventCreate(&h->ev[i]) == cudaSuccess;
     ok = ok && cudaEventCreate(&h->ev_fork) == cudaSuccess;
@@ -379,6 +390,7 @@ void dbslmm_b200_destroy(dbslmm_b200_handle* h) {
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     for (int c = 0; c < kNumClasses; ++c) {
         if (h->ev_join[c]) cudaEventDestroy(h->ev_join[c]);
+        if (h->ev_cend[c]) cudaEventDestroy(h->ev_cend[c]);
         if (h->cls_stream[c]) cudaStreamDestroy(h->cls_stream[c]);
     }
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -647,20 +659,27 @@ int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
                     n_launch += 2;
                     n_chol_launch += 2;
                 }
+                // the class's back substitution follows on its own stream: the big blocks' substitutions overlap
+                // the factorisation of the bulk classes, which finish last
+                CU_TRY(h, cudaEventRecord(h->ev_cend[c], cs));
+                CU_TRY(h, launch_backsolve(d_blocks, d_order + P.cls_off[c], P.cls_n[c], kClassMaxPanels[c] > 16,
+                                           (const double*)h->lbuf.p, inv_sqrt_n, bs, bl, P.max_mp, cs));
+                ++n_launch;
                 CU_TRY(h, cudaEventRecord(h->ev_join[c], cs));
                 CU_TRY(h, cudaStreamWaitEvent(st, h->ev_join[c], 0));
             }
-            CU_TRY(h, cudaEventRecord(h->ev[6], st));
-            CU_TRY(h, launch_backsolve(d_blocks, d_order, nb, P.n_big, (const double*)h->lbuf.p, inv_sqrt_n, bs, bl, P.max_mp, st));
-            ++n_launch;
-            if (a->timing && a->n_folds > 1) {
-                // per-fold factorisation time needs a sync; only paid when timing is requested
+            if (a->timing) {
+                // factorisation time of this fold = latest class end (events are read after a sync)
                 CU_TRY(h, cudaEventRecord(h->ev[7], st));
                 CU_TRY(h, cudaEventSynchronize(h->ev[7]));
-                float ms = 0.f;
-                cudaEventElapsedTime(&ms, (f == 0) ? h->ev[3] : h->ev[5], h->ev[6]);
-                chol_ms_total += ms;
-                CU_TRY(h, cudaEventRecord(h->ev[5], st));
+                float worst = 0.f;
+                for (int c = 0; c < kNumClasses; ++c) {
+                    if (P.steps[c].empty()) continue;
+                    float ms = 0.f;
+                    cudaEventElapsedTime(&ms, h->ev_fork, h->ev_cend[c]);
+                    worst = std::max(worst, ms);
+                }
+                chol_ms_total += worst;
             }
         } else {
             // reference-faithful Jacobi-PCG (pcg.cu): per-block scratch vectors live in `scratch`
@@ -730,11 +749,10 @@ int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
         cudaEventElapsedTime(&t->solve_ms, h->ev[3], h->ev[4]);
         cudaEventElapsedTime(&t->d2h_ms, h->ev[4], h->ev[5]);
         cudaEventElapsedTime(&t->total_ms, h->ev[0], h->ev[5]);
-        if (!pcg && a->n_folds == 1) { float ms = 0.f; cudaEventElapsedTime(&ms, h->ev[3], h->ev[6]); chol_ms_total = ms; }
         t->chol_ms = chol_ms_total;
         for (int c = 0; c < kNumClasses; ++c) {
             t->class_ms[c] = 0.f;
-            if (!pcg && !P.steps[c].empty()) cudaEventElapsedTime(&t->class_ms[c], h->ev_fork, h->ev_join[c]);
+            if (!pcg && !P.steps[c].empty()) cudaEventElapsedTime(&t->class_ms[c], h->ev_fork, h->ev_cend[c]);
         }
         t->n_launches = n_launch;
         t->n_chol_launches = n_chol_launch;

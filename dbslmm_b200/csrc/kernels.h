@@ -54,7 +54,7 @@ cudaError_t launch_chol_diag(const BlockDesc* blocks, const int32_t* items, int3
 cudaError_t launch_chol_panel(const BlockDesc* blocks, const int4* items, int32_t n_items, int32_t k,
                               const double* sigma, double* L, const double* wbuf, double ridge, double* scratch,
                               int32_t* counters, int32_t group_base, cudaStream_t st);
-cudaError_t launch_backsolve(const BlockDesc* blocks, const int32_t* order, int32_t n_blocks, int32_t n_big,
+cudaError_t launch_backsolve(const BlockDesc* blocks, const int32_t* order, int32_t n_blocks, bool big,
                              const double* L, double inv_sqrt_n, double* beta_s, double* beta_l, int32_t max_mp,
                              cudaStream_t st);
 cudaError_t chol_configure();
