@@ -44,7 +44,10 @@ class FitArgs(C.Structure):
                 ("n_folds", C.c_int32), ("sigma_s", C.c_void_p), ("n_obs", C.c_int64), ("tau", C.c_double),
                 ("solver", C.c_int32), ("flags", C.c_int32),
                 ("beta_s_out", C.c_void_p), ("beta_l_out", C.c_void_p), ("block_status_out", C.c_void_p),
-                ("timing", C.POINTER(Timing))]
+                ("timing", C.POINTER(Timing)),
+                ("test_bed", C.c_void_p), ("test_n_snp", C.c_int64), ("test_n_total", C.c_int32),
+                ("test_indicator", C.c_void_p), ("s_tpos", C.c_void_p), ("l_tpos", C.c_void_p),
+                ("variance_out", C.c_void_p)]
 
 
 _lib = None
@@ -142,8 +145,10 @@ class Engine:
         return owner, cost
 
     def fit(self, s_off, s_pos, s_z, l_off=None, l_pos=None, l_z=None, *, sigma_s, n_obs, tau=0.8,
-            solver=SOLVER_CHOLESKY, flags=0):
-        """Returns dict(beta_s[n_folds, S], beta_l[n_folds, L], status[n_blocks], n_bad, timing)."""
+            solver=SOLVER_CHOLESKY, flags=0, test=None):
+        """Returns dict(beta_s[n_folds, S], beta_l[n_folds, L], status[n_blocks], n_bad, timing[, variance]).
+        test = dict(bed=uint8[n_snp_t, pitch_t], n_total=int, indicator=int[n_total], s_tpos=int[S], l_tpos=int[L])
+        switches the fork's asymptotic-variance side channel on: variance[n_folds, n_blocks, n_test]."""
         s_off = np.ascontiguousarray(s_off, np.int32)
         s_pos = np.ascontiguousarray(s_pos, np.int32)
         s_z = np.ascontiguousarray(s_z, np.float64)
@@ -165,9 +170,23 @@ class Engine:
         a = FitArgs(nb, s_off.ctypes.data, _ptr(s_pos), _ptr(s_z), _ptr(l_off), _ptr(l_pos), _ptr(l_z),
                     nf, sig.ctypes.data, int(n_obs), float(tau), int(solver), int(flags),
                     beta_s.ctypes.data, _ptr(beta_l), status.ctypes.data, C.pointer(tm))
+        var = None
+        if test is not None:
+            tbed = np.ascontiguousarray(test["bed"], np.uint8)
+            ind = np.ascontiguousarray(test["indicator"], np.int32)
+            stp = np.ascontiguousarray(test["s_tpos"], np.int32)
+            ltp = None if l_off is None else np.ascontiguousarray(test["l_tpos"], np.int32)
+            n_total = int(test["n_total"])
+            var = np.zeros((nf, max(nb, 1), max(int((ind != 0).sum()), 1)), np.float64)
+            a.test_bed, a.test_n_snp, a.test_n_total = tbed.ctypes.data, tbed.size // ((n_total + 3) // 4), n_total
+            a.test_indicator, a.s_tpos, a.l_tpos, a.variance_out = ind.ctypes.data, _ptr(stp), _ptr(ltp), var.ctypes.data
+            self._keep = [tbed, ind, stp, ltp]
         rc = self._check(self.lib.dbslmm_b200_fit(self.h, C.byref(a)), "fit")
-        return {"beta_s": beta_s, "beta_l": None if beta_l is None else beta_l[:, :nl], "status": status[:nb],
-                "n_bad": rc, "timing": tm.as_dict()}
+        out = {"beta_s": beta_s, "beta_l": None if beta_l is None else beta_l[:, :nl], "status": status[:nb],
+               "n_bad": rc, "timing": tm.as_dict()}
+        if var is not None:
+            out["variance"] = var
+        return out
 
     def score(self, bed_val, n_val, pos, beta, flip=None):
         """PRS over a validation panel: returns (scores[n_folds, n_val], kernel_ms)."""

@@ -21,7 +21,7 @@ GXX = "/usr/bin/g++"
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CU_FLAGS = ["-O3", "-lineinfo", "-std=c++17", "-ccbin", GXX, "-Xcompiler", "-fPIC,-fvisibility=hidden",
             "-Xptxas", "-v"]
-CU_SOURCES = ["decode.cu", "gram.cu", "chol.cu", "score.cu", "pcg.cu", "engine.cu"]
+CU_SOURCES = ["decode.cu", "gram.cu", "chol.cu", "score.cu", "variance.cu", "pcg.cu", "engine.cu"]
 HOST_SOURCES = ["dbslmm_main.cpp", "ingest.cpp"]
 
 

@@ -321,7 +321,7 @@ __device__ __forceinline__ bool panel_body(const BlockDesc& bd, const int4 item,
     const int pc0 = k * NB;
     const int wk = min(NB, bd.mp - pc0);
     const int ld = bd.ld;
-    const int nrows = bd.mp + 8;
+    const int nrows = bd.nrows;
     const int r0 = pc0 + wk + item.y * TM;
     const int prow = min(TM, nrows - r0);
     double* Lb = Lbuf + bd.moff;

@@ -26,7 +26,7 @@ struct BlockDesc {
     int32_t has_missing;    // 1 => four integer Gram planes (Q, A, B, N)
     int32_t out_s;          // offset of this block's small betas in the output array
     int32_t out_l;          // offset of its large betas
-    int32_t pad;
+    int32_t nrows;          // matrix rows: mp + 8 (z row group) + appended test-genotype rows (variance side channel)
 };
 
 struct GramTile {           // one 128x128 output tile of a block's lower triangle

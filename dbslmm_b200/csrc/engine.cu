@@ -74,6 +74,7 @@ struct Plan {
     int64_t scratch_doubles = 0;
     int32_t n_groups = 0;                             // split-K groups (one arrival counter each)
     int32_t n_big = 0;                                // blocks with mp > 1024 (head of `order`)
+    int32_t n_test = 0;                               // selected test individuals (variance side channel), 0 = off
     int32_t cls_off[kNumClasses] = {0, 0, 0, 0};      // each size class is a contiguous range of `order`
     int32_t cls_n[kNumClasses] = {0, 0, 0, 0};
     // blob layout (byte offsets inside the plan blob, identical on host and device)
@@ -133,6 +134,9 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
     const int nb = a->n_blocks;
     P = Plan();
     P.n_blocks = nb;
+    int n_test = 0;
+    if (a->test_bed) for (int i = 0; i < a->test_n_total; ++i) n_test += (a->test_indicator[i] != 0);
+    P.n_test = n_test;
     P.blocks.resize(nb);
     P.tot_s = a->s_off[nb];
     P.tot_l = a->l_off ? a->l_off[nb] : 0;
@@ -152,7 +156,7 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
         d.moff = moff;
         d.out_s = a->s_off[b];
         d.out_l = a->l_off ? a->l_off[b] : 0;
-        d.pad = 0;
+        d.nrows = d.mp + 8 + n_test * (1 + (ml > 0 ? 1 : 0));       // test-genotype rows of the variance side channel
         const int miss = miss_in ? (miss_in[b] != 0) : 0;
         for (int j = 0; j < ms; ++j) {
             const int32_t p = a->s_pos[a->s_off[b] + j];
@@ -165,7 +169,7 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
         d.has_missing = miss;
         goff += d.m;
         croff += (int64_t)d.m * (miss ? 2 : 1);
-        if (d.m > 0) moff += align_up((size_t)(d.mp + 8) * d.ld, 16);
+        if (d.m > 0) moff += align_up((size_t)d.nrows * d.ld, 16);
         P.max_mp = std::max(P.max_mp, d.mp);
         const double m = d.m;
         P.gram_ops += (miss ? 4.0 : 1.0) * (double)h->n_pad * m * (m + 1.0);   // 2 ops per MAC, lower triangle
@@ -220,7 +224,7 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
                 const BlockDesc& d = P.blocks[b];
                 if ((d.mp + 63) / 64 <= k) continue;
                 const int wk = std::min(64, d.mp - 64 * k);
-                ntiles += (d.mp + 8 - (64 * k + wk) + 127) / 128;
+                ntiles += (d.nrows - (64 * k + wk) + 127) / 128;
             }
             int nsl = 1;
             if (ntiles > 0) nsl = std::max(1, std::min({8, k / 4, kTargetCtas / ntiles}));
@@ -233,7 +237,7 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
                 diag_items.push_back(b);
                 const int wk = std::min(64, d.mp - 64 * k);
                 const int below = 64 * k + wk;
-                const int nt = (d.mp + 8 - below + 127) / 128;
+                const int nt = (d.nrows - below + 127) / 128;
                 for (int t = 0; t < nt; ++t) {
                     const int gid = (nsl > 1) ? n_groups++ : 0;
                     for (int sl = 0; sl < nsl; ++sl) panel_items.push_back(make_int4(b, t, sl | (nsl << 8), gid));
@@ -482,6 +486,14 @@ int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
         return fail(h, DBSLMM_B200_ERR_ARG, "fit: unknown solver");
     for (int f = 0; f < a->n_folds; ++f)
         if (!(a->sigma_s[f] > 0.0)) return fail(h, DBSLMM_B200_ERR_ARG, "fit: sigma_s must be > 0");
+    const bool want_var = a->test_bed != nullptr;
+    if (want_var) {
+        if (a->solver != DBSLMM_B200_SOLVER_CHOLESKY) return fail(h, DBSLMM_B200_ERR_ARG, "fit: the variance side channel needs the Cholesky solver");
+        if (a->test_n_snp <= 0 || a->test_n_total <= 1 || !a->test_indicator || !a->variance_out || (a->s_off[a->n_blocks] > 0 && !a->s_tpos) ||
+            (a->l_off && a->l_off[a->n_blocks] > 0 && !a->l_tpos))
+            return fail(h, DBSLMM_B200_ERR_ARG, "fit: incomplete test-data arguments for the variance side channel");
+        if (a->flags & DBSLMM_B200_FLAG_PLAN_CACHED) return fail(h, DBSLMM_B200_ERR_ARG, "fit: PLAN_CACHED cannot be combined with the variance side channel");
+    }
     CU_TRY(h, cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
     const bool pcg = (a->solver == DBSLMM_B200_SOLVER_PCG);
@@ -631,6 +643,40 @@ int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
         CU_TRY(h, launch_fill_z(d_blocks, nb, d_z, (double*)h->sigma.p, st));
         ++n_launch;
     }
+    double* d_var = nullptr;
+    if (want_var && P.n_test > 0 && P.n_snp_rows > 0) {
+        // ---- variance side channel: test panel, selection list and per-SNP test rows to the device, then the
+        // standardised test genotypes become extra rows of every block matrix
+        const int32_t tpitch = (a->test_n_total + 3) / 4;
+        const size_t tbytes = (size_t)a->test_n_snp * tpitch;
+        std::vector<int32_t> sel, tpos((size_t)P.n_snp_rows);
+        for (int i = 0; i < a->test_n_total; ++i) if (a->test_indicator[i] != 0) sel.push_back(i);
+        for (int b = 0; b < nb; ++b) {
+            const BlockDesc& d = P.blocks[b];
+            for (int j = 0; j < d.m; ++j) {
+                const int32_t tp = (j < d.ms) ? a->s_tpos[a->s_off[b] + j] : a->l_tpos[a->l_off[b] + (j - d.ms)];
+                if (tp < 0 || tp >= a->test_n_snp) return fail(h, DBSLMM_B200_ERR_ARG, "fit: test .bed row out of range");
+                tpos[(size_t)d.goff + j] = tp;
+            }
+        }
+        size_t o = 0;
+        auto place = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
+        const size_t o_sel = place(sizeof(int32_t) * sel.size()), o_tpos = place(sizeof(int32_t) * tpos.size()),
+                     o_mu = place(sizeof(double) * tpos.size()), o_isd = place(sizeof(double) * tpos.size()),
+                     o_var = place(sizeof(double) * (size_t)a->n_folds * nb * P.n_test);
+        CU_TRY(h, h->vbed.ensure(tbytes + 64));
+        CU_TRY(h, h->vwork.ensure(o));
+        uint8_t* vw = (uint8_t*)h->vwork.p;
+        CU_TRY(h, cudaMemcpyAsync(h->vbed.p, a->test_bed, tbytes, cudaMemcpyHostToDevice, st));
+        CU_TRY(h, cudaMemcpyAsync(vw + o_sel, sel.data(), sizeof(int32_t) * sel.size(), cudaMemcpyHostToDevice, st));
+        CU_TRY(h, cudaMemcpyAsync(vw + o_tpos, tpos.data(), sizeof(int32_t) * tpos.size(), cudaMemcpyHostToDevice, st));
+        CU_TRY(h, cudaStreamSynchronize(st));      // sel / tpos are stack-lifetime host vectors
+        CU_TRY(h, launch_test_rows(d_blocks, nb, (const uint8_t*)h->vbed.p, a->test_n_total, (const int32_t*)(vw + o_sel),
+                                   P.n_test, (const int32_t*)(vw + o_tpos), P.n_snp_rows, (double*)(vw + o_mu),
+                                   (double*)(vw + o_isd), (double*)h->sigma.p, st));
+        n_launch += 2;
+        d_var = (double*)(vw + o_var);
+    }
     CU_TRY(h, cudaEventRecord(h->ev[3], st));
 
     // ---- solve, once per heritability fold (Sigma is shared: only the ridge changes)
@@ -667,6 +713,11 @@ int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
                 ++n_launch;
                 CU_TRY(h, cudaEventRecord(h->ev_join[c], cs));
                 CU_TRY(h, cudaStreamWaitEvent(st, h->ev_join[c], 0));
+            }
+            if (d_var) {
+                CU_TRY(h, launch_variance(d_blocks, nb, P.n_test, (const double*)h->sigma.p, (const double*)h->lbuf.p,
+                                          a->sigma_s[f], (double)a->n_obs, d_var + (size_t)f * nb * P.n_test, st));
+                ++n_launch;
             }
             if (a->timing) {
                 // factorisation time of this fold = latest class end (events are read after a sync)
@@ -721,6 +772,8 @@ int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
     if (n_out) CU_TRY(h, cudaMemcpyAsync(hout, d_beta, sizeof(double) * n_out * nfold, cudaMemcpyDeviceToHost, st));
     CU_TRY(h, cudaMemcpyAsync(hout + sizeof(double) * n_out * nfold, d_status, sizeof(int32_t) * (size_t)(2 * nb),
                               cudaMemcpyDeviceToHost, st));
+    if (d_var) CU_TRY(h, cudaMemcpyAsync(a->variance_out, d_var, sizeof(double) * (size_t)a->n_folds * nb * P.n_test,
+                                         cudaMemcpyDeviceToHost, st));
     CU_TRY(h, cudaEventRecord(h->ev[5], st));
     CU_TRY(h, cudaStreamSynchronize(st));
     {

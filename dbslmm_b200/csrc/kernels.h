@@ -59,6 +59,13 @@ cudaError_t launch_backsolve(const BlockDesc* blocks, const int32_t* order, int3
                              cudaStream_t st);
 cudaError_t chol_configure();
 
+// variance.cu
+cudaError_t launch_test_rows(const BlockDesc* blocks, int32_t n_blocks, const uint8_t* tbed, int32_t n_test_total,
+                             const int32_t* sel, int32_t n_test, const int32_t* tpos, int64_t n_rows, double* tmu,
+                             double* tisd, double* sigma, cudaStream_t st);
+cudaError_t launch_variance(const BlockDesc* blocks, int32_t n_blocks, int32_t n_test, const double* sigma,
+                            const double* Lbuf, double sigma_s, double n_obs, double* out, cudaStream_t st);
+
 // score.cu
 cudaError_t launch_prs(const uint8_t* bed, int32_t n_val, const SnpStat* stats, const int32_t* pos, const uint8_t* flip,
                        const double* beta, int64_t beta_stride, int32_t n_scored, int32_t nf, int32_t n_chunks,

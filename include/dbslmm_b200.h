@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DBSLMM_B200_ABI_VERSION 1
+#define DBSLMM_B200_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define DBSLMM_B200_API __attribute__((visibility("default")))
@@ -88,6 +88,18 @@ typedef struct dbslmm_b200_fit_args {
     double*  beta_l_out;      /* [n_folds][l_off[n_blocks]] or NULL                                  */
     int32_t* block_status_out;/* [n_blocks] or NULL                                                  */
     dbslmm_b200_timing* timing; /* or NULL                                                           */
+    /* ---- optional: the fork's asymptotic-variance side channel (scr/calc_asymptotic_variance.cpp:22-57,
+     * called from calcBlock, scr/dbslmmfit.cpp:484-490 / 516-519).  All NULL/0 => not computed.
+     * For every block and every selected test individual i: variance_out[f][b][i] =
+     * (X_l var_bl X_l' + X_s var_bs X_s')_ii with the test genotypes standardised within the selected
+     * subset (dbslmmfit.cpp:427-429).  Cholesky solver only. */
+    const uint8_t* test_bed;        /* host SNP-major .bed payload (after the magic bytes) of the test data    */
+    int64_t  test_n_snp;            /* rows of test_bed                                                        */
+    int32_t  test_n_total;          /* individuals in test_bed                                                 */
+    const int32_t* test_indicator;  /* [test_n_total] != 0 => individual belongs to the test set              */
+    const int32_t* s_tpos;          /* [s_off[n_blocks]] test .bed row of every small SNP                      */
+    const int32_t* l_tpos;          /* [l_off[n_blocks]] or NULL                                               */
+    double*  variance_out;          /* [n_folds][n_blocks][n_test], n_test = #selected individuals             */
 } dbslmm_b200_fit_args;
 
 #define DBSLMM_B200_FLAG_KEEP_INT_GRAM 1  /* also keep raw int32 Gram planes for dbslmm_b200_get_block_gram */

@@ -429,6 +429,74 @@ ORC_API int orc_est(const uint8_t* bed, int n_ref, int n_obs, double sigma_s, do
     return singular;
 }
 
+// ---- the fork's asymptotic-variance side channel for ONE block ------------------
+// calcBlock's test-genotype loop (dbslmmfit.cpp:427-429, 464-466: readSNPIm with the test indicator +
+// nomalizeVec WITHIN the test subset) and calc_nt_by_nt_matrix (calc_asymptotic_variance.cpp:22-57):
+//   Ainv = (I/(n sigma2) + Sigma_ss)^-1,  var_bl = (Sigma_ll - Sigma_sl' Ainv Sigma_sl)^-1 / n,
+//   var_bs = n sigma2^2 (mat1 + mat2 n var_bl mat2'),  mat1 = Sigma_ss - Sigma_ss Ainv Sigma_ss,
+//   mat2 = Sigma_sl - Sigma_ss Ainv Sigma_sl;  out_i = (X_l var_bl X_l' + X_s var_bs X_s')_ii.
+// Dense and O(m^3): for test sizes only.
+ORC_API int orc_variance_block(const uint8_t* bed, int n_ref, const uint8_t* tbed, int n_test_total,
+                               const int* indicator, int n_obs, double sigma_s, double tau,
+                               const int32_t* pos_s, const int32_t* tpos_s, int ms,
+                               const int32_t* pos_l, const int32_t* tpos_l, int ml, double* out) {
+    int n_test = 0;
+    for (int i = 0; i < n_test_total; ++i) n_test += (indicator[i] != 0);
+    const int m = ms + ml;
+    std::vector<int32_t> pos(m);
+    for (int j = 0; j < ms; ++j) pos[j] = pos_s[j];
+    for (int j = 0; j < ml; ++j) pos[ms + j] = pos_l[j];
+    std::vector<double> X;                                   // reference panel, all block SNPs (small first)
+    load_geno(bed, n_ref, pos.data(), m, X);
+    std::vector<double> Sg((size_t)m * m);
+    atb(X.data(), m, X.data(), m, n_ref, Sg.data());
+    for (auto& v : Sg) v *= tau / (double)n_ref;
+    for (int i = 0; i < m; ++i) Sg[(size_t)i * m + i] += (1.0 - tau);
+    auto S = [&](int i, int j) -> double { return Sg[(size_t)j * m + i]; };
+    // standardised test genotypes, n_test x m (col-major)
+    std::vector<double> T((size_t)n_test * m);
+    for (int j = 0; j < m; ++j) {
+        double maf;
+        const int32_t tp = (j < ms) ? tpos_s[j] : tpos_l[j - ms];
+        read_snp_im(tbed, tp, n_test_total, indicator, T.data() + (size_t)j * n_test, &maf);
+        normalize_vec(T.data() + (size_t)j * n_test, n_test);
+    }
+    const double dn = (double)n_obs;
+    // Ainv via Cholesky of A
+    std::vector<double> A((size_t)ms * ms), Ainv((size_t)ms * ms, 0.0);
+    for (int j = 0; j < ms; ++j) for (int i = 0; i < ms; ++i) A[(size_t)j * ms + i] = S(i, j) + (i == j ? 1.0 / (dn * sigma_s) : 0.0);
+    if (chol_lower(A.data(), ms)) return 1;
+    for (int c = 0; c < ms; ++c) { double* col = &Ainv[(size_t)c * ms]; col[c] = 1.0; chol_solve(A.data(), ms, col); }
+    auto AI = [&](int i, int j) -> double { return Ainv[(size_t)j * ms + i]; };
+    // G = Ainv Sigma_sl (ms x ml), SA = Sigma_ss Ainv (ms x ms)
+    std::vector<double> G((size_t)ms * std::max(ml, 1), 0.0), SA((size_t)ms * ms, 0.0);
+    for (int c = 0; c < ml; ++c) for (int i = 0; i < ms; ++i) { double s = 0; for (int k = 0; k < ms; ++k) s += AI(i, k) * S(k, ms + c); G[(size_t)c * ms + i] = s; }
+    for (int j = 0; j < ms; ++j) for (int i = 0; i < ms; ++i) { double s = 0; for (int k = 0; k < ms; ++k) s += S(i, k) * AI(k, j); SA[(size_t)j * ms + i] = s; }
+    std::vector<double> var_bl((size_t)std::max(ml, 1) * std::max(ml, 1), 0.0);
+    if (ml > 0) {
+        std::vector<double> big((size_t)ml * ml);
+        for (int b = 0; b < ml; ++b) for (int a = 0; a < ml; ++a) { double s = 0; for (int i = 0; i < ms; ++i) s += S(i, ms + a) * G[(size_t)b * ms + i]; big[(size_t)b * ml + a] = S(ms + a, ms + b) - s; }
+        if (chol_lower(big.data(), ml)) return 2;
+        for (int c = 0; c < ml; ++c) { double* col = &var_bl[(size_t)c * ml]; col[c] = 1.0; chol_solve(big.data(), ml, col); for (int a = 0; a < ml; ++a) col[a] /= dn; }
+    }
+    // var_bs = n sigma^2 sigma^2 (mat1 + mat2 n var_bl mat2')
+    std::vector<double> mat1((size_t)ms * ms), mat2((size_t)ms * std::max(ml, 1), 0.0), var_bs((size_t)ms * ms);
+    for (int j = 0; j < ms; ++j) for (int i = 0; i < ms; ++i) { double s = 0; for (int k = 0; k < ms; ++k) s += SA[(size_t)k * ms + i] * S(k, j); mat1[(size_t)j * ms + i] = S(i, j) - s; }
+    for (int c = 0; c < ml; ++c) for (int i = 0; i < ms; ++i) { double s = 0; for (int k = 0; k < ms; ++k) s += SA[(size_t)k * ms + i] * S(k, ms + c); mat2[(size_t)c * ms + i] = S(i, ms + c) - s; }
+    for (int j = 0; j < ms; ++j) for (int i = 0; i < ms; ++i) {
+        double s = 0;
+        for (int a = 0; a < ml; ++a) for (int b = 0; b < ml; ++b) s += mat2[(size_t)a * ms + i] * dn * var_bl[(size_t)b * ml + a] * mat2[(size_t)b * ms + j];
+        var_bs[(size_t)j * ms + i] = dn * sigma_s * sigma_s * (mat1[(size_t)j * ms + i] + s);
+    }
+    for (int t = 0; t < n_test; ++t) {
+        double d = 0;
+        for (int a = 0; a < ml; ++a) for (int b = 0; b < ml; ++b) d += T[(size_t)(ms + a) * n_test + t] * var_bl[(size_t)b * ml + a] * T[(size_t)(ms + b) * n_test + t];
+        for (int i = 0; i < ms; ++i) { double s = 0; for (int j = 0; j < ms; ++j) s += var_bs[(size_t)j * ms + i] * T[(size_t)j * n_test + t]; d += T[(size_t)i * n_test + t] * s; }
+        out[t] = d;
+    }
+    return 0;
+}
+
 ORC_API int orc_num_threads() {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -149,3 +149,22 @@ def est(bed, n_ref, n_obs, sigma_s, s_off, s_pos, s_z, l_off=None, l_pos=None, l
 
 def num_threads():
     return lib().orc_num_threads()
+
+
+def variance_block(bed, n_ref, tbed, n_test_total, indicator, n_obs, sigma_s, pos_s, tpos_s, pos_l=None, tpos_l=None, tau=0.8):
+    """The fork's per-block prediction-variance diagonal (calc_nt_by_nt_matrix(...).diag())."""
+    bed = _bed(bed); tbed = _bed(tbed)
+    ind = np.ascontiguousarray(indicator, np.int32)
+    pos_s = np.ascontiguousarray(pos_s, np.int32); tpos_s = np.ascontiguousarray(tpos_s, np.int32)
+    ml = 0 if pos_l is None else len(pos_l)
+    if ml:
+        pos_l = np.ascontiguousarray(pos_l, np.int32); tpos_l = np.ascontiguousarray(tpos_l, np.int32)
+    else:
+        pos_l = tpos_l = None
+    out = np.zeros(int(ind.sum()), np.float64)
+    rc = lib().orc_variance_block(_p(bed), C.c_int(n_ref), _p(tbed), C.c_int(n_test_total), _p(ind), C.c_int(n_obs),
+                                  C.c_double(sigma_s), C.c_double(tau), _p(pos_s), _p(tpos_s), C.c_int(pos_s.size),
+                                  _p(pos_l), _p(tpos_l), C.c_int(ml), _p(out))
+    if rc:
+        raise RuntimeError(f"orc_variance_block: not positive definite ({rc})")
+    return out

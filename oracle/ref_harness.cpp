@@ -10,6 +10,7 @@
 #include "omp.h"
 #include "dtpr.hpp"
 #include "dbslmmfit.hpp"
+#include "calc_asymptotic_variance.hpp"
 
 #define REF_API extern "C" __attribute__((visibility("default")))
 
@@ -108,4 +109,48 @@ REF_API int ref_est_path(const char* bed_path, int n_ref, int n_obs, double sigm
         }
     }
     return 0;
+}
+
+// The fork's variance side channel for one block through the reference's own functions:
+// test genotypes as calcBlock reads them (dbslmmfit.cpp:427-429, 464-466), estBlock's Sigma matrices,
+// calc_nt_by_nt_matrix(...).diag() (calc_asymptotic_variance.cpp:22-57).
+static arma::mat load_test_cols(const char* path, int n_total, const int* indicator, const int32_t* pos, int m) {
+    IO io; SNPPROC sp;
+    std::ifstream in(path, std::ios::binary);
+    std::vector<int> ind(indicator, indicator + n_total);
+    int n_test = 0;
+    for (int v : ind) n_test += (v != 0);
+    arma::mat X = arma::zeros<arma::mat>(n_test, m);
+    for (int j = 0; j < m; ++j) {
+        arma::vec g = arma::zeros<arma::vec>(n_test);
+        double maf = 0.0;
+        io.readSNPIm(pos[j], n_test, ind, in, g, maf);
+        sp.nomalizeVec(g);
+        X.col(j) = g;
+    }
+    return X;
+}
+
+REF_API int ref_variance_block(const char* bed_path, int n_ref, const char* tbed_path, int n_test_total,
+                               const int* indicator, int n_obs, double sigma_s,
+                               const int32_t* pos_s, const int32_t* tpos_s, int ms,
+                               const int32_t* pos_l, const int32_t* tpos_l, int ml, double* out) {
+    DBSLMMFIT f;
+    arma::mat Xs = load_cols(bed_path, n_ref, pos_s, ms);
+    arma::mat Ts = load_test_cols(tbed_path, n_test_total, indicator, tpos_s, ms);
+    arma::vec zs = arma::zeros<arma::vec>(ms), bs = arma::zeros<arma::vec>(ms);
+    arma::mat result;
+    if (ml > 0) {
+        arma::mat Xl = load_cols(bed_path, n_ref, pos_l, ml);
+        arma::mat Tl = load_test_cols(tbed_path, n_test_total, indicator, tpos_l, ml);
+        arma::vec zl = arma::zeros<arma::vec>(ml), bl = arma::zeros<arma::vec>(ml);
+        arma::field<arma::mat> o = f.estBlock(n_ref, n_obs, sigma_s, Xs, Xl, zs, zl, bs, bl);
+        result = calc_nt_by_nt_matrix(o(2), o(1), o(0), sigma_s, (unsigned)n_obs, Tl, Ts);   // as dbslmmfit.cpp:484-490
+    } else {
+        arma::field<arma::mat> o = f.estBlock(n_ref, n_obs, sigma_s, Xs, zs, bs);
+        result = calc_nt_by_nt_matrix(o(0), sigma_s, (unsigned)n_obs, Ts);                    // :516-519
+    }
+    arma::vec d = result.diag();
+    std::memcpy(out, d.memptr(), sizeof(double) * d.n_elem);
+    return (int)d.n_elem;
 }

@@ -110,3 +110,18 @@ def est_path(bed_path, n_ref, n_obs, sigma_s, s_off, s_pos, s_z, l_off=None, l_p
     lib().ref_est_path(bed_path.encode(), C.c_int(n_ref), C.c_int(n_obs), C.c_double(sigma_s), C.c_int(s_off.size - 1),
                        _p(s_off), _p(s_pos), _p(s_z), _p(l_off), _p(l_pos), _p(l_z), C.c_int(threads), _p(bs), _p(bl))
     return bs, bl[:nl]
+
+
+def variance_block(bed_path, n_ref, tbed_path, n_test_total, indicator, n_obs, sigma_s, pos_s, tpos_s, pos_l=None, tpos_l=None):
+    ind = np.ascontiguousarray(indicator, np.int32)
+    pos_s = np.ascontiguousarray(pos_s, np.int32); tpos_s = np.ascontiguousarray(tpos_s, np.int32)
+    ml = 0 if pos_l is None else len(pos_l)
+    if ml:
+        pos_l = np.ascontiguousarray(pos_l, np.int32); tpos_l = np.ascontiguousarray(tpos_l, np.int32)
+    else:
+        pos_l = tpos_l = None
+    out = np.zeros(int(ind.sum()), np.float64)
+    lib().ref_variance_block(bed_path.encode(), C.c_int(n_ref), tbed_path.encode(), C.c_int(n_test_total), _p(ind),
+                             C.c_int(n_obs), C.c_double(sigma_s), _p(pos_s), _p(tpos_s), C.c_int(pos_s.size),
+                             _p(pos_l), _p(tpos_l), C.c_int(ml), _p(out))
+    return out

@@ -24,12 +24,12 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), n
     assert sorted(_abi.EXPORTS) == names
-    assert lib.dbslmm_b200_abi_version() == 1
+    assert lib.dbslmm_b200_abi_version() == 2
 
 
 def test_fit_args_struct_layout_matches_header():
-    # 17 fields, natural alignment on LP64: the ctypes mirror must be 128 bytes like the C struct
-    assert C.sizeof(_abi.FitArgs) == 128
+    # natural alignment on LP64: the ctypes mirror must have the size of the C struct (17 + 7 fields)
+    assert C.sizeof(_abi.FitArgs) == 184
     assert C.sizeof(_abi.Timing) == 80
 
 

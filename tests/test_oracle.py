@@ -169,3 +169,23 @@ def test_oracle_against_live_reference_build(ragged):
         r_s, r_l = R.est_block(bf.path, n, int(d["n_obs"]), float(d["sigma_s"]), ps, zs, pl, zl)
         o_s, o_l, _, _ = O.est_block(d["bed"], n, int(d["n_obs"]), float(d["sigma_s"]), ps, zs, pl, zl, mode=O.MODE_REF)
         assert relmax(o_s, r_s) < 2e-7 and relmax(o_l, r_l) < 2e-7
+
+
+@pytest.mark.skipif(not R.available(), reason="oracle/_ref (unmodified reference build) not present")
+@pytest.mark.parametrize("with_large", [True, False])
+def test_variance_oracle_against_live_reference_build(ragged, with_large):
+    """calc_nt_by_nt_matrix(...).diag() through the reference's own functions vs the oracle restatement."""
+    d = ragged
+    n = int(d["n_ref"])
+    rng = np.random.default_rng(9)
+    from dbslmm_b200 import synth
+    Gt = synth.make_genotypes(rng, [int(d["sizes"].sum())], 57, missing_rate=0.02)
+    tbed = synth.pack_bed(Gt)
+    ind = (rng.random(57) < 0.6).astype(np.int32)
+    b = 0
+    ps = d["s_pos"][d["s_off"][b]:d["s_off"][b + 1]]
+    pl = d["l_pos"][d["l_off"][b]:d["l_off"][b + 1]] if with_large else None
+    with R.BedFile(d["bed"]) as b1, R.BedFile(tbed) as b2:
+        ref = R.variance_block(b1.path, n, b2.path, 57, ind, int(d["n_obs"]), float(d["sigma_s"]), ps, ps, pl, pl)
+    got = O.variance_block(d["bed"], n, tbed, 57, ind, int(d["n_obs"]), float(d["sigma_s"]), ps, ps, pl, pl)
+    assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max()
