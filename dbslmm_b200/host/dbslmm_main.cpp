@@ -6,8 +6,10 @@
 // through include/dbslmm_b200.h; there is no CPU path.
 //
 // Differences on purpose:
-//   * -test_indicator_file / -dat_str are accepted and ignored: the fork's asymptotic-variance
-//     side channel (variance.txt) is outside this path; nothing else depends on them.
+//   * -test_indicator_file / -dat_str are OPTIONAL (the fork crashes without them): when both are given the
+//     asymptotic-variance side channel runs on the GPU and `variance.txt` (n_test x num_block, Armadillo
+//     ASCII layout) is written to the working directory like scr/dbslmmfit.cpp:242; a SNP that is absent
+//     from the test .bim is an error (the reference silently misaligns its vectors in that case).
 //   * hidden additions: --solver chol|pcg, --gpus N, --tau T, --h2-folds a,b,c (one Gram, several
 //     ridge folds, outputs <eff>_f<k>.txt), --dump-beta-bin FILE (FP64 betas; the text output
 //     only has 6 significant digits), --verbose.
@@ -27,6 +29,7 @@
 #include <string>
 #include <sys/time.h>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "dbslmm_b200.h"
@@ -115,7 +118,8 @@ struct Shard {                                   // what one GPU fits
     vector<int> blocks;                          // global block ids, ascending
     vector<int32_t> s_off, s_pos, l_off, l_pos;
     vector<double> s_z, l_z, beta_s, beta_l;
-    vector<int32_t> status;
+    vector<int32_t> status, s_tpos, l_tpos;
+    vector<double> variance;                     // [n_folds][blocks][n_test]
     vector<uint8_t> bed;                         // compact .bed (only when gpus > 1)
     int64_t n_rows = 0;
     int rc = 0;
@@ -186,8 +190,9 @@ int main(int argc, char* argv[]) {
     if (cPar.t > 100 || cPar.t < 1) { cerr << "ERROR: -t is not correct (1, 100)!" << endl; exit(1); }
     if (cPar.n <= 0 || cPar.nsnp <= 0) { cerr << "ERROR: -n and -nsnp must be positive!" << endl; exit(1); }
     const int solver = (cPar.solver == "pcg") ? DBSLMM_B200_SOLVER_PCG : DBSLMM_B200_SOLVER_CHOLESKY;
-    if (!cPar.test_indicator_file.empty() || !cPar.dat_str.empty())
-        cout << "[NOTE] -test_indicator_file/-dat_str: the asymptotic-variance side channel is not part of this build; no variance.txt is written." << endl;
+    const bool want_var = !cPar.test_indicator_file.empty() && !cPar.dat_str.empty();
+    if (want_var && jobs.size() > 1) { cerr << "ERROR: the variance side channel (-dat_str) is per chromosome: not available with --manifest" << endl; exit(1); }
+    if (want_var && solver != DBSLMM_B200_SOLVER_CHOLESKY) { cerr << "ERROR: the variance side channel needs --solver chol" << endl; exit(1); }
 
     const int n_dev = dbslmm_b200_device_count();
     if (n_dev <= 0) { cerr << "ERROR: no CUDA device: dbslmm_b200 has no CPU fallback." << endl; exit(2); }
@@ -334,6 +339,48 @@ int main(int argc, char* argv[]) {
         sh.status.assign(sh.blocks.size() + 1, 0);
     }
 
+    // ---- variance side channel inputs (dbslmm.cpp:265-275, 300-304, 319-320): test .bim positions, indicator, test .bed
+    vector<int32_t> test_indicator;
+    vector<uint8_t> test_bed;
+    int64_t test_n_snp = 0;
+    int n_test = 0;
+    if (want_var) {
+        ifstream ind(cPar.test_indicator_file.c_str());
+        if (!ind) { cerr << "ERROR: " << cPar.test_indicator_file << " dose not exist!" << endl; exit(1); }
+        string line;
+        while (getline(ind, line)) test_indicator.push_back(atoi(line.c_str()));                 // read_indices_file: first field
+        for (int v : test_indicator) n_test += (v != 0);
+        unordered_map<long, int32_t> ps2row;                                                      // readTestBim + makePosObjectForTestBim
+        ifstream tb((cPar.dat_str + ".bim").c_str());
+        if (!tb) { cerr << "ERROR: " << cPar.dat_str << ".bim dose not exist!" << endl; exit(1); }
+        while (getline(tb, line)) {
+            vector<string> t; stringstream ss(line); string e;
+            while (getline(ss, e, '\t')) t.push_back(e);
+            if (t.size() >= 4) ps2row.emplace(atol(t[3].c_str()), (int32_t)test_n_snp);          // first match wins, like the linear scan
+            test_n_snp++;
+        }
+        if (!read_bed(cPar.dat_str + ".bed", test_n_snp, (int)test_indicator.size(), test_bed)) {
+            cerr << "ERROR: cannot read SNP-major " << cPar.dat_str << ".bed" << endl; exit(1);
+        }
+        auto lookup = [&](long ps, const string& snp) -> int32_t {
+            auto it = ps2row.find(ps);
+            if (it == ps2row.end()) { cerr << "ERROR: SNP " << snp << " (position " << ps << ") is not in " << cPar.dat_str << ".bim" << endl; exit(1); }
+            return it->second;
+        };
+        const Job& j = jobs[0];
+        vector<int32_t> s_tp(j.info_s.size()), l_tp(j.info_l.size());
+        for (size_t i = 0; i < j.info_s.size(); ++i) s_tp[i] = lookup(j.info_s.ps[i], j.info_s.snp[i]);
+        for (size_t i = 0; i < j.info_l.size(); ++i) l_tp[i] = lookup(j.info_l.ps[i], j.info_l.snp[i]);
+        for (int g = 0; g < n_gpus; ++g) {
+            Shard& sh = shards[g];
+            for (int b : sh.blocks) {
+                for (int q = s_off[b]; q < s_off[b + 1]; ++q) sh.s_tpos.push_back(s_tp[q]);
+                if (with_large) for (int q = l_off[b]; q < l_off[b + 1]; ++q) sh.l_tpos.push_back(l_tp[q]);
+            }
+            sh.variance.assign((size_t)n_folds * sh.blocks.size() * std::max(n_test, 1) + 1, 0.0);
+        }
+    }
+
     // ---- fit (the reference's "Fitting time" window, dbslmm.cpp:331-350 / 372-388)
     const double t_fitting = walltime();
     cout << "Fitting model..." << endl;
@@ -353,6 +400,11 @@ int main(int argc, char* argv[]) {
         a.solver = solver; a.flags = 0;
         a.beta_s_out = sh.beta_s.data(); a.beta_l_out = with_large ? sh.beta_l.data() : nullptr;
         a.block_status_out = sh.status.data(); a.timing = &sh.timing;
+        if (want_var) {
+            a.test_bed = test_bed.data(); a.test_n_snp = test_n_snp; a.test_n_total = (int32_t)test_indicator.size();
+            a.test_indicator = test_indicator.data(); a.s_tpos = sh.s_tpos.data();
+            a.l_tpos = with_large ? sh.l_tpos.data() : nullptr; a.variance_out = sh.variance.data();
+        }
         sh.rc = dbslmm_b200_fit(hs[g], &a);
         if (sh.rc < 0) sh.err = dbslmm_b200_last_error(hs[g]);
     };
@@ -411,6 +463,28 @@ int main(int argc, char* argv[]) {
                     effFout << j.info_s.snp[i] << " " << j.info_s.a1[i] << " " << b << " " << noscl << " " << 0 << endl;
             }
             effFout.close();
+        }
+    }
+    if (want_var) {
+        // diags.save("variance.txt", arma_ascii) (dbslmmfit.cpp:242, 361): n_test x num_block, cwd-relative
+        for (int f = 0; f < n_folds; ++f) {
+            vector<double> diags((size_t)n_test * num_block, 0.0);
+            for (int g = 0; g < n_gpus; ++g) {
+                const Shard& sh = shards[g];
+                for (size_t i = 0; i < sh.blocks.size(); ++i)
+                    for (int t = 0; t < n_test; ++t)
+                        diags[(size_t)t * num_block + sh.blocks[i]] = sh.variance[((size_t)f * sh.blocks.size() + i) * n_test + t];
+            }
+            string name = "variance.txt";
+            if (n_folds > 1) { ostringstream o; o << "variance_f" << f << ".txt"; name = o.str(); }
+            ofstream vf(name.c_str());
+            vf << "ARMA_MAT_TXT_FN008" << '\n' << n_test << ' ' << num_block << '\n';
+            vf.setf(ios::scientific);
+            vf.precision(16);
+            for (int t = 0; t < n_test; ++t) {
+                for (int b = 0; b < num_block; ++b) { vf.put(' '); vf.width(24); vf << diags[(size_t)t * num_block + b]; }
+                vf.put('\n');
+            }
         }
     }
     if (!cPar.dump_bin.empty()) {

@@ -114,3 +114,58 @@ def test_cli_manifest_two_chromosomes(tmp_path):
         vx, vy = np.array([g[2] for g in x]), np.array([g[2] for g in y])
         assert np.abs(vx - vy).max() <= 2e-6 * np.abs(vx).max()
         assert (tmp_path / f"{single}.badsnps").read_text() == (tmp_path / f"{multi}.badsnps").read_text()
+
+
+def _read_variance(path):
+    lines = path.read_text().split("\n")
+    assert lines[0] == "ARMA_MAT_TXT_FN008"
+    nr, nc = (int(x) for x in lines[1].split())
+    return np.array([[float(x) for x in ln.split()] for ln in lines[2:2 + nr]]).reshape(nr, nc)
+
+
+@pytest.mark.gpu
+def test_cli_variance_txt_c1_nan_pattern(tmp_path):
+    """test_dat has SNPs that are monomorphic in the test panel: the reference's variance column of block 0 is NaN
+    (stddev 0 in nomalizeVec, dtpr.cpp:378) and so is ours; the 132 empty blocks are 0 in both."""
+    d = _write_fixture(tmp_path)
+    (tmp_path / "test.bim").write_text(str(d["test_bim_txt"]))
+    with open(tmp_path / "test.bed", "wb") as f:
+        f.write(bytes([0x6C, 0x1B, 0x01]) + d["test_bed"].tobytes())
+    (tmp_path / "ind.txt").write_text("\n".join(str(int(x)) for x in d["test_indicator"]) + "\n")
+    cmd = [CLI, "-s", str(tmp_path / "s.txt"), "-l", str(tmp_path / "l.txt"), "-r", str(tmp_path / "ref"), "-n", "2400",
+           "-nsnp", "996", "-mafMax", "0.2", "-b", str(tmp_path / "blocks.bed"), "-h", "0.5", "-t", "1",
+           "-eff", str(tmp_path / "out"), "-test_indicator_file", str(tmp_path / "ind.txt"), "-dat_str", str(tmp_path / "test")]
+    r = subprocess.run(cmd, capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 0, r.stderr
+    got, ref = _read_variance(tmp_path / "variance.txt"), d["cli_dbslmm_variance"]
+    assert got.shape == ref.shape == (20, 133)
+    assert np.array_equal(np.isnan(got), np.isnan(ref)) and np.isnan(got[:, 0]).all() and not got[:, 1:].any()
+    got_txt, ref_txt = _parse((tmp_path / "out.txt").read_text()), _parse(str(d["cli_dbslmm_txt"]))
+    assert [(g[0], g[1], g[4]) for g in got_txt] == [(x[0], x[1], x[4]) for x in ref_txt]     # betas unaffected
+
+
+@pytest.mark.gpu
+def test_cli_variance_txt_matches_reference_cli(tmp_path):
+    """Synthetic chromosome as real PLINK/GEMMA files: <eff>.txt, <eff>.badsnps and variance.txt against what the
+    UNMODIFIED reference CLI wrote for the same files (tools/make_golden.py::synth_cli)."""
+    d = np.load(os.path.join(GOLD, "synth_cli.npz"))
+    for name, key in (("ref.bim", "bim_txt"), ("ref.fam", "fam_txt"), ("test.bim", "bim_txt"), ("test.fam", "test_fam_txt"),
+                      ("l.txt", "l_txt"), ("s.txt", "s_txt"), ("blocks.bed", "block_txt")):
+        (tmp_path / name).write_text(str(d[key]))
+    for name, key in (("ref.bed", "bed"), ("test.bed", "test_bed")):
+        with open(tmp_path / name, "wb") as f:
+            f.write(bytes([0x6C, 0x1B, 0x01]) + d[key].tobytes())
+    (tmp_path / "ind.txt").write_text("\n".join(str(int(x)) for x in d["test_indicator"]) + "\n")
+    cmd = [CLI, "-s", str(tmp_path / "s.txt"), "-l", str(tmp_path / "l.txt"), "-r", str(tmp_path / "ref"), "-n", "5000",
+           "-nsnp", "2000", "-mafMax", "0.2", "-b", str(tmp_path / "blocks.bed"), "-h", "0.4", "-t", "2",
+           "-eff", str(tmp_path / "out"), "-test_indicator_file", str(tmp_path / "ind.txt"), "-dat_str", str(tmp_path / "test")]
+    r = subprocess.run(cmd, capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 0, r.stderr
+    got, ref = _read_variance(tmp_path / "variance.txt"), d["cli_variance"]
+    assert got.shape == ref.shape and np.isfinite(got).all()
+    assert np.abs(got - ref).max() <= 1e-9 * np.abs(ref).max()
+    got_txt, ref_txt = _parse((tmp_path / "out.txt").read_text()), _parse(str(d["cli_txt"]))
+    assert [(g[0], g[1], g[4]) for g in got_txt] == [(x[0], x[1], x[4]) for x in ref_txt]
+    gb, rb = np.array([g[2] for g in got_txt]), np.array([x[2] for x in ref_txt])
+    assert np.abs(gb - rb).max() <= 5e-6 * np.abs(rb).max()
+    assert (tmp_path / "out.badsnps").read_text() == str(d["cli_badsnps"])

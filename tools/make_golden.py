@@ -81,6 +81,10 @@ def c1():
                 continue
             out["cli_" + mode + "_txt"] = open(td + "/out_" + mode + ".txt").read()
             out["cli_" + mode + "_badsnps"] = open(td + "/out_" + mode + ".badsnps").read()
+            # the fork's variance.txt (n_test x num_block; the shim writes Armadillo's arma_ascii layout)
+            vt = open(td + "/variance.txt").read().split("\n")
+            nr, nc = (int(x) for x in vt[1].split())
+            out["cli_" + mode + "_variance"] = np.array([[float(x) for x in ln.split()] for ln in vt[2:2 + nr]]).reshape(nr, nc)
     # ---- matched CSR problems + FP64 reference betas through the harness
     def problem(summ_subset_idx):
         sub = H.Summ([summ.snp[i] for i in summ_subset_idx], summ.ps[summ_subset_idx], [summ.a1[i] for i in summ_subset_idx],
@@ -98,6 +102,10 @@ def c1():
         s_off, s_pos, s_z = problem(small_idx)
         l_off, l_pos, l_z = problem(large_idx)
         b_s, b_l = R.est_path(bf.path, n_ref, n_obs, sigma_s, s_off, s_pos, s_z, l_off, l_pos, l_z, threads=1)
+    tn = H.read_fam_count(TD + "test_chr1.fam")
+    _, tnsnp = H.read_bim(TD + "test_chr1.bim")
+    out.update(dict(test_bed=H.read_bed(TD + "test_chr1.bed", tnsnp, tn), test_n_total=tn,
+                    test_bim_txt=open(TD + "test_chr1.bim").read(), test_indicator=np.array([1] * 20 + [0] * 83, np.int32)))
     out.update(dict(bed=bed, n_ref=n_ref, n_obs=n_obs, sigma_s=sigma_s, ref_maf=maf,
                     bim_txt=open(TD + "ref_chr1.bim").read(), fam_lines=n_ref, summary_txt="\n".join(lines) + "\n",
                     l_txt=l_txt, s_txt=s_txt, block_txt=blk_txt,
@@ -123,9 +131,55 @@ def ragged():
     print("ragged: large per block", np.diff(w["l_off"]))
 
 
+def synth_cli():
+    """A small synthetic chromosome as real PLINK / GEMMA text files, run through the UNMODIFIED reference CLI
+    including the fork's variance side channel (test_dat itself has SNPs that are monomorphic in the test
+    panel, which turns its whole variance column into NaN in the reference and here alike)."""
+    rng = np.random.default_rng(20240002)
+    sizes = [70, 110, 45]
+    n_ref, n_tt = 300, 90
+    w = synth.make_workload(20240002, sizes, n_ref, missing_rate=0.0, frac_large=0.03)
+    m = int(sum(sizes))
+    Gt = synth.make_genotypes(rng, [m], n_tt, missing_rate=0.01)
+    tbed = synth.pack_bed(Gt)
+    ind = (rng.random(n_tt) < 0.6).astype(np.int32)
+    starts = np.array([1000, 500000, 900000]); ends = np.array([500000, 900000, 2000000])
+    ps = np.concatenate([np.sort(rng.choice(np.arange(starts[b] + 1, ends[b] - 1), size=sizes[b], replace=False)) for b in range(3)])
+    z = np.zeros(m); z[w["s_pos"]] = w["s_z"]; z[w["l_pos"]] = w["l_z"]
+    S = np.where(w["G"] < 0, 0, w["G"]).sum(1); af = S / (2.0 * n_ref)
+    bim = "".join(f"1\trs{j}\t0\t{ps[j]}\tA\tG\n" for j in range(m))
+    fam = "".join(f"f{i} i{i} 0 0 0 -9\n" for i in range(n_ref))
+    tfam = "".join(f"t{i} i{i} 0 0 0 -9\n" for i in range(n_tt))
+    line = lambda j: f"1\trs{j}\t{ps[j]}\t0\t5000\tA\tG\t{af[j]:.6f}\t{z[j] * 0.01:.10e}\t1.0000000000e-02\t1.0e-03"
+    large = sorted(w["l_pos"].tolist()); ls = set(large)
+    l_txt = "\n".join(line(j) for j in large) + "\n"
+    s_txt = "\n".join(line(j) for j in range(m) if j not in ls) + "\n"
+    blk = "".join(f"chr1\t{starts[b]}\t{ends[b]}\n" for b in range(3))
+    out = dict(bed=w["bed"], n_ref=n_ref, bim_txt=bim, fam_txt=fam, test_bed=tbed, test_fam_txt=tfam, test_n_total=n_tt,
+               test_indicator=ind, l_txt=l_txt, s_txt=s_txt, block_txt=blk, sizes=np.asarray(sizes))
+    with tempfile.TemporaryDirectory() as td:
+        for name, txt in (("ref.bim", bim), ("ref.fam", fam), ("test.bim", bim), ("test.fam", tfam), ("l.txt", l_txt), ("s.txt", s_txt), ("blocks.bed", blk)):
+            open(os.path.join(td, name), "w").write(txt)
+        R.write_bed(w["bed"], os.path.join(td, "ref.bed"))
+        R.write_bed(tbed, os.path.join(td, "test.bed"))
+        open(os.path.join(td, "ind.txt"), "w").write("\n".join(str(int(x)) for x in ind) + "\n")
+        cmd = [R.CLI, "-s", td + "/s.txt", "-l", td + "/l.txt", "-r", td + "/ref", "-n", "5000", "-nsnp", "2000", "-mafMax", "0.2",
+               "-b", td + "/blocks.bed", "-h", "0.4", "-t", "2", "-eff", td + "/out", "-test_indicator_file", td + "/ind.txt", "-dat_str", td + "/test"]
+        subprocess.run(cmd, cwd=td, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        out["cli_txt"] = open(td + "/out.txt").read()
+        out["cli_badsnps"] = open(td + "/out.badsnps").read()
+        vt = open(td + "/variance.txt").read().split("\n")
+        nr, nc = (int(x) for x in vt[1].split())
+        out["cli_variance"] = np.array([[float(x) for x in ln.split()] for ln in vt[2:2 + nr]]).reshape(nr, nc)
+    assert np.isfinite(out["cli_variance"]).all()
+    np.savez_compressed(os.path.join(GOLD, "synth_cli.npz"), **out)
+    print("synth_cli: variance", out["cli_variance"].shape, "lines", len(out["cli_txt"].strip().split("\n")))
+
+
 if __name__ == "__main__":
     if not R.available():
         raise SystemExit("oracle/_ref missing: run oracle/build_ref.sh first")
     os.makedirs(GOLD, exist_ok=True)
     c1()
     ragged()
+    synth_cli()
