@@ -36,23 +36,24 @@ static constexpr int NST = 3;          // cp.async stages
 static constexpr int P_STAGE = TM * LDS;
 static constexpr int Q_STAGE = NB * LDS;
 static constexpr int STAGE = P_STAGE + Q_STAGE;
-static constexpr int LDT = NB + 4;     // stride of 64-wide epilogue tiles
+static constexpr int LDW = NB + 8;     // stride of the 64-wide epilogue tiles (W, L halves): conflict-free 128-bit fragment accesses
 static constexpr int CHOL_THREADS = 256;
 static constexpr int SMEM_PIPE = NST * STAGE * 8;
-static constexpr int SMEM_CT = 8 * 16 * LDT * 8;                           // macro tile C / L, aliases the pipeline
-static constexpr int W_OFF = SMEM_CT / 8;                                  // W tile follows the macro tile (doubles)
-static constexpr int SMEM_EPI = SMEM_CT + NB * LDT * 8;
-static constexpr int SMEM_CHOL = (SMEM_PIPE > SMEM_EPI ? SMEM_PIPE : SMEM_EPI);
+// The epilogue re-uses the three pipeline stages: one holds W_kk, the other two the two 64-row halves of L_ik.
+static_assert(NB * LDW == STAGE, "a 64 x LDW epilogue tile must fill exactly one pipeline stage");
+static constexpr int SMEM_CHOL = SMEM_PIPE;
 
 // acc (16 rows x 64 cols per warp) += P[r0.., 0:K] * Q[q0.., 0:K]^T, both row-major with K contiguous.
-// prow/qrow = number of valid rows (others are zero-filled).  All 256 threads must call.
+// prow/qrow = number of valid rows (others are zero-filled).  `wrow` = this warp's 16-row slot of the macro tile.
+// The dense 64x64 tile `wsrc` (W_kk of this step) rides through the ring as the chunk AFTER the last K chunk, so it
+// has landed (stride LDW) in stage (nchunk % NST) when the loop ends, at no extra latency.  All 256 threads must call.
 __device__ __forceinline__ void gemm_nt_core(const double* __restrict__ Pg, const double* __restrict__ Qg, int ld,
-                                             int prow, int qrow, int kbeg, int kend, double* smem,
-                                             double (&acc)[2][8][2]) {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+                                             int prow, int qrow, int kbeg, int kend, const double* __restrict__ wsrc,
+                                             int wrow, double* smem, double (&acc)[2][8][2]) {
+    const int tid = threadIdx.x, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     const int nchunk = (kend - kbeg) / KC;     // K range [kbeg, kend), both multiples of KC
-    const bool active = (16 * warp < prow);
+    const bool active = (16 * wrow < prow);
     Pg += kbeg;
     Qg += kbeg;
 
@@ -75,10 +76,20 @@ __device__ __forceinline__ void gemm_nt_core(const double* __restrict__ Pg, cons
             cp_async16(Qs + r * LDS + c2, Qg + (size_t)(v ? r : 0) * ld + k0 + c2, v);
         }
     };
+    auto load_w = [&](int s) {
+        double* Ws = smem + s * STAGE;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int idx = tid + u * CHOL_THREADS;
+            const int row = idx >> 5, ch = (idx & 31) * 2;
+            cp_async16(Ws + row * LDW + ch, wsrc + row * NB + ch, true);
+        }
+    };
 
 #pragma unroll
     for (int s = 0; s < NST - 1; ++s) {
         if (s < nchunk) load_stage(s, s);
+        else if (s == nchunk) load_w(s);
         cp_async_commit();
     }
     for (int kc = 0; kc < nchunk; ++kc) {
@@ -86,11 +97,12 @@ __device__ __forceinline__ void gemm_nt_core(const double* __restrict__ Pg, cons
         __syncthreads();
         const int nx = kc + NST - 1;
         if (nx < nchunk) load_stage(nx, nx % NST);
+        else if (nx == nchunk) load_w(nx % NST);
         cp_async_commit();
         if (active) {
             // One 128-bit load feeds two DMMAs: within each 8-wide K group lane t owns k = 2t (.x) and
             // k = 2t+1 (.y); A and B use the same assignment, so every product pairs the same k.
-            const double* Ps = smem + (kc % NST) * STAGE + (16 * warp + g) * LDS + 2 * t;
+            const double* Ps = smem + (kc % NST) * STAGE + (16 * wrow + g) * LDS + 2 * t;
             const double* Qs = smem + (kc % NST) * STAGE + P_STAGE + g * LDS + 2 * t;
 #pragma unroll
             for (int s8 = 0; s8 < KC / 8; ++s8) {
@@ -99,14 +111,14 @@ __device__ __forceinline__ void gemm_nt_core(const double* __restrict__ Pg, cons
                 double2 b[8];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) b[c] = *reinterpret_cast<const double2*>(Qs + c * 8 * LDS + s8 * 8);
+                // no per-column predicate (Q rows >= qrow are zero-filled): a predicated mma.sync costs a
+                // WARPSYNC + NOP pair per DMMA in SASS
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    if (8 * c < qrow) {
-                        dmma884(acc[0][c][0], acc[0][c][1], a0.x, b[c].x);
-                        dmma884(acc[1][c][0], acc[1][c][1], a1.x, b[c].x);
-                        dmma884(acc[0][c][0], acc[0][c][1], a0.y, b[c].y);
-                        dmma884(acc[1][c][0], acc[1][c][1], a1.y, b[c].y);
-                    }
+                    dmma884(acc[0][c][0], acc[0][c][1], a0.x, b[c].x);
+                    dmma884(acc[1][c][0], acc[1][c][1], a1.x, b[c].x);
+                    dmma884(acc[0][c][0], acc[0][c][1], a0.y, b[c].y);
+                    dmma884(acc[1][c][0], acc[1][c][1], a1.y, b[c].y);
                 }
             }
         }
@@ -304,19 +316,43 @@ chol_diag_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict
     diag_body(bd, blk, k, sigma, Lbuf, wbuf, ridge, status, smem);
 }
 
+// Look-ahead SYRK of one 16-row slot WL of a 64-row half: acc2 (rows 16WL.., columns 0 .. 16WL+15, lower triangle
+// of the tile) += A A^T with both operands read from the half tile in shared memory (stride LDW).
+template <int WL>
+__device__ __forceinline__ void syrk_rows(const double* __restrict__ A, const double* __restrict__ B,
+                                          double (&acc2)[2][8][2]) {
+#pragma unroll 2
+    for (int s8 = 0; s8 < NB / 8; ++s8) {
+        const double2 a0 = *reinterpret_cast<const double2*>(A + s8 * 8);
+        const double2 a1 = *reinterpret_cast<const double2*>(A + 8 * LDW + s8 * 8);
+#pragma unroll
+        for (int c = 0; c <= 2 * WL + 1; ++c) {
+            const double2 b = *reinterpret_cast<const double2*>(B + c * 8 * LDW + s8 * 8);
+            if (c <= 2 * WL) dmma884(acc2[0][c][0], acc2[0][c][1], a0.x, b.x);   // rows 16WL..+7 end at column block 2WL
+            dmma884(acc2[1][c][0], acc2[1][c][1], a1.x, b.x);
+            if (c <= 2 * WL) dmma884(acc2[0][c][0], acc2[0][c][1], a0.y, b.y);
+            dmma884(acc2[1][c][0], acc2[1][c][1], a1.y, b.y);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // Rows below the diagonal tile of panel k:
-//   C = K_ik - L_i,0:k L_k,0:k^T (DMMA, cp.async ring), L_ik = C W_kk^T (DMMA), then the
-//   look-ahead: each of the (up to two) 64-row tiles of this macro tile immediately applies
-//   its contribution  T_ii -= L_ik L_ik^T  to ITS OWN diagonal tile (one writer per tile and
-//   step, so no atomics), so the diagonal kernel never runs a GEMM.
+//   acc = L_i,0:k L_k,0:k^T - K_ik = -C (DMMA, cp.async ring), -L_ik = acc W_kk^T (DMMA, TRSM as a GEMM whose A
+//   operand is the accumulator fragment itself: with the K order permuted so that lane t owns k = 2t, 2t+1 of every
+//   8-wide group, the C fragment of m8n8k4 IS its A fragment -- no shared-memory round trip), then the look-ahead:
+//   each of the (up to two) 64-row halves of the macro tile immediately applies T_ii -= L_ik L_ik^T to ITS OWN
+//   diagonal tile (one writer per tile and step, so no atomics).  With kFuseDiag the CTA of macro tile 0 -- whose
+//   first half is the diagonal tile of panel k+1, now fully updated -- also factors and inverts that tile, so a
+//   panel step is ONE launch and the next step's W is ready when it starts.
 // ------------------------------------------------------------------------------------------
 // item: x = block, y = macro tile, z = slice | nslices << 8, w = split group id.
-// Returns false when this CTA was a non-final split-K slice (nothing more to do).
-__device__ __forceinline__ bool panel_body(const BlockDesc& bd, const int4 item, int k, const double* __restrict__ sigma,
-                                           double* __restrict__ Lbuf, const double* __restrict__ wbuf, double ridge,
-                                           double* __restrict__ scratch, int32_t* __restrict__ counters,
-                                           int32_t group_base, double* smem, int* s_last_p) {
+template <bool kFuseDiag>
+__device__ __forceinline__ void panel_body(const BlockDesc& bd, const int4 item, int k, const double* __restrict__ sigma,
+                                           double* __restrict__ Lbuf, double* __restrict__ wbuf, int64_t wpar,
+                                           int64_t wpar_next, double ridge, double* __restrict__ scratch,
+                                           int32_t* __restrict__ counters, int32_t group_base,
+                                           int32_t* __restrict__ status, double* smem, int* s_last_p) {
     int& s_last = *s_last_p;
     const int pc0 = k * NB;
     const int wk = min(NB, bd.mp - pc0);
@@ -327,9 +363,13 @@ __device__ __forceinline__ bool panel_body(const BlockDesc& bd, const int4 item,
     double* Lb = Lbuf + bd.moff;
     const double* Sb = sigma + bd.moff;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    // 16-row slot of this warp.  The second 64-row half is mirrored: warps w and w+4 share an SM sub-partition, and
+    // the look-ahead SYRK of slot wl costs ~(wl+1) units, so (wl, 3-wl) pairs balance the four tensor pipes.
+    const int grp = warp >> 2;
+    const int wl = grp ? 3 - (warp & 3) : (warp & 3);
+    const int wrow = 4 * grp + wl;
 
     const int slice = item.z & 0xFF, nsl = item.z >> 8;
-    double* Wsm = smem + W_OFF;                   // [64][LDT], W[c][c'] = (L_kk^-1)[c][c'], zero above the diagonal
     // accumulators start at -K_ik (slice 0 only), so the Sigma tile's HBM latency hides behind the pipeline
     // prologue: after the loop acc = L_i,0:k L_k,0:k^T - K_ik = -C
     double acc[2][8][2];
@@ -337,17 +377,16 @@ __device__ __forceinline__ bool panel_body(const BlockDesc& bd, const int4 item,
     for (int f = 0; f < 2; ++f)
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-            const int rl = 16 * warp + 8 * f + g, cc = 8 * c + 2 * t;
+            const int rl = 16 * wrow + 8 * f + g, cc = 8 * c + 2 * t;
             double2 a = make_double2(0.0, 0.0);
             if (slice == 0 && rl < prow && cc < wk) a = *reinterpret_cast<const double2*>(Sb + (size_t)(r0 + rl) * ld + pc0 + cc);
             acc[f][c][0] = -a.x;
             acc[f][c][1] = -a.y;
         }
-    {
-        // split-K: slice s of nsl owns 64-wide K blocks [k*s/nsl, k*(s+1)/nsl)
-        const int kb = (k * slice) / nsl * NB, ke = (k * (slice + 1)) / nsl * NB;
-        gemm_nt_core(Lb + (size_t)r0 * ld, Lb + (size_t)pc0 * ld, ld, prow, wk, kb, ke, smem, acc);
-    }
+    // split-K: slice s of nsl owns 64-wide K blocks [k*s/nsl, k*(s+1)/nsl)
+    const int kb = (k * slice) / nsl * NB, ke = (k * (slice + 1)) / nsl * NB;
+    gemm_nt_core(Lb + (size_t)r0 * ld, Lb + (size_t)pc0 * ld, ld, prow, wk, kb, ke,
+                 wbuf + wpar + (size_t)item.x * (NB * NB), wrow, smem, acc);
     if (nsl > 1) {
         // partial sums go to scratch; the CTA that arrives last adds them up IN SLICE ORDER (deterministic)
         double* part = scratch + ((size_t)(item.w - group_base) * nsl) * (TM * NB);
@@ -360,7 +399,7 @@ __device__ __forceinline__ bool panel_body(const BlockDesc& bd, const int4 item,
         __syncthreads();
         if (tid == 0) s_last = (atomicAdd(&counters[item.w], 1) == nsl - 1);
         __syncthreads();
-        if (!s_last) return false;
+        if (!s_last) return;
         __threadfence();
 #pragma unroll
         for (int f = 0; f < 2; ++f)
@@ -379,126 +418,118 @@ __device__ __forceinline__ bool panel_body(const BlockDesc& bd, const int4 item,
         }
     }
 
-    {
-        // W tile of this step (written dense by the diagonal kernel): its L2 latency overlaps the C write-out
-        const double* wsrc = wbuf + (size_t)item.x * (NB * NB);
+    // Shared memory now: stage s_w holds W_kk ([64][LDW], W[c][c'] = (L_kk^-1)[c][c'], zero above the diagonal);
+    // the other two stages take the two 64-row halves of -L_ik ([64][LDW] each).
+    const int s_w = ((ke - kb) / KC) % NST;
+    const double* Wsm = smem + s_w * STAGE;
+    double* Lh = smem + ((s_w + 1 + grp) % NST) * STAGE;
+    const bool active = (16 * wrow < prow);
+    const int trow0 = r0 + 64 * grp;              // first global row of this warp group's 64-row half
+    const int tw = min(NB, bd.mp - trow0);        // extent of its diagonal tile (<= 0: z / test rows, no tile)
+    const bool glook = (trow0 < bd.mp && wk == NB);   // group-uniform (a narrow last panel has no diagonal tile below)
+    const bool look = glook && (16 * wl < tw);
+
+    // ---- TRSM, 32 output columns at a time (keeps accumulators + outputs within the register budget)
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int idx = tid + u * CHOL_THREADS;
-            const int row = idx >> 5, ch = (idx & 31) * 2;
-            cp_async16(Wsm + row * LDT + ch, wsrc + row * NB + ch, true);
-        }
-        cp_async_commit();
-    }
-    double* Ct = smem;                            // [128][LDT] macro tile, 16 rows per warp
-    double* Cw = Ct + warp * 16 * LDT;
-    const double* W = Wsm;
-    const bool active = (16 * warp < prow);
+    for (int h = 0; h < 2; ++h) {
+        double out[2][4][2];
 #pragma unroll
-    for (int f = 0; f < 2; ++f)
+        for (int f = 0; f < 2; ++f)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const int cc = 8 * c + 2 * t;
-            Cw[(8 * f + g) * LDT + cc] = -acc[f][c][0];
-            Cw[(8 * f + g) * LDT + cc + 1] = -acc[f][c][1];
-            acc[f][c][0] = acc[f][c][1] = 0.0;
-        }
-    cp_async_wait<0>();
-    __syncthreads();
-    const double* Ca = Cw + g * LDT + t;
-    const double* Wb = W + g * LDT + t;
-    const int ns4 = wk / 4;
-    if (active) {
-#pragma unroll 4
-        for (int s4 = 0; s4 < ns4; ++s4) {
-            const double a0 = Ca[s4 * 4], a1 = Ca[8 * LDT + s4 * 4];
+            for (int cq = 0; cq < 4; ++cq) out[f][cq][0] = out[f][cq][1] = 0.0;
+        if (active) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                if (4 * s4 <= 8 * c + 7 && 8 * c < wk) {          // W is lower triangular
-                    const double b = Wb[c * 8 * LDT + s4 * 4];
-                    dmma884(acc[0][c][0], acc[0][c][1], a0, b);
-                    dmma884(acc[1][c][0], acc[1][c][1], a1, b);
+            for (int cp = 0; cp < 4 * h + 4; ++cp) {
+#pragma unroll
+                for (int cq = 0; cq < 4; ++cq) {
+                    const int c = 4 * h + cq;
+                    if (c >= cp) {                                  // W is lower triangular (static: no predicated mma)
+                        const double2 b = *reinterpret_cast<const double2*>(Wsm + (8 * c + g) * LDW + 8 * cp + 2 * t);
+                        dmma884(out[0][cq][0], out[0][cq][1], acc[0][cp][0], b.x);
+                        dmma884(out[1][cq][0], out[1][cq][1], acc[1][cp][0], b.x);
+                        dmma884(out[0][cq][0], out[0][cq][1], acc[0][cp][1], b.y);
+                        dmma884(out[1][cq][0], out[1][cq][1], acc[1][cp][1], b.y);
+                    }
                 }
             }
         }
+        // out = -L_ik: L to global, -L into this group's half tile (operand of the look-ahead SYRK; the sign cancels)
+#pragma unroll
+        for (int f = 0; f < 2; ++f)
+#pragma unroll
+            for (int cq = 0; cq < 4; ++cq) {
+                const int rl = 16 * wrow + 8 * f + g, cc = 8 * (4 * h + cq) + 2 * t;
+                if (rl < prow && cc < wk)
+                    *reinterpret_cast<double2*>(Lb + (size_t)(r0 + rl) * ld + pc0 + cc) =
+                        make_double2(-out[f][cq][0], -out[f][cq][1]);
+                *reinterpret_cast<double2*>(Lh + (16 * wl + 8 * f + g) * LDW + cc) = make_double2(out[f][cq][0], out[f][cq][1]);
+            }
     }
-    __syncwarp();
-    // L tile: to global and back into shared memory (operand of the look-ahead SYRK)
-#pragma unroll
-    for (int f = 0; f < 2; ++f)
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const int rl = 16 * warp + 8 * f + g, cc = 8 * c + 2 * t;
-            if (rl < prow && cc < wk)
-                *reinterpret_cast<double2*>(Lb + (size_t)(r0 + rl) * ld + pc0 + cc) =
-                    make_double2(acc[f][c][0], acc[f][c][1]);
-            Cw[(8 * f + g) * LDT + cc] = acc[f][c][0];
-            Cw[(8 * f + g) * LDT + cc + 1] = acc[f][c][1];
-            acc[f][c][0] = acc[f][c][1] = 0.0;
-        }
-    // ---- look-ahead: T_ii -= L_ik L_ik^T for the 64-row tile this warp belongs to
-    const int grp = warp >> 2, wl = warp & 3;
-    const int trow0 = r0 + 64 * grp;              // first global row of the 64-row tile
-    const int tw = min(NB, bd.mp - trow0);        // tile extent (<= 0: z rows, no diagonal tile)
-    const bool look = (trow0 < bd.mp && wk == NB && 16 * wl < tw);   // (a narrow last panel has no diagonal tile below)
-    if (look) {
+
+    // ---- look-ahead: T_ii -= L_ik L_ik^T on this group's diagonal tile
+    if (glook) {
         // the old tile values go straight into the accumulators (negated): their latency overlaps the barrier
+        double acc2[2][8][2];
         const double* src = (k == 0 ? sigma : Lbuf) + bd.moff;    // first touch reads Sigma (+ ridge)
 #pragma unroll
         for (int f = 0; f < 2; ++f)
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 const int rl = 16 * wl + 8 * f + g, cc = 8 * c + 2 * t;   // within the tile
-                if (c <= 2 * wl + 1 && rl < tw && cc <= rl) {
-                    double2 v = __ldcg(reinterpret_cast<const double2*>(src + (size_t)(trow0 + rl) * ld + trow0 + cc));
+                double2 v = make_double2(0.0, 0.0);
+                if (look && c <= 2 * wl + 1 && rl < tw && cc <= rl) {
+                    v = __ldcg(reinterpret_cast<const double2*>(src + (size_t)(trow0 + rl) * ld + trow0 + cc));
                     if (k == 0) {
                         if (cc == rl && trow0 + rl < bd.ms) v.x += ridge;
                         if (cc + 1 == rl && trow0 + rl < bd.ms) v.y += ridge;   // odd rows: the diagonal is the pair's second element
                     }
-                    acc[f][c][0] = -v.x;
-                    acc[f][c][1] = -v.y;
                 }
+                acc2[f][c][0] = -v.x;
+                acc2[f][c][1] = -v.y;
             }
-    }
-    __syncthreads();
-    if (look) {
-        const double* A = Ct + (64 * grp + 16 * wl + g) * LDT + t;
-        const double* B = Ct + (64 * grp + g) * LDT + t;
-#pragma unroll 4
-        for (int s4 = 0; s4 < NB / 4; ++s4) {
-            const double a0 = A[s4 * 4], a1 = A[8 * LDT + s4 * 4];
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");      // the four warps of this half
+        if (look) {
+            const double* A = Lh + (16 * wl + g) * LDW + 2 * t;
+            const double* B = Lh + g * LDW + 2 * t;
+            switch (wl) {                                              // static column count per row slot: no predicated mma
+                case 0: syrk_rows<0>(A, B, acc2); break;
+                case 1: syrk_rows<1>(A, B, acc2); break;
+                case 2: syrk_rows<2>(A, B, acc2); break;
+                default: syrk_rows<3>(A, B, acc2); break;
+            }
+            // acc2 = L L^T - T_old  =>  T_new = -acc2
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                if (c <= 2 * wl + 1) {                             // lower triangle of the tile only
-                    const double b = B[c * 8 * LDT + s4 * 4];
-                    dmma884(acc[0][c][0], acc[0][c][1], a0, b);
-                    dmma884(acc[1][c][0], acc[1][c][1], a1, b);
+            for (int f = 0; f < 2; ++f)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int rl = 16 * wl + 8 * f + g, cc = 8 * c + 2 * t;   // within the tile
+                    if (c <= 2 * wl + 1 && rl < tw && cc <= rl)
+                        *reinterpret_cast<double2*>(Lb + (size_t)(trow0 + rl) * ld + trow0 + cc) =
+                            make_double2(-acc2[f][c][0], -acc2[f][c][1]);
                 }
-            }
         }
-        // acc = L L^T - T_old  =>  T_new = -acc
-#pragma unroll
-        for (int f = 0; f < 2; ++f)
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const int rl = 16 * wl + 8 * f + g, cc = 8 * c + 2 * t;   // within the tile
-                if (c <= 2 * wl + 1 && rl < tw && cc <= rl)
-                    *reinterpret_cast<double2*>(Lb + (size_t)(trow0 + rl) * ld + trow0 + cc) =
-                        make_double2(-acc[f][c][0], -acc[f][c][1]);
-            }
     }
-    return true;
+    if constexpr (kFuseDiag) {
+        // macro tile 0: rows r0 .. r0+63 are the diagonal tile of panel k+1, which this step completed
+        if (item.y == 0 && r0 < bd.mp && wk == NB) {
+            __syncthreads();        // T_new is in L2 for the whole CTA; shared memory is free again
+            diag_body(bd, item.x, k + 1, sigma, Lbuf, wbuf + wpar_next, ridge, status, smem);
+        }
+    }
 }
 
+template <bool kFuseDiag>
 __global__ void __launch_bounds__(CHOL_THREADS, 2)
 chol_panel_kernel(const BlockDesc* __restrict__ blocks, const int4* __restrict__ items, int32_t k,
-                  const double* __restrict__ sigma, double* __restrict__ Lbuf, const double* __restrict__ wbuf,
-                  double ridge, double* __restrict__ scratch, int32_t* __restrict__ counters, int32_t group_base) {
+                  const double* __restrict__ sigma, double* __restrict__ Lbuf, double* __restrict__ wbuf, int64_t wpar,
+                  int64_t wpar_next, double ridge, double* __restrict__ scratch, int32_t* __restrict__ counters,
+                  int32_t group_base, int32_t* __restrict__ status) {
     extern __shared__ __align__(16) double smem[];
     __shared__ int s_last;
     const int4 item = items[blockIdx.x];
     const BlockDesc bd = blocks[item.x];
-    panel_body(bd, item, k, sigma, Lbuf, wbuf, ridge, scratch, counters, group_base, smem, &s_last);
+    panel_body<kFuseDiag>(bd, item, k, sigma, Lbuf, wbuf, wpar, wpar_next, ridge, scratch, counters, group_base, status,
+                          smem, &s_last);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -674,22 +705,33 @@ backsolve_cluster_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __
 cudaError_t chol_configure() {
     cudaError_t e = cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DIAG);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CHOL);
+    e = cudaFuncSetAttribute(chol_panel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CHOL);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(chol_panel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CHOL);
 }
 
+// W_k (the inverse of the diagonal tile of panel k) lives in wbuf[(k & 1) * wstride + block * 64 * 64]: two parities,
+// because with the fused diagonal the step-k launch reads W_k while its macro-tile-0 CTAs already write W_k+1.
 cudaError_t launch_chol_diag(const BlockDesc* blocks, const int32_t* items, int32_t n_items, int32_t k,
-                             const double* sigma, double* L, double* wbuf, double ridge, int32_t* status,
-                             cudaStream_t st) {
+                             const double* sigma, double* L, double* wbuf, int64_t wstride, double ridge,
+                             int32_t* status, cudaStream_t st) {
     if (n_items == 0) return cudaSuccess;
-    chol_diag_kernel<<<n_items, CHOL_THREADS, SMEM_DIAG, st>>>(blocks, items, k, sigma, L, wbuf, ridge, status);
+    chol_diag_kernel<<<n_items, CHOL_THREADS, SMEM_DIAG, st>>>(blocks, items, k, sigma, L, wbuf + (k & 1) * wstride, ridge,
+                                                              status);
     return cudaGetLastError();
 }
 cudaError_t launch_chol_panel(const BlockDesc* blocks, const int4* items, int32_t n_items, int32_t k,
-                              const double* sigma, double* L, const double* wbuf, double ridge, double* scratch,
-                              int32_t* counters, int32_t group_base, cudaStream_t st) {
+                              const double* sigma, double* L, double* wbuf, int64_t wstride, bool fuse_diag,
+                              double ridge, double* scratch, int32_t* counters, int32_t group_base, int32_t* status,
+                              cudaStream_t st) {
     if (n_items == 0) return cudaSuccess;
-    chol_panel_kernel<<<n_items, CHOL_THREADS, SMEM_CHOL, st>>>(blocks, items, k, sigma, L, wbuf, ridge, scratch,
-                                                                 counters, group_base);
+    const int64_t wpar = (k & 1) * wstride, wnext = ((k + 1) & 1) * wstride;
+    if (fuse_diag)
+        chol_panel_kernel<true><<<n_items, CHOL_THREADS, SMEM_CHOL, st>>>(blocks, items, k, sigma, L, wbuf, wpar, wnext, ridge,
+                                                                          scratch, counters, group_base, status);
+    else
+        chol_panel_kernel<false><<<n_items, CHOL_THREADS, SMEM_CHOL, st>>>(blocks, items, k, sigma, L, wbuf, wpar, wnext, ridge,
+                                                                           scratch, counters, group_base, status);
     return cudaGetLastError();
 }
 // Back substitution of `n_blocks` blocks listed in `order`: an 8-CTA cluster per block for the big size

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -94,6 +95,7 @@ struct dbslmm_b200_handle {
     cudaEvent_t ev[8] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[kNumClasses] = {}, ev_cend[kNumClasses] = {};
     std::string err;
+    bool fuse_diag = true;               // panel step k also factors the diagonal tile of panel k+1 (one launch per step)
     // reference panel
     DevBuf bed, stats;
     PinBuf h_stats;                      // per-SNP statistics, filled asynchronously by load_bed
@@ -230,19 +232,22 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
             if (ntiles > 0) nsl = std::max(1, std::min({8, k / 4, kTargetCtas / ntiles}));
             s.nsl = nsl;
             s.group_base = n_groups;
-            for (int b : members) {
-                const BlockDesc& d = P.blocks[b];
-                const int K = (d.mp + 63) / 64;
-                if (K <= k) continue;
-                diag_items.push_back(b);
-                const int wk = std::min(64, d.mp - 64 * k);
-                const int below = 64 * k + wk;
-                const int nt = (d.nrows - below + 127) / 128;
-                for (int t = 0; t < nt; ++t) {
-                    const int gid = (nsl > 1) ? n_groups++ : 0;
-                    for (int sl = 0; sl < nsl; ++sl) panel_items.push_back(make_int4(b, t, sl | (nsl << 8), gid));
+            // macro tile 0 of every block goes first: its CTA also factors the next diagonal tile (fused), so it
+            // should start in the first wave of the launch
+            for (int pass = 0; pass < 2; ++pass)
+                for (int b : members) {
+                    const BlockDesc& d = P.blocks[b];
+                    const int K = (d.mp + 63) / 64;
+                    if (K <= k) continue;
+                    if (pass == 0) diag_items.push_back(b);
+                    const int wk = std::min(64, d.mp - 64 * k);
+                    const int below = 64 * k + wk;
+                    const int nt = (d.nrows - below + 127) / 128;
+                    for (int t = (pass == 0 ? 0 : 1); t < (pass == 0 ? std::min(nt, 1) : nt); ++t) {
+                        const int gid = (nsl > 1) ? n_groups++ : 0;
+                        for (int sl = 0; sl < nsl; ++sl) panel_items.push_back(make_int4(b, t, sl | (nsl << 8), gid));
+                    }
                 }
-            }
             s.n_groups = n_groups - s.group_base;
             s.n_diag = (int32_t)diag_items.size() - s.diag_off;
             s.n_panel = (int32_t)panel_items.size() - s.panel_off;
@@ -361,6 +366,7 @@ int dbslmm_b200_create(int device, dbslmm_b200_handle** out) {
     if (!h) return DBSLMM_B200_ERR_NOMEM;
     h->device = device;
     h->n_sm = prop.multiProcessorCount;
+    if (const char* e = std::getenv("DBSLMM_B200_FUSE_DIAG")) h->fuse_diag = (e[0] != '0');   // tuning switch
     bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);     // numerically lower = higher priority
@@ -528,7 +534,7 @@ int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
     CU_TRY(h, h->status.ensure(sizeof(int32_t) * (size_t)std::max(2 * nb, 1)));
     if (!pcg) {
         CU_TRY(h, h->scratch.ensure(sizeof(double) * (size_t)std::max<int64_t>(P.scratch_doubles, 1)));
-        CU_TRY(h, h->wbuf.ensure(sizeof(double) * 64 * 64 * (size_t)std::max(nb, 1)));
+        CU_TRY(h, h->wbuf.ensure(2 * sizeof(double) * 64 * 64 * (size_t)std::max(nb, 1)));   // two parities, see launch_chol_diag
         CU_TRY(h, h->counters.ensure(sizeof(int32_t) * (size_t)std::max(P.n_groups, 1)));
     }
     if (keep_int) {
@@ -693,17 +699,23 @@ int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
                 if (P.steps[c].empty()) continue;
                 cudaStream_t cs = h->cls_stream[c];
                 CU_TRY(h, cudaStreamWaitEvent(cs, h->ev_fork, 0));
+                const int64_t wstride = (int64_t)64 * 64 * std::max(nb, 1);
                 for (size_t k = 0; k < P.steps[c].size(); ++k) {
                     const StepList& s = P.steps[c][k];
-                    CU_TRY(h, launch_chol_diag(d_blocks, d_diag + s.diag_off, s.n_diag, (int32_t)k,
-                                               (const double*)h->sigma.p, (double*)h->lbuf.p, (double*)h->wbuf.p, ridge,
-                                               d_status, cs));
+                    // the diagonal tile of panel k >= 1 is factored by the step k-1 panel launch (fused)
+                    if (k == 0 || !h->fuse_diag) {
+                        CU_TRY(h, launch_chol_diag(d_blocks, d_diag + s.diag_off, s.n_diag, (int32_t)k,
+                                                   (const double*)h->sigma.p, (double*)h->lbuf.p, (double*)h->wbuf.p, wstride,
+                                                   ridge, d_status, cs));
+                        ++n_launch;
+                        ++n_chol_launch;
+                    }
                     CU_TRY(h, launch_chol_panel(d_blocks, d_panel + s.panel_off, s.n_panel, (int32_t)k,
-                                                (const double*)h->sigma.p, (double*)h->lbuf.p, (const double*)h->wbuf.p,
-                                                ridge, (double*)h->scratch.p + P.scratch_off[c], (int32_t*)h->counters.p,
-                                                s.group_base, cs));
-                    n_launch += 2;
-                    n_chol_launch += 2;
+                                                (const double*)h->sigma.p, (double*)h->lbuf.p, (double*)h->wbuf.p, wstride,
+                                                h->fuse_diag, ridge, (double*)h->scratch.p + P.scratch_off[c],
+                                                (int32_t*)h->counters.p, s.group_base, d_status, cs));
+                    ++n_launch;
+                    ++n_chol_launch;
                 }
                 // the class's back substitution follows on its own stream: the big blocks' substitutions overlap
                 // the factorisation of the bulk classes, which finish last
