@@ -47,7 +47,8 @@ class FitArgs(C.Structure):
                 ("timing", C.POINTER(Timing)),
                 ("test_bed", C.c_void_p), ("test_n_snp", C.c_int64), ("test_n_total", C.c_int32),
                 ("test_indicator", C.c_void_p), ("s_tpos", C.c_void_p), ("l_tpos", C.c_void_p),
-                ("variance_out", C.c_void_p)]
+                ("variance_out", C.c_void_p),
+                ("bed", C.c_void_p), ("bed_n_snp", C.c_int64), ("bed_n_ref", C.c_int32)]
 
 
 _lib = None
@@ -145,10 +146,12 @@ class Engine:
         return owner, cost
 
     def fit(self, s_off, s_pos, s_z, l_off=None, l_pos=None, l_z=None, *, sigma_s, n_obs, tau=0.8,
-            solver=SOLVER_CHOLESKY, flags=0, test=None):
+            solver=SOLVER_CHOLESKY, flags=0, test=None, bed=None, n_ref=None):
         """Returns dict(beta_s[n_folds, S], beta_l[n_folds, L], status[n_blocks], n_bad, timing[, variance]).
         test = dict(bed=uint8[n_snp_t, pitch_t], n_total=int, indicator=int[n_total], s_tpos=int[S], l_tpos=int[L])
-        switches the fork's asymptotic-variance side channel on: variance[n_folds, n_blocks, n_test]."""
+        switches the fork's asymptotic-variance side channel on: variance[n_folds, n_blocks, n_test].
+        bed = uint8[n_snp, ceil(n_ref/4)] (with n_ref): the reference panel travels with the call, as in the reference's
+        DBSLMMFIT::est(bed_str, ...); its upload overlaps the fit, and it stays resident afterwards."""
         s_off = np.ascontiguousarray(s_off, np.int32)
         s_pos = np.ascontiguousarray(s_pos, np.int32)
         s_z = np.ascontiguousarray(s_z, np.float64)
@@ -181,6 +184,11 @@ class Engine:
             a.test_bed, a.test_n_snp, a.test_n_total = tbed.ctypes.data, tbed.size // ((n_total + 3) // 4), n_total
             a.test_indicator, a.s_tpos, a.l_tpos, a.variance_out = ind.ctypes.data, _ptr(stp), _ptr(ltp), var.ctypes.data
             self._keep = [tbed, ind, stp, ltp]
+        if bed is not None:
+            bed = np.ascontiguousarray(bed, dtype=np.uint8)
+            pitch = (int(n_ref) + 3) // 4
+            a.bed, a.bed_n_snp, a.bed_n_ref = bed.ctypes.data, bed.size // pitch, int(n_ref)
+            self.n_snp, self.n_ref = bed.size // pitch, int(n_ref)
         rc = self._check(self.lib.dbslmm_b200_fit(self.h, C.byref(a)), "fit")
         out = {"beta_s": beta_s, "beta_l": None if beta_l is None else beta_l[:, :nl], "status": status[:nb],
                "n_bad": rc, "timing": tm.as_dict()}

@@ -10,6 +10,7 @@
 //
 // Code map (dtpr.cpp:329-350): 2-bit v = b0 + 2*b1, low bits first within a byte:
 //   v=0 -> 2, v=2 -> 1, v=3 -> 0, v=1 -> missing (genotype plane 0, mask plane 0).
+#include <algorithm>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -122,6 +123,8 @@ __device__ __forceinline__ uint4 expand16(uint32_t w) {
 // Decoder: one warp per output code row.  row_src[r] = bed row | (mask plane ? 1<<31 : 0);
 // row_g[r] = SNP-row index that receives the scale factors (or -1 for mask rows).
 // ------------------------------------------------------------------------------------------
+// OWN = true: no statistics array; the warp counts the genotypes of the row it has staged (streaming fit).
+template <bool OWN>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 decode_rows_kernel(const uint8_t* __restrict__ bed, int32_t n_ref, int32_t pitch, int32_t n_pad,
                    int32_t buf_bytes, const uint32_t* __restrict__ row_src, const int32_t* __restrict__ row_g,
@@ -159,22 +162,41 @@ decode_rows_kernel(const uint8_t* __restrict__ bed, int32_t n_ref, int32_t pitch
         const uint32_t* w32 = reinterpret_cast<const uint32_t*>(bufs[cur]);
         uint4* out = reinterpret_cast<uint4*>(codes + (size_t)row * n_pad);
         const int nfull = n_ref >> 4;             // words whose 16 samples are all real
+        int c0 = 0, c1 = 0, c2 = 0;
         for (int i = lane; i < nout; i += 32) {
             uint4 o = make_uint4(0u, 0u, 0u, 0u);
             if (i < nwords) {
                 uint32_t w = row_word(w32, off[cur], i);
+                uint32_t ws = w;                          // for the counts: samples past n_ref -> code 3 (counts nothing)
                 if (i >= nfull) {
                     const uint32_t vb = valid_bits(n_ref, i);
+                    ws = w | ~vb;
                     w = (w & vb) | (0x55555555u & ~vb);   // samples past n_ref -> "missing": 0 in both planes
                 }
                 o = mask_plane ? expand16<true>(w) : expand16<false>(w);
+                if (OWN) {
+                    const uint32_t lo = ws & 0x55555555u, hi = (ws >> 1) & 0x55555555u;
+                    c0 += __popc(~(lo | hi) & 0x55555555u);    // code 0 -> allele count 2
+                    c1 += __popc(lo & ~hi);                    // code 1 -> missing
+                    c2 += __popc(hi & ~lo);                    // code 2 -> allele count 1
+                }
             }
             out[i] = o;
+        }
+        if (OWN) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+                c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+                c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+            }
         }
         if (lane == 0) {
             const int32_t g = row_g[row];
             if (g >= 0) {
-                const SnpStat s = stats[src & 0x7FFFFFFFu];
+                SnpStat s;
+                if (OWN) { s.n_nonmiss = n_ref - c1; s.sum = 2 * c0 + c2; s.sumsq = 4 * c0 + c2; s.pad = 0; }
+                else s = stats[src & 0x7FFFFFFFu];
                 const double ni = (double)s.n_nonmiss;
                 // d = n_i * sum g^2 - (sum g)^2  (exact integer), r = sqrt(tau (n-1) / (n n_i d))
                 const double d = ni * (double)s.sumsq - (double)s.sum * (double)s.sum;
@@ -206,9 +228,24 @@ __global__ void block_missing_kernel(const BlockDesc* __restrict__ blocks, int32
     if (lane == 0) flags[b] = miss ? 1 : 0;
 }
 
+// Streaming fit: did any decoded SNP row have a missing call?  (one flag for the whole fit)
+__global__ void rows_missing_kernel(const int32_t* __restrict__ rowN, int64_t n_rows, int32_t n_ref, int32_t* __restrict__ flag) {
+    int bad = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rows; i += (int64_t)gridDim.x * blockDim.x)
+        bad |= (rowN[i] != n_ref);
+    if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flag, 1);
+}
+
 // ------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------
+cudaError_t launch_rows_missing(const int32_t* rowN, int64_t n_rows, int32_t n_ref, int32_t* flag, cudaStream_t st) {
+    if (n_rows <= 0) return cudaSuccess;
+    const int ctas = (int)std::min<int64_t>((n_rows + 1023) / 1024, 296);
+    rows_missing_kernel<<<ctas, 256, 0, st>>>(rowN, n_rows, n_ref, flag);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_block_missing(const BlockDesc* blocks, int32_t n_blocks, const uint32_t* row_src,
                                  const SnpStat* stats, int32_t n_ref, int32_t* flags, cudaStream_t st) {
     if (n_blocks == 0) return cudaSuccess;
@@ -243,13 +280,19 @@ cudaError_t launch_decode_rows(const uint8_t* bed, int32_t n_ref, int32_t n_pad,
     const int buf = stage_bytes(pitch);
     const size_t smem = (size_t)kWarpsPerCta * 2 * buf;
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(decode_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(decode_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(decode_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int64_t ctas = (n_rows + kWarpsPerCta - 1) / kWarpsPerCta;
     const int64_t cap = (int64_t)n_sm * 8;
     if (ctas > cap) ctas = cap;
-    decode_rows_kernel<<<(unsigned)ctas, kWarpsPerCta * 32, smem, st>>>(bed, n_ref, pitch, n_pad, buf, row_src, row_g,
-                                                                      n_rows, stats, tau, codes, rowN, rowS, rowR);
+    if (stats)
+        decode_rows_kernel<false><<<(unsigned)ctas, kWarpsPerCta * 32, smem, st>>>(bed, n_ref, pitch, n_pad, buf, row_src, row_g,
+                                                                                 n_rows, stats, tau, codes, rowN, rowS, rowR);
+    else      // stats == nullptr: the decoder derives the per-SNP counts itself
+        decode_rows_kernel<true><<<(unsigned)ctas, kWarpsPerCta * 32, smem, st>>>(bed, n_ref, pitch, n_pad, buf, row_src, row_g,
+                                                                                n_rows, stats, tau, codes, rowN, rowS, rowR);
     return cudaGetLastError();
 }
 

@@ -7,12 +7,15 @@
 // back substitution, and read the betas back.  No CPU arithmetic on the data path: without a
 // CUDA device every entry point fails.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cudaTypedefs.h>
@@ -60,6 +63,21 @@ constexpr int kClassMaxPanels[kNumClasses] = {8, 16, 32, 1 << 30};
 
 struct StepList { int32_t diag_off, n_diag, panel_off, n_panel, group_base, n_groups, nsl; };
 
+// A batch = the blocks that run one Cholesky step loop together on one stream.  With the reference panel resident
+// (load_bed) there is one batch per size class.  When the panel streams in from host memory inside the fit
+// (fit_args.bed), batches are also the upload units: big classes first, the bulk class cut into sub-batches, so a
+// batch's decode -> Gram -> factorisation starts as soon as ITS rows have crossed PCIe.
+constexpr int kMaxBatches = 8;
+struct Batch {
+    int cls = 0;                          // size class: selects the stream (priority) and the back-substitution kernel
+    int32_t ord_off = 0, ord_n = 0;       // members = order[ord_off, ord_off + ord_n)
+    int64_t crow0 = 0, crow1 = 0;         // code rows of the members (contiguous only in the streaming layout)
+    int64_t grow0 = 0, grow1 = 0;         // SNP rows
+    int32_t tile0 = 0, tile1 = 0;         // range of the plain Gram tile list
+    std::vector<StepList> steps;          // per panel step
+    int64_t scratch_off = 0;              // split-K scratch region (doubles)
+};
+
 struct Plan {
     int32_t n_blocks = 0;
     int64_t n_snp_rows = 0;       // total SNP rows (sum m)
@@ -68,16 +86,13 @@ struct Plan {
     int64_t tot_s = 0, tot_l = 0;
     int32_t max_mp = 0;
     std::vector<BlockDesc> blocks;
-    std::vector<int32_t> order;                       // blocks by descending size
+    std::vector<int32_t> order;                       // concatenated batch member lists (big classes first)
+    std::vector<Batch> batches;
+    bool streaming = false;                           // layout in batch order (else block-index order)
     int32_t n_tiles_plain = 0, n_tiles_miss = 0;
-    std::vector<StepList> steps[kNumClasses];         // per class, per panel step
-    int64_t scratch_off[kNumClasses] = {0, 0, 0, 0};  // split-K scratch region of each class (doubles)
     int64_t scratch_doubles = 0;
     int32_t n_groups = 0;                             // split-K groups (one arrival counter each)
-    int32_t n_big = 0;                                // blocks with mp > 1024 (head of `order`)
     int32_t n_test = 0;                               // selected test individuals (variance side channel), 0 = off
-    int32_t cls_off[kNumClasses] = {0, 0, 0, 0};      // each size class is a contiguous range of `order`
-    int32_t cls_n[kNumClasses] = {0, 0, 0, 0};
     // blob layout (byte offsets inside the plan blob, identical on host and device)
     size_t o_blocks = 0, o_rowsrc = 0, o_rowg = 0, o_z = 0, o_tiles_plain = 0, o_tiles_miss = 0, o_order = 0,
            o_diag = 0, o_panel = 0, blob_bytes = 0;
@@ -91,21 +106,25 @@ struct dbslmm_b200_handle {
     int device = 0;
     int n_sm = 148;
     cudaStream_t stream = nullptr;
-    cudaStream_t cls_stream[kNumClasses] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t b_stream[kMaxBatches] = {};    // one Cholesky stream per batch, priority falling with the batch index
     cudaEvent_t ev[8] = {};
-    cudaEvent_t ev_fork = nullptr, ev_join[kNumClasses] = {}, ev_cend[kNumClasses] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[kMaxBatches] = {}, ev_cend[kMaxBatches] = {};
+    cudaStream_t up_stream = nullptr;    // streaming fit: class-ordered panel upload
+    cudaEvent_t ev_up[kMaxBatches] = {}, ev_gram[kMaxBatches] = {}, ev_blob = nullptr;
     std::string err;
     bool fuse_diag = true;               // panel step k also factors the diagonal tile of panel k+1 (one launch per step)
+    bool stream_bed = true;              // fit_args.bed: overlap the panel upload with the fit (else upload, then fit)
     // reference panel
     DevBuf bed, stats;
     PinBuf h_stats;                      // per-SNP statistics, filled asynchronously by load_bed
     cudaEvent_t ev_bed = nullptr;        // completes when the panel, its statistics and their host copy have landed
     bool bed_pending = false;
+    bool stats_valid = false;            // `stats` / `h_stats` describe the resident panel (a streaming fit skips them)
     std::vector<int32_t> miss_flags;     // per-block "has missing calls" of the current plan
     int64_t n_snp = 0;
     int32_t n_ref = 0, pitch = 0, n_pad = 0;
     // workspace
-    DevBuf codes, sigma, lbuf, rowN, rowS, rowR, planblob, beta, status, intQ, intA, intN, scratch, counters, wbuf, vbed, vstats, vwork;
+    DevBuf codes, sigma, lbuf, rowN, rowS, rowR, planblob, beta, status, intQ, intA, intN, scratch, counters, wbuf, vbed, vstats, vwork, flagbuf;
     PinBuf h_blob, h_out;
     Plan plan;
     int32_t last_flags = 0, last_solver = 0, last_nfolds = 0;
@@ -128,22 +147,31 @@ int fail(dbslmm_b200_handle* h, int code, const std::string& msg) {
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// DBSLMM_B200_TRACE=1: host-side wall-clock marks of one fit on stderr (tuning aid)
+struct Trace {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    Trace() : on(std::getenv("DBSLMM_B200_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char* what) const {
+        if (on) std::fprintf(stderr, "[dbslmm_b200 trace] %-28s %8.3f ms\n", what,
+                             std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    }
+};
+
 // ------------------------------------------------------------------------------------------
 // Plan construction (host): the block scheduler's bookkeeping
 // ------------------------------------------------------------------------------------------
-// `miss` = per-block missing-call flags (nullptr: assume none; verified on the device, see fit)
-int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, const int32_t* miss_in) {
+// Step 1: block sizes, size classes, batches and the block order.  Cheap (O(n_blocks)), so the streaming fit can
+// start its class-ordered uploads before the rest of the plan exists.
+int make_batches(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, bool streaming) {
     const int nb = a->n_blocks;
     P = Plan();
     P.n_blocks = nb;
-    int n_test = 0;
-    if (a->test_bed) for (int i = 0; i < a->test_n_total; ++i) n_test += (a->test_indicator[i] != 0);
-    P.n_test = n_test;
+    P.streaming = streaming;
     P.blocks.resize(nb);
     P.tot_s = a->s_off[nb];
     P.tot_l = a->l_off ? a->l_off[nb] : 0;
-    const int64_t n_snp = h->n_snp;
-    int64_t goff = 0, croff = 0, moff = 0;
+    std::vector<int32_t> by_cls[kNumClasses];
     for (int b = 0; b < nb; ++b) {
         const int ms = a->s_off[b + 1] - a->s_off[b];
         const int ml = a->l_off ? a->l_off[b + 1] - a->l_off[b] : 0;
@@ -153,6 +181,64 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
         d.ms = ms;
         d.mp = (d.m + 7) / 8 * 8;
         d.ld = d.mp;
+        const int K = (d.mp + 63) / 64;
+        int c = 0;
+        while (K > kClassMaxPanels[c]) ++c;
+        by_cls[c].push_back(b);          // m == 0 blocks land in class 0: no tiles, no steps, they only exist
+    }
+    P.order.reserve(nb);
+    auto add_batch = [&](std::vector<int32_t>& sub, int cls) {
+        if (sub.empty()) return;
+        Batch B;
+        B.cls = cls;
+        B.ord_off = (int32_t)P.order.size();
+        std::stable_sort(sub.begin(), sub.end(), [&](int x, int y) { return P.blocks[x].m > P.blocks[y].m; });
+        P.order.insert(P.order.end(), sub.begin(), sub.end());
+        B.ord_n = (int32_t)sub.size();
+        P.batches.push_back(std::move(B));
+    };
+    if (!streaming) {
+        for (int c = kNumClasses - 1; c >= 0; --c) add_batch(by_cls[c], c);
+        return DBSLMM_B200_OK;
+    }
+    // Streaming: the two big classes first (few, scattered blocks with the longest dependency chains), then the
+    // bulk (classes 1 and 0 together) cut into REGIONS of consecutive blocks with equal SNP counts: a region is one
+    // contiguous stretch of the .bed (minus the big blocks inside it), so its upload is a handful of large copies,
+    // and its factorisation starts while the next region is still crossing PCIe.  Regions alternate between the two
+    // bulk streams so the thin last steps of one overlap the first steps of the next.
+    add_batch(by_cls[3], 3);
+    add_batch(by_cls[2], 2);
+    std::vector<int32_t> bulk(by_cls[1].size() + by_cls[0].size());
+    std::merge(by_cls[1].begin(), by_cls[1].end(), by_cls[0].begin(), by_cls[0].end(), bulk.begin());
+    int64_t tot = 0;
+    for (int b : bulk) tot += P.blocks[b].m;
+    const int nsub = (bulk.size() >= 256 && tot >= 100000) ? 4 : 1;
+    size_t i = 0;
+    int64_t acc = 0;
+    for (int sb = 0; sb < nsub; ++sb) {
+        const int64_t target = tot * (sb + 1) / nsub;
+        std::vector<int32_t> sub;
+        while (i < bulk.size() && (sb == nsub - 1 || acc < target)) { acc += P.blocks[bulk[i]].m; sub.push_back(bulk[i]); ++i; }
+        add_batch(sub, (sb & 1) ? 0 : 1);
+    }
+    return DBSLMM_B200_OK;
+}
+
+// Step 2: device layout, Gram tiles, Cholesky step lists, the pinned blob.
+// `miss` = per-block missing-call flags (nullptr: assume none; verified on the device, see fit)
+int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, const int32_t* miss_in) {
+    const int nb = a->n_blocks;
+    int n_test = 0;
+    if (a->test_bed) for (int i = 0; i < a->test_n_total; ++i) n_test += (a->test_indicator[i] != 0);
+    P.n_test = n_test;
+    const int64_t n_snp = h->n_snp;
+    int64_t goff = 0, croff = 0, moff = 0;
+    // layout order: block index (resident panel) or batch order (streaming: a batch's rows are one range)
+    std::vector<int32_t> lay(nb);
+    if (P.streaming) lay = P.order; else std::iota(lay.begin(), lay.end(), 0);
+    for (int b : lay) {
+        BlockDesc& d = P.blocks[b];
+        const int ms = d.ms, ml = d.m - d.ms;
         d.goff = (int32_t)goff;
         d.croff = (int32_t)croff;
         d.moff = moff;
@@ -160,14 +246,7 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
         d.out_l = a->l_off ? a->l_off[b] : 0;
         d.nrows = d.mp + 8 + n_test * (1 + (ml > 0 ? 1 : 0));       // test-genotype rows of the variance side channel
         const int miss = miss_in ? (miss_in[b] != 0) : 0;
-        for (int j = 0; j < ms; ++j) {
-            const int32_t p = a->s_pos[a->s_off[b] + j];
-            if (p < 0 || p >= n_snp) return fail(h, DBSLMM_B200_ERR_ARG, "s_pos out of range of the loaded .bed");
-        }
-        for (int j = 0; j < ml; ++j) {
-            const int32_t p = a->l_pos[a->l_off[b] + j];
-            if (p < 0 || p >= n_snp) return fail(h, DBSLMM_B200_ERR_ARG, "l_pos out of range of the loaded .bed");
-        }
+        (void)ms;
         d.has_missing = miss;
         goff += d.m;
         croff += (int64_t)d.m * (miss ? 2 : 1);
@@ -183,47 +262,50 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
     P.mat_doubles = moff;
     P.decode_bytes = (double)croff * ((double)h->pitch + (double)h->n_pad);
 
-    P.order.resize(nb);
-    std::iota(P.order.begin(), P.order.end(), 0);
-    std::stable_sort(P.order.begin(), P.order.end(),
-                     [&](int x, int y) { return P.blocks[x].m > P.blocks[y].m; });
-
-    // Gram tiles (lower triangle of 128x128 tiles), big blocks first
+    // Gram tiles (lower triangle of 128x128 tiles) in batch order, big blocks first inside a batch
     std::vector<GramTile> tiles_plain, tiles_miss;
-    for (int b : P.order) {
-        const BlockDesc& d = P.blocks[b];
-        const int nt = (d.mp + 127) / 128;
-        for (int ti = 0; ti < nt; ++ti)
-            for (int tj = 0; tj <= ti; ++tj) (d.has_missing ? tiles_miss : tiles_plain).push_back({b, ti, tj, 0});
+    for (Batch& B : P.batches) {
+        B.tile0 = (int32_t)tiles_plain.size();
+        B.crow0 = B.grow0 = INT64_MAX;
+        B.crow1 = B.grow1 = 0;
+        for (int i = 0; i < B.ord_n; ++i) {
+            const int b = P.order[B.ord_off + i];
+            const BlockDesc& d = P.blocks[b];
+            if (d.m == 0) continue;
+            B.crow0 = std::min<int64_t>(B.crow0, d.croff);
+            B.crow1 = std::max<int64_t>(B.crow1, (int64_t)d.croff + (int64_t)d.m * (d.has_missing ? 2 : 1));
+            B.grow0 = std::min<int64_t>(B.grow0, d.goff);
+            B.grow1 = std::max<int64_t>(B.grow1, (int64_t)d.goff + d.m);
+            const int nt = (d.mp + 127) / 128;
+            for (int ti = 0; ti < nt; ++ti)
+                for (int tj = 0; tj <= ti; ++tj) (d.has_missing ? tiles_miss : tiles_plain).push_back({b, ti, tj, 0});
+        }
+        if (B.crow0 == INT64_MAX) B.crow0 = B.crow1 = B.grow0 = B.grow1 = 0;
+        B.tile1 = (int32_t)tiles_plain.size();
     }
     P.n_tiles_plain = (int32_t)tiles_plain.size();
     P.n_tiles_miss = (int32_t)tiles_miss.size();
 
-    // Cholesky step lists per size class
+    // Cholesky step lists per batch
     std::vector<int32_t> diag_items;
     std::vector<int4> panel_items;
     int32_t n_groups = 0;
     constexpr int kTargetCtas = 296;                  // 2 CTAs per SM on a 148-SM part
-    for (int c = 0; c < kNumClasses; ++c) {
-        const int lo = (c == 0) ? 0 : kClassMaxPanels[c - 1];
-        const int hi = kClassMaxPanels[c];
-        std::vector<int> members;
+    for (Batch& B : P.batches) {
+        const int32_t* members = P.order.data() + B.ord_off;
         int kmax = 0;
-        for (int b : P.order) {
-            const int K = (P.blocks[b].mp + 63) / 64;
-            if (K > lo && K <= hi) { members.push_back(b); kmax = std::max(kmax, K); }
-        }
-        P.steps[c].resize(kmax);
-        int64_t class_scratch = 0;
+        for (int i = 0; i < B.ord_n; ++i) kmax = std::max(kmax, (P.blocks[members[i]].mp + 63) / 64);
+        B.steps.resize(kmax);
+        int64_t batch_scratch = 0;
         for (int k = 0; k < kmax; ++k) {
-            StepList& s = P.steps[c][k];
+            StepList& s = B.steps[k];
             s.diag_off = (int32_t)diag_items.size();
             s.panel_off = (int32_t)panel_items.size();
             // macro tiles of this step, then the split-K factor: when a step has few tiles but a long K
             // loop (late panels of big blocks), slice K so the step still fills the GPU
             int ntiles = 0;
-            for (int b : members) {
-                const BlockDesc& d = P.blocks[b];
+            for (int i = 0; i < B.ord_n; ++i) {
+                const BlockDesc& d = P.blocks[members[i]];
                 if ((d.mp + 63) / 64 <= k) continue;
                 const int wk = std::min(64, d.mp - 64 * k);
                 ntiles += (d.nrows - (64 * k + wk) + 127) / 128;
@@ -235,7 +317,8 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
             // macro tile 0 of every block goes first: its CTA also factors the next diagonal tile (fused), so it
             // should start in the first wave of the launch
             for (int pass = 0; pass < 2; ++pass)
-                for (int b : members) {
+                for (int i = 0; i < B.ord_n; ++i) {
+                    const int b = members[i];
                     const BlockDesc& d = P.blocks[b];
                     const int K = (d.mp + 63) / 64;
                     if (K <= k) continue;
@@ -251,10 +334,10 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
             s.n_groups = n_groups - s.group_base;
             s.n_diag = (int32_t)diag_items.size() - s.diag_off;
             s.n_panel = (int32_t)panel_items.size() - s.panel_off;
-            class_scratch = std::max<int64_t>(class_scratch, (int64_t)s.n_groups * nsl * 128 * 64);
+            batch_scratch = std::max<int64_t>(batch_scratch, (int64_t)s.n_groups * nsl * 128 * 64);
         }
-        P.scratch_off[c] = P.scratch_doubles;
-        P.scratch_doubles += class_scratch;
+        B.scratch_off = P.scratch_doubles;
+        P.scratch_doubles += batch_scratch;
     }
 
     // ---- pack the blob
@@ -270,17 +353,6 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
     P.o_diag = place(sizeof(int32_t) * diag_items.size());
     P.o_panel = place(sizeof(int4) * panel_items.size());
     P.n_groups = n_groups;
-    P.n_big = 0;
-    for (int b : P.order) { if (P.blocks[b].mp > 1024) P.n_big++; else break; }
-    for (int c = 0; c < kNumClasses; ++c) { P.cls_off[c] = 0; P.cls_n[c] = 0; }
-    for (int i = 0; i < nb; ++i) {                    // `order` is by descending size => classes are contiguous
-        const int K = (P.blocks[P.order[i]].mp + 63) / 64;
-        if (K == 0) continue;
-        int c = 0;
-        while (K > kClassMaxPanels[c]) ++c;
-        if (P.cls_n[c] == 0) P.cls_off[c] = i;
-        P.cls_n[c]++;
-    }
     P.blob_bytes = o;
     // fill the pinned staging buffer in place (no intermediate copy; alignment gaps are never read)
     if (h->h_blob.ensure(o + 256) != cudaSuccess) return fail(h, DBSLMM_B200_ERR_NOMEM, "pinned plan buffer");
@@ -289,22 +361,55 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
     uint32_t* rs = reinterpret_cast<uint32_t*>(blob.data() + P.o_rowsrc);
     int32_t* rg = reinterpret_cast<int32_t*>(blob.data() + P.o_rowg);
     double* z = reinterpret_cast<double*>(blob.data() + P.o_z);
-    for (int b = 0; b < nb; ++b) {
-        const BlockDesc& d = P.blocks[b];
-        const int ml = d.m - d.ms;
-        for (int j = 0; j < d.m; ++j) {
-            const bool small = j < d.ms;
-            const int32_t p = small ? a->s_pos[a->s_off[b] + j] : a->l_pos[a->l_off[b] + (j - d.ms)];
-            const double zz = small ? a->s_z[a->s_off[b] + j] : a->l_z[a->l_off[b] + (j - d.ms)];
-            rs[d.croff + j] = (uint32_t)p;
-            rg[d.croff + j] = d.goff + j;
-            z[d.goff + j] = zz;
-            if (d.has_missing) {
-                rs[d.croff + d.m + j] = (uint32_t)p | 0x80000000u;
-                rg[d.croff + d.m + j] = -1;
+    // per-SNP rows (source .bed row, SNP-row index, z-score): the only O(#SNPs) part of the plan, filled by a few
+    // host threads, each owning a contiguous range of blocks; the .bed row range check rides along
+    {
+        const int nthr = (int)std::max<int64_t>(1, std::min<int64_t>({8, (int64_t)std::thread::hardware_concurrency(), goff / 65536}));
+        std::atomic<int> bad{0};
+        auto fill = [&](int b0, int b1) {
+            int oob = 0;
+            for (int b = b0; b < b1; ++b) {
+                const BlockDesc& d = P.blocks[b];
+                const int32_t* sp = a->s_pos + a->s_off[b];
+                const double* sz = a->s_z + a->s_off[b];
+                uint32_t* rsb = rs + d.croff;
+                int32_t* rgb = rg + d.croff;
+                double* zb = z + d.goff;
+                for (int j = 0; j < d.ms; ++j) {
+                    const int32_t p = sp[j];
+                    oob |= (p < 0) | (p >= n_snp);
+                    rsb[j] = (uint32_t)p; rgb[j] = d.goff + j; zb[j] = sz[j];
+                }
+                if (d.m > d.ms) {
+                    const int32_t* lp = a->l_pos + a->l_off[b];
+                    const double* lz = a->l_z + a->l_off[b];
+                    for (int j = d.ms; j < d.m; ++j) {
+                        const int32_t p = lp[j - d.ms];
+                        oob |= (p < 0) | (p >= n_snp);
+                        rsb[j] = (uint32_t)p; rgb[j] = d.goff + j; zb[j] = lz[j - d.ms];
+                    }
+                }
+                if (d.has_missing)
+                    for (int j = 0; j < d.m; ++j) { rsb[d.m + j] = rsb[j] | 0x80000000u; rgb[d.m + j] = -1; }
             }
+            if (oob) bad.store(1);
+        };
+        if (nthr == 1) fill(0, nb);
+        else {
+            std::vector<std::thread> th;
+            int b0 = 0;
+            for (int t = 0; t < nthr; ++t) {
+                // cut at equal SNP counts (block-index order; goff is monotone only in the resident layout, so count)
+                int b1 = b0;
+                int64_t acc = 0;
+                const int64_t share = (goff + nthr - 1) / nthr;
+                while (b1 < nb && (t == nthr - 1 || acc < share)) acc += P.blocks[b1++].m;
+                th.emplace_back(fill, b0, b1);
+                b0 = b1;
+            }
+            for (std::thread& x : th) x.join();
         }
-        (void)ml;
+        if (bad.load()) return fail(h, DBSLMM_B200_ERR_ARG, "s_pos / l_pos out of range of the loaded .bed");
     }
     if (!tiles_plain.empty()) std::memcpy(blob.data() + P.o_tiles_plain, tiles_plain.data(), sizeof(GramTile) * tiles_plain.size());
     if (!tiles_miss.empty()) std::memcpy(blob.data() + P.o_tiles_miss, tiles_miss.data(), sizeof(GramTile) * tiles_miss.size());
@@ -366,16 +471,23 @@ int dbslmm_b200_create(int device, dbslmm_b200_handle** out) {
     if (!h) return DBSLMM_B200_ERR_NOMEM;
     h->device = device;
     h->n_sm = prop.multiProcessorCount;
-    if (const char* e = std::getenv("DBSLMM_B200_FUSE_DIAG")) h->fuse_diag = (e[0] != '0');   // tuning switch
-    bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
+    if (const char* e = std::getenv("DBSLMM_B200_FUSE_DIAG")) h->fuse_diag = (e[0] != '0');   // tuning switches
+    if (const char* e = std::getenv("DBSLMM_B200_STREAM_BED")) h->stream_bed = (e[0] != '0');
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);     // numerically lower = higher priority
-    for (int c = 0; c < kNumClasses && ok; ++c) {
-        // the classes with the most panel steps have the longest dependency chains: schedule them first
-        const int prio = std::max(prio_hi, prio_lo - c);
-        ok = cudaStreamCreateWithPriority(&h->cls_stream[c], cudaStreamNonBlocking, prio) == cudaSuccess &&
-             cudaEventCreate(&h->ev_join[c]) == cudaSuccess && cudaEventCreate(&h->ev_cend[c]) == cudaSuccess;
+    // the main stream (decode, Gram, copies) outranks the Cholesky streams: in a streaming fit the decode/Gram of a
+    // later batch must get SMs while earlier batches are being factored
+    bool ok = cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
+    for (int b = 0; b < kMaxBatches && ok; ++b) {
+        // batches come in order of falling dependency-chain length (big classes first): schedule them first
+        const int prio = std::max(prio_hi + 1, prio_lo - std::max(0, 4 - b));
+        ok = cudaStreamCreateWithPriority(&h->b_stream[b], cudaStreamNonBlocking, prio) == cudaSuccess;
     }
+    for (int b = 0; b < kMaxBatches && ok; ++b)
+        ok = cudaEventCreate(&h->ev_join[b]) == cudaSuccess && cudaEventCreate(&h->ev_cend[b]) == cudaSuccess &&
+             cudaEventCreate(&h->ev_up[b]) == cudaSuccess && cudaEventCreate(&h->ev_gram[b]) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&h->up_stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->ev_blob, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < 8 && ok; ++i) ok = cudaEventCreate(&h->ev[i]) == cudaSuccess;
     ok = ok && cudaEventCreate(&h->ev_fork) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->ev_bed, cudaEventDisableTiming) == cudaSuccess;
@@ -390,7 +502,7 @@ void dbslmm_b200_destroy(dbslmm_b200_handle* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     DevBuf* bufs[] = {&h->bed, &h->stats, &h->codes, &h->sigma, &h->lbuf, &h->rowN, &h->rowS, &h->rowR,
-                      &h->planblob, &h->beta, &h->status, &h->intQ, &h->intA, &h->intN, &h->scratch, &h->counters, &h->wbuf, &h->vbed, &h->vstats, &h->vwork};
+                      &h->planblob, &h->beta, &h->status, &h->intQ, &h->intA, &h->intN, &h->scratch, &h->counters, &h->wbuf, &h->vbed, &h->vstats, &h->vwork, &h->flagbuf};
     for (DevBuf* b : bufs) b->release();
     h->h_blob.release();
     h->h_out.release();
@@ -398,11 +510,16 @@ void dbslmm_b200_destroy(dbslmm_b200_handle* h) {
     if (h->ev_bed) cudaEventDestroy(h->ev_bed);
     for (int i = 0; i < 8; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-    for (int c = 0; c < kNumClasses; ++c) {
-        if (h->ev_join[c]) cudaEventDestroy(h->ev_join[c]);
-        if (h->ev_cend[c]) cudaEventDestroy(h->ev_cend[c]);
-        if (h->cls_stream[c]) cudaStreamDestroy(h->cls_stream[c]);
+    for (int b = 0; b < kMaxBatches; ++b) {
+        if (h->ev_join[b]) cudaEventDestroy(h->ev_join[b]);
+        if (h->ev_cend[b]) cudaEventDestroy(h->ev_cend[b]);
+        if (h->ev_up[b]) cudaEventDestroy(h->ev_up[b]);
+        if (h->ev_gram[b]) cudaEventDestroy(h->ev_gram[b]);
     }
+    for (int b = 0; b < kMaxBatches; ++b)
+        if (h->b_stream[b]) cudaStreamDestroy(h->b_stream[b]);
+    if (h->up_stream) cudaStreamDestroy(h->up_stream);
+    if (h->ev_blob) cudaEventDestroy(h->ev_blob);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -433,6 +550,22 @@ int dbslmm_b200_load_bed(dbslmm_b200_handle* h, const uint8_t* bed, int64_t n_sn
     h->pitch = pitch;
     h->n_pad = (n_ref + 127) / 128 * 128;
     h->plan.valid = false;
+    h->stats_valid = true;
+    return DBSLMM_B200_OK;
+}
+
+// Per-SNP statistics of the resident panel, computed on demand: a streaming fit (fit_args.bed) uploads the panel
+// without them (its decoder derives the counts of the rows it reads itself).
+static int ensure_stats(dbslmm_b200_handle* h) {
+    if (h->stats_valid) return DBSLMM_B200_OK;
+    if (h->bed_pending) { CU_TRY(h, cudaEventSynchronize(h->ev_bed)); h->bed_pending = false; }
+    CU_TRY(h, h->stats.ensure(sizeof(SnpStat) * (size_t)h->n_snp));
+    CU_TRY(h, h->h_stats.ensure(sizeof(SnpStat) * (size_t)h->n_snp));
+    CU_TRY(h, launch_snp_stats((const uint8_t*)h->bed.p, h->n_snp, h->n_ref, (SnpStat*)h->stats.p, h->n_sm, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(h->h_stats.p, h->stats.p, sizeof(SnpStat) * (size_t)h->n_snp, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaEventRecord(h->ev_bed, h->stream));
+    h->bed_pending = true;
+    h->stats_valid = true;
     return DBSLMM_B200_OK;
 }
 
@@ -440,6 +573,7 @@ int dbslmm_b200_snp_stats(dbslmm_b200_handle* h, double* maf_out, int32_t* n_non
     if (!h) return DBSLMM_B200_ERR_ARG;
     if (h->n_snp == 0) return fail(h, DBSLMM_B200_ERR_STATE, "snp_stats before load_bed");
     CU_TRY(h, cudaSetDevice(h->device));
+    { int rc = ensure_stats(h); if (rc != DBSLMM_B200_OK) return rc; }
     if (h->bed_pending) { CU_TRY(h, cudaEventSynchronize(h->ev_bed)); h->bed_pending = false; }
     const SnpStat* hs = (const SnpStat*)h->h_stats.p;
     for (int64_t i = 0; i < h->n_snp; ++i) {
@@ -478,47 +612,133 @@ int dbslmm_b200_plan_shards(int32_t n_blocks, const int32_t* m_s, const int32_t*
     return DBSLMM_B200_OK;
 }
 
-int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
-    if (!h || !a) return DBSLMM_B200_ERR_ARG;
-    if (h->n_snp == 0) return fail(h, DBSLMM_B200_ERR_STATE, "fit before load_bed");
-    if (a->n_blocks < 0 || !a->s_off || a->n_folds < 1 || !a->sigma_s || a->n_obs <= 0 || !a->beta_s_out)
-        return fail(h, DBSLMM_B200_ERR_ARG, "fit: bad arguments");
-    if (a->n_blocks > 0 && a->s_off[a->n_blocks] > 0 && (!a->s_pos || !a->s_z))
-        return fail(h, DBSLMM_B200_ERR_ARG, "fit: s_pos/s_z missing");
-    if (a->l_off && a->l_off[a->n_blocks] > 0 && (!a->l_pos || !a->l_z || !a->beta_l_out))
-        return fail(h, DBSLMM_B200_ERR_ARG, "fit: l_pos/l_z/beta_l_out missing");
-    if (!(a->tau > 0.0 && a->tau <= 1.0)) return fail(h, DBSLMM_B200_ERR_ARG, "fit: tau must be in (0,1]");
-    if (a->solver != DBSLMM_B200_SOLVER_CHOLESKY && a->solver != DBSLMM_B200_SOLVER_PCG)
-        return fail(h, DBSLMM_B200_ERR_ARG, "fit: unknown solver");
-    for (int f = 0; f < a->n_folds; ++f)
-        if (!(a->sigma_s[f] > 0.0)) return fail(h, DBSLMM_B200_ERR_ARG, "fit: sigma_s must be > 0");
-    const bool want_var = a->test_bed != nullptr;
-    if (want_var) {
-        if (a->solver != DBSLMM_B200_SOLVER_CHOLESKY) return fail(h, DBSLMM_B200_ERR_ARG, "fit: the variance side channel needs the Cholesky solver");
-        if (a->test_n_snp <= 0 || a->test_n_total <= 1 || !a->test_indicator || !a->variance_out || (a->s_off[a->n_blocks] > 0 && !a->s_tpos) ||
-            (a->l_off && a->l_off[a->n_blocks] > 0 && !a->l_tpos))
-            return fail(h, DBSLMM_B200_ERR_ARG, "fit: incomplete test-data arguments for the variance side channel");
-        if (a->flags & DBSLMM_B200_FLAG_PLAN_CACHED) return fail(h, DBSLMM_B200_ERR_ARG, "fit: PLAN_CACHED cannot be combined with the variance side channel");
+}  // extern "C"
+
+namespace {
+
+// Streaming fit, host side: the class-ordered uploads of the panel rows each batch needs (one copy per run of
+// adjacent blocks), then the rows no block uses, so the device copy ends up complete.
+struct UploadPlan {
+    typedef std::pair<int64_t, int64_t> Range;                  // [first, last] rows
+    std::vector<std::vector<Range>> per_batch;
+    std::vector<Range> all;
+    int next_batch = 0;
+};
+
+// Returns 1 if the block -> row map is too scattered to stream (covering ranges would move far more than the
+// panel), 0 on success, < 0 on error.
+int upload_prepare(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, const Plan& P, UploadPlan& U) {
+    const int nb = P.n_blocks;
+    const int64_t n_snp = h->n_snp;
+    std::vector<int32_t> lo((size_t)std::max(nb, 1), INT32_MAX), hi((size_t)std::max(nb, 1), -1);
+    for (int b = 0; b < nb; ++b) {
+        int32_t l = INT32_MAX, u = -1;
+        for (int j = a->s_off[b]; j < a->s_off[b + 1]; ++j) { const int32_t p = a->s_pos[j]; l = std::min(l, p); u = std::max(u, p); }
+        if (a->l_off) for (int j = a->l_off[b]; j < a->l_off[b + 1]; ++j) { const int32_t p = a->l_pos[j]; l = std::min(l, p); u = std::max(u, p); }
+        if (u >= 0 && (l < 0 || u >= n_snp)) return fail(h, DBSLMM_B200_ERR_ARG, "fit: SNP row out of range of the .bed");
+        lo[b] = l; hi[b] = u;
     }
-    CU_TRY(h, cudaSetDevice(h->device));
+    typedef UploadPlan::Range Range;
+    U.per_batch.assign(P.batches.size(), std::vector<Range>());
+    int64_t rows_total = 0;
+    for (size_t bi = 0; bi < P.batches.size(); ++bi) {
+        const Batch& B = P.batches[bi];
+        std::vector<Range> r;
+        for (int i = 0; i < B.ord_n; ++i) {
+            const int b = P.order[B.ord_off + i];
+            if (hi[b] >= 0) r.push_back(Range(lo[b], hi[b]));
+        }
+        std::sort(r.begin(), r.end());
+        std::vector<Range>& m = U.per_batch[bi];
+        for (const Range& x : r) {
+            if (!m.empty() && x.first <= m.back().second + 33) m.back().second = std::max(m.back().second, x.second);
+            else m.push_back(x);
+        }
+        for (const Range& x : m) { rows_total += x.second - x.first + 1; U.all.push_back(x); }
+    }
+    return (rows_total > n_snp + n_snp / 4) ? 1 : 0;            // scattered subsets: a plain full upload is cheaper
+}
+
+// Issue the uploads of batches [next_batch, upto); upto == #batches also sends the rows outside every block.
+int upload_issue(dbslmm_b200_handle* h, const Plan& P, UploadPlan& U, const uint8_t* bed, int upto) {
+    typedef UploadPlan::Range Range;
+    const size_t pitch = (size_t)h->pitch;
+    const int64_t n_snp = h->n_snp;
+    uint8_t* dev = (uint8_t*)h->bed.p;
+    for (; U.next_batch < upto; ++U.next_batch) {
+        for (const Range& x : U.per_batch[U.next_batch])
+            CU_TRY(h, cudaMemcpyAsync(dev + (size_t)x.first * pitch, bed + (size_t)x.first * pitch,
+                                      (size_t)(x.second - x.first + 1) * pitch, cudaMemcpyHostToDevice, h->up_stream));
+        CU_TRY(h, cudaEventRecord(h->ev_up[U.next_batch], h->up_stream));
+    }
+    if (upto < (int)P.batches.size()) return 0;
+    // rows outside every block (unmatched SNPs): last, so the resident copy is complete for later calls
+    std::sort(U.all.begin(), U.all.end());
+    int64_t next = 0;
+    for (const Range& x : U.all) {
+        if (x.first > next)
+            CU_TRY(h, cudaMemcpyAsync(dev + (size_t)next * pitch, bed + (size_t)next * pitch, (size_t)(x.first - next) * pitch,
+                                      cudaMemcpyHostToDevice, h->up_stream));
+        next = std::max(next, x.second + 1);
+    }
+    if (next < n_snp)
+        CU_TRY(h, cudaMemcpyAsync(dev + (size_t)next * pitch, bed + (size_t)next * pitch, (size_t)(n_snp - next) * pitch,
+                                  cudaMemcpyHostToDevice, h->up_stream));
+    CU_TRY(h, cudaMemsetAsync(dev + (size_t)n_snp * pitch, 0xFF, 64, h->up_stream));
+    CU_TRY(h, cudaEventRecord(h->ev_bed, h->up_stream));
+    h->bed_pending = true;
+    return 0;
+}
+
+// One fit.  streaming = the panel is uploaded inside this call from a->bed, batch by batch (see Batch); otherwise the
+// panel loaded by load_bed is used.  Returns n_bad >= 0, an error < 0, or kRetryResident when a streaming fit met
+// missing calls (its speculative no-missing plan does not apply; the caller repeats the fit on the resident copy).
+constexpr int kRetryResident = 1 << 30;
+
+int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streaming) {
+    const bool want_var = a->test_bed != nullptr;
     cudaStream_t st = h->stream;
     const bool pcg = (a->solver == DBSLMM_B200_SOLVER_PCG);
     const bool full = pcg || (a->flags & DBSLMM_B200_FLAG_FULL_SIGMA);
     const bool keep_int = (a->flags & DBSLMM_B200_FLAG_KEEP_INT_GRAM) != 0;
 
+    Trace tr;
+    UploadPlan U;
     // ---- plan
     Plan& P = h->plan;
-    const bool reuse = (a->flags & DBSLMM_B200_FLAG_PLAN_CACHED) && P.valid && P.n_blocks == a->n_blocks &&
-                       P.tot_s == a->s_off[a->n_blocks] && P.tot_l == (a->l_off ? a->l_off[a->n_blocks] : 0);
+    const bool reuse = !streaming && (a->flags & DBSLMM_B200_FLAG_PLAN_CACHED) && P.valid && !P.streaming &&
+                       P.n_blocks == a->n_blocks && P.tot_s == a->s_off[a->n_blocks] &&
+                       P.tot_l == (a->l_off ? a->l_off[a->n_blocks] : 0);
     if (!reuse) {
-        // The plan is built while load_bed's upload may still be in flight, so it cannot look at the panel:
-        // it assumes no block has missing calls; block_missing_kernel checks that on the device (below) and
-        // the plan is rebuilt with the true flags in the rare case the assumption fails.
+        // The plan is built while the panel may still be crossing PCIe, so it cannot look at it: it assumes no
+        // block has missing calls; that is checked on the device (below) and the plan is rebuilt with the true
+        // flags in the rare case the assumption fails.
         h->miss_flags.assign((size_t)std::max(a->n_blocks, 1), 0);
-        int rc = build_plan(h, a, P, nullptr);
+        int rc = make_batches(h, a, P, streaming);
         if (rc != DBSLMM_B200_OK) { P.valid = false; return rc; }
+        if (streaming) {
+            tr.mark("batches");
+            rc = upload_prepare(h, a, P, U);
+            if (rc < 0) { P.valid = false; return rc; }
+            // the biggest classes go out before the plan is built (the H2D queue is in issue order: the plan blob must
+            // not wait behind the whole panel, and the DMA engine should not idle while the host builds the plan)
+            if (rc == 0) { rc = upload_issue(h, P, U, a->bed, std::min(2, (int)P.batches.size())); if (rc < 0) { P.valid = false; return rc; } }
+            tr.mark("first uploads issued");
+            if (rc == 1) {
+                // not streamable: plain full upload, then the resident path
+                P.valid = false;
+                rc = dbslmm_b200_load_bed(h, a->bed, a->bed_n_snp, a->bed_n_ref);
+                if (rc != DBSLMM_B200_OK) return rc;
+                return fit_impl(h, a, false);
+            }
+        }
+        rc = build_plan(h, a, P, nullptr);
+        if (rc != DBSLMM_B200_OK) { P.valid = false; return rc; }
+        tr.mark("plan built");
     }
+    if (!streaming) { int rc = ensure_stats(h); if (rc != DBSLMM_B200_OK) return rc; }
     const int nb = P.n_blocks;
+    const int nbatch = (int)P.batches.size();
     const size_t nfold = (size_t)a->n_folds;
 
     // ---- workspace
@@ -543,7 +763,7 @@ int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
         CU_TRY(h, h->intN.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(P.mat_doubles, 1)));
     }
     const size_t out_bytes = sizeof(double) * n_out * nfold + sizeof(int32_t) * (size_t)(2 * nb);
-    CU_TRY(h, h->h_out.ensure(out_bytes + 64));
+    CU_TRY(h, h->h_out.ensure(out_bytes + 128));
 
     uint8_t* dblob = (uint8_t*)h->planblob.p;   // (re-pointed below if the plan has to be rebuilt)
     const BlockDesc* d_blocks = (const BlockDesc*)(dblob + P.o_blocks);
@@ -563,7 +783,18 @@ int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
     CU_TRY(h, cudaEventRecord(h->ev[0], st));
     // ---- upload
     if (!reuse) {
-        if (P.blob_bytes) CU_TRY(h, cudaMemcpyAsync(dblob, h->h_blob.p, P.blob_bytes, cudaMemcpyHostToDevice, st));
+        if (!streaming) {
+            if (P.blob_bytes) CU_TRY(h, cudaMemcpyAsync(dblob, h->h_blob.p, P.blob_bytes, cudaMemcpyHostToDevice, st));
+        } else {
+            // The plan blob travels on the UPLOAD stream, between the first batches and the rest of the panel: copies
+            // of one stream run in issue order, whereas a copy on another stream may sit behind the whole panel.
+            if (P.blob_bytes) CU_TRY(h, cudaMemcpyAsync(dblob, h->h_blob.p, P.blob_bytes, cudaMemcpyHostToDevice, h->up_stream));
+            CU_TRY(h, cudaEventRecord(h->ev_blob, h->up_stream));
+            CU_TRY(h, cudaStreamWaitEvent(st, h->ev_blob, 0));
+            int rc = upload_issue(h, P, U, a->bed, nbatch);
+            if (rc < 0) return rc;
+            tr.mark("all uploads issued");
+        }
     } else if (P.n_snp_rows > 0) {
         // same CSR layout, new z-scores
         double* z = reinterpret_cast<double*>((uint8_t*)h->h_blob.p + P.o_z);
@@ -575,7 +806,9 @@ int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
         CU_TRY(h, cudaMemcpyAsync(dblob + P.o_z, z, sizeof(double) * (size_t)P.n_snp_rows, cudaMemcpyHostToDevice, st));
     }
     CU_TRY(h, cudaMemsetAsync(d_status, 0, sizeof(int32_t) * (size_t)std::max(2 * nb, 1), st));
-    if (!reuse && nb > 0 && P.n_code_rows > 0) {
+    CU_TRY(h, h->flagbuf.ensure(256));
+    CU_TRY(h, cudaMemsetAsync(h->flagbuf.p, 0, 256, st));
+    if (!streaming && !reuse && nb > 0 && P.n_code_rows > 0) {
         // verify the no-missing assumption: per-block flags from the device statistics (1 int per block)
         int32_t* hflags = (int32_t*)h->h_out.p;
         CU_TRY(h, launch_block_missing(d_blocks, nb, d_rowsrc, (const SnpStat*)h->stats.p, h->n_ref, d_iters, st));
@@ -607,21 +840,13 @@ int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
     }
     CU_TRY(h, cudaEventRecord(h->ev[1], st));
 
-    // ---- decode
+    if (!pcg && P.n_groups > 0) CU_TRY(h, cudaMemsetAsync(h->counters.p, 0, sizeof(int32_t) * (size_t)P.n_groups, st));
+    // ---- decode + gram
+    GramArgs g;
+    CUtensorMap tmap;
     if (P.n_code_rows > 0) {
-        CU_TRY(h, launch_decode_rows((const uint8_t*)h->bed.p, h->n_ref, h->n_pad, d_rowsrc, d_rowg, P.n_code_rows,
-                                     (const SnpStat*)h->stats.p, a->tau, (int8_t*)h->codes.p, (int32_t*)h->rowN.p,
-                                     (int32_t*)h->rowS.p, (double*)h->rowR.p, h->n_sm, st));
-        ++n_launch;
-    }
-    CU_TRY(h, cudaEventRecord(h->ev[2], st));
-
-    // ---- gram
-    if (P.n_code_rows > 0) {
-        CUtensorMap tmap;
         int rc = make_tensor_map(h, &tmap, h->codes.p, P.n_code_rows, h->n_pad);
         if (rc != DBSLMM_B200_OK) return rc;
-        GramArgs g;
         g.blocks = d_blocks;
         g.nk = h->n_pad / 128;
         g.n_ref = h->n_ref;
@@ -634,20 +859,60 @@ int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
         g.intA = keep_int ? (int32_t*)h->intA.p : nullptr;
         g.intN = keep_int ? (int32_t*)h->intN.p : nullptr;
         g.full = full ? 1 : 0;
-        if (P.n_tiles_plain) {
-            g.tiles = d_tiles_plain;
-            g.n_tiles = P.n_tiles_plain;
-            CU_TRY(h, launch_gram(tmap, g, false, st));
+        g.light = 0;
+    }
+    if (!streaming) {
+        if (P.n_code_rows > 0) {
+            CU_TRY(h, launch_decode_rows((const uint8_t*)h->bed.p, h->n_ref, h->n_pad, d_rowsrc, d_rowg, P.n_code_rows,
+                                         (const SnpStat*)h->stats.p, a->tau, (int8_t*)h->codes.p, (int32_t*)h->rowN.p,
+                                         (int32_t*)h->rowS.p, (double*)h->rowR.p, h->n_sm, st));
             ++n_launch;
         }
-        if (P.n_tiles_miss) {
-            g.tiles = d_tiles_miss;
-            g.n_tiles = P.n_tiles_miss;
-            CU_TRY(h, launch_gram(tmap, g, true, st));
+        CU_TRY(h, cudaEventRecord(h->ev[2], st));
+        if (P.n_code_rows > 0) {
+            if (P.n_tiles_plain) {
+                g.tiles = d_tiles_plain;
+                g.n_tiles = P.n_tiles_plain;
+                CU_TRY(h, launch_gram(tmap, g, false, st));
+                ++n_launch;
+            }
+            if (P.n_tiles_miss) {
+                g.tiles = d_tiles_miss;
+                g.n_tiles = P.n_tiles_miss;
+                CU_TRY(h, launch_gram(tmap, g, true, st));
+                ++n_launch;
+            }
+            CU_TRY(h, launch_fill_z(d_blocks, nullptr, nb, d_z, (double*)h->sigma.p, st));
             ++n_launch;
         }
-        CU_TRY(h, launch_fill_z(d_blocks, nb, d_z, (double*)h->sigma.p, st));
-        ++n_launch;
+    } else {
+        // one decode -> Gram chain per batch, each gated on the upload of that batch's rows; the batch's Cholesky
+        // (on its class stream, below) is gated on ev_gram, so big classes factor while the bulk is still in flight
+        CU_TRY(h, cudaEventRecord(h->ev[2], st));
+        for (int bi = 0; bi < nbatch; ++bi) {
+            const Batch& B = P.batches[bi];
+            CU_TRY(h, cudaStreamWaitEvent(st, h->ev_up[bi], 0));
+            const int64_t nrow = B.crow1 - B.crow0;
+            if (nrow > 0) {
+                // stats == nullptr: the decoder counts the genotypes of the rows it stages itself
+                CU_TRY(h, launch_decode_rows((const uint8_t*)h->bed.p, h->n_ref, h->n_pad, d_rowsrc + B.crow0, d_rowg + B.crow0,
+                                             nrow, nullptr, a->tau, (int8_t*)h->codes.p + (size_t)B.crow0 * h->n_pad,
+                                             (int32_t*)h->rowN.p, (int32_t*)h->rowS.p, (double*)h->rowR.p, h->n_sm, st));
+                CU_TRY(h, launch_rows_missing((const int32_t*)h->rowN.p + B.grow0, B.grow1 - B.grow0, h->n_ref,
+                                              (int32_t*)h->flagbuf.p, st));
+                n_launch += 2;
+                if (B.tile1 > B.tile0) {
+                    g.tiles = d_tiles_plain + B.tile0;
+                    g.n_tiles = B.tile1 - B.tile0;
+                    g.light = 1;                 // 3-stage ring: a Gram CTA fits on an SM next to one Cholesky panel CTA
+                    CU_TRY(h, launch_gram(tmap, g, false, st));
+                    ++n_launch;
+                }
+                CU_TRY(h, launch_fill_z(d_blocks, d_order + B.ord_off, B.ord_n, d_z, (double*)h->sigma.p, st));
+                ++n_launch;
+            }
+            CU_TRY(h, cudaEventRecord(h->ev_gram[bi], st));
+        }
     }
     double* d_var = nullptr;
     if (want_var && P.n_test > 0 && P.n_snp_rows > 0) {
@@ -684,6 +949,7 @@ int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
         d_var = (double*)(vw + o_var);
     }
     CU_TRY(h, cudaEventRecord(h->ev[3], st));
+    tr.mark("decode/gram launched");
 
     // ---- solve, once per heritability fold (Sigma is shared: only the ridge changes)
     float chol_ms_total = 0.f;
@@ -693,15 +959,16 @@ int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
         double* bs = d_beta + (size_t)f * n_out;
         double* bl = bs + P.tot_s;
         if (!pcg) {
-            if (P.n_groups > 0) CU_TRY(h, cudaMemsetAsync(h->counters.p, 0, sizeof(int32_t) * (size_t)P.n_groups, st));
+            if (f > 0 && P.n_groups > 0) CU_TRY(h, cudaMemsetAsync(h->counters.p, 0, sizeof(int32_t) * (size_t)P.n_groups, st));
             CU_TRY(h, cudaEventRecord(h->ev_fork, st));
-            for (int c = 0; c < kNumClasses; ++c) {
-                if (P.steps[c].empty()) continue;
-                cudaStream_t cs = h->cls_stream[c];
-                CU_TRY(h, cudaStreamWaitEvent(cs, h->ev_fork, 0));
-                const int64_t wstride = (int64_t)64 * 64 * std::max(nb, 1);
-                for (size_t k = 0; k < P.steps[c].size(); ++k) {
-                    const StepList& s = P.steps[c][k];
+            const int64_t wstride = (int64_t)64 * 64 * std::max(nb, 1);
+            for (int bi = 0; bi < nbatch; ++bi) {
+                const Batch& B = P.batches[bi];
+                cudaStream_t cs = h->b_stream[bi];
+                // a streaming fit's first fold starts each batch as soon as ITS Gram is done
+                CU_TRY(h, cudaStreamWaitEvent(cs, (streaming && f == 0) ? h->ev_gram[bi] : h->ev_fork, 0));
+                for (size_t k = 0; k < B.steps.size(); ++k) {
+                    const StepList& s = B.steps[k];
                     // the diagonal tile of panel k >= 1 is factored by the step k-1 panel launch (fused)
                     if (k == 0 || !h->fuse_diag) {
                         CU_TRY(h, launch_chol_diag(d_blocks, d_diag + s.diag_off, s.n_diag, (int32_t)k,
@@ -712,19 +979,19 @@ int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
                     }
                     CU_TRY(h, launch_chol_panel(d_blocks, d_panel + s.panel_off, s.n_panel, (int32_t)k,
                                                 (const double*)h->sigma.p, (double*)h->lbuf.p, (double*)h->wbuf.p, wstride,
-                                                h->fuse_diag, ridge, (double*)h->scratch.p + P.scratch_off[c],
+                                                h->fuse_diag, ridge, (double*)h->scratch.p + B.scratch_off,
                                                 (int32_t*)h->counters.p, s.group_base, d_status, cs));
                     ++n_launch;
                     ++n_chol_launch;
                 }
-                // the class's back substitution follows on its own stream: the big blocks' substitutions overlap
+                // the batch's back substitution follows on its own stream: the big blocks' substitutions overlap
                 // the factorisation of the bulk classes, which finish last
-                CU_TRY(h, cudaEventRecord(h->ev_cend[c], cs));
-                CU_TRY(h, launch_backsolve(d_blocks, d_order + P.cls_off[c], P.cls_n[c], kClassMaxPanels[c] > 16,
+                CU_TRY(h, cudaEventRecord(h->ev_cend[bi], cs));
+                CU_TRY(h, launch_backsolve(d_blocks, d_order + B.ord_off, B.ord_n, kClassMaxPanels[B.cls] > 16,
                                            (const double*)h->lbuf.p, inv_sqrt_n, bs, bl, P.max_mp, cs));
                 ++n_launch;
-                CU_TRY(h, cudaEventRecord(h->ev_join[c], cs));
-                CU_TRY(h, cudaStreamWaitEvent(st, h->ev_join[c], 0));
+                CU_TRY(h, cudaEventRecord(h->ev_join[bi], cs));
+                CU_TRY(h, cudaStreamWaitEvent(st, h->ev_join[bi], 0));
             }
             if (d_var) {
                 CU_TRY(h, launch_variance(d_blocks, nb, P.n_test, (const double*)h->sigma.p, (const double*)h->lbuf.p,
@@ -736,10 +1003,9 @@ int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
                 CU_TRY(h, cudaEventRecord(h->ev[7], st));
                 CU_TRY(h, cudaEventSynchronize(h->ev[7]));
                 float worst = 0.f;
-                for (int c = 0; c < kNumClasses; ++c) {
-                    if (P.steps[c].empty()) continue;
+                for (int bi = 0; bi < nbatch && !(streaming && f == 0); ++bi) {
                     float ms = 0.f;
-                    cudaEventElapsedTime(&ms, h->ev_fork, h->ev_cend[c]);
+                    cudaEventElapsedTime(&ms, h->ev_fork, h->ev_cend[bi]);
                     worst = std::max(worst, ms);
                 }
                 chol_ms_total += worst;
@@ -786,12 +1052,36 @@ int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
                               cudaMemcpyDeviceToHost, st));
     if (d_var) CU_TRY(h, cudaMemcpyAsync(a->variance_out, d_var, sizeof(double) * (size_t)a->n_folds * nb * P.n_test,
                                          cudaMemcpyDeviceToHost, st));
+    int32_t* h_flag = (int32_t*)(hout + align_up(out_bytes, 8));
+    CU_TRY(h, cudaMemcpyAsync(h_flag, h->flagbuf.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CU_TRY(h, cudaEventRecord(h->ev[5], st));
+    tr.mark("all launched");
+    if (tr.on && streaming) {
+        for (int bi = 0; bi < nbatch; ++bi) {
+            cudaEventSynchronize(h->ev_up[bi]);
+            char buf[64];
+            std::snprintf(buf, sizeof buf, "upload of batch %d (cls %d) done", bi, P.batches[bi].cls);
+            tr.mark(buf);
+        }
+    }
     CU_TRY(h, cudaStreamSynchronize(st));
+    tr.mark("device done");
+    if (tr.on && streaming && !pcg) {
+        for (int bi = 0; bi < nbatch; ++bi) {
+            float u = 0.f, g2 = 0.f, c = 0.f, j = 0.f;
+            cudaEventElapsedTime(&u, h->ev[0], h->ev_up[bi]);
+            cudaEventElapsedTime(&g2, h->ev[0], h->ev_gram[bi]);
+            cudaEventElapsedTime(&c, h->ev[0], h->ev_cend[bi]);
+            cudaEventElapsedTime(&j, h->ev[0], h->ev_join[bi]);
+            std::fprintf(stderr, "[dbslmm_b200 trace] batch %d cls %d blocks %d rows %lld: uploaded %.2f  gram done %.2f  chol done %.2f  backsolve done %.2f (device ms after fit start)\n",
+                         bi, P.batches[bi].cls, P.batches[bi].ord_n, (long long)(P.batches[bi].grow1 - P.batches[bi].grow0), u, g2, c, j);
+        }
+    }
     {
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return fail(h, DBSLMM_B200_ERR_CUDA, std::string("fit: ") + cudaGetErrorString(e));
     }
+    if (streaming && *h_flag != 0) { P.valid = false; return kRetryResident; }   // missing calls: see fit_impl's header
     const double* hb = (const double*)hout;
     for (int f = 0; f < a->n_folds; ++f) {
         std::memcpy(a->beta_s_out + (size_t)f * P.tot_s, hb + (size_t)f * n_out, sizeof(double) * (size_t)P.tot_s);
@@ -815,9 +1105,11 @@ int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
         cudaEventElapsedTime(&t->d2h_ms, h->ev[4], h->ev[5]);
         cudaEventElapsedTime(&t->total_ms, h->ev[0], h->ev[5]);
         t->chol_ms = chol_ms_total;
-        for (int c = 0; c < kNumClasses; ++c) {
-            t->class_ms[c] = 0.f;
-            if (!pcg && !P.steps[c].empty()) cudaEventElapsedTime(&t->class_ms[c], h->ev_fork, h->ev_cend[c]);
+        for (int c = 0; c < kNumClasses; ++c) t->class_ms[c] = 0.f;
+        for (int bi = 0; bi < nbatch && !pcg && !(streaming && a->n_folds == 1); ++bi) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, h->ev_fork, h->ev_cend[bi]);
+            t->class_ms[P.batches[bi].cls] = std::max(t->class_ms[P.batches[bi].cls], ms);
         }
         t->n_launches = n_launch;
         t->n_chol_launches = n_chol_launch;
@@ -826,6 +1118,58 @@ int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
         t->decode_bytes = P.decode_bytes;
     }
     return n_bad;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
+    if (!h || !a) return DBSLMM_B200_ERR_ARG;
+    if (!a->bed && h->n_snp == 0) return fail(h, DBSLMM_B200_ERR_STATE, "fit before load_bed (and no fit_args.bed)");
+    if (a->bed && (a->bed_n_snp <= 0 || a->bed_n_ref <= 1)) return fail(h, DBSLMM_B200_ERR_ARG, "fit: bad bed_n_snp / bed_n_ref");
+    if (a->n_blocks < 0 || !a->s_off || a->n_folds < 1 || !a->sigma_s || a->n_obs <= 0 || !a->beta_s_out)
+        return fail(h, DBSLMM_B200_ERR_ARG, "fit: bad arguments");
+    if (a->n_blocks > 0 && a->s_off[a->n_blocks] > 0 && (!a->s_pos || !a->s_z))
+        return fail(h, DBSLMM_B200_ERR_ARG, "fit: s_pos/s_z missing");
+    if (a->l_off && a->l_off[a->n_blocks] > 0 && (!a->l_pos || !a->l_z || !a->beta_l_out))
+        return fail(h, DBSLMM_B200_ERR_ARG, "fit: l_pos/l_z/beta_l_out missing");
+    if (!(a->tau > 0.0 && a->tau <= 1.0)) return fail(h, DBSLMM_B200_ERR_ARG, "fit: tau must be in (0,1]");
+    if (a->solver != DBSLMM_B200_SOLVER_CHOLESKY && a->solver != DBSLMM_B200_SOLVER_PCG)
+        return fail(h, DBSLMM_B200_ERR_ARG, "fit: unknown solver");
+    for (int f = 0; f < a->n_folds; ++f)
+        if (!(a->sigma_s[f] > 0.0)) return fail(h, DBSLMM_B200_ERR_ARG, "fit: sigma_s must be > 0");
+    const bool want_var = a->test_bed != nullptr;
+    if (want_var) {
+        if (a->solver != DBSLMM_B200_SOLVER_CHOLESKY) return fail(h, DBSLMM_B200_ERR_ARG, "fit: the variance side channel needs the Cholesky solver");
+        if (a->test_n_snp <= 0 || a->test_n_total <= 1 || !a->test_indicator || !a->variance_out || (a->s_off[a->n_blocks] > 0 && !a->s_tpos) ||
+            (a->l_off && a->l_off[a->n_blocks] > 0 && !a->l_tpos))
+            return fail(h, DBSLMM_B200_ERR_ARG, "fit: incomplete test-data arguments for the variance side channel");
+        if (a->flags & DBSLMM_B200_FLAG_PLAN_CACHED) return fail(h, DBSLMM_B200_ERR_ARG, "fit: PLAN_CACHED cannot be combined with the variance side channel");
+    }
+    CU_TRY(h, cudaSetDevice(h->device));
+    if (!a->bed) return fit_impl(h, a, false);
+
+    // ---- the panel comes with the call (what DBSLMMFIT::est does with its bed_str argument)
+    if (h->bed_pending) { CU_TRY(h, cudaEventSynchronize(h->ev_bed)); h->bed_pending = false; }
+    const bool can_stream = !want_var && a->solver == DBSLMM_B200_SOLVER_CHOLESKY && !(a->flags & DBSLMM_B200_FLAG_PLAN_CACHED) &&
+                            a->n_blocks > 0 && h->stream_bed;
+    if (!can_stream) {
+        int rc = dbslmm_b200_load_bed(h, a->bed, a->bed_n_snp, a->bed_n_ref);
+        if (rc != DBSLMM_B200_OK) return rc;
+        return fit_impl(h, a, false);
+    }
+    const int32_t pitch = (a->bed_n_ref + 3) / 4;
+    CU_TRY(h, h->bed.ensure((size_t)a->bed_n_snp * pitch + 64));
+    h->n_snp = a->bed_n_snp;
+    h->n_ref = a->bed_n_ref;
+    h->pitch = pitch;
+    h->n_pad = (a->bed_n_ref + 127) / 128 * 128;
+    h->stats_valid = false;
+    h->plan.valid = false;
+    int rc = fit_impl(h, a, true);
+    if (rc == kRetryResident) rc = fit_impl(h, a, false);       // the panel is resident by now; statistics are computed on demand
+    return rc;
 }
 
 int dbslmm_b200_score(dbslmm_b200_handle* h, const uint8_t* bed_val, int64_t n_snp_val, int32_t n_val,

@@ -222,10 +222,11 @@ gram_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs a) {
 //   warp 0: TMA producer   warp 1: TMEM alloc + MMA issuer   warps 2-9: epilogue
 //   (TMEM lane quarter = warp % 4, column half = (warp - 2) / 4)
 // ------------------------------------------------------------------------------------------
-static constexpr int kPStages = 5;
 static constexpr int kPThreads = 320;
-static constexpr int kPSmem = kPStages * 2 * kTileBytes + 1024;
+template <int kPStages>
+struct PCfg { static constexpr int kSmem = kPStages * 2 * kTileBytes + 1024; };
 
+template <int kPStages>
 __global__ void __launch_bounds__(kPThreads, 1)
 gram_persistent_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs a) {
     extern __shared__ uint8_t smem_raw[];
@@ -358,12 +359,18 @@ cudaError_t launch_gram(const CUtensorMap& tmap, const GramArgs& a, bool missing
     if (a.n_tiles == 0) return cudaSuccess;
     cudaError_t e;
     if (!missing) {
-        e = cudaFuncSetAttribute(gram_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmem);
-        if (e != cudaSuccess) return e;
         int dev = 0, n_sm = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        gram_persistent_kernel<<<std::min(a.n_tiles, n_sm), kPThreads, kPSmem, st>>>(tmap, a);
+        if (a.light) {
+            e = cudaFuncSetAttribute(gram_persistent_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg<3>::kSmem);
+            if (e != cudaSuccess) return e;
+            gram_persistent_kernel<3><<<std::min(a.n_tiles, n_sm), kPThreads, PCfg<3>::kSmem, st>>>(tmap, a);
+        } else {
+            e = cudaFuncSetAttribute(gram_persistent_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg<5>::kSmem);
+            if (e != cudaSuccess) return e;
+            gram_persistent_kernel<5><<<std::min(a.n_tiles, n_sm), kPThreads, PCfg<5>::kSmem, st>>>(tmap, a);
+        }
     } else {
         e = cudaFuncSetAttribute(gram_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GramCfg<4>::kSmem);
         if (e != cudaSuccess) return e;
@@ -397,19 +404,20 @@ cudaError_t launch_gram_simt(const int8_t* codes, int32_t n_pad, int64_t row0, i
 // z-score row of every block matrix: row mp <- [z_s ; z_l ; 0...], rows mp+1..mp+7 <- 0.
 // Appending z as one more row makes the left-looking factorisation produce y = L^-1 z
 // in that row, i.e. the forward substitution comes for free (chol.cu).
-__global__ void fill_z_kernel(const BlockDesc* __restrict__ blocks, const double* __restrict__ z,
-                              double* __restrict__ sigma) {
-    const BlockDesc bd = blocks[blockIdx.x];
+__global__ void fill_z_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict__ list,
+                              const double* __restrict__ z, double* __restrict__ sigma) {
+    const BlockDesc bd = blocks[list ? list[blockIdx.x] : (int)blockIdx.x];
     double* base = sigma + bd.moff + (size_t)bd.mp * bd.ld;
     for (int t = threadIdx.x; t < 8 * bd.ld; t += blockDim.x) {
         const int r = t / bd.ld, c = t - r * bd.ld;
         base[t] = (r == 0 && c < bd.m) ? z[bd.goff + c] : 0.0;
     }
 }
-cudaError_t launch_fill_z(const BlockDesc* blocks, int32_t n_blocks, const double* z, double* sigma,
+// `list` (device, or nullptr = all blocks 0..n_blocks-1) selects the blocks.
+cudaError_t launch_fill_z(const BlockDesc* blocks, const int32_t* list, int32_t n_blocks, const double* z, double* sigma,
                           cudaStream_t st) {
     if (n_blocks == 0) return cudaSuccess;
-    fill_z_kernel<<<n_blocks, 256, 0, st>>>(blocks, z, sigma);
+    fill_z_kernel<<<n_blocks, 256, 0, st>>>(blocks, list, z, sigma);
     return cudaGetLastError();
 }
 

@@ -15,6 +15,7 @@ cudaError_t launch_decode_rows(const uint8_t* bed, int32_t n_ref, int32_t n_pad,
                                int8_t* codes, int32_t* rowN, int32_t* rowS, double* rowR, int n_sm,
                                cudaStream_t st);
 
+cudaError_t launch_rows_missing(const int32_t* rowN, int64_t n_rows, int32_t n_ref, int32_t* flag, cudaStream_t st);
 cudaError_t launch_block_missing(const BlockDesc* blocks, int32_t n_blocks, const uint32_t* row_src,
                                  const SnpStat* stats, int32_t n_ref, int32_t* flags, cudaStream_t st);
 
@@ -34,11 +35,12 @@ struct GramArgs {
     int32_t* intA;
     int32_t* intN;
     int32_t full;               // also write the upper triangle
+    int32_t light;              // persistent kernel with a 3-stage ring (97 KB: co-resident with a Cholesky panel CTA)
 };
 cudaError_t launch_gram(const CUtensorMap& tmap, const GramArgs& a, bool missing, cudaStream_t st);
 cudaError_t launch_gram_simt(const int8_t* codes, int32_t n_pad, int64_t row0, int32_t m, int32_t* q_out,
                              cudaStream_t st);
-cudaError_t launch_fill_z(const BlockDesc* blocks, int32_t n_blocks, const double* z, double* sigma,
+cudaError_t launch_fill_z(const BlockDesc* blocks, const int32_t* list, int32_t n_blocks, const double* z, double* sigma,
                           cudaStream_t st);
 
 // chol.cu

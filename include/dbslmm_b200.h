@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DBSLMM_B200_ABI_VERSION 2
+#define DBSLMM_B200_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define DBSLMM_B200_API __attribute__((visibility("default")))
@@ -100,6 +100,14 @@ typedef struct dbslmm_b200_fit_args {
     const int32_t* s_tpos;          /* [s_off[n_blocks]] test .bed row of every small SNP                      */
     const int32_t* l_tpos;          /* [l_off[n_blocks]] or NULL                                               */
     double*  variance_out;          /* [n_folds][n_blocks][n_test], n_test = #selected individuals             */
+    /* ---- optional: the reference panel travels WITH the fit, as DBSLMMFIT::est receives it (its bed_str argument,
+     * scr/dbslmmfit.hpp:38-67, read row by row inside calcBlock).  bed != NULL replaces a prior load_bed: the SNP-major
+     * payload (after the 3 magic bytes; pinned host memory for full PCIe speed) is uploaded INSIDE the call, the rows of
+     * the biggest blocks first, and every batch of blocks is decoded and factored as soon as its rows have landed, so
+     * the upload overlaps the fit.  The panel stays resident afterwards (later calls may pass bed = NULL).          */
+    const uint8_t* bed;             /* or NULL: use the panel loaded by dbslmm_b200_load_bed                   */
+    int64_t  bed_n_snp;
+    int32_t  bed_n_ref;
 } dbslmm_b200_fit_args;
 
 #define DBSLMM_B200_FLAG_KEEP_INT_GRAM 1  /* also keep raw int32 Gram planes for dbslmm_b200_get_block_gram */

@@ -1,0 +1,101 @@
+"""Streaming fit: the reference panel travels with dbslmm_b200_fit (fit_args.bed), as DBSLMMFIT::est receives its
+bed_str (reference scr/dbslmmfit.hpp:38-67); the upload is cut into batches and overlaps the fit.  Results must be
+IDENTICAL (same kernels, same arithmetic, only a different schedule and device layout) to load_bed + fit."""
+import numpy as np
+import pytest
+
+from dbslmm_b200 import _abi, synth
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def relmax(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def csr_of(w):
+    return (w["s_off"], w["s_pos"], w["s_z"], w["l_off"], w["l_pos"], w["l_z"])
+
+
+@pytest.mark.parametrize("sizes,n_ref", [([300, 0, 1, 7, 8, 63, 64, 65, 127, 128, 129, 200], 400),
+                                         ([90, 33], 125 * 4 - 3),
+                                         ([520, 40, 1100, 70, 2100, 600, 9, 700], 500)])
+def test_streaming_equals_resident_and_oracle(engine, sizes, n_ref):
+    w = synth.make_workload(4321 + len(sizes), sizes, n_ref, missing_rate=0.0, frac_large=0.02)
+    csr = csr_of(w)
+    kw = dict(sigma_s=[2e-4], n_obs=20_000)
+    rs = engine.fit(*csr, bed=w["bed"], n_ref=n_ref, **kw)                 # panel uploaded inside the call
+    assert rs["n_bad"] == 0
+    engine.load_bed(w["bed"], n_ref)
+    rr = engine.fit(*csr, **kw)
+    assert np.array_equal(rs["beta_s"], rr["beta_s"]) and np.array_equal(rs["beta_l"], rr["beta_l"])
+    bs, bl, _, _ = O.est(w["bed"], n_ref, 20_000, 2e-4, *csr, threads=4, mode=O.MODE_EXACT)
+    assert relmax(rs["beta_s"][0], bs) <= 1e-10
+    if bl.size:
+        assert relmax(rs["beta_l"][0], bl) <= 1e-10
+    # the panel stayed resident and its statistics are computed on demand
+    maf, nn = engine.snp_stats()
+    assert np.array_equal(nn, (w["G"] >= 0).sum(axis=1))
+    r3 = engine.fit(*csr, **kw)
+    assert np.array_equal(r3["beta_s"], rr["beta_s"])
+
+
+def test_streaming_many_blocks_sub_batches(engine):
+    """A genome-like bulk (>= 256 small/medium blocks, >= 100k SNPs) is cut into four region batches (upload units)."""
+    rng = np.random.default_rng(11)
+    sizes = [int(x) for x in rng.integers(300, 440, size=290)] + [600, 1300, 2100]
+    w = synth.make_workload(99, sizes, 400, missing_rate=0.0, frac_large=0.01)
+    csr = csr_of(w)
+    kw = dict(sigma_s=[1e-4, 3e-4], n_obs=50_000)
+    rs = engine.fit(*csr, bed=w["bed"], n_ref=400, **kw)
+    assert rs["n_bad"] == 0
+    engine.load_bed(w["bed"], 400)
+    rr = engine.fit(*csr, **kw)
+    # (sub-batches may pick another split-K factor than the whole class: same arithmetic, different summation order)
+    assert relmax(rs["beta_s"], rr["beta_s"]) <= 1e-12 and relmax(rs["beta_l"], rr["beta_l"]) <= 1e-12
+
+
+def test_streaming_subset_of_rows_and_unordered_blocks(engine):
+    """Blocks use a subset of the panel rows, not in .bed order: unused rows are uploaded last, the panel ends up whole."""
+    w = synth.make_workload(17, [150, 260, 90, 400], 400, missing_rate=0.0, frac_large=0.0)
+    n_snp = w["bed"].shape[0]
+    keep = np.ones(n_snp, bool)
+    keep[::7] = False                                        # drop every 7th SNP from the fit
+    s_off = [0]
+    pos = []
+    for b in (2, 0, 3, 1):                                   # block order != .bed order
+        p = w["s_pos"][w["s_off"][b]:w["s_off"][b + 1]]
+        p = p[keep[p]]
+        pos.append(p)
+        s_off.append(s_off[-1] + p.size)
+    s_off = np.array(s_off, np.int32)
+    s_pos = np.concatenate(pos).astype(np.int32)
+    z = np.random.default_rng(5).standard_normal(s_pos.size)
+    rs = engine.fit(s_off, s_pos, z, sigma_s=[1e-4], n_obs=9000, bed=w["bed"], n_ref=400)
+    bs, _, _, _ = O.est(w["bed"], 400, 9000, 1e-4, s_off, s_pos, z, threads=4, mode=O.MODE_EXACT)
+    assert rs["n_bad"] == 0 and relmax(rs["beta_s"][0], bs) <= 1e-10
+    maf, _ = engine.snp_stats()
+    assert np.abs(maf - O.snp_maf(w["bed"], n_snp, 400)).max() <= 1e-15
+
+
+def test_streaming_with_missing_calls_falls_back(engine):
+    """The streaming plan assumes no missing calls; when the decoder meets one the fit is repeated on the resident copy."""
+    w = synth.make_workload(23, [150, 70, 5, 130, 0, 257], 403, missing_rate=0.02, frac_large=0.02)
+    csr = csr_of(w)
+    rs = engine.fit(*csr, sigma_s=[1e-4], n_obs=10_000, bed=w["bed"], n_ref=403)
+    bs, bl, _, _ = O.est(w["bed"], 403, 10_000, 1e-4, *csr, threads=4, mode=O.MODE_EXACT)
+    assert rs["n_bad"] == 0 and relmax(rs["beta_s"][0], bs) <= 1e-10 and relmax(rs["beta_l"][0], bl) <= 1e-10
+
+
+def test_streaming_scattered_rows_use_plain_upload(engine):
+    """Every block draws its SNPs from the whole panel: covering ranges would move ~n_blocks x the panel, so the call
+    degrades to a plain upload followed by the resident fit."""
+    w = synth.make_workload(31, [400, 400, 400], 400, missing_rate=0.0, frac_large=0.0)
+    n_snp = w["bed"].shape[0]
+    perm = np.random.default_rng(2).permutation(n_snp).astype(np.int32)
+    s_off = np.array([0, 400, 800, 1200], np.int32)
+    z = np.random.default_rng(3).standard_normal(n_snp)
+    rs = engine.fit(s_off, perm, z, sigma_s=[1e-4], n_obs=9000, bed=w["bed"], n_ref=400)
+    bs, _, _, _ = O.est(w["bed"], 400, 9000, 1e-4, s_off, perm, z, threads=4, mode=O.MODE_EXACT)
+    assert relmax(rs["beta_s"][0], bs) <= 1e-10
