@@ -135,6 +135,9 @@ __device__ __forceinline__ void gemm_nt_core(const double* __restrict__ Pg, cons
 //   W = L^-1 is then assembled block-wise from the four 16x16 inverses.
 // Tiles narrower than 64 (last panel) are padded with identity, so the code path is uniform.
 // ------------------------------------------------------------------------------------------
+#ifndef DIAG_STAMP
+#define DIAG_STAMP(n)               // probe hook (tools/diag_probe.cu records clock64() here)
+#endif
 static constexpr int DT = NB + 1;   // odd stride: conflict-free row and column walks in FP64
 static constexpr int SMEM_DIAG = (2 * NB * DT + 3 * 16 * 17) * 8;
 
@@ -150,6 +153,7 @@ __device__ __forceinline__ void diag_body(const BlockDesc& bd, int blk, int k, c
     double* Lb = Lbuf + bd.moff;
     const double* src = (k == 0 ? sigma : Lbuf) + bd.moff;     // step 0 reads Sigma, later steps the accumulated tile
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    DIAG_STAMP(0);
 
     {
         // all 16 loads of a thread are issued back to back (independent), then consumed
@@ -177,6 +181,7 @@ __device__ __forceinline__ void diag_body(const BlockDesc& bd, int blk, int k, c
     __syncthreads();
 
     bool bad = false;
+    DIAG_STAMP(1);
 #pragma unroll 1
     for (int jb = 0; jb < 4; ++jb) {
         const int o = 16 * jb;
@@ -209,6 +214,7 @@ __device__ __forceinline__ void diag_body(const BlockDesc& bd, int blk, int k, c
                 for (int c = 0; c < 16; ++c) T[(o + r) * DT + o + c] = (c <= r) ? row[c] : 0.0;
             }
             __syncwarp();
+            DIAG_STAMP(2 + 5 * jb);
             // inverse: lane c owns column c of W16; w[i] = -(sum_{k<i} l_ik w[k]) / l_ii
             const int c = r;
             double w[16];
@@ -232,6 +238,7 @@ __device__ __forceinline__ void diag_body(const BlockDesc& bd, int blk, int k, c
             }
         }
         __syncthreads();
+        DIAG_STAMP(3 + 5 * jb);
         if (jb == 3) break;
         // ---- sub-panel below: X = T[rows, o:o+16] * W16^T  (rows o+16 .. 63)
         const int nrem = 48 - o;
@@ -254,9 +261,11 @@ __device__ __forceinline__ void diag_body(const BlockDesc& bd, int blk, int k, c
             if (oi < nrem * 16) T[(o + 16 + (oi >> 4)) * DT + o + (oi & 15)] = x[u];
         }
         __syncthreads();
+        DIAG_STAMP(4 + 5 * jb);
         // ---- trailing update of the remaining lower triangle
+        const uint32_t inv_nrem = (1u << 20) / (uint32_t)nrem + 1u;       // oi / nrem == (oi * inv_nrem) >> 20 for oi < 2304
         for (int oi = tid; oi < nrem * nrem; oi += CHOL_THREADS) {
-            const int i = oi / nrem, c = oi - i * nrem;
+            const int i = (int)(((uint32_t)oi * inv_nrem) >> 20), c = oi - i * nrem;
             if (c <= i) {
                 const double* xi = T + (o + 16 + i) * DT + o;
                 const double* xc = T + (o + 16 + c) * DT + o;
@@ -267,6 +276,7 @@ __device__ __forceinline__ void diag_body(const BlockDesc& bd, int blk, int k, c
             }
         }
         __syncthreads();
+        DIAG_STAMP(5 + 5 * jb);
     }
     if (warp == 0 && __any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&status[blk], 1);
     // ---- off-diagonal 16x16 blocks of W:  W_ij = -W_ii * sum_{kb=j}^{i-1} L_i,kb W_kb,j, level by level in
@@ -292,10 +302,11 @@ __device__ __forceinline__ void diag_body(const BlockDesc& bd, int blk, int k, c
             __syncthreads();
         }
     }
+    DIAG_STAMP(22);
     // ---- write back: lower = L_kk, strict upper = W_kk^T (used by the back substitution) ...
-    for (int idx = tid; idx < wk * wk; idx += CHOL_THREADS) {
-        const int a = idx / wk, b = idx - a * wk;
-        Lb[(size_t)(pc0 + a) * ld + pc0 + b] = (b <= a) ? T[a * DT + b] : Wf[b * DT + a];
+    for (int idx = tid; idx < NB * NB; idx += CHOL_THREADS) {
+        const int a = idx >> 6, b = idx & 63;
+        if (a < wk && b < wk) Lb[(size_t)(pc0 + a) * ld + pc0 + b] = (b <= a) ? T[a * DT + b] : Wf[b * DT + a];
     }
     // ... and W_kk as a dense 64x64 lower-triangular tile for the panel kernel of this step, which
     // streams it into shared memory with cp.async while its GEMM loop runs
@@ -304,6 +315,7 @@ __device__ __forceinline__ void diag_body(const BlockDesc& bd, int blk, int k, c
         const int a = idx >> 6, b = idx & 63;
         wb[idx] = (b <= a) ? Wf[a * DT + b] : 0.0;
     }
+    DIAG_STAMP(23);
 }
 
 __global__ void __launch_bounds__(CHOL_THREADS, 3)

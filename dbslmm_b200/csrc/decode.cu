@@ -17,6 +17,7 @@
 namespace dbslmm {
 
 static constexpr int kWarpsPerCta = 8;
+static constexpr int kDecRing = 4;      // staged rows per warp in the decoder
 
 struct RowStage {
     // returns byte offset of the row inside the staged buffer
@@ -104,19 +105,21 @@ snp_stats_kernel(const uint8_t* __restrict__ bed, int64_t n_snp, int32_t n_ref, 
     }
 }
 
-// four 2-bit codes of byte x -> allele-count bytes (MASK = false) or call-mask bytes (MASK = true)
+// sixteen 2-bit codes of word w -> sixteen allele-count bytes (MASK = false: 0->2, 2->1, 1/3->0) or call-mask bytes
+// (MASK = true: 0 only for code 1 = missing).  Each 2-bit code is spread into its own nibble (three shift+LOP3
+// steps per 8 codes) and used as a PRMT byte selector into a 4-entry table held in one register.
 template <bool MASK>
-__device__ __forceinline__ uint32_t expand4(uint32_t x) {
-    const uint32_t t = (x | (x << 6) | (x << 12) | (x << 18)) & 0x03030303u;
-    const uint32_t b0 = t & 0x01010101u, b1 = (t >> 1) & 0x01010101u;
-    const uint32_t nb0 = b0 ^ 0x01010101u;
-    if (MASK) return nb0 | b1;              // 0 only for code 1 (missing)
-    return (nb0 << 1) - (nb0 & b1);         // (1-b0)*(2-b1): 0->2, 2->1, 1/3->0
+__device__ __forceinline__ uint2 expand8(uint32_t h) {                 // h: 8 codes in the low 16 bits
+    constexpr uint32_t lut = MASK ? 0x01010001u : 0x00010002u;         // byte c = value of code c
+    uint32_t t = (h | (h << 8)) & 0x00FF00FFu;
+    t = (t | (t << 4)) & 0x0F0F0F0Fu;
+    t = (t | (t << 2)) & 0x33333333u;
+    return make_uint2(__byte_perm(lut, 0u, t), __byte_perm(lut, 0u, t >> 16));
 }
 template <bool MASK>
 __device__ __forceinline__ uint4 expand16(uint32_t w) {
-    return make_uint4(expand4<MASK>(w & 0xFFu), expand4<MASK>((w >> 8) & 0xFFu), expand4<MASK>((w >> 16) & 0xFFu),
-                      expand4<MASK>(w >> 24));
+    const uint2 lo = expand8<MASK>(w & 0xFFFFu), hi = expand8<MASK>(w >> 16);
+    return make_uint4(lo.x, lo.y, hi.x, hi.y);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -132,11 +135,13 @@ decode_rows_kernel(const uint8_t* __restrict__ bed, int32_t n_ref, int32_t pitch
                    int8_t* __restrict__ codes, int32_t* __restrict__ rowN, int32_t* __restrict__ rowS,
                    double* __restrict__ rowR) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bars[kWarpsPerCta][2];
+    __shared__ __align__(8) uint64_t bars[kWarpsPerCta][kDecRing];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t* buf0 = smem + (size_t)warp * 2 * buf_bytes;
-    uint8_t* bufs[2] = {buf0, buf0 + buf_bytes};
-    if (lane == 0) { mbar_init(&bars[warp][0], 1); mbar_init(&bars[warp][1], 1); }
+    uint8_t* buf0 = smem + (size_t)warp * kDecRing * buf_bytes;
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < kDecRing; ++i) mbar_init(&bars[warp][i], 1);
+    }
     mbar_fence_init();
     __syncwarp();
 
@@ -144,29 +149,45 @@ decode_rows_kernel(const uint8_t* __restrict__ bed, int32_t n_ref, int32_t pitch
     const int64_t stride = (int64_t)gridDim.x * kWarpsPerCta;
     const int nwords = (pitch + 3) >> 2;     // input words holding real samples
     const int nout = n_pad >> 4;             // 16-byte output chunks per row
-    uint32_t phase[2] = {0, 0};
-    uint32_t off[2] = {0, 0};
-    int cur = 0;
+    // ring of kDecRing staged rows per warp: kDecRing - 1 TMA row copies in flight while one row is expanded
+    uint32_t phase = 0;                      // bit i = parity of buffer i
+    uint32_t off[kDecRing];
     int64_t row = gw;
-    if (row < n_rows)
-        off[0] = RowStage::issue(bed, (int64_t)(row_src[row] & 0x7FFFFFFFu), pitch, bufs[0], &bars[warp][0], lane);
+#pragma unroll
+    for (int i = 0; i < kDecRing - 1; ++i) {
+        const int64_t r = row + (int64_t)i * stride;
+        off[i] = 0;
+        if (r < n_rows)
+            off[i] = RowStage::issue(bed, (int64_t)(row_src[r] & 0x7FFFFFFFu), pitch, buf0 + i * buf_bytes, &bars[warp][i], lane);
+    }
+    off[kDecRing - 1] = 0;
+    int cur = 0;
     for (; row < n_rows; row += stride) {
-        const int64_t nxt = row + stride;
-        if (nxt < n_rows)
-            off[cur ^ 1] = RowStage::issue(bed, (int64_t)(row_src[nxt] & 0x7FFFFFFFu), pitch, bufs[cur ^ 1],
-                                           &bars[warp][cur ^ 1], lane);
+        {
+            const int64_t nxt = row + (int64_t)(kDecRing - 1) * stride;
+            const int nb = (cur + kDecRing - 1) % kDecRing;
+            if (nxt < n_rows) {
+                const uint32_t o = RowStage::issue(bed, (int64_t)(row_src[nxt] & 0x7FFFFFFFu), pitch, buf0 + nb * buf_bytes,
+                                                   &bars[warp][nb], lane);
+#pragma unroll
+                for (int i = 0; i < kDecRing; ++i) if (i == nb) off[i] = o;
+            }
+        }
         const uint32_t src = row_src[row];
         const bool mask_plane = (src >> 31) != 0;
-        mbar_wait(&bars[warp][cur], phase[cur]);
-        phase[cur] ^= 1;
-        const uint32_t* w32 = reinterpret_cast<const uint32_t*>(bufs[cur]);
+        mbar_wait(&bars[warp][cur], (phase >> cur) & 1u);
+        phase ^= 1u << cur;
+        uint32_t off_cur = 0;
+#pragma unroll
+        for (int i = 0; i < kDecRing; ++i) if (i == cur) off_cur = off[i];
+        const uint32_t* w32 = reinterpret_cast<const uint32_t*>(buf0 + cur * buf_bytes);
         uint4* out = reinterpret_cast<uint4*>(codes + (size_t)row * n_pad);
         const int nfull = n_ref >> 4;             // words whose 16 samples are all real
         int c0 = 0, c1 = 0, c2 = 0;
         for (int i = lane; i < nout; i += 32) {
             uint4 o = make_uint4(0u, 0u, 0u, 0u);
             if (i < nwords) {
-                uint32_t w = row_word(w32, off[cur], i);
+                uint32_t w = row_word(w32, off_cur, i);
                 uint32_t ws = w;                          // for the counts: samples past n_ref -> code 3 (counts nothing)
                 if (i >= nfull) {
                     const uint32_t vb = valid_bits(n_ref, i);
@@ -207,7 +228,7 @@ decode_rows_kernel(const uint8_t* __restrict__ bed, int32_t n_ref, int32_t pitch
             }
         }
         __syncwarp();
-        cur ^= 1;
+        cur = (cur + 1 == kDecRing) ? 0 : cur + 1;
     }
 }
 
@@ -278,7 +299,7 @@ cudaError_t launch_decode_rows(const uint8_t* bed, int32_t n_ref, int32_t n_pad,
     if (n_rows == 0) return cudaSuccess;
     const int32_t pitch = (n_ref + 3) / 4;
     const int buf = stage_bytes(pitch);
-    const size_t smem = (size_t)kWarpsPerCta * 2 * buf;
+    const size_t smem = (size_t)kWarpsPerCta * kDecRing * buf;
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(decode_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
