@@ -149,37 +149,55 @@ decode_rows_kernel(const uint8_t* __restrict__ bed, int32_t n_ref, int32_t pitch
     const int64_t stride = (int64_t)gridDim.x * kWarpsPerCta;
     const int nwords = (pitch + 3) >> 2;     // input words holding real samples
     const int nout = n_pad >> 4;             // 16-byte output chunks per row
-    // ring of kDecRing staged rows per warp: kDecRing - 1 TMA row copies in flight while one row is expanded
+    // ring of kDecRing staged rows per warp: kDecRing - 1 TMA row copies in flight while one row is expanded.
+    // Per-row metadata never stalls the loop: the source index of the row staged NEXT iteration is loaded one
+    // iteration ahead, the ring remembers the source of every staged row, and lane 0 fetches row_g / the statistics
+    // before it waits for the staged bytes.
     uint32_t phase = 0;                      // bit i = parity of buffer i
-    uint32_t off[kDecRing];
+    uint32_t off[kDecRing], srcs[kDecRing];
     int64_t row = gw;
+#pragma unroll
+    for (int i = 0; i < kDecRing; ++i) { off[i] = 0; srcs[i] = 0; }
 #pragma unroll
     for (int i = 0; i < kDecRing - 1; ++i) {
         const int64_t r = row + (int64_t)i * stride;
-        off[i] = 0;
-        if (r < n_rows)
-            off[i] = RowStage::issue(bed, (int64_t)(row_src[r] & 0x7FFFFFFFu), pitch, buf0 + i * buf_bytes, &bars[warp][i], lane);
+        if (r < n_rows) {
+            srcs[i] = row_src[r];
+            off[i] = RowStage::issue(bed, (int64_t)(srcs[i] & 0x7FFFFFFFu), pitch, buf0 + i * buf_bytes, &bars[warp][i], lane);
+        }
     }
-    off[kDecRing - 1] = 0;
+    uint32_t pre = 0;                        // row_src of the row that will be staged in the current iteration
+    {
+        const int64_t r = row + (int64_t)(kDecRing - 1) * stride;
+        if (r < n_rows) pre = row_src[r];
+    }
     int cur = 0;
     for (; row < n_rows; row += stride) {
         {
             const int64_t nxt = row + (int64_t)(kDecRing - 1) * stride;
             const int nb = (cur + kDecRing - 1) % kDecRing;
+            const uint32_t issue_src = pre;
+            const int64_t nxt2 = nxt + stride;
+            if (nxt2 < n_rows) pre = row_src[nxt2];          // consumed next iteration
             if (nxt < n_rows) {
-                const uint32_t o = RowStage::issue(bed, (int64_t)(row_src[nxt] & 0x7FFFFFFFu), pitch, buf0 + nb * buf_bytes,
+                const uint32_t o = RowStage::issue(bed, (int64_t)(issue_src & 0x7FFFFFFFu), pitch, buf0 + nb * buf_bytes,
                                                    &bars[warp][nb], lane);
 #pragma unroll
-                for (int i = 0; i < kDecRing; ++i) if (i == nb) off[i] = o;
+                for (int i = 0; i < kDecRing; ++i) if (i == nb) { off[i] = o; srcs[i] = issue_src; }
             }
         }
-        const uint32_t src = row_src[row];
+        uint32_t off_cur = 0, src = 0;
+#pragma unroll
+        for (int i = 0; i < kDecRing; ++i) if (i == cur) { off_cur = off[i]; src = srcs[i]; }
         const bool mask_plane = (src >> 31) != 0;
+        int32_t g_row = -1;
+        SnpStat s_row = {0, 0, 0, 0};
+        if (lane == 0) {
+            g_row = row_g[row];
+            if (!OWN && g_row >= 0) s_row = stats[src & 0x7FFFFFFFu];
+        }
         mbar_wait(&bars[warp][cur], (phase >> cur) & 1u);
         phase ^= 1u << cur;
-        uint32_t off_cur = 0;
-#pragma unroll
-        for (int i = 0; i < kDecRing; ++i) if (i == cur) off_cur = off[i];
         const uint32_t* w32 = reinterpret_cast<const uint32_t*>(buf0 + cur * buf_bytes);
         uint4* out = reinterpret_cast<uint4*>(codes + (size_t)row * n_pad);
         const int nfull = n_ref >> 4;             // words whose 16 samples are all real
@@ -213,11 +231,10 @@ decode_rows_kernel(const uint8_t* __restrict__ bed, int32_t n_ref, int32_t pitch
             }
         }
         if (lane == 0) {
-            const int32_t g = row_g[row];
+            const int32_t g = g_row;
             if (g >= 0) {
-                SnpStat s;
+                SnpStat s = s_row;
                 if (OWN) { s.n_nonmiss = n_ref - c1; s.sum = 2 * c0 + c2; s.sumsq = 4 * c0 + c2; s.pad = 0; }
-                else s = stats[src & 0x7FFFFFFFu];
                 const double ni = (double)s.n_nonmiss;
                 // d = n_i * sum g^2 - (sum g)^2  (exact integer), r = sqrt(tau (n-1) / (n n_i d))
                 const double d = ni * (double)s.sumsq - (double)s.sum * (double)s.sum;

@@ -226,11 +226,14 @@ static constexpr int kPThreads = 320;
 template <int kPStages>
 struct PCfg { static constexpr int kSmem = kPStages * 2 * kTileBytes + 1024; };
 
+// (min-blocks 2 only caps the registers at 102 per thread: with the 3-stage ring a Gram CTA then fits next to a
+//  Cholesky panel CTA -- 32 K registers, 110 KB shared memory -- during a streaming fit)
 template <int kPStages>
-__global__ void __launch_bounds__(kPThreads, 1)
+__global__ void __launch_bounds__(kPThreads, 2)
 gram_persistent_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs a) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[kPStages], empty_bar[kPStages], acc_full[2], acc_empty[2];
+    __shared__ __align__(16) double2 row_consts[8][64];          // per epilogue warp: {S_i, r_i} of its 64 rows
     __shared__ uint32_t tmem_slot;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -297,14 +300,27 @@ gram_persistent_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs 
     } else {
         const int q = warp & 3, half = (warp - 2) >> 2;
         const double dn = (double)a.n_ref;
+        double2* rc = row_consts[warp - 2];                      // this warp's 64 rows: {S_i, r_i}
         uint32_t lt = 0;
         for (int tile_i = blockIdx.x; tile_i < a.n_tiles; tile_i += gridDim.x, ++lt) {
             const GramTile tile = a.tiles[tile_i];
             const BlockDesc bd = a.blocks[tile.blk];
             const uint32_t as = lt & 1u;
             const int jl = tile.tj * kTile + q * 32 + lane;
+            const int i0 = tile.ti * kTile + half * 64;          // first row of this warp's half
             double Sj = 0.0, rj = 0.0;
             if (jl < bd.m) { Sj = (double)a.rowS[bd.goff + jl]; rj = a.rowR[bd.goff + jl] * dn; }
+            // per-row constants go through shared memory (one broadcast LDS.128 per row instead of four shuffles);
+            // their global loads overlap the wait for the accumulator
+            __syncwarp();
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int il = i0 + 32 * hh + lane;
+                double2 c = make_double2(0.0, 0.0);
+                if (il < bd.m) c = make_double2((double)a.rowS[bd.goff + il], a.rowR[bd.goff + il]);
+                rc[32 * hh + lane] = c;
+            }
+            __syncwarp();
             mbar_wait(&acc_full[as], (lt >> 1) & 1u);
             tc_fence_after();
             const uint32_t tlane = tmem_base + as * kTile + ((uint32_t)(q * 32) << 16);
@@ -316,37 +332,43 @@ gram_persistent_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs 
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[as]);               // accumulator copied out: MMA may reuse it
+            if (i0 >= bd.mp) continue;                                // warp-uniform: nothing of this half is inside the block
+            const size_t ld = (size_t)bd.ld;
+            if (tile.ti > tile.tj && i0 + 64 <= bd.m && !a.full && a.intQ == nullptr) {
+                // interior half tile (every entry below the diagonal, every row a real SNP): straight-line code
+                double* p = sig + (size_t)i0 * ld + jl;
 #pragma unroll
-            for (int ch = 0; ch < 2; ++ch) {
-                const int ibase = tile.ti * kTile + half * 64 + ch * 32;
-                if (ibase >= bd.mp) break;
-                double Si_l = 0.0, ri_l = 0.0;
-                {
-                    const int il = ibase + lane;
-                    if (il < bd.m) { Si_l = (double)a.rowS[bd.goff + il]; ri_l = a.rowR[bd.goff + il]; }
+                for (int r = 0; r < 64; ++r) {
+                    const double2 c = rc[r];
+                    // n Q - S_i S_j is an exact integer below 2^53: one FMA, no rounding
+                    const double t = fma(-c.x, Sj, dn * (double)(int32_t)v[r >> 5][r & 31]);
+                    p[(size_t)r * ld] = t * c.y * rj;
                 }
+                continue;
+            }
+            // general half tile (diagonal, last tile row, debug planes): same arithmetic, predicated stores
+            {
+                const int nreal = bd.m - i0;                           // rows r < nreal are real SNPs
+                double* p = sig + (size_t)i0 * ld + jl;
 #pragma unroll
-                for (int r = 0; r < 32; ++r) {
-                    const int il = ibase + r;
-                    const double Si = __shfl_sync(0xffffffffu, Si_l, r);
-                    const double ri = __shfl_sync(0xffffffffu, ri_l, r);
-                    if (il >= bd.mp || jl > il) continue;
-                    double val;
-                    if (il < bd.m) {
-                        // n Q - S_i S_j is an exact integer below 2^53: one FMA, no rounding
-                        const double t = fma(-Si, Sj, dn * (double)(int32_t)v[ch][r]);
-                        val = t * ri * rj;
-                        if (il == jl) val += a.one_minus_tau;
-                    } else {
-                        val = (il == jl) ? 1.0 : 0.0;
-                    }
-                    sig[(size_t)il * bd.ld + jl] = val;
-                    if (a.full && jl < il) sig[(size_t)jl * bd.ld + il] = val;
-                    if (a.intQ != nullptr && il < bd.m) {
-                        a.intQ[(size_t)bd.moff + (size_t)il * bd.ld + jl] = (int32_t)v[ch][r];
-                        a.intQ[(size_t)bd.moff + (size_t)jl * bd.ld + il] = (int32_t)v[ch][r];
+                for (int r = 0; r < 64; ++r) {
+                    const int il = i0 + r;
+                    const double2 c = rc[r];
+                    const double t = fma(-c.x, Sj, dn * (double)(int32_t)v[r >> 5][r & 31]);
+                    double val = t * c.y * rj;
+                    if (il == jl) val += a.one_minus_tau;
+                    if (r < nreal && jl <= il) {
+                        p[(size_t)r * ld] = val;
+                        if (a.full && jl < il) sig[(size_t)jl * ld + il] = val;
+                        if (a.intQ != nullptr) {
+                            a.intQ[(size_t)bd.moff + (size_t)il * ld + jl] = (int32_t)v[r >> 5][r & 31];
+                            a.intQ[(size_t)bd.moff + (size_t)jl * ld + il] = (int32_t)v[r >> 5][r & 31];
+                        }
                     }
                 }
+                // identity padding rows m .. mp-1 (at most 7 per block)
+                for (int il = max(bd.m, i0); il < min(bd.mp, i0 + 64); ++il)
+                    if (jl <= il) sig[(size_t)il * ld + jl] = (il == jl) ? 1.0 : 0.0;
             }
         }
     }
