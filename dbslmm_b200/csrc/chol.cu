@@ -129,24 +129,41 @@ __device__ __forceinline__ void gemm_nt_core(const double* __restrict__ Pg, cons
 
 // ------------------------------------------------------------------------------------------
 // Diagonal tile of panel k for every active block: factor + invert (no GEMM: the tile arrives
-// fully updated, see chol_panel_kernel's look-ahead SYRK).
-//   potrf: 4 sub-blocks of 16; each 16x16 diagonal sub-block is factored and inverted by ONE
-//   warp in registers (shuffles), the sub-panel below and the trailing part by all 8 warps.
-//   W = L^-1 is then assembled block-wise from the four 16x16 inverses.
+// fully updated, see chol_panel_kernel's look-ahead SYRK).  This is a latency chain (64 dependent
+// column eliminations), so everything that is not on the chain is moved off it:
+//   * warp 0 factors one 16x16 diagonal sub-block at a time in registers (shuffles);
+//   * the 16-column sub-panel below is solved by forward substitution, one row per thread
+//     (warps 2-4), while warp 1 inverts the 16x16 factor;
+//   * warp 0 then updates only the NEXT 16x16 diagonal sub-block and goes straight on with its
+//     factorisation, while warps 1-7 update the rest of the trailing matrix in its shadow;
+//   * W = L^-1 is assembled from the four 16x16 inverses by two levels of 2x2 block inversion.
 // Tiles narrower than 64 (last panel) are padded with identity, so the code path is uniform.
 // ------------------------------------------------------------------------------------------
 #ifndef DIAG_STAMP
 #define DIAG_STAMP(n)               // probe hook (tools/diag_probe.cu records clock64() here)
 #endif
 static constexpr int DT = NB + 1;   // odd stride: conflict-free row and column walks in FP64
-static constexpr int SMEM_DIAG = (2 * NB * DT + 3 * 16 * 17) * 8;
+static constexpr int DP = 33;       // stride of the 32x32 product scratch
+static constexpr int SMEM_DIAG = (2 * NB * DT + 32 * DP + NB) * 8;
+
+// One 8x8 output tile on the FP64 tensor pipe: C = scale * A[0:8, kb:ke] B[kb:ke, 0:8], A row-major (stride sa),
+// B row-major k x n (stride sb), all in shared memory; kb, ke multiples of 4.  Whole warp.
+__device__ __forceinline__ void mm_tile8(const double* A, int sa, const double* B, int sb, int kb, int ke, double* C, int sc,
+                                         double scale, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    double c0 = 0.0, c1 = 0.0;
+    for (int k0 = kb; k0 < ke; k0 += 4) dmma884(c0, c1, A[g * sa + k0 + t], B[(k0 + t) * sb + g]);
+    C[g * sc + 2 * t] = scale * c0;
+    C[g * sc + 2 * t + 1] = scale * c1;
+}
 
 __device__ __forceinline__ void diag_body(const BlockDesc& bd, int blk, int k, const double* __restrict__ sigma,
                                           double* __restrict__ Lbuf, double* __restrict__ wbuf, double ridge,
                                           int32_t* __restrict__ status, double* smem) {
     double* T = smem;                        // [64][DT] tile, becomes L (lower)
     double* Wf = T + NB * DT;                // [64][DT] W = L^-1 (lower)
-    double* tmp = Wf + NB * DT;              // [16][17]
+    double* Pm = Wf + NB * DT;               // [32][DP] product scratch of the W assembly
+    double* dinv_s = Pm + 32 * DP;           // [64] 1 / L_ii
     const int pc0 = k * NB;
     const int wk = min(NB, bd.mp - pc0);
     const int ld = bd.ld;
@@ -186,19 +203,18 @@ __device__ __forceinline__ void diag_body(const BlockDesc& bd, int blk, int k, c
     for (int jb = 0; jb < 4; ++jb) {
         const int o = 16 * jb;
         if (warp == 0) {
-            // ---- 16x16 potrf + inverse in registers; lane r (and r+16) holds row r
+            // ---- 16x16 potrf in registers; lane r (and r+16) holds row r
             const int r = lane & 15;
             double row[16];
 #pragma unroll
             for (int c = 0; c < 16; ++c) row[c] = T[(o + r) * DT + o + c];
-            double dinv[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 const double d = __shfl_sync(0xffffffffu, row[j], j);
                 if (!(d > 0.0)) bad = true;
                 const double inv = rsqrt(d);
                 const double sq = d * inv;
-                dinv[j] = inv;
+                if (lane == j) dinv_s[o + j] = inv;
                 double lrj = row[j] * inv;
                 if (r == j) lrj = sq;
                 if (r < j) lrj = 0.0;
@@ -213,10 +229,14 @@ __device__ __forceinline__ void diag_body(const BlockDesc& bd, int blk, int k, c
 #pragma unroll
                 for (int c = 0; c < 16; ++c) T[(o + r) * DT + o + c] = (c <= r) ? row[c] : 0.0;
             }
-            __syncwarp();
-            DIAG_STAMP(2 + 5 * jb);
-            // inverse: lane c owns column c of W16; w[i] = -(sum_{k<i} l_ik w[k]) / l_ii
-            const int c = r;
+        }
+        __syncthreads();                                   // [A] L16 and 1/diag are in shared memory
+        DIAG_STAMP(2 + 5 * jb);
+        const int nrem = 48 - o;                           // rows below this sub-block
+        if (warp == 1) {
+            // ---- inverse of the 16x16 factor (off the critical path): lane c owns column c of W16;
+            // w[i] = -(sum_{k<i} l_ik w[k]) / l_ii
+            const int c = lane & 15;
             double w[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
@@ -227,8 +247,9 @@ __device__ __forceinline__ void diag_body(const BlockDesc& bd, int blk, int k, c
                     acc1 += T[(o + i) * DT + o + kk + 1] * w[kk + 1];
                 }
                 if (i & 1) acc0 += T[(o + i) * DT + o + i - 1] * w[i - 1];
-                double wi = -(acc0 + acc1) * dinv[i];
-                if (i == c) wi = dinv[i];
+                const double di = dinv_s[o + i];
+                double wi = -(acc0 + acc1) * di;
+                if (i == c) wi = di;
                 if (i < c) wi = 0.0;
                 w[i] = wi;
             }
@@ -236,71 +257,91 @@ __device__ __forceinline__ void diag_body(const BlockDesc& bd, int blk, int k, c
 #pragma unroll
                 for (int i = 0; i < 16; ++i) Wf[(o + i) * DT + o + c] = w[i];
             }
+        } else if (warp >= 2 && tid - 64 < nrem) {
+            // ---- sub-panel below: one row per thread, X L16^T = T_sub by forward substitution
+            // (right-looking: each solved x_k is folded into the remaining entries at once, so the chain is
+            //  one multiply + one FMA per column)
+            const int i = o + 16 + (tid - 64);
+            double x[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) x[c] = T[i * DT + o + c];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                x[c] *= dinv_s[o + c];
+#pragma unroll
+                for (int c2 = c + 1; c2 < 16; ++c2) x[c2] -= x[c] * T[(o + c2) * DT + o + c];
+            }
+#pragma unroll
+            for (int c = 0; c < 16; ++c) T[i * DT + o + c] = x[c];
         }
-        __syncthreads();
+        __syncthreads();                                   // [B] sub-panel solved
         DIAG_STAMP(3 + 5 * jb);
         if (jb == 3) break;
-        // ---- sub-panel below: X = T[rows, o:o+16] * W16^T  (rows o+16 .. 63)
-        const int nrem = 48 - o;
-        double x[3];
+        // ---- next 16x16 diagonal sub-block first, one entry per thread; then warp 0 factors it while the other
+        // warps update the rest of the trailing matrix in its shadow (the next barrier [A] publishes that part)
+        if (tid >= 32 && tid < 32 + 136) {
+            // entry e of the packed lower triangle -> (i, c)
+            const int e = tid - 32;
+            int ri = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+            while ((ri + 1) * (ri + 2) / 2 <= e) ++ri;
+            while (ri * (ri + 1) / 2 > e) --ri;
+            const int ci = e - ri * (ri + 1) / 2;
+            const double* xi = T + (o + 16 + ri) * DT + o;
+            const double* xc = T + (o + 16 + ci) * DT + o;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
-        for (int u = 0; u < 3; ++u) {
-            const int oi = tid + u * CHOL_THREADS;
-            x[u] = 0.0;
-            if (oi < nrem * 16) {
-                const int i = o + 16 + (oi >> 4), c = oi & 15;
-                double a = 0.0;
-                for (int cp = 0; cp <= c; ++cp) a += T[i * DT + o + cp] * Wf[(o + c) * DT + o + cp];
-                x[u] = a;
+            for (int kk = 0; kk < 16; kk += 4) {
+                a0 += xi[kk] * xc[kk]; a1 += xi[kk + 1] * xc[kk + 1];
+                a2 += xi[kk + 2] * xc[kk + 2]; a3 += xi[kk + 3] * xc[kk + 3];
+            }
+            T[(o + 16 + ri) * DT + o + 16 + ci] -= (a0 + a1) + (a2 + a3);
+        }
+        __syncthreads();                                   // [C] next diagonal sub-block updated
+        if (warp != 0) {
+            const int h = 32 - o;                          // rows o+32.., columns o+16..row
+            for (int idx = tid - 32; idx < h * 64; idx += CHOL_THREADS - 32) {
+                const int i = o + 32 + (idx >> 6), c = o + 16 + (idx & 63);
+                if (c <= i) {
+                    const double* xi = T + i * DT + o;
+                    const double* xc = T + c * DT + o;
+                    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+                    for (int kk = 0; kk < 16; kk += 4) {
+                        a0 += xi[kk] * xc[kk]; a1 += xi[kk + 1] * xc[kk + 1];
+                        a2 += xi[kk + 2] * xc[kk + 2]; a3 += xi[kk + 3] * xc[kk + 3];
+                    }
+                    T[i * DT + c] -= (a0 + a1) + (a2 + a3);
+                }
             }
         }
-        __syncthreads();
-#pragma unroll
-        for (int u = 0; u < 3; ++u) {
-            const int oi = tid + u * CHOL_THREADS;
-            if (oi < nrem * 16) T[(o + 16 + (oi >> 4)) * DT + o + (oi & 15)] = x[u];
-        }
-        __syncthreads();
         DIAG_STAMP(4 + 5 * jb);
-        // ---- trailing update of the remaining lower triangle
-        const uint32_t inv_nrem = (1u << 20) / (uint32_t)nrem + 1u;       // oi / nrem == (oi * inv_nrem) >> 20 for oi < 2304
-        for (int oi = tid; oi < nrem * nrem; oi += CHOL_THREADS) {
-            const int i = (int)(((uint32_t)oi * inv_nrem) >> 20), c = oi - i * nrem;
-            if (c <= i) {
-                const double* xi = T + (o + 16 + i) * DT + o;
-                const double* xc = T + (o + 16 + c) * DT + o;
-                double a = 0.0;
-#pragma unroll
-                for (int kk = 0; kk < 16; ++kk) a += xi[kk] * xc[kk];
-                T[(o + 16 + i) * DT + o + 16 + c] -= a;
-            }
-        }
-        __syncthreads();
-        DIAG_STAMP(5 + 5 * jb);
     }
     if (warp == 0 && __any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&status[blk], 1);
-    // ---- off-diagonal 16x16 blocks of W:  W_ij = -W_ii * sum_{kb=j}^{i-1} L_i,kb W_kb,j, level by level in
-    // the block distance d = i - j (all blocks of a level at once; tmp holds up to three 16x16 products)
+    // ---- W = L^-1 from the four 16x16 inverses, two levels of [[A,0],[B,C]]^-1 = [[A^-1,0],[-C^-1 B A^-1, C^-1]];
+    // the small products run on the FP64 tensor pipe, one or two 8x8 output tiles per warp and stage
     {
-        const int r = tid >> 4, c = tid & 15;
-#pragma unroll 1
-        for (int d = 1; d < 4; ++d) {
-            const int nblk = 4 - d;
-            for (int q = 0; q < nblk; ++q) {
-                const int i = d + q, j = q;
-                double a = 0.0;
-                for (int kk = 16 * j; kk < 16 * i; ++kk) a += T[(16 * i + r) * DT + kk] * Wf[kk * DT + 16 * j + c];
-                tmp[q * 272 + r * 17 + c] = a;
-            }
-            __syncthreads();
-            for (int q = 0; q < nblk; ++q) {
-                const int i = d + q, j = q;
-                double wv = 0.0;
-                for (int kk = 0; kk <= r; ++kk) wv += Wf[(16 * i + r) * DT + 16 * i + kk] * tmp[q * 272 + kk * 17 + c];
-                Wf[(16 * i + r) * DT + 16 * j + c] = -wv;
-            }
-            __syncthreads();
+        // level 1: both 32x32 diagonal blocks at once (8 tiles = 8 warps).  P = B A^-1 (16x16 each), then W21 = -C^-1 P
+        const int half = warp >> 2, ob = 32 * half;
+        const int r0 = 8 * ((warp >> 1) & 1), c0 = 8 * (warp & 1);
+        // A^-1 is lower triangular: only k >= c0 contributes
+        mm_tile8(T + (ob + 16 + r0) * DT + ob, DT, Wf + ob * DT + ob + c0, DT, c0, 16, Pm + (16 * half + r0) * DP + c0, DP, 1.0, lane);
+        __syncthreads();
+        // C^-1 is lower triangular: only k <= r0 + 7 contributes
+        mm_tile8(Wf + (ob + 16 + r0) * DT + ob + 16, DT, Pm + (16 * half) * DP + c0, DP, 0, r0 + 8, Wf + (ob + 16 + r0) * DT + ob + c0, DT, -1.0, lane);
+        __syncthreads();
+        // level 2 (16 tiles, two per warp): P = L21 W11 (32x32), then W21 = -W22 P
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int tl = warp + 8 * u, R0 = 8 * (tl >> 2), C0 = 8 * (tl & 3);
+            mm_tile8(T + (32 + R0) * DT, DT, Wf + C0, DT, C0, 32, Pm + R0 * DP + C0, DP, 1.0, lane);
         }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int tl = warp + 8 * u, R0 = 8 * (tl >> 2), C0 = 8 * (tl & 3);
+            mm_tile8(Wf + (32 + R0) * DT + 32, DT, Pm + C0, DP, 0, R0 + 8, Wf + (32 + R0) * DT + C0, DT, -1.0, lane);
+        }
+        __syncthreads();
     }
     DIAG_STAMP(22);
     // ---- write back: lower = L_kk, strict upper = W_kk^T (used by the back substitution) ...

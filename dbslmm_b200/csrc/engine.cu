@@ -58,8 +58,8 @@ struct PinBuf {
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
-constexpr int kNumClasses = 4;                 // size classes of the Cholesky step loop (by #panels)
-constexpr int kClassMaxPanels[kNumClasses] = {8, 16, 32, 1 << 30};
+constexpr int kNumClasses = 4;                 // timing slots reported per size class (dbslmm_b200_timing.class_ms)
+constexpr int kBulkMaxPanels = 16;             // blocks up to 16 panels (m <= 1024) are "bulk": one-CTA back substitution
 
 struct StepList { int32_t diag_off, n_diag, panel_off, n_panel, group_base, n_groups, nsl; };
 
@@ -69,7 +69,8 @@ struct StepList { int32_t diag_off, n_diag, panel_off, n_panel, group_base, n_gr
 // batch's decode -> Gram -> factorisation starts as soon as ITS rows have crossed PCIe.
 constexpr int kMaxBatches = 8;
 struct Batch {
-    int cls = 0;                          // size class: selects the stream (priority) and the back-substitution kernel
+    int cls = 0;                          // size class (timing slot)
+    bool big = false;                     // some member has mp > 1024: cluster back substitution
     int32_t ord_off = 0, ord_n = 0;       // members = order[ord_off, ord_off + ord_n)
     int64_t crow0 = 0, crow1 = 0;         // code rows of the members (contiguous only in the streaming layout)
     int64_t grow0 = 0, grow1 = 0;         // SNP rows
@@ -114,6 +115,9 @@ struct dbslmm_b200_handle {
     std::string err;
     bool fuse_diag = true;               // panel step k also factors the diagonal tile of panel k+1 (one launch per step)
     bool stream_bed = true;              // fit_args.bed: overlap the panel upload with the fit (else upload, then fit)
+    // size classes of the Cholesky step loops, by #panels (upper bounds, ascending; the last class is unbounded).
+    // Each class (batch) has its own stream: the step loops interleave and fill each other's thin last steps.
+    std::vector<int> cls_bounds = {8, 16, 32};
     // reference panel
     DevBuf bed, stats;
     PinBuf h_stats;                      // per-SNP statistics, filled asynchronously by load_bed
@@ -171,7 +175,9 @@ int make_batches(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, 
     P.blocks.resize(nb);
     P.tot_s = a->s_off[nb];
     P.tot_l = a->l_off ? a->l_off[nb] : 0;
-    std::vector<int32_t> by_cls[kNumClasses];
+    const std::vector<int>& bounds = h->cls_bounds;
+    const int nc = (int)bounds.size() + 1;
+    std::vector<std::vector<int32_t>> by_cls((size_t)nc);
     for (int b = 0; b < nb; ++b) {
         const int ms = a->s_off[b + 1] - a->s_off[b];
         const int ml = a->l_off ? a->l_off[b + 1] - a->l_off[b] : 0;
@@ -183,7 +189,7 @@ int make_batches(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, 
         d.ld = d.mp;
         const int K = (d.mp + 63) / 64;
         int c = 0;
-        while (K > kClassMaxPanels[c]) ++c;
+        while (c < nc - 1 && K > bounds[c]) ++c;
         by_cls[c].push_back(b);          // m == 0 blocks land in class 0: no tiles, no steps, they only exist
     }
     P.order.reserve(nb);
@@ -195,10 +201,11 @@ int make_batches(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, 
         std::stable_sort(sub.begin(), sub.end(), [&](int x, int y) { return P.blocks[x].m > P.blocks[y].m; });
         P.order.insert(P.order.end(), sub.begin(), sub.end());
         B.ord_n = (int32_t)sub.size();
+        B.big = P.blocks[sub[0]].mp > 64 * kBulkMaxPanels;
         P.batches.push_back(std::move(B));
     };
     if (!streaming) {
-        for (int c = kNumClasses - 1; c >= 0; --c) add_batch(by_cls[c], c);
+        for (int c = nc - 1; c >= 0; --c) add_batch(by_cls[c], c);
         return DBSLMM_B200_OK;
     }
     // Streaming: the two big classes first (few, scattered blocks with the longest dependency chains), then the
@@ -206,10 +213,14 @@ int make_batches(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, 
     // contiguous stretch of the .bed (minus the big blocks inside it), so its upload is a handful of large copies,
     // and its factorisation starts while the next region is still crossing PCIe.  Regions alternate between the two
     // bulk streams so the thin last steps of one overlap the first steps of the next.
-    add_batch(by_cls[3], 3);
-    add_batch(by_cls[2], 2);
-    std::vector<int32_t> bulk(by_cls[1].size() + by_cls[0].size());
-    std::merge(by_cls[1].begin(), by_cls[1].end(), by_cls[0].begin(), by_cls[0].end(), bulk.begin());
+    std::vector<int32_t> bulk;
+    for (int c = nc - 1; c >= 0; --c) {
+        const bool is_bulk = (c < nc - 1) && bounds[c] <= kBulkMaxPanels;
+        if (!is_bulk && (int)P.batches.size() < kMaxBatches - 4) { add_batch(by_cls[c], c); continue; }
+        const size_t n0 = bulk.size();
+        bulk.insert(bulk.end(), by_cls[c].begin(), by_cls[c].end());
+        std::inplace_merge(bulk.begin(), bulk.begin() + n0, bulk.end());
+    }
     int64_t tot = 0;
     for (int b : bulk) tot += P.blocks[b].m;
     const int nsub = (bulk.size() >= 256 && tot >= 100000) ? 4 : 1;
@@ -473,6 +484,12 @@ int dbslmm_b200_create(int device, dbslmm_b200_handle** out) {
     h->n_sm = prop.multiProcessorCount;
     if (const char* e = std::getenv("DBSLMM_B200_FUSE_DIAG")) h->fuse_diag = (e[0] != '0');   // tuning switches
     if (const char* e = std::getenv("DBSLMM_B200_STREAM_BED")) h->stream_bed = (e[0] != '0');
+    if (const char* e = std::getenv("DBSLMM_B200_CLASSES")) {     // e.g. "4,8,12,16,32"
+        std::vector<int> b;
+        for (const char* p = e; *p;) { char* q; long v = std::strtol(p, &q, 10); if (q == p) break; if (v > 0) b.push_back((int)v); p = (*q == ',') ? q + 1 : q; }
+        std::sort(b.begin(), b.end());
+        if (!b.empty() && (int)b.size() < kMaxBatches) h->cls_bounds = b;
+    }
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);     // numerically lower = higher priority
     // the main stream (decode, Gram, copies) outranks the Cholesky streams: in a streaming fit the decode/Gram of a
@@ -987,7 +1004,7 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
                 // the batch's back substitution follows on its own stream: the big blocks' substitutions overlap
                 // the factorisation of the bulk classes, which finish last
                 CU_TRY(h, cudaEventRecord(h->ev_cend[bi], cs));
-                CU_TRY(h, launch_backsolve(d_blocks, d_order + B.ord_off, B.ord_n, kClassMaxPanels[B.cls] > 16,
+                CU_TRY(h, launch_backsolve(d_blocks, d_order + B.ord_off, B.ord_n, B.big,
                                            (const double*)h->lbuf.p, inv_sqrt_n, bs, bl, P.max_mp, cs));
                 ++n_launch;
                 CU_TRY(h, cudaEventRecord(h->ev_join[bi], cs));
@@ -1109,7 +1126,8 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
         for (int bi = 0; bi < nbatch && !pcg && !(streaming && a->n_folds == 1); ++bi) {
             float ms = 0.f;
             cudaEventElapsedTime(&ms, h->ev_fork, h->ev_cend[bi]);
-            t->class_ms[P.batches[bi].cls] = std::max(t->class_ms[P.batches[bi].cls], ms);
+            const int slot = std::min(P.batches[bi].cls, kNumClasses - 1);
+            t->class_ms[slot] = std::max(t->class_ms[slot], ms);
         }
         t->n_launches = n_launch;
         t->n_chol_launches = n_chol_launch;

@@ -1,6 +1,8 @@
 // Phase timing of chol_diag_kernel's body (clock64 stamps by thread 0 of one CTA).  Build + run on the GPU box:
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o build/diag_probe tools/diag_probe.cu && build/diag_probe
 #include <cstdio>
+#include <cmath>
+#include <algorithm>
 #include <vector>
 #include <cuda_runtime.h>
 __device__ long long g_stamps[32];
@@ -38,6 +40,37 @@ int main() {
             printf("\n");
             cudaMemset(dSt, 0, 4);
         }
+    }
+    // ---- check L (lower), W^T (strict upper of the tile) and the dense W tile against a host factorisation
+    {
+        std::vector<double> A(64 * 64), L(64 * 64, 0.0), W(64 * 64, 0.0);
+        for (int i = 0; i < 64; ++i) for (int j = 0; j < 64; ++j) A[i * 64 + j] = S[(size_t)std::max(i, j) * mp + std::min(i, j)] + (i == j ? 0.1 : 0.0);
+        for (int j = 0; j < 64; ++j) {
+            double d = A[j * 64 + j];
+            for (int k2 = 0; k2 < j; ++k2) d -= L[j * 64 + k2] * L[j * 64 + k2];
+            L[j * 64 + j] = sqrt(d);
+            for (int i = j + 1; i < 64; ++i) {
+                double v = A[i * 64 + j];
+                for (int k2 = 0; k2 < j; ++k2) v -= L[i * 64 + k2] * L[j * 64 + k2];
+                L[i * 64 + j] = v / L[j * 64 + j];
+            }
+        }
+        for (int c = 0; c < 64; ++c)
+            for (int i = c; i < 64; ++i) {
+                double v = (i == c) ? 1.0 : 0.0;
+                for (int k2 = c; k2 < i; ++k2) v -= L[i * 64 + k2] * W[k2 * 64 + c];
+                W[i * 64 + c] = v / L[i * 64 + i];
+            }
+        std::vector<double> dl((size_t)nrows * mp), dw(64 * 64);
+        cudaMemcpy(dl.data(), dL + (size_t)5 * S.size(), sizeof(double) * dl.size(), cudaMemcpyDeviceToHost);   // block 5
+        cudaMemcpy(dw.data(), dW + (size_t)5 * 64 * 64, sizeof(double) * 64 * 64, cudaMemcpyDeviceToHost);
+        double eL = 0, eWt = 0, eW = 0;
+        for (int i = 0; i < 64; ++i) for (int j = 0; j < 64; ++j) {
+            if (j <= i) eL = fmax(eL, fabs(dl[(size_t)i * mp + j] - L[i * 64 + j]));
+            else eWt = fmax(eWt, fabs(dl[(size_t)i * mp + j] - W[j * 64 + i]));
+            eW = fmax(eW, fabs(dw[i * 64 + j] - W[i * 64 + j]));
+        }
+        printf("max abs err: L %.3e  W^T (tile upper) %.3e  W (dense) %.3e\n", eL, eWt, eW);
     }
     printf("cuda: %s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
