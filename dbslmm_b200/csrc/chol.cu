@@ -47,9 +47,12 @@ static constexpr int SMEM_CHOL = SMEM_PIPE;
 // prow/qrow = number of valid rows (others are zero-filled).  `wrow` = this warp's 16-row slot of the macro tile.
 // The dense 64x64 tile `wsrc` (W_kk of this step) rides through the ring as the chunk AFTER the last K chunk, so it
 // has landed (stride LDW) in stage (nchunk % NST) when the loop ends, at no extra latency.  All 256 threads must call.
+// `init_acc` runs right after the ring prologue has been issued: the caller's accumulator preload (global loads)
+// then overlaps the first stages' latency instead of preceding it.
+template <class InitAcc>
 __device__ __forceinline__ void gemm_nt_core(const double* __restrict__ Pg, const double* __restrict__ Qg, int ld,
                                              int prow, int qrow, int kbeg, int kend, const double* __restrict__ wsrc,
-                                             int wrow, double* smem, double (&acc)[2][8][2]) {
+                                             int wrow, double* smem, double (&acc)[2][8][2], InitAcc&& init_acc) {
     const int tid = threadIdx.x, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     const int nchunk = (kend - kbeg) / KC;     // K range [kbeg, kend), both multiples of KC
@@ -92,6 +95,7 @@ __device__ __forceinline__ void gemm_nt_core(const double* __restrict__ Pg, cons
         else if (s == nchunk) load_w(s);
         cp_async_commit();
     }
+    init_acc();
     for (int kc = 0; kc < nchunk; ++kc) {
         cp_async_wait<NST - 2>();
         __syncthreads();
@@ -423,23 +427,24 @@ __device__ __forceinline__ void panel_body(const BlockDesc& bd, const int4 item,
     const int wrow = 4 * grp + wl;
 
     const int slice = item.z & 0xFF, nsl = item.z >> 8;
-    // accumulators start at -K_ik (slice 0 only), so the Sigma tile's HBM latency hides behind the pipeline
-    // prologue: after the loop acc = L_i,0:k L_k,0:k^T - K_ik = -C
+    // accumulators start at -K_ik (slice 0 only); the preload is issued after the ring prologue, so the Sigma tile's
+    // HBM latency and the first stages' latency overlap: after the loop acc = L_i,0:k L_k,0:k^T - K_ik = -C
     double acc[2][8][2];
-#pragma unroll
-    for (int f = 0; f < 2; ++f)
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const int rl = 16 * wrow + 8 * f + g, cc = 8 * c + 2 * t;
-            double2 a = make_double2(0.0, 0.0);
-            if (slice == 0 && rl < prow && cc < wk) a = *reinterpret_cast<const double2*>(Sb + (size_t)(r0 + rl) * ld + pc0 + cc);
-            acc[f][c][0] = -a.x;
-            acc[f][c][1] = -a.y;
-        }
     // split-K: slice s of nsl owns 64-wide K blocks [k*s/nsl, k*(s+1)/nsl)
     const int kb = (k * slice) / nsl * NB, ke = (k * (slice + 1)) / nsl * NB;
     gemm_nt_core(Lb + (size_t)r0 * ld, Lb + (size_t)pc0 * ld, ld, prow, wk, kb, ke,
-                 wbuf + wpar + (size_t)item.x * (NB * NB), wrow, smem, acc);
+                 wbuf + wpar + (size_t)item.x * (NB * NB), wrow, smem, acc, [&]() {
+#pragma unroll
+        for (int f = 0; f < 2; ++f)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int rl = 16 * wrow + 8 * f + g, cc = 8 * c + 2 * t;
+                double2 a = make_double2(0.0, 0.0);
+                if (slice == 0 && rl < prow && cc < wk) a = *reinterpret_cast<const double2*>(Sb + (size_t)(r0 + rl) * ld + pc0 + cc);
+                acc[f][c][0] = -a.x;
+                acc[f][c][1] = -a.y;
+            }
+    });
     if (nsl > 1) {
         // partial sums go to scratch; the CTA that arrives last adds them up IN SLICE ORDER (deterministic)
         double* part = scratch + ((size_t)(item.w - group_base) * nsl) * (TM * NB);
@@ -521,7 +526,8 @@ __device__ __forceinline__ void panel_body(const BlockDesc& bd, const int4 item,
 
     // ---- look-ahead: T_ii -= L_ik L_ik^T on this group's diagonal tile
     if (glook) {
-        // the old tile values go straight into the accumulators (negated): their latency overlaps the barrier
+        // the old tile values are loaded straight into the accumulators and NOT touched before the barrier (their
+        // latency overlaps it); sign and ridge are applied after it
         double acc2[2][8][2];
         const double* src = (k == 0 ? sigma : Lbuf) + bd.moff;    // first touch reads Sigma (+ ridge)
 #pragma unroll
@@ -530,18 +536,26 @@ __device__ __forceinline__ void panel_body(const BlockDesc& bd, const int4 item,
             for (int c = 0; c < 8; ++c) {
                 const int rl = 16 * wl + 8 * f + g, cc = 8 * c + 2 * t;   // within the tile
                 double2 v = make_double2(0.0, 0.0);
-                if (look && c <= 2 * wl + 1 && rl < tw && cc <= rl) {
+                if (look && c <= 2 * wl + 1 && rl < tw && cc <= rl)
                     v = __ldcg(reinterpret_cast<const double2*>(src + (size_t)(trow0 + rl) * ld + trow0 + cc));
-                    if (k == 0) {
-                        if (cc == rl && trow0 + rl < bd.ms) v.x += ridge;
-                        if (cc + 1 == rl && trow0 + rl < bd.ms) v.y += ridge;   // odd rows: the diagonal is the pair's second element
-                    }
-                }
-                acc2[f][c][0] = -v.x;
-                acc2[f][c][1] = -v.y;
+                acc2[f][c][0] = v.x;
+                acc2[f][c][1] = v.y;
             }
         asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");      // the four warps of this half
         if (look) {
+#pragma unroll
+            for (int f = 0; f < 2; ++f)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int rl = 16 * wl + 8 * f + g, cc = 8 * c + 2 * t;
+                    double vx = acc2[f][c][0], vy = acc2[f][c][1];
+                    if (k == 0 && trow0 + rl < bd.ms) {
+                        if (cc == rl) vx += ridge;
+                        if (cc + 1 == rl) vy += ridge;                    // odd rows: the diagonal is the pair's second element
+                    }
+                    acc2[f][c][0] = -vx;
+                    acc2[f][c][1] = -vy;
+                }
             const double* A = Lh + (16 * wl + g) * LDW + 2 * t;
             const double* B = Lh + g * LDW + 2 * t;
             switch (wl) {                                              // static column count per row slot: no predicated mma
