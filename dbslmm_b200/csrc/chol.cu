@@ -92,7 +92,7 @@ __device__ __forceinline__ void gemm_nt_core(const double* __restrict__ Pg, cons
 #pragma unroll
     for (int s = 0; s < NST - 1; ++s) {
         if (s < nchunk) load_stage(s, s);
-        else if (s == nchunk) load_w(s);
+        else if (s == nchunk && wsrc != nullptr) load_w(s);
         cp_async_commit();
     }
     init_acc();
@@ -101,7 +101,7 @@ __device__ __forceinline__ void gemm_nt_core(const double* __restrict__ Pg, cons
         __syncthreads();
         const int nx = kc + NST - 1;
         if (nx < nchunk) load_stage(nx, nx % NST);
-        else if (nx == nchunk) load_w(nx % NST);
+        else if (nx == nchunk && wsrc != nullptr) load_w(nx % NST);
         cp_async_commit();
         if (active) {
             // One 128-bit load feeds two DMMAs: within each 8-wide K group lane t owns k = 2t (.x) and
@@ -404,12 +404,15 @@ __device__ __forceinline__ void syrk_rows(const double* __restrict__ A, const do
 //   panel step is ONE launch and the next step's W is ready when it starts.
 // ------------------------------------------------------------------------------------------
 // item: x = block, y = macro tile, z = slice | nslices << 8, w = split group id.
-template <bool kFuseDiag>
+// fuse_end: the CTA of macro tile 0 factors the diagonal tile of panel k+1 when it is done.  wait_w: W_k is being
+// produced by a diagonal CTA of THIS launch (see chol_panel_kernel): the main loop runs without it and the TRSM
+// waits for dflag[block] >= k+1.
 __device__ __forceinline__ void panel_body(const BlockDesc& bd, const int4 item, int k, const double* __restrict__ sigma,
                                            double* __restrict__ Lbuf, double* __restrict__ wbuf, int64_t wpar,
                                            int64_t wpar_next, double ridge, double* __restrict__ scratch,
                                            int32_t* __restrict__ counters, int32_t group_base,
-                                           int32_t* __restrict__ status, double* smem, int* s_last_p) {
+                                           int32_t* __restrict__ status, const int32_t* __restrict__ dflag, bool fuse_end,
+                                           bool wait_w, double* smem, int* s_last_p) {
     int& s_last = *s_last_p;
     const int pc0 = k * NB;
     const int wk = min(NB, bd.mp - pc0);
@@ -432,8 +435,9 @@ __device__ __forceinline__ void panel_body(const BlockDesc& bd, const int4 item,
     double acc[2][8][2];
     // split-K: slice s of nsl owns 64-wide K blocks [k*s/nsl, k*(s+1)/nsl)
     const int kb = (k * slice) / nsl * NB, ke = (k * (slice + 1)) / nsl * NB;
+    const double* wsrc = wbuf + wpar + (size_t)item.x * (NB * NB);
     gemm_nt_core(Lb + (size_t)r0 * ld, Lb + (size_t)pc0 * ld, ld, prow, wk, kb, ke,
-                 wbuf + wpar + (size_t)item.x * (NB * NB), wrow, smem, acc, [&]() {
+                 wait_w ? nullptr : wsrc, wrow, smem, acc, [&]() {
 #pragma unroll
         for (int f = 0; f < 2; ++f)
 #pragma unroll
@@ -479,6 +483,25 @@ __device__ __forceinline__ void panel_body(const BlockDesc& bd, const int4 item,
     // Shared memory now: stage s_w holds W_kk ([64][LDW], W[c][c'] = (L_kk^-1)[c][c'], zero above the diagonal);
     // the other two stages take the two 64-row halves of -L_ik ([64][LDW] each).
     const int s_w = ((ke - kb) / KC) % NST;
+    if (wait_w) {
+        // W_k comes from a diagonal CTA of this launch (lower blockIdx, so it is resident or done): acquire, then load
+        if (tid == 0) {
+            const volatile int32_t* f = dflag + item.x;
+            while (*f < k + 1) __nanosleep(40);
+            __threadfence();
+        }
+        __syncthreads();
+        double* Ws = smem + s_w * STAGE;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int idx = tid + u * CHOL_THREADS;
+            const int row = idx >> 5, ch = (idx & 31) * 2;
+            cp_async16(Ws + row * LDW + ch, wsrc + row * NB + ch, true);
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+    }
     const double* Wsm = smem + s_w * STAGE;
     double* Lh = smem + ((s_w + 1 + grp) % NST) * STAGE;
     const bool active = (16 * wrow < prow);
@@ -576,7 +599,7 @@ __device__ __forceinline__ void panel_body(const BlockDesc& bd, const int4 item,
                 }
         }
     }
-    if constexpr (kFuseDiag) {
+    if (fuse_end) {
         // macro tile 0: rows r0 .. r0+63 are the diagonal tile of panel k+1, which this step completed
         if (item.y == 0 && r0 < bd.mp && wk == NB) {
             __syncthreads();        // T_new is in L2 for the whole CTA; shared memory is free again
@@ -585,18 +608,31 @@ __device__ __forceinline__ void panel_body(const BlockDesc& bd, const int4 item,
     }
 }
 
-template <bool kFuseDiag>
+// One panel step of a batch.  CTAs [0, n_diag_first) factor the diagonal tile of panel k of their block (when step k-1
+// deferred it: chain-bound steps, where the factorisation then overlaps this step's main loops instead of extending
+// step k-1) and publish it through dflag; the others are panel CTAs.  CTAs are dispatched in blockIdx order, so a
+// panel CTA never waits for a diagonal CTA that is not resident or finished.
 __global__ void __launch_bounds__(CHOL_THREADS, 2)
-chol_panel_kernel(const BlockDesc* __restrict__ blocks, const int4* __restrict__ items, int32_t k,
+chol_panel_kernel(const BlockDesc* __restrict__ blocks, const int4* __restrict__ items,
+                  const int32_t* __restrict__ diag_items, int32_t n_diag_first, int32_t k,
                   const double* __restrict__ sigma, double* __restrict__ Lbuf, double* __restrict__ wbuf, int64_t wpar,
                   int64_t wpar_next, double ridge, double* __restrict__ scratch, int32_t* __restrict__ counters,
-                  int32_t group_base, int32_t* __restrict__ status) {
+                  int32_t group_base, int32_t* __restrict__ status, int32_t* __restrict__ dflag, int32_t fuse_end) {
     extern __shared__ __align__(16) double smem[];
     __shared__ int s_last;
-    const int4 item = items[blockIdx.x];
+    if ((int)blockIdx.x < n_diag_first) {
+        const int blk = diag_items[blockIdx.x];
+        const BlockDesc bd = blocks[blk];
+        diag_body(bd, blk, k, sigma, Lbuf, wbuf + wpar, ridge, status, smem);
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) atomicExch(dflag + blk, k + 1);
+        return;
+    }
+    const int4 item = items[blockIdx.x - n_diag_first];
     const BlockDesc bd = blocks[item.x];
-    panel_body<kFuseDiag>(bd, item, k, sigma, Lbuf, wbuf, wpar, wpar_next, ridge, scratch, counters, group_base, status,
-                          smem, &s_last);
+    panel_body(bd, item, k, sigma, Lbuf, wbuf, wpar, wpar_next, ridge, scratch, counters, group_base, status, dflag,
+               fuse_end != 0, n_diag_first > 0, smem, &s_last);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -772,9 +808,7 @@ backsolve_cluster_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __
 cudaError_t chol_configure() {
     cudaError_t e = cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DIAG);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(chol_panel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CHOL);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(chol_panel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CHOL);
+    return cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CHOL);
 }
 
 // W_k (the inverse of the diagonal tile of panel k) lives in wbuf[(k & 1) * wstride + block * 64 * 64]: two parities,
@@ -787,18 +821,17 @@ cudaError_t launch_chol_diag(const BlockDesc* blocks, const int32_t* items, int3
                                                               status);
     return cudaGetLastError();
 }
-cudaError_t launch_chol_panel(const BlockDesc* blocks, const int4* items, int32_t n_items, int32_t k,
-                              const double* sigma, double* L, double* wbuf, int64_t wstride, bool fuse_diag,
-                              double ridge, double* scratch, int32_t* counters, int32_t group_base, int32_t* status,
-                              cudaStream_t st) {
-    if (n_items == 0) return cudaSuccess;
+// diag_first: the n_diag blocks of `diag_items` get their diagonal tile of panel k factored by extra CTAs of this
+// launch (step k-1 deferred it); fuse_end: macro tile 0 factors the diagonal tile of panel k+1 at its end.
+cudaError_t launch_chol_panel(const BlockDesc* blocks, const int4* items, int32_t n_items, const int32_t* diag_items,
+                              int32_t n_diag_first, int32_t k, const double* sigma, double* L, double* wbuf, int64_t wstride,
+                              bool fuse_end, double ridge, double* scratch, int32_t* counters, int32_t group_base,
+                              int32_t* status, int32_t* dflag, cudaStream_t st) {
+    if (n_items + n_diag_first == 0) return cudaSuccess;
     const int64_t wpar = (k & 1) * wstride, wnext = ((k + 1) & 1) * wstride;
-    if (fuse_diag)
-        chol_panel_kernel<true><<<n_items, CHOL_THREADS, SMEM_CHOL, st>>>(blocks, items, k, sigma, L, wbuf, wpar, wnext, ridge,
-                                                                          scratch, counters, group_base, status);
-    else
-        chol_panel_kernel<false><<<n_items, CHOL_THREADS, SMEM_CHOL, st>>>(blocks, items, k, sigma, L, wbuf, wpar, wnext, ridge,
-                                                                           scratch, counters, group_base, status);
+    chol_panel_kernel<<<n_items + n_diag_first, CHOL_THREADS, SMEM_CHOL, st>>>(blocks, items, diag_items, n_diag_first, k, sigma, L,
+                                                                             wbuf, wpar, wnext, ridge, scratch, counters,
+                                                                             group_base, status, dflag, fuse_end ? 1 : 0);
     return cudaGetLastError();
 }
 // Back substitution of `n_blocks` blocks listed in `order`: an 8-CTA cluster per block for the big size

@@ -61,7 +61,10 @@ struct PinBuf {
 constexpr int kNumClasses = 4;                 // timing slots reported per size class (dbslmm_b200_timing.class_ms)
 constexpr int kBulkMaxPanels = 16;             // blocks up to 16 panels (m <= 1024) are "bulk": one-CTA back substitution
 
-struct StepList { int32_t diag_off, n_diag, panel_off, n_panel, group_base, n_groups, nsl; };
+struct StepList {
+    int32_t diag_off, n_diag, panel_off, n_panel, group_base, n_groups, nsl;
+    int32_t defer;      // the diagonal tile of panel k+1 is NOT factored at the end of this step but first thing in step k+1
+};
 
 // A batch = the blocks that run one Cholesky step loop together on one stream.  With the reference panel resident
 // (load_bed) there is one batch per size class.  When the panel streams in from host memory inside the fit
@@ -118,17 +121,20 @@ struct dbslmm_b200_handle {
     // size classes of the Cholesky step loops, by #panels (upper bounds, ascending; the last class is unbounded).
     // Each class (batch) has its own stream: the step loops interleave and fill each other's thin last steps.
     std::vector<int> cls_bounds = {8, 16, 32};
+    int splitk_max = 16, splitk_min_blocks = 2;  // split-K: at most this many slices, each at least this many 64-deep K blocks
+    int defer_max_ctas = 296;                    // steps with at most this many CTAs take their diagonal tile first (see StepList)
     // reference panel
     DevBuf bed, stats;
     PinBuf h_stats;                      // per-SNP statistics, filled asynchronously by load_bed
     cudaEvent_t ev_bed = nullptr;        // completes when the panel, its statistics and their host copy have landed
     bool bed_pending = false;
     bool stats_valid = false;            // `stats` / `h_stats` describe the resident panel (a streaming fit skips them)
+    bool missing_hint = false;           // the last panel had missing calls: the next fit_args.bed call uploads first
     std::vector<int32_t> miss_flags;     // per-block "has missing calls" of the current plan
     int64_t n_snp = 0;
     int32_t n_ref = 0, pitch = 0, n_pad = 0;
     // workspace
-    DevBuf codes, sigma, lbuf, rowN, rowS, rowR, planblob, beta, status, intQ, intA, intN, scratch, counters, wbuf, vbed, vstats, vwork, flagbuf;
+    DevBuf codes, sigma, lbuf, rowN, rowS, rowR, planblob, beta, status, intQ, intA, intN, scratch, counters, wbuf, vbed, vstats, vwork, flagbuf, dflag;
     PinBuf h_blob, h_out;
     Plan plan;
     int32_t last_flags = 0, last_solver = 0, last_nfolds = 0;
@@ -322,7 +328,7 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
                 ntiles += (d.nrows - (64 * k + wk) + 127) / 128;
             }
             int nsl = 1;
-            if (ntiles > 0) nsl = std::max(1, std::min({8, k / 4, kTargetCtas / ntiles}));
+            if (ntiles > 0) nsl = std::max(1, std::min({h->splitk_max, k / h->splitk_min_blocks, kTargetCtas / ntiles}));
             s.nsl = nsl;
             s.group_base = n_groups;
             // macro tile 0 of every block goes first: its CTA also factors the next diagonal tile (fused), so it
@@ -347,6 +353,11 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
             s.n_panel = (int32_t)panel_items.size() - s.panel_off;
             batch_scratch = std::max<int64_t>(batch_scratch, (int64_t)s.n_groups * nsl * 128 * 64);
         }
+        // A chain-bound step (the whole next step fits in one wave of CTAs) defers the next diagonal tile to the
+        // next launch, where it overlaps the main loops; otherwise macro tile 0 factors it at the end of this step,
+        // in the shadow of the step's later waves.
+        for (int k = 0; k < kmax; ++k)
+            B.steps[k].defer = (k + 1 < kmax && B.steps[k + 1].n_panel + B.steps[k + 1].n_diag <= h->defer_max_ctas) ? 1 : 0;
         B.scratch_off = P.scratch_doubles;
         P.scratch_doubles += batch_scratch;
     }
@@ -484,6 +495,11 @@ int dbslmm_b200_create(int device, dbslmm_b200_handle** out) {
     h->n_sm = prop.multiProcessorCount;
     if (const char* e = std::getenv("DBSLMM_B200_FUSE_DIAG")) h->fuse_diag = (e[0] != '0');   // tuning switches
     if (const char* e = std::getenv("DBSLMM_B200_STREAM_BED")) h->stream_bed = (e[0] != '0');
+    if (const char* e = std::getenv("DBSLMM_B200_SPLITK")) {      // "max,min_blocks"
+        int a = 0, b = 0;
+        if (std::sscanf(e, "%d,%d", &a, &b) == 2 && a >= 1 && a <= 255 && b >= 1) { h->splitk_max = a; h->splitk_min_blocks = b; }
+    }
+    if (const char* e = std::getenv("DBSLMM_B200_DEFER_CTAS")) h->defer_max_ctas = std::atoi(e);
     if (const char* e = std::getenv("DBSLMM_B200_CLASSES")) {     // e.g. "4,8,12,16,32"
         std::vector<int> b;
         for (const char* p = e; *p;) { char* q; long v = std::strtol(p, &q, 10); if (q == p) break; if (v > 0) b.push_back((int)v); p = (*q == ',') ? q + 1 : q; }
@@ -519,7 +535,7 @@ void dbslmm_b200_destroy(dbslmm_b200_handle* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     DevBuf* bufs[] = {&h->bed, &h->stats, &h->codes, &h->sigma, &h->lbuf, &h->rowN, &h->rowS, &h->rowR,
-                      &h->planblob, &h->beta, &h->status, &h->intQ, &h->intA, &h->intN, &h->scratch, &h->counters, &h->wbuf, &h->vbed, &h->vstats, &h->vwork, &h->flagbuf};
+                      &h->planblob, &h->beta, &h->status, &h->intQ, &h->intA, &h->intN, &h->scratch, &h->counters, &h->wbuf, &h->vbed, &h->vstats, &h->vwork, &h->flagbuf, &h->dflag};
     for (DevBuf* b : bufs) b->release();
     h->h_blob.release();
     h->h_out.release();
@@ -773,6 +789,7 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
         CU_TRY(h, h->scratch.ensure(sizeof(double) * (size_t)std::max<int64_t>(P.scratch_doubles, 1)));
         CU_TRY(h, h->wbuf.ensure(2 * sizeof(double) * 64 * 64 * (size_t)std::max(nb, 1)));   // two parities, see launch_chol_diag
         CU_TRY(h, h->counters.ensure(sizeof(int32_t) * (size_t)std::max(P.n_groups, 1)));
+        CU_TRY(h, h->dflag.ensure(sizeof(int32_t) * (size_t)std::max(nb, 1)));
     }
     if (keep_int) {
         CU_TRY(h, h->intQ.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(P.mat_doubles, 1)));
@@ -834,6 +851,7 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
         h->bed_pending = false;
         bool any = false;
         for (int b = 0; b < nb; ++b) any = any || (hflags[b] != 0);
+        h->missing_hint = any;
         if (any) {
             h->miss_flags.assign(hflags, hflags + nb);
             int rc = build_plan(h, a, P, h->miss_flags.data());
@@ -858,6 +876,7 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
     CU_TRY(h, cudaEventRecord(h->ev[1], st));
 
     if (!pcg && P.n_groups > 0) CU_TRY(h, cudaMemsetAsync(h->counters.p, 0, sizeof(int32_t) * (size_t)P.n_groups, st));
+    if (!pcg) CU_TRY(h, cudaMemsetAsync(h->dflag.p, 0, sizeof(int32_t) * (size_t)std::max(nb, 1), st));
     // ---- decode + gram
     GramArgs g;
     CUtensorMap tmap;
@@ -977,6 +996,7 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
         double* bl = bs + P.tot_s;
         if (!pcg) {
             if (f > 0 && P.n_groups > 0) CU_TRY(h, cudaMemsetAsync(h->counters.p, 0, sizeof(int32_t) * (size_t)P.n_groups, st));
+            if (f > 0) CU_TRY(h, cudaMemsetAsync(h->dflag.p, 0, sizeof(int32_t) * (size_t)std::max(nb, 1), st));
             CU_TRY(h, cudaEventRecord(h->ev_fork, st));
             const int64_t wstride = (int64_t)64 * 64 * std::max(nb, 1);
             for (int bi = 0; bi < nbatch; ++bi) {
@@ -986,7 +1006,9 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
                 CU_TRY(h, cudaStreamWaitEvent(cs, (streaming && f == 0) ? h->ev_gram[bi] : h->ev_fork, 0));
                 for (size_t k = 0; k < B.steps.size(); ++k) {
                     const StepList& s = B.steps[k];
-                    // the diagonal tile of panel k >= 1 is factored by the step k-1 panel launch (fused)
+                    // Who factors the diagonal tile of panel k: its own launch (k == 0, or no fusion at all), macro tile 0
+                    // of step k-1 (fused at the end), or extra CTAs at the head of THIS launch (step k-1 deferred it).
+                    const bool deferred_here = h->fuse_diag && k > 0 && B.steps[k - 1].defer;
                     if (k == 0 || !h->fuse_diag) {
                         CU_TRY(h, launch_chol_diag(d_blocks, d_diag + s.diag_off, s.n_diag, (int32_t)k,
                                                    (const double*)h->sigma.p, (double*)h->lbuf.p, (double*)h->wbuf.p, wstride,
@@ -994,10 +1016,11 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
                         ++n_launch;
                         ++n_chol_launch;
                     }
-                    CU_TRY(h, launch_chol_panel(d_blocks, d_panel + s.panel_off, s.n_panel, (int32_t)k,
-                                                (const double*)h->sigma.p, (double*)h->lbuf.p, (double*)h->wbuf.p, wstride,
-                                                h->fuse_diag, ridge, (double*)h->scratch.p + B.scratch_off,
-                                                (int32_t*)h->counters.p, s.group_base, d_status, cs));
+                    CU_TRY(h, launch_chol_panel(d_blocks, d_panel + s.panel_off, s.n_panel, d_diag + s.diag_off,
+                                                deferred_here ? s.n_diag : 0, (int32_t)k, (const double*)h->sigma.p,
+                                                (double*)h->lbuf.p, (double*)h->wbuf.p, wstride, h->fuse_diag && !s.defer, ridge,
+                                                (double*)h->scratch.p + B.scratch_off, (int32_t*)h->counters.p, s.group_base,
+                                                d_status, (int32_t*)h->dflag.p, cs));
                     ++n_launch;
                     ++n_chol_launch;
                 }
@@ -1171,7 +1194,7 @@ int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
     // ---- the panel comes with the call (what DBSLMMFIT::est does with its bed_str argument)
     if (h->bed_pending) { CU_TRY(h, cudaEventSynchronize(h->ev_bed)); h->bed_pending = false; }
     const bool can_stream = !want_var && a->solver == DBSLMM_B200_SOLVER_CHOLESKY && !(a->flags & DBSLMM_B200_FLAG_PLAN_CACHED) &&
-                            a->n_blocks > 0 && h->stream_bed;
+                            a->n_blocks > 0 && h->stream_bed && !h->missing_hint;
     if (!can_stream) {
         int rc = dbslmm_b200_load_bed(h, a->bed, a->bed_n_snp, a->bed_n_ref);
         if (rc != DBSLMM_B200_OK) return rc;
@@ -1186,7 +1209,12 @@ int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
     h->stats_valid = false;
     h->plan.valid = false;
     int rc = fit_impl(h, a, true);
-    if (rc == kRetryResident) rc = fit_impl(h, a, false);       // the panel is resident by now; statistics are computed on demand
+    if (rc == kRetryResident) {
+        // the panel is resident by now; statistics are computed on demand.  Panels with missing calls tend to come
+        // again (folds, repeated fits): remember, so the next call does not stream speculatively
+        h->missing_hint = true;
+        rc = fit_impl(h, a, false);
+    }
     return rc;
 }
 

@@ -54,6 +54,7 @@ gram_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs a) {
     using Cfg = GramCfg<NPROD>;
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], accum_bar;
+    __shared__ __align__(16) double4 row_consts[kTile];          // {S_i, n_i, r_i} of the tile's rows
     __shared__ uint32_t tmem_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -138,10 +139,18 @@ gram_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs a) {
         const int q = warp & 3;
         const int jl = tile.tj * kTile + q * 32 + lane;          // Sigma column (block local)
         const bool jvalid = jl < bd.m;
-        int32_t Sj = 0, Nj = 1;
-        double rj = 0.0;
-        if (jvalid) { Sj = a.rowS[bd.goff + jl]; Nj = a.rowN[bd.goff + jl]; rj = a.rowR[bd.goff + jl]; }
+        double Sj = 0.0, Nj = 1.0, rj = 0.0;
+        if (jvalid) { Sj = (double)a.rowS[bd.goff + jl]; Nj = (double)a.rowN[bd.goff + jl]; rj = a.rowR[bd.goff + jl]; }
         const double dn = (double)a.n_ref;
+        // per-row constants {S_i, n_i, r_i} of the tile's 128 rows go through shared memory (one broadcast read per
+        // row instead of shuffles); their global loads overlap the main loop
+        {
+            const int il = tile.ti * kTile + (warp - 2) * 32 + lane;
+            double s_i = 0.0, n_i = 1.0, r_i = 0.0;
+            if (il < bd.m) { s_i = (double)a.rowS[bd.goff + il]; n_i = (double)a.rowN[bd.goff + il]; r_i = a.rowR[bd.goff + il]; }
+            row_consts[(warp - 2) * 32 + lane] = make_double4(s_i, n_i, r_i, 0.0);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");           // the four epilogue warps
         mbar_wait(&accum_bar, 0);
         tc_fence_after();
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -160,33 +169,23 @@ gram_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs a) {
                 tmem_ld16(tlane + 2 * kTile + c0, v2);
                 tmem_ld16(tlane + 3 * kTile + c0, v3);
             }
-            // per-row constants for the CH rows of this chunk, one per lane, broadcast by shuffle
-            int32_t Si_l = 0, Ni_l = 1;
-            double ri_l = 0.0;
-            {
-                const int il = ibase + (lane % CH);
-                if (il < bd.m) { Si_l = a.rowS[bd.goff + il]; Ni_l = a.rowN[bd.goff + il]; ri_l = a.rowR[bd.goff + il]; }
-            }
             tmem_ld_wait();
 #pragma unroll
             for (int r = 0; r < CH; ++r) {
                 const int il = ibase + r;
-                const int32_t Si = __shfl_sync(0xffffffffu, Si_l, r);
-                const int32_t Ni = __shfl_sync(0xffffffffu, Ni_l, r);
-                const double ri = __shfl_sync(0xffffffffu, ri_l, r);
+                const double4 rc = row_consts[c0 + r];
+                const double Si = rc.x, Ni = rc.y, ri = rc.z;
                 if (il >= bd.mp || jl > il) continue;
                 double val;
                 if (il < bd.m) {
                     double num;
                     if constexpr (NPROD == 1) {
-                        const long long t = (long long)a.n_ref * (long long)(int32_t)v0[r] - (long long)Si * (long long)Sj;
-                        num = dn * (double)t;
+                        num = dn * fma(-Si, Sj, dn * (double)(int32_t)v0[r]);        // n (n Q - S_i S_j): exact integer < 2^53
                     } else {
                         const double Q = (double)(int32_t)v0[r], P1 = (double)(int32_t)v1[r];
                         const double P2 = (double)(int32_t)v2[r], Nn = (double)(int32_t)v3[r];
                         // A_ij = sum g_i M_j = P2,  A_ji = sum g_j M_i = P1
-                        num = (double)Ni * (double)Nj * Q - (double)Ni * (double)Sj * P2 -
-                              (double)Nj * (double)Si * P1 + (double)Si * (double)Sj * Nn;
+                        num = Ni * Nj * Q - Ni * Sj * P2 - Nj * Si * P1 + Si * Sj * Nn;
                     }
                     val = num * ri * rj;
                     if (il == jl) val += a.one_minus_tau;

@@ -221,8 +221,11 @@ int main(int argc, char* argv[]) {
     vector<dbslmm_b200_handle*> hs(n_gpus, nullptr);
     for (int g = 0; g < n_gpus; ++g)
         if (dbslmm_b200_create(g, &hs[g]) != DBSLMM_B200_OK) { cerr << "ERROR: cannot initialise GPU " << g << endl; exit(2); }
-    // GPU 0 holds the whole panel: its statistics kernel IS the MAF pre-pass (dtpr.cpp:93-102)
-    if (dbslmm_b200_load_bed(hs[0], bed.data(), n_snp_all, n_ref) != DBSLMM_B200_OK) {
+    // With a MAF constraint GPU 0 takes the whole panel now: its statistics kernel IS the MAF pre-pass
+    // (dtpr.cpp:93-102).  Without one (mafMax == 1, dbslmm.cpp:238-241) nothing needs the panel before the fit, and
+    // it travels with dbslmm_b200_fit (fit_args.bed): the upload then overlaps the fit.
+    const bool early_load = constr;
+    if (early_load && dbslmm_b200_load_bed(hs[0], bed.data(), n_snp_all, n_ref) != DBSLMM_B200_OK) {
         cerr << "ERROR: load_bed: " << dbslmm_b200_last_error(hs[0]) << endl; exit(2);
     }
     vector<double> ref_maf;
@@ -386,13 +389,12 @@ int main(int argc, char* argv[]) {
     cout << "Fitting model..." << endl;
     auto run = [&](int g) {
         Shard& sh = shards[g];
-        if (n_gpus > 1 && sh.n_rows > 0) {
-            sh.rc = dbslmm_b200_load_bed(hs[g], sh.bed.data(), sh.n_rows, n_ref);
-            if (sh.rc < 0) { sh.err = dbslmm_b200_last_error(hs[g]); return; }
-        } else if (n_gpus > 1) {
-            return;
-        }
+        if (n_gpus > 1 && sh.n_rows == 0) return;
         dbslmm_b200_fit_args a{};
+        // the panel (this GPU's shard of it) travels with the fit, like est()'s bed_str: uploaded in batches that
+        // overlap decode / Gram / Cholesky.  One GPU with a MAF constraint already holds the panel (pre-pass above).
+        if (n_gpus > 1) { a.bed = sh.bed.data(); a.bed_n_snp = sh.n_rows; a.bed_n_ref = n_ref; }
+        else if (!early_load) { a.bed = bed.data(); a.bed_n_snp = n_snp_all; a.bed_n_ref = n_ref; }
         a.n_blocks = (int32_t)sh.blocks.size();
         a.s_off = sh.s_off.data(); a.s_pos = sh.s_pos.data(); a.s_z = sh.s_z.data();
         if (with_large) { a.l_off = sh.l_off.data(); a.l_pos = sh.l_pos.data(); a.l_z = sh.l_z.data(); }

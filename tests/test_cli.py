@@ -169,3 +169,21 @@ def test_cli_variance_txt_matches_reference_cli(tmp_path):
     gb, rb = np.array([g[2] for g in got_txt]), np.array([x[2] for x in ref_txt])
     assert np.abs(gb - rb).max() <= 5e-6 * np.abs(rb).max()
     assert (tmp_path / "out.badsnps").read_text() == str(d["cli_badsnps"])
+
+
+@pytest.mark.gpu
+def test_cli_without_maf_constraint_streams_the_panel(tmp_path):
+    """mafMax == 1 (the reference's 'do not consider the difference' branch, dbslmm.cpp:238-241): nothing needs the
+    panel before the fit, so the CLI hands it to dbslmm_b200_fit (fit_args.bed, upload overlapped with the fit).
+    The result must equal the upload-then-fit path bit for bit."""
+    _write_fixture(tmp_path)
+    outs = []
+    for tag, env in (("stream", {}), ("plain", {"DBSLMM_B200_STREAM_BED": "0"})):
+        cmd = [CLI, "-s", str(tmp_path / "s.txt"), "-l", str(tmp_path / "l.txt"), "-r", str(tmp_path / "ref"), "-n", "2400",
+               "-nsnp", "996", "-mafMax", "1", "-b", str(tmp_path / "blocks.bed"), "-h", "0.5", "-t", "1",
+               "-eff", str(tmp_path / tag), "--dump-beta-bin", str(tmp_path / (tag + ".bin"))]
+        r = subprocess.run(cmd, capture_output=True, text=True, env={**os.environ, **env})
+        assert r.returncode == 0, r.stderr
+        outs.append(((tmp_path / (tag + ".txt")).read_text(), (tmp_path / (tag + ".bin")).read_bytes()))
+    assert outs[0][0] == outs[1][0] and outs[0][1] == outs[1][1]
+    assert len(outs[0][0].strip().split("\n")) > 700
