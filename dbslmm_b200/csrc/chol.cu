@@ -694,9 +694,21 @@ backsolve_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict
         if (tid < 256) {
             const int c = tid >> 2, q = tid & 3;
             double p = 0.0;
-            if (c < wk) {
-                const double* row = Lb + (size_t)(pc0 + c) * ld + pc0;
-                for (int cp = c + q; cp < wk; cp += 4) p += ((cp == c) ? 1.0 / row[c] : row[cp]) * v[cp];
+            {
+                // x_k = W_kk^T v: the row of the diagonal tile is fetched with all (up to 16) loads in flight at once --
+                // this matvec is on the per-panel dependent chain
+                const double* row = Lb + (size_t)(pc0 + min(c, wk - 1)) * ld + pc0;
+                double a[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int cp = c + q + 4 * i;
+                    a[i] = (c < wk && cp < wk) ? row[cp] : 0.0;
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int cp = c + q + 4 * i;
+                    if (c < wk && cp < wk) p += ((cp == c) ? 1.0 / a[i] : a[i]) * v[cp];
+                }
             }
             p += __shfl_xor_sync(0xffffffffu, p, 1);
             p += __shfl_xor_sync(0xffffffffu, p, 2);
@@ -712,19 +724,41 @@ backsolve_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict
 }
 
 // ------------------------------------------------------------------------------------------
-// Back substitution for big blocks (mp > 1024): a thread-block CLUSTER of 8 CTAs per block.
-// Each CTA streams one eighth of the rows below the current panel, the eight 64-entry partial
-// sums are exchanged through distributed shared memory, and every CTA then forms x_k itself
-// (redundantly: cheaper than a broadcast).  Two cluster barriers per panel.  One CTA alone is
-// latency-bound at ~30 GB/s on a 36 MB factor and was the critical path of the 8-GPU shards.
+// Back substitution for big blocks (mp > 1024): a thread-block CLUSTER of 8 CTAs per block, right-looking and
+// flag-driven, so that the dependent chain per panel is one 64x64 tile update + one 64x64 matvec with the stored
+// W_kk^T and nothing else:
+//   * CTA c owns the column panels j = c (mod 8) and keeps their running right-hand sides y_j in shared memory
+//     (every update of y_j is done by its owner: no cross-CTA reduction);
+//   * every CTA holds the whole solution vector x; the owner of panel k forms x_k = W_kk^T y_k, writes it into all
+//     eight CTAs' shared memory through DSMEM and then raises flag k there (release at cluster scope);
+//   * each CTA walks k downwards on its own: wait for flag k, fold row panel k into its panels j < k
+//     (y_j -= L[k-rows][j-cols]^T x_k, 64 contiguous 512-byte row segments per tile, up to four tiles per pass);
+//     the owner of panel k-1 folds that tile first and publishes x_k-1 before its other tiles.
+// No cluster barrier inside the loop.  The column-panel form this replaces summed over ALL rows below per panel (two
+// cluster barriers and a DSMEM reduction per panel, 14 us per panel); it was the critical path of the 8-GPU shards
+// after the factorisation.
 // ------------------------------------------------------------------------------------------
 static constexpr int kBsCluster = 8;
 static constexpr int kBsThreads = 512;
 
+__device__ __forceinline__ void st_release_cluster_u32(uint32_t cluster_addr, uint32_t v) {
+    asm volatile("st.release.cluster.shared::cluster.u32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_cluster_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.cluster.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t cta_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(rank));
+    return r;
+}
+
 __global__ void __cluster_dims__(kBsCluster, 1, 1) __launch_bounds__(kBsThreads)
 backsolve_cluster_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict__ order,
                          const double* __restrict__ Lbuf, double inv_sqrt_n, double* __restrict__ beta_s,
-                         double* __restrict__ beta_l) {
+                         double* __restrict__ beta_l, int32_t max_panels) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ __align__(16) double smem[];
@@ -732,77 +766,106 @@ backsolve_cluster_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __
     const BlockDesc bd = blocks[order[blockIdx.x / kBsCluster]];
     const int mp = bd.mp, ld = bd.ld;
     const double* Lb = Lbuf + bd.moff;
-    const double* y = Lb + (size_t)mp * ld;
-    constexpr int NRG = kBsThreads / 32;          // row groups per CTA
-    constexpr int RS = NRG * kBsCluster;          // row stride of one (CTA, row group)
-    double* x = smem;                              // [mp]   full solution vector, kept by every CTA
-    double* part = smem + mp;                      // [64]   this CTA's partial sums (read by the others)
-    double* red = part + NB;                       // [NRG][64]
-    double* v = red + NRG * NB;                    // [64]
+    const int max_owned = (max_panels + kBsCluster - 1) / kBsCluster;
+    double* xall = smem;                           // [max_panels][64]  solution, every panel written by its owner (DSMEM)
+    double* red = xall + max_panels * NB;          // [4][8][64]  per-row-group partial sums of up to four tiles
+    double* yo = red + 32 * NB;                    // [max_owned][64] running right-hand sides of the owned panels
+    uint32_t* flag = reinterpret_cast<uint32_t*>(yo + max_owned * NB);   // [max_panels] x_k has landed
     const int tid = threadIdx.x;
     const int K = (mp + NB - 1) / NB;
-    for (int k = K - 1; k >= 0; --k) {
-        const int pc0 = k * NB, wk = min(NB, mp - pc0), below = pc0 + wk;
+    // y = L^-1 z rides as matrix row mp
+    for (int idx = tid; idx < max_owned * NB; idx += kBsThreads) {
+        const int j = (idx >> 6) * kBsCluster + (int)cr, c = idx & 63;
+        yo[idx] = (j < K && j * NB + c < mp) ? Lb[(size_t)mp * ld + j * NB + c] : 0.0;
+    }
+    for (int idx = tid; idx < max_panels; idx += kBsThreads) flag[idx] = 0u;
+    __syncthreads();
+    cluster.sync();                                // every CTA's flags are cleared before anyone publishes
+
+    // x_k = W_kk^T y_k by the owner, delivered to every CTA, then flag k raised everywhere; beta written out
+    auto solve_and_publish = [&](int k) {
+        const int pc0 = k * NB, wk = min(NB, mp - pc0);
+        const double* yk = yo + (k / kBsCluster) * NB;
+        const int c = tid >> 3, q = tid & 7;       // 8 threads per entry
+        double p = 0.0;
         {
-            const int rg = tid >> 5, c2 = (tid & 31) * 2;
-            double2 p0 = make_double2(0.0, 0.0), p1 = p0, p2 = p0, p3 = p0;
-            if (c2 < wk) {
-                const double* col = Lb + pc0 + c2;
-                int i = below + (int)cr * NRG + rg;
-                for (; i + 3 * RS < mp; i += 4 * RS) {
-                    const double2 a0 = *reinterpret_cast<const double2*>(col + (size_t)i * ld);
-                    const double2 a1 = *reinterpret_cast<const double2*>(col + (size_t)(i + RS) * ld);
-                    const double2 a2 = *reinterpret_cast<const double2*>(col + (size_t)(i + 2 * RS) * ld);
-                    const double2 a3 = *reinterpret_cast<const double2*>(col + (size_t)(i + 3 * RS) * ld);
-                    const double x0 = x[i], x1 = x[i + RS], x2 = x[i + 2 * RS], x3 = x[i + 3 * RS];
-                    p0.x += a0.x * x0; p0.y += a0.y * x0;
-                    p1.x += a1.x * x1; p1.y += a1.y * x1;
-                    p2.x += a2.x * x2; p2.y += a2.y * x2;
-                    p3.x += a3.x * x3; p3.y += a3.y * x3;
-                }
-                for (; i < mp; i += RS) {
-                    const double2 a0 = *reinterpret_cast<const double2*>(col + (size_t)i * ld);
-                    p0.x += a0.x * x[i]; p0.y += a0.y * x[i];
-                }
+            // all (up to eight) loads of a thread are issued together: this matvec sits on the dependent chain
+            const double* row = Lb + (size_t)(pc0 + min(c, wk - 1)) * ld + pc0;   // diagonal at row[c], W^T[c][cp] at row[cp], cp > c
+            double a[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int cp = c + q + 8 * i;
+                a[i] = (c < wk && cp < wk) ? row[cp] : 0.0;
             }
-            red[rg * NB + c2] = (p0.x + p1.x) + (p2.x + p3.x);
-            red[rg * NB + c2 + 1] = (p0.y + p1.y) + (p2.y + p3.y);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int cp = c + q + 8 * i;
+                if (c < wk && cp < wk) p += ((cp == c) ? 1.0 / a[i] : a[i]) * yk[cp];
+            }
+        }
+        p += __shfl_xor_sync(0xffffffffu, p, 1);
+        p += __shfl_xor_sync(0xffffffffu, p, 2);
+        p += __shfl_xor_sync(0xffffffffu, p, 4);
+        cluster.map_shared_rank(xall, q)[k * NB + c] = (c < wk) ? p : 0.0;    // thread (c, q) delivers x_k[c] to CTA q
+        if (q == 0 && c < wk) {
+            const int j = pc0 + c;
+            if (j < bd.m) {
+                const double b = p * inv_sqrt_n;
+                if (j < bd.ms) beta_s[bd.out_s + j] = b;
+                else beta_l[bd.out_l + (j - bd.ms)] = b;
+            }
+        }
+        asm volatile("fence.acq_rel.cluster;" ::: "memory");
+        __syncthreads();                           // all 512 deliveries are ordered before the flags
+        if (tid < kBsCluster) st_release_cluster_u32(mapa_u32(smem_u32(flag + k), (uint32_t)tid), 1u);
+    };
+    // y_j -= L[panel k rows][panel j cols]^T x_k for up to four owned panels j0, j0-8, ... in ONE pass
+    auto fold_batch = [&](int k, int j0, int ntile) {
+        const int pc0 = k * NB, wk = min(NB, mp - pc0);
+        const double* x = xall + k * NB;
+        const int rg = tid >> 6, c = tid & 63;     // 8 row groups x 64 columns
+        double p[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 - u * kBsCluster;
+            if (u < ntile && j >= 0) {
+                const double* col = Lb + (size_t)pc0 * ld + j * NB + c;
+                double a[8];                                   // eight independent loads in flight per tile
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { const int r = rg + 8 * i; a[i] = (r < wk) ? col[(size_t)r * ld] : 0.0; }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { const int r = rg + 8 * i; if (r < wk) p[u] += a[i] * x[r]; }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) red[(u * 8 + rg) * NB + c] = p[u];
+        __syncthreads();
+        if (tid < 4 * NB) {
+            const int u = tid >> 6, c2 = tid & 63, j = j0 - u * kBsCluster;
+            if (u < ntile && j >= 0) {
+                double sacc = 0.0;
+#pragma unroll
+                for (int g2 = 0; g2 < 8; ++g2) sacc += red[(u * 8 + g2) * NB + c2];  // fixed order
+                yo[(j / kBsCluster) * NB + c2] -= sacc;
+            }
         }
         __syncthreads();
-        if (tid < NB) {
-            double sacc = 0.0;
-#pragma unroll
-            for (int q = 0; q < NRG; ++q) sacc += red[q * NB + tid];
-            part[tid] = sacc;
+    };
+
+    if ((K - 1) % kBsCluster == (int)cr) solve_and_publish(K - 1);
+    for (int k = K - 1; k >= 1; --k) {
+        if (tid == 0) { while (ld_acquire_cluster_u32(flag + k) == 0u) { } }
+        __syncthreads();                           // x_k is in xall
+        // owned panels below k, highest first: j = k-1 (if mine) is on the critical path and goes alone
+        int j = k - 1 - (((k - 1) - (int)cr) % kBsCluster + kBsCluster) % kBsCluster;   // largest j <= k-1 with j = cr (mod 8)
+        if (j == k - 1) {
+            fold_batch(k, j, 1);
+            solve_and_publish(k - 1);
+            j -= kBsCluster;
         }
-        cluster.sync();                            // all eight partial vectors are in place
-        if (tid < NB) {
-            double sacc = 0.0;
-#pragma unroll
-            for (unsigned r = 0; r < (unsigned)kBsCluster; ++r) sacc += cluster.map_shared_rank(part, r)[tid];   // fixed order
-            v[tid] = (tid < wk) ? y[pc0 + tid] - sacc : 0.0;
-        }
-        __syncthreads();
-        if (tid < 256) {
-            const int c = tid >> 2, q = tid & 3;
-            double p = 0.0;
-            if (c < wk) {
-                const double* row = Lb + (size_t)(pc0 + c) * ld + pc0;
-                for (int cp = c + q; cp < wk; cp += 4) p += ((cp == c) ? 1.0 / row[c] : row[cp]) * v[cp];
-            }
-            p += __shfl_xor_sync(0xffffffffu, p, 1);
-            p += __shfl_xor_sync(0xffffffffu, p, 2);
-            if (q == 0 && c < wk) x[pc0 + c] = p;
-        }
-        cluster.sync();                            // everyone has read the partials: they may be overwritten
+        for (; j >= 0; j -= 4 * kBsCluster) fold_batch(k, j, 4);
     }
-    if (cr == 0) {
-        for (int j = tid; j < bd.m; j += kBsThreads) {
-            const double b = x[j] * inv_sqrt_n;
-            if (j < bd.ms) beta_s[bd.out_s + j] = b;
-            else beta_l[bd.out_l + (j - bd.ms)] = b;
-        }
-    }
+    cluster.sync();                                // nobody exits while its shared memory may still be written
 }
 
 cudaError_t chol_configure() {
@@ -841,10 +904,12 @@ cudaError_t launch_backsolve(const BlockDesc* blocks, const int32_t* order, int3
                              cudaStream_t st) {
     if (n_blocks == 0) return cudaSuccess;
     if (big) {
-        const size_t smem = (size_t)(max_mp + (kBsThreads / 32 + 2) * NB) * sizeof(double);
+        const int K = (max_mp + NB - 1) / NB;
+        const int max_owned = (K + kBsCluster - 1) / kBsCluster;
+        const size_t smem = (size_t)(K * NB + 32 * NB + max_owned * NB) * sizeof(double) + (size_t)K * sizeof(uint32_t) + 16;
         cudaError_t e = cudaFuncSetAttribute(backsolve_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        backsolve_cluster_kernel<<<n_blocks * kBsCluster, kBsThreads, smem, st>>>(blocks, order, L, inv_sqrt_n, beta_s, beta_l);
+        backsolve_cluster_kernel<<<n_blocks * kBsCluster, kBsThreads, smem, st>>>(blocks, order, L, inv_sqrt_n, beta_s, beta_l, K);
     } else {
         const size_t smem = (size_t)(1024 + 9 * NB) * sizeof(double);
         backsolve_kernel<256><<<n_blocks, 256, smem, st>>>(blocks, order, L, inv_sqrt_n, beta_s, beta_l);
