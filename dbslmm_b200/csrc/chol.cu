@@ -156,7 +156,17 @@ __device__ __forceinline__ void mm_tile8(const double* A, int sa, const double* 
                                          double scale, int lane) {
     const int g = lane >> 2, t = lane & 3;
     double c0 = 0.0, c1 = 0.0;
-    for (int k0 = kb; k0 < ke; k0 += 4) dmma884(c0, c1, A[g * sa + k0 + t], B[(k0 + t) * sb + g]);
+    // at most 8 k-steps (K <= 32): operands are fetched up front (zeros outside [kb, ke)), then 8 unconditional DMMAs
+    double a[8], b[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int k0 = kb + 4 * i;
+        const bool v = k0 < ke;
+        a[i] = v ? A[g * sa + k0 + t] : 0.0;
+        b[i] = v ? B[(k0 + t) * sb + g] : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dmma884(c0, c1, a[i], b[i]);
     C[g * sc + 2 * t] = scale * c0;
     C[g * sc + 2 * t + 1] = scale * c1;
 }
@@ -356,9 +366,10 @@ __device__ __forceinline__ void diag_body(const BlockDesc& bd, int blk, int k, c
     // ... and W_kk as a dense 64x64 lower-triangular tile for the panel kernel of this step, which
     // streams it into shared memory with cp.async while its GEMM loop runs
     double* wb = wbuf + (size_t)blk * (NB * NB);
+    // (8x8 blocks strictly above the diagonal are never read by the TRSM: skip them)
     for (int idx = tid; idx < NB * NB; idx += CHOL_THREADS) {
         const int a = idx >> 6, b = idx & 63;
-        wb[idx] = (b <= a) ? Wf[a * DT + b] : 0.0;
+        if ((b >> 3) <= (a >> 3)) wb[idx] = (b <= a) ? Wf[a * DT + b] : 0.0;
     }
     DIAG_STAMP(23);
 }
@@ -620,6 +631,11 @@ chol_panel_kernel(const BlockDesc* __restrict__ blocks, const int4* __restrict__
                   int32_t group_base, int32_t* __restrict__ status, int32_t* __restrict__ dflag, int32_t fuse_end) {
     extern __shared__ __align__(16) double smem[];
     __shared__ int s_last;
+    // Programmatic dependent launch (only when the host set the launch attribute; no-ops otherwise): the CTAs of step
+    // k+1 become resident while step k is still running -- they take SM slots as lower-priority work frees them --
+    // and block here until step k has completed and its writes are visible.  Everything below reads step k's output.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if ((int)blockIdx.x < n_diag_first) {
         const int blk = diag_items[blockIdx.x];
         const BlockDesc bd = blocks[blk];
@@ -889,13 +905,21 @@ cudaError_t launch_chol_diag(const BlockDesc* blocks, const int32_t* items, int3
 cudaError_t launch_chol_panel(const BlockDesc* blocks, const int4* items, int32_t n_items, const int32_t* diag_items,
                               int32_t n_diag_first, int32_t k, const double* sigma, double* L, double* wbuf, int64_t wstride,
                               bool fuse_end, double ridge, double* scratch, int32_t* counters, int32_t group_base,
-                              int32_t* status, int32_t* dflag, cudaStream_t st) {
+                              int32_t* status, int32_t* dflag, bool pdl, cudaStream_t st) {
     if (n_items + n_diag_first == 0) return cudaSuccess;
     const int64_t wpar = (k & 1) * wstride, wnext = ((k + 1) & 1) * wstride;
-    chol_panel_kernel<<<n_items + n_diag_first, CHOL_THREADS, SMEM_CHOL, st>>>(blocks, items, diag_items, n_diag_first, k, sigma, L,
-                                                                             wbuf, wpar, wnext, ridge, scratch, counters,
-                                                                             group_base, status, dflag, fuse_end ? 1 : 0);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(n_items + n_diag_first));
+    cfg.blockDim = dim3(CHOL_THREADS);
+    cfg.dynamicSmemBytes = SMEM_CHOL;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, chol_panel_kernel, blocks, items, diag_items, n_diag_first, k, sigma, L, wbuf, wpar, wnext, ridge,
+                              scratch, counters, group_base, status, dflag, (int32_t)(fuse_end ? 1 : 0));
 }
 // Back substitution of `n_blocks` blocks listed in `order`: an 8-CTA cluster per block for the big size
 // classes (mp > 1024), one 256-thread CTA per block otherwise.

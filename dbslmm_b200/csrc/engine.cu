@@ -122,6 +122,10 @@ struct dbslmm_b200_handle {
     // Each class (batch) has its own stream: the step loops interleave and fill each other's thin last steps.
     std::vector<int> cls_bounds = {8, 16, 32};
     int splitk_max = 16, splitk_min_blocks = 2;  // split-K: at most this many slices, each at least this many 64-deep K blocks
+    // programmatic dependent launch for chain-bound batches (0 = never; DBSLMM_B200_PDL=0.8 turns it on for batches
+    // whose chain rivals the fit's throughput time).  Measured on an 8-GPU shard: the longest chain shrinks by 4 %, but
+    // the waiting CTAs hold SM slots the bulk batches need, and the streaming fit gets slower -- off by default.
+    double pdl_ratio = 0.0;
     int defer_max_ctas = 296;                    // steps with at most this many CTAs take their diagonal tile first (see StepList)
     // reference panel
     DevBuf bed, stats;
@@ -500,6 +504,7 @@ int dbslmm_b200_create(int device, dbslmm_b200_handle** out) {
         if (std::sscanf(e, "%d,%d", &a, &b) == 2 && a >= 1 && a <= 255 && b >= 1) { h->splitk_max = a; h->splitk_min_blocks = b; }
     }
     if (const char* e = std::getenv("DBSLMM_B200_DEFER_CTAS")) h->defer_max_ctas = std::atoi(e);
+    if (const char* e = std::getenv("DBSLMM_B200_PDL")) h->pdl_ratio = std::atof(e);
     if (const char* e = std::getenv("DBSLMM_B200_CLASSES")) {     // e.g. "4,8,12,16,32"
         std::vector<int> b;
         for (const char* p = e; *p;) { char* q; long v = std::strtol(p, &q, 10); if (q == p) break; if (v > 0) b.push_back((int)v); p = (*q == ',') ? q + 1 : q; }
@@ -1002,6 +1007,11 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
             for (int bi = 0; bi < nbatch; ++bi) {
                 const Batch& B = P.batches[bi];
                 cudaStream_t cs = h->b_stream[bi];
+                // A batch whose dependency chain (steps x ~50 us) rivals the whole fit's throughput time is latency-bound:
+                // its steps are launched programmatically dependent, so the next step's CTAs are resident (and waiting)
+                // before the current step ends instead of queueing for SM slots behind lower-priority tiles afterwards.
+                const bool pdl_batch = h->pdl_ratio > 0.0 &&
+                                       (double)B.steps.size() * 50.0 > h->pdl_ratio * (P.solve_flops / 17.0e6);
                 // a streaming fit's first fold starts each batch as soon as ITS Gram is done
                 CU_TRY(h, cudaStreamWaitEvent(cs, (streaming && f == 0) ? h->ev_gram[bi] : h->ev_fork, 0));
                 for (size_t k = 0; k < B.steps.size(); ++k) {
@@ -1020,7 +1030,7 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
                                                 deferred_here ? s.n_diag : 0, (int32_t)k, (const double*)h->sigma.p,
                                                 (double*)h->lbuf.p, (double*)h->wbuf.p, wstride, h->fuse_diag && !s.defer, ridge,
                                                 (double*)h->scratch.p + B.scratch_off, (int32_t*)h->counters.p, s.group_base,
-                                                d_status, (int32_t*)h->dflag.p, cs));
+                                                d_status, (int32_t*)h->dflag.p, pdl_batch && k > 0, cs));
                     ++n_launch;
                     ++n_chol_launch;
                 }

@@ -56,7 +56,7 @@ cudaError_t launch_chol_diag(const BlockDesc* blocks, const int32_t* items, int3
 cudaError_t launch_chol_panel(const BlockDesc* blocks, const int4* items, int32_t n_items, const int32_t* diag_items,
                               int32_t n_diag_first, int32_t k, const double* sigma, double* L, double* wbuf, int64_t wstride,
                               bool fuse_end, double ridge, double* scratch, int32_t* counters, int32_t group_base,
-                              int32_t* status, int32_t* dflag, cudaStream_t st);
+                              int32_t* status, int32_t* dflag, bool pdl, cudaStream_t st);
 cudaError_t launch_backsolve(const BlockDesc* blocks, const int32_t* order, int32_t n_blocks, bool big,
                              const double* L, double inv_sqrt_n, double* beta_s, double* beta_l, int32_t max_mp,
                              cudaStream_t st);
