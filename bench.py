@@ -9,8 +9,8 @@ so the job size is fixed: "strong" scaling as BASELINE.json's config asks ("shar
 1/2/4/8 GPUs"); `--scaling weak` gives every rank its own genome instead.
 
   value : blocks/s from the library's CUDA-event device time (bed, plan and z resident in HBM)
-  e2e   : blocks/s through ONE C-ABI call per step from HOST buffers (fit_args.bed: batched panel H2D overlapped with the fit,
-          (plan/z H2D, kernels, beta D2H), wall clock around the synchronous calls
+  e2e   : blocks/s through ONE C-ABI call per step from HOST buffers (fit_args.bed: batched panel H2D overlapped with the
+          fit, plan/z H2D, kernels, beta D2H), wall clock around the synchronous calls
   --impl reference : the reference's CPU path on this box's host cores on a bounded sample.
 """
 import argparse
