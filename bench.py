@@ -279,7 +279,9 @@ def main():
         torch.cuda.set_device(dev)
         w = build_workload(args, torch, dev, args.seed)
         threads = min(os.cpu_count() or 1, 100)                 # reference caps -t at 100 (dbslmm.cpp:224)
-        blocks, stride = cpu_sample(w, args.cpu_seconds, threads)
+        # every step is a bounded sample; the sample shrinks with the step count so the whole run stays within ~3 minutes
+        per_step = max(1.5, min(args.cpu_seconds, 150.0 / (args.steps + min(args.warmup, 1))))
+        blocks, stride = cpu_sample(w, per_step, threads)
         times = []
         kind = "port"
         for i in range(min(args.warmup, 1) + args.steps):       # one warm-up pass is enough on the CPU
