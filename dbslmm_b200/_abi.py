@@ -103,6 +103,7 @@ class Engine:
         self.n_snp = 0
         self.n_ref = 0
         self._keep = []
+        self._outbuf = {}
 
     def close(self):
         if getattr(self, "h", None):
@@ -146,7 +147,7 @@ class Engine:
         return owner, cost
 
     def fit(self, s_off, s_pos, s_z, l_off=None, l_pos=None, l_z=None, *, sigma_s, n_obs, tau=0.8,
-            solver=SOLVER_CHOLESKY, flags=0, test=None, bed=None, n_ref=None):
+            solver=SOLVER_CHOLESKY, flags=0, test=None, bed=None, n_ref=None, reuse_outputs=False):
         """Returns dict(beta_s[n_folds, S], beta_l[n_folds, L], status[n_blocks], n_bad, timing[, variance]).
         test = dict(bed=uint8[n_snp_t, pitch_t], n_total=int, indicator=int[n_total], s_tpos=int[S], l_tpos=int[L])
         switches the fork's asymptotic-variance side channel on: variance[n_folds, n_blocks, n_test].
@@ -158,12 +159,19 @@ class Engine:
         nb = s_off.size - 1
         sig = np.atleast_1d(np.asarray(sigma_s, np.float64)).copy()
         nf = sig.size
-        beta_s = np.zeros((nf, s_pos.size), np.float64)
+        def out(name, shape):
+            if not reuse_outputs:
+                return np.zeros(shape, np.float64)
+            buf = self._outbuf.get(name)
+            if buf is None or buf.shape != shape:
+                buf = self._outbuf[name] = np.zeros(shape, np.float64)
+            return buf
+        beta_s = out("beta_s", (nf, s_pos.size))
         if l_off is not None:
             l_off = np.ascontiguousarray(l_off, np.int32)
             l_pos = np.ascontiguousarray(l_pos, np.int32)
             l_z = np.ascontiguousarray(l_z, np.float64)
-            beta_l = np.zeros((nf, max(l_pos.size, 1)), np.float64)
+            beta_l = out("beta_l", (nf, max(l_pos.size, 1)))
             nl = l_pos.size
         else:
             beta_l = None

@@ -669,12 +669,27 @@ int upload_prepare(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, const P
     const int nb = P.n_blocks;
     const int64_t n_snp = h->n_snp;
     std::vector<int32_t> lo((size_t)std::max(nb, 1), INT32_MAX), hi((size_t)std::max(nb, 1), -1);
-    for (int b = 0; b < nb; ++b) {
-        int32_t l = INT32_MAX, u = -1;
-        for (int j = a->s_off[b]; j < a->s_off[b + 1]; ++j) { const int32_t p = a->s_pos[j]; l = std::min(l, p); u = std::max(u, p); }
-        if (a->l_off) for (int j = a->l_off[b]; j < a->l_off[b + 1]; ++j) { const int32_t p = a->l_pos[j]; l = std::min(l, p); u = std::max(u, p); }
-        if (u >= 0 && (l < 0 || u >= n_snp)) return fail(h, DBSLMM_B200_ERR_ARG, "fit: SNP row out of range of the .bed");
-        lo[b] = l; hi[b] = u;
+    {
+        // row range of every block: the only O(#SNPs) scan before the first copy can be issued -> a few host threads
+        std::atomic<int> bad{0};
+        auto scan = [&](int b0, int b1) {
+            for (int b = b0; b < b1; ++b) {
+                int32_t l = INT32_MAX, u = -1;
+                for (int j = a->s_off[b]; j < a->s_off[b + 1]; ++j) { const int32_t p = a->s_pos[j]; l = std::min(l, p); u = std::max(u, p); }
+                if (a->l_off) for (int j = a->l_off[b]; j < a->l_off[b + 1]; ++j) { const int32_t p = a->l_pos[j]; l = std::min(l, p); u = std::max(u, p); }
+                if (u >= 0 && (l < 0 || u >= n_snp)) bad.store(1);
+                lo[b] = l; hi[b] = u;
+            }
+        };
+        const int64_t tot = P.tot_s + P.tot_l;
+        const int nthr = (int)std::max<int64_t>(1, std::min<int64_t>({4, (int64_t)std::thread::hardware_concurrency(), tot / 131072}));
+        if (nthr == 1) scan(0, nb);
+        else {
+            std::vector<std::thread> th;
+            for (int t = 0; t < nthr; ++t) th.emplace_back(scan, (int)((int64_t)nb * t / nthr), (int)((int64_t)nb * (t + 1) / nthr));
+            for (std::thread& x : th) x.join();
+        }
+        if (bad.load()) return fail(h, DBSLMM_B200_ERR_ARG, "fit: SNP row out of range of the .bed");
     }
     typedef UploadPlan::Range Range;
     U.per_batch.assign(P.batches.size(), std::vector<Range>());
