@@ -11,13 +11,16 @@
 // (the Schur complement S is the trailing block of K's Cholesky factor), so every block --
 // LMM or DBSLMM mode -- is one factorisation and one right-hand side.
 //
-// Algorithm: left-looking tile Cholesky, panel width 64, batched over ALL blocks of a size
-// class per panel step k (two launches per step):
-//   chol_diag_kernel  : potrf of the (already updated) 64x64 diagonal tile T_kk and W_kk = L_kk^-1;
-//                       L_kk -> lower, W_kk^T -> upper triangle of the tile.
-//   chol_panel_kernel : for each 128-row macro tile below: C = K_ik - L_i,0:k L_k,0:k^T (DMMA,
-//                       cp.async 3-stage ring), L_ik = C W_kk^T (DMMA) -- TRSM as a GEMM -- and the
-//                       look-ahead T_ii -= L_ik L_ik^T on the macro tile's own diagonal tiles.
+// Algorithm: left-looking tile Cholesky, panel width 64, batched over ALL blocks of a batch (a size class, or an
+// upload region of a streaming fit) per panel step k -- ONE launch per step:
+//   chol_panel_kernel : for each 128-row macro tile below the diagonal tile: -C = L_i,0:k L_k,0:k^T - K_ik (DMMA,
+//                       cp.async 3-stage ring), -L_ik = (-C) W_kk^T (DMMA, TRSM as a GEMM fed from the accumulator
+//                       fragments), the look-ahead T_ii -= L_ik L_ik^T on the macro tile's own diagonal tiles, and the
+//                       factorisation of the diagonal tile of panel k+1 (diag_body): by the CTA of macro tile 0 at the
+//                       end of a multi-wave step, or by extra CTAs at the head of step k+1 when that step is
+//                       chain-bound (they overlap its main loops and publish W through a flag).
+//   chol_diag_kernel  : diag_body on its own, for k = 0: potrf of the 64x64 diagonal tile T_kk and W_kk = L_kk^-1;
+//                       L_kk -> lower, W_kk^T -> upper triangle of the tile, W_kk dense for the panel kernel.
 // The z-scores ride along as matrix row `mp`, so that row of L ends up holding y = L^-1 z;
 // backsolve_kernel then solves L^T x = y per block and writes beta = x / sqrt(N).
 // Matrices are row-major, lower triangle, ld = mp (m padded to 8 with identity rows).

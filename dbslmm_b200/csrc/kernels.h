@@ -44,12 +44,9 @@ cudaError_t launch_fill_z(const BlockDesc* blocks, const int32_t* list, int32_t 
                           cudaStream_t st);
 
 // chol.cu
-struct CholStep {               // work lists of one panel step (device pointers)
-    const int32_t* diag_blk;    // blocks active at this step
-    int32_t n_diag;
-    const int4* panel_items;    // (block, row macro-tile, slice | nslices << 8, split group) below the diagonal tile
-    int32_t n_panel;
-};
+// Work lists of one panel step (device pointers): `items` of launch_chol_diag / `diag_items` = blocks active at the step;
+// `items` of launch_chol_panel = int4 (block, row macro tile, slice | nslices << 8, split-K group) per CTA, macro tile 0
+// of every block first.
 cudaError_t launch_chol_diag(const BlockDesc* blocks, const int32_t* items, int32_t n_items, int32_t k,
                              const double* sigma, double* L, double* wbuf, int64_t wstride, double ridge,
                              int32_t* status, cudaStream_t st);
