@@ -48,7 +48,8 @@ class FitArgs(C.Structure):
                 ("test_bed", C.c_void_p), ("test_n_snp", C.c_int64), ("test_n_total", C.c_int32),
                 ("test_indicator", C.c_void_p), ("s_tpos", C.c_void_p), ("l_tpos", C.c_void_p),
                 ("variance_out", C.c_void_p),
-                ("bed", C.c_void_p), ("bed_n_snp", C.c_int64), ("bed_n_ref", C.c_int32)]
+                ("bed", C.c_void_p), ("bed_n_snp", C.c_int64), ("bed_n_ref", C.c_int32),
+                ("quadform_out", C.c_void_p)]
 
 
 _lib = None
@@ -203,6 +204,20 @@ class Engine:
         if var is not None:
             out["variance"] = var
         return out
+
+    def quadform(self, off, pos, z, tau=1.0):
+        """z_b' Sigma_b z_b per block (Sigma_b = tau X'X/n + (1-tau) I of the block's SNPs): the `deno` of the reference's
+        external-validation tool `valid` (scr/validate.cpp:255-258, tau = 1).  Returns float64[n_blocks]."""
+        off = np.ascontiguousarray(off, np.int32)
+        pos = np.ascontiguousarray(pos, np.int32)
+        z = np.ascontiguousarray(z, np.float64)
+        nb = off.size - 1
+        out = np.zeros(max(nb, 1), np.float64)
+        a = FitArgs()
+        a.n_blocks, a.s_off, a.s_pos, a.s_z = nb, off.ctypes.data, _ptr(pos), _ptr(z)
+        a.tau, a.solver, a.quadform_out = float(tau), SOLVER_CHOLESKY, out.ctypes.data
+        self._check(self.lib.dbslmm_b200_fit(self.h, C.byref(a)), "fit(quadform)")
+        return out[:nb]
 
     def score(self, bed_val, n_val, pos, beta, flip=None):
         """PRS over a validation panel: returns (scores[n_folds, n_val], kernel_ms)."""

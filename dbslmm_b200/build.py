@@ -15,6 +15,7 @@ HOST = os.path.join(PKG, "host")
 BUILD = os.path.join(ROOT, "build")
 LIB = os.path.join(PKG, "libdbslmm_b200.so")
 CLI = os.path.join(BUILD, "dbslmm")
+VALID_CLI = os.path.join(BUILD, "valid")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 GXX = "/usr/bin/g++"
@@ -70,6 +71,11 @@ def build_cli(force=False):
     deps = srcs + [LIB, os.path.join(HOST, "ingest.hpp"), os.path.join(ROOT, "include", "dbslmm_b200.h")]
     if force or _newer(CLI, deps):
         _run([GXX, "-O2", "-std=c++17", "-pthread", "-I", os.path.join(ROOT, "include"), "-o", CLI] + srcs +
+             ["-L", PKG, "-ldbslmm_b200", "-Wl,-rpath,$ORIGIN/../dbslmm_b200", "-Wl,-rpath," + PKG])
+    # the reference's second binary, `valid` (external validation)
+    vsrcs = [os.path.join(HOST, "valid_main.cpp"), os.path.join(HOST, "ingest.cpp")]
+    if os.path.exists(vsrcs[0]) and (force or _newer(VALID_CLI, vsrcs + deps)):
+        _run([GXX, "-O2", "-std=c++17", "-pthread", "-I", os.path.join(ROOT, "include"), "-o", VALID_CLI] + vsrcs +
              ["-L", PKG, "-ldbslmm_b200", "-Wl,-rpath,$ORIGIN/../dbslmm_b200", "-Wl,-rpath," + PKG])
     return CLI
 

@@ -252,6 +252,11 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
     int n_test = 0;
     if (a->test_bed) for (int i = 0; i < a->test_n_total; ++i) n_test += (a->test_indicator[i] != 0);
     P.n_test = n_test;
+    // build_plan may run twice on the same batches (speculative no-missing plan, then the real flags): start the
+    // accumulated quantities from zero every time -- the split-K scratch offsets are derived from them
+    P.scratch_doubles = 0;
+    P.gram_ops = P.solve_flops = 0.0;
+    P.max_mp = 0;
     const int64_t n_snp = h->n_snp;
     int64_t goff = 0, croff = 0, moff = 0;
     // layout order: block index (resident panel) or batch order (streaming: a batch's rows are one range)
@@ -754,6 +759,7 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
     const bool pcg = (a->solver == DBSLMM_B200_SOLVER_PCG);
     const bool full = pcg || (a->flags & DBSLMM_B200_FLAG_FULL_SIGMA);
     const bool keep_int = (a->flags & DBSLMM_B200_FLAG_KEEP_INT_GRAM) != 0;
+    const bool quad = a->quadform_out != nullptr;          // `valid`: z' Sigma z per block instead of the solve
 
     Trace tr;
     UploadPlan U;
@@ -792,20 +798,21 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
     if (!streaming) { int rc = ensure_stats(h); if (rc != DBSLMM_B200_OK) return rc; }
     const int nb = P.n_blocks;
     const int nbatch = (int)P.batches.size();
-    const size_t nfold = (size_t)a->n_folds;
+    const size_t nfold = quad ? 1 : (size_t)a->n_folds;
 
     // ---- workspace
     CU_TRY(h, h->planblob.ensure(P.blob_bytes + 256));
     CU_TRY(h, h->codes.ensure((size_t)std::max<int64_t>(P.n_code_rows, 1) * h->n_pad));
     CU_TRY(h, h->sigma.ensure(sizeof(double) * (size_t)std::max<int64_t>(P.mat_doubles, 1)));
-    if (!pcg) CU_TRY(h, h->lbuf.ensure(sizeof(double) * (size_t)std::max<int64_t>(P.mat_doubles, 1)));
+    if (!pcg && !quad) CU_TRY(h, h->lbuf.ensure(sizeof(double) * (size_t)std::max<int64_t>(P.mat_doubles, 1)));
     CU_TRY(h, h->rowN.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(P.n_snp_rows, 1)));
     CU_TRY(h, h->rowS.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(P.n_snp_rows, 1)));
     CU_TRY(h, h->rowR.ensure(sizeof(double) * (size_t)std::max<int64_t>(P.n_snp_rows, 1)));
     const size_t n_out = (size_t)(P.tot_s + P.tot_l);
-    CU_TRY(h, h->beta.ensure(sizeof(double) * std::max<size_t>(n_out * nfold, 1)));
+    const size_t n_res = quad ? (size_t)nb : n_out * nfold;          // doubles coming back: betas of all folds, or one z'Sigma z per block
+    CU_TRY(h, h->beta.ensure(sizeof(double) * std::max<size_t>(n_res, 1)));
     CU_TRY(h, h->status.ensure(sizeof(int32_t) * (size_t)std::max(2 * nb, 1)));
-    if (!pcg) {
+    if (!pcg && !quad) {
         CU_TRY(h, h->scratch.ensure(sizeof(double) * (size_t)std::max<int64_t>(P.scratch_doubles, 1)));
         CU_TRY(h, h->wbuf.ensure(2 * sizeof(double) * 64 * 64 * (size_t)std::max(nb, 1)));   // two parities, see launch_chol_diag
         CU_TRY(h, h->counters.ensure(sizeof(int32_t) * (size_t)std::max(P.n_groups, 1)));
@@ -816,7 +823,7 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
         CU_TRY(h, h->intA.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(P.mat_doubles, 1)));
         CU_TRY(h, h->intN.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(P.mat_doubles, 1)));
     }
-    const size_t out_bytes = sizeof(double) * n_out * nfold + sizeof(int32_t) * (size_t)(2 * nb);
+    const size_t out_bytes = sizeof(double) * n_res + sizeof(int32_t) * (size_t)(2 * nb);
     CU_TRY(h, h->h_out.ensure(out_bytes + 128));
 
     uint8_t* dblob = (uint8_t*)h->planblob.p;   // (re-pointed below if the plan has to be rebuilt)
@@ -895,8 +902,8 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
     }
     CU_TRY(h, cudaEventRecord(h->ev[1], st));
 
-    if (!pcg && P.n_groups > 0) CU_TRY(h, cudaMemsetAsync(h->counters.p, 0, sizeof(int32_t) * (size_t)P.n_groups, st));
-    if (!pcg) CU_TRY(h, cudaMemsetAsync(h->dflag.p, 0, sizeof(int32_t) * (size_t)std::max(nb, 1), st));
+    if (!pcg && !quad && P.n_groups > 0) CU_TRY(h, cudaMemsetAsync(h->counters.p, 0, sizeof(int32_t) * (size_t)P.n_groups, st));
+    if (!pcg && !quad) CU_TRY(h, cudaMemsetAsync(h->dflag.p, 0, sizeof(int32_t) * (size_t)std::max(nb, 1), st));
     // ---- decode + gram
     GramArgs g;
     CUtensorMap tmap;
@@ -1009,8 +1016,13 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
 
     // ---- solve, once per heritability fold (Sigma is shared: only the ridge changes)
     float chol_ms_total = 0.f;
-    const double inv_sqrt_n = 1.0 / std::sqrt((double)a->n_obs);
-    for (int f = 0; f < a->n_folds; ++f) {
+    const double inv_sqrt_n = quad ? 0.0 : 1.0 / std::sqrt((double)a->n_obs);
+    if (quad && nb > 0) {
+        // scr/validate.cpp:255-258: deno_b = z1' Sigma_b z1.  The per-block results take the place of the betas.
+        CU_TRY(h, launch_quadform(d_blocks, nb, (const double*)h->sigma.p, d_z, d_beta, st));
+        ++n_launch;
+    }
+    for (int f = 0; f < a->n_folds && !quad; ++f) {
         const double ridge = 1.0 / (a->sigma_s[f] * (double)a->n_obs);    // dbslmmfit.cpp:712 / :759
         double* bs = d_beta + (size_t)f * n_out;
         double* bl = bs + P.tot_s;
@@ -1112,8 +1124,8 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
 
     // ---- download
     uint8_t* hout = (uint8_t*)h->h_out.p;
-    if (n_out) CU_TRY(h, cudaMemcpyAsync(hout, d_beta, sizeof(double) * n_out * nfold, cudaMemcpyDeviceToHost, st));
-    CU_TRY(h, cudaMemcpyAsync(hout + sizeof(double) * n_out * nfold, d_status, sizeof(int32_t) * (size_t)(2 * nb),
+    if (n_res) CU_TRY(h, cudaMemcpyAsync(hout, d_beta, sizeof(double) * n_res, cudaMemcpyDeviceToHost, st));
+    CU_TRY(h, cudaMemcpyAsync(hout + sizeof(double) * n_res, d_status, sizeof(int32_t) * (size_t)(2 * nb),
                               cudaMemcpyDeviceToHost, st));
     if (d_var) CU_TRY(h, cudaMemcpyAsync(a->variance_out, d_var, sizeof(double) * (size_t)a->n_folds * nb * P.n_test,
                                          cudaMemcpyDeviceToHost, st));
@@ -1148,11 +1160,12 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
     }
     if (streaming && *h_flag != 0) { P.valid = false; return kRetryResident; }   // missing calls: see fit_impl's header
     const double* hb = (const double*)hout;
-    for (int f = 0; f < a->n_folds; ++f) {
+    if (quad && nb > 0) std::memcpy(a->quadform_out, hb, sizeof(double) * (size_t)nb);
+    for (int f = 0; f < a->n_folds && !quad; ++f) {
         std::memcpy(a->beta_s_out + (size_t)f * P.tot_s, hb + (size_t)f * n_out, sizeof(double) * (size_t)P.tot_s);
         if (P.tot_l) std::memcpy(a->beta_l_out + (size_t)f * P.tot_l, hb + (size_t)f * n_out + P.tot_s, sizeof(double) * (size_t)P.tot_l);
     }
-    const int32_t* hs = (const int32_t*)(hout + sizeof(double) * n_out * nfold);
+    const int32_t* hs = (const int32_t*)(hout + sizeof(double) * n_res);
     int n_bad = 0;
     for (int b = 0; b < nb; ++b) {
         if (a->block_status_out) a->block_status_out[b] = hs[b];
@@ -1171,7 +1184,7 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
         cudaEventElapsedTime(&t->total_ms, h->ev[0], h->ev[5]);
         t->chol_ms = chol_ms_total;
         for (int c = 0; c < kNumClasses; ++c) t->class_ms[c] = 0.f;
-        for (int bi = 0; bi < nbatch && !pcg && !(streaming && a->n_folds == 1); ++bi) {
+        for (int bi = 0; bi < nbatch && !pcg && !quad && !(streaming && a->n_folds == 1); ++bi) {
             float ms = 0.f;
             cudaEventElapsedTime(&ms, h->ev_fork, h->ev_cend[bi]);
             const int slot = std::min(P.batches[bi].cls, kNumClasses - 1);
@@ -1180,7 +1193,7 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
         t->n_launches = n_launch;
         t->n_chol_launches = n_chol_launch;
         t->gram_ops = P.gram_ops;
-        t->solve_flops = P.solve_flops * (double)a->n_folds;
+        t->solve_flops = quad ? 0.0 : P.solve_flops * (double)a->n_folds;
         t->decode_bytes = P.decode_bytes;
     }
     return n_bad;
@@ -1194,8 +1207,11 @@ int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
     if (!h || !a) return DBSLMM_B200_ERR_ARG;
     if (!a->bed && h->n_snp == 0) return fail(h, DBSLMM_B200_ERR_STATE, "fit before load_bed (and no fit_args.bed)");
     if (a->bed && (a->bed_n_snp <= 0 || a->bed_n_ref <= 1)) return fail(h, DBSLMM_B200_ERR_ARG, "fit: bad bed_n_snp / bed_n_ref");
-    if (a->n_blocks < 0 || !a->s_off || a->n_folds < 1 || !a->sigma_s || a->n_obs <= 0 || !a->beta_s_out)
+    const bool quad = a->quadform_out != nullptr;
+    if (a->n_blocks < 0 || !a->s_off || (!quad && (a->n_folds < 1 || !a->sigma_s || a->n_obs <= 0 || !a->beta_s_out)))
         return fail(h, DBSLMM_B200_ERR_ARG, "fit: bad arguments");
+    if (quad && (a->l_off || a->test_bed || a->solver != DBSLMM_B200_SOLVER_CHOLESKY))
+        return fail(h, DBSLMM_B200_ERR_ARG, "fit: quadform_out takes small-effect lists only, no variance side channel, default solver");
     if (a->n_blocks > 0 && a->s_off[a->n_blocks] > 0 && (!a->s_pos || !a->s_z))
         return fail(h, DBSLMM_B200_ERR_ARG, "fit: s_pos/s_z missing");
     if (a->l_off && a->l_off[a->n_blocks] > 0 && (!a->l_pos || !a->l_z || !a->beta_l_out))
@@ -1203,7 +1219,7 @@ int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
     if (!(a->tau > 0.0 && a->tau <= 1.0)) return fail(h, DBSLMM_B200_ERR_ARG, "fit: tau must be in (0,1]");
     if (a->solver != DBSLMM_B200_SOLVER_CHOLESKY && a->solver != DBSLMM_B200_SOLVER_PCG)
         return fail(h, DBSLMM_B200_ERR_ARG, "fit: unknown solver");
-    for (int f = 0; f < a->n_folds; ++f)
+    for (int f = 0; f < a->n_folds && !quad; ++f)
         if (!(a->sigma_s[f] > 0.0)) return fail(h, DBSLMM_B200_ERR_ARG, "fit: sigma_s must be > 0");
     const bool want_var = a->test_bed != nullptr;
     if (want_var) {
@@ -1218,7 +1234,7 @@ int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
 
     // ---- the panel comes with the call (what DBSLMMFIT::est does with its bed_str argument)
     if (h->bed_pending) { CU_TRY(h, cudaEventSynchronize(h->ev_bed)); h->bed_pending = false; }
-    const bool can_stream = !want_var && a->solver == DBSLMM_B200_SOLVER_CHOLESKY && !(a->flags & DBSLMM_B200_FLAG_PLAN_CACHED) &&
+    const bool can_stream = !want_var && !quad && a->solver == DBSLMM_B200_SOLVER_CHOLESKY && !(a->flags & DBSLMM_B200_FLAG_PLAN_CACHED) &&
                             a->n_blocks > 0 && h->stream_bed && !h->missing_hint;
     if (!can_stream) {
         int rc = dbslmm_b200_load_bed(h, a->bed, a->bed_n_snp, a->bed_n_ref);

@@ -66,6 +66,10 @@ cudaError_t launch_test_rows(const BlockDesc* blocks, int32_t n_blocks, const ui
 cudaError_t launch_variance(const BlockDesc* blocks, int32_t n_blocks, int32_t n_test, const double* sigma,
                             const double* Lbuf, double sigma_s, double n_obs, double* out, cudaStream_t st);
 
+// z' Sigma z per block from the lower triangle of Sigma (variance.cu); z = the plan's z array (block-ordered SNP rows)
+cudaError_t launch_quadform(const BlockDesc* blocks, int32_t n_blocks, const double* sigma, const double* z, double* out,
+                            cudaStream_t st);
+
 // score.cu
 cudaError_t launch_prs(const uint8_t* bed, int32_t n_val, const SnpStat* stats, const int32_t* pos, const uint8_t* flip,
                        const double* beta, int64_t beta_stride, int32_t n_scored, int32_t nf, int32_t n_chunks,

@@ -127,4 +127,47 @@ cudaError_t launch_variance(const BlockDesc* blocks, int32_t n_blocks, int32_t n
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------
+// Quadratic form of the reference's `valid` tool (scr/validate.cpp:255-258): deno_b = z' Sigma_b z from the LOWER
+// triangle of Sigma_b (as the Gram kernels write it): sum_i z_i (Sigma_ii z_i + 2 sum_{j<i} Sigma_ij z_j).
+// One CTA per block, one warp per row (coalesced row reads), fixed-order reductions.  HBM-bound: 4 m^2 bytes.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+quadform_kernel(const BlockDesc* __restrict__ blocks, const double* __restrict__ sigma, const double* __restrict__ z,
+                double* __restrict__ out) {
+    __shared__ double wsum[8];
+    const BlockDesc bd = blocks[blockIdx.x];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const double* S = sigma + bd.moff;
+    const double* zb = z + bd.goff;
+    double acc = 0.0;                                  // lane 0 of each warp: sum over its rows
+    for (int i = warp; i < bd.m; i += 8) {
+        const double* row = S + (size_t)i * bd.ld;
+        double p0 = 0.0, p1 = 0.0;
+        int j = lane;
+        for (; j + 32 < i; j += 64) { p0 += row[j] * zb[j]; p1 += row[j + 32] * zb[j + 32]; }
+        if (j < i) p0 += row[j] * zb[j];
+        double p = p0 + p1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+        const double zi = zb[i];
+        acc += zi * (row[i] * zi + 2.0 * p);
+    }
+    if (lane == 0) wsum[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += wsum[w];
+        out[blockIdx.x] = t;
+    }
+}
+
+cudaError_t launch_quadform(const BlockDesc* blocks, int32_t n_blocks, const double* sigma, const double* z, double* out,
+                            cudaStream_t st) {
+    if (n_blocks == 0) return cudaSuccess;
+    quadform_kernel<<<n_blocks, 256, 0, st>>>(blocks, sigma, z, out);
+    return cudaGetLastError();
+}
+
 }  // namespace dbslmm

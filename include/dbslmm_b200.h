@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DBSLMM_B200_ABI_VERSION 3
+#define DBSLMM_B200_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define DBSLMM_B200_API __attribute__((visibility("default")))
@@ -108,6 +108,11 @@ typedef struct dbslmm_b200_fit_args {
     const uint8_t* bed;             /* or NULL: use the panel loaded by dbslmm_b200_load_bed                   */
     int64_t  bed_n_snp;
     int32_t  bed_n_ref;
+    /* ---- optional: the quadratic form of the reference's external-validation tool `valid` (scr/validate.cpp:225-259,
+     * SURVEY 8f-4) INSTEAD of the solve: quadform_out[b] = z_b' Sigma_b z_b with Sigma_b = tau X'X/n + (1-tau) I of the
+     * block's SNPs (s_pos, s_z; `valid` uses the un-shrunk tau = 1: deno = z1' (X'X/n) z1).  Same decoder and integer
+     * Gram as the fit; no factorisation.  beta_s_out may then be NULL; l_off must be NULL.                            */
+    double*  quadform_out;          /* [n_blocks] or NULL                                                      */
 } dbslmm_b200_fit_args;
 
 #define DBSLMM_B200_FLAG_KEEP_INT_GRAM 1  /* also keep raw int32 Gram planes for dbslmm_b200_get_block_gram */

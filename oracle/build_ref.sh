@@ -18,4 +18,8 @@ $CXX $FLAGS -c "$REF/main_dbslmm.cpp" -o "$OUT/obj/main_dbslmm.o"
 OBJS=""; for s in $SRCS; do OBJS="$OBJS $OUT/obj/$s.o"; done
 $CXX -fopenmp -o "$OUT/dbslmm_ref" "$OUT/obj/main_dbslmm.o" $OBJS
 $CXX $FLAGS -shared -o "$OUT/libref_harness.so" "$HERE/ref_harness.cpp" $OBJS
-echo "built $OUT/dbslmm_ref and $OUT/libref_harness.so"
+# the reference's second binary, `valid` (external validation): its Makefile never builds it, the sources compile as they are
+$CXX $FLAGS -c "$REF/validate.cpp" -o "$OUT/obj/validate.o"
+$CXX $FLAGS -c "$REF/main_valid.cpp" -o "$OUT/obj/main_valid.o"
+$CXX -fopenmp -o "$OUT/valid_ref" "$OUT/obj/main_valid.o" "$OUT/obj/validate.o" "$OUT/obj/dtpr.o" "$OUT/obj/helpers.o"
+echo "built $OUT/dbslmm_ref, $OUT/valid_ref and $OUT/libref_harness.so"

@@ -93,6 +93,58 @@ def sigma(bed, n_ref, pos, tau=0.8):
     return S
 
 
+def valid_block(bed, n_ref, pos, z1, z2):
+    """One block of the external-validation tool `valid` (reference scr/validate.cpp:225-259): the SNPs are decoded and
+    standardised like in the fit (readSNPIm + nomalizeVec, :249-251), Sigma = X'X / n WITHOUT the tau shrinkage
+    (:255-256), nume = z1'z2 (:257), deno = z1' Sigma z1 (:258).  Returns (nume, deno)."""
+    z1 = np.asarray(z1, np.float64)
+    z2 = np.asarray(z2, np.float64)
+    if z1.size == 0:
+        return 0.0, 0.0
+    S = sigma(bed, n_ref, pos, tau=1.0)
+    return float(z1 @ z2), float(z1 @ S @ z1)
+
+
+def valid_run(dbslmm_txt, ext_txt, bim_txt, block_txt, bed, n_ref, maf_max):
+    """File-level restatement of the reference's `valid` tool (scr/validate.cpp:120-265 with the readers and matchers it
+    calls: readDBSLMM dtpr.cpp:223-245, readExt :248-270, matchSumm :411-434, readBim :125-165, matchAll :436-453,
+    the sequential block scan validate.cpp:225-259).  Returns (nume[num_block], deno[num_block])."""
+    dbs = [ln.split(" ") for ln in dbslmm_txt.strip().split("\n") if ln]
+    ext = {}
+    for ln in ext_txt.strip().split("\n"):
+        t = ln.split(" ")
+        if len(t) >= 4 and t[0] not in ext:                         # map::insert keeps the first
+            ext[t[0]] = (t[1], float(t[2]), float(t[3]))
+    comb = []
+    for t in dbs:
+        if t[0] in ext:
+            a1e, mafe, ze = ext[t[0]]
+            comb.append((t[0], t[1], mafe, float(t[2]), ze if a1e == t[1] else -ze))
+    n_snp = bed.shape[0]
+    constr = not abs(maf_max - 1.0) < 1e-10
+    maf = snp_maf(bed, n_snp, n_ref) if constr else np.zeros(n_snp)
+    bim = {}
+    for i, ln in enumerate(bim_txt.strip().split("\n")):
+        t = ln.split("\t")
+        if t[1] not in bim:
+            bim[t[1]] = (i, int(t[3]), t[4], maf[i])
+    rows = []
+    for snp, a1, mafe, z1, z2 in comb:
+        if snp in bim and bim[snp][2] == a1 and abs(bim[snp][3] - mafe) < maf_max:
+            rows.append((bim[snp][1], bim[snp][0], z1, z2))
+    rows.sort(key=lambda r: r[0])
+    blocks = [tuple(int(x) for x in ln.split("\t")[1:3]) for ln in block_txt.strip().split("\n")]
+    nume, deno = np.zeros(len(blocks)), np.zeros(len(blocks))
+    cur = 0
+    for b, (start, end) in enumerate(blocks):
+        pos, z1, z2 = [], [], []
+        while cur < len(rows) and start <= rows[cur][0] < end:     # stops at the first SNP outside the block, like the reference
+            pos.append(rows[cur][1]); z1.append(rows[cur][2]); z2.append(rows[cur][3])
+            cur += 1
+        nume[b], deno[b] = valid_block(bed, n_ref, np.asarray(pos, np.int32), z1, z2)
+    return nume, deno
+
+
 def pcgv(A, b, maxiter=1000, tol=1e-7):
     A = np.asfortranarray(A, dtype=np.float64)
     b = np.ascontiguousarray(b, dtype=np.float64)

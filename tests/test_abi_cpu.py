@@ -24,12 +24,12 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), n
     assert sorted(_abi.EXPORTS) == names
-    assert lib.dbslmm_b200_abi_version() == 3
+    assert lib.dbslmm_b200_abi_version() == 4
 
 
 def test_fit_args_struct_layout_matches_header():
-    # natural alignment on LP64: the ctypes mirror must have the size of the C struct (17 + 7 + 3 fields)
-    assert C.sizeof(_abi.FitArgs) == 208
+    # natural alignment on LP64: the ctypes mirror must have the size of the C struct (17 + 7 + 3 + 1 fields)
+    assert C.sizeof(_abi.FitArgs) == 216
     assert C.sizeof(_abi.Timing) == 80
 
 

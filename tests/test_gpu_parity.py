@@ -34,6 +34,7 @@ CASES = {
     "ragged_missing": ([150, 70, 5, 130, 0, 257], 403, 0.02),
     "odd_pitch": ([90, 33], 125 * 4 - 3, 0.0),        # pitch 125 B: unaligned rows, 3 padding samples
     "wide_n": ([260, 140], 2000, 0.005),
+    "big_missing": ([1500, 40, 700], 403, 0.02),      # split-K steps + the four-plane Gram + the plan rebuilt with missing flags
 }
 
 

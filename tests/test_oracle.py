@@ -189,3 +189,17 @@ def test_variance_oracle_against_live_reference_build(ragged, with_large):
         ref = R.variance_block(b1.path, n, b2.path, 57, ind, int(d["n_obs"]), float(d["sigma_s"]), ps, ps, pl, pl)
     got = O.variance_block(d["bed"], n, tbed, 57, ind, int(d["n_obs"]), float(d["sigma_s"]), ps, ps, pl, pl)
     assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max()
+
+
+def test_valid_tool_restatement_matches_the_reference_binary():
+    """oracle.valid_run against <r2>.txt written by the UNMODIFIED scr/main_valid.cpp + scr/validate.cpp
+    (oracle/_ref/valid_ref, tools/make_golden.py valid_synth), with and without the MAF constraint."""
+    g = np.load(os.path.join(GOLD, "synth_cli.npz"))
+    v = np.load(os.path.join(GOLD, "valid_synth.npz"))
+    for key, maf_max in (("r2_c", 0.2), ("r2_u", 1.0)):
+        nume, deno = O.valid_run(str(g["cli_txt"]), str(v["ext_txt"]), str(g["bim_txt"]), str(g["block_txt"]), g["bed"], int(g["n_ref"]), maf_max)
+        ref = np.array([[float(x) for x in ln.split()] for ln in str(v[key]).strip().split("\n")])
+        assert ref.shape == (3, 2)
+        assert np.abs(nume - ref[:, 0]).max() <= 5e-6 * np.abs(ref[:, 0]).max()       # 6 printed digits
+        assert np.abs(deno - ref[:, 1]).max() <= 5e-6 * np.abs(ref[:, 1]).max()
+    assert str(v["r2_c"]) != str(v["r2_u"])                                              # the MAF filter really removed SNPs

@@ -176,10 +176,60 @@ def synth_cli():
     print("synth_cli: variance", out["cli_variance"].shape, "lines", len(out["cli_txt"].strip().split("\n")))
 
 
+def valid_synth():
+    """The reference's `valid` binary (oracle/_ref/valid_ref = scr/main_valid.cpp + scr/validate.cpp, unmodified, over the
+    shim) on the synthetic chromosome of synth_cli: -d is the reference dbslmm CLI's own output (<eff>.txt), -s an
+    external summary file (snp a1 maf z) that drops some SNPs, flips some alleles (z2 changes sign, dtpr.cpp:424-428)
+    and gives a few SNPs a MAF far from the panel's (filtered by -mafMax, dtpr.cpp:440)."""
+    g = np.load(os.path.join(GOLD, "synth_cli.npz"))
+    rng = np.random.default_rng(20240005)
+    n_ref = int(g["n_ref"])
+    bed = g["bed"]
+    G = O_counts(bed, n_ref)
+    af = G.sum(1) / (2.0 * n_ref)
+    maf = np.minimum(af, 1 - af)
+    rows = [ln.split(" ") for ln in str(g["cli_txt"]).strip().split("\n")]
+    lines = []
+    for r in rows:
+        j = int(r[0][2:])
+        u = rng.random()
+        if u < 0.08:
+            continue                                              # not in the external study
+        a1 = "G" if u < 0.2 else r[1]                             # allele discrepancy -> sign flip
+        mf = maf[j] + (0.35 if u > 0.95 else 0.0)                 # a few fail the MAF filter
+        lines.append(f"{r[0]} {a1} {mf:.6f} {rng.standard_normal():.8f}")
+    lines.append("rs_not_in_panel A 0.200000 1.50000000")
+    ext_txt = "\n".join(lines) + "\n"
+    out = dict(ext_txt=ext_txt)
+    with tempfile.TemporaryDirectory() as td:
+        for name, key in (("ref.bim", "bim_txt"), ("ref.fam", "fam_txt"), ("blocks.bed", "block_txt"), ("dbslmm.txt", "cli_txt")):
+            open(os.path.join(td, name), "w").write(str(g[key]))
+        open(os.path.join(td, "ext.txt"), "w").write(ext_txt)
+        R.write_bed(bed, os.path.join(td, "ref.bed"))
+        for tag, mm in (("c", "0.2"), ("u", "1")):
+            cmd = [os.path.join(ROOT, "oracle", "_ref", "valid_ref"), "-d", td + "/dbslmm.txt", "-s", td + "/ext.txt", "-r", td + "/ref",
+                   "-mafMax", mm, "-b", td + "/blocks.bed", "-r2", td + "/r2" + tag]
+            subprocess.run(cmd, cwd=td, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            out["r2_" + tag] = open(td + "/r2" + tag + ".txt").read()
+    np.savez_compressed(os.path.join(GOLD, "valid_synth.npz"), **out)
+    print("valid_synth:", out["r2_c"].strip().replace("\n", " | "))
+
+
+def O_counts(bed, n_ref):
+    """allele counts 0/1/2 per SNP row (missing -> 0) from a packed .bed payload"""
+    b = np.asarray(bed, np.uint8)
+    codes = np.stack([(b >> s) & 3 for s in (0, 2, 4, 6)], axis=-1).reshape(b.shape[0], -1)[:, :n_ref]
+    return np.where(codes == 0, 2, np.where(codes == 2, 1, 0))
+
+
 if __name__ == "__main__":
+    if "valid" in sys.argv[1:]:
+        valid_synth()
+        raise SystemExit(0)
     if not R.available():
         raise SystemExit("oracle/_ref missing: run oracle/build_ref.sh first")
     os.makedirs(GOLD, exist_ok=True)
     c1()
     ragged()
     synth_cli()
+    valid_synth()
