@@ -12,6 +12,19 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _built_artifacts():
+    """The in-tree library and the two command lines normally travel with the tree; build whatever is missing
+    (nvcc cross-compiles without a GPU), so a bare checkout can run the suite too."""
+    from dbslmm_b200 import build as b
+    if not (os.path.exists(b.LIB) and os.path.exists(b.CLI) and os.path.exists(b.VALID_CLI)):
+        b.build_lib()
+        b.build_cli()
+    from oracle import oracle
+    oracle.build()
+    yield
+
+
 @pytest.fixture(scope="session")
 def engine():
     from dbslmm_b200 import _abi
