@@ -1,11 +1,14 @@
 // engine.cu -- C-ABI implementation: handle, device workspace, block plan (the scheduler side of
 // DBSLMMFIT::est, reference scr/dbslmmfit.cpp:56-244) and the launch sequence of one fit.
 //
-// Host work per fit: walk the CSR block lists once, lay the blocks out in device memory
-// (int8 code rows, one row-major FP64 matrix per block), build the tile / panel work lists,
-// ship everything in ONE pinned blob, launch decode -> gram -> (per fold) cholesky steps ->
-// back substitution, and read the betas back.  No CPU arithmetic on the data path: without a
-// CUDA device every entry point fails.
+// Host work per fit: group the blocks into batches (size classes; upload regions when the panel
+// streams in with the call), lay the blocks out in device memory (int8 code rows, one row-major
+// FP64 matrix per block), build the tile / panel work lists, ship everything in ONE pinned blob,
+// launch decode -> gram -> (per fold, per batch on its own stream) cholesky steps -> back
+// substitution, and read the betas back.  With fit_args.bed the panel upload is cut along the
+// batches and overlaps all of that; with fit_args.quadform_out the solve is replaced by the
+// `valid` tool's quadratic form.  No CPU arithmetic on the data path: without a CUDA device every
+// entry point fails.
 #include <algorithm>
 #include <chrono>
 #include <cmath>
