@@ -187,3 +187,26 @@ def test_cli_without_maf_constraint_streams_the_panel(tmp_path):
         outs.append(((tmp_path / (tag + ".txt")).read_text(), (tmp_path / (tag + ".bin")).read_bytes()))
     assert outs[0][0] == outs[1][0] and outs[0][1] == outs[1][1]
     assert len(outs[0][0].strip().split("\n")) > 700
+
+
+@pytest.mark.gpu
+def test_cli_two_gpus_match_one_gpu(tmp_path):
+    """--gpus 2: blocks sharded by the library's cost model, every GPU gets only its shard of the panel (handed to
+    dbslmm_b200_fit with the call, uploaded in batches), betas gathered on the host: same files as one GPU."""
+    from dbslmm_b200 import _abi
+    if _abi.load().dbslmm_b200_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    _write_fixture(tmp_path)
+    (tmp_path / "manifest.tsv").write_text(
+        f"{tmp_path / 's.txt'}\t{tmp_path / 'l.txt'}\t{tmp_path / 'ref'}\t{tmp_path / 'blocks.bed'}\t{tmp_path / 'x'}\n"
+        f"{tmp_path / 'summ.txt'}\t-\t{tmp_path / 'ref'}\t{tmp_path / 'blocks.bed'}\t{tmp_path / 'y'}\n")
+    common = ["-n", "2400", "-nsnp", "996", "-mafMax", "0.2", "-h", "0.5", "-t", "1"]
+    outs = {}
+    for g in ("1", "2"):
+        r = subprocess.run([CLI, "--manifest", str(tmp_path / "manifest.tsv"), "--gpus", g] + common, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        outs[g] = [_parse((tmp_path / f"{t}.txt").read_text()) for t in ("x", "y")]
+    for a, b in zip(outs["1"], outs["2"]):
+        assert [(g[0], g[1], g[4]) for g in a] == [(g[0], g[1], g[4]) for g in b]
+        va, vb = np.array([g[2] for g in a]), np.array([g[2] for g in b])
+        assert np.abs(va - vb).max() <= 2e-6 * np.abs(va).max()
