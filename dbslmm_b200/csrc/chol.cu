@@ -174,9 +174,12 @@ __device__ __forceinline__ void mm_tile8(const double* A, int sa, const double* 
     C[g * sc + 2 * t + 1] = scale * c1;
 }
 
+// `w_ready()` runs (all threads) once the dense W tile is in global memory, before the L / W^T tile is written back:
+// the diagonal CTAs of a chain-bound step raise their flag there -- the waiting TRSMs need W only.
+template <class WReady>
 __device__ __forceinline__ void diag_body(const BlockDesc& bd, int blk, int k, const double* __restrict__ sigma,
                                           double* __restrict__ Lbuf, double* __restrict__ wbuf, double ridge,
-                                          int32_t* __restrict__ status, double* smem) {
+                                          int32_t* __restrict__ status, double* smem, WReady&& w_ready) {
     double* T = smem;                        // [64][DT] tile, becomes L (lower)
     double* Wf = T + NB * DT;                // [64][DT] W = L^-1 (lower)
     double* Pm = Wf + NB * DT;               // [32][DP] product scratch of the W assembly
@@ -361,18 +364,18 @@ __device__ __forceinline__ void diag_body(const BlockDesc& bd, int blk, int k, c
         __syncthreads();
     }
     DIAG_STAMP(22);
-    // ---- write back: lower = L_kk, strict upper = W_kk^T (used by the back substitution) ...
-    for (int idx = tid; idx < NB * NB; idx += CHOL_THREADS) {
-        const int a = idx >> 6, b = idx & 63;
-        if (a < wk && b < wk) Lb[(size_t)(pc0 + a) * ld + pc0 + b] = (b <= a) ? T[a * DT + b] : Wf[b * DT + a];
-    }
-    // ... and W_kk as a dense 64x64 lower-triangular tile for the panel kernel of this step, which
-    // streams it into shared memory with cp.async while its GEMM loop runs
+    // ---- write back: W_kk as a dense 64x64 lower-triangular tile for the panel kernel of this step (which streams it
+    // into shared memory with cp.async; 8x8 blocks strictly above the diagonal are never read by the TRSM: skipped) ...
     double* wb = wbuf + (size_t)blk * (NB * NB);
-    // (8x8 blocks strictly above the diagonal are never read by the TRSM: skip them)
     for (int idx = tid; idx < NB * NB; idx += CHOL_THREADS) {
         const int a = idx >> 6, b = idx & 63;
         if ((b >> 3) <= (a >> 3)) wb[idx] = (b <= a) ? Wf[a * DT + b] : 0.0;
+    }
+    w_ready();
+    // ... and the tile itself: lower = L_kk, strict upper = W_kk^T (used by the back substitution)
+    for (int idx = tid; idx < NB * NB; idx += CHOL_THREADS) {
+        const int a = idx >> 6, b = idx & 63;
+        if (a < wk && b < wk) Lb[(size_t)(pc0 + a) * ld + pc0 + b] = (b <= a) ? T[a * DT + b] : Wf[b * DT + a];
     }
     DIAG_STAMP(23);
 }
@@ -384,7 +387,7 @@ chol_diag_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict
     extern __shared__ __align__(16) double smem[];
     const int blk = items[blockIdx.x];
     const BlockDesc bd = blocks[blk];
-    diag_body(bd, blk, k, sigma, Lbuf, wbuf, ridge, status, smem);
+    diag_body(bd, blk, k, sigma, Lbuf, wbuf, ridge, status, smem, []() {});
 }
 
 // Look-ahead SYRK of one 16-row slot WL of a 64-row half: acc2 (rows 16WL.., columns 0 .. 16WL+15, lower triangle
@@ -617,7 +620,7 @@ __device__ __forceinline__ void panel_body(const BlockDesc& bd, const int4 item,
         // macro tile 0: rows r0 .. r0+63 are the diagonal tile of panel k+1, which this step completed
         if (item.y == 0 && r0 < bd.mp && wk == NB) {
             __syncthreads();        // T_new is in L2 for the whole CTA; shared memory is free again
-            diag_body(bd, item.x, k + 1, sigma, Lbuf, wbuf + wpar_next, ridge, status, smem);
+            diag_body(bd, item.x, k + 1, sigma, Lbuf, wbuf + wpar_next, ridge, status, smem, []() {});
         }
     }
 }
@@ -642,10 +645,11 @@ chol_panel_kernel(const BlockDesc* __restrict__ blocks, const int4* __restrict__
     if ((int)blockIdx.x < n_diag_first) {
         const int blk = diag_items[blockIdx.x];
         const BlockDesc bd = blocks[blk];
-        diag_body(bd, blk, k, sigma, Lbuf, wbuf + wpar, ridge, status, smem);
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) atomicExch(dflag + blk, k + 1);
+        diag_body(bd, blk, k, sigma, Lbuf, wbuf + wpar, ridge, status, smem, [&]() {
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) atomicExch(dflag + blk, k + 1);      // W_k is visible: the step's TRSMs may start
+        });
         return;
     }
     const int4 item = items[blockIdx.x - n_diag_first];
