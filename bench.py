@@ -137,8 +137,13 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index = index
-        self.lines = []
+        self.lines = []          # (arrival time, text)
         self.proc = None
+        self.t_mark = 0.0
+
+    def mark(self):
+        """Samples that arrive from now on count (nvidia-smi needs a moment to start: it is launched before the warm-up)."""
+        self.t_mark = time.perf_counter()
 
     def start(self):
         try:
@@ -152,7 +157,7 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.perf_counter(), ln.strip()))
 
     def stop(self):
         if not self.proc:
@@ -165,7 +170,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ts, ln in self.lines:
+            if ts < self.t_mark:
+                continue
             t = [x.strip() for x in ln.split(",")]
             if len(t) < 9:
                 continue
@@ -343,11 +350,12 @@ def main():
 
     # ---- device-resident throughput (value)
     eng.load_bed(sh["bed"], n_ref)
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         r = eng.fit(*csr, **fit_kw)
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
+    sampler.mark()
     dev_ms, tms = [], []
     t0 = time.perf_counter()
     for _ in range(args.steps):
