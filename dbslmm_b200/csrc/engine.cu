@@ -164,6 +164,21 @@ int fail(dbslmm_b200_handle* h, int code, const std::string& msg) {
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// memcpy split over up to four host threads (large result vectors only)
+inline void par_memcpy(void* dst, const void* src, size_t bytes) {
+    const size_t kMin = (size_t)2 << 20;
+    const int nthr = (int)std::min<size_t>(4, bytes / kMin);
+    if (nthr <= 1) { std::memcpy(dst, src, bytes); return; }
+    std::vector<std::thread> th;
+    const size_t chunk = (bytes / nthr + 63) & ~(size_t)63;
+    for (int t = 1; t < nthr; ++t) {
+        const size_t o = chunk * t, n = (t == nthr - 1) ? bytes - o : chunk;
+        th.emplace_back([=]() { std::memcpy((char*)dst + o, (const char*)src + o, n); });
+    }
+    std::memcpy(dst, src, chunk);
+    for (std::thread& x : th) x.join();
+}
+
 // DBSLMM_B200_TRACE=1: host-side wall-clock marks of one fit on stderr (tuning aid)
 struct Trace {
     bool on;
@@ -1165,7 +1180,8 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
     const double* hb = (const double*)hout;
     if (quad && nb > 0) std::memcpy(a->quadform_out, hb, sizeof(double) * (size_t)nb);
     for (int f = 0; f < a->n_folds && !quad; ++f) {
-        std::memcpy(a->beta_s_out + (size_t)f * P.tot_s, hb + (size_t)f * n_out, sizeof(double) * (size_t)P.tot_s);
+        // pinned staging -> caller's arrays; a genome-wide beta vector is ~9 MB, so the copy is split over a few threads
+        par_memcpy(a->beta_s_out + (size_t)f * P.tot_s, hb + (size_t)f * n_out, sizeof(double) * (size_t)P.tot_s);
         if (P.tot_l) std::memcpy(a->beta_l_out + (size_t)f * P.tot_l, hb + (size_t)f * n_out + P.tot_s, sizeof(double) * (size_t)P.tot_l);
     }
     const int32_t* hs = (const int32_t*)(hout + sizeof(double) * n_res);
