@@ -71,3 +71,24 @@ def test_plan_shards_lpt_balance():
 def test_plan_shards_rejects_bad_arguments():
     lib = _abi.load()
     assert lib.dbslmm_b200_plan_shards(3, None, None, 100, 2, None, None) == -2
+
+
+def test_fit_args_field_offsets_match_the_c_header(tmp_path):
+    """Field-by-field: offsetof() from a C program compiled against include/dbslmm_b200.h vs the ctypes mirror."""
+    import subprocess
+    fields = [name for name, _ in _abi.FitArgs._fields_]
+    tfields = [name for name, _ in _abi.Timing._fields_]
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "dbslmm_b200.h"', 'int main(void) {']
+    src += [f'  printf("{f} %zu\\n", offsetof(dbslmm_b200_fit_args, {f}));' for f in fields]
+    src += [f'  printf("t.{f} %zu\\n", offsetof(dbslmm_b200_timing, {f}));' for f in tfields]
+    src += ['  return 0;', '}']
+    c = tmp_path / "off.c"
+    c.write_text("\n".join(src))
+    exe = tmp_path / "off"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["gcc", "-I", os.path.join(root, "include"), str(c), "-o", str(exe)], check=True)
+    out = dict(ln.split() for ln in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.strip().split("\n"))
+    for f in fields:
+        assert int(out[f]) == getattr(_abi.FitArgs, f).offset, f
+    for f in tfields:
+        assert int(out["t." + f]) == getattr(_abi.Timing, f).offset, f
