@@ -128,6 +128,7 @@ class Engine:
         pitch = (n_ref + 3) // 4
         n_snp = bed.size // pitch
         self._check(self.lib.dbslmm_b200_load_bed(self.h, bed.ctypes.data, n_snp, n_ref), "load_bed")
+        self._bed_keep = bed          # the upload is asynchronous: the buffer must outlive this call (see the C header)
         self.n_snp, self.n_ref = n_snp, n_ref
 
     def snp_stats(self):

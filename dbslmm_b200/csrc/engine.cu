@@ -1176,6 +1176,12 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return fail(h, DBSLMM_B200_ERR_CUDA, std::string("fit: ") + cudaGetErrorString(e));
     }
+    if (streaming) {
+        // the caller's panel buffer must not be needed after the call returns: the batch uploads are done (their batches
+        // consumed them), this only waits for the rows no block uses
+        CU_TRY(h, cudaEventSynchronize(h->ev_bed));
+        h->bed_pending = false;
+    }
     if (streaming && *h_flag != 0) { P.valid = false; return kRetryResident; }   // missing calls: see fit_impl's header
     const double* hb = (const double*)hout;
     if (quad && nb > 0) std::memcpy(a->quadform_out, hb, sizeof(double) * (size_t)nb);

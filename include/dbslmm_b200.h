@@ -128,7 +128,12 @@ DBSLMM_B200_API const char* dbslmm_b200_last_error(const dbslmm_b200_handle* h);
 
 /* Reference panel.  `bed` points just after the 3 magic bytes of a SNP-major PLINK .bed
  * (pitch = ceil(n_ref/4) bytes per SNP).  Copies to the device and runs the statistics
- * kernel (per-SNP allele sum, sum of squares, non-missing count). */
+ * kernel (per-SNP allele sum, sum of squares, non-missing count).  ASYNCHRONOUS: the call
+ * returns while the copy is in flight (the caller's next step -- building the block lists,
+ * dbslmm_b200_fit planning -- overlaps it), so `bed` must stay valid and unchanged until the
+ * next dbslmm_b200_snp_stats / dbslmm_b200_fit / dbslmm_b200_load_bed / dbslmm_b200_destroy
+ * on this handle has returned.  (fit_args.bed, by contrast, is no longer needed once that
+ * fit call returns.) */
 DBSLMM_B200_API int  dbslmm_b200_load_bed(dbslmm_b200_handle* h, const uint8_t* bed, int64_t n_snp, int32_t n_ref);
 
 /* MAF pre-pass product (dtpr.cpp:93-102, 361-362): maf after mean imputation; optional
