@@ -150,6 +150,9 @@ __device__ __forceinline__ void gemm_nt_core(const double* __restrict__ Pg, cons
 #define DIAG_STAMP(n)               // probe hook (tools/diag_probe.cu records clock64() here)
 #endif
 static constexpr int DT = NB + 1;   // odd stride: conflict-free row and column walks in FP64
+// barrier of the 256 threads that run diag_body (the whole CTA, except in the TMA panel kernel, whose ninth warp -- the
+// TMA producer -- never enters)
+__device__ __forceinline__ void diag_sync() { asm volatile("bar.sync 4, 256;" ::: "memory"); }
 static constexpr int DP = 33;       // stride of the 32x32 product scratch
 static constexpr int SMEM_DIAG = (2 * NB * DT + 32 * DP + NB) * 8;
 
@@ -215,7 +218,7 @@ __device__ __forceinline__ void diag_body(const BlockDesc& bd, int blk, int k, c
             Wf[a * DT + b] = 0.0;
         }
     }
-    __syncthreads();
+    diag_sync();
 
     bool bad = false;
     DIAG_STAMP(1);
@@ -250,7 +253,7 @@ __device__ __forceinline__ void diag_body(const BlockDesc& bd, int blk, int k, c
                 for (int c = 0; c < 16; ++c) T[(o + r) * DT + o + c] = (c <= r) ? row[c] : 0.0;
             }
         }
-        __syncthreads();                                   // [A] L16 and 1/diag are in shared memory
+        diag_sync();                                   // [A] L16 and 1/diag are in shared memory
         DIAG_STAMP(2 + 5 * jb);
         const int nrem = 48 - o;                           // rows below this sub-block
         if (warp == 1) {
@@ -294,7 +297,7 @@ __device__ __forceinline__ void diag_body(const BlockDesc& bd, int blk, int k, c
 #pragma unroll
             for (int c = 0; c < 16; ++c) T[i * DT + o + c] = x[c];
         }
-        __syncthreads();                                   // [B] sub-panel solved
+        diag_sync();                                   // [B] sub-panel solved
         DIAG_STAMP(3 + 5 * jb);
         if (jb == 3) break;
         // ---- next 16x16 diagonal sub-block first, one entry per thread; then warp 0 factors it while the other
@@ -316,7 +319,7 @@ __device__ __forceinline__ void diag_body(const BlockDesc& bd, int blk, int k, c
             }
             T[(o + 16 + ri) * DT + o + 16 + ci] -= (a0 + a1) + (a2 + a3);
         }
-        __syncthreads();                                   // [C] next diagonal sub-block updated
+        diag_sync();                                   // [C] next diagonal sub-block updated
         if (warp != 0) {
             const int h = 32 - o;                          // rows o+32.., columns o+16..row
             for (int idx = tid - 32; idx < h * 64; idx += CHOL_THREADS - 32) {
@@ -345,23 +348,23 @@ __device__ __forceinline__ void diag_body(const BlockDesc& bd, int blk, int k, c
         const int r0 = 8 * ((warp >> 1) & 1), c0 = 8 * (warp & 1);
         // A^-1 is lower triangular: only k >= c0 contributes
         mm_tile8(T + (ob + 16 + r0) * DT + ob, DT, Wf + ob * DT + ob + c0, DT, c0, 16, Pm + (16 * half + r0) * DP + c0, DP, 1.0, lane);
-        __syncthreads();
+        diag_sync();
         // C^-1 is lower triangular: only k <= r0 + 7 contributes
         mm_tile8(Wf + (ob + 16 + r0) * DT + ob + 16, DT, Pm + (16 * half) * DP + c0, DP, 0, r0 + 8, Wf + (ob + 16 + r0) * DT + ob + c0, DT, -1.0, lane);
-        __syncthreads();
+        diag_sync();
         // level 2 (16 tiles, two per warp): P = L21 W11 (32x32), then W21 = -W22 P
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int tl = warp + 8 * u, R0 = 8 * (tl >> 2), C0 = 8 * (tl & 3);
             mm_tile8(T + (32 + R0) * DT, DT, Wf + C0, DT, C0, 32, Pm + R0 * DP + C0, DP, 1.0, lane);
         }
-        __syncthreads();
+        diag_sync();
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int tl = warp + 8 * u, R0 = 8 * (tl >> 2), C0 = 8 * (tl & 3);
             mm_tile8(Wf + (32 + R0) * DT + 32, DT, Pm + C0, DP, 0, R0 + 8, Wf + (32 + R0) * DT + C0, DT, -1.0, lane);
         }
-        __syncthreads();
+        diag_sync();
     }
     DIAG_STAMP(22);
     // ---- write back: W_kk as a dense 64x64 lower-triangular tile for the panel kernel of this step (which streams it
@@ -659,6 +662,403 @@ chol_panel_kernel(const BlockDesc* __restrict__ blocks, const int4* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------
+// TMA panel kernel: the same panel step as chol_panel_kernel (same arithmetic, same work lists), restructured around
+// what the round-1 profile of that kernel showed -- 29 % of its warp samples sat in the per-chunk __syncthreads of the
+// cp.async ring, 8 % in cp.async.wait, every CTA paid two dependent descriptor loads, a cold ring and the HBM latency
+// of its Sigma tile before its first DMMA:
+//   * a ninth warp is the PRODUCER: it walks the CTA's items and feeds a 3-stage ring of [64 rows x 16 doubles] boxes
+//     (two for the 128 macro-tile rows, one for the 64 panel rows) with 4-D tiled TMA loads (cp.async.bulk.tensor,
+//     SWIZZLE_128B; one tensor map per block, in the plan blob), completion on `full` mbarriers;
+//   * the eight CONSUMER warps never meet in the K loop: each waits for `full[s]`, reads its fragments, and releases
+//     the stage on `empty[s]` -- no CTA-wide barrier, no per-thread address arithmetic, no cp.async bookkeeping;
+//   * bank conflicts: the tensor map splits a row index r = 8a + 2b + c into (b, c, a) and lists b before c, so the
+//     rows of an 8-row group land in shared memory in the order 0,2,4,6,1,3,5,7; with the 128-byte swizzle the eight
+//     lanes of every 128-bit load phase (fragment rows g = 2j, 2j+1, four 16-byte chunks each) then hit eight distinct
+//     bank groups -- unpadded stages (24 KB instead of 36.9 KB);
+//   * W_kk arrives by TMA in its own four boxes while the ring is busy; the epilogue tiles (the two 64-row halves of
+//     -L_ik) reuse the ring boxes in the same permuted/swizzled format, so one address function serves all;
+//   * a CTA may own several consecutive items (macro tiles of the same block and step): the producer is then already
+//     waiting with the next item's loads, its Sigma tile has been pulled into L2 during the previous item, and W_kk
+//     is loaded once per block.
+// ------------------------------------------------------------------------------------------
+static constexpr int TP_THREADS = CHOL_THREADS;          // eight warps; thread 0 doubles as the TMA producer
+static constexpr int BOXB = NB * KC * 8;                 // bytes of one [64 x 16] box (8 KB)
+static constexpr int TP_NST = 3;                         // ring stages, 3 boxes each
+static constexpr int TP_RING = 3 * TP_NST * BOXB;        // 72 KB: also the two L halves of the epilogue (4 boxes each)
+static constexpr int SMEM_TP = TP_RING + 4 * BOXB + 1024;    // + W_kk (4 boxes) + alignment slack
+static_assert(SMEM_TP - 1024 >= SMEM_DIAG, "the fused diagonal factorisation reuses the panel kernel's shared memory");
+static_assert(KC == 16, "a box row is one 128-byte swizzle span");
+
+struct TpBars {
+    uint64_t full[TP_NST], empty[TP_NST];
+    uint64_t w_full, w_free, ring_free;
+};
+
+template <int WL>
+__device__ __forceinline__ void syrk_rows_pt(uint32_t Lh, uint32_t lrow, uint32_t x0, double (&acc2)[2][8][2]) {
+#pragma unroll 2
+    for (int s8 = 0; s8 < NB / 8; ++s8) {
+        const uint32_t bx = Lh + (uint32_t)(s8 >> 1) * BOXB + lrow + (x0 ^ ((uint32_t)(s8 & 1) << 6));
+        const double2 a0 = lds_f64x2(bx + (2 * WL) * 1024);
+        const double2 a1 = lds_f64x2(bx + (2 * WL + 1) * 1024);
+#pragma unroll
+        for (int c = 0; c <= 2 * WL + 1; ++c) {
+            const double2 b = lds_f64x2(bx + c * 1024);
+            if (c <= 2 * WL) dmma884(acc2[0][c][0], acc2[0][c][1], a0.x, b.x);
+            dmma884(acc2[1][c][0], acc2[1][c][1], a1.x, b.x);
+            if (c <= 2 * WL) dmma884(acc2[0][c][0], acc2[0][c][1], a0.y, b.y);
+            dmma884(acc2[1][c][0], acc2[1][c][1], a1.y, b.y);
+        }
+    }
+}
+
+// geometry of one item
+struct TpGeom {
+    int pc0, wk, r0, prow, kb, ke, slice, nsl;
+};
+__device__ __forceinline__ TpGeom tp_geom(const BlockDesc& bd, const int4 item, int k) {
+    TpGeom q;
+    q.pc0 = k * NB;
+    q.wk = min(NB, bd.mp - q.pc0);
+    q.r0 = q.pc0 + q.wk + item.y * TM;
+    q.prow = min(TM, bd.nrows - q.r0);
+    q.slice = item.z & 0xFF;
+    q.nsl = item.z >> 8;
+    q.kb = (k * q.slice) / q.nsl * NB;
+    q.ke = (k * (q.slice + 1)) / q.nsl * NB;
+    return q;
+}
+
+// lmaps: one 4-D tensor map per block over its matrix in Lbuf (dims {ld, 4, 2, rows/8}, box {16, 4, 2, 8}; `perm` = 0:
+// plain 2-D maps {ld, rows}, box {16, 64} -- rows in natural order, two-way bank conflicts -- if the driver refuses the
+// permuting strides).  wmap: the dense W tiles of `wbuf` as one tensor, same box.
+// CTA c (after the n_diag_first diagonal CTAs): c < n_single owns item c; the others own `tpc` consecutive items.
+__global__ void __launch_bounds__(TP_THREADS, 2)
+chol_panel_tma_kernel(const BlockDesc* __restrict__ blocks, const int4* __restrict__ items, int32_t n_items,
+                      int32_t n_single, int32_t tpc, const int32_t* __restrict__ diag_items, int32_t n_diag_first,
+                      int32_t k, const CUtensorMap* __restrict__ lmaps, const __grid_constant__ CUtensorMap wmap,
+                      int32_t perm, int32_t wrow8_cur, const double* __restrict__ sigma, double* __restrict__ Lbuf,
+                      double* __restrict__ wbuf, int64_t wpar, int64_t wpar_next, double ridge,
+                      double* __restrict__ scratch, int32_t* __restrict__ counters, int32_t group_base,
+                      int32_t* __restrict__ status, int32_t* __restrict__ dflag, int32_t fuse_end) {
+    extern __shared__ __align__(16) uint8_t tp_smem_raw[];
+    __shared__ __align__(8) TpBars bars;
+    __shared__ int s_last;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint8_t* smem_al = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tp_smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t sbase = smem_u32(smem_al);
+
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if ((int)blockIdx.x < n_diag_first) {
+        const int blk = diag_items[blockIdx.x];
+        const BlockDesc bd = blocks[blk];
+        diag_body(bd, blk, k, sigma, Lbuf, wbuf + wpar, ridge, status, reinterpret_cast<double*>(smem_al), [&]() {
+            __threadfence();
+            diag_sync();
+            if (threadIdx.x == 0) atomicExch(dflag + blk, k + 1);
+        });
+        return;
+    }
+    const bool wait_w = n_diag_first > 0;
+    const int cta = (int)blockIdx.x - n_diag_first;
+    int i0, n_my;
+    if (cta < n_single) { i0 = cta; n_my = 1; }
+    else { i0 = n_single + (cta - n_single) * tpc; n_my = min(tpc, n_items - i0); }
+
+    if (tid == 0) {
+        for (int s = 0; s < TP_NST; ++s) { mbar_init(&bars.full[s], 1); mbar_init(&bars.empty[s], 8); }
+        mbar_init(&bars.w_full, 1);
+        mbar_init(&bars.w_free, 8);
+        mbar_init(&bars.ring_free, 8);
+        mbar_fence_init();
+        tma_prefetch_desc(&wmap);
+    }
+    __syncthreads();
+
+    const uint32_t wbox = sbase + TP_RING;                    // W_kk: 4 boxes (64 rows x 16 columns each)
+    const int g = lane >> 2, t = lane & 3;
+    const int sig = perm ? ((g >> 1) | ((g & 1) << 2)) : g;     // shared-memory row of fragment row g inside its 8-row group
+    const uint32_t lrow = (uint32_t)sig * 128u;
+    const uint32_t x0 = (uint32_t)((t ^ sig) & 7) << 4;          // 16-byte chunk of columns 2t, 2t+1 of the first 8-column group
+    const int grp = warp >> 2;
+    const int wl = grp ? 3 - (warp & 3) : (warp & 3);
+    const int wrow = 4 * grp + wl;
+    uint32_t it = 0, wcount = 0;                                 // ring uses / W loads so far (all threads keep count)
+    int prev_blk = -1;
+
+    for (int j = 0; j < n_my; ++j) {
+        const int4 item = items[i0 + j];
+        const BlockDesc bd = blocks[item.x];
+        const TpGeom q = tp_geom(bd, item, k);
+        const int pc0 = q.pc0, wk = q.wk, r0 = q.r0, prow = q.prow, ld = bd.ld;
+        double* Lb = Lbuf + bd.moff;
+        const double* Sb = sigma + bd.moff;
+        const bool active = (16 * wrow < prow);
+        const bool load_w = (item.x != prev_blk);
+        prev_blk = item.x;
+        const int nchunk = (q.ke - q.kb) / KC;
+        const CUtensorMap* lm = lmaps + item.x;
+
+        // ---- producer duties of thread 0.  Chunk c of this item is ring use u = it + c: stage u % 3, and it may be
+        // written once all eight warps have released the stage's previous use.
+        auto issue_chunk = [&](int c) {
+            const uint32_t u = it + (uint32_t)c;
+            const int s = (int)(u % TP_NST);
+            mbar_wait(&bars.empty[s], ((u / TP_NST) & 1u) ^ 1u);
+            mbar_expect_tx(&bars.full[s], (uint32_t)((prow > NB ? 3 : 2) * BOXB));
+            const int k0 = q.kb + c * KC;
+            if (perm) {
+                const uint32_t st = sbase + (uint32_t)s * 3 * BOXB;
+                tma_load_4d(st, lm, k0, 0, 0, r0 >> 3, &bars.full[s]);
+                if (prow > NB) tma_load_4d(st + BOXB, lm, k0, 0, 0, (r0 >> 3) + 8, &bars.full[s]);
+                tma_load_4d(st + 2 * BOXB, lm, k0, 0, 0, pc0 >> 3, &bars.full[s]);
+            } else {
+                uint8_t* sp = smem_al + (size_t)s * 3 * BOXB;
+                tma_load_2d(sp, lm, k0, r0, &bars.full[s]);
+                if (prow > NB) tma_load_2d(sp + BOXB, lm, k0, r0 + NB, &bars.full[s]);
+                tma_load_2d(sp + 2 * BOXB, lm, k0, pc0, &bars.full[s]);
+            }
+        };
+        auto issue_w = [&]() {
+            mbar_expect_tx(&bars.w_full, 4 * BOXB);
+            const int wr = wrow8_cur + item.x * (NB / 8);
+            for (int b4 = 0; b4 < 4; ++b4) {
+                if (perm) tma_load_4d(wbox + b4 * BOXB, &wmap, 16 * b4, 0, 0, wr, &bars.w_full);
+                else tma_load_2d(smem_al + TP_RING + b4 * BOXB, &wmap, 16 * b4, wr * 8, &bars.w_full);
+            }
+        };
+        if (tid == 0) {
+            if (load_w) tensormap_acquire(lm);
+            // the ring first (it gates the main loop), then W_kk (needed only by the epilogue)
+            if (j > 0) mbar_wait(&bars.ring_free, (uint32_t)((j - 1) & 1));
+            if (nchunk > 0) issue_chunk(0);
+            if (nchunk > 1) issue_chunk(1);
+            if (load_w && !wait_w) {
+                if (j > 0) mbar_wait(&bars.w_free, (uint32_t)((j - 1) & 1));
+                issue_w();
+            }
+        }
+
+        // accumulators start at -K_ik (slice 0 only): after the loop acc = L_i,0:k L_k,0:k^T - K_ik = -C
+        double acc[2][8][2];
+#pragma unroll
+        for (int f = 0; f < 2; ++f)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int rl = 16 * wrow + 8 * f + g, cc = 8 * c + 2 * t;
+                double2 a = make_double2(0.0, 0.0);
+                if (q.slice == 0 && rl < prow && cc < wk) a = *reinterpret_cast<const double2*>(Sb + (size_t)(r0 + rl) * ld + pc0 + cc);
+                acc[f][c][0] = -a.x;
+                acc[f][c][1] = -a.y;
+            }
+
+        // ---- main loop: no CTA-wide barrier; thread 0 keeps the ring two chunks ahead
+        for (int kc = 0; kc < nchunk; ++kc) {
+            if (tid == 0 && kc + 2 < nchunk) issue_chunk(kc + 2);
+            const uint32_t u = it + (uint32_t)kc;
+            const int s = (int)(u % TP_NST);
+            mbar_wait(&bars.full[s], (u / TP_NST) & 1u);
+            if (active) {
+                const uint32_t st = sbase + (uint32_t)s * 3 * BOXB;
+                const uint32_t Pa = st + (uint32_t)grp * BOXB + (uint32_t)(2 * wl) * 1024 + lrow;
+                const uint32_t Qa = st + 2 * BOXB + lrow;
+#pragma unroll
+                for (int s8 = 0; s8 < 2; ++s8) {
+                    const uint32_t xo = x0 ^ ((uint32_t)s8 << 6);
+                    const double2 a0 = lds_f64x2(Pa + xo);
+                    const double2 a1 = lds_f64x2(Pa + 1024 + xo);
+#pragma unroll
+                    for (int hc = 0; hc < 2; ++hc) {
+                        double2 b[4];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) b[c] = lds_f64x2(Qa + (uint32_t)(4 * hc + c) * 1024 + xo);
+                        if (s8 == 1 && hc == 1) {
+                            // last shared-memory read of this stage: hand it back
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&bars.empty[s]);
+                        }
+                        // eight independent accumulators per pass (x, then y): dependent DMMAs are 8 apart
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            dmma884(acc[0][4 * hc + c][0], acc[0][4 * hc + c][1], a0.x, b[c].x);
+                            dmma884(acc[1][4 * hc + c][0], acc[1][4 * hc + c][1], a1.x, b[c].x);
+                        }
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            dmma884(acc[0][4 * hc + c][0], acc[0][4 * hc + c][1], a0.y, b[c].y);
+                            dmma884(acc[1][4 * hc + c][0], acc[1][4 * hc + c][1], a1.y, b[c].y);
+                        }
+                    }
+                }
+            } else {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars.empty[s]);
+            }
+        }
+        it += (uint32_t)nchunk;
+        if (wait_w && load_w && tid == 0) {
+            // W_k is being produced by a diagonal CTA of THIS launch (lower blockIdx: resident or done)
+            const volatile int32_t* fl = dflag + item.x;
+            while (*fl < k + 1) __nanosleep(40);
+            __threadfence();
+            fence_proxy_async();
+            issue_w();
+        }
+        __syncthreads();          // every warp is done with the ring: its boxes become the epilogue's L halves
+
+        if (j + 1 < n_my) {
+            // the next item's Sigma tile (its accumulator preload) -> L2 while this item's epilogue runs
+            const int4 item2 = items[i0 + j + 1];
+            const BlockDesc bd2 = blocks[item2.x];
+            const TpGeom q2 = tp_geom(bd2, item2, k);
+            if (q2.slice == 0 && tid < q2.prow)
+                l2_prefetch_bulk(sigma + bd2.moff + (size_t)(q2.r0 + tid) * bd2.ld + q2.pc0, (uint32_t)(q2.wk * 8));
+        }
+
+        if (q.nsl > 1) {
+            // split-K (single-item CTAs only): partial sums to scratch, the last arriver adds them up IN SLICE ORDER
+            double* part = scratch + ((size_t)(item.w - group_base) * q.nsl) * (TM * NB);
+            double2* mine = reinterpret_cast<double2*>(part + (size_t)q.slice * (TM * NB)) + tid;
+#pragma unroll
+            for (int f = 0; f < 2; ++f)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) mine[(f * 8 + c) * CHOL_THREADS] = make_double2(acc[f][c][0], acc[f][c][1]);
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) s_last = (atomicAdd(&counters[item.w], 1) == q.nsl - 1);
+            __syncthreads();
+            if (!s_last) {
+                if (load_w) mbar_wait(&bars.w_full, wcount & 1u);     // no bulk copy may be in flight when the CTA exits
+                return;
+            }
+            __threadfence();
+#pragma unroll
+            for (int f = 0; f < 2; ++f)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) acc[f][c][0] = acc[f][c][1] = 0.0;
+            for (int sl = 0; sl < q.nsl; ++sl) {
+                const double2* src2 = reinterpret_cast<const double2*>(part + (size_t)sl * (TM * NB)) + tid;
+#pragma unroll
+                for (int f = 0; f < 2; ++f)
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const double2 v = __ldcg(src2 + (f * 8 + c) * CHOL_THREADS);
+                        acc[f][c][0] += v.x;
+                        acc[f][c][1] += v.y;
+                    }
+            }
+        }
+
+        if (load_w) { mbar_wait(&bars.w_full, wcount & 1u); ++wcount; }
+        const uint32_t Lh = sbase + (uint32_t)grp * 4 * BOXB;          // this warp group's half of -L_ik
+        const int trow0 = r0 + 64 * grp;
+        const int tw = min(NB, bd.mp - trow0);
+        const bool glook = (trow0 < bd.mp && wk == NB);
+        const bool look = glook && (16 * wl < tw);
+
+        // ---- TRSM: -L_ik = (-C) W_kk^T, A operand = the accumulator fragments, 32 output columns at a time
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            double out[2][4][2];
+#pragma unroll
+            for (int f = 0; f < 2; ++f)
+#pragma unroll
+                for (int cq = 0; cq < 4; ++cq) out[f][cq][0] = out[f][cq][1] = 0.0;
+            if (active) {
+#pragma unroll
+                for (int cp = 0; cp < 4 * h + 4; ++cp) {
+#pragma unroll
+                    for (int cq = 0; cq < 4; ++cq) {
+                        const int c = 4 * h + cq;
+                        if (c >= cp) {
+                            const double2 b = lds_f64x2(wbox + (uint32_t)(cp >> 1) * BOXB + (uint32_t)c * 1024 + lrow +
+                                                        (x0 ^ ((uint32_t)(cp & 1) << 6)));
+                            dmma884(out[0][cq][0], out[0][cq][1], acc[0][cp][0], b.x);
+                            dmma884(out[1][cq][0], out[1][cq][1], acc[1][cp][0], b.x);
+                            dmma884(out[0][cq][0], out[0][cq][1], acc[0][cp][1], b.y);
+                            dmma884(out[1][cq][0], out[1][cq][1], acc[1][cp][1], b.y);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int f = 0; f < 2; ++f)
+#pragma unroll
+                for (int cq = 0; cq < 4; ++cq) {
+                    const int c = 4 * h + cq;
+                    const int rl = 16 * wrow + 8 * f + g, cc = 8 * c + 2 * t;
+                    if (rl < prow && cc < wk)
+                        *reinterpret_cast<double2*>(Lb + (size_t)(r0 + rl) * ld + pc0 + cc) =
+                            make_double2(-out[f][cq][0], -out[f][cq][1]);
+                    sts_f64x2(Lh + (uint32_t)(c >> 1) * BOXB + (uint32_t)(2 * wl + f) * 1024 + lrow + (x0 ^ ((uint32_t)(c & 1) << 6)),
+                              out[f][cq][0], out[f][cq][1]);
+                }
+        }
+        // W_kk is dead: thread 0 may overwrite it for the next block
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars.w_free);
+
+        // ---- look-ahead: T_ii -= L_ik L_ik^T on this group's diagonal tile
+        if (glook) {
+            double acc2[2][8][2];
+            const double* src = (k == 0 ? sigma : Lbuf) + bd.moff;
+#pragma unroll
+            for (int f = 0; f < 2; ++f)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int rl = 16 * wl + 8 * f + g, cc = 8 * c + 2 * t;
+                    double2 v = make_double2(0.0, 0.0);
+                    if (look && c <= 2 * wl + 1 && rl < tw && cc <= rl)
+                        v = __ldcg(reinterpret_cast<const double2*>(src + (size_t)(trow0 + rl) * ld + trow0 + cc));
+                    acc2[f][c][0] = v.x;
+                    acc2[f][c][1] = v.y;
+                }
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+            if (look) {
+#pragma unroll
+                for (int f = 0; f < 2; ++f)
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const int rl = 16 * wl + 8 * f + g, cc = 8 * c + 2 * t;
+                        double vx = acc2[f][c][0], vy = acc2[f][c][1];
+                        if (k == 0 && trow0 + rl < bd.ms) {
+                            if (cc == rl) vx += ridge;
+                            if (cc + 1 == rl) vy += ridge;
+                        }
+                        acc2[f][c][0] = -vx;
+                        acc2[f][c][1] = -vy;
+                    }
+                switch (wl) {
+                    case 0: syrk_rows_pt<0>(Lh, lrow, x0, acc2); break;
+                    case 1: syrk_rows_pt<1>(Lh, lrow, x0, acc2); break;
+                    case 2: syrk_rows_pt<2>(Lh, lrow, x0, acc2); break;
+                    default: syrk_rows_pt<3>(Lh, lrow, x0, acc2); break;
+                }
+#pragma unroll
+                for (int f = 0; f < 2; ++f)
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const int rl = 16 * wl + 8 * f + g, cc = 8 * c + 2 * t;
+                        if (c <= 2 * wl + 1 && rl < tw && cc <= rl)
+                            *reinterpret_cast<double2*>(Lb + (size_t)(trow0 + rl) * ld + trow0 + cc) =
+                                make_double2(-acc2[f][c][0], -acc2[f][c][1]);
+                    }
+            }
+        }
+        // the ring boxes are free again (for the next item's chunks)
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars.ring_free);
+
+        if (fuse_end && item.y == 0 && r0 < bd.mp && wk == NB && j == n_my - 1) {
+            __syncthreads();        // T_new is in L2 for the whole CTA; shared memory is free (last item: nothing in flight)
+            diag_body(bd, item.x, k + 1, sigma, Lbuf, wbuf + wpar_next, ridge, status, reinterpret_cast<double*>(smem_al), []() {});
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Back substitution L^T x = y (y = matrix row mp), beta = x / sqrt(N).  One CTA per block.
 // ------------------------------------------------------------------------------------------
 template <int NT>
@@ -894,7 +1294,38 @@ backsolve_cluster_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __
 cudaError_t chol_configure() {
     cudaError_t e = cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DIAG);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(chol_panel_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TP);
+    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CHOL);
+}
+
+// TMA panel step (see chol_panel_tma_kernel).  n_single leading items get a CTA each, the rest `tpc` consecutive items
+// per CTA; nb_total = number of blocks of the plan (W tiles per parity).
+cudaError_t launch_chol_panel_tma(const BlockDesc* blocks, const int4* items, int32_t n_items, int32_t n_single, int32_t tpc,
+                                  const int32_t* diag_items, int32_t n_diag_first, int32_t k, const CUtensorMap* lmaps,
+                                  const CUtensorMap& wmap, int32_t perm, int32_t nb_total, const double* sigma, double* L,
+                                  double* wbuf, int64_t wstride, bool fuse_end, double ridge, double* scratch,
+                                  int32_t* counters, int32_t group_base, int32_t* status, int32_t* dflag, bool pdl,
+                                  cudaStream_t st) {
+    if (n_items + n_diag_first == 0) return cudaSuccess;
+    const int64_t wpar = (k & 1) * wstride, wnext = ((k + 1) & 1) * wstride;
+    n_single = std::min(n_single, n_items);
+    tpc = std::max(tpc, 1);
+    const int rest = n_items - n_single;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(n_diag_first + n_single + (rest + tpc - 1) / tpc));
+    cfg.blockDim = dim3(TP_THREADS);
+    cfg.dynamicSmemBytes = SMEM_TP;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    const int32_t wrow8_cur = (int32_t)((k & 1) * (int64_t)nb_total * (NB / 8));
+    return cudaLaunchKernelEx(&cfg, chol_panel_tma_kernel, blocks, items, n_items, n_single, tpc, diag_items, n_diag_first, k,
+                              lmaps, wmap, perm, wrow8_cur, sigma, L, wbuf, wpar, wnext, ridge, scratch, counters, group_base,
+                              status, dflag, (int32_t)(fuse_end ? 1 : 0));
 }
 
 // W_k (the inverse of the diagonal tile of panel k) lives in wbuf[(k & 1) * wstride + block * 64 * 64]: two parities,

@@ -89,6 +89,35 @@ __device__ __forceinline__ void tma_load_2d(void* dst_smem, const void* tmap, in
         "l"(tmap), "r"(smem_u32(bar)), "r"(x), "r"(y)
         : "memory");
 }
+// 4-D tiled TMA load (SASS UTMALDG): the FP64 panel operands of the block solver (chol.cu) -- the two middle
+// dimensions permute the rows of every 8-row group on their way into shared memory.
+__device__ __forceinline__ void tma_load_4d(uint32_t dst_smem, const void* tmap, int32_t c0, int32_t c1, int32_t c2,
+                                            int32_t c3, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::
+            "r"(dst_smem),
+        "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+// a tensor map that lives in global memory (written by the host before the launch): acquire it for the TMA unit
+__device__ __forceinline__ void tensormap_acquire(const void* tmap) {
+    asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tmap) : "memory");
+}
+// generic-proxy accesses (before) are ordered with async-proxy (TMA) accesses (after)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// pull `bytes` (multiple of 16, 16-byte aligned address) into L2 without a destination
+__device__ __forceinline__ void l2_prefetch_bulk(const void* gptr, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
+// 128-bit shared-memory accesses by 32-bit shared address
+__device__ __forceinline__ double2 lds_f64x2(uint32_t addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_f64x2(uint32_t addr, double x, double y) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(x), "d"(y) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }

@@ -66,6 +66,7 @@ constexpr int kBulkMaxPanels = 16;             // blocks up to 16 panels (m <= 1
 
 struct StepList {
     int32_t diag_off, n_diag, panel_off, n_panel, group_base, n_groups, nsl;
+    int32_t n_first;    // leading panel items that are macro tile 0 of their block (one CTA each when the diagonal tile is fused)
     int32_t defer;      // the diagonal tile of panel k+1 is NOT factored at the end of this step but first thing in step k+1
 };
 
@@ -102,7 +103,8 @@ struct Plan {
     int32_t n_test = 0;                               // selected test individuals (variance side channel), 0 = off
     // blob layout (byte offsets inside the plan blob, identical on host and device)
     size_t o_blocks = 0, o_rowsrc = 0, o_rowg = 0, o_z = 0, o_tiles_plain = 0, o_tiles_miss = 0, o_order = 0,
-           o_diag = 0, o_panel = 0, blob_bytes = 0;
+           o_diag = 0, o_panel = 0, o_lmaps = 0, blob_bytes = 0;
+    const void* lmaps_base = nullptr;                 // L buffer the per-block tensor maps in the blob were encoded for
     double gram_ops = 0, solve_flops = 0, decode_bytes = 0;
     bool valid = false;
 };
@@ -130,6 +132,13 @@ struct dbslmm_b200_handle {
     // the waiting CTAs hold SM slots the bulk batches need, and the streaming fit gets slower -- off by default.
     double pdl_ratio = 0.0;
     int defer_max_ctas = 296;                    // steps with at most this many CTAs take their diagonal tile first (see StepList)
+    // panel step kernel: TMA/mbarrier pipeline (default) or the cp.async version (DBSLMM_B200_PANEL=legacy)
+    bool panel_tma = true;
+    int tpc_max = 4, tpc_waves = 4;              // items per CTA: at most tpc_max, and only while a step keeps >= tpc_waves waves of CTAs
+    int tmap_perm = -1;                          // 1: 4-D row-permuting tensor maps, 0: plain 2-D maps (driver refused), -1: not probed yet
+    CUtensorMap wmap;                            // the W tiles (wbuf) as one tensor
+    const void* wmap_base = nullptr;
+    int64_t wmap_tiles = 0;
     // reference panel
     DevBuf bed, stats;
     PinBuf h_stats;                      // per-SNP statistics, filled asynchronously by load_bed
@@ -334,7 +343,7 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
     std::vector<int32_t> diag_items;
     std::vector<int4> panel_items;
     int32_t n_groups = 0;
-    constexpr int kTargetCtas = 296;                  // 2 CTAs per SM on a 148-SM part
+    const int kTargetCtas = 2 * h->n_sm;              // 2 panel CTAs per SM
     for (Batch& B : P.batches) {
         const int32_t* members = P.order.data() + B.ord_off;
         int kmax = 0;
@@ -360,7 +369,9 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
             s.group_base = n_groups;
             // macro tile 0 of every block goes first: its CTA also factors the next diagonal tile (fused), so it
             // should start in the first wave of the launch
-            for (int pass = 0; pass < 2; ++pass)
+            int32_t n_first = 0;
+            for (int pass = 0; pass < 2; ++pass) {
+                if (pass == 1) n_first = (int32_t)panel_items.size() - s.panel_off;
                 for (int i = 0; i < B.ord_n; ++i) {
                     const int b = members[i];
                     const BlockDesc& d = P.blocks[b];
@@ -375,7 +386,9 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
                         for (int sl = 0; sl < nsl; ++sl) panel_items.push_back(make_int4(b, t, sl | (nsl << 8), gid));
                     }
                 }
+            }
             s.n_groups = n_groups - s.group_base;
+            s.n_first = n_first;
             s.n_diag = (int32_t)diag_items.size() - s.diag_off;
             s.n_panel = (int32_t)panel_items.size() - s.panel_off;
             batch_scratch = std::max<int64_t>(batch_scratch, (int64_t)s.n_groups * nsl * 128 * 64);
@@ -401,6 +414,8 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
     P.o_order = place(sizeof(int32_t) * (size_t)nb);
     P.o_diag = place(sizeof(int32_t) * diag_items.size());
     P.o_panel = place(sizeof(int4) * panel_items.size());
+    P.o_lmaps = place(sizeof(CUtensorMap) * (size_t)nb);     // filled by encode_lmaps once the L buffer exists
+    P.lmaps_base = nullptr;
     P.n_groups = n_groups;
     P.blob_bytes = o;
     // fill the pinned staging buffer in place (no intermediate copy; alignment gaps are never read)
@@ -489,6 +504,90 @@ int make_tensor_map(dbslmm_b200_handle* h, CUtensorMap* tm, void* base, int64_t 
     return DBSLMM_B200_OK;
 }
 
+// ---- tensor maps of the TMA panel kernel (chol.cu: chol_panel_tma_kernel)
+int ensure_encoder(dbslmm_b200_handle* h) {
+    if (h->encode) return DBSLMM_B200_OK;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+        return fail(h, DBSLMM_B200_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    h->encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    return DBSLMM_B200_OK;
+}
+// A row-major FP64 matrix (ld doubles per row, `rows` rows) as [64 rows x 16 columns] boxes, 128-byte swizzle.
+// perm: the row index r = 8a + 2b + c is split into the dimensions (b, c, a) with b listed first, so the rows of an
+// 8-row group arrive in shared memory in the order 0,2,4,6,1,3,5,7 (conflict-free FP64 fragment loads, see chol.cu).
+CUresult encode_f64_boxes(dbslmm_b200_handle* h, CUtensorMap* tm, const void* base, int64_t ld, int64_t rows, bool perm) {
+    const cuuint64_t row_bytes = (cuuint64_t)ld * 8;
+    if (perm) {
+        cuuint64_t dims[4] = {(cuuint64_t)ld, 4, 2, (cuuint64_t)((rows + 7) / 8)};
+        cuuint64_t strides[3] = {2 * row_bytes, row_bytes, 8 * row_bytes};
+        cuuint32_t box[4] = {16, 4, 2, 8};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        return h->encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {row_bytes};
+    cuuint32_t box[2] = {16, 64};
+    cuuint32_t estr[2] = {1, 1};
+    return h->encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+// Decide once per handle whether the driver accepts the permuting (non-monotonic stride) 4-D form.
+int probe_perm(dbslmm_b200_handle* h, const void* some_device_ptr) {
+    if (h->tmap_perm >= 0) return DBSLMM_B200_OK;
+    int rc = ensure_encoder(h);
+    if (rc != DBSLMM_B200_OK) return rc;
+    CUtensorMap tm;
+    h->tmap_perm = (encode_f64_boxes(h, &tm, some_device_ptr, 64, 64, true) == CUDA_SUCCESS) ? 1 : 0;
+    return DBSLMM_B200_OK;
+}
+// One tensor map per block over its matrix in the L buffer, written into the pinned plan blob (they travel with it).
+// Blocks of a single panel never run a K loop: their slot stays zero.
+int encode_lmaps(dbslmm_b200_handle* h, Plan& P) {
+    int rc = ensure_encoder(h);
+    if (rc != DBSLMM_B200_OK) return rc;
+    rc = probe_perm(h, h->lbuf.p);
+    if (rc != DBSLMM_B200_OK) return rc;
+    CUtensorMap* maps = reinterpret_cast<CUtensorMap*>((uint8_t*)h->h_blob.p + P.o_lmaps);
+    const int nb = P.n_blocks;
+    const bool perm = h->tmap_perm == 1;
+    std::atomic<int> bad{0};
+    auto work = [&](int b0, int b1) {
+        for (int b = b0; b < b1; ++b) {
+            const BlockDesc& d = P.blocks[b];
+            if (d.mp <= 64) { std::memset(&maps[b], 0, sizeof(CUtensorMap)); continue; }
+            if (encode_f64_boxes(h, &maps[b], (const double*)h->lbuf.p + d.moff, d.ld, d.nrows, perm) != CUDA_SUCCESS) bad.store(1);
+        }
+    };
+    const int nthr = (int)std::max<int64_t>(1, std::min<int64_t>({8, (int64_t)std::thread::hardware_concurrency(), (int64_t)nb / 128}));
+    if (nthr == 1) work(0, nb);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nthr; ++t) th.emplace_back(work, (int)((int64_t)nb * t / nthr), (int)((int64_t)nb * (t + 1) / nthr));
+        for (std::thread& x : th) x.join();
+    }
+    if (bad.load()) return fail(h, DBSLMM_B200_ERR_CUDA, "cuTensorMapEncodeTiled failed for a block matrix");
+    P.lmaps_base = h->lbuf.p;
+    return DBSLMM_B200_OK;
+}
+int encode_wmap(dbslmm_b200_handle* h, int64_t n_tiles) {
+    if (h->wmap_base == h->wbuf.p && h->wmap_tiles == n_tiles) return DBSLMM_B200_OK;
+    int rc = ensure_encoder(h);
+    if (rc != DBSLMM_B200_OK) return rc;
+    rc = probe_perm(h, h->wbuf.p);
+    if (rc != DBSLMM_B200_OK) return rc;
+    if (encode_f64_boxes(h, &h->wmap, h->wbuf.p, 64, 64 * n_tiles, h->tmap_perm == 1) != CUDA_SUCCESS)
+        return fail(h, DBSLMM_B200_ERR_CUDA, "cuTensorMapEncodeTiled failed for the W tiles");
+    h->wmap_base = h->wbuf.p;
+    h->wmap_tiles = n_tiles;
+    return DBSLMM_B200_OK;
+}
+
 }  // namespace
 
 // =============================================================================================
@@ -527,6 +626,15 @@ int dbslmm_b200_create(int device, dbslmm_b200_handle** out) {
         if (std::sscanf(e, "%d,%d", &a, &b) == 2 && a >= 1 && a <= 255 && b >= 1) { h->splitk_max = a; h->splitk_min_blocks = b; }
     }
     if (const char* e = std::getenv("DBSLMM_B200_DEFER_CTAS")) h->defer_max_ctas = std::atoi(e);
+    else h->defer_max_ctas = 2 * h->n_sm;
+    if (const char* e = std::getenv("DBSLMM_B200_PANEL")) h->panel_tma = (std::strcmp(e, "legacy") != 0);
+    if (const char* e = std::getenv("DBSLMM_B200_TPC")) {         // "max[,waves]"
+        int a = 0, b = 0;
+        const int n = std::sscanf(e, "%d,%d", &a, &b);
+        if (n >= 1 && a >= 1 && a <= 64) h->tpc_max = a;
+        if (n >= 2 && b >= 0) h->tpc_waves = b;
+    }
+    if (const char* e = std::getenv("DBSLMM_B200_TMAP_PERM")) h->tmap_perm = (e[0] != '0') ? -1 : 0;
     if (const char* e = std::getenv("DBSLMM_B200_PDL")) h->pdl_ratio = std::atof(e);
     if (const char* e = std::getenv("DBSLMM_B200_CLASSES")) {     // e.g. "4,8,12,16,32"
         std::vector<int> b;
@@ -843,6 +951,18 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
     }
     const size_t out_bytes = sizeof(double) * n_res + sizeof(int32_t) * (size_t)(2 * nb);
     CU_TRY(h, h->h_out.ensure(out_bytes + 128));
+    const bool tma_panel = h->panel_tma && !pcg && !quad;
+    bool lmaps_dirty = false;                   // the maps in the pinned blob were (re)encoded: a cached device plan needs them again
+    if (tma_panel && nb > 0) {
+        int rc = encode_wmap(h, 2 * (int64_t)std::max(nb, 1));
+        if (rc != DBSLMM_B200_OK) return rc;
+        if (P.lmaps_base != h->lbuf.p) {
+            rc = encode_lmaps(h, P);
+            if (rc != DBSLMM_B200_OK) return rc;
+            lmaps_dirty = true;
+            tr.mark("tensor maps encoded");
+        }
+    }
 
     uint8_t* dblob = (uint8_t*)h->planblob.p;   // (re-pointed below if the plan has to be rebuilt)
     const BlockDesc* d_blocks = (const BlockDesc*)(dblob + P.o_blocks);
@@ -875,6 +995,9 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
             tr.mark("all uploads issued");
         }
     } else if (P.n_snp_rows > 0) {
+        if (lmaps_dirty)
+            CU_TRY(h, cudaMemcpyAsync(dblob + P.o_lmaps, (uint8_t*)h->h_blob.p + P.o_lmaps, sizeof(CUtensorMap) * (size_t)nb,
+                                      cudaMemcpyHostToDevice, st));
         // same CSR layout, new z-scores
         double* z = reinterpret_cast<double*>((uint8_t*)h->h_blob.p + P.o_z);
         for (int b = 0; b < nb; ++b) {
@@ -914,6 +1037,7 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
             d_order = (const int32_t*)(dblob + P.o_order);
             d_diag = (const int32_t*)(dblob + P.o_diag);
             d_panel = (const int4*)(dblob + P.o_panel);
+            if (tma_panel) { rc = encode_lmaps(h, P); if (rc != DBSLMM_B200_OK) return rc; }   // the blob was rebuilt
             CU_TRY(h, cudaMemcpyAsync(dblob, h->h_blob.p, P.blob_bytes, cudaMemcpyHostToDevice, st));
             CU_TRY(h, cudaMemsetAsync(d_status, 0, sizeof(int32_t) * (size_t)std::max(2 * nb, 1), st));
         }
@@ -1071,11 +1195,31 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
                         ++n_launch;
                         ++n_chol_launch;
                     }
-                    CU_TRY(h, launch_chol_panel(d_blocks, d_panel + s.panel_off, s.n_panel, d_diag + s.diag_off,
-                                                deferred_here ? s.n_diag : 0, (int32_t)k, (const double*)h->sigma.p,
-                                                (double*)h->lbuf.p, (double*)h->wbuf.p, wstride, h->fuse_diag && !s.defer, ridge,
-                                                (double*)h->scratch.p + B.scratch_off, (int32_t*)h->counters.p, s.group_base,
-                                                d_status, (int32_t*)h->dflag.p, pdl_batch && k > 0, cs));
+                    const bool fuse_end = h->fuse_diag && !s.defer;
+                    if (tma_panel) {
+                        // CTAs: one per item for split-K / flag-synchronised steps and for the macro tiles that factor
+                        // the next diagonal tile; otherwise up to tpc_max consecutive items (same block, same W) per CTA
+                        // as long as the step keeps several waves of CTAs
+                        int n_single = s.n_panel, tpc = 1;
+                        if (s.nsl == 1 && !deferred_here) {
+                            n_single = fuse_end ? s.n_first : 0;
+                            const int rest = s.n_panel - n_single;
+                            tpc = std::max(1, std::min(h->tpc_max, rest / std::max(1, h->tpc_waves * 2 * h->n_sm)));   // tpc_waves = 0: always tpc_max
+                        }
+                        CU_TRY(h, launch_chol_panel_tma(d_blocks, d_panel + s.panel_off, s.n_panel, n_single, tpc,
+                                                        d_diag + s.diag_off, deferred_here ? s.n_diag : 0, (int32_t)k,
+                                                        (const CUtensorMap*)(dblob + P.o_lmaps), h->wmap, h->tmap_perm == 1 ? 1 : 0,
+                                                        nb, (const double*)h->sigma.p, (double*)h->lbuf.p, (double*)h->wbuf.p,
+                                                        wstride, fuse_end, ridge, (double*)h->scratch.p + B.scratch_off,
+                                                        (int32_t*)h->counters.p, s.group_base, d_status, (int32_t*)h->dflag.p,
+                                                        pdl_batch && k > 0, cs));
+                    } else {
+                        CU_TRY(h, launch_chol_panel(d_blocks, d_panel + s.panel_off, s.n_panel, d_diag + s.diag_off,
+                                                    deferred_here ? s.n_diag : 0, (int32_t)k, (const double*)h->sigma.p,
+                                                    (double*)h->lbuf.p, (double*)h->wbuf.p, wstride, fuse_end, ridge,
+                                                    (double*)h->scratch.p + B.scratch_off, (int32_t*)h->counters.p, s.group_base,
+                                                    d_status, (int32_t*)h->dflag.p, pdl_batch && k > 0, cs));
+                    }
                     ++n_launch;
                     ++n_chol_launch;
                 }

@@ -21,6 +21,13 @@ MODES = {
     "deep_split_k": {"DBSLMM_B200_SPLITK": "32,1"},
     "programmatic_dependent_launch": {"DBSLMM_B200_PDL": "0.000001"},
     "seven_size_classes": {"DBSLMM_B200_CLASSES": "2,4,8,12,16,24"},
+    # the panel step kernel: TMA/mbarrier pipeline (default) with several items per CTA, one item per CTA, plain 2-D
+    # tensor maps (no row permutation), and the cp.async kernel of round 1
+    "tma_many_items_per_cta": {"DBSLMM_B200_TPC": "8,0"},
+    "tma_three_items_per_cta_diag_first": {"DBSLMM_B200_TPC": "3,0", "DBSLMM_B200_DEFER_CTAS": "1000000"},
+    "tma_one_item_per_cta": {"DBSLMM_B200_TPC": "1"},
+    "tma_plain_2d_tensor_maps": {"DBSLMM_B200_TMAP_PERM": "0", "DBSLMM_B200_TPC": "2,0"},
+    "legacy_cp_async_panel_kernel": {"DBSLMM_B200_PANEL": "legacy"},
 }
 KEYS = sorted({k for m in MODES.values() for k in m})
 
