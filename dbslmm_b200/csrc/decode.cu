@@ -17,7 +17,7 @@
 namespace dbslmm {
 
 static constexpr int kWarpsPerCta = 8;
-static constexpr int kDecRing = 4;      // staged rows per warp in the decoder
+// staged rows per warp in the decoder: 4 (three row copies in flight per warp), 2 for very long rows (n_ref > ~25,000)
 
 struct RowStage {
     // returns byte offset of the row inside the staged buffer
@@ -63,8 +63,9 @@ snp_stats_kernel(const uint8_t* __restrict__ bed, int64_t n_snp, int32_t n_ref, 
     mbar_fence_init();
     __syncwarp();
 
-    const int64_t gw = (int64_t)blockIdx.x * kWarpsPerCta + warp;
-    const int64_t stride = (int64_t)gridDim.x * kWarpsPerCta;
+    const int wpc = blockDim.x >> 5;          // warps per CTA (8 unless a row is too long for 16 staging buffers)
+    const int64_t gw = (int64_t)blockIdx.x * wpc + warp;
+    const int64_t stride = (int64_t)gridDim.x * wpc;
     const int nwords = (pitch + 3) >> 2;
     uint32_t phase[2] = {0, 0};
     uint32_t off[2] = {0, 0};
@@ -127,7 +128,7 @@ __device__ __forceinline__ uint4 expand16(uint32_t w) {
 // row_g[r] = SNP-row index that receives the scale factors (or -1 for mask rows).
 // ------------------------------------------------------------------------------------------
 // OWN = true: no statistics array; the warp counts the genotypes of the row it has staged (streaming fit).
-template <bool OWN>
+template <bool OWN, int kDecRing>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 decode_rows_kernel(const uint8_t* __restrict__ bed, int32_t n_ref, int32_t pitch, int32_t n_pad,
                    int32_t buf_bytes, const uint32_t* __restrict__ row_src, const int32_t* __restrict__ row_g,
@@ -145,8 +146,9 @@ decode_rows_kernel(const uint8_t* __restrict__ bed, int32_t n_ref, int32_t pitch
     mbar_fence_init();
     __syncwarp();
 
-    const int64_t gw = (int64_t)blockIdx.x * kWarpsPerCta + warp;
-    const int64_t stride = (int64_t)gridDim.x * kWarpsPerCta;
+    const int wpc = blockDim.x >> 5;
+    const int64_t gw = (int64_t)blockIdx.x * wpc + warp;
+    const int64_t stride = (int64_t)gridDim.x * wpc;
     const int nwords = (pitch + 3) >> 2;     // input words holding real samples
     const int nout = n_pad >> 4;             // 16-byte output chunks per row
     // ring of kDecRing staged rows per warp: kDecRing - 1 TMA row copies in flight while one row is expanded.
@@ -292,23 +294,55 @@ cudaError_t launch_block_missing(const BlockDesc* blocks, int32_t n_blocks, cons
 }
 
 static int stage_bytes(int32_t pitch) { return ((pitch + 15 + 16 + 15) / 16) * 16 + 16; }
+static constexpr size_t kStageSmemMax = 200 * 1024;
+
+// Largest reference panel the row-staging kernels take: one warp must hold two whole .bed rows in shared memory.
+int32_t decode_max_n_ref() {
+    int32_t pitch = (int32_t)(kStageSmemMax / 2) - 64;
+    while (2 * (size_t)stage_bytes(pitch) > kStageSmemMax) --pitch;
+    return pitch * 4;
+}
+// warps per CTA for `ring` staging buffers per warp (8, halved until the buffers fit; 0: even one warp does not fit)
+static int stage_warps(int buf, int ring) {
+    int w = kWarpsPerCta;
+    while (w >= 1 && (size_t)w * ring * buf > kStageSmemMax) w >>= 1;
+    return w;
+}
 
 cudaError_t launch_snp_stats(const uint8_t* bed, int64_t n_snp, int32_t n_ref, SnpStat* stats, int n_sm,
                              cudaStream_t st) {
     const int32_t pitch = (n_ref + 3) / 4;
     const int buf = stage_bytes(pitch);
-    const size_t smem = (size_t)kWarpsPerCta * 2 * buf;
-    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    const int wpc = stage_warps(buf, 2);
+    if (wpc < 1) return cudaErrorInvalidValue;
+    const size_t smem = (size_t)wpc * 2 * buf;
     cudaError_t e = cudaFuncSetAttribute(snp_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    int64_t ctas = (n_snp + kWarpsPerCta - 1) / kWarpsPerCta;
+    int64_t ctas = (n_snp + wpc - 1) / wpc;
     const int64_t cap = (int64_t)n_sm * 8;
     if (ctas > cap) ctas = cap;
     if (ctas < 1) ctas = 1;
-    snp_stats_kernel<<<(unsigned)ctas, kWarpsPerCta * 32, smem, st>>>(bed, n_snp, n_ref, pitch, buf, stats);
+    snp_stats_kernel<<<(unsigned)ctas, wpc * 32, smem, st>>>(bed, n_snp, n_ref, pitch, buf, stats);
     return cudaGetLastError();
 }
 
+template <bool OWN, int RING>
+static cudaError_t launch_decode_t(const uint8_t* bed, int32_t n_ref, int32_t pitch, int32_t n_pad, int buf, int wpc,
+                                   const uint32_t* row_src, const int32_t* row_g, int64_t n_rows, const SnpStat* stats,
+                                   double tau, int8_t* codes, int32_t* rowN, int32_t* rowS, double* rowR, int n_sm,
+                                   cudaStream_t st) {
+    const size_t smem = (size_t)wpc * RING * buf;
+    cudaError_t e = cudaFuncSetAttribute(decode_rows_kernel<OWN, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int64_t ctas = (n_rows + wpc - 1) / wpc;
+    const int64_t cap = (int64_t)n_sm * 8;
+    if (ctas > cap) ctas = cap;
+    decode_rows_kernel<OWN, RING><<<(unsigned)ctas, wpc * 32, smem, st>>>(bed, n_ref, pitch, n_pad, buf, row_src, row_g, n_rows,
+                                                                        stats, tau, codes, rowN, rowS, rowR);
+    return cudaGetLastError();
+}
+
+// stats == nullptr: the decoder derives the per-SNP counts itself (streaming fit)
 cudaError_t launch_decode_rows(const uint8_t* bed, int32_t n_ref, int32_t n_pad, const uint32_t* row_src,
                                const int32_t* row_g, int64_t n_rows, const SnpStat* stats, double tau,
                                int8_t* codes, int32_t* rowN, int32_t* rowS, double* rowR, int n_sm,
@@ -316,22 +350,16 @@ cudaError_t launch_decode_rows(const uint8_t* bed, int32_t n_ref, int32_t n_pad,
     if (n_rows == 0) return cudaSuccess;
     const int32_t pitch = (n_ref + 3) / 4;
     const int buf = stage_bytes(pitch);
-    const size_t smem = (size_t)kWarpsPerCta * kDecRing * buf;
-    if (smem > 200 * 1024) return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(decode_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(decode_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    int64_t ctas = (n_rows + kWarpsPerCta - 1) / kWarpsPerCta;
-    const int64_t cap = (int64_t)n_sm * 8;
-    if (ctas > cap) ctas = cap;
-    if (stats)
-        decode_rows_kernel<false><<<(unsigned)ctas, kWarpsPerCta * 32, smem, st>>>(bed, n_ref, pitch, n_pad, buf, row_src, row_g,
-                                                                                 n_rows, stats, tau, codes, rowN, rowS, rowR);
-    else      // stats == nullptr: the decoder derives the per-SNP counts itself
-        decode_rows_kernel<true><<<(unsigned)ctas, kWarpsPerCta * 32, smem, st>>>(bed, n_ref, pitch, n_pad, buf, row_src, row_g,
-                                                                                n_rows, stats, tau, codes, rowN, rowS, rowR);
-    return cudaGetLastError();
+    // four staging buffers per warp and eight warps per CTA while they fit; long rows fall back to two buffers, then
+    // to fewer warps (n_ref up to decode_max_n_ref())
+    if (stage_warps(buf, 4) == kWarpsPerCta) {
+        return stats ? launch_decode_t<false, 4>(bed, n_ref, pitch, n_pad, buf, kWarpsPerCta, row_src, row_g, n_rows, stats, tau, codes, rowN, rowS, rowR, n_sm, st)
+                     : launch_decode_t<true, 4>(bed, n_ref, pitch, n_pad, buf, kWarpsPerCta, row_src, row_g, n_rows, stats, tau, codes, rowN, rowS, rowR, n_sm, st);
+    }
+    const int wpc = stage_warps(buf, 2);
+    if (wpc < 1) return cudaErrorInvalidValue;
+    return stats ? launch_decode_t<false, 2>(bed, n_ref, pitch, n_pad, buf, wpc, row_src, row_g, n_rows, stats, tau, codes, rowN, rowS, rowR, n_sm, st)
+                 : launch_decode_t<true, 2>(bed, n_ref, pitch, n_pad, buf, wpc, row_src, row_g, n_rows, stats, tau, codes, rowN, rowS, rowR, n_sm, st);
 }
 
 }  // namespace dbslmm

@@ -105,6 +105,7 @@ struct Plan {
     size_t o_blocks = 0, o_rowsrc = 0, o_rowg = 0, o_z = 0, o_tiles_plain = 0, o_tiles_miss = 0, o_order = 0,
            o_diag = 0, o_panel = 0, o_lmaps = 0, blob_bytes = 0;
     const void* lmaps_base = nullptr;                 // L buffer the per-block tensor maps in the blob were encoded for
+    uint64_t fingerprint = 0;                         // of the inputs the plan was built from (FLAG_PLAN_CACHED re-use check)
     double gram_ops = 0, solve_flops = 0, decode_bytes = 0;
     bool valid = false;
 };
@@ -134,7 +135,7 @@ struct dbslmm_b200_handle {
     int defer_max_ctas = 296;                    // steps with at most this many CTAs take their diagonal tile first (see StepList)
     // panel step kernel: TMA/mbarrier pipeline (default) or the cp.async version (DBSLMM_B200_PANEL=legacy)
     bool panel_tma = true;
-    int tpc_max = 4, tpc_waves = 4;              // items per CTA: at most tpc_max, and only while a step keeps >= tpc_waves waves of CTAs
+    int tpc_max = 4, tpc_waves = 2;              // items per CTA: at most tpc_max, and only while a step keeps >= tpc_waves waves of CTAs
     int tmap_perm = -1;                          // 1: 4-D row-permuting tensor maps, 0: plain 2-D maps (driver refused), -1: not probed yet
     CUtensorMap wmap;                            // the W tiles (wbuf) as one tensor
     const void* wmap_base = nullptr;
@@ -484,6 +485,39 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
     return DBSLMM_B200_OK;
 }
 
+// Fingerprint of everything a cached plan depends on: the CSR block lists (not the z-scores, which a cached plan
+// refreshes), the variance side channel's row count and the panel's shape.  Four independent multiply-xor lanes over
+// 64-bit words: ~0.3 ms for a genome-wide call.
+uint64_t hash_words(const void* p, size_t bytes, uint64_t seed) {
+    const uint64_t* w = (const uint64_t*)p;
+    const size_t n = bytes / 8;
+    uint64_t h0 = seed ^ 0x9E3779B97F4A7C15ull, h1 = seed + 0xC2B2AE3D27D4EB4Full, h2 = ~seed, h3 = seed * 0x165667B19E3779F9ull + 1;
+    size_t i = 0;
+    for (; i + 4 <= n; i += 4) {
+        h0 = (h0 ^ w[i]) * 0xFF51AFD7ED558CCDull; h1 = (h1 ^ w[i + 1]) * 0xC4CEB9FE1A85EC53ull;
+        h2 = (h2 ^ w[i + 2]) * 0x9FB21C651E98DF25ull; h3 = (h3 ^ w[i + 3]) * 0xD6E8FEB86659FD93ull;
+        h0 ^= h0 >> 29; h1 ^= h1 >> 31; h2 ^= h2 >> 30; h3 ^= h3 >> 28;
+    }
+    uint64_t tail = 0;
+    for (size_t b = i * 8; b < bytes; ++b) tail = tail * 257 + ((const uint8_t*)p)[b];
+    uint64_t h = h0 ^ (h1 * 3) ^ (h2 * 5) ^ (h3 * 7) ^ tail ^ (uint64_t)bytes;
+    h ^= h >> 33; h *= 0xFF51AFD7ED558CCDull; h ^= h >> 33;
+    return h;
+}
+uint64_t plan_fingerprint(const dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
+    const int nb = a->n_blocks;
+    uint64_t f = hash_words(a->s_off, sizeof(int32_t) * (size_t)(nb + 1), 1);
+    f = hash_words(a->s_pos, sizeof(int32_t) * (size_t)a->s_off[nb], f);
+    if (a->l_off) {
+        f = hash_words(a->l_off, sizeof(int32_t) * (size_t)(nb + 1), f + 2);
+        f = hash_words(a->l_pos, sizeof(int32_t) * (size_t)a->l_off[nb], f);
+    }
+    int64_t n_test = 0;
+    if (a->test_bed) for (int i = 0; i < a->test_n_total; ++i) n_test += (a->test_indicator[i] != 0);
+    const int64_t shape[4] = {h->n_snp, (int64_t)h->n_ref, n_test, (int64_t)(a->l_off != nullptr)};
+    return hash_words(shape, sizeof shape, f);
+}
+
 int make_tensor_map(dbslmm_b200_handle* h, CUtensorMap* tm, void* base, int64_t n_rows, int32_t n_pad) {
     if (!h->encode) {
         void* fn = nullptr;
@@ -558,10 +592,12 @@ int encode_lmaps(dbslmm_b200_handle* h, Plan& P) {
     const bool perm = h->tmap_perm == 1;
     std::atomic<int> bad{0};
     auto work = [&](int b0, int b1) {
+        cudaSetDevice(h->device);          // worker threads: the driver entry point wants a current context
         for (int b = b0; b < b1; ++b) {
             const BlockDesc& d = P.blocks[b];
             if (d.mp <= 64) { std::memset(&maps[b], 0, sizeof(CUtensorMap)); continue; }
-            if (encode_f64_boxes(h, &maps[b], (const double*)h->lbuf.p + d.moff, d.ld, d.nrows, perm) != CUDA_SUCCESS) bad.store(1);
+            const CUresult r = encode_f64_boxes(h, &maps[b], (const double*)h->lbuf.p + d.moff, d.ld, d.nrows, perm);
+            if (r != CUDA_SUCCESS) bad.store((int)r);
         }
     };
     const int nthr = (int)std::max<int64_t>(1, std::min<int64_t>({8, (int64_t)std::thread::hardware_concurrency(), (int64_t)nb / 128}));
@@ -571,7 +607,8 @@ int encode_lmaps(dbslmm_b200_handle* h, Plan& P) {
         for (int t = 0; t < nthr; ++t) th.emplace_back(work, (int)((int64_t)nb * t / nthr), (int)((int64_t)nb * (t + 1) / nthr));
         for (std::thread& x : th) x.join();
     }
-    if (bad.load()) return fail(h, DBSLMM_B200_ERR_CUDA, "cuTensorMapEncodeTiled failed for a block matrix");
+    if (bad.load() && nthr > 1) { bad.store(0); work(0, nb); }      // once more on the calling thread
+    if (bad.load()) return fail(h, DBSLMM_B200_ERR_CUDA, "cuTensorMapEncodeTiled failed for a block matrix (CUresult " + std::to_string(bad.load()) + ")");
     P.lmaps_base = h->lbuf.p;
     return DBSLMM_B200_OK;
 }
@@ -698,6 +735,9 @@ const char* dbslmm_b200_last_error(const dbslmm_b200_handle* h) { return h ? h->
 int dbslmm_b200_load_bed(dbslmm_b200_handle* h, const uint8_t* bed, int64_t n_snp, int32_t n_ref) {
     if (!h) return DBSLMM_B200_ERR_ARG;
     if (!bed || n_snp <= 0 || n_ref <= 1) return fail(h, DBSLMM_B200_ERR_ARG, "load_bed: bad arguments");
+    if (n_ref > decode_max_n_ref())
+        return fail(h, DBSLMM_B200_ERR_ARG, "load_bed: n_ref = " + std::to_string(n_ref) + " is above the decoder's limit of " +
+                                            std::to_string(decode_max_n_ref()) + " individuals (two .bed rows must fit in shared memory)");
     CU_TRY(h, cudaSetDevice(h->device));
     if (h->bed_pending) { CU_TRY(h, cudaEventSynchronize(h->ev_bed)); h->bed_pending = false; }   // buffers may be re-allocated
     const int32_t pitch = (n_ref + 3) / 4;
@@ -891,9 +931,13 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
     UploadPlan U;
     // ---- plan
     Plan& P = h->plan;
-    const bool reuse = !streaming && (a->flags & DBSLMM_B200_FLAG_PLAN_CACHED) && P.valid && !P.streaming &&
-                       P.n_blocks == a->n_blocks && P.tot_s == a->s_off[a->n_blocks] &&
-                       P.tot_l == (a->l_off ? a->l_off[a->n_blocks] : 0);
+    // FLAG_PLAN_CACHED re-uses the device plan only if the block lists, the test-row count and the panel shape are the
+    // ones it was built from (fingerprint); otherwise the plan is silently rebuilt
+    const bool want_reuse = !streaming && (a->flags & DBSLMM_B200_FLAG_PLAN_CACHED) && P.valid && !P.streaming &&
+                            P.n_blocks == a->n_blocks && P.tot_s == a->s_off[a->n_blocks] &&
+                            P.tot_l == (a->l_off ? a->l_off[a->n_blocks] : 0);
+    const uint64_t fp = (want_reuse || !streaming) ? plan_fingerprint(h, a) : 0;
+    const bool reuse = want_reuse && P.fingerprint == fp;
     if (!reuse) {
         // The plan is built while the panel may still be crossing PCIe, so it cannot look at it: it assumes no
         // block has missing calls; that is checked on the device (below) and the plan is rebuilt with the true
@@ -919,6 +963,7 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
         }
         rc = build_plan(h, a, P, nullptr);
         if (rc != DBSLMM_B200_OK) { P.valid = false; return rc; }
+        P.fingerprint = fp;
         tr.mark("plan built");
     }
     if (!streaming) { int rc = ensure_stats(h); if (rc != DBSLMM_B200_OK) return rc; }
@@ -979,6 +1024,15 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
     int32_t* d_iters = d_status + nb;
 
     int n_launch = 0, n_chol_launch = 0;
+    if (reuse && P.n_snp_rows > 0) {
+        // same CSR layout, new z-scores: refill the pinned z array (host work, before the first event)
+        double* z = reinterpret_cast<double*>((uint8_t*)h->h_blob.p + P.o_z);
+        for (int b = 0; b < nb; ++b) {
+            const BlockDesc& d = P.blocks[b];
+            if (d.ms > 0) std::memcpy(z + d.goff, a->s_z + a->s_off[b], sizeof(double) * (size_t)d.ms);
+            if (d.m > d.ms) std::memcpy(z + d.goff + d.ms, a->l_z + a->l_off[b], sizeof(double) * (size_t)(d.m - d.ms));
+        }
+    }
     CU_TRY(h, cudaEventRecord(h->ev[0], st));
     // ---- upload
     if (!reuse) {
@@ -998,14 +1052,8 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
         if (lmaps_dirty)
             CU_TRY(h, cudaMemcpyAsync(dblob + P.o_lmaps, (uint8_t*)h->h_blob.p + P.o_lmaps, sizeof(CUtensorMap) * (size_t)nb,
                                       cudaMemcpyHostToDevice, st));
-        // same CSR layout, new z-scores
-        double* z = reinterpret_cast<double*>((uint8_t*)h->h_blob.p + P.o_z);
-        for (int b = 0; b < nb; ++b) {
-            const BlockDesc& d = P.blocks[b];
-            for (int j = 0; j < d.m; ++j)
-                z[d.goff + j] = (j < d.ms) ? a->s_z[a->s_off[b] + j] : a->l_z[a->l_off[b] + (j - d.ms)];
-        }
-        CU_TRY(h, cudaMemcpyAsync(dblob + P.o_z, z, sizeof(double) * (size_t)P.n_snp_rows, cudaMemcpyHostToDevice, st));
+        CU_TRY(h, cudaMemcpyAsync(dblob + P.o_z, (uint8_t*)h->h_blob.p + P.o_z, sizeof(double) * (size_t)P.n_snp_rows,
+                                  cudaMemcpyHostToDevice, st));
     }
     CU_TRY(h, cudaMemsetAsync(d_status, 0, sizeof(int32_t) * (size_t)std::max(2 * nb, 1), st));
     CU_TRY(h, h->flagbuf.ensure(256));
@@ -1376,6 +1424,9 @@ int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
     if (!h || !a) return DBSLMM_B200_ERR_ARG;
     if (!a->bed && h->n_snp == 0) return fail(h, DBSLMM_B200_ERR_STATE, "fit before load_bed (and no fit_args.bed)");
     if (a->bed && (a->bed_n_snp <= 0 || a->bed_n_ref <= 1)) return fail(h, DBSLMM_B200_ERR_ARG, "fit: bad bed_n_snp / bed_n_ref");
+    if (a->bed && a->bed_n_ref > decode_max_n_ref())
+        return fail(h, DBSLMM_B200_ERR_ARG, "fit: bed_n_ref = " + std::to_string(a->bed_n_ref) + " is above the decoder's limit of " +
+                                            std::to_string(decode_max_n_ref()) + " individuals");
     const bool quad = a->quadform_out != nullptr;
     if (a->n_blocks < 0 || !a->s_off || (!quad && (a->n_folds < 1 || !a->sigma_s || a->n_obs <= 0 || !a->beta_s_out)))
         return fail(h, DBSLMM_B200_ERR_ARG, "fit: bad arguments");
@@ -1419,6 +1470,20 @@ int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
     h->stats_valid = false;
     h->plan.valid = false;
     int rc = fit_impl(h, a, true);
+    if (rc < 0) {
+        // A streaming fit that failed part-way may have copies from the caller's buffer and kernels in flight, and the
+        // panel on the device is incomplete: drain everything (the header promises `bed` is not needed after the call
+        // returns) and forget the panel, so a later fit without fit_args.bed fails with ERR_STATE instead of decoding it.
+        const std::string msg = h->err;
+        cudaDeviceSynchronize();
+        cudaGetLastError();
+        h->n_snp = 0; h->n_ref = 0; h->pitch = 0; h->n_pad = 0;
+        h->bed_pending = false;
+        h->stats_valid = false;
+        h->plan.valid = false;
+        h->err = msg;
+        return rc;
+    }
     if (rc == kRetryResident) {
         // the panel is resident by now; statistics are computed on demand.  Panels with missing calls tend to come
         // again (folds, repeated fits): remember, so the next call does not stream speculatively

@@ -15,6 +15,7 @@ cudaError_t launch_decode_rows(const uint8_t* bed, int32_t n_ref, int32_t n_pad,
                                int8_t* codes, int32_t* rowN, int32_t* rowS, double* rowR, int n_sm,
                                cudaStream_t st);
 
+int32_t decode_max_n_ref();          // largest n_ref the row-staging kernels (decoder, statistics) can take
 cudaError_t launch_rows_missing(const int32_t* rowN, int64_t n_rows, int32_t n_ref, int32_t* flag, cudaStream_t st);
 cudaError_t launch_block_missing(const BlockDesc* blocks, int32_t n_blocks, const uint32_t* row_src,
                                  const SnpStat* stats, int32_t n_ref, int32_t* flags, cudaStream_t st);

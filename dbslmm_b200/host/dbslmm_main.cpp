@@ -187,6 +187,8 @@ int main(int argc, char* argv[]) {
         if (j.r.size() == 0) { cerr << "ERROR: " << j.r << " dose not exist!" << endl; exit(1); }
     }
     if (cPar.h > 1 || cPar.h < 0) { cerr << "ERROR: -h is not correct (0, 1)!" << endl; exit(1); }   // :220-227
+    // the reference accepts -h 0 and then prints NaN effects (the ridge 1 / (h / nsnp * n) is infinite); say so instead
+    if (cPar.h == 0) { cerr << "ERROR: -h 0 leaves the ridge 1/(h/nsnp*n) undefined (the reference prints NaN effects): give -h > 0" << endl; exit(1); }
     if (cPar.t > 100 || cPar.t < 1) { cerr << "ERROR: -t is not correct (1, 100)!" << endl; exit(1); }
     if (cPar.n <= 0 || cPar.nsnp <= 0) { cerr << "ERROR: -n and -nsnp must be positive!" << endl; exit(1); }
     const int solver = (cPar.solver == "pcg") ? DBSLMM_B200_SOLVER_PCG : DBSLMM_B200_SOLVER_CHOLESKY;
@@ -232,7 +234,9 @@ int main(int argc, char* argv[]) {
     if (constr) {
         cout << "Calculating MAF of reference panel ..." << endl;
         ref_maf.resize((size_t)n_snp_all);
-        dbslmm_b200_snp_stats(hs[0], ref_maf.data(), nullptr);
+        if (dbslmm_b200_snp_stats(hs[0], ref_maf.data(), nullptr) != DBSLMM_B200_OK) {
+            cerr << "ERROR: snp_stats: " << dbslmm_b200_last_error(hs[0]) << endl; exit(2);
+        }
     } else {
         cout << "[WARNING] Do not consider the difference between reference panel and summary data ..." << endl;
     }

@@ -7,7 +7,7 @@
 //
 // PARITY PIN: the restatement is checked against the UNMODIFIED reference sources
 // compiled over a minimal Armadillo/Boost shim (oracle/shim, oracle/build_ref.sh ->
-// oracle/_ref/) in tests/test_oracle_vs_ref.py and against the committed golden
+// oracle/_ref/) in tests/test_oracle.py and against the committed golden
 // vectors in tests/golden/ that the same reference build produced.  The shim replaces
 // Armadillo's BLAS/LAPACK back end with plain loops, so pins are at the 1e-12 level,
 // not bit level ("Armadillo version unpinned").

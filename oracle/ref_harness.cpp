@@ -1,6 +1,6 @@
 // oracle/ref_harness.cpp -- extern "C" doorway into the UNMODIFIED reference classes
 // (IO, SNPPROC, DBSLMMFIT from /root/reference/scr, compiled over oracle/shim).
-// TEST INFRASTRUCTURE: used to pin the oracle (tests/test_oracle_vs_ref.py), to generate the
+// TEST INFRASTRUCTURE: used to pin the oracle (tests/test_oracle.py), to generate the
 // golden vectors under tests/golden/ and as bench.py's `--impl reference` arm.
 #include <cstdint>
 #include <cstring>
