@@ -37,6 +37,7 @@ CONFIGS = {
     "c4": (1_100_000, list(range(1, 23)), 3000, 2000, 300_000),      # c3 + 3 heritability folds + PRS over a 10k-sample panel
     "c5": (1_100_000, list(range(1, 23)), 5000, 20_000, 300_000),    # large-reference stress
     "c2": (90_000, [1], 3000, 500, 300_000),
+    "chr20_22": (60_000, [20, 21, 22], 3000, 2000, 300_000),         # three real-sized chromosomes at the c3 SNP density (CLI tests)
     "tiny": (6_000, [22], 400, 400, 2400),
 }
 WORKLOAD_NAME = {
@@ -44,6 +45,7 @@ WORKLOAD_NAME = {
     "c4": "tuning version: the c3 genome with h2 folds 0.8/1.0/1.2 sharing one Gram per block + PRS of the 3 folds over a 10k-sample validation .bed",
     "c5": "large-reference stress: 22 chr, ~1.1M SNPs, 1,703 EUR LD blocks of up to 5,000 SNPs, n_ref=20000",
     "c2": "LMM-size synthetic chr1: ~90k SNPs, 133 EUR LD blocks, n_ref=500",
+    "chr20_22": "chromosomes 20-22 at the genome-wide SNP density, n_ref=2000",
     "tiny": "tiny synthetic chr22 slice",
 }
 N_VAL = 10_000          # c4: individuals of the validation panel

@@ -16,11 +16,12 @@ SOLVER_PCG = 1
 FLAG_KEEP_INT_GRAM = 1
 FLAG_FULL_SIGMA = 2
 FLAG_PLAN_CACHED = 4
+FLAG_PANEL_SUBSET = 8
 
 EXPORTS = [
     "dbslmm_b200_abi_version", "dbslmm_b200_device_count", "dbslmm_b200_create", "dbslmm_b200_destroy",
     "dbslmm_b200_last_error", "dbslmm_b200_load_bed", "dbslmm_b200_snp_stats", "dbslmm_b200_plan_shards",
-    "dbslmm_b200_fit", "dbslmm_b200_score", "dbslmm_b200_get_row_codes", "dbslmm_b200_get_block_sigma",
+    "dbslmm_b200_fit", "dbslmm_b200_host_alloc", "dbslmm_b200_host_free", "dbslmm_b200_score", "dbslmm_b200_get_row_codes", "dbslmm_b200_get_block_sigma",
     "dbslmm_b200_get_block_gram", "dbslmm_b200_get_block_iters",
 ]
 
@@ -72,6 +73,9 @@ def load():
         lib.dbslmm_b200_plan_shards.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                                 C.c_void_p, C.c_void_p]
         lib.dbslmm_b200_fit.argtypes = [C.c_void_p, C.POINTER(FitArgs)]
+        lib.dbslmm_b200_host_alloc.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
+        lib.dbslmm_b200_host_free.argtypes = [C.c_void_p, C.c_void_p]
+        lib.dbslmm_b200_host_free.restype = None
         lib.dbslmm_b200_score.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,
                                           C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_float)]
         lib.dbslmm_b200_get_row_codes.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32]

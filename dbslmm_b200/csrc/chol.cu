@@ -907,6 +907,13 @@ chol_panel_tma_kernel(const BlockDesc* __restrict__ blocks, const int4* __restri
         }
         __syncthreads();          // every warp is done with the ring: its boxes become the epilogue's L halves
 
+        {
+            // this item's two diagonal tiles (old values of the look-ahead update, read after the TRSM) -> L2 now
+            const int hrow0 = r0 + 64 * (tid >> 6), hr = tid & 63;
+            if (tid < 128 && wk == NB && hrow0 + hr < bd.mp)
+                l2_prefetch_bulk((k == 0 ? sigma : Lbuf) + bd.moff + (size_t)(hrow0 + hr) * ld + hrow0,
+                                 (uint32_t)(min(NB, bd.mp - hrow0) * 8));
+        }
         if (j + 1 < n_my) {
             // the next item's Sigma tile (its accumulator preload) -> L2 while this item's epilogue runs
             const int4 item2 = items[i0 + j + 1];

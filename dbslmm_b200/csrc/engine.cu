@@ -884,7 +884,7 @@ int upload_prepare(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, const P
 }
 
 // Issue the uploads of batches [next_batch, upto); upto == #batches also sends the rows outside every block.
-int upload_issue(dbslmm_b200_handle* h, const Plan& P, UploadPlan& U, const uint8_t* bed, int upto) {
+int upload_issue(dbslmm_b200_handle* h, const Plan& P, UploadPlan& U, const uint8_t* bed, int upto, bool subset) {
     typedef UploadPlan::Range Range;
     const size_t pitch = (size_t)h->pitch;
     const int64_t n_snp = h->n_snp;
@@ -897,9 +897,11 @@ int upload_issue(dbslmm_b200_handle* h, const Plan& P, UploadPlan& U, const uint
     }
     if (upto < (int)P.batches.size()) return 0;
     // rows outside every block (unmatched SNPs): last, so the resident copy is complete for later calls
+    // (FLAG_PANEL_SUBSET: not sent at all -- the handle forgets the panel after the call)
     std::sort(U.all.begin(), U.all.end());
-    int64_t next = 0;
+    int64_t next = subset ? n_snp : 0;
     for (const Range& x : U.all) {
+        if (subset) break;
         if (x.first > next)
             CU_TRY(h, cudaMemcpyAsync(dev + (size_t)next * pitch, bed + (size_t)next * pitch, (size_t)(x.first - next) * pitch,
                                       cudaMemcpyHostToDevice, h->up_stream));
@@ -926,6 +928,7 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
     const bool full = pcg || (a->flags & DBSLMM_B200_FLAG_FULL_SIGMA);
     const bool keep_int = (a->flags & DBSLMM_B200_FLAG_KEEP_INT_GRAM) != 0;
     const bool quad = a->quadform_out != nullptr;          // `valid`: z' Sigma z per block instead of the solve
+    const bool subset = streaming && (a->flags & DBSLMM_B200_FLAG_PANEL_SUBSET) != 0;
 
     Trace tr;
     UploadPlan U;
@@ -951,7 +954,7 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
             if (rc < 0) { P.valid = false; return rc; }
             // the biggest classes go out before the plan is built (the H2D queue is in issue order: the plan blob must
             // not wait behind the whole panel, and the DMA engine should not idle while the host builds the plan)
-            if (rc == 0) { rc = upload_issue(h, P, U, a->bed, std::min(2, (int)P.batches.size())); if (rc < 0) { P.valid = false; return rc; } }
+            if (rc == 0) { rc = upload_issue(h, P, U, a->bed, std::min(2, (int)P.batches.size()), subset); if (rc < 0) { P.valid = false; return rc; } }
             tr.mark("first uploads issued");
             if (rc == 1) {
                 // not streamable: plain full upload, then the resident path
@@ -1044,7 +1047,7 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
             if (P.blob_bytes) CU_TRY(h, cudaMemcpyAsync(dblob, h->h_blob.p, P.blob_bytes, cudaMemcpyHostToDevice, h->up_stream));
             CU_TRY(h, cudaEventRecord(h->ev_blob, h->up_stream));
             CU_TRY(h, cudaStreamWaitEvent(st, h->ev_blob, 0));
-            int rc = upload_issue(h, P, U, a->bed, nbatch);
+            int rc = upload_issue(h, P, U, a->bed, nbatch, subset);
             if (rc < 0) return rc;
             tr.mark("all uploads issued");
         }
@@ -1490,7 +1493,27 @@ int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
         h->missing_hint = true;
         rc = fit_impl(h, a, false);
     }
+    if (a->flags & DBSLMM_B200_FLAG_PANEL_SUBSET) {
+        // only the rows of this call's blocks were uploaded: the device copy is no panel a later call could use
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+        h->n_snp = 0; h->n_ref = 0; h->pitch = 0; h->n_pad = 0;
+        h->stats_valid = false;
+        h->plan.valid = false;
+    }
     return rc;
+}
+
+int dbslmm_b200_host_alloc(dbslmm_b200_handle* h, uint64_t bytes, void** out) {
+    if (!h || !out) return DBSLMM_B200_ERR_ARG;
+    *out = nullptr;
+    CU_TRY(h, cudaSetDevice(h->device));
+    CU_TRY(h, cudaHostAlloc(out, (size_t)std::max<uint64_t>(bytes, 1), cudaHostAllocPortable));
+    return DBSLMM_B200_OK;
+}
+void dbslmm_b200_host_free(dbslmm_b200_handle* h, void* p) {
+    if (!h || !p) return;
+    cudaSetDevice(h->device);
+    cudaFreeHost(p);
 }
 
 int dbslmm_b200_score(dbslmm_b200_handle* h, const uint8_t* bed_val, int64_t n_snp_val, int32_t n_val,

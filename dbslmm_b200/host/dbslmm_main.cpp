@@ -19,6 +19,7 @@
 //     `<eff>.txt` / `<eff>.badsnps` with the same rows as a separate run (values agree to FP64 rounding: the
 //     split-K slicing of the Cholesky depends on how many blocks share a panel step).
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -114,6 +115,18 @@ static void assign(int argc, char** argv, Param& p) {       // scr/dbslmm.cpp:67
 
 static double walltime() { struct timeval t; gettimeofday(&t, NULL); return (double)t.tv_sec + (double)t.tv_usec * 1e-6; }
 
+// fn(i) for i in [0, n) on up to `width` host threads (chromosomes are independent until the block plan is merged)
+template <class F>
+static void parallel_for(int n, int width, F&& fn) {
+    width = std::max(1, std::min(width, n));
+    if (width == 1) { for (int i = 0; i < n; ++i) fn(i); return; }
+    std::atomic<int> next{0};
+    vector<thread> th;
+    for (int t = 0; t < width; ++t)
+        th.emplace_back([&]() { for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) fn(i); });
+    for (auto& x : th) x.join();
+}
+
 struct Shard {                                   // what one GPU fits
     vector<int> blocks;                          // global block ids, ascending
     vector<int32_t> s_off, s_pos, l_off, l_pos;
@@ -135,6 +148,9 @@ struct Job {
     BimMap bim;
     Info info_s, info_l;
     bool with_large = false;
+    int n_fam = 0;
+    string log;                                  // this chromosome's share of the stdout log (printed in manifest order)
+    string err;                                  // first fatal problem met by a worker thread
 };
 
 int main(int argc, char* argv[]) {
@@ -200,36 +216,63 @@ int main(int argc, char* argv[]) {
     if (n_dev <= 0) { cerr << "ERROR: no CUDA device: dbslmm_b200 has no CPU fallback." << endl; exit(2); }
     const int n_gpus = std::max(1, std::min(cPar.gpus, n_dev));
 
-    // ---- reference panels: .fam / .bim / .bed of every chromosome, concatenated row-wise
-    int n_ref = -1;
-    vector<uint8_t> bed;
-    int64_t n_snp_all = 0;
-    for (Job& j : jobs) {
-        cout << "Reading reference PLINK FAM file from [" << j.r << ".fam]" << endl;
-        const int nr = get_row(j.r + ".fam");                                                 // :232
-        cout << nr << " individuals to be included from reference FAM file." << endl;
-        if (n_ref >= 0 && nr != n_ref) { cerr << "ERROR: all panels of a manifest must hold the same individuals" << endl; exit(1); }
-        n_ref = nr;
-        cout << "Reading reference PLINK BIM file from [" << j.r << ".bim]" << endl;
-        j.n_snp_ref = read_bim(j.r + ".bim", j.bim);
-        cout << j.bim.size() << " SNPs to be included from reference BIM file." << endl;
-        j.row0 = n_snp_all;
-        vector<uint8_t> part;
-        if (!read_bed(j.r + ".bed", j.n_snp_ref, n_ref, part)) { cerr << "ERROR: cannot read SNP-major " << j.r << ".bed" << endl; exit(1); }
-        bed.insert(bed.end(), part.begin(), part.end());
-        n_snp_all += j.n_snp_ref;
-    }
+    // host threads for the text / file phases: -t as given for one chromosome; a manifest run takes the machine
+    const int host_threads = jobs.size() > 1 ? std::max(cPar.t, (int)std::thread::hardware_concurrency()) : cPar.t;
+    const double t_start = walltime();
+    // GPU contexts come up in the background while the text files are read (~0.3 s each on a cold process)
     const bool constr = !(fabs(cPar.mafMax - 1.0) < 1e-10);                                   // :238-241
     vector<dbslmm_b200_handle*> hs(n_gpus, nullptr);
+    vector<int> hs_rc(n_gpus, 0);
+    vector<thread> gpu_init;
+    for (int g = 0; g < n_gpus; ++g) gpu_init.emplace_back([&, g]() { hs_rc[g] = dbslmm_b200_create(g, &hs[g]); });
+
+    // ---- reference panels: .fam / .bim of every chromosome (in parallel), then the .bed files straight into ONE
+    // page-locked buffer, concatenated row-wise
+    parallel_for((int)jobs.size(), host_threads, [&](int i) {
+        Job& j = jobs[i];
+        ostringstream out;
+        out << "Reading reference PLINK FAM file from [" << j.r << ".fam]" << endl;
+        j.n_fam = get_row(j.r + ".fam");                                                      // :232
+        out << j.n_fam << " individuals to be included from reference FAM file." << endl;
+        out << "Reading reference PLINK BIM file from [" << j.r << ".bim]" << endl;
+        j.n_snp_ref = read_bim(j.r + ".bim", j.bim);
+        out << j.bim.size() << " SNPs to be included from reference BIM file." << endl;
+        j.log = out.str();
+    });
+    int n_ref = -1;
+    int64_t n_snp_all = 0;
+    for (Job& j : jobs) {
+        if (n_ref >= 0 && j.n_fam != n_ref) { cerr << "ERROR: all panels of a manifest must hold the same individuals" << endl; exit(1); }
+        n_ref = j.n_fam;
+        j.row0 = n_snp_all;
+        n_snp_all += j.n_snp_ref;
+    }
+    for (auto& t : gpu_init) t.join();
     for (int g = 0; g < n_gpus; ++g)
-        if (dbslmm_b200_create(g, &hs[g]) != DBSLMM_B200_OK) { cerr << "ERROR: cannot initialise GPU " << g << endl; exit(2); }
+        if (hs_rc[g] != DBSLMM_B200_OK) { cerr << "ERROR: cannot initialise GPU " << g << endl; exit(2); }
+    const size_t pitch_all = (size_t)((n_ref + 3) / 4);
+    uint8_t* bed = nullptr;
+    {
+        void* p = nullptr;
+        if (dbslmm_b200_host_alloc(hs[0], (uint64_t)n_snp_all * pitch_all + 64, &p) != DBSLMM_B200_OK) {
+            cerr << "ERROR: cannot allocate " << n_snp_all * pitch_all << " bytes of page-locked host memory: " << dbslmm_b200_last_error(hs[0]) << endl; exit(2);
+        }
+        bed = (uint8_t*)p;
+    }
+    parallel_for((int)jobs.size(), host_threads, [&](int i) {
+        Job& j = jobs[i];
+        if (!read_bed_into(j.r + ".bed", j.n_snp_ref, n_ref, bed + (size_t)j.row0 * pitch_all)) j.err = "ERROR: cannot read SNP-major " + j.r + ".bed";
+    });
+    for (Job& j : jobs) if (!j.err.empty()) { cerr << j.err << endl; exit(1); }
+    const double t_panel = walltime();
     // With a MAF constraint GPU 0 takes the whole panel now: its statistics kernel IS the MAF pre-pass
     // (dtpr.cpp:93-102).  Without one (mafMax == 1, dbslmm.cpp:238-241) nothing needs the panel before the fit, and
     // it travels with dbslmm_b200_fit (fit_args.bed): the upload then overlaps the fit.
     const bool early_load = constr;
-    if (early_load && dbslmm_b200_load_bed(hs[0], bed.data(), n_snp_all, n_ref) != DBSLMM_B200_OK) {
+    if (early_load && dbslmm_b200_load_bed(hs[0], bed, n_snp_all, n_ref) != DBSLMM_B200_OK) {
         cerr << "ERROR: load_bed: " << dbslmm_b200_last_error(hs[0]) << endl; exit(2);
     }
+    for (Job& j : jobs) { cout << j.log; j.log.clear(); }
     vector<double> ref_maf;
     if (constr) {
         cout << "Calculating MAF of reference panel ..." << endl;
@@ -241,52 +284,62 @@ int main(int argc, char* argv[]) {
         cout << "[WARNING] Do not consider the difference between reference panel and summary data ..." << endl;
     }
 
-    // ---- per chromosome: blocks, summary statistics, matching, block assignment, badsnps
-    int num_block = 0;
-    for (Job& j : jobs) {
+    // ---- per chromosome (in parallel): blocks, summary statistics, matching, block assignment, badsnps
+    parallel_for((int)jobs.size(), host_threads, [&](int ji) {
+        Job& j = jobs[ji];
+        ostringstream out;
         vector<Block> block_dat;
         read_block(j.b, block_dat);                                                           // :248
         j.num_block = (int)block_dat.size();
-        j.block0 = num_block;
-        num_block += j.num_block;
         const double* maf = constr ? ref_maf.data() + j.row0 : nullptr;
-        cout << "Reading summary data of small effect SNPs from [" << j.s << "]" << endl;
+        out << "Reading summary data of small effect SNPs from [" << j.s << "]" << endl;
         Summ summ_s;
         read_summ(j.s, summ_s);
         Info inter_s;
         vector<char> matched_s;
         int dis = 0, mafc = 0;
         match_ref(summ_s, j.bim, maf, cPar.mafMax, inter_s, matched_s, dis, mafc);
-        cout << "Number of allele discrepency: " << dis << endl;
-        cout << "Number of maf discrepency:    " << mafc << endl;
-        cout << "After filtering, " << inter_s.size() << " small effect SNPs are selected." << endl;
+        out << "Number of allele discrepency: " << dis << endl;
+        out << "Number of maf discrepency:    " << mafc << endl;
+        out << "After filtering, " << inter_s.size() << " small effect SNPs are selected." << endl;
         add_block(inter_s, block_dat, j.info_s);
         const string badsnps_str = j.eff + ".badsnps";
-        ofstream badsnpsFout(badsnps_str.c_str());
+        string bad;
         for (size_t i = 0; i < summ_s.size(); ++i)
-            if (!matched_s[i]) badsnpsFout << summ_s.snp[i] << " " << 0 << endl;             // :282-285
+            if (!matched_s[i]) { bad += summ_s.snp[i]; bad += " 0\n"; }                      // :282-285
         ifstream leff(j.l.c_str());
         Info inter_l;
         if (!j.l.empty() && leff) {                                                           // :292-317
-            cout << "Reading summary data of large effect SNPs from [" << j.l << "]" << endl;
+            out << "Reading summary data of large effect SNPs from [" << j.l << "]" << endl;
             Summ summ_l;
             read_summ(j.l, summ_l);
             vector<char> matched_l;
             match_ref(summ_l, j.bim, maf, cPar.mafMax, inter_l, matched_l, dis, mafc);
-            cout << "Number of allele discrepency: " << dis << endl;
-            cout << "Number of maf discrepency:    " << mafc << endl;
+            out << "Number of allele discrepency: " << dis << endl;
+            out << "Number of maf discrepency:    " << mafc << endl;
             if (inter_l.size() != 0) {
                 add_block(inter_l, block_dat, j.info_l);
-                cout << "After filtering, " << inter_l.size() << " large effect SNPs are selected." << endl;
+                out << "After filtering, " << inter_l.size() << " large effect SNPs are selected." << endl;
             } else {
-                cout << "After filtering, no large effect SNP is selected." << endl;
+                out << "After filtering, no large effect SNP is selected." << endl;
             }
             for (size_t i = 0; i < summ_l.size(); ++i)
-                if (!matched_l[i]) badsnpsFout << summ_l.snp[i] << " " << 1 << endl;
+                if (!matched_l[i]) { bad += summ_l.snp[i]; bad += " 1\n"; }
         }
+        ofstream badsnpsFout(badsnps_str.c_str(), ios::binary);
+        badsnpsFout.write(bad.data(), (streamsize)bad.size());
         badsnpsFout.close();
         j.with_large = inter_l.size() != 0;                                                   // :325 / :366
+        BimMap().swap(j.bim);                                                                 // not needed any more
+        j.log = out.str();
+    });
+    int num_block = 0;
+    for (Job& j : jobs) {
+        cout << j.log; j.log.clear();
+        j.block0 = num_block;
+        num_block += j.num_block;
     }
+    const double t_ingest = walltime();
     bool with_large = false;
     for (const Job& j : jobs) with_large = with_large || j.with_large;
 
@@ -320,17 +373,9 @@ int main(int argc, char* argv[]) {
         Shard& sh = shards[g];
         sh.s_off.push_back(0);
         if (with_large) sh.l_off.push_back(0);
-        vector<int64_t> remap;
-        if (n_gpus > 1) remap.assign((size_t)n_snp_all, -1);
-        const size_t pitch = (size_t)((n_ref + 3) / 4);
-        auto map_row = [&](int32_t p) -> int32_t {
-            if (n_gpus == 1) return p;
-            if (remap[p] < 0) {
-                remap[p] = sh.n_rows++;
-                sh.bed.insert(sh.bed.end(), bed.begin() + (size_t)p * pitch, bed.begin() + (size_t)(p + 1) * pitch);
-            }
-            return (int32_t)remap[p];
-        };
+        // several GPUs: every GPU is handed the whole host panel and uploads only the rows of ITS blocks
+        // (DBSLMM_B200_FLAG_PANEL_SUBSET): no per-GPU compaction on the host
+        auto map_row = [&](int32_t p) -> int32_t { return p; };
         for (int b = 0; b < num_block; ++b) {
             if (owner[b] != g) continue;
             sh.blocks.push_back(b);
@@ -393,17 +438,17 @@ int main(int argc, char* argv[]) {
     cout << "Fitting model..." << endl;
     auto run = [&](int g) {
         Shard& sh = shards[g];
-        if (n_gpus > 1 && sh.n_rows == 0) return;
+        if (sh.blocks.empty()) return;
         dbslmm_b200_fit_args a{};
         // the panel (this GPU's shard of it) travels with the fit, like est()'s bed_str: uploaded in batches that
         // overlap decode / Gram / Cholesky.  One GPU with a MAF constraint already holds the panel (pre-pass above).
-        if (n_gpus > 1) { a.bed = sh.bed.data(); a.bed_n_snp = sh.n_rows; a.bed_n_ref = n_ref; }
-        else if (!early_load) { a.bed = bed.data(); a.bed_n_snp = n_snp_all; a.bed_n_ref = n_ref; }
+        if (n_gpus > 1) { a.bed = bed; a.bed_n_snp = n_snp_all; a.bed_n_ref = n_ref; }
+        else if (!early_load) { a.bed = bed; a.bed_n_snp = n_snp_all; a.bed_n_ref = n_ref; }
         a.n_blocks = (int32_t)sh.blocks.size();
         a.s_off = sh.s_off.data(); a.s_pos = sh.s_pos.data(); a.s_z = sh.s_z.data();
         if (with_large) { a.l_off = sh.l_off.data(); a.l_pos = sh.l_pos.data(); a.l_z = sh.l_z.data(); }
         a.n_folds = n_folds; a.sigma_s = sigma_s.data(); a.n_obs = cPar.n; a.tau = cPar.tau;
-        a.solver = solver; a.flags = 0;
+        a.solver = solver; a.flags = (n_gpus > 1) ? DBSLMM_B200_FLAG_PANEL_SUBSET : 0;
         a.beta_s_out = sh.beta_s.data(); a.beta_l_out = with_large ? sh.beta_l.data() : nullptr;
         a.block_status_out = sh.status.data(); a.timing = &sh.timing;
         if (want_var) {
@@ -449,28 +494,44 @@ int main(int argc, char* argv[]) {
         }
     }
 
-    // ---- output effect per chromosome (dbslmm.cpp:353-364 / 391-395): large first (flag 1), then small (flag 0)
-    for (const Job& j : jobs) {
+    // ---- output effect per chromosome (dbslmm.cpp:353-364 / 391-395): large first (flag 1), then small (flag 0);
+    // the chromosomes' files are formatted and written in parallel ("%g" = the default ostream formatting of a double)
+    const double t_out0 = walltime();
+    parallel_for((int)jobs.size(), host_threads, [&](int ji) {
+        const Job& j = jobs[ji];
         const size_t js = (size_t)s_off[j.block0], jl = (size_t)l_off[j.block0];   // this chromosome's slice of the global arrays
         for (int f = 0; f < n_folds; ++f) {
             string eff_str = j.eff + ".txt";
             if (n_folds > 1) { ostringstream o; o << j.eff << "_f" << f << ".txt"; eff_str = o.str(); }
-            ofstream effFout(eff_str.c_str());
+            string txt;
+            txt.reserve((j.info_s.size() + j.info_l.size()) * 48 + 64);
+            char num[80];
+            auto row = [&](const string& snp, const string& a1, double bta, double noscl, int flag) {
+                txt += snp; txt += ' '; txt += a1; txt += ' ';
+                const int n = snprintf(num, sizeof num, "%g %g %d\n", bta, noscl, flag);
+                txt.append(num, (size_t)n);
+            };
             if (j.with_large)
                 for (size_t i = 0; i < j.info_l.size(); ++i) {
-                    const double b = beta_l[f * tot_l + jl + i];
-                    const double noscl = b / sqrt(2 * j.info_l.maf[i] * (1 - j.info_l.maf[i]));
-                    if (isinf(noscl) == false) effFout << j.info_l.snp[i] << " " << j.info_l.a1[i] << " " << b << " " << noscl << " " << 1 << endl;
+                    const double bta = beta_l[f * tot_l + jl + i];
+                    const double noscl = bta / sqrt(2 * j.info_l.maf[i] * (1 - j.info_l.maf[i]));
+                    if (isinf(noscl) == false) row(j.info_l.snp[i], j.info_l.a1[i], bta, noscl, 1);
                 }
             for (size_t i = 0; i < j.info_s.size(); ++i) {
-                const double b = beta_s[f * tot_s + js + i];
-                const double noscl = b / sqrt(2 * j.info_s.maf[i] * (1 - j.info_s.maf[i]));
-                if (j.info_s.snp[i].size() != 0 && isinf(noscl) == false)
-                    effFout << j.info_s.snp[i] << " " << j.info_s.a1[i] << " " << b << " " << noscl << " " << 0 << endl;
+                const double bta = beta_s[f * tot_s + js + i];
+                const double noscl = bta / sqrt(2 * j.info_s.maf[i] * (1 - j.info_s.maf[i]));
+                if (j.info_s.snp[i].size() != 0 && isinf(noscl) == false) row(j.info_s.snp[i], j.info_s.a1[i], bta, noscl, 0);
             }
+            ofstream effFout(eff_str.c_str(), ios::binary);
+            effFout.write(txt.data(), (streamsize)txt.size());
             effFout.close();
         }
-    }
+    });
+    const double t_out1 = walltime();
+    if (cPar.verbose || jobs.size() > 1)
+        cout << "[timing] panel files " << (t_panel - t_start) << " s, summary statistics + matching " << (t_ingest - t_panel)
+             << " s, plan + fit " << (t_out0 - t_ingest) << " s (Fitting time " << time_fitting << " s), output " << (t_out1 - t_out0)
+             << " s; " << host_threads << " host thread(s), " << n_gpus << " GPU(s)" << endl;
     if (want_var) {
         // diags.save("variance.txt", arma_ascii) (dbslmmfit.cpp:242, 361): n_test x num_block, cwd-relative
         for (int f = 0; f < n_folds; ++f) {
@@ -501,6 +562,7 @@ int main(int argc, char* argv[]) {
         o.write((const char*)beta_l.data(), sizeof(double) * tot_l * n_folds);
         o.write((const char*)beta_s.data(), sizeof(double) * tot_s * n_folds);
     }
+    dbslmm_b200_host_free(hs[0], bed);
     for (auto* h : hs) dbslmm_b200_destroy(h);
     return EXIT_SUCCESS;
 }

@@ -35,6 +35,8 @@ bool read_block(const std::string& path, std::vector<Block>& out);          // I
 int64_t read_bim(const std::string& path, BimMap& out);                     // IO::readBim (map part)
 bool read_summ(const std::string& path, Summ& out);                         // IO::readSumm
 bool read_bed(const std::string& path, int64_t n_snp, int n_ref, std::vector<uint8_t>& out);
+// the same into caller memory (n_snp * ceil(n_ref / 4) bytes), e.g. a slice of one pinned genome-wide buffer
+bool read_bed_into(const std::string& path, int64_t n_snp, int n_ref, uint8_t* dst);
 
 // SNPPROC::matchRef: alleles must match exactly, |maf_ref - maf_summ| < mafMax (ref_maf == nullptr
 // when the MAF pre-pass is disabled: the reference then compares against 0).  `matched[i]` mirrors

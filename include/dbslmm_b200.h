@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DBSLMM_B200_ABI_VERSION 4
+#define DBSLMM_B200_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define DBSLMM_B200_API __attribute__((visibility("default")))
@@ -118,6 +118,9 @@ typedef struct dbslmm_b200_fit_args {
 #define DBSLMM_B200_FLAG_KEEP_INT_GRAM 1  /* also keep raw int32 Gram planes for dbslmm_b200_get_block_gram */
 #define DBSLMM_B200_FLAG_FULL_SIGMA    2  /* write both triangles of Sigma (implied by the PCG solver)       */
 #define DBSLMM_B200_FLAG_PLAN_CACHED   4  /* reuse the device plan of the previous fit (same CSR arrays)     */
+#define DBSLMM_B200_FLAG_PANEL_SUBSET  8  /* with fit_args.bed: upload only the .bed rows this call's blocks use (one GPU of
+                                             several, each given the whole host panel and its own blocks); the handle
+                                             does NOT keep the panel for later calls                                */
 
 DBSLMM_B200_API int  dbslmm_b200_abi_version(void);
 DBSLMM_B200_API int  dbslmm_b200_device_count(void);
@@ -146,6 +149,13 @@ DBSLMM_B200_API int  dbslmm_b200_plan_shards(int32_t n_blocks, const int32_t* m_
                              int32_t n_ref, int32_t n_ranks, int32_t* owner_out, double* rank_cost_out);
 
 DBSLMM_B200_API int  dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* args);
+
+/* Page-locked host memory for the panel (`bed` of load_bed / fit_args.bed): uploads from it run at full PCIe speed and
+ * truly asynchronously; ordinary memory works too, but is staged by the driver.  The reference has no counterpart (it
+ * reads the .bed through an ifstream, scr/dtpr.cpp:302-315); the `dbslmm` command line reads its .bed files straight
+ * into such a buffer.  Needs a created handle (a CUDA context); free with dbslmm_b200_host_free before destroy. */
+DBSLMM_B200_API int  dbslmm_b200_host_alloc(dbslmm_b200_handle* h, uint64_t bytes, void** out);
+DBSLMM_B200_API void dbslmm_b200_host_free(dbslmm_b200_handle* h, void* p);
 
 /* Polygenic scores over a validation panel (BASELINE config 4; replaces the per-fold
  * `plink --score <eff>.txt 1 2 4 sum` of DBSLMM_script.sh:87): score[f][i] = sum_j beta[f][j] * dosage_ij,

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), n
     assert sorted(_abi.EXPORTS) == names
-    assert lib.dbslmm_b200_abi_version() == 4
+    assert lib.dbslmm_b200_abi_version() == 5
 
 
 def test_fit_args_struct_layout_matches_header():

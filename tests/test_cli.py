@@ -210,3 +210,46 @@ def test_cli_two_gpus_match_one_gpu(tmp_path):
         assert [(g[0], g[1], g[4]) for g in a] == [(g[0], g[1], g[4]) for g in b]
         va, vb = np.array([g[2] for g in a]), np.array([g[2] for g in b])
         assert np.abs(va - vb).max() <= 2e-6 * np.abs(va).max()
+
+
+@pytest.mark.gpu
+def test_cli_manifest_three_real_sized_chromosomes(tmp_path):
+    """Chromosomes 20-22 at the genome-wide SNP density (n_ref = 2,000, ~60k SNPs, 70 EUR LD blocks) as REAL files
+    (tools/cli_genome_wide.py writes the PLINK / GEMMA / block files): one cold `dbslmm --manifest` process against the
+    same problem fitted through the C ABI, with and without the MAF pre-pass, on one GPU and -- when the box has two --
+    with the blocks sharded over two GPUs that each take the whole host panel (FLAG_PANEL_SUBSET)."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import cli_genome_wide as G
+    from dbslmm_b200 import _abi
+    mf, jobs, w = G.write_genome(str(tmp_path / "gw"), "chr20_22", 20240003)
+    nsnp, n_obs, n_ref = int(w["n_snp"]), int(w["n_obs"]), int(w["n_ref"])
+    eng = _abi.Engine(0)
+    try:
+        eng.load_bed(w["bed"], n_ref)
+        r = eng.fit(w["s_off"], w["s_pos"], w["z"][w["s_pos"]], w["l_off"], w["l_pos"], w["z"][w["l_pos"]],
+                    sigma_s=[0.5 / nsnp], n_obs=n_obs)
+        n_dev = _abi.load().dbslmm_b200_device_count()
+    finally:
+        eng.close()
+    assert r["n_bad"] == 0
+    runs = [("1", "1"), ("0.2", "1")] + ([("1", "2")] if n_dev >= 2 else [])
+    for maf, gpus in runs:
+        out = tmp_path / f"beta_{maf}_{gpus}.bin"
+        cmd = [CLI, "--manifest", mf, "-n", str(n_obs), "-nsnp", str(nsnp), "-h", "0.5", "-t", "8", "-mafMax", maf, "--gpus", gpus,
+               "--dump-beta-bin", str(out)]
+        p = subprocess.run(cmd, capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr
+        assert "Fitting time:" in p.stdout and "[timing] panel files" in p.stdout
+        raw = out.read_bytes()
+        nf, tl, ts = struct.unpack("<qqq", raw[:24])
+        v = np.frombuffer(raw[24:], np.float64)
+        assert (nf, tl, ts) == (1, w["l_pos"].size, w["s_pos"].size)
+        bl, bs = v[:tl], v[tl:]
+        # the text round trip of the z-scores (beta and se printed with 11 / 7 digits) bounds the agreement
+        assert np.abs(bs - r["beta_s"][0]).max() <= 1e-9 * np.abs(r["beta_s"][0]).max()
+        assert np.abs(bl - r["beta_l"][0]).max() <= 1e-9 * np.abs(r["beta_l"][0]).max()
+        for j in jobs:
+            rows = open(j["pre"] + "_out.txt").read().strip().split("\n")
+            assert len(rows) == j["n_snp"]                       # every SNP matched, large effects first
+            assert os.path.getsize(j["pre"] + "_out.badsnps") == 0
