@@ -31,7 +31,7 @@ class Timing(C.Structure):
                 ("solve_ms", C.c_float), ("d2h_ms", C.c_float), ("total_ms", C.c_float),
                 ("n_launches", C.c_int32), ("n_chol_launches", C.c_int32),
                 ("gram_ops", C.c_double), ("solve_flops", C.c_double), ("decode_bytes", C.c_double),
-                ("chol_ms", C.c_double), ("class_ms", C.c_float * 4)]
+                ("chol_ms", C.c_double), ("class_ms", C.c_float * 4), ("streamed", C.c_int32), ("n_blocks_missing", C.c_int32)]
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_}
@@ -78,7 +78,7 @@ def load():
         lib.dbslmm_b200_host_free.restype = None
         lib.dbslmm_b200_score.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,
                                           C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_float)]
-        lib.dbslmm_b200_get_row_codes.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32]
+        lib.dbslmm_b200_get_row_codes.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]
         lib.dbslmm_b200_get_block_sigma.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         lib.dbslmm_b200_get_block_gram.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.dbslmm_b200_get_block_iters.argtypes = [C.c_void_p, C.c_int32]
@@ -239,9 +239,10 @@ class Engine:
         return out, ms.value
 
     # ---- inspection hooks (parity tests)
-    def row_codes(self, row, n):
+    def row_codes(self, block, j, n, plane=0):
+        """int8 codes of SNP j of `block` in the last fit: plane 0 = allele counts, plane 1 = call mask."""
         out = np.zeros(n, np.int8)
-        self._check(self.lib.dbslmm_b200_get_row_codes(self.h, int(row), out.ctypes.data, n), "get_row_codes")
+        self._check(self.lib.dbslmm_b200_get_row_codes(self.h, int(block), int(j), int(plane), out.ctypes.data, n), "get_row_codes")
         return out
 
     def block_sigma(self, block, m):

@@ -124,17 +124,22 @@ __device__ __forceinline__ uint4 expand16(uint32_t w) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Decoder: one warp per output code row.  row_src[r] = bed row | (mask plane ? 1<<31 : 0);
-// row_g[r] = SNP-row index that receives the scale factors (or -1 for mask rows).
+// Decoder: one warp per SNP row of the plan.  The warp stages the .bed row ONCE, counts its genotypes (the per-SNP
+// statistics of the standardisation: no separate pass), writes the int8 allele-count row, and -- only if the SNP has
+// missing calls, or the mask row at that position was written for an earlier fit -- the int8 call-mask row.
+//   row_src[g]  .bed row of SNP row g          row_crow[g]  its genotype code row      row_mrow[g]  its mask code row
+//   dirty[c]    code row c holds a non-default mask (device state that lives across fits; starts all-ones)
+// Invariant: a mask row whose dirty byte is 0 holds the default pattern (1 for every real sample, 0 for padding), so a
+// panel without missing calls never pays for the mask plane, and the correlation builder can pick the one- or the
+// four-plane path per block from a flag computed on the device (block_flags_kernel).
 // ------------------------------------------------------------------------------------------
-// OWN = true: no statistics array; the warp counts the genotypes of the row it has staged (streaming fit).
-template <bool OWN, int kDecRing>
+template <int kDecRing>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 decode_rows_kernel(const uint8_t* __restrict__ bed, int32_t n_ref, int32_t pitch, int32_t n_pad,
-                   int32_t buf_bytes, const uint32_t* __restrict__ row_src, const int32_t* __restrict__ row_g,
-                   int64_t n_rows, const SnpStat* __restrict__ stats, double tau,
-                   int8_t* __restrict__ codes, int32_t* __restrict__ rowN, int32_t* __restrict__ rowS,
-                   double* __restrict__ rowR) {
+                   int32_t buf_bytes, const uint32_t* __restrict__ row_src, const int32_t* __restrict__ row_crow,
+                   const int32_t* __restrict__ row_mrow, int64_t g0, int64_t n_rows, double tau,
+                   int8_t* __restrict__ codes, uint8_t* __restrict__ dirty, int32_t* __restrict__ rowN,
+                   int32_t* __restrict__ rowS, double* __restrict__ rowR) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bars[kWarpsPerCta][kDecRing];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -151,27 +156,23 @@ decode_rows_kernel(const uint8_t* __restrict__ bed, int32_t n_ref, int32_t pitch
     const int64_t stride = (int64_t)gridDim.x * wpc;
     const int nwords = (pitch + 3) >> 2;     // input words holding real samples
     const int nout = n_pad >> 4;             // 16-byte output chunks per row
-    // ring of kDecRing staged rows per warp: kDecRing - 1 TMA row copies in flight while one row is expanded.
-    // Per-row metadata never stalls the loop: the source index of the row staged NEXT iteration is loaded one
-    // iteration ahead, the ring remembers the source of every staged row, and lane 0 fetches row_g / the statistics
-    // before it waits for the staged bytes.
+    // ring of kDecRing staged rows per warp: kDecRing - 1 TMA row copies in flight while one row is expanded.  The
+    // source index of the row staged NEXT iteration is loaded one iteration ahead, so no global load sits on the
+    // loop's critical path.
     uint32_t phase = 0;                      // bit i = parity of buffer i
-    uint32_t off[kDecRing], srcs[kDecRing];
-    int64_t row = gw;
+    uint32_t off[kDecRing];
+    int64_t row = gw;                        // relative to g0
 #pragma unroll
-    for (int i = 0; i < kDecRing; ++i) { off[i] = 0; srcs[i] = 0; }
+    for (int i = 0; i < kDecRing; ++i) off[i] = 0;
 #pragma unroll
     for (int i = 0; i < kDecRing - 1; ++i) {
         const int64_t r = row + (int64_t)i * stride;
-        if (r < n_rows) {
-            srcs[i] = row_src[r];
-            off[i] = RowStage::issue(bed, (int64_t)(srcs[i] & 0x7FFFFFFFu), pitch, buf0 + i * buf_bytes, &bars[warp][i], lane);
-        }
+        if (r < n_rows) off[i] = RowStage::issue(bed, (int64_t)row_src[g0 + r], pitch, buf0 + i * buf_bytes, &bars[warp][i], lane);
     }
     uint32_t pre = 0;                        // row_src of the row that will be staged in the current iteration
     {
         const int64_t r = row + (int64_t)(kDecRing - 1) * stride;
-        if (r < n_rows) pre = row_src[r];
+        if (r < n_rows) pre = row_src[g0 + r];
     }
     int cur = 0;
     for (; row < n_rows; row += stride) {
@@ -180,28 +181,23 @@ decode_rows_kernel(const uint8_t* __restrict__ bed, int32_t n_ref, int32_t pitch
             const int nb = (cur + kDecRing - 1) % kDecRing;
             const uint32_t issue_src = pre;
             const int64_t nxt2 = nxt + stride;
-            if (nxt2 < n_rows) pre = row_src[nxt2];          // consumed next iteration
+            if (nxt2 < n_rows) pre = row_src[g0 + nxt2];     // consumed next iteration
             if (nxt < n_rows) {
-                const uint32_t o = RowStage::issue(bed, (int64_t)(issue_src & 0x7FFFFFFFu), pitch, buf0 + nb * buf_bytes,
-                                                   &bars[warp][nb], lane);
+                const uint32_t o = RowStage::issue(bed, (int64_t)issue_src, pitch, buf0 + nb * buf_bytes, &bars[warp][nb], lane);
 #pragma unroll
-                for (int i = 0; i < kDecRing; ++i) if (i == nb) { off[i] = o; srcs[i] = issue_src; }
+                for (int i = 0; i < kDecRing; ++i) if (i == nb) off[i] = o;
             }
         }
-        uint32_t off_cur = 0, src = 0;
+        uint32_t off_cur = 0;
 #pragma unroll
-        for (int i = 0; i < kDecRing; ++i) if (i == cur) { off_cur = off[i]; src = srcs[i]; }
-        const bool mask_plane = (src >> 31) != 0;
-        int32_t g_row = -1;
-        SnpStat s_row = {0, 0, 0, 0};
-        if (lane == 0) {
-            g_row = row_g[row];
-            if (!OWN && g_row >= 0) s_row = stats[src & 0x7FFFFFFFu];
-        }
+        for (int i = 0; i < kDecRing; ++i) if (i == cur) off_cur = off[i];
+        const int64_t g = g0 + row;
+        const int32_t crow = row_crow[g], mrow = row_mrow[g];
+        const uint8_t was_dirty = dirty[mrow];
         mbar_wait(&bars[warp][cur], (phase >> cur) & 1u);
         phase ^= 1u << cur;
         const uint32_t* w32 = reinterpret_cast<const uint32_t*>(buf0 + cur * buf_bytes);
-        uint4* out = reinterpret_cast<uint4*>(codes + (size_t)row * n_pad);
+        uint4* out = reinterpret_cast<uint4*>(codes + (size_t)crow * n_pad);
         const int nfull = n_ref >> 4;             // words whose 16 samples are all real
         int c0 = 0, c1 = 0, c2 = 0;
         for (int i = lane; i < nout; i += 32) {
@@ -214,37 +210,43 @@ decode_rows_kernel(const uint8_t* __restrict__ bed, int32_t n_ref, int32_t pitch
                     ws = w | ~vb;
                     w = (w & vb) | (0x55555555u & ~vb);   // samples past n_ref -> "missing": 0 in both planes
                 }
-                o = mask_plane ? expand16<true>(w) : expand16<false>(w);
-                if (OWN) {
-                    const uint32_t lo = ws & 0x55555555u, hi = (ws >> 1) & 0x55555555u;
-                    c0 += __popc(~(lo | hi) & 0x55555555u);    // code 0 -> allele count 2
-                    c1 += __popc(lo & ~hi);                    // code 1 -> missing
-                    c2 += __popc(hi & ~lo);                    // code 2 -> allele count 1
-                }
+                o = expand16<false>(w);
+                const uint32_t lo = ws & 0x55555555u, hi = (ws >> 1) & 0x55555555u;
+                c0 += __popc(~(lo | hi) & 0x55555555u);    // code 0 -> allele count 2
+                c1 += __popc(lo & ~hi);                    // code 1 -> missing
+                c2 += __popc(hi & ~lo);                    // code 2 -> allele count 1
             }
             out[i] = o;
         }
-        if (OWN) {
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                c0 += __shfl_xor_sync(0xffffffffu, c0, o);
-                c1 += __shfl_xor_sync(0xffffffffu, c1, o);
-                c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+        for (int o = 16; o > 0; o >>= 1) {
+            c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+            c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+            c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+        }
+        if (c1 > 0 || was_dirty) {
+            // the call-mask plane of this SNP (second pass over the staged row; rare on real reference panels)
+            uint4* outm = reinterpret_cast<uint4*>(codes + (size_t)mrow * n_pad);
+            for (int i = lane; i < nout; i += 32) {
+                uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                if (i < nwords) {
+                    uint32_t w = row_word(w32, off_cur, i);
+                    if (i >= nfull) { const uint32_t vb = valid_bits(n_ref, i); w = (w & vb) | (0x55555555u & ~vb); }
+                    o = expand16<true>(w);
+                }
+                outm[i] = o;
             }
         }
         if (lane == 0) {
-            const int32_t g = g_row;
-            if (g >= 0) {
-                SnpStat s = s_row;
-                if (OWN) { s.n_nonmiss = n_ref - c1; s.sum = 2 * c0 + c2; s.sumsq = 4 * c0 + c2; s.pad = 0; }
-                const double ni = (double)s.n_nonmiss;
-                // d = n_i * sum g^2 - (sum g)^2  (exact integer), r = sqrt(tau (n-1) / (n n_i d))
-                const double d = ni * (double)s.sumsq - (double)s.sum * (double)s.sum;
-                const double n = (double)n_ref;
-                rowN[g] = s.n_nonmiss;
-                rowS[g] = s.sum;
-                rowR[g] = sqrt(tau * (n - 1.0) / (n * ni * d));
-            }
+            if ((c1 > 0) != (was_dirty != 0)) dirty[mrow] = (c1 > 0) ? 1 : 0;
+            const int32_t nn = n_ref - c1, sum = 2 * c0 + c2, sumsq = 4 * c0 + c2;
+            const double ni = (double)nn;
+            // d = n_i * sum g^2 - (sum g)^2  (exact integer), r = sqrt(tau (n-1) / (n n_i d))
+            const double d = ni * (double)sumsq - (double)sum * (double)sum;
+            const double n = (double)n_ref;
+            rowN[g] = nn;
+            rowS[g] = sum;
+            rowR[g] = sqrt(tau * (n - 1.0) / (n * ni * d));
         }
         __syncwarp();
         cur = (cur + 1 == kDecRing) ? 0 : cur + 1;
@@ -252,44 +254,34 @@ decode_rows_kernel(const uint8_t* __restrict__ bed, int32_t n_ref, int32_t pitch
 }
 
 // ------------------------------------------------------------------------------------------
-// Per-block "has missing calls" flag from the per-SNP statistics: one warp per block over the block's
-// genotype rows.  Lets the host plan a fit without ever reading the panel or its statistics.
+// Per-block "has missing calls" flag from the counts the decoder just wrote: one warp per listed block.  The
+// correlation builder reads flags[b] per tile (one integer plane or four); any[0] tells the four-plane kernel whether
+// there is anything to do at all.
 // ------------------------------------------------------------------------------------------
-__global__ void block_missing_kernel(const BlockDesc* __restrict__ blocks, int32_t n_blocks,
-                                     const uint32_t* __restrict__ row_src, const SnpStat* __restrict__ stats,
-                                     int32_t n_ref, int32_t* __restrict__ flags) {
-    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (b >= n_blocks) return;
+__global__ void block_flags_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict__ list, int32_t n_list,
+                                   const int32_t* __restrict__ rowN, int32_t n_ref, int32_t* __restrict__ flags,
+                                   int32_t* __restrict__ any) {
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n_list) return;
     const int lane = threadIdx.x & 31;
+    const int b = list ? list[i] : i;
     const BlockDesc bd = blocks[b];
     int miss = 0;
-    for (int j = lane; j < bd.m; j += 32) miss |= (stats[row_src[bd.croff + j] & 0x7FFFFFFFu].n_nonmiss != n_ref);
+    for (int j = lane; j < bd.m; j += 32) miss |= (rowN[bd.goff + j] != n_ref);
     miss = __any_sync(0xffffffffu, miss);
-    if (lane == 0) flags[b] = miss ? 1 : 0;
-}
-
-// Streaming fit: did any decoded SNP row have a missing call?  (one flag for the whole fit)
-__global__ void rows_missing_kernel(const int32_t* __restrict__ rowN, int64_t n_rows, int32_t n_ref, int32_t* __restrict__ flag) {
-    int bad = 0;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rows; i += (int64_t)gridDim.x * blockDim.x)
-        bad |= (rowN[i] != n_ref);
-    if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flag, 1);
+    if (lane == 0) {
+        flags[b] = miss ? 1 : 0;
+        if (miss) atomicOr(any, 1);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------
-cudaError_t launch_rows_missing(const int32_t* rowN, int64_t n_rows, int32_t n_ref, int32_t* flag, cudaStream_t st) {
-    if (n_rows <= 0) return cudaSuccess;
-    const int ctas = (int)std::min<int64_t>((n_rows + 1023) / 1024, 296);
-    rows_missing_kernel<<<ctas, 256, 0, st>>>(rowN, n_rows, n_ref, flag);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_block_missing(const BlockDesc* blocks, int32_t n_blocks, const uint32_t* row_src,
-                                 const SnpStat* stats, int32_t n_ref, int32_t* flags, cudaStream_t st) {
-    if (n_blocks == 0) return cudaSuccess;
-    block_missing_kernel<<<(n_blocks + 7) / 8, 256, 0, st>>>(blocks, n_blocks, row_src, stats, n_ref, flags);
+cudaError_t launch_block_flags(const BlockDesc* blocks, const int32_t* list, int32_t n_list, const int32_t* rowN,
+                               int32_t n_ref, int32_t* flags, int32_t* any, cudaStream_t st) {
+    if (n_list == 0) return cudaSuccess;
+    block_flags_kernel<<<(n_list + 7) / 8, 256, 0, st>>>(blocks, list, n_list, rowN, n_ref, flags, any);
     return cudaGetLastError();
 }
 
@@ -326,40 +318,37 @@ cudaError_t launch_snp_stats(const uint8_t* bed, int64_t n_snp, int32_t n_ref, S
     return cudaGetLastError();
 }
 
-template <bool OWN, int RING>
+template <int RING>
 static cudaError_t launch_decode_t(const uint8_t* bed, int32_t n_ref, int32_t pitch, int32_t n_pad, int buf, int wpc,
-                                   const uint32_t* row_src, const int32_t* row_g, int64_t n_rows, const SnpStat* stats,
-                                   double tau, int8_t* codes, int32_t* rowN, int32_t* rowS, double* rowR, int n_sm,
-                                   cudaStream_t st) {
+                                   const uint32_t* row_src, const int32_t* row_crow, const int32_t* row_mrow, int64_t g0,
+                                   int64_t n_rows, double tau, int8_t* codes, uint8_t* dirty, int32_t* rowN, int32_t* rowS,
+                                   double* rowR, int n_sm, cudaStream_t st) {
     const size_t smem = (size_t)wpc * RING * buf;
-    cudaError_t e = cudaFuncSetAttribute(decode_rows_kernel<OWN, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(decode_rows_kernel<RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int64_t ctas = (n_rows + wpc - 1) / wpc;
     const int64_t cap = (int64_t)n_sm * 8;
     if (ctas > cap) ctas = cap;
-    decode_rows_kernel<OWN, RING><<<(unsigned)ctas, wpc * 32, smem, st>>>(bed, n_ref, pitch, n_pad, buf, row_src, row_g, n_rows,
-                                                                        stats, tau, codes, rowN, rowS, rowR);
+    decode_rows_kernel<RING><<<(unsigned)ctas, wpc * 32, smem, st>>>(bed, n_ref, pitch, n_pad, buf, row_src, row_crow, row_mrow, g0,
+                                                                   n_rows, tau, codes, dirty, rowN, rowS, rowR);
     return cudaGetLastError();
 }
 
-// stats == nullptr: the decoder derives the per-SNP counts itself (streaming fit)
+// SNP rows [g0, g0 + n_rows) of the plan
 cudaError_t launch_decode_rows(const uint8_t* bed, int32_t n_ref, int32_t n_pad, const uint32_t* row_src,
-                               const int32_t* row_g, int64_t n_rows, const SnpStat* stats, double tau,
-                               int8_t* codes, int32_t* rowN, int32_t* rowS, double* rowR, int n_sm,
+                               const int32_t* row_crow, const int32_t* row_mrow, int64_t g0, int64_t n_rows, double tau,
+                               int8_t* codes, uint8_t* dirty, int32_t* rowN, int32_t* rowS, double* rowR, int n_sm,
                                cudaStream_t st) {
     if (n_rows == 0) return cudaSuccess;
     const int32_t pitch = (n_ref + 3) / 4;
     const int buf = stage_bytes(pitch);
     // four staging buffers per warp and eight warps per CTA while they fit; long rows fall back to two buffers, then
     // to fewer warps (n_ref up to decode_max_n_ref())
-    if (stage_warps(buf, 4) == kWarpsPerCta) {
-        return stats ? launch_decode_t<false, 4>(bed, n_ref, pitch, n_pad, buf, kWarpsPerCta, row_src, row_g, n_rows, stats, tau, codes, rowN, rowS, rowR, n_sm, st)
-                     : launch_decode_t<true, 4>(bed, n_ref, pitch, n_pad, buf, kWarpsPerCta, row_src, row_g, n_rows, stats, tau, codes, rowN, rowS, rowR, n_sm, st);
-    }
+    if (stage_warps(buf, 4) == kWarpsPerCta)
+        return launch_decode_t<4>(bed, n_ref, pitch, n_pad, buf, kWarpsPerCta, row_src, row_crow, row_mrow, g0, n_rows, tau, codes, dirty, rowN, rowS, rowR, n_sm, st);
     const int wpc = stage_warps(buf, 2);
     if (wpc < 1) return cudaErrorInvalidValue;
-    return stats ? launch_decode_t<false, 2>(bed, n_ref, pitch, n_pad, buf, wpc, row_src, row_g, n_rows, stats, tau, codes, rowN, rowS, rowR, n_sm, st)
-                 : launch_decode_t<true, 2>(bed, n_ref, pitch, n_pad, buf, wpc, row_src, row_g, n_rows, stats, tau, codes, rowN, rowS, rowR, n_sm, st);
+    return launch_decode_t<2>(bed, n_ref, pitch, n_pad, buf, wpc, row_src, row_crow, row_mrow, g0, n_rows, tau, codes, dirty, rowN, rowS, rowR, n_sm, st);
 }
 
 }  // namespace dbslmm

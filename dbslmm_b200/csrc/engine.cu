@@ -79,9 +79,9 @@ struct Batch {
     int cls = 0;                          // size class (timing slot)
     bool big = false;                     // some member has mp > 1024: cluster back substitution
     int32_t ord_off = 0, ord_n = 0;       // members = order[ord_off, ord_off + ord_n)
-    int64_t crow0 = 0, crow1 = 0;         // code rows of the members (contiguous only in the streaming layout)
-    int64_t grow0 = 0, grow1 = 0;         // SNP rows
-    int32_t tile0 = 0, tile1 = 0;         // range of the plain Gram tile list
+    int64_t grow0 = 0, grow1 = 0;         // SNP rows of the members (contiguous only in the streaming layout)
+    int32_t tile0 = 0, tile1 = 0;         // range of the one-plane Gram tile list (128 x 128 tiles)
+    int32_t mtile0 = 0, mtile1 = 0;       // range of the four-plane Gram tile list (64-row x 128-column tiles)
     std::vector<StepList> steps;          // per panel step
     int64_t scratch_off = 0;              // split-K scratch region (doubles)
 };
@@ -89,7 +89,7 @@ struct Batch {
 struct Plan {
     int32_t n_blocks = 0;
     int64_t n_snp_rows = 0;       // total SNP rows (sum m)
-    int64_t n_code_rows = 0;      // genotype + mask rows
+    int64_t n_code_rows = 0;      // int8 code rows: per block m genotype rows followed by m call-mask rows
     int64_t mat_doubles = 0;      // total doubles of all block matrices
     int64_t tot_s = 0, tot_l = 0;
     int32_t max_mp = 0;
@@ -102,7 +102,7 @@ struct Plan {
     int32_t n_groups = 0;                             // split-K groups (one arrival counter each)
     int32_t n_test = 0;                               // selected test individuals (variance side channel), 0 = off
     // blob layout (byte offsets inside the plan blob, identical on host and device)
-    size_t o_blocks = 0, o_rowsrc = 0, o_rowg = 0, o_z = 0, o_tiles_plain = 0, o_tiles_miss = 0, o_order = 0,
+    size_t o_blocks = 0, o_rowsrc = 0, o_crow = 0, o_mrow = 0, o_z = 0, o_tiles_plain = 0, o_tiles_miss = 0, o_order = 0,
            o_diag = 0, o_panel = 0, o_lmaps = 0, blob_bytes = 0;
     const void* lmaps_base = nullptr;                 // L buffer the per-block tensor maps in the blob were encoded for
     uint64_t fingerprint = 0;                         // of the inputs the plan was built from (FLAG_PLAN_CACHED re-use check)
@@ -146,12 +146,14 @@ struct dbslmm_b200_handle {
     cudaEvent_t ev_bed = nullptr;        // completes when the panel, its statistics and their host copy have landed
     bool bed_pending = false;
     bool stats_valid = false;            // `stats` / `h_stats` describe the resident panel (a streaming fit skips them)
-    bool missing_hint = false;           // the last panel had missing calls: the next fit_args.bed call uploads first
-    std::vector<int32_t> miss_flags;     // per-block "has missing calls" of the current plan
+    std::vector<int32_t> miss_flags;     // per-block "has missing calls" of the last fit (computed on the device, copied back)
     int64_t n_snp = 0;
     int32_t n_ref = 0, pitch = 0, n_pad = 0;
     // workspace
-    DevBuf codes, sigma, lbuf, rowN, rowS, rowR, planblob, beta, status, intQ, intA, intN, scratch, counters, wbuf, vbed, vstats, vwork, flagbuf, dflag;
+    DevBuf codes, sigma, lbuf, rowN, rowS, rowR, planblob, beta, status, intQ, intA, intN, scratch, counters, wbuf, vbed, vstats, vwork, dflag, dirty, bflags;
+    size_t dirty_rows = 0;               // code rows the dirty map covers
+    int32_t dirty_n_ref = 0;             // ... for this panel width (another width = another default mask pattern)
+    const void* dirty_codes = nullptr;   // ... and this code buffer
     PinBuf h_blob, h_out;
     Plan plan;
     int32_t last_flags = 0, last_solver = 0, last_nfolds = 0;
@@ -274,8 +276,9 @@ int make_batches(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, 
 }
 
 // Step 2: device layout, Gram tiles, Cholesky step lists, the pinned blob.
-// `miss` = per-block missing-call flags (nullptr: assume none; verified on the device, see fit)
-int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, const int32_t* miss_in) {
+// Every block gets m genotype code rows followed by m call-mask code rows; which blocks really have missing calls is
+// found out on the device (decoder counts -> block_flags_kernel), so the plan never looks at the panel.
+int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P) {
     const int nb = a->n_blocks;
     int n_test = 0;
     if (a->test_bed) for (int i = 0; i < a->test_n_total; ++i) n_test += (a->test_indicator[i] != 0);
@@ -299,43 +302,47 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
         d.out_s = a->s_off[b];
         d.out_l = a->l_off ? a->l_off[b] : 0;
         d.nrows = d.mp + 8 + n_test * (1 + (ml > 0 ? 1 : 0));       // test-genotype rows of the variance side channel
-        const int miss = miss_in ? (miss_in[b] != 0) : 0;
         (void)ms;
-        d.has_missing = miss;
+        d.has_missing = 0;            // (unused: the flag lives on the device)
         goff += d.m;
-        croff += (int64_t)d.m * (miss ? 2 : 1);
+        croff += 2 * (int64_t)d.m;
         if (d.m > 0) moff += align_up((size_t)d.nrows * d.ld, 16);
         P.max_mp = std::max(P.max_mp, d.mp);
         const double m = d.m;
-        P.gram_ops += (miss ? 4.0 : 1.0) * (double)h->n_pad * m * (m + 1.0);   // 2 ops per MAC, lower triangle
+        P.gram_ops += (double)h->n_pad * m * (m + 1.0);   // one plane; 2 ops per MAC, lower triangle (x4 for blocks with missing calls, added after the fit)
         P.solve_flops += m * m * m / 3.0 + 2.0 * m * m;
     }
     if (goff > INT32_MAX || croff > INT32_MAX) return fail(h, DBSLMM_B200_ERR_ARG, "too many SNP rows for one call");
     P.n_snp_rows = goff;
     P.n_code_rows = croff;
     P.mat_doubles = moff;
-    P.decode_bytes = (double)croff * ((double)h->pitch + (double)h->n_pad);
+    P.decode_bytes = (double)goff * ((double)h->pitch + (double)h->n_pad);   // .bed row read + genotype code row written (mask rows: see fit)
 
-    // Gram tiles (lower triangle of 128x128 tiles) in batch order, big blocks first inside a batch
+    // Gram tiles in batch order, big blocks first inside a batch: the lower triangle as 128 x 128 tiles for the one-plane
+    // kernel and as 64-row x 128-column tiles for the four-plane kernel (every block is in both lists; the kernels pick
+    // their blocks by the device-side flag)
     std::vector<GramTile> tiles_plain, tiles_miss;
     for (Batch& B : P.batches) {
         B.tile0 = (int32_t)tiles_plain.size();
-        B.crow0 = B.grow0 = INT64_MAX;
-        B.crow1 = B.grow1 = 0;
+        B.mtile0 = (int32_t)tiles_miss.size();
+        B.grow0 = INT64_MAX;
+        B.grow1 = 0;
         for (int i = 0; i < B.ord_n; ++i) {
             const int b = P.order[B.ord_off + i];
             const BlockDesc& d = P.blocks[b];
             if (d.m == 0) continue;
-            B.crow0 = std::min<int64_t>(B.crow0, d.croff);
-            B.crow1 = std::max<int64_t>(B.crow1, (int64_t)d.croff + (int64_t)d.m * (d.has_missing ? 2 : 1));
             B.grow0 = std::min<int64_t>(B.grow0, d.goff);
             B.grow1 = std::max<int64_t>(B.grow1, (int64_t)d.goff + d.m);
             const int nt = (d.mp + 127) / 128;
             for (int ti = 0; ti < nt; ++ti)
-                for (int tj = 0; tj <= ti; ++tj) (d.has_missing ? tiles_miss : tiles_plain).push_back({b, ti, tj, 0});
+                for (int tj = 0; tj <= ti; ++tj) tiles_plain.push_back({b, ti, tj, 0});
+            const int nt64 = (d.mp + 63) / 64;
+            for (int ti = 0; ti < nt64; ++ti)
+                for (int tj = 0; 128 * tj <= 64 * ti + 63; ++tj) tiles_miss.push_back({b, ti, tj, 0});
         }
-        if (B.crow0 == INT64_MAX) B.crow0 = B.crow1 = B.grow0 = B.grow1 = 0;
+        if (B.grow0 == INT64_MAX) B.grow0 = B.grow1 = 0;
         B.tile1 = (int32_t)tiles_plain.size();
+        B.mtile1 = (int32_t)tiles_miss.size();
     }
     P.n_tiles_plain = (int32_t)tiles_plain.size();
     P.n_tiles_miss = (int32_t)tiles_miss.size();
@@ -407,8 +414,9 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
     size_t o = 0;
     auto place = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
     P.o_blocks = place(sizeof(BlockDesc) * (size_t)nb);
-    P.o_rowsrc = place(sizeof(uint32_t) * (size_t)croff);
-    P.o_rowg = place(sizeof(int32_t) * (size_t)croff);
+    P.o_rowsrc = place(sizeof(uint32_t) * (size_t)goff);
+    P.o_crow = place(sizeof(int32_t) * (size_t)goff);
+    P.o_mrow = place(sizeof(int32_t) * (size_t)goff);
     P.o_z = place(sizeof(double) * (size_t)goff);
     P.o_tiles_plain = place(sizeof(GramTile) * tiles_plain.size());
     P.o_tiles_miss = place(sizeof(GramTile) * tiles_miss.size());
@@ -424,7 +432,8 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
     struct { uint8_t* p; uint8_t* data() const { return p; } } blob{(uint8_t*)h->h_blob.p};
     std::memcpy(blob.data() + P.o_blocks, P.blocks.data(), sizeof(BlockDesc) * (size_t)nb);
     uint32_t* rs = reinterpret_cast<uint32_t*>(blob.data() + P.o_rowsrc);
-    int32_t* rg = reinterpret_cast<int32_t*>(blob.data() + P.o_rowg);
+    int32_t* rcr = reinterpret_cast<int32_t*>(blob.data() + P.o_crow);
+    int32_t* rmr = reinterpret_cast<int32_t*>(blob.data() + P.o_mrow);
     double* z = reinterpret_cast<double*>(blob.data() + P.o_z);
     // per-SNP rows (source .bed row, SNP-row index, z-score): the only O(#SNPs) part of the plan, filled by a few
     // host threads, each owning a contiguous range of blocks; the .bed row range check rides along
@@ -437,13 +446,14 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
                 const BlockDesc& d = P.blocks[b];
                 const int32_t* sp = a->s_pos + a->s_off[b];
                 const double* sz = a->s_z + a->s_off[b];
-                uint32_t* rsb = rs + d.croff;
-                int32_t* rgb = rg + d.croff;
+                uint32_t* rsb = rs + d.goff;
+                int32_t* rcb = rcr + d.goff;
+                int32_t* rmb = rmr + d.goff;
                 double* zb = z + d.goff;
                 for (int j = 0; j < d.ms; ++j) {
                     const int32_t p = sp[j];
                     oob |= (p < 0) | (p >= n_snp);
-                    rsb[j] = (uint32_t)p; rgb[j] = d.goff + j; zb[j] = sz[j];
+                    rsb[j] = (uint32_t)p; rcb[j] = d.croff + j; rmb[j] = d.croff + d.m + j; zb[j] = sz[j];
                 }
                 if (d.m > d.ms) {
                     const int32_t* lp = a->l_pos + a->l_off[b];
@@ -451,11 +461,9 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
                     for (int j = d.ms; j < d.m; ++j) {
                         const int32_t p = lp[j - d.ms];
                         oob |= (p < 0) | (p >= n_snp);
-                        rsb[j] = (uint32_t)p; rgb[j] = d.goff + j; zb[j] = lz[j - d.ms];
+                        rsb[j] = (uint32_t)p; rcb[j] = d.croff + j; rmb[j] = d.croff + d.m + j; zb[j] = lz[j - d.ms];
                     }
                 }
-                if (d.has_missing)
-                    for (int j = 0; j < d.m; ++j) { rsb[d.m + j] = rsb[j] | 0x80000000u; rgb[d.m + j] = -1; }
             }
             if (oob) bad.store(1);
         };
@@ -518,7 +526,7 @@ uint64_t plan_fingerprint(const dbslmm_b200_handle* h, const dbslmm_b200_fit_arg
     return hash_words(shape, sizeof shape, f);
 }
 
-int make_tensor_map(dbslmm_b200_handle* h, CUtensorMap* tm, void* base, int64_t n_rows, int32_t n_pad) {
+int make_tensor_map(dbslmm_b200_handle* h, CUtensorMap* tm, void* base, int64_t n_rows, int32_t n_pad, int box_rows) {
     if (!h->encode) {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
@@ -529,7 +537,7 @@ int make_tensor_map(dbslmm_b200_handle* h, CUtensorMap* tm, void* base, int64_t 
     }
     cuuint64_t dims[2] = {(cuuint64_t)n_pad, (cuuint64_t)n_rows};
     cuuint64_t strides[1] = {(cuuint64_t)n_pad};
-    cuuint32_t box[2] = {128, 128};
+    cuuint32_t box[2] = {128, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = h->encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -708,7 +716,7 @@ void dbslmm_b200_destroy(dbslmm_b200_handle* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     DevBuf* bufs[] = {&h->bed, &h->stats, &h->codes, &h->sigma, &h->lbuf, &h->rowN, &h->rowS, &h->rowR,
-                      &h->planblob, &h->beta, &h->status, &h->intQ, &h->intA, &h->intN, &h->scratch, &h->counters, &h->wbuf, &h->vbed, &h->vstats, &h->vwork, &h->flagbuf, &h->dflag};
+                      &h->planblob, &h->beta, &h->status, &h->intQ, &h->intA, &h->intN, &h->scratch, &h->counters, &h->wbuf, &h->vbed, &h->vstats, &h->vwork, &h->dflag, &h->dirty, &h->bflags};
     for (DevBuf* b : bufs) b->release();
     h->h_blob.release();
     h->h_out.release();
@@ -917,9 +925,7 @@ int upload_issue(dbslmm_b200_handle* h, const Plan& P, UploadPlan& U, const uint
 }
 
 // One fit.  streaming = the panel is uploaded inside this call from a->bed, batch by batch (see Batch); otherwise the
-// panel loaded by load_bed is used.  Returns n_bad >= 0, an error < 0, or kRetryResident when a streaming fit met
-// missing calls (its speculative no-missing plan does not apply; the caller repeats the fit on the resident copy).
-constexpr int kRetryResident = 1 << 30;
+// panel loaded by load_bed is used.  Returns n_bad >= 0 or an error < 0.
 
 int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streaming) {
     const bool want_var = a->test_bed != nullptr;
@@ -942,10 +948,8 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
     const uint64_t fp = (want_reuse || !streaming) ? plan_fingerprint(h, a) : 0;
     const bool reuse = want_reuse && P.fingerprint == fp;
     if (!reuse) {
-        // The plan is built while the panel may still be crossing PCIe, so it cannot look at it: it assumes no
-        // block has missing calls; that is checked on the device (below) and the plan is rebuilt with the true
-        // flags in the rare case the assumption fails.
-        h->miss_flags.assign((size_t)std::max(a->n_blocks, 1), 0);
+        // The plan is built while the panel may still be crossing PCIe and never looks at it: every block is laid out
+        // with both code planes, and which blocks have missing calls is decided on the device.
         int rc = make_batches(h, a, P, streaming);
         if (rc != DBSLMM_B200_OK) { P.valid = false; return rc; }
         if (streaming) {
@@ -964,12 +968,12 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
                 return fit_impl(h, a, false);
             }
         }
-        rc = build_plan(h, a, P, nullptr);
+        rc = build_plan(h, a, P);
         if (rc != DBSLMM_B200_OK) { P.valid = false; return rc; }
         P.fingerprint = fp;
         tr.mark("plan built");
     }
-    if (!streaming) { int rc = ensure_stats(h); if (rc != DBSLMM_B200_OK) return rc; }
+    if (!streaming && h->bed_pending) { CU_TRY(h, cudaEventSynchronize(h->ev_bed)); h->bed_pending = false; }   // load_bed's copy runs on the same stream, but its source buffer may go away
     const int nb = P.n_blocks;
     const int nbatch = (int)P.batches.size();
     const size_t nfold = quad ? 1 : (size_t)a->n_folds;
@@ -977,6 +981,20 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
     // ---- workspace
     CU_TRY(h, h->planblob.ensure(P.blob_bytes + 256));
     CU_TRY(h, h->codes.ensure((size_t)std::max<int64_t>(P.n_code_rows, 1) * h->n_pad));
+    {
+        // dirty[c] = code row c holds a mask that is NOT the default pattern (decode.cu).  Rows the map has never covered,
+        // and all rows when the panel width changes, start dirty: the first fit then writes their mask rows once.
+        const size_t need = (size_t)std::max<int64_t>(P.n_code_rows, 1);
+        if (h->dirty_n_ref != h->n_ref || need > h->dirty_rows || h->dirty_codes != h->codes.p) {
+            CU_TRY(h, h->dirty.ensure(need));
+            const size_t cover = h->dirty.cap;
+            CU_TRY(h, cudaMemsetAsync(h->dirty.p, 1, cover, st));
+            h->dirty_rows = cover;
+            h->dirty_n_ref = h->n_ref;
+            h->dirty_codes = h->codes.p;         // a re-allocated code buffer has lost every mask row
+        }
+    }
+    CU_TRY(h, h->bflags.ensure(sizeof(int32_t) * (size_t)(std::max(nb, 1) + kMaxBatches + 1)));
     CU_TRY(h, h->sigma.ensure(sizeof(double) * (size_t)std::max<int64_t>(P.mat_doubles, 1)));
     if (!pcg && !quad) CU_TRY(h, h->lbuf.ensure(sizeof(double) * (size_t)std::max<int64_t>(P.mat_doubles, 1)));
     CU_TRY(h, h->rowN.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(P.n_snp_rows, 1)));
@@ -997,7 +1015,7 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
         CU_TRY(h, h->intA.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(P.mat_doubles, 1)));
         CU_TRY(h, h->intN.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(P.mat_doubles, 1)));
     }
-    const size_t out_bytes = sizeof(double) * n_res + sizeof(int32_t) * (size_t)(2 * nb);
+    const size_t out_bytes = sizeof(double) * n_res + sizeof(int32_t) * (size_t)(3 * nb);     // results, status, iterations, missing-call flags
     CU_TRY(h, h->h_out.ensure(out_bytes + 128));
     const bool tma_panel = h->panel_tma && !pcg && !quad;
     bool lmaps_dirty = false;                   // the maps in the pinned blob were (re)encoded: a cached device plan needs them again
@@ -1015,7 +1033,10 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
     uint8_t* dblob = (uint8_t*)h->planblob.p;   // (re-pointed below if the plan has to be rebuilt)
     const BlockDesc* d_blocks = (const BlockDesc*)(dblob + P.o_blocks);
     const uint32_t* d_rowsrc = (const uint32_t*)(dblob + P.o_rowsrc);
-    const int32_t* d_rowg = (const int32_t*)(dblob + P.o_rowg);
+    const int32_t* d_crow = (const int32_t*)(dblob + P.o_crow);
+    const int32_t* d_mrow = (const int32_t*)(dblob + P.o_mrow);
+    int32_t* d_bflags = (int32_t*)h->bflags.p;               // [nb] per-block flag, then one "any" word per batch
+    int32_t* d_any = d_bflags + std::max(nb, 1);
     const double* d_z = (const double*)(dblob + P.o_z);
     const GramTile* d_tiles_plain = (const GramTile*)(dblob + P.o_tiles_plain);
     const GramTile* d_tiles_miss = (const GramTile*)(dblob + P.o_tiles_miss);
@@ -1059,49 +1080,18 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
                                   cudaMemcpyHostToDevice, st));
     }
     CU_TRY(h, cudaMemsetAsync(d_status, 0, sizeof(int32_t) * (size_t)std::max(2 * nb, 1), st));
-    CU_TRY(h, h->flagbuf.ensure(256));
-    CU_TRY(h, cudaMemsetAsync(h->flagbuf.p, 0, 256, st));
-    if (!streaming && !reuse && nb > 0 && P.n_code_rows > 0) {
-        // verify the no-missing assumption: per-block flags from the device statistics (1 int per block)
-        int32_t* hflags = (int32_t*)h->h_out.p;
-        CU_TRY(h, launch_block_missing(d_blocks, nb, d_rowsrc, (const SnpStat*)h->stats.p, h->n_ref, d_iters, st));
-        CU_TRY(h, cudaMemcpyAsync(hflags, d_iters, sizeof(int32_t) * (size_t)nb, cudaMemcpyDeviceToHost, st));
-        CU_TRY(h, cudaStreamSynchronize(st));
-        h->bed_pending = false;
-        bool any = false;
-        for (int b = 0; b < nb; ++b) any = any || (hflags[b] != 0);
-        h->missing_hint = any;
-        if (any) {
-            h->miss_flags.assign(hflags, hflags + nb);
-            int rc = build_plan(h, a, P, h->miss_flags.data());
-            if (rc != DBSLMM_B200_OK) { P.valid = false; return rc; }
-            // buffers sized from the speculative plan may be too small now: re-run the sizing + upload
-            CU_TRY(h, h->planblob.ensure(P.blob_bytes + 256));
-            CU_TRY(h, h->codes.ensure((size_t)std::max<int64_t>(P.n_code_rows, 1) * h->n_pad));
-            dblob = (uint8_t*)h->planblob.p;
-            d_blocks = (const BlockDesc*)(dblob + P.o_blocks);
-            d_rowsrc = (const uint32_t*)(dblob + P.o_rowsrc);
-            d_rowg = (const int32_t*)(dblob + P.o_rowg);
-            d_z = (const double*)(dblob + P.o_z);
-            d_tiles_plain = (const GramTile*)(dblob + P.o_tiles_plain);
-            d_tiles_miss = (const GramTile*)(dblob + P.o_tiles_miss);
-            d_order = (const int32_t*)(dblob + P.o_order);
-            d_diag = (const int32_t*)(dblob + P.o_diag);
-            d_panel = (const int4*)(dblob + P.o_panel);
-            if (tma_panel) { rc = encode_lmaps(h, P); if (rc != DBSLMM_B200_OK) return rc; }   // the blob was rebuilt
-            CU_TRY(h, cudaMemcpyAsync(dblob, h->h_blob.p, P.blob_bytes, cudaMemcpyHostToDevice, st));
-            CU_TRY(h, cudaMemsetAsync(d_status, 0, sizeof(int32_t) * (size_t)std::max(2 * nb, 1), st));
-        }
-    }
+    CU_TRY(h, cudaMemsetAsync(d_any, 0, sizeof(int32_t) * (size_t)(kMaxBatches + 1), st));
     CU_TRY(h, cudaEventRecord(h->ev[1], st));
 
     if (!pcg && !quad && P.n_groups > 0) CU_TRY(h, cudaMemsetAsync(h->counters.p, 0, sizeof(int32_t) * (size_t)P.n_groups, st));
     if (!pcg && !quad) CU_TRY(h, cudaMemsetAsync(h->dflag.p, 0, sizeof(int32_t) * (size_t)std::max(nb, 1), st));
     // ---- decode + gram
     GramArgs g;
-    CUtensorMap tmap;
+    CUtensorMap tmap, tmap64;
     if (P.n_code_rows > 0) {
-        int rc = make_tensor_map(h, &tmap, h->codes.p, P.n_code_rows, h->n_pad);
+        int rc = make_tensor_map(h, &tmap, h->codes.p, P.n_code_rows, h->n_pad, 128);
+        if (rc != DBSLMM_B200_OK) return rc;
+        rc = make_tensor_map(h, &tmap64, h->codes.p, P.n_code_rows, h->n_pad, 64);      // I side of the four-plane kernel
         if (rc != DBSLMM_B200_OK) return rc;
         g.blocks = d_blocks;
         g.nk = h->n_pad / 128;
@@ -1116,57 +1106,67 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
         g.intN = keep_int ? (int32_t*)h->intN.p : nullptr;
         g.full = full ? 1 : 0;
         g.light = 0;
+        g.flags = d_bflags;
     }
-    if (!streaming) {
-        if (P.n_code_rows > 0) {
-            CU_TRY(h, launch_decode_rows((const uint8_t*)h->bed.p, h->n_ref, h->n_pad, d_rowsrc, d_rowg, P.n_code_rows,
-                                         (const SnpStat*)h->stats.p, a->tau, (int8_t*)h->codes.p, (int32_t*)h->rowN.p,
-                                         (int32_t*)h->rowS.p, (double*)h->rowR.p, h->n_sm, st));
+    // One chain per batch of blocks: decode its SNP rows (both code planes where needed) -> per-block missing-call flags
+    // -> one-plane Gram over the blocks without missing calls -> four-plane Gram over the others (returns at once if
+    // there are none) -> z rows.  A resident fit runs ONE chain over everything.
+    auto chain = [&](int64_t g0, int64_t g1, const int32_t* list, int32_t n_list, int32_t t0, int32_t t1, int32_t mt0, int32_t mt1,
+                     int32_t* any, bool light) -> int {
+        if (g1 <= g0) return DBSLMM_B200_OK;
+        CU_TRY(h, launch_decode_rows((const uint8_t*)h->bed.p, h->n_ref, h->n_pad, d_rowsrc, d_crow, d_mrow, g0, g1 - g0, a->tau,
+                                     (int8_t*)h->codes.p, (uint8_t*)h->dirty.p, (int32_t*)h->rowN.p, (int32_t*)h->rowS.p,
+                                     (double*)h->rowR.p, h->n_sm, st));
+        CU_TRY(h, launch_block_flags(d_blocks, list, n_list, (const int32_t*)h->rowN.p, h->n_ref, d_bflags, any, st));
+        n_launch += 2;
+        g.any = any;
+        g.light = light ? 1 : 0;         // 3-stage ring: a Gram CTA fits on an SM next to one Cholesky panel CTA
+        if (t1 > t0) {
+            g.tiles = d_tiles_plain + t0;
+            g.n_tiles = t1 - t0;
+            CU_TRY(h, launch_gram(tmap, g, st));
             ++n_launch;
         }
-        CU_TRY(h, cudaEventRecord(h->ev[2], st));
-        if (P.n_code_rows > 0) {
-            if (P.n_tiles_plain) {
-                g.tiles = d_tiles_plain;
-                g.n_tiles = P.n_tiles_plain;
-                CU_TRY(h, launch_gram(tmap, g, false, st));
-                ++n_launch;
-            }
-            if (P.n_tiles_miss) {
-                g.tiles = d_tiles_miss;
-                g.n_tiles = P.n_tiles_miss;
-                CU_TRY(h, launch_gram(tmap, g, true, st));
-                ++n_launch;
-            }
-            CU_TRY(h, launch_fill_z(d_blocks, nullptr, nb, d_z, (double*)h->sigma.p, st));
+        if (mt1 > mt0) {
+            g.tiles = d_tiles_miss + mt0;
+            g.n_tiles = mt1 - mt0;
+            CU_TRY(h, launch_gram_missing(tmap, tmap64, g, st));
             ++n_launch;
+        }
+        CU_TRY(h, launch_fill_z(d_blocks, list, n_list, d_z, (double*)h->sigma.p, st));
+        ++n_launch;
+        return DBSLMM_B200_OK;
+    };
+    if (!streaming) {
+        if (P.n_snp_rows > 0) {
+            CU_TRY(h, launch_decode_rows((const uint8_t*)h->bed.p, h->n_ref, h->n_pad, d_rowsrc, d_crow, d_mrow, 0, P.n_snp_rows, a->tau,
+                                         (int8_t*)h->codes.p, (uint8_t*)h->dirty.p, (int32_t*)h->rowN.p, (int32_t*)h->rowS.p,
+                                         (double*)h->rowR.p, h->n_sm, st));
+            ++n_launch;
+        }
+        CU_TRY(h, cudaEventRecord(h->ev[2], st));          // decoder done
+        if (P.n_snp_rows > 0) {
+            CU_TRY(h, launch_block_flags(d_blocks, nullptr, nb, (const int32_t*)h->rowN.p, h->n_ref, d_bflags, d_any, st));
+            ++n_launch;
+            g.any = d_any;
+            g.tiles = d_tiles_plain;
+            g.n_tiles = P.n_tiles_plain;
+            CU_TRY(h, launch_gram(tmap, g, st));
+            g.tiles = d_tiles_miss;
+            g.n_tiles = P.n_tiles_miss;
+            CU_TRY(h, launch_gram_missing(tmap, tmap64, g, st));
+            CU_TRY(h, launch_fill_z(d_blocks, nullptr, nb, d_z, (double*)h->sigma.p, st));
+            n_launch += 3;
         }
     } else {
-        // one decode -> Gram chain per batch, each gated on the upload of that batch's rows; the batch's Cholesky
-        // (on its class stream, below) is gated on ev_gram, so big classes factor while the bulk is still in flight
+        // one chain per batch, each gated on the upload of that batch's rows; the batch's Cholesky (on its class
+        // stream, below) is gated on ev_gram, so big classes factor while the bulk is still in flight
         CU_TRY(h, cudaEventRecord(h->ev[2], st));
         for (int bi = 0; bi < nbatch; ++bi) {
             const Batch& B = P.batches[bi];
             CU_TRY(h, cudaStreamWaitEvent(st, h->ev_up[bi], 0));
-            const int64_t nrow = B.crow1 - B.crow0;
-            if (nrow > 0) {
-                // stats == nullptr: the decoder counts the genotypes of the rows it stages itself
-                CU_TRY(h, launch_decode_rows((const uint8_t*)h->bed.p, h->n_ref, h->n_pad, d_rowsrc + B.crow0, d_rowg + B.crow0,
-                                             nrow, nullptr, a->tau, (int8_t*)h->codes.p + (size_t)B.crow0 * h->n_pad,
-                                             (int32_t*)h->rowN.p, (int32_t*)h->rowS.p, (double*)h->rowR.p, h->n_sm, st));
-                CU_TRY(h, launch_rows_missing((const int32_t*)h->rowN.p + B.grow0, B.grow1 - B.grow0, h->n_ref,
-                                              (int32_t*)h->flagbuf.p, st));
-                n_launch += 2;
-                if (B.tile1 > B.tile0) {
-                    g.tiles = d_tiles_plain + B.tile0;
-                    g.n_tiles = B.tile1 - B.tile0;
-                    g.light = 1;                 // 3-stage ring: a Gram CTA fits on an SM next to one Cholesky panel CTA
-                    CU_TRY(h, launch_gram(tmap, g, false, st));
-                    ++n_launch;
-                }
-                CU_TRY(h, launch_fill_z(d_blocks, d_order + B.ord_off, B.ord_n, d_z, (double*)h->sigma.p, st));
-                ++n_launch;
-            }
+            int rc = chain(B.grow0, B.grow1, d_order + B.ord_off, B.ord_n, B.tile0, B.tile1, B.mtile0, B.mtile1, d_any + 1 + bi, true);
+            if (rc != DBSLMM_B200_OK) return rc;
             CU_TRY(h, cudaEventRecord(h->ev_gram[bi], st));
         }
     }
@@ -1342,8 +1342,9 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
                               cudaMemcpyDeviceToHost, st));
     if (d_var) CU_TRY(h, cudaMemcpyAsync(a->variance_out, d_var, sizeof(double) * (size_t)a->n_folds * nb * P.n_test,
                                          cudaMemcpyDeviceToHost, st));
-    int32_t* h_flag = (int32_t*)(hout + align_up(out_bytes, 8));
-    CU_TRY(h, cudaMemcpyAsync(h_flag, h->flagbuf.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (nb > 0)     // which blocks had missing calls (decided on the device): for the work accounting and the inspection hooks
+        CU_TRY(h, cudaMemcpyAsync(hout + sizeof(double) * n_res + sizeof(int32_t) * (size_t)(2 * nb), d_bflags, sizeof(int32_t) * (size_t)nb,
+                                  cudaMemcpyDeviceToHost, st));
     CU_TRY(h, cudaEventRecord(h->ev[5], st));
     tr.mark("all launched");
     if (tr.on && streaming) {
@@ -1377,7 +1378,6 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
         CU_TRY(h, cudaEventSynchronize(h->ev_bed));
         h->bed_pending = false;
     }
-    if (streaming && *h_flag != 0) { P.valid = false; return kRetryResident; }   // missing calls: see fit_impl's header
     const double* hb = (const double*)hout;
     if (quad && nb > 0) std::memcpy(a->quadform_out, hb, sizeof(double) * (size_t)nb);
     for (int f = 0; f < a->n_folds && !quad; ++f) {
@@ -1390,6 +1390,14 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
     for (int b = 0; b < nb; ++b) {
         if (a->block_status_out) a->block_status_out[b] = hs[b];
         n_bad += (hs[b] != 0);
+    }
+    // which blocks took the four-plane path
+    h->miss_flags.assign(hs + 2 * nb, hs + 3 * nb);
+    double gram_ops = 0.0, mask_bytes = 0.0;
+    for (int b = 0; b < nb; ++b) {
+        const double m = P.blocks[b].m;
+        gram_ops += (h->miss_flags[b] ? 4.0 : 1.0) * (double)h->n_pad * m * (m + 1.0);
+        if (h->miss_flags[b]) mask_bytes += m * (double)h->n_pad;            // (upper bound: mask rows of SNPs with missing calls)
     }
     h->last_flags = a->flags | (full ? DBSLMM_B200_FLAG_FULL_SIGMA : 0);
     h->last_solver = a->solver;
@@ -1412,9 +1420,12 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
         }
         t->n_launches = n_launch;
         t->n_chol_launches = n_chol_launch;
-        t->gram_ops = P.gram_ops;
+        t->gram_ops = gram_ops;
+        t->streamed = streaming ? 1 : 0;
+        t->n_blocks_missing = 0;
+        for (int b = 0; b < nb; ++b) t->n_blocks_missing += (h->miss_flags[b] != 0);
         t->solve_flops = quad ? 0.0 : P.solve_flops * (double)a->n_folds;
-        t->decode_bytes = P.decode_bytes;
+        t->decode_bytes = P.decode_bytes + mask_bytes;
     }
     return n_bad;
 }
@@ -1458,7 +1469,7 @@ int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
     // ---- the panel comes with the call (what DBSLMMFIT::est does with its bed_str argument)
     if (h->bed_pending) { CU_TRY(h, cudaEventSynchronize(h->ev_bed)); h->bed_pending = false; }
     const bool can_stream = !want_var && !quad && a->solver == DBSLMM_B200_SOLVER_CHOLESKY && !(a->flags & DBSLMM_B200_FLAG_PLAN_CACHED) &&
-                            a->n_blocks > 0 && h->stream_bed && !h->missing_hint;
+                            a->n_blocks > 0 && h->stream_bed;
     if (!can_stream) {
         int rc = dbslmm_b200_load_bed(h, a->bed, a->bed_n_snp, a->bed_n_ref);
         if (rc != DBSLMM_B200_OK) return rc;
@@ -1486,12 +1497,6 @@ int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
         h->plan.valid = false;
         h->err = msg;
         return rc;
-    }
-    if (rc == kRetryResident) {
-        // the panel is resident by now; statistics are computed on demand.  Panels with missing calls tend to come
-        // again (folds, repeated fits): remember, so the next call does not stream speculatively
-        h->missing_hint = true;
-        rc = fit_impl(h, a, false);
     }
     if (a->flags & DBSLMM_B200_FLAG_PANEL_SUBSET) {
         // only the rows of this call's blocks were uploaded: the device copy is no panel a later call could use
@@ -1569,10 +1574,14 @@ int dbslmm_b200_score(dbslmm_b200_handle* h, const uint8_t* bed_val, int64_t n_s
 // ---------------------------------------------------------------------------------------------
 // inspection hooks
 // ---------------------------------------------------------------------------------------------
-int dbslmm_b200_get_row_codes(dbslmm_b200_handle* h, int64_t row, int8_t* codes_out, int32_t n_out) {
+int dbslmm_b200_get_row_codes(dbslmm_b200_handle* h, int32_t block, int32_t j, int32_t plane, int8_t* codes_out, int32_t n_out) {
     if (!h || !codes_out) return DBSLMM_B200_ERR_ARG;
     if (!h->plan.valid) return fail(h, DBSLMM_B200_ERR_STATE, "no fit yet");
-    if (row < 0 || row >= h->plan.n_code_rows || n_out > h->n_pad || n_out < 0) return fail(h, DBSLMM_B200_ERR_ARG, "row out of range");
+    if (block < 0 || block >= h->plan.n_blocks || n_out > h->n_pad || n_out < 0 || plane < 0 || plane > 1)
+        return fail(h, DBSLMM_B200_ERR_ARG, "row out of range");
+    const BlockDesc& bd = h->plan.blocks[block];
+    if (j < 0 || j >= bd.m) return fail(h, DBSLMM_B200_ERR_ARG, "row out of range");
+    const int64_t row = (int64_t)bd.croff + (plane ? bd.m : 0) + j;
     CU_TRY(h, cudaSetDevice(h->device));
     CU_TRY(h, cudaMemcpy(codes_out, (const int8_t*)h->codes.p + (size_t)row * h->n_pad, (size_t)n_out, cudaMemcpyDeviceToHost));
     return DBSLMM_B200_OK;
@@ -1621,7 +1630,7 @@ int dbslmm_b200_get_block_gram(dbslmm_b200_handle* h, int32_t block, int32_t* q_
             for (int j = 0; j < m; ++j) out[(size_t)i * m + j] = s[(size_t)i * bd->ld + j];
     };
     copy_plane(q_out);
-    if (bd->has_missing) {
+    if (h->miss_flags.size() > (size_t)block && h->miss_flags[block]) {
         if (a_out) { rc = fetch_block(h, block, h->intA.p, sizeof(int32_t), tmp, &bd); if (rc) return rc; copy_plane(a_out); }
         if (n_out) { rc = fetch_block(h, block, h->intN.p, sizeof(int32_t), tmp, &bd); if (rc) return rc; copy_plane(n_out); }
     } else {

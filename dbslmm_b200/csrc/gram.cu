@@ -12,12 +12,15 @@
 // the reference.  Blocks without missing calls need only Q
 // (A_ij = S_i, N_ij = n): one accumulator plane; blocks with missing calls use four.
 //
-// Kernel shape: one CTA per 128 x 128 tile of the block's lower triangle, 192 threads:
-//   warp 0   TMA producer: int8 code tiles [128 rows x 128 B], SWIZZLE_128B, 3-stage ring
-//   warp 1   TMEM allocator + single-thread tcgen05.mma.kind::i8 issuer (M=128, N=128, K=32)
-//   warps 2-5 epilogue: tcgen05.ld -> FP64 transform -> coalesced stores of the LOWER tile.
+// Kernel shape (both kernels are persistent, one CTA per SM walking a tile list, warp-specialised):
+//   warp 0   TMA producer: int8 code tiles [rows x 128 B], SWIZZLE_128B, multi-stage ring
+//   warp 1   TMEM allocator + single-thread tcgen05.mma.kind::i8 issuer (s32 accumulators double-buffered in TMEM)
+//   warps 2-9 epilogue: tcgen05.ld -> FP64 transform -> coalesced stores of the LOWER tile, overlapping the next
+//            tile's main loop.
 // The A operand is the J (column) side and the B operand the I (row) side, so a TMEM lane
 // holds one Sigma column and consecutive lanes store consecutive addresses of one Sigma row.
+// Which kernel owns a block is decided ON THE DEVICE: block_flags_kernel (decode.cu) sets flags[b] from the counts the
+// decoder just produced; the one-plane kernel skips flagged blocks, the four-plane kernel the others.
 #include <algorithm>
 #include "common.cuh"
 #include "kernels.h"
@@ -26,17 +29,6 @@ namespace dbslmm {
 
 static constexpr int kTile = 128;            // output tile edge and UMMA M = N
 static constexpr int kTileBytes = kTile * 128;   // one operand stage: 128 rows x 128 B (K chunk = 128 samples)
-static constexpr int kStages = 3;
-static constexpr int kGramThreads = 192;
-
-template <int NPROD>
-struct GramCfg {
-    static constexpr int kOper = (NPROD == 1) ? 2 : 4;           // operand tiles per stage
-    static constexpr int kStageBytes = kOper * kTileBytes;
-    static constexpr int kSmem = kStages * kStageBytes + 1024;   // + alignment slack
-    static constexpr uint32_t kTmemCols = (NPROD == 1) ? 128 : 512;
-    static constexpr int kChunk = (NPROD == 1) ? 32 : 16;        // TMEM columns per epilogue step
-};
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
@@ -48,173 +40,8 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         : "memory");
 }
 
-template <int NPROD>
-__global__ void __launch_bounds__(kGramThreads, (NPROD == 1) ? 2 : 1)
-gram_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs a) {
-    using Cfg = GramCfg<NPROD>;
-    extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], accum_bar;
-    __shared__ __align__(16) double4 row_consts[kTile];          // {S_i, n_i, r_i} of the tile's rows
-    __shared__ uint32_t tmem_slot;
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-
-    const GramTile tile = a.tiles[blockIdx.x];
-    const BlockDesc bd = a.blocks[tile.blk];
-    const bool diag = (tile.ti == tile.tj);
-    const int nk = a.nk;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(&accum_bar, 1);
-        mbar_fence_init();
-        tma_prefetch_desc(&tmap);
-    }
-    if (warp == 1) tmem_alloc<Cfg::kTmemCols>(&tmem_slot);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = tmem_slot;
-
-    // operand rows in the global code array: genotype rows then (missing blocks) mask rows
-    const int32_t rowJ = bd.croff + tile.tj * kTile;
-    const int32_t rowI = bd.croff + tile.ti * kTile;
-    const int32_t rowJm = rowJ + bd.m, rowIm = rowI + bd.m;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            // ---------------- TMA producer ----------------
-            const uint32_t bytes = (uint32_t)((diag ? Cfg::kOper / 2 : Cfg::kOper) * kTileBytes);
-            for (int ks = 0; ks < nk; ++ks) {
-                const int s = ks % kStages;
-                const uint32_t ph = (uint32_t)((ks / kStages) & 1);
-                mbar_wait(&empty_bar[s], ph ^ 1u);
-                uint8_t* st = smem + (size_t)s * Cfg::kStageBytes;
-                mbar_expect_tx(&full_bar[s], bytes);
-                const int32_t x = ks * 128;
-                tma_load_2d(st + 0 * kTileBytes, &tmap, x, rowJ, &full_bar[s]);
-                if (!diag) tma_load_2d(st + 1 * kTileBytes, &tmap, x, rowI, &full_bar[s]);
-                if (NPROD == 4) {
-                    tma_load_2d(st + 2 * kTileBytes, &tmap, x, rowJm, &full_bar[s]);
-                    if (!diag) tma_load_2d(st + 3 * kTileBytes, &tmap, x, rowIm, &full_bar[s]);
-                }
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            // ---------------- MMA issuer ----------------
-            constexpr uint32_t idesc = make_i8_idesc(kTile, kTile);
-            for (int ks = 0; ks < nk; ++ks) {
-                const int s = ks % kStages;
-                const uint32_t ph = (uint32_t)((ks / kStages) & 1);
-                mbar_wait(&full_bar[s], ph);
-                tc_fence_after();
-                const uint32_t st = smem_u32(smem + (size_t)s * Cfg::kStageBytes);
-                const uint32_t gJ = st, gI = diag ? st : st + kTileBytes;
-                const uint64_t dgJ = make_sw128_kmajor_desc(gJ), dgI = make_sw128_kmajor_desc(gI);
-                uint64_t dmJ = 0, dmI = 0;
-                if (NPROD == 4) {
-                    const uint32_t mJ = st + 2 * kTileBytes, mI = diag ? mJ : st + 3 * kTileBytes;
-                    dmJ = make_sw128_kmajor_desc(mJ);
-                    dmI = make_sw128_kmajor_desc(mI);
-                }
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                    const uint32_t acc = (ks > 0 || kk > 0) ? 1u : 0u;
-                    const uint64_t adv = (uint64_t)(kk * 2);   // +32 bytes inside the 128 B swizzle atom
-                    umma_i8(tmem_base + 0 * kTile, dgJ + adv, dgI + adv, idesc, acc);       // Q  : g_j . g_i
-                    if (NPROD == 4) {
-                        umma_i8(tmem_base + 1 * kTile, dgJ + adv, dmI + adv, idesc, acc);   // P1 : g_j . M_i
-                        umma_i8(tmem_base + 2 * kTile, dmJ + adv, dgI + adv, idesc, acc);   // P2 : M_j . g_i
-                        umma_i8(tmem_base + 3 * kTile, dmJ + adv, dmI + adv, idesc, acc);   // N  : M_j . M_i
-                    }
-                }
-                umma_commit(&empty_bar[s]);        // frees the smem stage when these MMAs retire
-            }
-            umma_commit(&accum_bar);               // accumulators complete
-        }
-    } else {
-        // ---------------- epilogue: 4 warps, TMEM lane quarter = warp % 4 ----------------
-        const int q = warp & 3;
-        const int jl = tile.tj * kTile + q * 32 + lane;          // Sigma column (block local)
-        const bool jvalid = jl < bd.m;
-        double Sj = 0.0, Nj = 1.0, rj = 0.0;
-        if (jvalid) { Sj = (double)a.rowS[bd.goff + jl]; Nj = (double)a.rowN[bd.goff + jl]; rj = a.rowR[bd.goff + jl]; }
-        const double dn = (double)a.n_ref;
-        // per-row constants {S_i, n_i, r_i} of the tile's 128 rows go through shared memory (one broadcast read per
-        // row instead of shuffles); their global loads overlap the main loop
-        {
-            const int il = tile.ti * kTile + (warp - 2) * 32 + lane;
-            double s_i = 0.0, n_i = 1.0, r_i = 0.0;
-            if (il < bd.m) { s_i = (double)a.rowS[bd.goff + il]; n_i = (double)a.rowN[bd.goff + il]; r_i = a.rowR[bd.goff + il]; }
-            row_consts[(warp - 2) * 32 + lane] = make_double4(s_i, n_i, r_i, 0.0);
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");           // the four epilogue warps
-        mbar_wait(&accum_bar, 0);
-        tc_fence_after();
-        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
-        double* sig = a.sigma + bd.moff;
-        constexpr int CH = Cfg::kChunk;
-#pragma unroll 1
-        for (int c0 = 0; c0 < kTile; c0 += CH) {
-            const int ibase = tile.ti * kTile + c0;
-            if (ibase >= bd.mp) break;                            // warp-uniform
-            uint32_t v0[CH], v1[NPROD == 4 ? CH : 1], v2[NPROD == 4 ? CH : 1], v3[NPROD == 4 ? CH : 1];
-            if constexpr (CH == 32) {
-                tmem_ld32(tlane + c0, v0);
-            } else {
-                tmem_ld16(tlane + 0 * kTile + c0, v0);
-                tmem_ld16(tlane + 1 * kTile + c0, v1);
-                tmem_ld16(tlane + 2 * kTile + c0, v2);
-                tmem_ld16(tlane + 3 * kTile + c0, v3);
-            }
-            tmem_ld_wait();
-#pragma unroll
-            for (int r = 0; r < CH; ++r) {
-                const int il = ibase + r;
-                const double4 rc = row_consts[c0 + r];
-                const double Si = rc.x, Ni = rc.y, ri = rc.z;
-                if (il >= bd.mp || jl > il) continue;
-                double val;
-                if (il < bd.m) {
-                    double num;
-                    if constexpr (NPROD == 1) {
-                        num = dn * fma(-Si, Sj, dn * (double)(int32_t)v0[r]);        // n (n Q - S_i S_j): exact integer < 2^53
-                    } else {
-                        const double Q = (double)(int32_t)v0[r], P1 = (double)(int32_t)v1[r];
-                        const double P2 = (double)(int32_t)v2[r], Nn = (double)(int32_t)v3[r];
-                        // A_ij = sum g_i M_j = P2,  A_ji = sum g_j M_i = P1
-                        num = Ni * Nj * Q - Ni * Sj * P2 - Nj * Si * P1 + Si * Sj * Nn;
-                    }
-                    val = num * ri * rj;
-                    if (il == jl) val += a.one_minus_tau;
-                } else {
-                    val = (il == jl) ? 1.0 : 0.0;                 // identity padding rows m..mp-1
-                }
-                sig[(size_t)il * bd.ld + jl] = val;
-                if (a.full && jl < il) sig[(size_t)jl * bd.ld + il] = val;
-                if (a.intQ != nullptr && il < bd.m) {
-                    const size_t o = (size_t)bd.moff + (size_t)il * bd.ld + jl, ot = (size_t)bd.moff + (size_t)jl * bd.ld + il;
-                    a.intQ[o] = (int32_t)v0[r];
-                    a.intQ[ot] = (int32_t)v0[r];
-                    if constexpr (NPROD == 4) {
-                        a.intA[o] = (int32_t)v2[r];
-                        a.intA[ot] = (int32_t)v1[r];
-                        a.intN[o] = (int32_t)v3[r];
-                        a.intN[ot] = (int32_t)v3[r];
-                    }
-                }
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
-}
-
 // ------------------------------------------------------------------------------------------
-// Persistent variant for blocks WITHOUT missing calls (one accumulator plane): one CTA per SM walks
+// Blocks WITHOUT missing calls (one accumulator plane): one CTA per SM walks
 // the tile list; the s32 accumulator is double-buffered in TMEM (2 x 128 columns) so the FP64
 // epilogue of tile i (8 warps) overlaps the TMA/MMA main loop of tile i+1, and a 5-stage smem
 // ring keeps more TMA requests in flight.  Same arithmetic as gram_kernel<1>.
@@ -255,6 +82,7 @@ gram_persistent_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs 
             uint32_t it = 0;
             for (int tile_i = blockIdx.x; tile_i < a.n_tiles; tile_i += gridDim.x) {
                 const GramTile tile = a.tiles[tile_i];
+                if (a.flags[tile.blk] != 0) continue;                 // missing calls: the four-plane kernel's block
                 const BlockDesc bd = a.blocks[tile.blk];
                 const bool diag = (tile.ti == tile.tj);
                 const int32_t rowJ = bd.croff + tile.tj * kTile, rowI = bd.croff + tile.ti * kTile;
@@ -274,8 +102,9 @@ gram_persistent_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs 
         if (lane == 0) {
             constexpr uint32_t idesc = make_i8_idesc(kTile, kTile);
             uint32_t it = 0, lt = 0;
-            for (int tile_i = blockIdx.x; tile_i < a.n_tiles; tile_i += gridDim.x, ++lt) {
+            for (int tile_i = blockIdx.x; tile_i < a.n_tiles; tile_i += gridDim.x) {
                 const GramTile tile = a.tiles[tile_i];
+                if (a.flags[tile.blk] != 0) continue;
                 const bool diag = (tile.ti == tile.tj);
                 const uint32_t as = lt & 1u;
                 mbar_wait(&acc_empty[as], ((lt >> 1) & 1u) ^ 1u);      // epilogue has drained this accumulator
@@ -294,6 +123,7 @@ gram_persistent_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs 
                     umma_commit(&empty_bar[s]);
                 }
                 umma_commit(&acc_full[as]);
+                ++lt;
             }
         }
     } else {
@@ -301,10 +131,12 @@ gram_persistent_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs 
         const double dn = (double)a.n_ref;
         double2* rc = row_consts[warp - 2];                      // this warp's 64 rows: {S_i, r_i}
         uint32_t lt = 0;
-        for (int tile_i = blockIdx.x; tile_i < a.n_tiles; tile_i += gridDim.x, ++lt) {
+        for (int tile_i = blockIdx.x; tile_i < a.n_tiles; tile_i += gridDim.x) {
             const GramTile tile = a.tiles[tile_i];
+            if (a.flags[tile.blk] != 0) continue;
             const BlockDesc bd = a.blocks[tile.blk];
-            const uint32_t as = lt & 1u;
+            const uint32_t my_lt = lt++;                         // tiles this CTA has processed so far
+            const uint32_t as = my_lt & 1u;
             const int jl = tile.tj * kTile + q * 32 + lane;
             const int i0 = tile.ti * kTile + half * 64;          // first row of this warp's half
             double Sj = 0.0, rj = 0.0;
@@ -320,7 +152,7 @@ gram_persistent_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs 
                 rc[32 * hh + lane] = c;
             }
             __syncwarp();
-            mbar_wait(&acc_full[as], (lt >> 1) & 1u);
+            mbar_wait(&acc_full[as], (my_lt >> 1) & 1u);
             tc_fence_after();
             const uint32_t tlane = tmem_base + as * kTile + ((uint32_t)(q * 32) << 16);
             double* sig = a.sigma + bd.moff;
@@ -376,27 +208,204 @@ gram_persistent_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs 
     if (warp == 1) tmem_dealloc<256>(tmem_base);
 }
 
-cudaError_t launch_gram(const CUtensorMap& tmap, const GramArgs& a, bool missing, cudaStream_t st) {
-    if (a.n_tiles == 0) return cudaSuccess;
-    cudaError_t e;
-    if (!missing) {
-        int dev = 0, n_sm = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        if (a.light) {
-            e = cudaFuncSetAttribute(gram_persistent_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg<3>::kSmem);
-            if (e != cudaSuccess) return e;
-            gram_persistent_kernel<3><<<std::min(a.n_tiles, n_sm), kPThreads, PCfg<3>::kSmem, st>>>(tmap, a);
-        } else {
-            e = cudaFuncSetAttribute(gram_persistent_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg<5>::kSmem);
-            if (e != cudaSuccess) return e;
-            gram_persistent_kernel<5><<<std::min(a.n_tiles, n_sm), kPThreads, PCfg<5>::kSmem, st>>>(tmap, a);
+// ------------------------------------------------------------------------------------------
+// Blocks WITH missing calls: four accumulator planes per tile (Q = g.g, P1 = g_j.M_i, P2 = M_j.g_i, N = M.M) and the
+// four-term exact numerator.  Same persistent, warp-specialised shape as above; the output tile is 128 columns (J, the
+// A operand, TMEM lanes) x 64 rows (I, the B operand, N = 64), so the four s32 planes take 256 TMEM columns and are
+// double-buffered in the 512 the SM has: the FP64 epilogue of one tile overlaps the main loop of the next.
+// Stage = J genotype + J mask rows (2 x 16 KB) and I genotype + I mask rows (2 x 8 KB); 4 stages.
+// Tile: ti counts 64-row units, tj 128-column units; listed if any entry lies in the lower triangle.
+// ------------------------------------------------------------------------------------------
+static constexpr int kMStages = 4;
+static constexpr int kMStageBytes = 2 * kTileBytes + 2 * (kTileBytes / 2);
+static constexpr int kMSmem = kMStages * kMStageBytes + 1024;
+static constexpr int kTileI = 64;
+
+__global__ void __launch_bounds__(kPThreads, 1)
+gram_missing_kernel(const __grid_constant__ CUtensorMap tmapJ, const __grid_constant__ CUtensorMap tmapI, const GramArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[kMStages], empty_bar[kMStages], acc_full[2], acc_empty[2];
+    __shared__ __align__(16) double4 row_consts[8][32];          // per epilogue warp: {S_i, n_i, r_i} of its 32 rows
+    __shared__ uint32_t tmem_slot;
+    if (*a.any == 0) return;                                     // no block of this launch has missing calls
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int nk = a.nk;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kMStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
+        mbar_fence_init();
+        tma_prefetch_desc(&tmapJ);
+        tma_prefetch_desc(&tmapI);
+    }
+    if (warp == 1) tmem_alloc<512>(&tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile_i = blockIdx.x; tile_i < a.n_tiles; tile_i += gridDim.x) {
+                const GramTile tile = a.tiles[tile_i];
+                if (a.flags[tile.blk] == 0) continue;
+                const BlockDesc bd = a.blocks[tile.blk];
+                const int32_t rowJ = bd.croff + tile.tj * kTile, rowI = bd.croff + tile.ti * kTileI;
+                for (int ks = 0; ks < nk; ++ks, ++it) {
+                    const int s = it % kMStages;
+                    mbar_wait(&empty_bar[s], ((it / kMStages) & 1u) ^ 1u);
+                    uint8_t* st = smem + (size_t)s * kMStageBytes;
+                    mbar_expect_tx(&full_bar[s], (uint32_t)kMStageBytes);
+                    tma_load_2d(st, &tmapJ, ks * 128, rowJ, &full_bar[s]);
+                    tma_load_2d(st + kTileBytes, &tmapJ, ks * 128, rowJ + bd.m, &full_bar[s]);
+                    tma_load_2d(st + 2 * kTileBytes, &tmapI, ks * 128, rowI, &full_bar[s]);
+                    tma_load_2d(st + 2 * kTileBytes + kTileBytes / 2, &tmapI, ks * 128, rowI + bd.m, &full_bar[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_i8_idesc(kTile, kTileI);
+            uint32_t it = 0, lt = 0;
+            for (int tile_i = blockIdx.x; tile_i < a.n_tiles; tile_i += gridDim.x) {
+                const GramTile tile = a.tiles[tile_i];
+                if (a.flags[tile.blk] == 0) continue;
+                const uint32_t as = lt & 1u;
+                mbar_wait(&acc_empty[as], ((lt >> 1) & 1u) ^ 1u);      // epilogue has drained this accumulator set
+                tc_fence_after();
+                const uint32_t tm = tmem_base + as * 256;
+                for (int ks = 0; ks < nk; ++ks, ++it) {
+                    const int s = it % kMStages;
+                    mbar_wait(&full_bar[s], (it / kMStages) & 1u);
+                    tc_fence_after();
+                    const uint32_t st = smem_u32(smem + (size_t)s * kMStageBytes);
+                    const uint64_t dgJ = make_sw128_kmajor_desc(st), dmJ = make_sw128_kmajor_desc(st + kTileBytes);
+                    const uint64_t dgI = make_sw128_kmajor_desc(st + 2 * kTileBytes);
+                    const uint64_t dmI = make_sw128_kmajor_desc(st + 2 * kTileBytes + kTileBytes / 2);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const uint32_t acc = (ks > 0 || kk > 0) ? 1u : 0u;
+                        const uint64_t adv = (uint64_t)(kk * 2);   // +32 bytes inside the 128 B swizzle atom
+                        umma_i8(tm + 0 * kTileI, dgJ + adv, dgI + adv, idesc, acc);       // Q  : g_j . g_i
+                        umma_i8(tm + 1 * kTileI, dgJ + adv, dmI + adv, idesc, acc);       // P1 : g_j . M_i
+                        umma_i8(tm + 2 * kTileI, dmJ + adv, dgI + adv, idesc, acc);       // P2 : M_j . g_i
+                        umma_i8(tm + 3 * kTileI, dmJ + adv, dmI + adv, idesc, acc);       // N  : M_j . M_i
+                    }
+                    umma_commit(&empty_bar[s]);
+                }
+                umma_commit(&acc_full[as]);
+                ++lt;
+            }
         }
     } else {
-        e = cudaFuncSetAttribute(gram_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GramCfg<4>::kSmem);
-        if (e != cudaSuccess) return e;
-        gram_kernel<4><<<a.n_tiles, kGramThreads, GramCfg<4>::kSmem, st>>>(tmap, a);
+        const int q = warp & 3, half = (warp - 2) >> 2;              // TMEM lane quarter (columns j), half of the 64 rows
+        double4* rc = row_consts[warp - 2];
+        uint32_t lt = 0;
+        for (int tile_i = blockIdx.x; tile_i < a.n_tiles; tile_i += gridDim.x) {
+            const GramTile tile = a.tiles[tile_i];
+            if (a.flags[tile.blk] == 0) continue;
+            const BlockDesc bd = a.blocks[tile.blk];
+            const uint32_t my_lt = lt++;
+            const uint32_t as = my_lt & 1u;
+            const int jl = tile.tj * kTile + q * 32 + lane;          // Sigma column (block local)
+            const int i0 = tile.ti * kTileI + half * 32;             // first row of this warp's 32
+            double Sj = 0.0, Nj = 1.0, rj = 0.0;
+            if (jl < bd.m) { Sj = (double)a.rowS[bd.goff + jl]; Nj = (double)a.rowN[bd.goff + jl]; rj = a.rowR[bd.goff + jl]; }
+            __syncwarp();
+            {
+                const int il = i0 + lane;
+                double4 c = make_double4(0.0, 1.0, 0.0, 0.0);
+                if (il < bd.m) c = make_double4((double)a.rowS[bd.goff + il], (double)a.rowN[bd.goff + il], a.rowR[bd.goff + il], 0.0);
+                rc[lane] = c;
+            }
+            __syncwarp();
+            mbar_wait(&acc_full[as], (my_lt >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t tlane = tmem_base + as * 256 + half * 32 + ((uint32_t)(q * 32) << 16);
+            double* sig = a.sigma + bd.moff;
+            const size_t ld = (size_t)bd.ld;
+#pragma unroll 1
+            for (int c0 = 0; c0 < 32; c0 += 16) {
+                uint32_t v0[16], v1[16], v2[16], v3[16];
+                tmem_ld16(tlane + 0 * kTileI + c0, v0);
+                tmem_ld16(tlane + 1 * kTileI + c0, v1);
+                tmem_ld16(tlane + 2 * kTileI + c0, v2);
+                tmem_ld16(tlane + 3 * kTileI + c0, v3);
+                tmem_ld_wait();
+                if (c0 == 16) {
+                    // both chunks are in registers: the MMA issuer may reuse this accumulator set
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[as]);
+                }
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    const int il = i0 + c0 + r;
+                    const double4 rcv = rc[c0 + r];
+                    if (il >= bd.mp || jl > il) continue;
+                    double val;
+                    if (il < bd.m) {
+                        const double Si = rcv.x, Ni = rcv.y, ri = rcv.z;
+                        const double Q = (double)(int32_t)v0[r], P1 = (double)(int32_t)v1[r];
+                        const double P2 = (double)(int32_t)v2[r], Nn = (double)(int32_t)v3[r];
+                        // A_ij = sum g_i M_j = P2,  A_ji = sum g_j M_i = P1; every product is an exact integer < 2^53
+                        const double num = Ni * Nj * Q - Ni * Sj * P2 - Nj * Si * P1 + Si * Sj * Nn;
+                        val = num * ri * rj;
+                        if (il == jl) val += a.one_minus_tau;
+                    } else {
+                        val = (il == jl) ? 1.0 : 0.0;                 // identity padding rows m..mp-1
+                    }
+                    sig[(size_t)il * ld + jl] = val;
+                    if (a.full && jl < il) sig[(size_t)jl * ld + il] = val;
+                    if (a.intQ != nullptr && il < bd.m) {
+                        const size_t o = (size_t)bd.moff + (size_t)il * ld + jl, ot = (size_t)bd.moff + (size_t)jl * ld + il;
+                        a.intQ[o] = (int32_t)v0[r];
+                        a.intQ[ot] = (int32_t)v0[r];
+                        a.intA[o] = (int32_t)v2[r];
+                        a.intA[ot] = (int32_t)v1[r];
+                        a.intN[o] = (int32_t)v3[r];
+                        a.intN[ot] = (int32_t)v3[r];
+                    }
+                }
+            }
+        }
     }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// One-plane kernel over `a.tiles` (128 x 128 tiles; blocks whose flag is set are skipped).
+cudaError_t launch_gram(const CUtensorMap& tmap, const GramArgs& a, cudaStream_t st) {
+    if (a.n_tiles == 0) return cudaSuccess;
+    cudaError_t e;
+    int dev = 0, n_sm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (a.light) {
+        e = cudaFuncSetAttribute(gram_persistent_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg<3>::kSmem);
+        if (e != cudaSuccess) return e;
+        gram_persistent_kernel<3><<<std::min(a.n_tiles, n_sm), kPThreads, PCfg<3>::kSmem, st>>>(tmap, a);
+    } else {
+        e = cudaFuncSetAttribute(gram_persistent_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg<5>::kSmem);
+        if (e != cudaSuccess) return e;
+        gram_persistent_kernel<5><<<std::min(a.n_tiles, n_sm), kPThreads, PCfg<5>::kSmem, st>>>(tmap, a);
+    }
+    return cudaGetLastError();
+}
+
+// Four-plane kernel over `a.tiles` (64-row x 128-column tiles; blocks whose flag is clear are skipped, and the whole
+// launch returns at once when *a.any == 0).  tmapI: the same code array with a 64-row box.
+cudaError_t launch_gram_missing(const CUtensorMap& tmapJ, const CUtensorMap& tmapI, const GramArgs& a, cudaStream_t st) {
+    if (a.n_tiles == 0) return cudaSuccess;
+    int dev = 0, n_sm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e = cudaFuncSetAttribute(gram_missing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMSmem);
+    if (e != cudaSuccess) return e;
+    gram_missing_kernel<<<std::min(a.n_tiles, n_sm), kPThreads, kMSmem, st>>>(tmapJ, tmapI, a);
     return cudaGetLastError();
 }
 

@@ -10,15 +10,16 @@ namespace dbslmm {
 // decode.cu
 cudaError_t launch_snp_stats(const uint8_t* bed, int64_t n_snp, int32_t n_ref, SnpStat* stats, int n_sm,
                              cudaStream_t st);
+// SNP rows [g0, g0 + n_rows) of the plan: genotype code rows always, mask code rows where needed (see decode.cu)
 cudaError_t launch_decode_rows(const uint8_t* bed, int32_t n_ref, int32_t n_pad, const uint32_t* row_src,
-                               const int32_t* row_g, int64_t n_rows, const SnpStat* stats, double tau,
-                               int8_t* codes, int32_t* rowN, int32_t* rowS, double* rowR, int n_sm,
+                               const int32_t* row_crow, const int32_t* row_mrow, int64_t g0, int64_t n_rows, double tau,
+                               int8_t* codes, uint8_t* dirty, int32_t* rowN, int32_t* rowS, double* rowR, int n_sm,
                                cudaStream_t st);
-
 int32_t decode_max_n_ref();          // largest n_ref the row-staging kernels (decoder, statistics) can take
-cudaError_t launch_rows_missing(const int32_t* rowN, int64_t n_rows, int32_t n_ref, int32_t* flag, cudaStream_t st);
-cudaError_t launch_block_missing(const BlockDesc* blocks, int32_t n_blocks, const uint32_t* row_src,
-                                 const SnpStat* stats, int32_t n_ref, int32_t* flags, cudaStream_t st);
+// flags[b] = block b has missing calls (from the decoder's counts), for the blocks in `list` (nullptr: 0..n_list-1);
+// *any |= flags
+cudaError_t launch_block_flags(const BlockDesc* blocks, const int32_t* list, int32_t n_list, const int32_t* rowN,
+                               int32_t n_ref, int32_t* flags, int32_t* any, cudaStream_t st);
 
 // gram.cu
 struct GramArgs {
@@ -37,8 +38,11 @@ struct GramArgs {
     int32_t* intN;
     int32_t full;               // also write the upper triangle
     int32_t light;              // persistent kernel with a 3-stage ring (97 KB: co-resident with a Cholesky panel CTA)
+    const int32_t* flags;       // per block: has missing calls (device, written by block_flags_kernel)
+    const int32_t* any;         // some block of this launch has missing calls
 };
-cudaError_t launch_gram(const CUtensorMap& tmap, const GramArgs& a, bool missing, cudaStream_t st);
+cudaError_t launch_gram(const CUtensorMap& tmap, const GramArgs& a, cudaStream_t st);
+cudaError_t launch_gram_missing(const CUtensorMap& tmapJ, const CUtensorMap& tmapI, const GramArgs& a, cudaStream_t st);
 cudaError_t launch_gram_simt(const int8_t* codes, int32_t n_pad, int64_t row0, int32_t m, int32_t* q_out,
                              cudaStream_t st);
 cudaError_t launch_fill_z(const BlockDesc* blocks, const int32_t* list, int32_t n_blocks, const double* z, double* sigma,

@@ -68,6 +68,9 @@ typedef struct dbslmm_b200_timing {
     double decode_bytes; /* algorithmic bytes read + written by the decoder                                */
     double chol_ms;      /* factorisation kernels only (subset of solve_ms), summed over folds             */
     float class_ms[4];   /* last fold: fork -> end of each Cholesky size class (streams run concurrently)  */
+    int32_t streamed;    /* 1: the panel came with the call (fit_args.bed) and its upload overlapped the fit;
+                            0: the fit ran on a panel that was already complete on the device                 */
+    int32_t n_blocks_missing; /* blocks that had missing calls (four-plane Gram), decided on the device      */
 } dbslmm_b200_timing;
 
 typedef struct dbslmm_b200_fit_args {
@@ -168,9 +171,10 @@ DBSLMM_B200_API int  dbslmm_b200_score(dbslmm_b200_handle* h, const uint8_t* bed
                        const double* beta, int32_t n_folds, double* scores_out, float* kernel_ms_out);
 
 /* ---- inspection hooks used by the parity tests (operate on the state of the last fit) ---- */
-/* int8 codes of one decoded row of the last fit (row = global row index in block order:
- * block b's rows are its small SNPs then its large SNPs); n_pad bytes. */
-DBSLMM_B200_API int  dbslmm_b200_get_row_codes(dbslmm_b200_handle* h, int64_t row, int8_t* codes_out, int32_t n_out);
+/* int8 codes of one decoded row of the last fit: SNP j of block `block` (its small SNPs first, then its large ones),
+ * plane 0 = allele counts (missing -> 0), plane 1 = call mask (1 = called; holds the last mask written at that position,
+ * which is the current one whenever the block has missing calls); n_out <= n_pad bytes. */
+DBSLMM_B200_API int  dbslmm_b200_get_row_codes(dbslmm_b200_handle* h, int32_t block, int32_t j, int32_t plane, int8_t* codes_out, int32_t n_out);
 /* Sigma of block b as dense row-major m x m (m = m_s + m_l, small SNPs first).  Lower triangle is
  * always valid; the upper one only with FLAG_FULL_SIGMA / PCG solver (else mirrored on the host). */
 DBSLMM_B200_API int  dbslmm_b200_get_block_sigma(dbslmm_b200_handle* h, int32_t block, double* sigma_out);

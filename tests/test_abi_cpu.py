@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 def test_fit_args_struct_layout_matches_header():
     # natural alignment on LP64: the ctypes mirror must have the size of the C struct (17 + 7 + 3 + 1 fields)
     assert C.sizeof(_abi.FitArgs) == 216
-    assert C.sizeof(_abi.Timing) == 80
+    assert C.sizeof(_abi.Timing) == 88
 
 
 def test_no_cpu_fallback():

@@ -79,13 +79,58 @@ def test_streaming_subset_of_rows_and_unordered_blocks(engine):
     assert np.abs(maf - O.snp_maf(w["bed"], n_snp, 400)).max() <= 1e-15
 
 
-def test_streaming_with_missing_calls_falls_back(engine):
-    """The streaming plan assumes no missing calls; when the decoder meets one the fit is repeated on the resident copy."""
-    w = synth.make_workload(23, [150, 70, 5, 130, 0, 257], 403, missing_rate=0.02, frac_large=0.02)
+def test_streaming_with_missing_calls_does_not_fall_back(engine):
+    """Which blocks have missing calls is decided on the device (decoder counts -> per-block flag -> one- or four-plane
+    Gram), so a panel with missing calls streams like any other: no second pass on a resident copy."""
+    w = synth.make_workload(23, [150, 70, 5, 130, 0, 257, 90], 403, missing_rate=0.02, frac_large=0.02)
+    # one block without any missing call between blocks that have them (mixed one- / four-plane tiles in one launch)
+    G = w["G"].copy()
+    lo = int(np.sum(w["block_sizes"][:6])); hi = lo + 90
+    G[lo:hi] = np.where(G[lo:hi] < 0, 1, G[lo:hi])
+    bed = synth.pack_bed(G)
     csr = csr_of(w)
-    rs = engine.fit(*csr, sigma_s=[1e-4], n_obs=10_000, bed=w["bed"], n_ref=403)
-    bs, bl, _, _ = O.est(w["bed"], 403, 10_000, 1e-4, *csr, threads=4, mode=O.MODE_EXACT)
-    assert rs["n_bad"] == 0 and relmax(rs["beta_s"][0], bs) <= 1e-10 and relmax(rs["beta_l"][0], bl) <= 1e-10
+    bs, bl, _, _ = O.est(bed, 403, 10_000, 1e-4, *csr, threads=4, mode=O.MODE_EXACT)
+    for rep in range(2):
+        rs = engine.fit(*csr, sigma_s=[1e-4], n_obs=10_000, bed=bed, n_ref=403)
+        assert rs["timing"]["streamed"] == 1 and rs["timing"]["n_blocks_missing"] == 5
+        assert rs["n_bad"] == 0 and relmax(rs["beta_s"][0], bs) <= 1e-10 and relmax(rs["beta_l"][0], bl) <= 1e-10
+    # the same layout again with a panel WITHOUT missing calls: the mask rows written above must not leak into it
+    G0 = np.where(G < 0, 0, G)
+    bed0 = synth.pack_bed(G0)
+    b0, l0, _, _ = O.est(bed0, 403, 10_000, 1e-4, *csr, threads=4, mode=O.MODE_EXACT)
+    r0 = engine.fit(*csr, sigma_s=[1e-4], n_obs=10_000, bed=bed0, n_ref=403)
+    assert r0["timing"]["n_blocks_missing"] == 0 and relmax(r0["beta_s"][0], b0) <= 1e-10 and relmax(r0["beta_l"][0], l0) <= 1e-10
+    # and back: SNPs whose mask row went back to the default pattern sit next to SNPs with missing calls again
+    rs = engine.fit(*csr, sigma_s=[1e-4], n_obs=10_000, bed=bed, n_ref=403, flags=_abi.FLAG_KEEP_INT_GRAM)
+    assert relmax(rs["beta_s"][0], bs) <= 1e-10
+    pos0 = np.concatenate([w["s_pos"][w["s_off"][0]:w["s_off"][1]], w["l_pos"][w["l_off"][0]:w["l_off"][1]]]).astype(np.int32)
+    Q, A, N = engine.block_gram(0, pos0.size)
+    Qo, Ao, No = O.gram_int(bed, 403, pos0)
+    assert np.array_equal(Q, Qo) and np.array_equal(A, Ao) and np.array_equal(N, No)
+
+
+def test_streaming_failure_leaves_no_half_loaded_panel(engine):
+    """A streaming fit that fails (here: a SNP row outside the panel) must not leave a panel a later call could use."""
+    w = synth.make_workload(5, [60, 80], 400, frac_large=0.0)
+    bad = w["s_pos"].copy(); bad[-1] = 10_000_000
+    with pytest.raises(_abi.EngineError):
+        engine.fit(w["s_off"], bad, w["s_z"], sigma_s=[1e-4], n_obs=5000, bed=w["bed"], n_ref=400)
+    with pytest.raises(_abi.EngineError):
+        engine.fit(w["s_off"], w["s_pos"], w["s_z"], sigma_s=[1e-4], n_obs=5000)          # no panel: ERR_STATE
+    r = engine.fit(w["s_off"], w["s_pos"], w["s_z"], sigma_s=[1e-4], n_obs=5000, bed=w["bed"], n_ref=400)
+    b, _, _, _ = O.est(w["bed"], 400, 5000, 1e-4, w["s_off"], w["s_pos"], w["s_z"], threads=2, mode=O.MODE_EXACT)
+    assert relmax(r["beta_s"][0], b) <= 1e-10
+
+
+def test_plan_cache_flag_rebuilds_when_the_block_lists_change(engine):
+    """FLAG_PLAN_CACHED with the same totals but other SNP rows must not reuse the stale row map (fingerprint)."""
+    w = synth.make_workload(6, [120, 300], 400, frac_large=0.0)
+    engine.load_bed(w["bed"], 400)
+    engine.fit(w["s_off"], w["s_pos"], w["s_z"], sigma_s=[1e-4], n_obs=5000)
+    pos2 = w["s_pos"][::-1].copy()                                    # same counts, other rows per block
+    r2 = engine.fit(w["s_off"], pos2, w["s_z"], sigma_s=[1e-4], n_obs=5000, flags=_abi.FLAG_PLAN_CACHED)
+    b2, _, _, _ = O.est(w["bed"], 400, 5000, 1e-4, w["s_off"], pos2, w["s_z"], threads=2, mode=O.MODE_EXACT)
+    assert relmax(r2["beta_s"][0], b2) <= 1e-10
 
 
 def test_streaming_scattered_rows_use_plain_upload(engine):

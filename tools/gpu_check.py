@@ -43,10 +43,10 @@ def main():
                     continue
                 has_miss = bool((w["G"][pos_b] < 0).any())
                 for j in (0, m - 1):
-                    c = eng.row_codes(row + j, n_ref)
+                    c = eng.row_codes(b, j, n_ref)
                     okc &= np.array_equal(c, Gz[pos_b[j]])
                     if has_miss:
-                        mk = eng.row_codes(row + m + j, n_ref)
+                        mk = eng.row_codes(b, j, n_ref, plane=1)
                         okc &= np.array_equal(mk, (w["G"][pos_b[j]] >= 0).astype(np.int8))
                 Q, A, N = eng.block_gram(b, m)
                 Qo, Ao, No = O.gram_int(bed, n_ref, pos_b)
