@@ -445,9 +445,9 @@ def main():
         if dist is not None:
             dist.barrier()
 
-    def score(r):
+    def score(r, prefetched=False):
         beta = np.concatenate([r["beta_s"], r["beta_l"]], axis=1)
-        return eng.score(val["bed"], N_VAL, val["pos"], beta)
+        return eng.score(None if prefetched else val["bed"], N_VAL, val["pos"], beta)
 
     # ---- device-resident throughput (value)
     eng.load_bed(sh["bed"], n_ref)
@@ -481,16 +481,21 @@ def main():
     # ---- end to end from host buffers (e2e): ONE C-ABI call per step takes the pinned host .bed shard and the CSR
     # block lists and returns the betas on the host -- the shape of the reference's DBSLMMFIT::est(bed_str, info, ...).
     # Inside the call the panel upload is cut into batches (big blocks first) and overlaps decode/Gram/Cholesky.
-    for _ in range(min(args.warmup, 2)):
-        r2 = eng.fit(*csr, bed=sh["bed"], n_ref=n_ref, reuse_outputs=True, **fit_kw)
+    # (c4: the validation panel is announced before the fit, so its 2.75 GB upload queues behind the reference panel's and
+    # overlaps the fit's kernels; the scoring call then finds it on the device)
+    def e2e_step():
         if val:
-            score(r2)
+            eng.score_prefetch(val["bed"], N_VAL)
+        rr = eng.fit(*csr, bed=sh["bed"], n_ref=n_ref, reuse_outputs=True, **fit_kw)
+        if val:
+            score(rr, prefetched=True)
+        return rr
+    for _ in range(min(args.warmup, 2)):
+        r2 = e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        r2 = eng.fit(*csr, bed=sh["bed"], n_ref=n_ref, reuse_outputs=True, **fit_kw)
-        if val:
-            score(r2)
+        r2 = e2e_step()
     barrier()
     wall_e2e = time.perf_counter() - t0
     stream_vs_resident = relmax(r2["beta_s"], beta_s_timed)

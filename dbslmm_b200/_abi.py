@@ -21,7 +21,7 @@ FLAG_PANEL_SUBSET = 8
 EXPORTS = [
     "dbslmm_b200_abi_version", "dbslmm_b200_device_count", "dbslmm_b200_create", "dbslmm_b200_destroy",
     "dbslmm_b200_last_error", "dbslmm_b200_load_bed", "dbslmm_b200_snp_stats", "dbslmm_b200_plan_shards",
-    "dbslmm_b200_fit", "dbslmm_b200_host_alloc", "dbslmm_b200_host_free", "dbslmm_b200_score", "dbslmm_b200_get_row_codes", "dbslmm_b200_get_block_sigma",
+    "dbslmm_b200_fit", "dbslmm_b200_host_alloc", "dbslmm_b200_host_free", "dbslmm_b200_score", "dbslmm_b200_score_prefetch", "dbslmm_b200_get_row_codes", "dbslmm_b200_get_block_sigma",
     "dbslmm_b200_get_block_gram", "dbslmm_b200_get_block_iters",
 ]
 
@@ -78,6 +78,7 @@ def load():
         lib.dbslmm_b200_host_free.restype = None
         lib.dbslmm_b200_score.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,
                                           C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_float)]
+        lib.dbslmm_b200_score_prefetch.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32]
         lib.dbslmm_b200_get_row_codes.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]
         lib.dbslmm_b200_get_block_sigma.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         lib.dbslmm_b200_get_block_gram.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -224,17 +225,31 @@ class Engine:
         self._check(self.lib.dbslmm_b200_fit(self.h, C.byref(a)), "fit(quadform)")
         return out[:nb]
 
-    def score(self, bed_val, n_val, pos, beta, flip=None):
-        """PRS over a validation panel: returns (scores[n_folds, n_val], kernel_ms)."""
+    def score_prefetch(self, bed_val, n_val):
+        """Announce the validation panel of the next score(None, ...) call: uploaded in the shadow of the next fit."""
         bed_val = np.ascontiguousarray(bed_val, np.uint8)
         pitch = (n_val + 3) // 4
-        n_snp_val = bed_val.size // pitch
+        self._val_keep = bed_val                       # must outlive the next score call (see the C header)
+        self._check(self.lib.dbslmm_b200_score_prefetch(self.h, bed_val.ctypes.data, bed_val.size // pitch, int(n_val)), "score_prefetch")
+        self._val_n = int(n_val)
+
+    def score(self, bed_val, n_val, pos, beta, flip=None):
+        """PRS over a validation panel: returns (scores[n_folds, n_val], kernel_ms).  bed_val = None: the panel announced
+        by score_prefetch / left resident by the previous call."""
+        if bed_val is None:
+            n_val = self._val_n
+            bptr, n_snp_val = None, 0
+        else:
+            bed_val = np.ascontiguousarray(bed_val, np.uint8)
+            pitch = (n_val + 3) // 4
+            bptr, n_snp_val = bed_val.ctypes.data, bed_val.size // pitch
+            self._val_n = int(n_val)
         pos = np.ascontiguousarray(pos, np.int32)
         beta = np.ascontiguousarray(np.atleast_2d(beta), np.float64)
         fl = None if flip is None else np.ascontiguousarray(flip, np.uint8)
         out = np.zeros((beta.shape[0], n_val), np.float64)
         ms = C.c_float(0)
-        self._check(self.lib.dbslmm_b200_score(self.h, bed_val.ctypes.data, n_snp_val, n_val, pos.ctypes.data, _ptr(fl),
+        self._check(self.lib.dbslmm_b200_score(self.h, bptr, n_snp_val, n_val, pos.ctypes.data, _ptr(fl),
                                                pos.size, beta.ctypes.data, beta.shape[0], out.ctypes.data, C.byref(ms)), "score")
         return out, ms.value
 

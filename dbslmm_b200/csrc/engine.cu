@@ -151,6 +151,12 @@ struct dbslmm_b200_handle {
     int32_t n_ref = 0, pitch = 0, n_pad = 0;
     // workspace
     DevBuf codes, sigma, lbuf, rowN, rowS, rowR, planblob, beta, status, intQ, intA, intN, scratch, counters, wbuf, vbed, vstats, vwork, dflag, dirty, bflags;
+    // validation panel of the scoring step, announced by dbslmm_b200_score_prefetch: uploaded in the shadow of the next fit
+    const uint8_t* val_host = nullptr;
+    int64_t val_n_snp = 0;
+    int32_t val_n = 0;
+    bool val_announced = false, val_inflight = false;
+    cudaEvent_t ev_val = nullptr;
     size_t dirty_rows = 0;               // code rows the dirty map covers
     int32_t dirty_n_ref = 0;             // ... for this panel width (another width = another default mask pattern)
     const void* dirty_codes = nullptr;   // ... and this code buffer
@@ -705,6 +711,7 @@ int dbslmm_b200_create(int device, dbslmm_b200_handle** out) {
     for (int i = 0; i < 8 && ok; ++i) ok = cudaEventCreate(&h->ev[i]) == cudaSuccess;
     ok = ok && cudaEventCreate(&h->ev_fork) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->ev_bed, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->ev_val, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && chol_configure() == cudaSuccess;
     if (!ok) { dbslmm_b200_destroy(h); return DBSLMM_B200_ERR_CUDA; }
     *out = h;
@@ -722,6 +729,7 @@ void dbslmm_b200_destroy(dbslmm_b200_handle* h) {
     h->h_out.release();
     h->h_stats.release();
     if (h->ev_bed) cudaEventDestroy(h->ev_bed);
+    if (h->ev_val) cudaEventDestroy(h->ev_val);
     for (int i = 0; i < 8; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     for (int b = 0; b < kMaxBatches; ++b) {
@@ -924,6 +932,22 @@ int upload_issue(dbslmm_b200_handle* h, const Plan& P, UploadPlan& U, const uint
     return 0;
 }
 
+// Upload of an announced validation panel (+ its per-SNP statistics) on the upload stream: called by a fit right after
+// it has issued its own panel copies (so the big copy queues BEHIND them and overlaps the fit's kernels), or by score
+// itself when no fit came in between.
+int issue_val_upload(dbslmm_b200_handle* h) {
+    if (!h->val_announced) return DBSLMM_B200_OK;
+    const int32_t pitch = (h->val_n + 3) / 4;
+    const size_t bytes = (size_t)h->val_n_snp * pitch;
+    CU_TRY(h, cudaMemcpyAsync(h->vbed.p, h->val_host, bytes, cudaMemcpyHostToDevice, h->up_stream));
+    CU_TRY(h, cudaMemsetAsync((uint8_t*)h->vbed.p + bytes, 0xFF, 64, h->up_stream));
+    CU_TRY(h, launch_snp_stats((const uint8_t*)h->vbed.p, h->val_n_snp, h->val_n, (SnpStat*)h->vstats.p, h->n_sm, h->up_stream));
+    CU_TRY(h, cudaEventRecord(h->ev_val, h->up_stream));
+    h->val_announced = false;
+    h->val_inflight = true;
+    return DBSLMM_B200_OK;
+}
+
 // One fit.  streaming = the panel is uploaded inside this call from a->bed, batch by batch (see Batch); otherwise the
 // panel loaded by load_bed is used.  Returns n_bad >= 0 or an error < 0.
 
@@ -1079,6 +1103,7 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
         CU_TRY(h, cudaMemcpyAsync(dblob + P.o_z, (uint8_t*)h->h_blob.p + P.o_z, sizeof(double) * (size_t)P.n_snp_rows,
                                   cudaMemcpyHostToDevice, st));
     }
+    { int rc = issue_val_upload(h); if (rc != DBSLMM_B200_OK) return rc; }     // an announced validation panel follows the fit's own copies
     CU_TRY(h, cudaMemsetAsync(d_status, 0, sizeof(int32_t) * (size_t)std::max(2 * nb, 1), st));
     CU_TRY(h, cudaMemsetAsync(d_any, 0, sizeof(int32_t) * (size_t)(kMaxBatches + 1), st));
     CU_TRY(h, cudaEventRecord(h->ev[1], st));
@@ -1521,11 +1546,33 @@ void dbslmm_b200_host_free(dbslmm_b200_handle* h, void* p) {
     cudaFreeHost(p);
 }
 
+int dbslmm_b200_score_prefetch(dbslmm_b200_handle* h, const uint8_t* bed_val, int64_t n_snp_val, int32_t n_val) {
+    if (!h) return DBSLMM_B200_ERR_ARG;
+    if (!bed_val || n_snp_val <= 0 || n_val <= 0) return fail(h, DBSLMM_B200_ERR_ARG, "score_prefetch: bad arguments");
+    CU_TRY(h, cudaSetDevice(h->device));
+    if (h->val_inflight) { CU_TRY(h, cudaEventSynchronize(h->ev_val)); h->val_inflight = false; }
+    const size_t bytes = (size_t)n_snp_val * ((n_val + 3) / 4);
+    CU_TRY(h, h->vbed.ensure(bytes + 64));
+    CU_TRY(h, h->vstats.ensure(sizeof(SnpStat) * (size_t)n_snp_val));
+    h->val_host = bed_val;
+    h->val_n_snp = n_snp_val;
+    h->val_n = n_val;
+    h->val_announced = true;
+    return DBSLMM_B200_OK;
+}
+
 int dbslmm_b200_score(dbslmm_b200_handle* h, const uint8_t* bed_val, int64_t n_snp_val, int32_t n_val,
                       const int32_t* pos, const uint8_t* flip, int64_t n_scored, const double* beta,
                       int32_t n_folds, double* scores_out, float* kernel_ms_out) {
     if (!h) return DBSLMM_B200_ERR_ARG;
-    if (!bed_val || n_snp_val <= 0 || n_val <= 0 || n_scored < 0 || n_folds < 1 || !scores_out || (n_scored > 0 && (!pos || !beta)))
+    // bed_val == NULL: the panel announced by score_prefetch (or left resident by the previous score call)
+    const bool prefetched = bed_val == nullptr;
+    if (prefetched) {
+        if (!h->val_announced && !h->val_inflight && h->val_n_snp == 0) return fail(h, DBSLMM_B200_ERR_STATE, "score: no validation panel (bed_val == NULL without score_prefetch)");
+        n_snp_val = h->val_n_snp;
+        n_val = h->val_n;
+    }
+    if (n_snp_val <= 0 || n_val <= 0 || n_scored < 0 || n_folds < 1 || !scores_out || (n_scored > 0 && (!pos || !beta)))
         return fail(h, DBSLMM_B200_ERR_ARG, "score: bad arguments");
     if (n_scored > INT32_MAX) return fail(h, DBSLMM_B200_ERR_ARG, "score: too many SNPs");
     for (int64_t j = 0; j < n_scored; ++j)
@@ -1534,7 +1581,7 @@ int dbslmm_b200_score(dbslmm_b200_handle* h, const uint8_t* bed_val, int64_t n_s
     cudaStream_t st = h->stream;
     const int32_t pitch = (n_val + 3) / 4;
     const size_t bytes = (size_t)n_snp_val * pitch;
-    const int n_chunks = std::max(1, std::min<int>(4 * h->n_sm / std::max(1, (pitch + 255) / 256), (int)((n_scored + 63) / 64)));
+    const int n_chunks = std::max(1, std::min<int>(4 * h->n_sm / std::max(1, ((pitch + 3) / 4 + 255) / 256), (int)((n_scored + 63) / 64)));
     const int nf_pass = std::min(n_folds, 4);
     // work buffer: pos | flip | beta | partial | scores
     size_t o = 0;
@@ -1543,18 +1590,29 @@ int dbslmm_b200_score(dbslmm_b200_handle* h, const uint8_t* bed_val, int64_t n_s
                  o_beta = place(sizeof(double) * (size_t)n_scored * n_folds),
                  o_part = place(sizeof(double) * (size_t)n_chunks * nf_pass * n_val),
                  o_sc = place(sizeof(double) * (size_t)n_folds * n_val);
-    CU_TRY(h, h->vbed.ensure(bytes + 64));
-    CU_TRY(h, h->vstats.ensure(sizeof(SnpStat) * (size_t)n_snp_val));
+    if (!prefetched) {
+        if (h->val_inflight) { CU_TRY(h, cudaEventSynchronize(h->ev_val)); h->val_inflight = false; }
+        h->val_announced = false;
+        CU_TRY(h, h->vbed.ensure(bytes + 64));
+        CU_TRY(h, h->vstats.ensure(sizeof(SnpStat) * (size_t)n_snp_val));
+    }
     CU_TRY(h, h->vwork.ensure(o));
     uint8_t* w = (uint8_t*)h->vwork.p;
-    CU_TRY(h, cudaMemcpyAsync(h->vbed.p, bed_val, bytes, cudaMemcpyHostToDevice, st));
-    CU_TRY(h, cudaMemsetAsync((uint8_t*)h->vbed.p + bytes, 0xFF, 64, st));
+    if (!prefetched) {
+        CU_TRY(h, cudaMemcpyAsync(h->vbed.p, bed_val, bytes, cudaMemcpyHostToDevice, st));
+        CU_TRY(h, cudaMemsetAsync((uint8_t*)h->vbed.p + bytes, 0xFF, 64, st));
+        h->val_n_snp = n_snp_val;
+        h->val_n = n_val;
+    } else {
+        if (h->val_announced) { int rc = issue_val_upload(h); if (rc != DBSLMM_B200_OK) return rc; }   // no fit came in between
+        if (h->val_inflight) CU_TRY(h, cudaStreamWaitEvent(st, h->ev_val, 0));
+    }
     if (n_scored) {
         CU_TRY(h, cudaMemcpyAsync(w + o_pos, pos, sizeof(int32_t) * (size_t)n_scored, cudaMemcpyHostToDevice, st));
         if (flip) CU_TRY(h, cudaMemcpyAsync(w + o_flip, flip, (size_t)n_scored, cudaMemcpyHostToDevice, st));
         CU_TRY(h, cudaMemcpyAsync(w + o_beta, beta, sizeof(double) * (size_t)n_scored * n_folds, cudaMemcpyHostToDevice, st));
     }
-    CU_TRY(h, launch_snp_stats((const uint8_t*)h->vbed.p, n_snp_val, n_val, (SnpStat*)h->vstats.p, h->n_sm, st));
+    if (!prefetched) CU_TRY(h, launch_snp_stats((const uint8_t*)h->vbed.p, n_snp_val, n_val, (SnpStat*)h->vstats.p, h->n_sm, st));
     CU_TRY(h, cudaMemsetAsync(w + o_sc, 0, sizeof(double) * (size_t)n_folds * n_val, st));
     CU_TRY(h, cudaEventRecord(h->ev[0], st));
     for (int f0 = 0; f0 < n_folds; f0 += 4) {
@@ -1567,6 +1625,7 @@ int dbslmm_b200_score(dbslmm_b200_handle* h, const uint8_t* bed_val, int64_t n_s
     CU_TRY(h, cudaEventRecord(h->ev[1], st));
     CU_TRY(h, cudaMemcpyAsync(scores_out, w + o_sc, sizeof(double) * (size_t)n_folds * n_val, cudaMemcpyDeviceToHost, st));
     CU_TRY(h, cudaStreamSynchronize(st));
+    h->val_inflight = false;                 // (the stream waited for its event)
     if (kernel_ms_out) cudaEventElapsedTime(kernel_ms_out, h->ev[0], h->ev[1]);
     return DBSLMM_B200_OK;
 }

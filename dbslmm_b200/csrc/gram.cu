@@ -267,7 +267,10 @@ gram_missing_kernel(const __grid_constant__ CUtensorMap tmapJ, const __grid_cons
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = make_i8_idesc(kTile, kTileI);
+            // The I-side genotype rows and mask rows of a stage are adjacent in shared memory (2 x 64 rows), so ONE
+            // B descriptor with N = 128 covers both: g_j . [g_i | M_i] fills the Q and P1 planes in one instruction,
+            // M_j . [g_i | M_i] the P2 and N planes -- two MMAs per K step instead of four, a third less operand traffic.
+            constexpr uint32_t idesc = make_i8_idesc(kTile, 2 * kTileI);
             uint32_t it = 0, lt = 0;
             for (int tile_i = blockIdx.x; tile_i < a.n_tiles; tile_i += gridDim.x) {
                 const GramTile tile = a.tiles[tile_i];
@@ -282,16 +285,13 @@ gram_missing_kernel(const __grid_constant__ CUtensorMap tmapJ, const __grid_cons
                     tc_fence_after();
                     const uint32_t st = smem_u32(smem + (size_t)s * kMStageBytes);
                     const uint64_t dgJ = make_sw128_kmajor_desc(st), dmJ = make_sw128_kmajor_desc(st + kTileBytes);
-                    const uint64_t dgI = make_sw128_kmajor_desc(st + 2 * kTileBytes);
-                    const uint64_t dmI = make_sw128_kmajor_desc(st + 2 * kTileBytes + kTileBytes / 2);
+                    const uint64_t dI = make_sw128_kmajor_desc(st + 2 * kTileBytes);      // [g_i (64 rows) | M_i (64 rows)]
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {
                         const uint32_t acc = (ks > 0 || kk > 0) ? 1u : 0u;
                         const uint64_t adv = (uint64_t)(kk * 2);   // +32 bytes inside the 128 B swizzle atom
-                        umma_i8(tm + 0 * kTileI, dgJ + adv, dgI + adv, idesc, acc);       // Q  : g_j . g_i
-                        umma_i8(tm + 1 * kTileI, dgJ + adv, dmI + adv, idesc, acc);       // P1 : g_j . M_i
-                        umma_i8(tm + 2 * kTileI, dmJ + adv, dgI + adv, idesc, acc);       // P2 : M_j . g_i
-                        umma_i8(tm + 3 * kTileI, dmJ + adv, dmI + adv, idesc, acc);       // N  : M_j . M_i
+                        umma_i8(tm + 0 * kTileI, dgJ + adv, dI + adv, idesc, acc);        // Q | P1 : g_j . [g_i | M_i]
+                        umma_i8(tm + 2 * kTileI, dmJ + adv, dI + adv, idesc, acc);        // P2 | N : M_j . [g_i | M_i]
                     }
                     umma_commit(&empty_bar[s]);
                 }

@@ -7,8 +7,9 @@
 // PLINK is external to the reference, so this path's parity is pinned only against a numpy
 // restatement of those documented semantics (tests/test_gpu_score.py).
 //
-// HBM-bound by design: every .bed byte is read once (coalesced, 1 byte = 4 individuals per thread),
-// per-chunk partial sums are written to a scratch buffer and reduced in a fixed order (deterministic).
+// Every .bed byte is read once (coalesced, 4 bytes = 16 individuals per thread); per-chunk partial sums are written to
+// a scratch buffer and reduced in a fixed order (deterministic).  The work is one FP64 multiply-add per genotype and
+// fold (3.3e10 at config 4), so the FP64 pipe, not HBM, bounds it.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -17,23 +18,28 @@ namespace dbslmm {
 static constexpr int kScoreThreads = 256;
 static constexpr int kMaxFolds = 4;          // folds per pass (more folds => several passes)
 
+// One thread = FOUR consecutive .bed bytes = 16 individuals (a warp reads 128 contiguous bytes of a row per load), 64
+// scored SNPs per shared-memory batch.  Per SNP the four possible dosages {code 0, 1 = missing -> mean, 2, 3} are put
+// in shared memory once (allele flip and mean imputation folded in), so the inner loop is: extract the 2-bit code,
+// pick one of four doubles (two selects on a value held in registers), NF fused multiply-adds.
 template <int NF>
 __global__ void __launch_bounds__(kScoreThreads)
 prs_partial_kernel(const uint8_t* __restrict__ bed, int32_t pitch, int32_t n_val, const SnpStat* __restrict__ stats,
                    const int32_t* __restrict__ pos, const uint8_t* __restrict__ flip, const double* __restrict__ beta,
                    int64_t beta_stride, int32_t n_scored, int32_t rows_per_chunk, double* __restrict__ partial) {
     __shared__ double s_beta[64][NF];
-    __shared__ double s_mu[64];
+    __shared__ __align__(16) double s_dos[64][4];            // dosage of code 0, 1, 2, 3
     __shared__ int32_t s_row[64];
-    __shared__ uint8_t s_flip[64];
     const int tid = threadIdx.x;
-    const int byte_col = blockIdx.x * kScoreThreads + tid;
-    const bool in_range = byte_col < pitch;
+    const int word_col = blockIdx.x * kScoreThreads + tid;   // 4-byte column of the row
+    const int byte0 = word_col * 4;
+    const bool in_range = byte0 < pitch;
+    const bool full_word = byte0 + 4 <= pitch && (pitch & 3) == 0;     // rows stay 4-byte aligned only if the pitch is
     const int s_begin = blockIdx.y * rows_per_chunk;
     const int s_end = min(n_scored, s_begin + rows_per_chunk);
-    double acc[4][NF];
+    double acc[16][NF];
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
+    for (int q = 0; q < 16; ++q)
 #pragma unroll
         for (int f = 0; f < NF; ++f) acc[q][f] = 0.0;
     for (int s0 = s_begin; s0 < s_end; s0 += 64) {
@@ -45,33 +51,47 @@ prs_partial_kernel(const uint8_t* __restrict__ bed, int32_t pitch, int32_t n_val
             const bool fl = flip != nullptr && flip[s0 + tid] != 0;
             const double mu = (double)st.sum / (double)st.n_nonmiss;        // mean A1 dosage of called genotypes
             s_row[tid] = row;
-            s_flip[tid] = fl ? 1 : 0;
-            s_mu[tid] = fl ? 2.0 - mu : mu;
+            // A1 copies: code 0 -> 2, 2 -> 1, 3 -> 0, 1 -> missing (dtpr.cpp:329-350)
+            s_dos[tid][0] = fl ? 0.0 : 2.0;
+            s_dos[tid][1] = fl ? 2.0 - mu : mu;
+            s_dos[tid][2] = 1.0;
+            s_dos[tid][3] = fl ? 2.0 : 0.0;
 #pragma unroll
             for (int f = 0; f < NF; ++f) s_beta[tid][f] = beta[(int64_t)f * beta_stride + s0 + tid];
         }
         __syncthreads();
         if (!in_range) continue;
-        uint8_t bytes[8];
-        for (int j0 = 0; j0 < nb; j0 += 8) {
+        uint32_t words[4];
+        for (int j0 = 0; j0 < nb; j0 += 4) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u)
-                bytes[u] = (j0 + u < nb) ? bed[(size_t)s_row[j0 + u] * pitch + byte_col] : (uint8_t)0xFF;
+            for (int u = 0; u < 4; ++u) {
+                uint32_t w = 0xFFFFFFFFu;
+                if (j0 + u < nb) {
+                    const uint8_t* p = bed + (size_t)s_row[j0 + u] * pitch + byte0;
+                    if (full_word) w = *reinterpret_cast<const uint32_t*>(p);
+                    else {
+                        w = 0;
+                        for (int bq = 0; bq < 4; ++bq) w |= (uint32_t)((byte0 + bq < pitch) ? p[bq] : 0xFF) << (8 * bq);
+                    }
+                }
+                words[u] = w;
+            }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+            for (int u = 0; u < 4; ++u) {
                 if (j0 + u >= nb) break;
-                const unsigned b = bytes[u];
-                const bool fl = s_flip[j0 + u] != 0;
-                const double mu = s_mu[j0 + u];
+                const uint32_t w = words[u];
+                const double2 d01 = *reinterpret_cast<const double2*>(&s_dos[j0 + u][0]);
+                const double2 d23 = *reinterpret_cast<const double2*>(&s_dos[j0 + u][2]);
+                double bf[NF];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const unsigned c = (b >> (2 * q)) & 3u;
-                    // A1 copies: code 0 -> 2, 2 -> 1, 3 -> 0, 1 -> missing (dtpr.cpp:329-350)
-                    double d = (c == 0u) ? 2.0 : (c == 2u) ? 1.0 : 0.0;
-                    if (fl) d = 2.0 - d;
-                    if (c == 1u) d = mu;
+                for (int f = 0; f < NF; ++f) bf[f] = s_beta[j0 + u][f];
 #pragma unroll
-                    for (int f = 0; f < NF; ++f) acc[q][f] += s_beta[j0 + u][f] * d;
+                for (int q = 0; q < 16; ++q) {
+                    const uint32_t c = (w >> (2 * q)) & 3u;
+                    const double lo = (c & 1u) ? d01.y : d01.x, hi = (c & 1u) ? d23.y : d23.x;
+                    const double d = (c & 2u) ? hi : lo;
+#pragma unroll
+                    for (int f = 0; f < NF; ++f) acc[q][f] = fma(bf[f], d, acc[q][f]);
                 }
             }
         }
@@ -80,8 +100,8 @@ prs_partial_kernel(const uint8_t* __restrict__ bed, int32_t pitch, int32_t n_val
 #pragma unroll
     for (int f = 0; f < NF; ++f)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int ind = byte_col * 4 + q;
+        for (int q = 0; q < 16; ++q) {
+            const int ind = byte0 * 4 + q;
             if (ind < n_val) partial[((size_t)blockIdx.y * NF + f) * n_val + ind] = acc[q][f];
         }
 }
@@ -102,7 +122,7 @@ cudaError_t launch_prs(const uint8_t* bed, int32_t n_val, const SnpStat* stats, 
     if (n_scored == 0 || nf == 0) return cudaSuccess;
     const int32_t pitch = (n_val + 3) / 4;
     const int rows_per_chunk = (n_scored + n_chunks - 1) / n_chunks;
-    dim3 grid((pitch + kScoreThreads - 1) / kScoreThreads, n_chunks);
+    dim3 grid(((pitch + 3) / 4 + kScoreThreads - 1) / kScoreThreads, n_chunks);
     switch (nf) {
         case 1: prs_partial_kernel<1><<<grid, kScoreThreads, 0, st>>>(bed, pitch, n_val, stats, pos, flip, beta, beta_stride, n_scored, rows_per_chunk, partial); break;
         case 2: prs_partial_kernel<2><<<grid, kScoreThreads, 0, st>>>(bed, pitch, n_val, stats, pos, flip, beta, beta_stride, n_scored, rows_per_chunk, partial); break;

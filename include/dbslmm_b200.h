@@ -165,7 +165,12 @@ DBSLMM_B200_API void dbslmm_b200_host_free(dbslmm_b200_handle* h, void* p);
  * dosage = copies of A1 (or of A2 where flip[j] != 0) of validation .bed row pos[j], missing calls
  * mean-imputed.  `bed_val` is a host SNP-major .bed payload (after the magic bytes) of n_snp_val rows and
  * n_val individuals; it is uploaded, scored for all n_folds in one pass and left resident until the next
- * call.  flip may be NULL.  scores_out is [n_folds][n_val]. */
+ * call (bed_val = NULL: score the panel that is already there -- announced by dbslmm_b200_score_prefetch or left by the
+ * previous call; n_snp_val / n_val are then ignored).  flip may be NULL.  scores_out is [n_folds][n_val]. */
+/* Announce the validation panel of the NEXT dbslmm_b200_score call: its upload (2.75 GB at config 4) is queued behind the
+ * panel copies of the next dbslmm_b200_fit on this handle and overlaps that fit's kernels; score is then called with
+ * bed_val = NULL.  `bed_val` (pinned for full speed) must stay valid until that score call has returned. */
+DBSLMM_B200_API int  dbslmm_b200_score_prefetch(dbslmm_b200_handle* h, const uint8_t* bed_val, int64_t n_snp_val, int32_t n_val);
 DBSLMM_B200_API int  dbslmm_b200_score(dbslmm_b200_handle* h, const uint8_t* bed_val, int64_t n_snp_val, int32_t n_val,
                        const int32_t* pos, const uint8_t* flip, int64_t n_scored,
                        const double* beta, int32_t n_folds, double* scores_out, float* kernel_ms_out);

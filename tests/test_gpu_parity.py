@@ -5,8 +5,8 @@ Bars (DESIGN.md "Parity"):
   maf ........................................................ <= 1e-15 abs (one FP64 division)
   Sigma ...................................................... <= 1e-13 abs vs the reference float path
   beta, Cholesky solver vs `exact` oracle .................... <= 1e-10 of max|beta| per call
-  beta vs the UNMODIFIED reference's golden vectors .......... <= 2e-7 of max|beta|: the reference stops PCG at an
-       absolute residual of 1e-7, so ITS answer carries a few 1e-8 of truncation error (tests/test_oracle.py)
+  beta vs the UNMODIFIED reference's golden vectors .......... <= 2 x the gap measured per fixture (tests/parity_bars.py):
+       the reference stops PCG at an absolute residual of 1e-7, so ITS answer carries up to a few 1e-8 of truncation error
 """
 import os
 
@@ -15,6 +15,7 @@ import pytest
 
 from dbslmm_b200 import _abi, synth
 from oracle import oracle as O
+from parity_bars import bar, record
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
@@ -135,9 +136,12 @@ def test_golden_c1_testdat(engine):
     assert np.abs(maf - d["ref_maf"]).max() <= 1e-15
     r = engine.fit(d["lmm_off"], d["lmm_pos"], d["lmm_z"], sigma_s=[sig], n_obs=n_obs)
     assert r["n_bad"] == 0
-    assert relmax(r["beta_s"][0], d["lmm_beta"]) <= 2e-8            # measured reference truncation gap: 3e-9
+    g = relmax(r["beta_s"][0], d["lmm_beta"]); record("gpu_chol_vs_reference/c1_testdat/lmm_beta", g)
+    assert g <= bar("c1_testdat", "lmm_beta")                       # the reference's own truncation gap
     r = engine.fit(d["s_off"], d["s_pos"], d["s_z"], d["l_off"], d["l_pos"], d["l_z"], sigma_s=[sig], n_obs=n_obs)
-    assert relmax(r["beta_s"][0], d["beta_s"]) <= 2e-7 and relmax(r["beta_l"][0], d["beta_l"]) <= 2e-7
+    gs, gl = relmax(r["beta_s"][0], d["beta_s"]), relmax(r["beta_l"][0], d["beta_l"])
+    record("gpu_chol_vs_reference/c1_testdat/beta_s", gs); record("gpu_chol_vs_reference/c1_testdat/beta_l", gl)
+    assert gs <= bar("c1_testdat", "beta_s") and gl <= bar("c1_testdat", "beta_l")
     bs, bl, _, _ = O.est(d["bed"], n_ref, n_obs, sig, d["s_off"], d["s_pos"], d["s_z"], d["l_off"], d["l_pos"], d["l_z"],
                          mode=O.MODE_EXACT)
     assert relmax(r["beta_s"][0], bs) <= 1e-10 and relmax(r["beta_l"][0], bl) <= 1e-10
@@ -149,7 +153,9 @@ def test_golden_synth_ragged(engine):
     engine.load_bed(d["bed"], n_ref)
     r = engine.fit(d["s_off"], d["s_pos"], d["s_z"], d["l_off"], d["l_pos"], d["l_z"], sigma_s=[sig], n_obs=n_obs)
     assert r["n_bad"] == 0
-    assert relmax(r["beta_s"][0], d["beta_s"]) <= 2e-7 and relmax(r["beta_l"][0], d["beta_l"]) <= 2e-7
+    gs, gl = relmax(r["beta_s"][0], d["beta_s"]), relmax(r["beta_l"][0], d["beta_l"])
+    record("gpu_chol_vs_reference/synth_ragged/beta_s", gs); record("gpu_chol_vs_reference/synth_ragged/beta_l", gl)
+    assert gs <= bar("synth_ragged", "beta_s") and gl <= bar("synth_ragged", "beta_l")
 
 
 def test_monomorphic_snp_poisons_only_its_block(engine):
@@ -194,6 +200,26 @@ def test_full_size_properties(engine):
         x = r["beta_s"][0][lo:hi] * np.sqrt(n_obs)
         res = np.abs(K @ x - z[lo:hi]).max() / np.abs(z[lo:hi]).max()
         assert res < 1e-11, res
+
+
+def test_baseline_size_block_vs_exact_oracle(engine):
+    """A BASELINE-sized block (m = 3,000 SNPs, n_ref = 2,000: 47 panels, split-K steps, cluster back substitution) in DBSLMM
+    mode, compared DIRECTLY with the exact oracle -- a wrong Sigma cannot hide here the way it could behind a residual
+    computed from the library's own Sigma.  Genome-wide ridge (nsnp = 1.1 M, N = 300,000)."""
+    w = synth.make_workload(3000, [3000], 2000, missing_rate=0.0, frac_large=0.003)
+    assert w["l_pos"].size >= 3
+    engine.load_bed(w["bed"], 2000)
+    csr = (w["s_off"], w["s_pos"], w["s_z"], w["l_off"], w["l_pos"], w["l_z"])
+    sig, n_obs = 0.5 / 1.1e6, 300_000
+    r = engine.fit(*csr, sigma_s=[sig], n_obs=n_obs)
+    assert r["n_bad"] == 0
+    bs, bl, sing, _ = O.est(w["bed"], 2000, n_obs, sig, *csr, threads=1, mode=O.MODE_EXACT)
+    assert sing == 0
+    gs, gl = relmax(r["beta_s"][0], bs), relmax(r["beta_l"][0], bl)
+    record("gpu_chol_vs_exact_oracle/m3000_n2000_dbslmm/beta_s", gs); record("gpu_chol_vs_exact_oracle/m3000_n2000_dbslmm/beta_l", gl)
+    assert gs <= 1e-10 and gl <= 1e-10
+    rs = engine.fit(*csr, sigma_s=[sig], n_obs=n_obs, bed=w["bed"], n_ref=2000)            # and through the streaming path
+    assert relmax(rs["beta_s"][0], bs) <= 1e-10 and relmax(rs["beta_l"][0], bl) <= 1e-10
 
 
 def test_config5_large_reference_panel(engine):
@@ -270,7 +296,12 @@ def test_pcg_solver_matches_ref_mode_oracle(engine):
     assert r["n_bad"] == 0
     bs, bl, sing, it = O.est(w["bed"], 400, n_obs, sig, *csr, threads=4, mode=O.MODE_REF)
     assert sing == 0
-    assert relmax(r["beta_s"][0], bs) <= 2e-7 and relmax(r["beta_l"][0], bl) <= 2e-7
+    # two faithful PCG implementations (this kernel, the ref-mode oracle): same algorithm, other summation order; the
+    # iteration count may flip by one at the 1e-7 threshold, which moves a solve by up to ~1e-7 / lambda_min(A) = 5e-7 of
+    # |u|; measured here 1e-9 .. 3e-8
+    gs, gl = relmax(r["beta_s"][0], bs), relmax(r["beta_l"][0], bl)
+    record("gpu_pcg_vs_ref_oracle/synth321/beta_s", gs); record("gpu_pcg_vs_ref_oracle/synth321/beta_l", gl)
+    assert gs <= 1e-7 and gl <= 1e-7
     its = [engine.block_iters(b) for b in range(5)]
     assert abs(max(its) - it) <= 1 and its[1] == 0
     # and it differs from the exact solve by the reference's own truncation error, not by more
@@ -283,8 +314,11 @@ def test_pcg_solver_golden_c1(engine):
     n_ref, n_obs, sig = int(d["n_ref"]), int(d["n_obs"]), float(d["sigma_s"])
     engine.load_bed(d["bed"], n_ref)
     r = engine.fit(d["lmm_off"], d["lmm_pos"], d["lmm_z"], sigma_s=[sig], n_obs=n_obs, solver=_abi.SOLVER_PCG)
-    assert relmax(r["beta_s"][0], d["lmm_beta"]) <= 2e-8           # same iteration count as the reference: ~1e-10
+    g = relmax(r["beta_s"][0], d["lmm_beta"]); record("gpu_pcg_vs_reference/c1_testdat/lmm_beta", g)
+    assert g <= 5e-9                                                # same iteration count as the reference: ~1e-10 expected
     assert 40 <= engine.block_iters(0) <= 50                        # the reference takes 45-46 iterations here
     r = engine.fit(d["s_off"], d["s_pos"], d["s_z"], d["l_off"], d["l_pos"], d["l_z"], sigma_s=[sig], n_obs=n_obs,
                    solver=_abi.SOLVER_PCG)
-    assert relmax(r["beta_s"][0], d["beta_s"]) <= 2e-7 and relmax(r["beta_l"][0], d["beta_l"]) <= 2e-7
+    gs, gl = relmax(r["beta_s"][0], d["beta_s"]), relmax(r["beta_l"][0], d["beta_l"])
+    record("gpu_pcg_vs_reference/c1_testdat/beta_s", gs); record("gpu_pcg_vs_reference/c1_testdat/beta_l", gl)
+    assert gs <= 1e-7 and gl <= 1e-7                                # measured (ref-mode oracle vs golden): 1.8e-8 / 1.2e-8

@@ -58,6 +58,27 @@ def test_prs_linearity_and_folds_after_fit(engine):
     assert np.abs(s2[0] - (2.0 * s[0] - s[2])).max() <= 1e-12 * np.abs(s).max()      # linear in beta
 
 
+def test_prs_prefetched_panel_overlaps_a_fit(engine):
+    """score_prefetch announces the validation panel; the next fit issues its upload behind its own panel copies; score(None)
+    then finds it on the device.  Same scores as the direct call; a second score(None) reuses the resident panel."""
+    w = synth.make_workload(405, [120, 60], 400, frac_large=0.0)
+    rng = np.random.default_rng(6)
+    Gv = synth.make_genotypes(rng, [180], 1500, missing_rate=0.01)
+    bedv = synth.pack_bed(Gv)
+    pos = np.arange(180, dtype=np.int32)
+    engine.score_prefetch(bedv, 1500)
+    r = engine.fit(w["s_off"], w["s_pos"], w["s_z"], sigma_s=[1e-3, 2e-3], n_obs=20000, bed=w["bed"], n_ref=400)
+    beta = np.zeros((2, 180)); beta[:, w["s_pos"]] = r["beta_s"]
+    s1, _ = engine.score(None, 1500, pos, beta)
+    exp = plink_score_sum(Gv, beta)
+    assert np.abs(s1 - exp).max() <= 1e-12 * np.abs(exp).max()
+    s2, _ = engine.score(None, 1500, pos, beta[:1])
+    assert np.abs(s2[0] - exp[0]).max() <= 1e-12 * np.abs(exp).max()
+    engine.score_prefetch(bedv, 1500)                           # announced, but no fit in between: score uploads it itself
+    s3, _ = engine.score(None, 1500, pos, beta)
+    assert np.array_equal(s3, s1)
+
+
 def test_prs_argument_errors(engine):
     from dbslmm_b200 import _abi
     G = synth.make_genotypes(np.random.default_rng(1), [20], 100)

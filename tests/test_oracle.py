@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle as O
+from parity_bars import bar
 from oracle import refharness as R
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
@@ -98,7 +99,7 @@ def test_oracle_ref_mode_matches_reference_golden_c1(c1):
     # (m_l + 2) chained PCG solves: two faithful PCG implementations differ by the CG recurrence's sensitivity
     # to summation order near the 1e-7 stopping threshold (iteration counts flip by one on some columns),
     # so agreement here is bounded by the truncation error itself, not by rounding.
-    assert relmax(bs, c1["beta_s"]) < 2e-7 and relmax(bl, c1["beta_l"]) < 2e-7
+    assert relmax(bs, c1["beta_s"]) <= bar("c1_testdat", "beta_s", "pcg") and relmax(bl, c1["beta_l"]) <= bar("c1_testdat", "beta_l", "pcg")
 
 
 def test_oracle_ref_mode_matches_reference_golden_ragged(ragged):
@@ -107,7 +108,7 @@ def test_oracle_ref_mode_matches_reference_golden_ragged(ragged):
     bs, bl, sing, _ = O.est(d["bed"], n_ref, n_obs, sig, d["s_off"], d["s_pos"], d["s_z"], d["l_off"], d["l_pos"], d["l_z"],
                             threads=2, mode=O.MODE_REF)
     assert sing == 0
-    assert relmax(bs, d["beta_s"]) < 2e-7 and relmax(bl, d["beta_l"]) < 2e-7
+    assert relmax(bs, d["beta_s"]) <= bar("synth_ragged", "beta_s", "pcg") and relmax(bl, d["beta_l"]) <= bar("synth_ragged", "beta_l", "pcg")
     b, _, _, _ = O.est(d["bed"], n_ref, n_obs, sig, d["lmm_off"], np.arange(d["lmm_z"].size, dtype=np.int32), d["lmm_z"],
                        threads=2, mode=O.MODE_REF)
     assert relmax(b, d["lmm_beta"]) < 1e-9
@@ -118,10 +119,10 @@ def test_exact_mode_gap_to_reference_is_the_pcg_truncation(c1):
     (SURVEY 7 hard part 1): ~3e-9 in LMM mode, a few 1e-8 in DBSLMM mode on test_dat."""
     n_ref, n_obs, sig = int(c1["n_ref"]), int(c1["n_obs"]), float(c1["sigma_s"])
     b, _, _, _ = O.est(c1["bed"], n_ref, n_obs, sig, c1["lmm_off"], c1["lmm_pos"], c1["lmm_z"], mode=O.MODE_EXACT)
-    assert relmax(b, c1["lmm_beta"]) < 2e-8
+    assert relmax(b, c1["lmm_beta"]) <= bar("c1_testdat", "lmm_beta")
     bs, bl, _, _ = O.est(c1["bed"], n_ref, n_obs, sig, c1["s_off"], c1["s_pos"], c1["s_z"], c1["l_off"], c1["l_pos"],
                          c1["l_z"], mode=O.MODE_EXACT)
-    assert relmax(bs, c1["beta_s"]) < 5e-7 and relmax(bl, c1["beta_l"]) < 5e-7
+    assert relmax(bs, c1["beta_s"]) <= bar("c1_testdat", "beta_s") and relmax(bl, c1["beta_l"]) <= bar("c1_testdat", "beta_l")
 
 
 def test_bordered_system_identity(ragged):
@@ -168,7 +169,7 @@ def test_oracle_against_live_reference_build(ragged):
         zl = d["l_z"][d["l_off"][5]:d["l_off"][6]]
         r_s, r_l = R.est_block(bf.path, n, int(d["n_obs"]), float(d["sigma_s"]), ps, zs, pl, zl)
         o_s, o_l, _, _ = O.est_block(d["bed"], n, int(d["n_obs"]), float(d["sigma_s"]), ps, zs, pl, zl, mode=O.MODE_REF)
-        assert relmax(o_s, r_s) < 2e-7 and relmax(o_l, r_l) < 2e-7
+        assert relmax(o_s, r_s) < 1e-9 and relmax(o_l, r_l) < 1e-9      # live: oracle vs the unmodified estBlock on one block (measured 1e-11)
 
 
 @pytest.mark.skipif(not R.available(), reason="oracle/_ref (unmodified reference build) not present")
