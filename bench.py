@@ -675,7 +675,7 @@ def main():
                            "overlapped with decode/Gram/Cholesky, plan + z H2D, beta D2H; wall clock",
                     "upload_then_fit_ms_per_step": wall_two_call * 1e3},
             "resident_wall_ms_per_step": wall_resident / K * 1e3,
-            "gpu_launches": int(sum(t["n_launches"] for t in tms)) + (2 * K * ((len(folds) + 3) // 4) if val else 0),
+            "gpu_launches": int(sum(t["n_launches"] for t in tms)) + (2 * K * ((len(folds) + 2) // 3) if val else 0),
             "clocks": clocks, "roofline": roofline, "rooflines_other": other, "blocks_not_spd": n_bad}
     if parity:
         line["parity"] = parity

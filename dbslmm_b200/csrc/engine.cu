@@ -1582,7 +1582,7 @@ int dbslmm_b200_score(dbslmm_b200_handle* h, const uint8_t* bed_val, int64_t n_s
     const int32_t pitch = (n_val + 3) / 4;
     const size_t bytes = (size_t)n_snp_val * pitch;
     const int n_chunks = std::max(1, std::min<int>(4 * h->n_sm / std::max(1, ((pitch + 3) / 4 + 255) / 256), (int)((n_scored + 63) / 64)));
-    const int nf_pass = std::min(n_folds, 4);
+    const int nf_pass = std::min(n_folds, 3);            // folds per pass of the scoring kernel (score.cu: kMaxFolds)
     // work buffer: pos | flip | beta | partial | scores
     size_t o = 0;
     auto place = [&](size_t b) { size_t r = o; o = align_up(o + b, 256); return r; };
@@ -1615,8 +1615,8 @@ int dbslmm_b200_score(dbslmm_b200_handle* h, const uint8_t* bed_val, int64_t n_s
     if (!prefetched) CU_TRY(h, launch_snp_stats((const uint8_t*)h->vbed.p, n_snp_val, n_val, (SnpStat*)h->vstats.p, h->n_sm, st));
     CU_TRY(h, cudaMemsetAsync(w + o_sc, 0, sizeof(double) * (size_t)n_folds * n_val, st));
     CU_TRY(h, cudaEventRecord(h->ev[0], st));
-    for (int f0 = 0; f0 < n_folds; f0 += 4) {
-        const int nf = std::min(4, n_folds - f0);
+    for (int f0 = 0; f0 < n_folds; f0 += 3) {
+        const int nf = std::min(3, n_folds - f0);
         CU_TRY(h, launch_prs((const uint8_t*)h->vbed.p, n_val, (const SnpStat*)h->vstats.p, (const int32_t*)(w + o_pos),
                              flip ? (const uint8_t*)(w + o_flip) : nullptr, (const double*)(w + o_beta) + (size_t)f0 * n_scored,
                              n_scored, (int32_t)n_scored, nf, n_chunks, (double*)(w + o_part),

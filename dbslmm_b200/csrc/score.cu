@@ -16,14 +16,14 @@
 namespace dbslmm {
 
 static constexpr int kScoreThreads = 256;
-static constexpr int kMaxFolds = 4;          // folds per pass (more folds => several passes)
+static constexpr int kMaxFolds = 3;          // folds per pass (more folds => several passes): 16 individuals x 3 folds of FP64 accumulators per thread
 
 // One thread = FOUR consecutive .bed bytes = 16 individuals (a warp reads 128 contiguous bytes of a row per load), 64
 // scored SNPs per shared-memory batch.  Per SNP the four possible dosages {code 0, 1 = missing -> mean, 2, 3} are put
 // in shared memory once (allele flip and mean imputation folded in), so the inner loop is: extract the 2-bit code,
-// pick one of four doubles (two selects on a value held in registers), NF fused multiply-adds.
+// load the dosage it selects (one LDS.64), NF fused multiply-adds.
 template <int NF>
-__global__ void __launch_bounds__(kScoreThreads)
+__global__ void __launch_bounds__(kScoreThreads, 2)
 prs_partial_kernel(const uint8_t* __restrict__ bed, int32_t pitch, int32_t n_val, const SnpStat* __restrict__ stats,
                    const int32_t* __restrict__ pos, const uint8_t* __restrict__ flip, const double* __restrict__ beta,
                    int64_t beta_stride, int32_t n_scored, int32_t rows_per_chunk, double* __restrict__ partial) {
@@ -61,35 +61,37 @@ prs_partial_kernel(const uint8_t* __restrict__ bed, int32_t pitch, int32_t n_val
         }
         __syncthreads();
         if (!in_range) continue;
-        uint32_t words[4];
+        // software pipeline: the four row words of the NEXT group are in flight while this group is accumulated
+        auto load_word = [&](int j) -> uint32_t {
+            if (j >= nb) return 0xFFFFFFFFu;
+            const uint8_t* p = bed + (size_t)s_row[j] * pitch + byte0;
+            if (full_word) return __ldg(reinterpret_cast<const uint32_t*>(p));
+            uint32_t w = 0;
+            for (int bq = 0; bq < 4; ++bq) w |= (uint32_t)((byte0 + bq < pitch) ? p[bq] : 0xFF) << (8 * bq);
+            return w;
+        };
+        uint32_t words[4], next[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) next[u] = load_word(u);
         for (int j0 = 0; j0 < nb; j0 += 4) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                uint32_t w = 0xFFFFFFFFu;
-                if (j0 + u < nb) {
-                    const uint8_t* p = bed + (size_t)s_row[j0 + u] * pitch + byte0;
-                    if (full_word) w = *reinterpret_cast<const uint32_t*>(p);
-                    else {
-                        w = 0;
-                        for (int bq = 0; bq < 4; ++bq) w |= (uint32_t)((byte0 + bq < pitch) ? p[bq] : 0xFF) << (8 * bq);
-                    }
-                }
-                words[u] = w;
-            }
+            for (int u = 0; u < 4; ++u) words[u] = next[u];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) next[u] = load_word(j0 + 4 + u);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 if (j0 + u >= nb) break;
                 const uint32_t w = words[u];
-                const double2 d01 = *reinterpret_cast<const double2*>(&s_dos[j0 + u][0]);
-                const double2 d23 = *reinterpret_cast<const double2*>(&s_dos[j0 + u][2]);
+                // the SNP's four dosages sit in 32 contiguous bytes of shared memory: one broadcast-class LDS.64 indexed
+                // by the 2-bit code replaces the compare/select chain
+                const char* dos = reinterpret_cast<const char*>(&s_dos[j0 + u][0]);
                 double bf[NF];
 #pragma unroll
                 for (int f = 0; f < NF; ++f) bf[f] = s_beta[j0 + u][f];
 #pragma unroll
                 for (int q = 0; q < 16; ++q) {
-                    const uint32_t c = (w >> (2 * q)) & 3u;
-                    const double lo = (c & 1u) ? d01.y : d01.x, hi = (c & 1u) ? d23.y : d23.x;
-                    const double d = (c & 2u) ? hi : lo;
+                    const uint32_t c8 = (q < 15) ? ((w >> (2 * q)) & 3u) << 3 : (w >> 30) << 3;     // code * 8 bytes
+                    const double d = *reinterpret_cast<const double*>(dos + c8);
 #pragma unroll
                     for (int f = 0; f < NF; ++f) acc[q][f] = fma(bf[f], d, acc[q][f]);
                 }
@@ -127,7 +129,6 @@ cudaError_t launch_prs(const uint8_t* bed, int32_t n_val, const SnpStat* stats, 
         case 1: prs_partial_kernel<1><<<grid, kScoreThreads, 0, st>>>(bed, pitch, n_val, stats, pos, flip, beta, beta_stride, n_scored, rows_per_chunk, partial); break;
         case 2: prs_partial_kernel<2><<<grid, kScoreThreads, 0, st>>>(bed, pitch, n_val, stats, pos, flip, beta, beta_stride, n_scored, rows_per_chunk, partial); break;
         case 3: prs_partial_kernel<3><<<grid, kScoreThreads, 0, st>>>(bed, pitch, n_val, stats, pos, flip, beta, beta_stride, n_scored, rows_per_chunk, partial); break;
-        case 4: prs_partial_kernel<4><<<grid, kScoreThreads, 0, st>>>(bed, pitch, n_val, stats, pos, flip, beta, beta_stride, n_scored, rows_per_chunk, partial); break;
         default: return cudaErrorInvalidValue;
     }
     cudaError_t e = cudaGetLastError();
