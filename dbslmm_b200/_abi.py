@@ -21,7 +21,7 @@ FLAG_PANEL_SUBSET = 8
 EXPORTS = [
     "dbslmm_b200_abi_version", "dbslmm_b200_device_count", "dbslmm_b200_create", "dbslmm_b200_destroy",
     "dbslmm_b200_last_error", "dbslmm_b200_load_bed", "dbslmm_b200_snp_stats", "dbslmm_b200_plan_shards",
-    "dbslmm_b200_fit", "dbslmm_b200_host_alloc", "dbslmm_b200_host_free", "dbslmm_b200_score", "dbslmm_b200_score_prefetch", "dbslmm_b200_get_row_codes", "dbslmm_b200_get_block_sigma",
+    "dbslmm_b200_fit", "dbslmm_b200_fit_multi", "dbslmm_b200_host_alloc", "dbslmm_b200_host_free", "dbslmm_b200_score", "dbslmm_b200_score_prefetch", "dbslmm_b200_get_row_codes", "dbslmm_b200_get_block_sigma",
     "dbslmm_b200_get_block_gram", "dbslmm_b200_get_block_iters",
 ]
 
@@ -73,6 +73,7 @@ def load():
         lib.dbslmm_b200_plan_shards.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                                 C.c_void_p, C.c_void_p]
         lib.dbslmm_b200_fit.argtypes = [C.c_void_p, C.POINTER(FitArgs)]
+        lib.dbslmm_b200_fit_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.POINTER(FitArgs)]
         lib.dbslmm_b200_host_alloc.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
         lib.dbslmm_b200_host_free.argtypes = [C.c_void_p, C.c_void_p]
         lib.dbslmm_b200_host_free.restype = None
@@ -275,3 +276,37 @@ class Engine:
 
     def block_iters(self, block):
         return self._check(self.lib.dbslmm_b200_get_block_iters(self.h, int(block)), "get_block_iters")
+
+
+def fit_multi(engines, s_off, s_pos, s_z, l_off=None, l_pos=None, l_z=None, *, sigma_s, n_obs, bed, n_ref, tau=0.8,
+              solver=SOLVER_CHOLESKY):
+    """dbslmm_b200_fit_multi: one fit fanned out over several handles (normally one per GPU); the panel must come with the
+    call.  Returns dict(beta_s[n_folds, S], beta_l[n_folds, L], status[n_blocks], n_bad, timing)."""
+    lib = load()
+    s_off = np.ascontiguousarray(s_off, np.int32); s_pos = np.ascontiguousarray(s_pos, np.int32)
+    s_z = np.ascontiguousarray(s_z, np.float64)
+    nb = s_off.size - 1
+    sig = np.atleast_1d(np.asarray(sigma_s, np.float64)).copy()
+    nf = sig.size
+    beta_s = np.zeros((nf, s_pos.size), np.float64)
+    if l_off is not None:
+        l_off = np.ascontiguousarray(l_off, np.int32); l_pos = np.ascontiguousarray(l_pos, np.int32)
+        l_z = np.ascontiguousarray(l_z, np.float64)
+        beta_l = np.zeros((nf, max(l_pos.size, 1)), np.float64)
+        nl = l_pos.size
+    else:
+        beta_l, nl = None, 0
+    status = np.zeros(max(nb, 1), np.int32)
+    tm = Timing()
+    bed = np.ascontiguousarray(bed, np.uint8)
+    pitch = (int(n_ref) + 3) // 4
+    a = FitArgs(nb, s_off.ctypes.data, _ptr(s_pos), _ptr(s_z), _ptr(l_off), _ptr(l_pos), _ptr(l_z),
+                nf, sig.ctypes.data, int(n_obs), float(tau), int(solver), 0,
+                beta_s.ctypes.data, _ptr(beta_l), status.ctypes.data, C.pointer(tm))
+    a.bed, a.bed_n_snp, a.bed_n_ref = bed.ctypes.data, bed.size // pitch, int(n_ref)
+    hs = (C.c_void_p * len(engines))(*[e.h for e in engines])
+    rc = lib.dbslmm_b200_fit_multi(hs, len(engines), C.byref(a))
+    if rc < 0:
+        raise EngineError(f"fit_multi failed ({rc}): {lib.dbslmm_b200_last_error(engines[0].h).decode()}")
+    return {"beta_s": beta_s, "beta_l": None if beta_l is None else beta_l[:, :nl], "status": status[:nb], "n_bad": rc,
+            "timing": tm.as_dict()}

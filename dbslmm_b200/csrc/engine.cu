@@ -97,6 +97,7 @@ struct Plan {
     std::vector<int32_t> order;                       // concatenated batch member lists (big classes first)
     std::vector<Batch> batches;
     bool streaming = false;                           // layout in batch order (else block-index order)
+    std::vector<int32_t> up_order;                    // streaming: the order in which the batches' rows cross PCIe
     int32_t n_tiles_plain = 0, n_tiles_miss = 0;
     int64_t scratch_doubles = 0;
     int32_t n_groups = 0;                             // split-K groups (one arrival counter each)
@@ -134,6 +135,7 @@ struct dbslmm_b200_handle {
     double pdl_ratio = 0.0;
     int defer_max_ctas = 296;                    // steps with at most this many CTAs take their diagonal tile first (see StepList)
     // panel step kernel: TMA/mbarrier pipeline (default) or the cp.async version (DBSLMM_B200_PANEL=legacy)
+    int upload_bulk_first = 1;                   // streaming fit: bulk regions sent before the big classes (see make_batches)
     bool panel_tma = true;
     int tpc_max = 4, tpc_waves = 2;              // items per CTA: at most tpc_max, and only while a step keeps >= tpc_waves waves of CTAs
     int tmap_perm = -1;                          // 1: 4-D row-permuting tensor maps, 0: plain 2-D maps (driver refused), -1: not probed yet
@@ -278,6 +280,17 @@ int make_batches(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, 
         while (i < bulk.size() && (sb == nsub - 1 || acc < target)) { acc += P.blocks[bulk[i]].m; sub.push_back(bulk[i]); ++i; }
         add_batch(sub, (sb & 1) ? 0 : 1);
     }
+    // Upload order.  The batches are NUMBERED big classes first (their streams get the highest priorities: longest
+    // dependency chains), but the fit as a whole is throughput-bound on the bulk, and the big classes' chains (about half the
+    // fit) fit in the bulk's shadow: sending `upload_bulk_first` bulk regions ahead of the big classes gets the GPU busy
+    // earlier.  0 = big classes first (the numbering order).
+    const int nbt = (int)P.batches.size();
+    int n_big = 0;
+    while (n_big < nbt && P.batches[n_big].cls > 1) ++n_big;          // bulk regions carry class 0 / 1
+    const int lead = std::max(0, std::min(h->upload_bulk_first, nbt - n_big));
+    for (int i = 0; i < lead; ++i) P.up_order.push_back(n_big + i);
+    for (int i = 0; i < n_big; ++i) P.up_order.push_back(i);
+    for (int i = n_big + lead; i < nbt; ++i) P.up_order.push_back(i);
     return DBSLMM_B200_OK;
 }
 
@@ -678,6 +691,7 @@ int dbslmm_b200_create(int device, dbslmm_b200_handle** out) {
     }
     if (const char* e = std::getenv("DBSLMM_B200_DEFER_CTAS")) h->defer_max_ctas = std::atoi(e);
     else h->defer_max_ctas = 2 * h->n_sm;
+    if (const char* e = std::getenv("DBSLMM_B200_UPLOAD_BULK_FIRST")) h->upload_bulk_first = std::atoi(e);
     if (const char* e = std::getenv("DBSLMM_B200_PANEL")) h->panel_tma = (std::strcmp(e, "legacy") != 0);
     if (const char* e = std::getenv("DBSLMM_B200_TPC")) {         // "max[,waves]"
         int a = 0, b = 0;
@@ -899,17 +913,18 @@ int upload_prepare(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, const P
     return (rows_total > n_snp + n_snp / 4) ? 1 : 0;            // scattered subsets: a plain full upload is cheaper
 }
 
-// Issue the uploads of batches [next_batch, upto); upto == #batches also sends the rows outside every block.
+// Issue the uploads of the batches up_order[next_batch .. upto); upto == #batches also sends the rows outside every block.
 int upload_issue(dbslmm_b200_handle* h, const Plan& P, UploadPlan& U, const uint8_t* bed, int upto, bool subset) {
     typedef UploadPlan::Range Range;
     const size_t pitch = (size_t)h->pitch;
     const int64_t n_snp = h->n_snp;
     uint8_t* dev = (uint8_t*)h->bed.p;
     for (; U.next_batch < upto; ++U.next_batch) {
-        for (const Range& x : U.per_batch[U.next_batch])
+        const int bi = P.up_order[U.next_batch];
+        for (const Range& x : U.per_batch[bi])
             CU_TRY(h, cudaMemcpyAsync(dev + (size_t)x.first * pitch, bed + (size_t)x.first * pitch,
                                       (size_t)(x.second - x.first + 1) * pitch, cudaMemcpyHostToDevice, h->up_stream));
-        CU_TRY(h, cudaEventRecord(h->ev_up[U.next_batch], h->up_stream));
+        CU_TRY(h, cudaEventRecord(h->ev_up[bi], h->up_stream));
     }
     if (upto < (int)P.batches.size()) return 0;
     // rows outside every block (unmatched SNPs): last, so the resident copy is complete for later calls
@@ -1187,7 +1202,8 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
         // one chain per batch, each gated on the upload of that batch's rows; the batch's Cholesky (on its class
         // stream, below) is gated on ev_gram, so big classes factor while the bulk is still in flight
         CU_TRY(h, cudaEventRecord(h->ev[2], st));
-        for (int bi = 0; bi < nbatch; ++bi) {
+        for (int ui = 0; ui < nbatch; ++ui) {
+            const int bi = P.up_order[ui];                 // decode / Gram in the order the rows arrive
             const Batch& B = P.batches[bi];
             CU_TRY(h, cudaStreamWaitEvent(st, h->ev_up[bi], 0));
             int rc = chain(B.grow0, B.grow1, d_order + B.ord_off, B.ord_n, B.tile0, B.tile1, B.mtile0, B.mtile1, d_any + 1 + bi, true);
@@ -1531,6 +1547,116 @@ int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
         h->plan.valid = false;
     }
     return rc;
+}
+
+// One fit over several GPUs: the block scheduler (dbslmm_b200_plan_shards) assigns every block to one handle, every handle
+// fits its blocks from the SAME host panel (FLAG_PANEL_SUBSET: it uploads only the rows its blocks use) on its own host
+// thread, and the results are written straight into the caller's block-major arrays.  No collective: LD blocks are
+// independent (scr/dbslmmfit.cpp:193-213).
+int dbslmm_b200_fit_multi(dbslmm_b200_handle* const* hs, int32_t n_handles, const dbslmm_b200_fit_args* a) {
+    if (!hs || n_handles < 1 || !a || !hs[0]) return DBSLMM_B200_ERR_ARG;
+    dbslmm_b200_handle* h0 = hs[0];
+    if (n_handles == 1) return dbslmm_b200_fit(h0, a);
+    if (!a->bed) return fail(h0, DBSLMM_B200_ERR_ARG, "fit_multi: the panel must come with the call (fit_args.bed)");
+    if (a->test_bed || a->quadform_out || (a->flags & DBSLMM_B200_FLAG_PLAN_CACHED))
+        return fail(h0, DBSLMM_B200_ERR_ARG, "fit_multi: variance side channel, quadform and PLAN_CACHED are single-GPU features");
+    if (a->n_blocks < 0 || !a->s_off || a->n_folds < 1) return fail(h0, DBSLMM_B200_ERR_ARG, "fit_multi: bad arguments");
+    const int nb = a->n_blocks;
+    const bool with_large = a->l_off != nullptr;
+    std::vector<int32_t> m_s((size_t)std::max(nb, 1)), m_l((size_t)std::max(nb, 1), 0), owner((size_t)std::max(nb, 1), 0);
+    for (int b = 0; b < nb; ++b) {
+        m_s[b] = a->s_off[b + 1] - a->s_off[b];
+        if (with_large) m_l[b] = a->l_off[b + 1] - a->l_off[b];
+    }
+    int rc = dbslmm_b200_plan_shards(nb, m_s.data(), m_l.data(), a->bed_n_ref, n_handles, owner.data(), nullptr);
+    if (rc != DBSLMM_B200_OK) return fail(h0, rc, "fit_multi: plan_shards failed");
+    struct Shard {
+        std::vector<int32_t> blocks, s_off, s_pos, l_off, l_pos, status;
+        std::vector<double> s_z, l_z, beta_s, beta_l;
+        dbslmm_b200_timing timing{};
+        int rc = 0;
+    };
+    std::vector<Shard> sh((size_t)n_handles);
+    const int nf = a->n_folds;
+    for (int g = 0; g < n_handles; ++g) {
+        Shard& S = sh[g];
+        S.s_off.push_back(0);
+        if (with_large) S.l_off.push_back(0);
+        for (int b = 0; b < nb; ++b) {
+            if (owner[b] != g) continue;
+            S.blocks.push_back(b);
+            S.s_pos.insert(S.s_pos.end(), a->s_pos + a->s_off[b], a->s_pos + a->s_off[b + 1]);
+            S.s_z.insert(S.s_z.end(), a->s_z + a->s_off[b], a->s_z + a->s_off[b + 1]);
+            S.s_off.push_back((int32_t)S.s_pos.size());
+            if (with_large) {
+                S.l_pos.insert(S.l_pos.end(), a->l_pos + a->l_off[b], a->l_pos + a->l_off[b + 1]);
+                S.l_z.insert(S.l_z.end(), a->l_z + a->l_off[b], a->l_z + a->l_off[b + 1]);
+                S.l_off.push_back((int32_t)S.l_pos.size());
+            }
+        }
+        S.beta_s.assign(S.s_pos.size() * (size_t)nf + 1, 0.0);
+        S.beta_l.assign(S.l_pos.size() * (size_t)nf + 1, 0.0);
+        S.status.assign(S.blocks.size() + 1, 0);
+    }
+    auto run = [&](int g) {
+        Shard& S = sh[g];
+        if (S.blocks.empty()) return;
+        dbslmm_b200_fit_args x = *a;
+        x.n_blocks = (int32_t)S.blocks.size();
+        x.s_off = S.s_off.data(); x.s_pos = S.s_pos.data(); x.s_z = S.s_z.data();
+        x.l_off = with_large ? S.l_off.data() : nullptr;
+        x.l_pos = with_large ? S.l_pos.data() : nullptr;
+        x.l_z = with_large ? S.l_z.data() : nullptr;
+        x.beta_s_out = S.beta_s.data();
+        x.beta_l_out = with_large ? S.beta_l.data() : nullptr;
+        x.block_status_out = S.status.data();
+        x.timing = &S.timing;
+        x.flags = a->flags | DBSLMM_B200_FLAG_PANEL_SUBSET;
+        S.rc = dbslmm_b200_fit(hs[g], &x);
+    };
+    {
+        std::vector<std::thread> th;
+        for (int g = 1; g < n_handles; ++g) th.emplace_back(run, g);
+        run(0);
+        for (std::thread& t : th) t.join();
+    }
+    int n_bad = 0;
+    for (int g = 0; g < n_handles; ++g) {
+        if (sh[g].rc < 0) return fail(h0, sh[g].rc, "fit_multi: GPU " + std::to_string(g) + ": " + dbslmm_b200_last_error(hs[g]));
+        n_bad += sh[g].rc;
+    }
+    // gather to the caller's block-major arrays
+    const size_t tot_s = (size_t)a->s_off[nb], tot_l = with_large ? (size_t)a->l_off[nb] : 0;
+    for (int g = 0; g < n_handles; ++g) {
+        const Shard& S = sh[g];
+        const size_t ns = S.s_pos.size(), nl = S.l_pos.size();
+        for (size_t i = 0; i < S.blocks.size(); ++i) {
+            const int b = S.blocks[i];
+            if (a->block_status_out) a->block_status_out[b] = S.status[i];
+            for (int f = 0; f < nf; ++f) {
+                std::memcpy(a->beta_s_out + (size_t)f * tot_s + a->s_off[b], S.beta_s.data() + (size_t)f * ns + S.s_off[i], sizeof(double) * (size_t)m_s[b]);
+                if (with_large && m_l[b] > 0)
+                    std::memcpy(a->beta_l_out + (size_t)f * tot_l + a->l_off[b], S.beta_l.data() + (size_t)f * nl + S.l_off[i], sizeof(double) * (size_t)m_l[b]);
+            }
+        }
+    }
+    if (a->timing) {
+        // the slowest GPU's phase times; work counters summed over the GPUs
+        int slow = 0;
+        double gram_ops = 0.0, solve_flops = 0.0, decode_bytes = 0.0;
+        int n_launches = 0, n_chol = 0, n_miss = 0;
+        for (int g = 0; g < n_handles; ++g) {
+            const dbslmm_b200_timing& u = sh[g].timing;
+            if (u.total_ms > sh[slow].timing.total_ms) slow = g;
+            gram_ops += u.gram_ops; solve_flops += u.solve_flops; decode_bytes += u.decode_bytes;
+            n_launches += u.n_launches; n_chol += u.n_chol_launches; n_miss += u.n_blocks_missing;
+        }
+        dbslmm_b200_timing t = sh[slow].timing;
+        t.gram_ops = gram_ops; t.solve_flops = solve_flops; t.decode_bytes = decode_bytes;
+        t.n_launches = n_launches; t.n_chol_launches = n_chol; t.n_blocks_missing = n_miss;
+        *a->timing = t;
+    }
+    return n_bad;
 }
 
 int dbslmm_b200_host_alloc(dbslmm_b200_handle* h, uint64_t bytes, void** out) {

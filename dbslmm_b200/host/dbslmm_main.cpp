@@ -459,15 +459,34 @@ int main(int argc, char* argv[]) {
         sh.rc = dbslmm_b200_fit(hs[g], &a);
         if (sh.rc < 0) sh.err = dbslmm_b200_last_error(hs[g]);
     };
-    {
+    // Several GPUs without the variance side channel: ONE library call fans the blocks out (dbslmm_b200_fit_multi) and
+    // returns block-major betas; the per-GPU shards above serve the variance side channel and the single-GPU run.
+    const bool use_multi = n_gpus > 1 && !want_var;
+    vector<double> multi_s, multi_l;
+    if (use_multi) {
+        multi_s.assign(s_pos_all.size() * n_folds + 1, 0.0);
+        multi_l.assign(l_pos_all.size() * n_folds + 1, 0.0);
+        dbslmm_b200_fit_args a{};
+        a.bed = bed; a.bed_n_snp = n_snp_all; a.bed_n_ref = n_ref;
+        a.n_blocks = num_block;
+        a.s_off = s_off.data(); a.s_pos = s_pos_all.data(); a.s_z = s_z_all.data();
+        if (with_large) { a.l_off = l_off.data(); a.l_pos = l_pos_all.data(); a.l_z = l_z_all.data(); }
+        a.n_folds = n_folds; a.sigma_s = sigma_s.data(); a.n_obs = cPar.n; a.tau = cPar.tau;
+        a.solver = solver;
+        a.beta_s_out = multi_s.data(); a.beta_l_out = with_large ? multi_l.data() : nullptr;
+        a.timing = &shards[0].timing;
+        const int rc = dbslmm_b200_fit_multi(hs.data(), n_gpus, &a);
+        if (rc < 0) { cerr << "ERROR: " << dbslmm_b200_last_error(hs[0]) << endl; exit(2); }
+        if (rc > 0) cerr << "ERROR: Matrix is Singular! (" << rc << " block(s))" << endl;                  // dbslmmfit.cpp:665
+    } else {
         vector<thread> th;
         for (int g = 1; g < n_gpus; ++g) th.emplace_back(run, g);
         run(0);
         for (auto& t : th) t.join();
-    }
-    for (int g = 0; g < n_gpus; ++g) {
-        if (shards[g].rc < 0) { cerr << "ERROR: GPU " << g << ": " << shards[g].err << endl; exit(2); }
-        if (shards[g].rc > 0) cerr << "ERROR: Matrix is Singular! (" << shards[g].rc << " block(s) on GPU " << g << ")" << endl;   // dbslmmfit.cpp:665
+        for (int g = 0; g < n_gpus; ++g) {
+            if (shards[g].rc < 0) { cerr << "ERROR: GPU " << g << ": " << shards[g].err << endl; exit(2); }
+            if (shards[g].rc > 0) cerr << "ERROR: Matrix is Singular! (" << shards[g].rc << " block(s) on GPU " << g << ")" << endl;   // dbslmmfit.cpp:665
+        }
     }
     const double time_fitting = walltime() - t_fitting;
     cout << "Fitting time: " << time_fitting << " seconds." << endl;
@@ -481,7 +500,8 @@ int main(int argc, char* argv[]) {
     // ---- gather to block-major global order
     const size_t tot_s = s_pos_all.size(), tot_l = l_pos_all.size();
     vector<double> beta_s(tot_s * n_folds + 1), beta_l(tot_l * n_folds + 1);
-    for (int g = 0; g < n_gpus; ++g) {
+    if (use_multi) { beta_s.swap(multi_s); beta_l.swap(multi_l); }
+    for (int g = 0; g < n_gpus && !use_multi; ++g) {
         const Shard& sh = shards[g];
         const size_t ns = sh.s_pos.size(), nl = sh.l_pos.size();
         for (size_t i = 0; i < sh.blocks.size(); ++i) {

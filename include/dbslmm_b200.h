@@ -153,6 +153,14 @@ DBSLMM_B200_API int  dbslmm_b200_plan_shards(int32_t n_blocks, const int32_t* m_
 
 DBSLMM_B200_API int  dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* args);
 
+/* The same fit fanned out over several GPUs of one box: hs[0..n_handles) are handles created on different devices.  The
+ * blocks are assigned by dbslmm_b200_plan_shards, every GPU uploads only the panel rows its blocks use (args->bed is required;
+ * one host thread per GPU inside the call), and the betas / block statuses land in the caller's block-major arrays as in
+ * dbslmm_b200_fit.  This is the multi-GPU shape of DBSLMMFIT::est (one call, scr/dbslmmfit.hpp:38-67; its `thread` argument
+ * becomes the handle list).  Not available with the variance side channel, quadform_out or FLAG_PLAN_CACHED.  timing: the
+ * slowest GPU's phase times, work counters summed.  Errors are reported on hs[0] (dbslmm_b200_last_error(hs[0])). */
+DBSLMM_B200_API int  dbslmm_b200_fit_multi(dbslmm_b200_handle* const* hs, int32_t n_handles, const dbslmm_b200_fit_args* args);
+
 /* Page-locked host memory for the panel (`bed` of load_bed / fit_args.bed): uploads from it run at full PCIe speed and
  * truly asynchronously; ordinary memory works too, but is staged by the driver.  The reference has no counterpart (it
  * reads the .bed through an ifstream, scr/dtpr.cpp:302-315); the `dbslmm` command line reads its .bed files straight

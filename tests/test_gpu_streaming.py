@@ -144,3 +144,26 @@ def test_streaming_scattered_rows_use_plain_upload(engine):
     rs = engine.fit(s_off, perm, z, sigma_s=[1e-4], n_obs=9000, bed=w["bed"], n_ref=400)
     bs, _, _, _ = O.est(w["bed"], 400, 9000, 1e-4, s_off, perm, z, threads=4, mode=O.MODE_EXACT)
     assert relmax(rs["beta_s"][0], bs) <= 1e-10
+
+
+def test_fit_multi_fans_out_over_handles(engine):
+    """dbslmm_b200_fit_multi: blocks assigned by the scheduler, every handle uploads only its rows, betas gathered block-major.
+    Two handles (on two GPUs when the box has them, else both on GPU 0) against the exact oracle and a single-handle fit."""
+    n_dev = _abi.load().dbslmm_b200_device_count()
+    w = synth.make_workload(77, [300, 0, 90, 1100, 40, 520, 260, 700], 400, missing_rate=0.003, frac_large=0.02)
+    csr = csr_of(w)
+    kw = dict(sigma_s=[1e-4, 2e-4], n_obs=20_000)
+    second = _abi.Engine(1 if n_dev >= 2 else 0)
+    try:
+        rm = _abi.fit_multi([engine, second], *csr, bed=w["bed"], n_ref=400, **kw)
+        r1 = engine.fit(*csr, bed=w["bed"], n_ref=400, **kw)
+        assert rm["n_bad"] == 0 and rm["status"].shape == r1["status"].shape
+        assert relmax(rm["beta_s"], r1["beta_s"]) <= 1e-12 and relmax(rm["beta_l"], r1["beta_l"]) <= 1e-12
+        for f, sg in enumerate(kw["sigma_s"]):
+            bs, bl, _, _ = O.est(w["bed"], 400, 20_000, sg, *csr, threads=4, mode=O.MODE_EXACT)
+            assert relmax(rm["beta_s"][f], bs) <= 1e-10 and relmax(rm["beta_l"][f], bl) <= 1e-10
+        # the handles keep no panel after a subset upload: a fit without fit_args.bed must say so
+        with pytest.raises(_abi.EngineError):
+            second.fit(*csr, **kw)
+    finally:
+        second.close()
