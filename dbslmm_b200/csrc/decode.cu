@@ -139,9 +139,11 @@ decode_rows_kernel(const uint8_t* __restrict__ bed, int32_t n_ref, int32_t pitch
                    int32_t buf_bytes, const uint32_t* __restrict__ row_src, const int32_t* __restrict__ row_crow,
                    const int32_t* __restrict__ row_mrow, int64_t g0, int64_t n_rows, double tau,
                    int8_t* __restrict__ codes, uint8_t* __restrict__ dirty, int32_t* __restrict__ rowN,
-                   int32_t* __restrict__ rowS, double* __restrict__ rowR) {
+                   int32_t* __restrict__ rowS, double* __restrict__ rowR, const int32_t* __restrict__ gate) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bars[kWarpsPerCta][kDecRing];
+    // gate (fused-Gram pipeline): int8 rows are needed only by blocks with missing calls; *gate == 0 says there are none
+    if (gate != nullptr && *gate == 0) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* buf0 = smem + (size_t)warp * kDecRing * buf_bytes;
     if (lane == 0) {
@@ -254,6 +256,106 @@ decode_rows_kernel(const uint8_t* __restrict__ bed, int32_t n_ref, int32_t pitch
 }
 
 // ------------------------------------------------------------------------------------------
+// Packer: the decoder's front half for the fused correlation builder (gram.cu: gram_packed_kernel).  One warp per SNP row
+// of the plan stages the .bed row (same TMA bulk ring), counts its genotypes (per-SNP statistics) and writes the row as
+// 2-BIT codes again -- but gathered into plan order, 16-byte aligned (pitch n_pad / 4) and with the samples past n_ref set
+// to code 3 (zero copies) -- so the correlation builder can fetch [128 rows x 128 samples] operand tiles with ONE 2-D TMA
+// load each and unpack them in shared memory.  4 x less operand traffic through L2 than int8 rows; a quarter of the bytes
+// written here.
+// ------------------------------------------------------------------------------------------
+template <int kDecRing>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+pack_rows_kernel(const uint8_t* __restrict__ bed, int32_t n_ref, int32_t pitch, int32_t n_pad, int32_t buf_bytes,
+                 const uint32_t* __restrict__ row_src, int64_t g0, int64_t n_rows, double tau,
+                 uint32_t* __restrict__ packed, int32_t* __restrict__ rowN, int32_t* __restrict__ rowS,
+                 double* __restrict__ rowR) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bars[kWarpsPerCta][kDecRing];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* buf0 = smem + (size_t)warp * kDecRing * buf_bytes;
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < kDecRing; ++i) mbar_init(&bars[warp][i], 1);
+    }
+    mbar_fence_init();
+    __syncwarp();
+    const int wpc = blockDim.x >> 5;
+    const int64_t gw = (int64_t)blockIdx.x * wpc + warp;
+    const int64_t stride = (int64_t)gridDim.x * wpc;
+    const int nwords = (pitch + 3) >> 2;     // input words holding real samples
+    const int nout = n_pad >> 4;             // 32-bit output words per row (16 samples each)
+    const int nfull = n_ref >> 4;
+    uint32_t phase = 0;
+    uint32_t off[kDecRing];
+    int64_t row = gw;
+#pragma unroll
+    for (int i = 0; i < kDecRing; ++i) off[i] = 0;
+#pragma unroll
+    for (int i = 0; i < kDecRing - 1; ++i) {
+        const int64_t r = row + (int64_t)i * stride;
+        if (r < n_rows) off[i] = RowStage::issue(bed, (int64_t)row_src[g0 + r], pitch, buf0 + i * buf_bytes, &bars[warp][i], lane);
+    }
+    uint32_t pre = 0;
+    {
+        const int64_t r = row + (int64_t)(kDecRing - 1) * stride;
+        if (r < n_rows) pre = row_src[g0 + r];
+    }
+    int cur = 0;
+    for (; row < n_rows; row += stride) {
+        {
+            const int64_t nxt = row + (int64_t)(kDecRing - 1) * stride;
+            const int nb = (cur + kDecRing - 1) % kDecRing;
+            const uint32_t issue_src = pre;
+            const int64_t nxt2 = nxt + stride;
+            if (nxt2 < n_rows) pre = row_src[g0 + nxt2];
+            if (nxt < n_rows) {
+                const uint32_t o = RowStage::issue(bed, (int64_t)issue_src, pitch, buf0 + nb * buf_bytes, &bars[warp][nb], lane);
+#pragma unroll
+                for (int i = 0; i < kDecRing; ++i) if (i == nb) off[i] = o;
+            }
+        }
+        uint32_t off_cur = 0;
+#pragma unroll
+        for (int i = 0; i < kDecRing; ++i) if (i == cur) off_cur = off[i];
+        const int64_t g = g0 + row;
+        mbar_wait(&bars[warp][cur], (phase >> cur) & 1u);
+        phase ^= 1u << cur;
+        const uint32_t* w32 = reinterpret_cast<const uint32_t*>(buf0 + cur * buf_bytes);
+        uint32_t* out = packed + (size_t)g * nout;
+        int c0 = 0, c1 = 0, c2 = 0;
+        for (int i = lane; i < nout; i += 32) {
+            uint32_t w = 0xFFFFFFFFu;                     // 16 x code 3: samples past the panel count nothing, unpack to 0
+            if (i < nwords) {
+                w = row_word(w32, off_cur, i);
+                if (i >= nfull) w |= ~valid_bits(n_ref, i);
+                const uint32_t lo = w & 0x55555555u, hi = (w >> 1) & 0x55555555u;
+                c0 += __popc(~(lo | hi) & 0x55555555u);    // code 0 -> allele count 2
+                c1 += __popc(lo & ~hi);                    // code 1 -> missing
+                c2 += __popc(hi & ~lo);                    // code 2 -> allele count 1
+            }
+            out[i] = w;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+            c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+            c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+        }
+        if (lane == 0) {
+            const int32_t nn = n_ref - c1, sum = 2 * c0 + c2, sumsq = 4 * c0 + c2;
+            const double ni = (double)nn;
+            const double d = ni * (double)sumsq - (double)sum * (double)sum;
+            const double n = (double)n_ref;
+            rowN[g] = nn;
+            rowS[g] = sum;
+            rowR[g] = sqrt(tau * (n - 1.0) / (n * ni * d));
+        }
+        __syncwarp();
+        cur = (cur + 1 == kDecRing) ? 0 : cur + 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Per-block "has missing calls" flag from the counts the decoder just wrote: one warp per listed block.  The
 // correlation builder reads flags[b] per tile (one integer plane or four); any[0] tells the four-plane kernel whether
 // there is anything to do at all.
@@ -322,7 +424,7 @@ template <int RING>
 static cudaError_t launch_decode_t(const uint8_t* bed, int32_t n_ref, int32_t pitch, int32_t n_pad, int buf, int wpc,
                                    const uint32_t* row_src, const int32_t* row_crow, const int32_t* row_mrow, int64_t g0,
                                    int64_t n_rows, double tau, int8_t* codes, uint8_t* dirty, int32_t* rowN, int32_t* rowS,
-                                   double* rowR, int n_sm, cudaStream_t st) {
+                                   double* rowR, const int32_t* gate, int n_sm, cudaStream_t st) {
     const size_t smem = (size_t)wpc * RING * buf;
     cudaError_t e = cudaFuncSetAttribute(decode_rows_kernel<RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -330,25 +432,52 @@ static cudaError_t launch_decode_t(const uint8_t* bed, int32_t n_ref, int32_t pi
     const int64_t cap = (int64_t)n_sm * 8;
     if (ctas > cap) ctas = cap;
     decode_rows_kernel<RING><<<(unsigned)ctas, wpc * 32, smem, st>>>(bed, n_ref, pitch, n_pad, buf, row_src, row_crow, row_mrow, g0,
-                                                                   n_rows, tau, codes, dirty, rowN, rowS, rowR);
+                                                                   n_rows, tau, codes, dirty, rowN, rowS, rowR, gate);
     return cudaGetLastError();
+}
+
+template <int RING>
+static cudaError_t launch_pack_t(const uint8_t* bed, int32_t n_ref, int32_t pitch, int32_t n_pad, int buf, int wpc,
+                                 const uint32_t* row_src, int64_t g0, int64_t n_rows, double tau, uint32_t* packed,
+                                 int32_t* rowN, int32_t* rowS, double* rowR, int n_sm, cudaStream_t st) {
+    const size_t smem = (size_t)wpc * RING * buf;
+    cudaError_t e = cudaFuncSetAttribute(pack_rows_kernel<RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int64_t ctas = (n_rows + wpc - 1) / wpc;
+    const int64_t cap = (int64_t)n_sm * 8;
+    if (ctas > cap) ctas = cap;
+    pack_rows_kernel<RING><<<(unsigned)ctas, wpc * 32, smem, st>>>(bed, n_ref, pitch, n_pad, buf, row_src, g0, n_rows, tau, packed,
+                                                                 rowN, rowS, rowR);
+    return cudaGetLastError();
+}
+// SNP rows [g0, g0 + n_rows) of the plan -> packed 2-bit rows (pitch n_pad / 4 bytes, row g at packed + g * n_pad / 16 words)
+cudaError_t launch_pack_rows(const uint8_t* bed, int32_t n_ref, int32_t n_pad, const uint32_t* row_src, int64_t g0, int64_t n_rows,
+                             double tau, uint32_t* packed, int32_t* rowN, int32_t* rowS, double* rowR, int n_sm, cudaStream_t st) {
+    if (n_rows == 0) return cudaSuccess;
+    const int32_t pitch = (n_ref + 3) / 4;
+    const int buf = stage_bytes(pitch);
+    if (stage_warps(buf, 4) == kWarpsPerCta)
+        return launch_pack_t<4>(bed, n_ref, pitch, n_pad, buf, kWarpsPerCta, row_src, g0, n_rows, tau, packed, rowN, rowS, rowR, n_sm, st);
+    const int wpc = stage_warps(buf, 2);
+    if (wpc < 1) return cudaErrorInvalidValue;
+    return launch_pack_t<2>(bed, n_ref, pitch, n_pad, buf, wpc, row_src, g0, n_rows, tau, packed, rowN, rowS, rowR, n_sm, st);
 }
 
 // SNP rows [g0, g0 + n_rows) of the plan
 cudaError_t launch_decode_rows(const uint8_t* bed, int32_t n_ref, int32_t n_pad, const uint32_t* row_src,
                                const int32_t* row_crow, const int32_t* row_mrow, int64_t g0, int64_t n_rows, double tau,
-                               int8_t* codes, uint8_t* dirty, int32_t* rowN, int32_t* rowS, double* rowR, int n_sm,
-                               cudaStream_t st) {
+                               int8_t* codes, uint8_t* dirty, int32_t* rowN, int32_t* rowS, double* rowR, const int32_t* gate,
+                               int n_sm, cudaStream_t st) {
     if (n_rows == 0) return cudaSuccess;
     const int32_t pitch = (n_ref + 3) / 4;
     const int buf = stage_bytes(pitch);
     // four staging buffers per warp and eight warps per CTA while they fit; long rows fall back to two buffers, then
     // to fewer warps (n_ref up to decode_max_n_ref())
     if (stage_warps(buf, 4) == kWarpsPerCta)
-        return launch_decode_t<4>(bed, n_ref, pitch, n_pad, buf, kWarpsPerCta, row_src, row_crow, row_mrow, g0, n_rows, tau, codes, dirty, rowN, rowS, rowR, n_sm, st);
+        return launch_decode_t<4>(bed, n_ref, pitch, n_pad, buf, kWarpsPerCta, row_src, row_crow, row_mrow, g0, n_rows, tau, codes, dirty, rowN, rowS, rowR, gate, n_sm, st);
     const int wpc = stage_warps(buf, 2);
     if (wpc < 1) return cudaErrorInvalidValue;
-    return launch_decode_t<2>(bed, n_ref, pitch, n_pad, buf, wpc, row_src, row_crow, row_mrow, g0, n_rows, tau, codes, dirty, rowN, rowS, rowR, n_sm, st);
+    return launch_decode_t<2>(bed, n_ref, pitch, n_pad, buf, wpc, row_src, row_crow, row_mrow, g0, n_rows, tau, codes, dirty, rowN, rowS, rowR, gate, n_sm, st);
 }
 
 }  // namespace dbslmm

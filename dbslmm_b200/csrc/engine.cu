@@ -136,6 +136,9 @@ struct dbslmm_b200_handle {
     int defer_max_ctas = 296;                    // steps with at most this many CTAs take their diagonal tile first (see StepList)
     // panel step kernel: TMA/mbarrier pipeline (default) or the cp.async version (DBSLMM_B200_PANEL=legacy)
     int upload_bulk_first = 1;                   // streaming fit: bulk regions sent before the big classes (see make_batches)
+    // correlation builder for blocks without missing calls: fused unpack + Gram from packed 2-bit rows (default) or the
+    // int8-row kernel of round 1 (DBSLMM_B200_GRAM=codes)
+    bool gram_packed = true;
     bool panel_tma = true;
     int tpc_max = 4, tpc_waves = 2;              // items per CTA: at most tpc_max, and only while a step keeps >= tpc_waves waves of CTAs
     int tmap_perm = -1;                          // 1: 4-D row-permuting tensor maps, 0: plain 2-D maps (driver refused), -1: not probed yet
@@ -152,7 +155,7 @@ struct dbslmm_b200_handle {
     int64_t n_snp = 0;
     int32_t n_ref = 0, pitch = 0, n_pad = 0;
     // workspace
-    DevBuf codes, sigma, lbuf, rowN, rowS, rowR, planblob, beta, status, intQ, intA, intN, scratch, counters, wbuf, vbed, vstats, vwork, dflag, dirty, bflags;
+    DevBuf codes, sigma, lbuf, rowN, rowS, rowR, planblob, beta, status, intQ, intA, intN, scratch, counters, wbuf, vbed, vstats, vwork, dflag, dirty, bflags, packed;
     // validation panel of the scoring step, announced by dbslmm_b200_score_prefetch: uploaded in the shadow of the next fit
     const uint8_t* val_host = nullptr;
     int64_t val_n_snp = 0;
@@ -335,7 +338,8 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P) {
     P.n_snp_rows = goff;
     P.n_code_rows = croff;
     P.mat_doubles = moff;
-    P.decode_bytes = (double)goff * ((double)h->pitch + (double)h->n_pad);   // .bed row read + genotype code row written (mask rows: see fit)
+    // .bed row read + what the packer (2-bit rows, n_pad / 4 bytes) or the decoder (int8 rows) writes; mask rows: see fit
+    P.decode_bytes = (double)goff * ((double)h->pitch + (h->gram_packed ? (double)h->n_pad / 4.0 : (double)h->n_pad));
 
     // Gram tiles in batch order, big blocks first inside a batch: the lower triangle as 128 x 128 tiles for the one-plane
     // kernel and as 64-row x 128-column tiles for the four-plane kernel (every block is in both lists; the kernels pick
@@ -692,6 +696,7 @@ int dbslmm_b200_create(int device, dbslmm_b200_handle** out) {
     if (const char* e = std::getenv("DBSLMM_B200_DEFER_CTAS")) h->defer_max_ctas = std::atoi(e);
     else h->defer_max_ctas = 2 * h->n_sm;
     if (const char* e = std::getenv("DBSLMM_B200_UPLOAD_BULK_FIRST")) h->upload_bulk_first = std::atoi(e);
+    if (const char* e = std::getenv("DBSLMM_B200_GRAM")) h->gram_packed = (std::strcmp(e, "codes") != 0);
     if (const char* e = std::getenv("DBSLMM_B200_PANEL")) h->panel_tma = (std::strcmp(e, "legacy") != 0);
     if (const char* e = std::getenv("DBSLMM_B200_TPC")) {         // "max[,waves]"
         int a = 0, b = 0;
@@ -737,7 +742,7 @@ void dbslmm_b200_destroy(dbslmm_b200_handle* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     DevBuf* bufs[] = {&h->bed, &h->stats, &h->codes, &h->sigma, &h->lbuf, &h->rowN, &h->rowS, &h->rowR,
-                      &h->planblob, &h->beta, &h->status, &h->intQ, &h->intA, &h->intN, &h->scratch, &h->counters, &h->wbuf, &h->vbed, &h->vstats, &h->vwork, &h->dflag, &h->dirty, &h->bflags};
+                      &h->planblob, &h->beta, &h->status, &h->intQ, &h->intA, &h->intN, &h->scratch, &h->counters, &h->wbuf, &h->vbed, &h->vstats, &h->vwork, &h->dflag, &h->dirty, &h->bflags, &h->packed};
     for (DevBuf* b : bufs) b->release();
     h->h_blob.release();
     h->h_out.release();
@@ -1034,6 +1039,8 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
         }
     }
     CU_TRY(h, h->bflags.ensure(sizeof(int32_t) * (size_t)(std::max(nb, 1) + kMaxBatches + 1)));
+    const bool packed_gram = h->gram_packed;
+    if (packed_gram) CU_TRY(h, h->packed.ensure((size_t)std::max<int64_t>(P.n_snp_rows, 1) * (size_t)(h->n_pad / 4) + 4096));
     CU_TRY(h, h->sigma.ensure(sizeof(double) * (size_t)std::max<int64_t>(P.mat_doubles, 1)));
     if (!pcg && !quad) CU_TRY(h, h->lbuf.ensure(sizeof(double) * (size_t)std::max<int64_t>(P.mat_doubles, 1)));
     CU_TRY(h, h->rowN.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(P.n_snp_rows, 1)));
@@ -1127,12 +1134,22 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
     if (!pcg && !quad) CU_TRY(h, cudaMemsetAsync(h->dflag.p, 0, sizeof(int32_t) * (size_t)std::max(nb, 1), st));
     // ---- decode + gram
     GramArgs g;
-    CUtensorMap tmap, tmap64;
+    CUtensorMap tmap, tmap64, pmap;
     if (P.n_code_rows > 0) {
         int rc = make_tensor_map(h, &tmap, h->codes.p, P.n_code_rows, h->n_pad, 128);
         if (rc != DBSLMM_B200_OK) return rc;
         rc = make_tensor_map(h, &tmap64, h->codes.p, P.n_code_rows, h->n_pad, 64);      // I side of the four-plane kernel
         if (rc != DBSLMM_B200_OK) return rc;
+        if (packed_gram) {
+            // packed 2-bit rows: [n_snp_rows][n_pad / 4 bytes], operand tile = 128 rows x 32 bytes (128 samples), no swizzle
+            cuuint64_t dims[2] = {(cuuint64_t)(h->n_pad / 4), (cuuint64_t)P.n_snp_rows};
+            cuuint64_t strides[1] = {(cuuint64_t)(h->n_pad / 4)};
+            cuuint32_t box[2] = {32, 128};
+            cuuint32_t estr[2] = {1, 1};
+            if (h->encode(&pmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, h->packed.p, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                return fail(h, DBSLMM_B200_ERR_CUDA, "cuTensorMapEncodeTiled failed for the packed rows");
+        }
         g.blocks = d_blocks;
         g.nk = h->n_pad / 128;
         g.n_ref = h->n_ref;
@@ -1154,9 +1171,13 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
     auto chain = [&](int64_t g0, int64_t g1, const int32_t* list, int32_t n_list, int32_t t0, int32_t t1, int32_t mt0, int32_t mt1,
                      int32_t* any, bool light) -> int {
         if (g1 <= g0) return DBSLMM_B200_OK;
-        CU_TRY(h, launch_decode_rows((const uint8_t*)h->bed.p, h->n_ref, h->n_pad, d_rowsrc, d_crow, d_mrow, g0, g1 - g0, a->tau,
-                                     (int8_t*)h->codes.p, (uint8_t*)h->dirty.p, (int32_t*)h->rowN.p, (int32_t*)h->rowS.p,
-                                     (double*)h->rowR.p, h->n_sm, st));
+        if (packed_gram)        // 2-bit rows in plan order + per-SNP statistics; int8 rows only if a block turns out to need them
+            CU_TRY(h, launch_pack_rows((const uint8_t*)h->bed.p, h->n_ref, h->n_pad, d_rowsrc, g0, g1 - g0, a->tau, (uint32_t*)h->packed.p,
+                                       (int32_t*)h->rowN.p, (int32_t*)h->rowS.p, (double*)h->rowR.p, h->n_sm, st));
+        else
+            CU_TRY(h, launch_decode_rows((const uint8_t*)h->bed.p, h->n_ref, h->n_pad, d_rowsrc, d_crow, d_mrow, g0, g1 - g0, a->tau,
+                                         (int8_t*)h->codes.p, (uint8_t*)h->dirty.p, (int32_t*)h->rowN.p, (int32_t*)h->rowS.p,
+                                         (double*)h->rowR.p, nullptr, h->n_sm, st));
         CU_TRY(h, launch_block_flags(d_blocks, list, n_list, (const int32_t*)h->rowN.p, h->n_ref, d_bflags, any, st));
         n_launch += 2;
         g.any = any;
@@ -1164,7 +1185,14 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
         if (t1 > t0) {
             g.tiles = d_tiles_plain + t0;
             g.n_tiles = t1 - t0;
-            CU_TRY(h, launch_gram(tmap, g, st));
+            if (packed_gram) CU_TRY(h, launch_gram_packed(pmap, g, st));
+            else CU_TRY(h, launch_gram(tmap, g, st));
+            ++n_launch;
+        }
+        if (packed_gram) {      // returns at once unless some block of this chain has missing calls
+            CU_TRY(h, launch_decode_rows((const uint8_t*)h->bed.p, h->n_ref, h->n_pad, d_rowsrc, d_crow, d_mrow, g0, g1 - g0, a->tau,
+                                         (int8_t*)h->codes.p, (uint8_t*)h->dirty.p, (int32_t*)h->rowN.p, (int32_t*)h->rowS.p,
+                                         (double*)h->rowR.p, any, h->n_sm, st));
             ++n_launch;
         }
         if (mt1 > mt0) {
@@ -1178,20 +1206,33 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
         return DBSLMM_B200_OK;
     };
     if (!streaming) {
+        // ONE chain over everything.  decode_ms = the packer / decoder; the rest of the chain counts as Gram time
         if (P.n_snp_rows > 0) {
-            CU_TRY(h, launch_decode_rows((const uint8_t*)h->bed.p, h->n_ref, h->n_pad, d_rowsrc, d_crow, d_mrow, 0, P.n_snp_rows, a->tau,
-                                         (int8_t*)h->codes.p, (uint8_t*)h->dirty.p, (int32_t*)h->rowN.p, (int32_t*)h->rowS.p,
-                                         (double*)h->rowR.p, h->n_sm, st));
+            if (packed_gram)
+                CU_TRY(h, launch_pack_rows((const uint8_t*)h->bed.p, h->n_ref, h->n_pad, d_rowsrc, 0, P.n_snp_rows, a->tau, (uint32_t*)h->packed.p,
+                                           (int32_t*)h->rowN.p, (int32_t*)h->rowS.p, (double*)h->rowR.p, h->n_sm, st));
+            else
+                CU_TRY(h, launch_decode_rows((const uint8_t*)h->bed.p, h->n_ref, h->n_pad, d_rowsrc, d_crow, d_mrow, 0, P.n_snp_rows, a->tau,
+                                             (int8_t*)h->codes.p, (uint8_t*)h->dirty.p, (int32_t*)h->rowN.p, (int32_t*)h->rowS.p,
+                                             (double*)h->rowR.p, nullptr, h->n_sm, st));
             ++n_launch;
         }
-        CU_TRY(h, cudaEventRecord(h->ev[2], st));          // decoder done
+        CU_TRY(h, cudaEventRecord(h->ev[2], st));          // packer / decoder done
         if (P.n_snp_rows > 0) {
             CU_TRY(h, launch_block_flags(d_blocks, nullptr, nb, (const int32_t*)h->rowN.p, h->n_ref, d_bflags, d_any, st));
             ++n_launch;
             g.any = d_any;
             g.tiles = d_tiles_plain;
             g.n_tiles = P.n_tiles_plain;
-            CU_TRY(h, launch_gram(tmap, g, st));
+            if (packed_gram) {
+                CU_TRY(h, launch_gram_packed(pmap, g, st));
+                CU_TRY(h, launch_decode_rows((const uint8_t*)h->bed.p, h->n_ref, h->n_pad, d_rowsrc, d_crow, d_mrow, 0, P.n_snp_rows, a->tau,
+                                             (int8_t*)h->codes.p, (uint8_t*)h->dirty.p, (int32_t*)h->rowN.p, (int32_t*)h->rowS.p,
+                                             (double*)h->rowR.p, d_any, h->n_sm, st));
+                ++n_launch;
+            } else {
+                CU_TRY(h, launch_gram(tmap, g, st));
+            }
             g.tiles = d_tiles_miss;
             g.n_tiles = P.n_tiles_miss;
             CU_TRY(h, launch_gram_missing(tmap, tmap64, g, st));

@@ -40,6 +40,77 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         : "memory");
 }
 
+// FP64 epilogue of one 128 x 128 one-plane tile for one epilogue warp (TMEM lane quarter q = Sigma columns, row half):
+// tcgen05.ld -> n Q - S_i S_j (exact) -> scale -> coalesced row stores of the lower triangle.  Shared by the int8-row and the
+// packed-row kernels.  rc: this warp's 64 x {S_i, r_i} staging in shared memory.
+__device__ __forceinline__ void plain_epilogue_tile(const GramArgs& a, const GramTile& tile, const BlockDesc& bd, uint32_t tmem_acc,
+                                                    int q, int half, int lane, double2* rc, uint64_t* acc_full_bar,
+                                                    uint32_t full_parity, uint64_t* acc_empty_bar) {
+    const double dn = (double)a.n_ref;
+    const int jl = tile.tj * kTile + q * 32 + lane;
+    const int i0 = tile.ti * kTile + half * 64;          // first row of this warp's half
+    double Sj = 0.0, rj = 0.0;
+    if (jl < bd.m) { Sj = (double)a.rowS[bd.goff + jl]; rj = a.rowR[bd.goff + jl] * dn; }
+    // per-row constants go through shared memory (one broadcast LDS.128 per row instead of four shuffles);
+    // their global loads overlap the wait for the accumulator
+    __syncwarp();
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+        const int il = i0 + 32 * hh + lane;
+        double2 c = make_double2(0.0, 0.0);
+        if (il < bd.m) c = make_double2((double)a.rowS[bd.goff + il], a.rowR[bd.goff + il]);
+        rc[32 * hh + lane] = c;
+    }
+    __syncwarp();
+    mbar_wait(acc_full_bar, full_parity);
+    tc_fence_after();
+    const uint32_t tlane = tmem_acc + ((uint32_t)(q * 32) << 16);
+    double* sig = a.sigma + bd.moff;
+    uint32_t v[2][32];
+    tmem_ld32(tlane + half * 64, v[0]);
+    tmem_ld32(tlane + half * 64 + 32, v[1]);
+    tmem_ld_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(acc_empty_bar);                // accumulator copied out: MMA may reuse it
+    if (i0 >= bd.mp) return;                                  // warp-uniform: nothing of this half is inside the block
+    const size_t ld = (size_t)bd.ld;
+    if (tile.ti > tile.tj && i0 + 64 <= bd.m && !a.full && a.intQ == nullptr) {
+        // interior half tile (every entry below the diagonal, every row a real SNP): straight-line code
+        double* p = sig + (size_t)i0 * ld + jl;
+#pragma unroll
+        for (int r = 0; r < 64; ++r) {
+            const double2 c = rc[r];
+            // n Q - S_i S_j is an exact integer below 2^53: one FMA, no rounding
+            const double t = fma(-c.x, Sj, dn * (double)(int32_t)v[r >> 5][r & 31]);
+            p[(size_t)r * ld] = t * c.y * rj;
+        }
+        return;
+    }
+    // general half tile (diagonal, last tile row, debug planes): same arithmetic, predicated stores
+    const int nreal = bd.m - i0;                           // rows r < nreal are real SNPs
+    double* p = sig + (size_t)i0 * ld + jl;
+#pragma unroll
+    for (int r = 0; r < 64; ++r) {
+        const int il = i0 + r;
+        const double2 c = rc[r];
+        const double t = fma(-c.x, Sj, dn * (double)(int32_t)v[r >> 5][r & 31]);
+        double val = t * c.y * rj;
+        if (il == jl) val += a.one_minus_tau;
+        if (r < nreal && jl <= il) {
+            p[(size_t)r * ld] = val;
+            if (a.full && jl < il) sig[(size_t)jl * ld + il] = val;
+            if (a.intQ != nullptr) {
+                a.intQ[(size_t)bd.moff + (size_t)il * ld + jl] = (int32_t)v[r >> 5][r & 31];
+                a.intQ[(size_t)bd.moff + (size_t)jl * ld + il] = (int32_t)v[r >> 5][r & 31];
+            }
+        }
+    }
+    // identity padding rows m .. mp-1 (at most 7 per block)
+    for (int il = max(bd.m, i0); il < min(bd.mp, i0 + 64); ++il)
+        if (jl <= il) sig[(size_t)il * ld + jl] = (il == jl) ? 1.0 : 0.0;
+}
+
 // ------------------------------------------------------------------------------------------
 // Blocks WITHOUT missing calls (one accumulator plane): one CTA per SM walks
 // the tile list; the s32 accumulator is double-buffered in TMEM (2 x 128 columns) so the FP64
@@ -128,7 +199,6 @@ gram_persistent_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs 
         }
     } else {
         const int q = warp & 3, half = (warp - 2) >> 2;
-        const double dn = (double)a.n_ref;
         double2* rc = row_consts[warp - 2];                      // this warp's 64 rows: {S_i, r_i}
         uint32_t lt = 0;
         for (int tile_i = blockIdx.x; tile_i < a.n_tiles; tile_i += gridDim.x) {
@@ -137,70 +207,155 @@ gram_persistent_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs 
             const BlockDesc bd = a.blocks[tile.blk];
             const uint32_t my_lt = lt++;                         // tiles this CTA has processed so far
             const uint32_t as = my_lt & 1u;
-            const int jl = tile.tj * kTile + q * 32 + lane;
-            const int i0 = tile.ti * kTile + half * 64;          // first row of this warp's half
-            double Sj = 0.0, rj = 0.0;
-            if (jl < bd.m) { Sj = (double)a.rowS[bd.goff + jl]; rj = a.rowR[bd.goff + jl] * dn; }
-            // per-row constants go through shared memory (one broadcast LDS.128 per row instead of four shuffles);
-            // their global loads overlap the wait for the accumulator
-            __syncwarp();
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-                const int il = i0 + 32 * hh + lane;
-                double2 c = make_double2(0.0, 0.0);
-                if (il < bd.m) c = make_double2((double)a.rowS[bd.goff + il], a.rowR[bd.goff + il]);
-                rc[32 * hh + lane] = c;
-            }
-            __syncwarp();
-            mbar_wait(&acc_full[as], (my_lt >> 1) & 1u);
-            tc_fence_after();
-            const uint32_t tlane = tmem_base + as * kTile + ((uint32_t)(q * 32) << 16);
-            double* sig = a.sigma + bd.moff;
-            uint32_t v[2][32];
-            tmem_ld32(tlane + half * 64, v[0]);
-            tmem_ld32(tlane + half * 64 + 32, v[1]);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[as]);               // accumulator copied out: MMA may reuse it
-            if (i0 >= bd.mp) continue;                                // warp-uniform: nothing of this half is inside the block
-            const size_t ld = (size_t)bd.ld;
-            if (tile.ti > tile.tj && i0 + 64 <= bd.m && !a.full && a.intQ == nullptr) {
-                // interior half tile (every entry below the diagonal, every row a real SNP): straight-line code
-                double* p = sig + (size_t)i0 * ld + jl;
-#pragma unroll
-                for (int r = 0; r < 64; ++r) {
-                    const double2 c = rc[r];
-                    // n Q - S_i S_j is an exact integer below 2^53: one FMA, no rounding
-                    const double t = fma(-c.x, Sj, dn * (double)(int32_t)v[r >> 5][r & 31]);
-                    p[(size_t)r * ld] = t * c.y * rj;
+            plain_epilogue_tile(a, tile, bd, tmem_base + as * kTile, q, half, lane, rc, &acc_full[as], (my_lt >> 1) & 1u, &acc_empty[as]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<256>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused unpack + Gram for blocks WITHOUT missing calls (the default).  Operands are fetched as 2-BIT rows (packed by
+// pack_rows_kernel in plan order, 16-byte aligned pitch) -- [128 rows x 32 B] per 128-sample K step and operand, one 2-D
+// TMA load -- and expanded to the int8 SWIZZLE_128B K-major layout in shared memory by four unpack warps (generic-proxy
+// stores + fence.proxy.async), so the int8 rows never exist in HBM or L2: a quarter of the operand traffic of the int8-row
+// kernel above, which runs at the L2 -> SM bandwidth limit at n_ref = 2,000 (105 int8 op per operand/result byte).
+//   warp 0      TMA producer of packed tiles (4-stage ring, 8 KB per stage)
+//   warp 1      TMEM allocator + tcgen05.mma issuer (int8 ring of 3 stages, 32 KB each; accumulators double-buffered)
+//   warps 2-5   unpack: thread t owns operand row t of the stage: 2 x LDS.128 -> 8 x (16 codes -> 16 bytes) -> 8 x STS.128
+//   warps 6-13  FP64 epilogue (plain_epilogue_tile), overlapping the next tile's main loop
+// ------------------------------------------------------------------------------------------
+static constexpr int kUThreads = 448;
+static constexpr int kUPStages = 4;                       // packed stages
+static constexpr int kUIStages = 3;                       // int8 operand stages
+static constexpr int kPackedTile = kTile * 32;            // 128 rows x 32 bytes (128 samples)
+static constexpr int kUSmem = kUIStages * 2 * kTileBytes + kUPStages * 2 * kPackedTile + 1024;
+
+// sixteen 2-bit codes -> sixteen allele-count bytes (0 -> 2, 2 -> 1, 1 = missing and 3 -> 0), as decode.cu's expand16<false>
+__device__ __forceinline__ uint2 gram_expand8(uint32_t h) {
+    constexpr uint32_t lut = 0x00010002u;
+    uint32_t t = (h | (h << 8)) & 0x00FF00FFu;
+    t = (t | (t << 4)) & 0x0F0F0F0Fu;
+    t = (t | (t << 2)) & 0x33333333u;
+    return make_uint2(__byte_perm(lut, 0u, t), __byte_perm(lut, 0u, t >> 16));
+}
+
+__global__ void __launch_bounds__(kUThreads, 1)
+gram_packed_kernel(const __grid_constant__ CUtensorMap pmap, const GramArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t pfull[kUPStages], pempty[kUPStages], ifull[kUIStages], iempty[kUIStages], acc_full[2], acc_empty[2];
+    __shared__ __align__(16) double2 row_consts[8][64];
+    __shared__ uint32_t tmem_slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* pk = smem + kUIStages * 2 * kTileBytes;      // packed ring behind the int8 ring
+    const int nk = a.nk;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kUPStages; ++s) { mbar_init(&pfull[s], 1); mbar_init(&pempty[s], 4); }
+        for (int s = 0; s < kUIStages; ++s) { mbar_init(&ifull[s], 4); mbar_init(&iempty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
+        mbar_fence_init();
+        tma_prefetch_desc(&pmap);
+    }
+    if (warp == 1) tmem_alloc<256>(&tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t pit = 0;
+            for (int tile_i = blockIdx.x; tile_i < a.n_tiles; tile_i += gridDim.x) {
+                const GramTile tile = a.tiles[tile_i];
+                if (a.flags[tile.blk] != 0) continue;
+                const BlockDesc bd = a.blocks[tile.blk];
+                const bool diag = (tile.ti == tile.tj);
+                const int32_t rowJ = bd.goff + tile.tj * kTile, rowI = bd.goff + tile.ti * kTile;      // packed rows = SNP rows
+                for (int ks = 0; ks < nk; ++ks, ++pit) {
+                    const int s = pit % kUPStages;
+                    mbar_wait(&pempty[s], ((pit / kUPStages) & 1u) ^ 1u);
+                    uint8_t* st = pk + (size_t)s * 2 * kPackedTile;
+                    mbar_expect_tx(&pfull[s], (uint32_t)((diag ? 1 : 2) * kPackedTile));
+                    tma_load_2d(st, &pmap, ks * 32, rowJ, &pfull[s]);
+                    if (!diag) tma_load_2d(st + kPackedTile, &pmap, ks * 32, rowI, &pfull[s]);
                 }
-                continue;
             }
-            // general half tile (diagonal, last tile row, debug planes): same arithmetic, predicated stores
-            {
-                const int nreal = bd.m - i0;                           // rows r < nreal are real SNPs
-                double* p = sig + (size_t)i0 * ld + jl;
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_i8_idesc(kTile, kTile);
+            uint32_t iit = 0, lt = 0;
+            for (int tile_i = blockIdx.x; tile_i < a.n_tiles; tile_i += gridDim.x) {
+                const GramTile tile = a.tiles[tile_i];
+                if (a.flags[tile.blk] != 0) continue;
+                const bool diag = (tile.ti == tile.tj);
+                const uint32_t as = lt & 1u;
+                mbar_wait(&acc_empty[as], ((lt >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                for (int ks = 0; ks < nk; ++ks, ++iit) {
+                    const int s = iit % kUIStages;
+                    mbar_wait(&ifull[s], (iit / kUIStages) & 1u);
+                    tc_fence_after();
+                    const uint32_t st = smem_u32(smem + (size_t)s * 2 * kTileBytes);
+                    const uint64_t dJ = make_sw128_kmajor_desc(st), dI = make_sw128_kmajor_desc(diag ? st : st + kTileBytes);
 #pragma unroll
-                for (int r = 0; r < 64; ++r) {
-                    const int il = i0 + r;
-                    const double2 c = rc[r];
-                    const double t = fma(-c.x, Sj, dn * (double)(int32_t)v[r >> 5][r & 31]);
-                    double val = t * c.y * rj;
-                    if (il == jl) val += a.one_minus_tau;
-                    if (r < nreal && jl <= il) {
-                        p[(size_t)r * ld] = val;
-                        if (a.full && jl < il) sig[(size_t)jl * ld + il] = val;
-                        if (a.intQ != nullptr) {
-                            a.intQ[(size_t)bd.moff + (size_t)il * ld + jl] = (int32_t)v[r >> 5][r & 31];
-                            a.intQ[(size_t)bd.moff + (size_t)jl * ld + il] = (int32_t)v[r >> 5][r & 31];
-                        }
+                    for (int kk = 0; kk < 4; ++kk)
+                        umma_i8(tmem_base + as * kTile, dJ + (uint64_t)(kk * 2), dI + (uint64_t)(kk * 2), idesc, (ks > 0 || kk > 0) ? 1u : 0u);
+                    umma_commit(&iempty[s]);
+                }
+                umma_commit(&acc_full[as]);
+                ++lt;
+            }
+        }
+    } else if (warp < 6) {
+        // ---- unpack: operand row `ut` of every stage
+        const int ut = threadIdx.x - 64;
+        const uint32_t src_off = (uint32_t)ut * 32u;
+        const uint32_t dst_row = (uint32_t)(ut >> 3) * 1024u + (uint32_t)(ut & 7) * 128u;
+        const uint32_t sw = (uint32_t)(ut & 7);
+        const uint32_t pk_u32 = smem_u32(pk), i8_u32 = smem_u32(smem);
+        uint32_t pit = 0;
+        for (int tile_i = blockIdx.x; tile_i < a.n_tiles; tile_i += gridDim.x) {
+            const GramTile tile = a.tiles[tile_i];
+            if (a.flags[tile.blk] != 0) continue;
+            const int nop = (tile.ti == tile.tj) ? 1 : 2;
+            for (int ks = 0; ks < nk; ++ks, ++pit) {
+                const int ps = pit % kUPStages, is = pit % kUIStages;      // one packed stage feeds one int8 stage
+                mbar_wait(&pfull[ps], (pit / kUPStages) & 1u);
+                mbar_wait(&iempty[is], ((pit / kUIStages) & 1u) ^ 1u);
+                for (int op = 0; op < nop; ++op) {
+                    const uint32_t src = pk_u32 + (uint32_t)ps * 2 * kPackedTile + (uint32_t)op * kPackedTile + src_off;
+                    uint32_t w[8];
+                    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(src));
+                    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "r"(src + 16));
+                    const uint32_t dst = i8_u32 + (uint32_t)is * 2 * kTileBytes + (uint32_t)op * kTileBytes + dst_row;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const uint2 lo = gram_expand8(w[c] & 0xFFFFu), hi = gram_expand8(w[c] >> 16);
+                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + (((uint32_t)c ^ sw) << 4)), "r"(lo.x), "r"(lo.y),
+                                     "r"(hi.x), "r"(hi.y)
+                                     : "memory");
                     }
                 }
-                // identity padding rows m .. mp-1 (at most 7 per block)
-                for (int il = max(bd.m, i0); il < min(bd.mp, i0 + 64); ++il)
-                    if (jl <= il) sig[(size_t)il * ld + jl] = (il == jl) ? 1.0 : 0.0;
+                fence_proxy_async();                // the int8 tile was written through the generic proxy, UMMA reads it through the async proxy
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(&ifull[is]); mbar_arrive(&pempty[ps]); }
             }
+        }
+    } else {
+        const int q = warp & 3, half = (warp - 6) >> 2;
+        double2* rc = row_consts[warp - 6];
+        uint32_t lt = 0;
+        for (int tile_i = blockIdx.x; tile_i < a.n_tiles; tile_i += gridDim.x) {
+            const GramTile tile = a.tiles[tile_i];
+            if (a.flags[tile.blk] != 0) continue;
+            const BlockDesc bd = a.blocks[tile.blk];
+            const uint32_t my_lt = lt++;
+            const uint32_t as = my_lt & 1u;
+            plain_epilogue_tile(a, tile, bd, tmem_base + as * kTile, q, half, lane, rc, &acc_full[as], (my_lt >> 1) & 1u, &acc_empty[as]);
         }
     }
     tc_fence_before();
@@ -393,6 +548,19 @@ cudaError_t launch_gram(const CUtensorMap& tmap, const GramArgs& a, cudaStream_t
         if (e != cudaSuccess) return e;
         gram_persistent_kernel<5><<<std::min(a.n_tiles, n_sm), kPThreads, PCfg<5>::kSmem, st>>>(tmap, a);
     }
+    return cudaGetLastError();
+}
+
+// Fused unpack + one-plane Gram over `a.tiles` from the packed 2-bit rows (pmap: 2-D map over the packed buffer, box
+// 32 bytes x 128 rows, no swizzle).
+cudaError_t launch_gram_packed(const CUtensorMap& pmap, const GramArgs& a, cudaStream_t st) {
+    if (a.n_tiles == 0) return cudaSuccess;
+    int dev = 0, n_sm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e = cudaFuncSetAttribute(gram_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kUSmem);
+    if (e != cudaSuccess) return e;
+    gram_packed_kernel<<<std::min(a.n_tiles, n_sm), kUThreads, kUSmem, st>>>(pmap, a);
     return cudaGetLastError();
 }
 

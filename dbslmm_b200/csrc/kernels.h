@@ -13,8 +13,12 @@ cudaError_t launch_snp_stats(const uint8_t* bed, int64_t n_snp, int32_t n_ref, S
 // SNP rows [g0, g0 + n_rows) of the plan: genotype code rows always, mask code rows where needed (see decode.cu)
 cudaError_t launch_decode_rows(const uint8_t* bed, int32_t n_ref, int32_t n_pad, const uint32_t* row_src,
                                const int32_t* row_crow, const int32_t* row_mrow, int64_t g0, int64_t n_rows, double tau,
-                               int8_t* codes, uint8_t* dirty, int32_t* rowN, int32_t* rowS, double* rowR, int n_sm,
-                               cudaStream_t st);
+                               int8_t* codes, uint8_t* dirty, int32_t* rowN, int32_t* rowS, double* rowR, const int32_t* gate,
+                               int n_sm, cudaStream_t st);
+// the same rows as 2-bit codes in plan order with an aligned pitch (n_pad / 4 bytes) + the per-SNP statistics: the input of
+// the fused unpack + Gram kernel
+cudaError_t launch_pack_rows(const uint8_t* bed, int32_t n_ref, int32_t n_pad, const uint32_t* row_src, int64_t g0, int64_t n_rows,
+                             double tau, uint32_t* packed, int32_t* rowN, int32_t* rowS, double* rowR, int n_sm, cudaStream_t st);
 int32_t decode_max_n_ref();          // largest n_ref the row-staging kernels (decoder, statistics) can take
 // flags[b] = block b has missing calls (from the decoder's counts), for the blocks in `list` (nullptr: 0..n_list-1);
 // *any |= flags
@@ -42,6 +46,7 @@ struct GramArgs {
     const int32_t* any;         // some block of this launch has missing calls
 };
 cudaError_t launch_gram(const CUtensorMap& tmap, const GramArgs& a, cudaStream_t st);
+cudaError_t launch_gram_packed(const CUtensorMap& pmap, const GramArgs& a, cudaStream_t st);
 cudaError_t launch_gram_missing(const CUtensorMap& tmapJ, const CUtensorMap& tmapI, const GramArgs& a, cudaStream_t st);
 cudaError_t launch_gram_simt(const int8_t* codes, int32_t n_pad, int64_t row0, int32_t m, int32_t* q_out,
                              cudaStream_t st);
