@@ -300,7 +300,7 @@ int make_batches(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, 
 // Step 2: device layout, Gram tiles, Cholesky step lists, the pinned blob.
 // Every block gets m genotype code rows followed by m call-mask code rows; which blocks really have missing calls is
 // found out on the device (decoder counts -> block_flags_kernel), so the plan never looks at the panel.
-int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P) {
+int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, const Trace* tr = nullptr) {
     const int nb = a->n_blocks;
     int n_test = 0;
     if (a->test_bed) for (int i = 0; i < a->test_n_total; ++i) n_test += (a->test_indicator[i] != 0);
@@ -341,10 +341,21 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P) {
     // .bed row read + what the packer (2-bit rows, n_pad / 4 bytes) or the decoder (int8 rows) writes; mask rows: see fit
     P.decode_bytes = (double)goff * ((double)h->pitch + (h->gram_packed ? (double)h->n_pad / 4.0 : (double)h->n_pad));
 
+    if (tr) tr->mark("  plan: layout");
     // Gram tiles in batch order, big blocks first inside a batch: the lower triangle as 128 x 128 tiles for the one-plane
     // kernel and as 64-row x 128-column tiles for the four-plane kernel (every block is in both lists; the kernels pick
     // their blocks by the device-side flag)
     std::vector<GramTile> tiles_plain, tiles_miss;
+    {
+        size_t n1 = 0, n2 = 0;
+        for (int b = 0; b < nb; ++b) {
+            const size_t nt = (size_t)(P.blocks[b].mp + 127) / 128, nt64 = (size_t)(P.blocks[b].mp + 63) / 64;
+            n1 += nt * (nt + 1) / 2;
+            n2 += nt64 * (nt64 / 2 + 1);
+        }
+        tiles_plain.reserve(n1);
+        tiles_miss.reserve(n2);
+    }
     for (Batch& B : P.batches) {
         B.tile0 = (int32_t)tiles_plain.size();
         B.mtile0 = (int32_t)tiles_miss.size();
@@ -370,9 +381,12 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P) {
     P.n_tiles_plain = (int32_t)tiles_plain.size();
     P.n_tiles_miss = (int32_t)tiles_miss.size();
 
+    if (tr) tr->mark("  plan: gram tiles");
     // Cholesky step lists per batch
     std::vector<int32_t> diag_items;
     std::vector<int4> panel_items;
+    diag_items.reserve((size_t)(goff / 64 + 2 * nb + 16));
+    panel_items.reserve((size_t)(goff / 64 + 2 * nb + 16) * 6);
     int32_t n_groups = 0;
     const int kTargetCtas = 2 * h->n_sm;              // 2 panel CTAs per SM
     for (Batch& B : P.batches) {
@@ -433,6 +447,7 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P) {
         P.scratch_doubles += batch_scratch;
     }
 
+    if (tr) tr->mark("  plan: step lists");
     // ---- pack the blob
     size_t o = 0;
     auto place = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
@@ -507,6 +522,7 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P) {
         }
         if (bad.load()) return fail(h, DBSLMM_B200_ERR_ARG, "s_pos / l_pos out of range of the loaded .bed");
     }
+    if (tr) tr->mark("  plan: per-SNP arrays");
     if (!tiles_plain.empty()) std::memcpy(blob.data() + P.o_tiles_plain, tiles_plain.data(), sizeof(GramTile) * tiles_plain.size());
     if (!tiles_miss.empty()) std::memcpy(blob.data() + P.o_tiles_miss, tiles_miss.data(), sizeof(GramTile) * tiles_miss.size());
     std::memcpy(blob.data() + P.o_order, P.order.data(), sizeof(int32_t) * (size_t)nb);
@@ -1012,7 +1028,7 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
                 return fit_impl(h, a, false);
             }
         }
-        rc = build_plan(h, a, P);
+        rc = build_plan(h, a, P, &tr);
         if (rc != DBSLMM_B200_OK) { P.valid = false; return rc; }
         P.fingerprint = fp;
         tr.mark("plan built");

@@ -223,10 +223,12 @@ gram_persistent_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs 
 // kernel above, which runs at the L2 -> SM bandwidth limit at n_ref = 2,000 (105 int8 op per operand/result byte).
 //   warp 0      TMA producer of packed tiles (4-stage ring, 8 KB per stage)
 //   warp 1      TMEM allocator + tcgen05.mma issuer (int8 ring of 3 stages, 32 KB each; accumulators double-buffered)
-//   warps 2-5   unpack: thread t owns operand row t of the stage: 2 x LDS.128 -> 8 x (16 codes -> 16 bytes) -> 8 x STS.128
-//   warps 6-13  FP64 epilogue (plain_epilogue_tile), overlapping the next tile's main loop
+//   warps 2-9   unpack: thread t owns half of operand row t / 2 of the stage: LDS.128 -> 4 x (16 codes -> 16 bytes) -> 4 x STS.128
+//               (two unpack warps per SM sub-partition: one alone cannot hide the ALU latency of the expansion chain)
+//   warps 10-17 FP64 epilogue (plain_epilogue_tile), overlapping the next tile's main loop
 // ------------------------------------------------------------------------------------------
-static constexpr int kUThreads = 448;
+static constexpr int kUThreads = 576;
+static constexpr int kUWarps = 8;                         // unpack warps
 static constexpr int kUPStages = 4;                       // packed stages
 static constexpr int kUIStages = 3;                       // int8 operand stages
 static constexpr int kPackedTile = kTile * 32;            // 128 rows x 32 bytes (128 samples)
@@ -253,8 +255,8 @@ gram_packed_kernel(const __grid_constant__ CUtensorMap pmap, const GramArgs a) {
     const int nk = a.nk;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kUPStages; ++s) { mbar_init(&pfull[s], 1); mbar_init(&pempty[s], 4); }
-        for (int s = 0; s < kUIStages; ++s) { mbar_init(&ifull[s], 4); mbar_init(&iempty[s], 1); }
+        for (int s = 0; s < kUPStages; ++s) { mbar_init(&pfull[s], 1); mbar_init(&pempty[s], kUWarps); }
+        for (int s = 0; s < kUIStages; ++s) { mbar_init(&ifull[s], kUWarps); mbar_init(&iempty[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
         mbar_fence_init();
         tma_prefetch_desc(&pmap);
@@ -310,12 +312,13 @@ gram_packed_kernel(const __grid_constant__ CUtensorMap pmap, const GramArgs a) {
                 ++lt;
             }
         }
-    } else if (warp < 6) {
-        // ---- unpack: operand row `ut` of every stage
+    } else if (warp < 2 + kUWarps) {
+        // ---- unpack: half of operand row `ur` of every stage (16 bytes = 64 samples = four 16-byte output chunks)
         const int ut = threadIdx.x - 64;
-        const uint32_t src_off = (uint32_t)ut * 32u;
-        const uint32_t dst_row = (uint32_t)(ut >> 3) * 1024u + (uint32_t)(ut & 7) * 128u;
-        const uint32_t sw = (uint32_t)(ut & 7);
+        const int ur = ut >> 1, uh = ut & 1;
+        const uint32_t src_off = (uint32_t)ur * 32u + (uint32_t)uh * 16u;
+        const uint32_t dst_row = (uint32_t)(ur >> 3) * 1024u + (uint32_t)(ur & 7) * 128u;
+        const uint32_t sw = (uint32_t)(ur & 7);
         const uint32_t pk_u32 = smem_u32(pk), i8_u32 = smem_u32(smem);
         uint32_t pit = 0;
         for (int tile_i = blockIdx.x; tile_i < a.n_tiles; tile_i += gridDim.x) {
@@ -326,28 +329,33 @@ gram_packed_kernel(const __grid_constant__ CUtensorMap pmap, const GramArgs a) {
                 const int ps = pit % kUPStages, is = pit % kUIStages;      // one packed stage feeds one int8 stage
                 mbar_wait(&pfull[ps], (pit / kUPStages) & 1u);
                 mbar_wait(&iempty[is], ((pit / kUIStages) & 1u) ^ 1u);
-                for (int op = 0; op < nop; ++op) {
-                    const uint32_t src = pk_u32 + (uint32_t)ps * 2 * kPackedTile + (uint32_t)op * kPackedTile + src_off;
-                    uint32_t w[8];
-                    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(src));
-                    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "r"(src + 16));
-                    const uint32_t dst = i8_u32 + (uint32_t)is * 2 * kTileBytes + (uint32_t)op * kTileBytes + dst_row;
+                uint32_t w[2][4];
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const uint2 lo = gram_expand8(w[c] & 0xFFFFu), hi = gram_expand8(w[c] >> 16);
-                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + (((uint32_t)c ^ sw) << 4)), "r"(lo.x), "r"(lo.y),
-                                     "r"(hi.x), "r"(hi.y)
-                                     : "memory");
+                for (int op = 0; op < 2; ++op)
+                    if (op < nop) {
+                        const uint32_t src = pk_u32 + (uint32_t)ps * 2 * kPackedTile + (uint32_t)op * kPackedTile + src_off;
+                        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w[op][0]), "=r"(w[op][1]), "=r"(w[op][2]), "=r"(w[op][3]) : "r"(src));
                     }
-                }
+#pragma unroll
+                for (int op = 0; op < 2; ++op)
+                    if (op < nop) {
+                        const uint32_t dst = i8_u32 + (uint32_t)is * 2 * kTileBytes + (uint32_t)op * kTileBytes + dst_row;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const uint2 lo = gram_expand8(w[op][c] & 0xFFFFu), hi = gram_expand8(w[op][c] >> 16);
+                            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + (((uint32_t)(4 * uh + c) ^ sw) << 4)), "r"(lo.x),
+                                         "r"(lo.y), "r"(hi.x), "r"(hi.y)
+                                         : "memory");
+                        }
+                    }
                 fence_proxy_async();                // the int8 tile was written through the generic proxy, UMMA reads it through the async proxy
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(&ifull[is]); mbar_arrive(&pempty[ps]); }
             }
         }
     } else {
-        const int q = warp & 3, half = (warp - 6) >> 2;
-        double2* rc = row_consts[warp - 6];
+        const int q = warp & 3, half = (warp - 2 - kUWarps) >> 2;
+        double2* rc = row_consts[warp - 2 - kUWarps];
         uint32_t lt = 0;
         for (int tile_i = blockIdx.x; tile_i < a.n_tiles; tile_i += gridDim.x) {
             const GramTile tile = a.tiles[tile_i];

@@ -68,11 +68,13 @@ def test_decode_gram_sigma(case, engine):
         pos = block_pos(w, b)
         miss = bool((w["G"][pos] < 0).any())
         for j in sorted({0, m // 2, m - 1}):
+            if not miss:
+                continue         # int8 rows exist only for blocks with missing calls (the others are unpacked in shared memory:
+                                 # their decode is checked through the bit-exact Q below and in test_int8_rows_of_the_decoder)
             codes = engine.row_codes(b, j, n_pad)
             assert np.array_equal(codes[:n_ref], Gz[pos[j]]) and not codes[n_ref:].any()
-            if miss:
-                mk = engine.row_codes(b, j, n_pad, plane=1)
-                assert np.array_equal(mk[:n_ref], (w["G"][pos[j]] >= 0).astype(np.int8)) and not mk[n_ref:].any()
+            mk = engine.row_codes(b, j, n_pad, plane=1)
+            assert np.array_equal(mk[:n_ref], (w["G"][pos[j]] >= 0).astype(np.int8)) and not mk[n_ref:].any()
         Q, A, N = engine.block_gram(b, m)
         Qo, Ao, No = O.gram_int(w["bed"], n_ref, pos)
         assert np.array_equal(Q, Qo), (name, b)
@@ -80,6 +82,35 @@ def test_decode_gram_sigma(case, engine):
         S = engine.block_sigma(b, m)
         assert np.abs(S - O.sigma(w["bed"], n_ref, pos)).max() <= 1e-13, (name, b)
         assert np.array_equal(S, S.T)
+
+
+def test_int8_rows_of_the_decoder():
+    """DBSLMM_B200_GRAM=codes: every block goes through the decoder's int8 rows (the round-1 path, still the path of blocks
+    with missing calls): codes of every plane bit for bit, Q / A / N and betas as in the default path."""
+    sizes, n_ref, missr = CASES["odd_pitch"]
+    w = synth.make_workload(99, sizes, n_ref, missing_rate=0.0, frac_large=0.02)
+    os.environ["DBSLMM_B200_GRAM"] = "codes"
+    try:
+        eng = _abi.Engine(0)
+    finally:
+        os.environ.pop("DBSLMM_B200_GRAM", None)
+    try:
+        eng.load_bed(w["bed"], n_ref)
+        csr = (w["s_off"], w["s_pos"], w["s_z"], w["l_off"], w["l_pos"], w["l_z"])
+        r = eng.fit(*csr, sigma_s=[1e-4], n_obs=10_000, flags=_abi.FLAG_KEEP_INT_GRAM)
+        n_pad = (n_ref + 127) // 128 * 128
+        for b, m in enumerate(w["block_sizes"]):
+            pos = block_pos(w, b)
+            for j in (0, m // 2, m - 1):
+                codes = eng.row_codes(b, j, n_pad)
+                assert np.array_equal(codes[:n_ref], w["G"][pos[j]]) and not codes[n_ref:].any()
+            Q, A, N = eng.block_gram(b, m)
+            Qo, Ao, No = O.gram_int(w["bed"], n_ref, pos)
+            assert np.array_equal(Q, Qo) and np.array_equal(A, Ao) and np.array_equal(N, No)
+        bs, bl, _, _ = O.est(w["bed"], n_ref, 10_000, 1e-4, *csr, threads=2, mode=O.MODE_EXACT)
+        assert relmax(r["beta_s"][0], bs) <= 1e-10
+    finally:
+        eng.close()
 
 
 @pytest.mark.parametrize("mode", ["dbslmm", "lmm"])
