@@ -136,9 +136,11 @@ struct dbslmm_b200_handle {
     int defer_max_ctas = 296;                    // steps with at most this many CTAs take their diagonal tile first (see StepList)
     // panel step kernel: TMA/mbarrier pipeline (default) or the cp.async version (DBSLMM_B200_PANEL=legacy)
     int upload_bulk_first = 1;                   // streaming fit: bulk regions sent before the big classes (see make_batches)
-    // correlation builder for blocks without missing calls: fused unpack + Gram from packed 2-bit rows (default) or the
-    // int8-row kernel of round 1 (DBSLMM_B200_GRAM=codes)
-    bool gram_packed = true;
+    // correlation builder for blocks without missing calls: the int8-row kernel fed by the decoder (default), or the fused
+    // unpack + Gram from packed 2-bit rows (DBSLMM_B200_GRAM=packed).  Measured on C3 / C5: 1.8 / 10.8 ms against 3.9 / 34.7 ms --
+    // expanding the operands in shared memory (8 unpack warps, generic-proxy stores + fence.proxy.async per K step) costs
+    // more than the L2 traffic it saves, so the fused kernel stays an experiment.
+    bool gram_packed = false;
     bool panel_tma = true;
     int tpc_max = 4, tpc_waves = 2;              // items per CTA: at most tpc_max, and only while a step keeps >= tpc_waves waves of CTAs
     int tmap_perm = -1;                          // 1: 4-D row-permuting tensor maps, 0: plain 2-D maps (driver refused), -1: not probed yet
@@ -341,21 +343,95 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
     // .bed row read + what the packer (2-bit rows, n_pad / 4 bytes) or the decoder (int8 rows) writes; mask rows: see fit
     P.decode_bytes = (double)goff * ((double)h->pitch + (h->gram_packed ? (double)h->n_pad / 4.0 : (double)h->n_pad));
 
+    // ---- the per-SNP part of the blob (block descriptors, .bed row / code row maps, z-scores) has a size that is known
+    // now: it is filled by a few host threads WHILE this thread builds the tile and step lists, which follow it in the blob
+    size_t o = 0;
+    auto place = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
+    P.o_blocks = place(sizeof(BlockDesc) * (size_t)nb);
+    P.o_rowsrc = place(sizeof(uint32_t) * (size_t)goff);
+    P.o_crow = place(sizeof(int32_t) * (size_t)goff);
+    P.o_mrow = place(sizeof(int32_t) * (size_t)goff);
+    P.o_z = place(sizeof(double) * (size_t)goff);
+    size_t n_t1 = 0, n_t2 = 0, n_steps_tiles = 0, n_diag_max = 0;
+    for (int b = 0; b < nb; ++b) {
+        const BlockDesc& d = P.blocks[b];
+        const size_t nt = (size_t)(d.mp + 127) / 128, nt64 = (size_t)(d.mp + 63) / 64;
+        n_t1 += nt * (nt + 1) / 2;
+        n_t2 += nt64 * (nt64 / 2 + 1);
+        const int K = (d.mp + 63) / 64;
+        n_diag_max += (size_t)K;
+        for (int k = 0; k < K; ++k) {
+            const int wk = std::min(64, d.mp - 64 * k);
+            n_steps_tiles += (size_t)((d.nrows - (64 * k + wk) + 127) / 128);
+        }
+    }
+    // upper bound of the list part: a split-K step has at most max(#tiles, 2 n_sm) items
+    const size_t n_panel_max = n_steps_tiles + (size_t)2 * h->n_sm * kMaxBatches * (size_t)(P.max_mp / 64 + 2);
+    const size_t lists_max = sizeof(GramTile) * (n_t1 + n_t2) + sizeof(int32_t) * ((size_t)nb + n_diag_max) + sizeof(int4) * n_panel_max +
+                             sizeof(CUtensorMap) * (size_t)nb + 8 * 256;
+    if (h->h_blob.ensure(o + lists_max + 256) != cudaSuccess) return fail(h, DBSLMM_B200_ERR_NOMEM, "pinned plan buffer");
+    struct { uint8_t* p; uint8_t* data() const { return p; } } blob{(uint8_t*)h->h_blob.p};
+    std::memcpy(blob.data() + P.o_blocks, P.blocks.data(), sizeof(BlockDesc) * (size_t)nb);
+    uint32_t* rs = reinterpret_cast<uint32_t*>(blob.data() + P.o_rowsrc);
+    int32_t* rcr = reinterpret_cast<int32_t*>(blob.data() + P.o_crow);
+    int32_t* rmr = reinterpret_cast<int32_t*>(blob.data() + P.o_mrow);
+    double* z = reinterpret_cast<double*>(blob.data() + P.o_z);
+    std::vector<std::thread> fill_threads;
+    std::atomic<int> fill_bad{0};
+    struct Joiner { std::vector<std::thread>& t; ~Joiner() { for (std::thread& x : t) if (x.joinable()) x.join(); } } joiner{fill_threads};
+    // per-SNP rows (source .bed row, SNP-row index, z-score): the only O(#SNPs) part of the plan, filled by a few
+    // host threads, each owning a contiguous range of blocks; the .bed row range check rides along
+    {
+        const int nthr = (int)std::max<int64_t>(1, std::min<int64_t>({8, (int64_t)std::thread::hardware_concurrency(), goff / 65536}));
+        auto fill = [&, rs, rcr, rmr, z](int b0, int b1) {
+            int oob = 0;
+            for (int b = b0; b < b1; ++b) {
+                const BlockDesc& d = P.blocks[b];
+                const int32_t* sp = a->s_pos + a->s_off[b];
+                const double* sz = a->s_z + a->s_off[b];
+                uint32_t* rsb = rs + d.goff;
+                int32_t* rcb = rcr + d.goff;
+                int32_t* rmb = rmr + d.goff;
+                double* zb = z + d.goff;
+                for (int j = 0; j < d.ms; ++j) {
+                    const int32_t p = sp[j];
+                    oob |= (p < 0) | (p >= n_snp);
+                    rsb[j] = (uint32_t)p; rcb[j] = d.croff + j; rmb[j] = d.croff + d.m + j; zb[j] = sz[j];
+                }
+                if (d.m > d.ms) {
+                    const int32_t* lp = a->l_pos + a->l_off[b];
+                    const double* lz = a->l_z + a->l_off[b];
+                    for (int j = d.ms; j < d.m; ++j) {
+                        const int32_t p = lp[j - d.ms];
+                        oob |= (p < 0) | (p >= n_snp);
+                        rsb[j] = (uint32_t)p; rcb[j] = d.croff + j; rmb[j] = d.croff + d.m + j; zb[j] = lz[j - d.ms];
+                    }
+                }
+            }
+            if (oob) fill_bad.store(1);
+        };
+        if (nthr == 1) fill(0, nb);
+        else {
+            std::vector<std::thread>& th = fill_threads;
+            int b0 = 0;
+            for (int t = 0; t < nthr; ++t) {
+                // cut at equal SNP counts (block-index order; goff is monotone only in the resident layout, so count)
+                int b1 = b0;
+                int64_t acc = 0;
+                const int64_t share = (goff + nthr - 1) / nthr;
+                while (b1 < nb && (t == nthr - 1 || acc < share)) acc += P.blocks[b1++].m;
+                th.emplace_back(fill, b0, b1);
+                b0 = b1;
+            }
+        }
+    }
     if (tr) tr->mark("  plan: layout");
     // Gram tiles in batch order, big blocks first inside a batch: the lower triangle as 128 x 128 tiles for the one-plane
     // kernel and as 64-row x 128-column tiles for the four-plane kernel (every block is in both lists; the kernels pick
     // their blocks by the device-side flag)
     std::vector<GramTile> tiles_plain, tiles_miss;
-    {
-        size_t n1 = 0, n2 = 0;
-        for (int b = 0; b < nb; ++b) {
-            const size_t nt = (size_t)(P.blocks[b].mp + 127) / 128, nt64 = (size_t)(P.blocks[b].mp + 63) / 64;
-            n1 += nt * (nt + 1) / 2;
-            n2 += nt64 * (nt64 / 2 + 1);
-        }
-        tiles_plain.reserve(n1);
-        tiles_miss.reserve(n2);
-    }
+    tiles_plain.reserve(n_t1);
+    tiles_miss.reserve(n_t2);
     for (Batch& B : P.batches) {
         B.tile0 = (int32_t)tiles_plain.size();
         B.mtile0 = (int32_t)tiles_miss.size();
@@ -385,8 +461,8 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
     // Cholesky step lists per batch
     std::vector<int32_t> diag_items;
     std::vector<int4> panel_items;
-    diag_items.reserve((size_t)(goff / 64 + 2 * nb + 16));
-    panel_items.reserve((size_t)(goff / 64 + 2 * nb + 16) * 6);
+    diag_items.reserve(n_diag_max);
+    panel_items.reserve(n_panel_max);
     int32_t n_groups = 0;
     const int kTargetCtas = 2 * h->n_sm;              // 2 panel CTAs per SM
     for (Batch& B : P.batches) {
@@ -448,14 +524,7 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
     }
 
     if (tr) tr->mark("  plan: step lists");
-    // ---- pack the blob
-    size_t o = 0;
-    auto place = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
-    P.o_blocks = place(sizeof(BlockDesc) * (size_t)nb);
-    P.o_rowsrc = place(sizeof(uint32_t) * (size_t)goff);
-    P.o_crow = place(sizeof(int32_t) * (size_t)goff);
-    P.o_mrow = place(sizeof(int32_t) * (size_t)goff);
-    P.o_z = place(sizeof(double) * (size_t)goff);
+    // ---- the list part of the blob
     P.o_tiles_plain = place(sizeof(GramTile) * tiles_plain.size());
     P.o_tiles_miss = place(sizeof(GramTile) * tiles_miss.size());
     P.o_order = place(sizeof(int32_t) * (size_t)nb);
@@ -465,63 +534,10 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
     P.lmaps_base = nullptr;
     P.n_groups = n_groups;
     P.blob_bytes = o;
-    // fill the pinned staging buffer in place (no intermediate copy; alignment gaps are never read)
-    if (h->h_blob.ensure(o + 256) != cudaSuccess) return fail(h, DBSLMM_B200_ERR_NOMEM, "pinned plan buffer");
-    struct { uint8_t* p; uint8_t* data() const { return p; } } blob{(uint8_t*)h->h_blob.p};
-    std::memcpy(blob.data() + P.o_blocks, P.blocks.data(), sizeof(BlockDesc) * (size_t)nb);
-    uint32_t* rs = reinterpret_cast<uint32_t*>(blob.data() + P.o_rowsrc);
-    int32_t* rcr = reinterpret_cast<int32_t*>(blob.data() + P.o_crow);
-    int32_t* rmr = reinterpret_cast<int32_t*>(blob.data() + P.o_mrow);
-    double* z = reinterpret_cast<double*>(blob.data() + P.o_z);
-    // per-SNP rows (source .bed row, SNP-row index, z-score): the only O(#SNPs) part of the plan, filled by a few
-    // host threads, each owning a contiguous range of blocks; the .bed row range check rides along
-    {
-        const int nthr = (int)std::max<int64_t>(1, std::min<int64_t>({8, (int64_t)std::thread::hardware_concurrency(), goff / 65536}));
-        std::atomic<int> bad{0};
-        auto fill = [&](int b0, int b1) {
-            int oob = 0;
-            for (int b = b0; b < b1; ++b) {
-                const BlockDesc& d = P.blocks[b];
-                const int32_t* sp = a->s_pos + a->s_off[b];
-                const double* sz = a->s_z + a->s_off[b];
-                uint32_t* rsb = rs + d.goff;
-                int32_t* rcb = rcr + d.goff;
-                int32_t* rmb = rmr + d.goff;
-                double* zb = z + d.goff;
-                for (int j = 0; j < d.ms; ++j) {
-                    const int32_t p = sp[j];
-                    oob |= (p < 0) | (p >= n_snp);
-                    rsb[j] = (uint32_t)p; rcb[j] = d.croff + j; rmb[j] = d.croff + d.m + j; zb[j] = sz[j];
-                }
-                if (d.m > d.ms) {
-                    const int32_t* lp = a->l_pos + a->l_off[b];
-                    const double* lz = a->l_z + a->l_off[b];
-                    for (int j = d.ms; j < d.m; ++j) {
-                        const int32_t p = lp[j - d.ms];
-                        oob |= (p < 0) | (p >= n_snp);
-                        rsb[j] = (uint32_t)p; rcb[j] = d.croff + j; rmb[j] = d.croff + d.m + j; zb[j] = lz[j - d.ms];
-                    }
-                }
-            }
-            if (oob) bad.store(1);
-        };
-        if (nthr == 1) fill(0, nb);
-        else {
-            std::vector<std::thread> th;
-            int b0 = 0;
-            for (int t = 0; t < nthr; ++t) {
-                // cut at equal SNP counts (block-index order; goff is monotone only in the resident layout, so count)
-                int b1 = b0;
-                int64_t acc = 0;
-                const int64_t share = (goff + nthr - 1) / nthr;
-                while (b1 < nb && (t == nthr - 1 || acc < share)) acc += P.blocks[b1++].m;
-                th.emplace_back(fill, b0, b1);
-                b0 = b1;
-            }
-            for (std::thread& x : th) x.join();
-        }
-        if (bad.load()) return fail(h, DBSLMM_B200_ERR_ARG, "s_pos / l_pos out of range of the loaded .bed");
-    }
+    if (o + 256 > h->h_blob.cap) return fail(h, DBSLMM_B200_ERR_NOMEM, "pinned plan buffer: list bound exceeded");
+    for (std::thread& x : fill_threads) x.join();
+    fill_threads.clear();
+    if (fill_bad.load()) return fail(h, DBSLMM_B200_ERR_ARG, "s_pos / l_pos out of range of the loaded .bed");
     if (tr) tr->mark("  plan: per-SNP arrays");
     if (!tiles_plain.empty()) std::memcpy(blob.data() + P.o_tiles_plain, tiles_plain.data(), sizeof(GramTile) * tiles_plain.size());
     if (!tiles_miss.empty()) std::memcpy(blob.data() + P.o_tiles_miss, tiles_miss.data(), sizeof(GramTile) * tiles_miss.size());
@@ -712,7 +728,7 @@ int dbslmm_b200_create(int device, dbslmm_b200_handle** out) {
     if (const char* e = std::getenv("DBSLMM_B200_DEFER_CTAS")) h->defer_max_ctas = std::atoi(e);
     else h->defer_max_ctas = 2 * h->n_sm;
     if (const char* e = std::getenv("DBSLMM_B200_UPLOAD_BULK_FIRST")) h->upload_bulk_first = std::atoi(e);
-    if (const char* e = std::getenv("DBSLMM_B200_GRAM")) h->gram_packed = (std::strcmp(e, "codes") != 0);
+    if (const char* e = std::getenv("DBSLMM_B200_GRAM")) h->gram_packed = (std::strcmp(e, "packed") == 0);
     if (const char* e = std::getenv("DBSLMM_B200_PANEL")) h->panel_tma = (std::strcmp(e, "legacy") != 0);
     if (const char* e = std::getenv("DBSLMM_B200_TPC")) {         // "max[,waves]"
         int a = 0, b = 0;

@@ -28,9 +28,9 @@ MODES = {
     "tma_one_item_per_cta": {"DBSLMM_B200_TPC": "1"},
     "tma_plain_2d_tensor_maps": {"DBSLMM_B200_TMAP_PERM": "0", "DBSLMM_B200_TPC": "2,0"},
     "legacy_cp_async_panel_kernel": {"DBSLMM_B200_PANEL": "legacy"},
-    # the correlation builder of blocks without missing calls: fused unpack + Gram from packed 2-bit rows (default) or the
-    # int8-row kernel fed by the decoder
-    "int8_row_gram": {"DBSLMM_B200_GRAM": "codes"},
+    # the correlation builder of blocks without missing calls: the int8-row kernel fed by the decoder (default) or the
+    # experimental fused unpack + Gram from packed 2-bit rows
+    "fused_unpack_gram_from_packed_rows": {"DBSLMM_B200_GRAM": "packed"},
 }
 KEYS = sorted({k for m in MODES.values() for k in m})
 

@@ -68,13 +68,11 @@ def test_decode_gram_sigma(case, engine):
         pos = block_pos(w, b)
         miss = bool((w["G"][pos] < 0).any())
         for j in sorted({0, m // 2, m - 1}):
-            if not miss:
-                continue         # int8 rows exist only for blocks with missing calls (the others are unpacked in shared memory:
-                                 # their decode is checked through the bit-exact Q below and in test_int8_rows_of_the_decoder)
             codes = engine.row_codes(b, j, n_pad)
             assert np.array_equal(codes[:n_ref], Gz[pos[j]]) and not codes[n_ref:].any()
-            mk = engine.row_codes(b, j, n_pad, plane=1)
-            assert np.array_equal(mk[:n_ref], (w["G"][pos[j]] >= 0).astype(np.int8)) and not mk[n_ref:].any()
+            if miss:
+                mk = engine.row_codes(b, j, n_pad, plane=1)
+                assert np.array_equal(mk[:n_ref], (w["G"][pos[j]] >= 0).astype(np.int8)) and not mk[n_ref:].any()
         Q, A, N = engine.block_gram(b, m)
         Qo, Ao, No = O.gram_int(w["bed"], n_ref, pos)
         assert np.array_equal(Q, Qo), (name, b)
@@ -84,31 +82,36 @@ def test_decode_gram_sigma(case, engine):
         assert np.array_equal(S, S.T)
 
 
-def test_int8_rows_of_the_decoder():
-    """DBSLMM_B200_GRAM=codes: every block goes through the decoder's int8 rows (the round-1 path, still the path of blocks
-    with missing calls): codes of every plane bit for bit, Q / A / N and betas as in the default path."""
-    sizes, n_ref, missr = CASES["odd_pitch"]
-    w = synth.make_workload(99, sizes, n_ref, missing_rate=0.0, frac_large=0.02)
-    os.environ["DBSLMM_B200_GRAM"] = "codes"
+def test_fused_unpack_gram_is_bit_exact():
+    """DBSLMM_B200_GRAM=packed (experimental): blocks without missing calls are built from 2-bit rows packed in plan order
+    and expanded to int8 in shared memory; blocks with missing calls still take the decoder's int8 rows.  Q / A / N bit for
+    bit and betas as in the default path, on a panel that mixes both kinds of blocks."""
+    sizes, n_ref = [90, 260, 33, 140], 125 * 4 - 3
+    w = synth.make_workload(99, sizes, n_ref, missing_rate=0.01, frac_large=0.02)
+    G = w["G"].copy()
+    G[90:350] = np.where(G[90:350] < 0, 1, G[90:350])            # block 1 has no missing call
+    bed = synth.pack_bed(G)
+    os.environ["DBSLMM_B200_GRAM"] = "packed"
     try:
         eng = _abi.Engine(0)
     finally:
         os.environ.pop("DBSLMM_B200_GRAM", None)
     try:
-        eng.load_bed(w["bed"], n_ref)
         csr = (w["s_off"], w["s_pos"], w["s_z"], w["l_off"], w["l_pos"], w["l_z"])
-        r = eng.fit(*csr, sigma_s=[1e-4], n_obs=10_000, flags=_abi.FLAG_KEEP_INT_GRAM)
-        n_pad = (n_ref + 127) // 128 * 128
-        for b, m in enumerate(w["block_sizes"]):
-            pos = block_pos(w, b)
-            for j in (0, m // 2, m - 1):
-                codes = eng.row_codes(b, j, n_pad)
-                assert np.array_equal(codes[:n_ref], w["G"][pos[j]]) and not codes[n_ref:].any()
-            Q, A, N = eng.block_gram(b, m)
-            Qo, Ao, No = O.gram_int(w["bed"], n_ref, pos)
-            assert np.array_equal(Q, Qo) and np.array_equal(A, Ao) and np.array_equal(N, No)
-        bs, bl, _, _ = O.est(w["bed"], n_ref, 10_000, 1e-4, *csr, threads=2, mode=O.MODE_EXACT)
-        assert relmax(r["beta_s"][0], bs) <= 1e-10
+        for streaming in (False, True):
+            if streaming:
+                r = eng.fit(*csr, sigma_s=[1e-4], n_obs=10_000, flags=_abi.FLAG_KEEP_INT_GRAM, bed=bed, n_ref=n_ref)
+            else:
+                eng.load_bed(bed, n_ref)
+                r = eng.fit(*csr, sigma_s=[1e-4], n_obs=10_000, flags=_abi.FLAG_KEEP_INT_GRAM)
+            assert r["timing"]["n_blocks_missing"] == 3
+            for b, m in enumerate(w["block_sizes"]):
+                pos = block_pos(w, b)
+                Q, A, N = eng.block_gram(b, m)
+                Qo, Ao, No = O.gram_int(bed, n_ref, pos)
+                assert np.array_equal(Q, Qo) and np.array_equal(A, Ao) and np.array_equal(N, No)
+            bs, bl, _, _ = O.est(bed, n_ref, 10_000, 1e-4, *csr, threads=2, mode=O.MODE_EXACT)
+            assert relmax(r["beta_s"][0], bs) <= 1e-10 and relmax(r["beta_l"][0], bl) <= 1e-10
     finally:
         eng.close()
 
