@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libdbslmm_b200.so")
+LIB_PATH = os.environ.get("DBSLMM_B200_LIB") or os.path.join(_PKG, "libdbslmm_b200.so")      # override: kernel-variant builds (tools/build_variants.sh)
 
 SOLVER_CHOLESKY = 0
 SOLVER_PCG = 1

@@ -25,6 +25,7 @@
 // backsolve_kernel then solves L^T x = y per block and writes beta = x / sqrt(N).
 // Matrices are row-major, lower triangle, ld = mp (m padded to 8 with identity rows).
 #include <algorithm>
+#include <cstdlib>
 #include <cooperative_groups.h>
 #include "common.cuh"
 #include "kernels.h"
@@ -45,6 +46,19 @@ static constexpr int SMEM_PIPE = NST * STAGE * 8;
 // The epilogue re-uses the three pipeline stages: one holds W_kk, the other two the two 64-row halves of L_ik.
 static_assert(NB * LDW == STAGE, "a 64 x LDW epilogue tile must fill exactly one pipeline stage");
 static constexpr int SMEM_CHOL = SMEM_PIPE;
+
+// W_kk = L_kk^-1 travels from the diagonal-tile code to the panel CTAs as a ready-made shared-memory IMAGE: the ten
+// 16x16 blocks of its lower triangle (block (rb, cb), cb <= rb, at 2 KB * (rb (rb + 1) / 2 + cb)), each block in the
+// format a 128-byte-swizzled, row-permuting TMA box would have produced (8-row groups of 1 KB, rows of a group in the
+// order 0,2,4,6,1,3,5,7, 16-byte chunks XOR-ed with the row slot).  One 1-D bulk copy of 20 KB brings it in, and the
+// TRSM reads it with the same conflict-free 128-bit fragment loads as the ring boxes.
+static constexpr int W_IMG_DOUBLES = 10 * 256;
+static constexpr int W_IMG_BYTES = W_IMG_DOUBLES * 8;
+__host__ __device__ __forceinline__ int w_img_off(int a, int b) {       // element (row a, column b), (b >> 4) <= (a >> 4)
+    const int rb = a >> 4, cb = b >> 4;
+    const int g = a & 7, sig = (g >> 1) | ((g & 1) << 2);
+    return (rb * (rb + 1) / 2 + cb) * 256 + ((a >> 3) & 1) * 128 + sig * 16 + ((((b & 15) >> 1) ^ sig) << 1) + (b & 1);
+}
 
 // acc (16 rows x 64 cols per warp) += P[r0.., 0:K] * Q[q0.., 0:K]^T, both row-major with K contiguous.
 // prow/qrow = number of valid rows (others are zero-filled).  `wrow` = this warp's 16-row slot of the macro tile.
@@ -88,7 +102,8 @@ __device__ __forceinline__ void gemm_nt_core(const double* __restrict__ Pg, cons
         for (int u = 0; u < 8; ++u) {
             const int idx = tid + u * CHOL_THREADS;
             const int row = idx >> 5, ch = (idx & 31) * 2;
-            cp_async16(Ws + row * LDW + ch, wsrc + row * NB + ch, true);
+            const bool v = (ch >> 4) <= (row >> 4);                  // 16x16 blocks above the diagonal: zero-filled
+            cp_async16(Ws + row * LDW + ch, wsrc + (v ? w_img_off(row, ch) : 0), v);
         }
     };
 
@@ -150,11 +165,12 @@ __device__ __forceinline__ void gemm_nt_core(const double* __restrict__ Pg, cons
 #define DIAG_STAMP(n)               // probe hook (tools/diag_probe.cu records clock64() here)
 #endif
 static constexpr int DT = NB + 1;   // odd stride: conflict-free row and column walks in FP64
-// barrier of the 256 threads that run diag_body (the whole CTA, except in the TMA panel kernel, whose ninth warp -- the
-// TMA producer -- never enters)
-__device__ __forceinline__ void diag_sync() { asm volatile("bar.sync 4, 256;" ::: "memory"); }
-static constexpr int DP = 33;       // stride of the 32x32 product scratch
-static constexpr int SMEM_DIAG = (2 * NB * DT + 32 * DP + NB) * 8;
+// barrier of the NT threads that run diag_body (the whole CTA)
+template <int NT>
+__device__ __forceinline__ void diag_sync() { asm volatile("bar.sync 4, %0;" ::"n"(NT) : "memory"); }
+// T and W tiles + 1/diag.  The 32x32 product scratch of the W assembly lives in the (otherwise unused) upper-right
+// quarter of the T tile: rows 0..31, columns 32..63.
+static constexpr int SMEM_DIAG = (2 * NB * DT + NB) * 8;
 
 // One 8x8 output tile on the FP64 tensor pipe: C = scale * A[0:8, kb:ke] B[kb:ke, 0:8], A row-major (stride sa),
 // B row-major k x n (stride sb), all in shared memory; kb, ke multiples of 4.  Whole warp.
@@ -177,16 +193,20 @@ __device__ __forceinline__ void mm_tile8(const double* A, int sa, const double* 
     C[g * sc + 2 * t + 1] = scale * c1;
 }
 
-// `w_ready()` runs (all threads) once the dense W tile is in global memory, before the L / W^T tile is written back:
+// `w_ready()` runs (all threads) once the W image is in global memory, before the L / W^T tile is written back:
 // the diagonal CTAs of a chain-bound step raise their flag there -- the waiting TRSMs need W only.
-template <class WReady>
+// NT = threads of the calling CTA (256, or 128 in the 64-row panel kernel); all of them must call.
+template <int NT, class WReady>
 __device__ __forceinline__ void diag_body(const BlockDesc& bd, int blk, int k, const double* __restrict__ sigma,
                                           double* __restrict__ Lbuf, double* __restrict__ wbuf, double ridge,
                                           int32_t* __restrict__ status, double* smem, WReady&& w_ready) {
+    static_assert(NT == 128 || NT == 256, "diag_body: 4 or 8 warps");
+    constexpr int NWARP = NT / 32;
     double* T = smem;                        // [64][DT] tile, becomes L (lower)
     double* Wf = T + NB * DT;                // [64][DT] W = L^-1 (lower)
-    double* Pm = Wf + NB * DT;               // [32][DP] product scratch of the W assembly
-    double* dinv_s = Pm + 32 * DP;           // [64] 1 / L_ii
+    double* dinv_s = Wf + NB * DT;           // [64] 1 / L_ii
+    double* Pm = T + 32;                     // [32][DT] product scratch of the W assembly (upper-right quarter of T)
+    constexpr int DP = DT;
     const int pc0 = k * NB;
     const int wk = min(NB, bd.mp - pc0);
     const int ld = bd.ld;
@@ -196,29 +216,32 @@ __device__ __forceinline__ void diag_body(const BlockDesc& bd, int blk, int k, c
     DIAG_STAMP(0);
 
     {
-        // all 16 loads of a thread are issued back to back (independent), then consumed
-        double tv[16];
+        // loads are issued 16 at a time per thread, back to back (independent), then consumed
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-            const int idx = tid + u * CHOL_THREADS;
-            const int a = idx >> 6, b = idx & 63;
-            const bool ld_it = (a < wk) && (b <= a);
-            tv[u] = ld_it ? __ldcg(src + (size_t)(pc0 + a) * ld + pc0 + b) : 0.0;
-        }
+        for (int u0 = 0; u0 < NB * NB / NT; u0 += 16) {
+            double tv[16];
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-            const int idx = tid + u * CHOL_THREADS;
-            const int a = idx >> 6, b = idx & 63;
-            double v = tv[u];
-            if (a == b) {
-                if (a >= wk) v = 1.0;                                   // identity padding
-                else if (k == 0 && pc0 + a < bd.ms) v += ridge;
+            for (int u = 0; u < 16; ++u) {
+                const int idx = tid + (u0 + u) * NT;
+                const int a = idx >> 6, b = idx & 63;
+                const bool ld_it = (a < wk) && (b <= a);
+                tv[u] = ld_it ? __ldcg(src + (size_t)(pc0 + a) * ld + pc0 + b) : 0.0;
             }
-            T[a * DT + b] = v;
-            Wf[a * DT + b] = 0.0;
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const int idx = tid + (u0 + u) * NT;
+                const int a = idx >> 6, b = idx & 63;
+                double v = tv[u];
+                if (a == b) {
+                    if (a >= wk) v = 1.0;                                   // identity padding
+                    else if (k == 0 && pc0 + a < bd.ms) v += ridge;
+                }
+                T[a * DT + b] = v;
+                Wf[a * DT + b] = 0.0;
+            }
         }
     }
-    diag_sync();
+    diag_sync<NT>();
 
     bool bad = false;
     DIAG_STAMP(1);
@@ -253,7 +276,7 @@ __device__ __forceinline__ void diag_body(const BlockDesc& bd, int blk, int k, c
                 for (int c = 0; c < 16; ++c) T[(o + r) * DT + o + c] = (c <= r) ? row[c] : 0.0;
             }
         }
-        diag_sync();                                   // [A] L16 and 1/diag are in shared memory
+        diag_sync<NT>();                               // [A] L16 and 1/diag are in shared memory
         DIAG_STAMP(2 + 5 * jb);
         const int nrem = 48 - o;                           // rows below this sub-block
         if (warp == 1) {
@@ -297,32 +320,34 @@ __device__ __forceinline__ void diag_body(const BlockDesc& bd, int blk, int k, c
 #pragma unroll
             for (int c = 0; c < 16; ++c) T[i * DT + o + c] = x[c];
         }
-        diag_sync();                                   // [B] sub-panel solved
+        diag_sync<NT>();                               // [B] sub-panel solved
         DIAG_STAMP(3 + 5 * jb);
         if (jb == 3) break;
-        // ---- next 16x16 diagonal sub-block first, one entry per thread; then warp 0 factors it while the other
-        // warps update the rest of the trailing matrix in its shadow (the next barrier [A] publishes that part)
-        if (tid >= 32 && tid < 32 + 136) {
-            // entry e of the packed lower triangle -> (i, c)
-            const int e = tid - 32;
-            int ri = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
-            while ((ri + 1) * (ri + 2) / 2 <= e) ++ri;
-            while (ri * (ri + 1) / 2 > e) --ri;
-            const int ci = e - ri * (ri + 1) / 2;
-            const double* xi = T + (o + 16 + ri) * DT + o;
-            const double* xc = T + (o + 16 + ci) * DT + o;
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        // ---- next 16x16 diagonal sub-block first (136 packed entries over the threads of warps 1..); then warp 0
+        // factors it while the other warps update the rest of the trailing matrix in its shadow (the next barrier [A]
+        // publishes that part)
+        if (tid >= 32) {
+            for (int e = tid - 32; e < 136; e += NT - 32) {
+                // entry e of the packed lower triangle -> (i, c)
+                int ri = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+                while ((ri + 1) * (ri + 2) / 2 <= e) ++ri;
+                while (ri * (ri + 1) / 2 > e) --ri;
+                const int ci = e - ri * (ri + 1) / 2;
+                const double* xi = T + (o + 16 + ri) * DT + o;
+                const double* xc = T + (o + 16 + ci) * DT + o;
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
-            for (int kk = 0; kk < 16; kk += 4) {
-                a0 += xi[kk] * xc[kk]; a1 += xi[kk + 1] * xc[kk + 1];
-                a2 += xi[kk + 2] * xc[kk + 2]; a3 += xi[kk + 3] * xc[kk + 3];
+                for (int kk = 0; kk < 16; kk += 4) {
+                    a0 += xi[kk] * xc[kk]; a1 += xi[kk + 1] * xc[kk + 1];
+                    a2 += xi[kk + 2] * xc[kk + 2]; a3 += xi[kk + 3] * xc[kk + 3];
+                }
+                T[(o + 16 + ri) * DT + o + 16 + ci] -= (a0 + a1) + (a2 + a3);
             }
-            T[(o + 16 + ri) * DT + o + 16 + ci] -= (a0 + a1) + (a2 + a3);
         }
-        diag_sync();                                   // [C] next diagonal sub-block updated
+        diag_sync<NT>();                               // [C] next diagonal sub-block updated
         if (warp != 0) {
             const int h = 32 - o;                          // rows o+32.., columns o+16..row
-            for (int idx = tid - 32; idx < h * 64; idx += CHOL_THREADS - 32) {
+            for (int idx = tid - 32; idx < h * 64; idx += NT - 32) {
                 const int i = o + 32 + (idx >> 6), c = o + 16 + (idx & 63);
                 if (c <= i) {
                     const double* xi = T + i * DT + o;
@@ -341,42 +366,52 @@ __device__ __forceinline__ void diag_body(const BlockDesc& bd, int blk, int k, c
     }
     if (warp == 0 && __any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&status[blk], 1);
     // ---- W = L^-1 from the four 16x16 inverses, two levels of [[A,0],[B,C]]^-1 = [[A^-1,0],[-C^-1 B A^-1, C^-1]];
-    // the small products run on the FP64 tensor pipe, one or two 8x8 output tiles per warp and stage
+    // the small products run on the FP64 tensor pipe, 8x8 output tiles dealt out to the warps.  (The last barrier [B]
+    // ordered every write of the loop before this point; the scratch Pm overlays entries of T that hold zeros and are
+    // never read again.)
     {
-        // level 1: both 32x32 diagonal blocks at once (8 tiles = 8 warps).  P = B A^-1 (16x16 each), then W21 = -C^-1 P
-        const int half = warp >> 2, ob = 32 * half;
-        const int r0 = 8 * ((warp >> 1) & 1), c0 = 8 * (warp & 1);
-        // A^-1 is lower triangular: only k >= c0 contributes
-        mm_tile8(T + (ob + 16 + r0) * DT + ob, DT, Wf + ob * DT + ob + c0, DT, c0, 16, Pm + (16 * half + r0) * DP + c0, DP, 1.0, lane);
-        diag_sync();
-        // C^-1 is lower triangular: only k <= r0 + 7 contributes
-        mm_tile8(Wf + (ob + 16 + r0) * DT + ob + 16, DT, Pm + (16 * half) * DP + c0, DP, 0, r0 + 8, Wf + (ob + 16 + r0) * DT + ob + c0, DT, -1.0, lane);
-        diag_sync();
-        // level 2 (16 tiles, two per warp): P = L21 W11 (32x32), then W21 = -W22 P
+        // level 1: both 32x32 diagonal blocks at once (8 tiles).  P = B A^-1 (16x16 each), then W21 = -C^-1 P
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int tl = warp + 8 * u, R0 = 8 * (tl >> 2), C0 = 8 * (tl & 3);
+        for (int tl = warp; tl < 8; tl += NWARP) {
+            const int half = tl >> 2, ob = 32 * half;
+            const int r0 = 8 * ((tl >> 1) & 1), c0 = 8 * (tl & 1);
+            // A^-1 is lower triangular: only k >= c0 contributes
+            mm_tile8(T + (ob + 16 + r0) * DT + ob, DT, Wf + ob * DT + ob + c0, DT, c0, 16, Pm + (16 * half + r0) * DP + c0, DP, 1.0, lane);
+        }
+        diag_sync<NT>();
+#pragma unroll
+        for (int tl = warp; tl < 8; tl += NWARP) {
+            const int half = tl >> 2, ob = 32 * half;
+            const int r0 = 8 * ((tl >> 1) & 1), c0 = 8 * (tl & 1);
+            // C^-1 is lower triangular: only k <= r0 + 7 contributes
+            mm_tile8(Wf + (ob + 16 + r0) * DT + ob + 16, DT, Pm + (16 * half) * DP + c0, DP, 0, r0 + 8, Wf + (ob + 16 + r0) * DT + ob + c0, DT, -1.0, lane);
+        }
+        diag_sync<NT>();
+        // level 2 (16 tiles): P = L21 W11 (32x32), then W21 = -W22 P
+#pragma unroll
+        for (int tl = warp; tl < 16; tl += NWARP) {
+            const int R0 = 8 * (tl >> 2), C0 = 8 * (tl & 3);
             mm_tile8(T + (32 + R0) * DT, DT, Wf + C0, DT, C0, 32, Pm + R0 * DP + C0, DP, 1.0, lane);
         }
-        diag_sync();
+        diag_sync<NT>();
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int tl = warp + 8 * u, R0 = 8 * (tl >> 2), C0 = 8 * (tl & 3);
+        for (int tl = warp; tl < 16; tl += NWARP) {
+            const int R0 = 8 * (tl >> 2), C0 = 8 * (tl & 3);
             mm_tile8(Wf + (32 + R0) * DT + 32, DT, Pm + C0, DP, 0, R0 + 8, Wf + (32 + R0) * DT + C0, DT, -1.0, lane);
         }
-        diag_sync();
+        diag_sync<NT>();
     }
     DIAG_STAMP(22);
-    // ---- write back: W_kk as a dense 64x64 lower-triangular tile for the panel kernel of this step (which streams it
-    // into shared memory with cp.async; 8x8 blocks strictly above the diagonal are never read by the TRSM: skipped) ...
+    // ---- write back: W_kk as the shared-memory image the panel kernel of this step copies in with one bulk copy
+    // (w_img_off; 16x16 blocks above the diagonal do not exist in it) ...
     double* wb = wbuf + (size_t)blk * (NB * NB);
-    for (int idx = tid; idx < NB * NB; idx += CHOL_THREADS) {
+    for (int idx = tid; idx < NB * NB; idx += NT) {
         const int a = idx >> 6, b = idx & 63;
-        if ((b >> 3) <= (a >> 3)) wb[idx] = (b <= a) ? Wf[a * DT + b] : 0.0;
+        if ((b >> 4) <= (a >> 4)) wb[w_img_off(a, b)] = (b <= a) ? Wf[a * DT + b] : 0.0;
     }
     w_ready();
     // ... and the tile itself: lower = L_kk, strict upper = W_kk^T (used by the back substitution)
-    for (int idx = tid; idx < NB * NB; idx += CHOL_THREADS) {
+    for (int idx = tid; idx < NB * NB; idx += NT) {
         const int a = idx >> 6, b = idx & 63;
         if (a < wk && b < wk) Lb[(size_t)(pc0 + a) * ld + pc0 + b] = (b <= a) ? T[a * DT + b] : Wf[b * DT + a];
     }
@@ -390,7 +425,7 @@ chol_diag_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __restrict
     extern __shared__ __align__(16) double smem[];
     const int blk = items[blockIdx.x];
     const BlockDesc bd = blocks[blk];
-    diag_body(bd, blk, k, sigma, Lbuf, wbuf, ridge, status, smem, []() {});
+    diag_body<CHOL_THREADS>(bd, blk, k, sigma, Lbuf, wbuf, ridge, status, smem, []() {});
 }
 
 // Look-ahead SYRK of one 16-row slot WL of a 64-row half: acc2 (rows 16WL.., columns 0 .. 16WL+15, lower triangle
@@ -516,7 +551,8 @@ __device__ __forceinline__ void panel_body(const BlockDesc& bd, const int4 item,
         for (int u = 0; u < 8; ++u) {
             const int idx = tid + u * CHOL_THREADS;
             const int row = idx >> 5, ch = (idx & 31) * 2;
-            cp_async16(Ws + row * LDW + ch, wsrc + row * NB + ch, true);
+            const bool v = (ch >> 4) <= (row >> 4);
+            cp_async16(Ws + row * LDW + ch, wsrc + (v ? w_img_off(row, ch) : 0), v);
         }
         cp_async_commit();
         cp_async_wait<0>();
@@ -623,7 +659,7 @@ __device__ __forceinline__ void panel_body(const BlockDesc& bd, const int4 item,
         // macro tile 0: rows r0 .. r0+63 are the diagonal tile of panel k+1, which this step completed
         if (item.y == 0 && r0 < bd.mp && wk == NB) {
             __syncthreads();        // T_new is in L2 for the whole CTA; shared memory is free again
-            diag_body(bd, item.x, k + 1, sigma, Lbuf, wbuf + wpar_next, ridge, status, smem, []() {});
+            diag_body<CHOL_THREADS>(bd, item.x, k + 1, sigma, Lbuf, wbuf + wpar_next, ridge, status, smem, []() {});
         }
     }
 }
@@ -648,7 +684,7 @@ chol_panel_kernel(const BlockDesc* __restrict__ blocks, const int4* __restrict__
     if ((int)blockIdx.x < n_diag_first) {
         const int blk = diag_items[blockIdx.x];
         const BlockDesc bd = blocks[blk];
-        diag_body(bd, blk, k, sigma, Lbuf, wbuf + wpar, ridge, status, smem, [&]() {
+        diag_body<CHOL_THREADS>(bd, blk, k, sigma, Lbuf, wbuf + wpar, ridge, status, smem, [&]() {
             __threadfence();
             __syncthreads();
             if (threadIdx.x == 0) atomicExch(dflag + blk, k + 1);      // W_k is visible: the step's TRSMs may start
@@ -666,33 +702,63 @@ chol_panel_kernel(const BlockDesc* __restrict__ blocks, const int4* __restrict__
 // what the round-1 profile of that kernel showed -- 29 % of its warp samples sat in the per-chunk __syncthreads of the
 // cp.async ring, 8 % in cp.async.wait, every CTA paid two dependent descriptor loads, a cold ring and the HBM latency
 // of its Sigma tile before its first DMMA:
-//   * a ninth warp is the PRODUCER: it walks the CTA's items and feeds a 3-stage ring of [64 rows x 16 doubles] boxes
-//     (two for the 128 macro-tile rows, one for the 64 panel rows) with 4-D tiled TMA loads (cp.async.bulk.tensor,
+//   * thread 0 is the PRODUCER: it walks the CTA's items and feeds a 3-stage ring of [64 rows x 16 doubles] boxes
+//     (one per 64 macro-tile rows, one for the 64 panel rows) with 4-D tiled TMA loads (cp.async.bulk.tensor,
 //     SWIZZLE_128B; one tensor map per block, in the plan blob), completion on `full` mbarriers;
-//   * the eight CONSUMER warps never meet in the K loop: each waits for `full[s]`, reads its fragments, and releases
+//   * the CONSUMER warps never meet in the K loop: each waits for `full[s]`, reads its fragments, and releases
 //     the stage on `empty[s]` -- no CTA-wide barrier, no per-thread address arithmetic, no cp.async bookkeeping;
 //   * bank conflicts: the tensor map splits a row index r = 8a + 2b + c into (b, c, a) and lists b before c, so the
 //     rows of an 8-row group land in shared memory in the order 0,2,4,6,1,3,5,7; with the 128-byte swizzle the eight
 //     lanes of every 128-bit load phase (fragment rows g = 2j, 2j+1, four 16-byte chunks each) then hit eight distinct
-//     bank groups -- unpadded stages (24 KB instead of 36.9 KB);
-//   * W_kk arrives by TMA in its own four boxes while the ring is busy; the epilogue tiles (the two 64-row halves of
-//     -L_ik) reuse the ring boxes in the same permuted/swizzled format, so one address function serves all;
+//     bank groups -- unpadded stages;
+//   * W_kk arrives as a ready-made 20 KB image (w_img_off) by ONE bulk copy while the ring is busy; the epilogue tiles
+//     (the 64-row halves of -L_ik) reuse the ring boxes in the same permuted/swizzled format, so one address function
+//     serves all;
 //   * a CTA may own several consecutive items (macro tiles of the same block and step): the producer is then already
 //     waiting with the next item's loads, its Sigma tile has been pulled into L2 during the previous item, and W_kk
-//     is loaded once per block.
+//     is loaded once per block;
+//   * `pf` > 0: the rows of chunk c + pf are pulled into L2 (tensor prefetch) when chunk c is issued, so that the two
+//     chunks the ring keeps in flight come from L2 rather than from HBM.
+// Two shapes (template NG = 64-row warp groups per CTA):
+//   NG = 2: 128-row macro tiles, 256 threads, 93 KB, two CTAs per SM (128 registers);
+//   NG = 1:  64-row macro tiles, 128 threads, 69 KB, THREE CTAs per SM (168 registers, no spills).  The round-2 profile
+//            of the NG = 2 shape read: FP64 tensor pipe 66 % busy with each CTA "DMMA-ready" only 42 % of its time --
+//            exactly what two independent CTAs per SM give (1 - 0.58^2); what is missing is a third independent
+//            instruction stream per SM, not more warps per CTA.  Partially filled macro tiles also idle fewer warps.
 // ------------------------------------------------------------------------------------------
-static constexpr int TP_THREADS = CHOL_THREADS;          // eight warps; thread 0 doubles as the TMA producer
+#ifndef CHOL_VARIANT
+#define CHOL_VARIANT 0          // hook for tuning/debugging variants of this file (tools/build_variants.sh)
+#endif
 static constexpr int BOXB = NB * KC * 8;                 // bytes of one [64 x 16] box (8 KB)
-static constexpr int TP_NST = 3;                         // ring stages, 3 boxes each
-static constexpr int TP_RING = 3 * TP_NST * BOXB;        // 72 KB: also the two L halves of the epilogue (4 boxes each)
-static constexpr int SMEM_TP = TP_RING + 4 * BOXB + 1024;    // + W_kk (4 boxes) + alignment slack
-static_assert(SMEM_TP - 1024 >= SMEM_DIAG, "the fused diagonal factorisation reuses the panel kernel's shared memory");
+static constexpr int TP_NST = 3;                         // ring stages
 static_assert(KC == 16, "a box row is one 128-byte swizzle span");
+
+template <int NG>
+struct TpCfg {
+    static constexpr int NT = 128 * NG;                  // threads; thread 0 doubles as the TMA producer
+    static constexpr int NW = 4 * NG;                    // warps
+    static constexpr int TMR = 64 * NG;                  // rows per macro tile
+    static constexpr int SB = NG + 1;                    // boxes per stage: NG row boxes + the panel-row box
+    static constexpr int RING = TP_NST * SB * BOXB;      // also the NG L halves of the epilogue (4 boxes each)
+    static constexpr int SMEM = RING + W_IMG_BYTES + 1024;   // + W_kk image + alignment slack
+    static constexpr int MINB = (NG == 2) ? 2 : 3;       // CTAs per SM
+    static_assert(4 * NG <= TP_NST * SB, "the L halves must fit into the ring");
+    static_assert(RING + W_IMG_BYTES >= SMEM_DIAG, "the fused diagonal factorisation reuses the panel kernel's shared memory");
+};
 
 struct TpBars {
     uint64_t full[TP_NST], empty[TP_NST];
     uint64_t w_full, w_free, ring_free;
 };
+
+__device__ __forceinline__ void tma_prefetch_4d(const void* tmap, int32_t c0, int32_t c1, int32_t c2, int32_t c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(tmap), "r"(c0), "r"(c1),
+                 "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_2d(const void* tmap, int32_t x, int32_t y) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tmap), "r"(x), "r"(y) : "memory");
+}
 
 template <int WL>
 __device__ __forceinline__ void syrk_rows_pt(uint32_t Lh, uint32_t lrow, uint32_t x0, double (&acc2)[2][8][2]) {
@@ -712,16 +778,17 @@ __device__ __forceinline__ void syrk_rows_pt(uint32_t Lh, uint32_t lrow, uint32_
     }
 }
 
-// geometry of one item
+// geometry of one item (TMR = rows per macro tile)
 struct TpGeom {
     int pc0, wk, r0, prow, kb, ke, slice, nsl;
 };
+template <int TMR>
 __device__ __forceinline__ TpGeom tp_geom(const BlockDesc& bd, const int4 item, int k) {
     TpGeom q;
     q.pc0 = k * NB;
     q.wk = min(NB, bd.mp - q.pc0);
-    q.r0 = q.pc0 + q.wk + item.y * TM;
-    q.prow = min(TM, bd.nrows - q.r0);
+    q.r0 = q.pc0 + q.wk + item.y * TMR;
+    q.prow = min(TMR, bd.nrows - q.r0);
     q.slice = item.z & 0xFF;
     q.nsl = item.z >> 8;
     q.kb = (k * q.slice) / q.nsl * NB;
@@ -731,16 +798,19 @@ __device__ __forceinline__ TpGeom tp_geom(const BlockDesc& bd, const int4 item, 
 
 // lmaps: one 4-D tensor map per block over its matrix in Lbuf (dims {ld, 4, 2, rows/8}, box {16, 4, 2, 8}; `perm` = 0:
 // plain 2-D maps {ld, rows}, box {16, 64} -- rows in natural order, two-way bank conflicts -- if the driver refuses the
-// permuting strides).  wmap: the dense W tiles of `wbuf` as one tensor, same box.
+// permuting strides).
 // CTA c (after the n_diag_first diagonal CTAs): c < n_single owns item c; the others own `tpc` consecutive items.
-__global__ void __launch_bounds__(TP_THREADS, 2)
+template <int NG>
+__global__ void __launch_bounds__(TpCfg<NG>::NT, TpCfg<NG>::MINB)
 chol_panel_tma_kernel(const BlockDesc* __restrict__ blocks, const int4* __restrict__ items, int32_t n_items,
                       int32_t n_single, int32_t tpc, const int32_t* __restrict__ diag_items, int32_t n_diag_first,
-                      int32_t k, const CUtensorMap* __restrict__ lmaps, const __grid_constant__ CUtensorMap wmap,
-                      int32_t perm, int32_t wrow8_cur, const double* __restrict__ sigma, double* __restrict__ Lbuf,
+                      int32_t k, const CUtensorMap* __restrict__ lmaps, int32_t perm, int32_t pf,
+                      const double* __restrict__ sigma, double* __restrict__ Lbuf,
                       double* __restrict__ wbuf, int64_t wpar, int64_t wpar_next, double ridge,
                       double* __restrict__ scratch, int32_t* __restrict__ counters, int32_t group_base,
                       int32_t* __restrict__ status, int32_t* __restrict__ dflag, int32_t fuse_end) {
+    using C = TpCfg<NG>;
+    constexpr int NT = C::NT, NW = C::NW, TMR = C::TMR, SB = C::SB;
     extern __shared__ __align__(16) uint8_t tp_smem_raw[];
     __shared__ __align__(8) TpBars bars;
     __shared__ int s_last;
@@ -753,9 +823,9 @@ chol_panel_tma_kernel(const BlockDesc* __restrict__ blocks, const int4* __restri
     if ((int)blockIdx.x < n_diag_first) {
         const int blk = diag_items[blockIdx.x];
         const BlockDesc bd = blocks[blk];
-        diag_body(bd, blk, k, sigma, Lbuf, wbuf + wpar, ridge, status, reinterpret_cast<double*>(smem_al), [&]() {
+        diag_body<NT>(bd, blk, k, sigma, Lbuf, wbuf + wpar, ridge, status, reinterpret_cast<double*>(smem_al), [&]() {
             __threadfence();
-            diag_sync();
+            diag_sync<NT>();
             if (threadIdx.x == 0) atomicExch(dflag + blk, k + 1);
         });
         return;
@@ -767,20 +837,23 @@ chol_panel_tma_kernel(const BlockDesc* __restrict__ blocks, const int4* __restri
     else { i0 = n_single + (cta - n_single) * tpc; n_my = min(tpc, n_items - i0); }
 
     if (tid == 0) {
-        for (int s = 0; s < TP_NST; ++s) { mbar_init(&bars.full[s], 1); mbar_init(&bars.empty[s], 8); }
+        for (int s = 0; s < TP_NST; ++s) { mbar_init(&bars.full[s], 1); mbar_init(&bars.empty[s], NW); }
         mbar_init(&bars.w_full, 1);
-        mbar_init(&bars.w_free, 8);
-        mbar_init(&bars.ring_free, 8);
+        mbar_init(&bars.w_free, NW);
+        mbar_init(&bars.ring_free, NW);
         mbar_fence_init();
-        tma_prefetch_desc(&wmap);
     }
     __syncthreads();
 
-    const uint32_t wbox = sbase + TP_RING;                    // W_kk: 4 boxes (64 rows x 16 columns each)
+    uint8_t* wimg = smem_al + C::RING;                         // W_kk image (w_img_off)
+    const uint32_t wbox = sbase + C::RING;
     const int g = lane >> 2, t = lane & 3;
-    const int sig = perm ? ((g >> 1) | ((g & 1) << 2)) : g;     // shared-memory row of fragment row g inside its 8-row group
+    const int sigp = (g >> 1) | ((g & 1) << 2);                 // row slot of fragment row g in a row-permuted 8-row group
+    const int sig = perm ? sigp : g;                            // ... in the ring boxes (natural order with plain 2-D maps)
     const uint32_t lrow = (uint32_t)sig * 128u;
     const uint32_t x0 = (uint32_t)((t ^ sig) & 7) << 4;          // 16-byte chunk of columns 2t, 2t+1 of the first 8-column group
+    const uint32_t wlrow = (uint32_t)sigp * 128u;                // the same two for the W image (always permuted)
+    const uint32_t wx0 = (uint32_t)((t ^ sigp) & 7) << 4;
     const int grp = warp >> 2;
     const int wl = grp ? 3 - (warp & 3) : (warp & 3);
     const int wrow = 4 * grp + wl;
@@ -790,7 +863,7 @@ chol_panel_tma_kernel(const BlockDesc* __restrict__ blocks, const int4* __restri
     for (int j = 0; j < n_my; ++j) {
         const int4 item = items[i0 + j];
         const BlockDesc bd = blocks[item.x];
-        const TpGeom q = tp_geom(bd, item, k);
+        const TpGeom q = tp_geom<TMR>(bd, item, k);
         const int pc0 = q.pc0, wk = q.wk, r0 = q.r0, prow = q.prow, ld = bd.ld;
         double* Lb = Lbuf + bd.moff;
         const double* Sb = sigma + bd.moff;
@@ -799,34 +872,39 @@ chol_panel_tma_kernel(const BlockDesc* __restrict__ blocks, const int4* __restri
         prev_blk = item.x;
         const int nchunk = (q.ke - q.kb) / KC;
         const CUtensorMap* lm = lmaps + item.x;
+        const bool two_row_boxes = (NG == 2) && prow > NB;
 
         // ---- producer duties of thread 0.  Chunk c of this item is ring use u = it + c: stage u % 3, and it may be
-        // written once all eight warps have released the stage's previous use.
+        // written once all consumer warps have released the stage's previous use.
         auto issue_chunk = [&](int c) {
             const uint32_t u = it + (uint32_t)c;
             const int s = (int)(u % TP_NST);
             mbar_wait(&bars.empty[s], ((u / TP_NST) & 1u) ^ 1u);
-            mbar_expect_tx(&bars.full[s], (uint32_t)((prow > NB ? 3 : 2) * BOXB));
+            mbar_expect_tx(&bars.full[s], (uint32_t)((two_row_boxes ? 3 : 2) * BOXB));
             const int k0 = q.kb + c * KC;
             if (perm) {
-                const uint32_t st = sbase + (uint32_t)s * 3 * BOXB;
+                const uint32_t st = sbase + (uint32_t)s * SB * BOXB;
                 tma_load_4d(st, lm, k0, 0, 0, r0 >> 3, &bars.full[s]);
-                if (prow > NB) tma_load_4d(st + BOXB, lm, k0, 0, 0, (r0 >> 3) + 8, &bars.full[s]);
-                tma_load_4d(st + 2 * BOXB, lm, k0, 0, 0, pc0 >> 3, &bars.full[s]);
+                if (two_row_boxes) tma_load_4d(st + BOXB, lm, k0, 0, 0, (r0 >> 3) + 8, &bars.full[s]);
+                tma_load_4d(st + NG * BOXB, lm, k0, 0, 0, pc0 >> 3, &bars.full[s]);
+                if (pf > 0 && c + pf < nchunk) {
+                    tma_prefetch_4d(lm, k0 + pf * KC, 0, 0, r0 >> 3);
+                    if (two_row_boxes) tma_prefetch_4d(lm, k0 + pf * KC, 0, 0, (r0 >> 3) + 8);
+                }
             } else {
-                uint8_t* sp = smem_al + (size_t)s * 3 * BOXB;
+                uint8_t* sp = smem_al + (size_t)s * SB * BOXB;
                 tma_load_2d(sp, lm, k0, r0, &bars.full[s]);
-                if (prow > NB) tma_load_2d(sp + BOXB, lm, k0, r0 + NB, &bars.full[s]);
-                tma_load_2d(sp + 2 * BOXB, lm, k0, pc0, &bars.full[s]);
+                if (two_row_boxes) tma_load_2d(sp + BOXB, lm, k0, r0 + NB, &bars.full[s]);
+                tma_load_2d(sp + NG * BOXB, lm, k0, pc0, &bars.full[s]);
+                if (pf > 0 && c + pf < nchunk) {
+                    tma_prefetch_2d(lm, k0 + pf * KC, r0);
+                    if (two_row_boxes) tma_prefetch_2d(lm, k0 + pf * KC, r0 + NB);
+                }
             }
         };
         auto issue_w = [&]() {
-            mbar_expect_tx(&bars.w_full, 4 * BOXB);
-            const int wr = wrow8_cur + item.x * (NB / 8);
-            for (int b4 = 0; b4 < 4; ++b4) {
-                if (perm) tma_load_4d(wbox + b4 * BOXB, &wmap, 16 * b4, 0, 0, wr, &bars.w_full);
-                else tma_load_2d(smem_al + TP_RING + b4 * BOXB, &wmap, 16 * b4, wr * 8, &bars.w_full);
-            }
+            mbar_expect_tx(&bars.w_full, W_IMG_BYTES);
+            bulk_g2s(wimg, wbuf + wpar + (size_t)item.x * (NB * NB), W_IMG_BYTES, &bars.w_full);
         };
         if (tid == 0) {
             if (load_w) tensormap_acquire(lm);
@@ -853,16 +931,28 @@ chol_panel_tma_kernel(const BlockDesc* __restrict__ blocks, const int4* __restri
                 acc[f][c][1] = -a.y;
             }
 
-        // ---- main loop: no CTA-wide barrier; thread 0 keeps the ring two chunks ahead
+        // ---- main loop: no CTA-wide barrier; thread 0 keeps the ring two chunks ahead.
+        // A stage is handed back one iteration late, AFTER the wait for the next chunk: by then every DMMA that consumes
+        // its fragments has been issued (in-order issue), and an issued DMMA has its operands, i.e. the shared-memory loads
+        // have really returned.  Until round 2 the release sat right after the last LDS of the stage -- ptxas is free to
+        // move an mbarrier arrive above DMMAs (it did), an arrive does not wait for LDS that are still queued in the
+        // shared-memory pipe, and under load the next TMA box then landed beneath them: run-to-run differences of ~1e-5
+        // in a few percent of the blocks once three CTAs per SM kept that pipe busy (tools/stream_vs_resident.py,
+        // tools/l_diff.py: one warp's 16 rows, last column groups of a panel).  The spin loop of the wait is a point the
+        // arrive cannot be hoisted across.
         for (int kc = 0; kc < nchunk; ++kc) {
-            if (tid == 0 && kc + 2 < nchunk) issue_chunk(kc + 2);
             const uint32_t u = it + (uint32_t)kc;
             const int s = (int)(u % TP_NST);
             mbar_wait(&bars.full[s], (u / TP_NST) & 1u);
+            if (kc > 0) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars.empty[(int)((u - 1) % TP_NST)]);
+            }
+            if (tid == 0 && kc + 2 < nchunk) issue_chunk(kc + 2);
             if (active) {
-                const uint32_t st = sbase + (uint32_t)s * 3 * BOXB;
+                const uint32_t st = sbase + (uint32_t)s * SB * BOXB;
                 const uint32_t Pa = st + (uint32_t)grp * BOXB + (uint32_t)(2 * wl) * 1024 + lrow;
-                const uint32_t Qa = st + 2 * BOXB + lrow;
+                const uint32_t Qa = st + NG * BOXB + lrow;
 #pragma unroll
                 for (int s8 = 0; s8 < 2; ++s8) {
                     const uint32_t xo = x0 ^ ((uint32_t)s8 << 6);
@@ -873,11 +963,6 @@ chol_panel_tma_kernel(const BlockDesc* __restrict__ blocks, const int4* __restri
                         double2 b[4];
 #pragma unroll
                         for (int c = 0; c < 4; ++c) b[c] = lds_f64x2(Qa + (uint32_t)(4 * hc + c) * 1024 + xo);
-                        if (s8 == 1 && hc == 1) {
-                            // last shared-memory read of this stage: hand it back
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&bars.empty[s]);
-                        }
                         // eight independent accumulators per pass (x, then y): dependent DMMAs are 8 apart
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
@@ -891,9 +976,6 @@ chol_panel_tma_kernel(const BlockDesc* __restrict__ blocks, const int4* __restri
                         }
                     }
                 }
-            } else {
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bars.empty[s]);
             }
         }
         it += (uint32_t)nchunk;
@@ -906,11 +988,15 @@ chol_panel_tma_kernel(const BlockDesc* __restrict__ blocks, const int4* __restri
             issue_w();
         }
         __syncthreads();          // every warp is done with the ring: its boxes become the epilogue's L halves
+        if (nchunk > 0) {         // the last chunk's stage (behind the barrier: see the main loop)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars.empty[(int)((it - 1) % TP_NST)]);
+        }
 
         {
-            // this item's two diagonal tiles (old values of the look-ahead update, read after the TRSM) -> L2 now
+            // this item's diagonal tiles (old values of the look-ahead update, read after the TRSM) -> L2 now
             const int hrow0 = r0 + 64 * (tid >> 6), hr = tid & 63;
-            if (tid < 128 && wk == NB && hrow0 + hr < bd.mp)
+            if (tid < 64 * NG && wk == NB && hrow0 + hr < bd.mp)
                 l2_prefetch_bulk((k == 0 ? sigma : Lbuf) + bd.moff + (size_t)(hrow0 + hr) * ld + hrow0,
                                  (uint32_t)(min(NB, bd.mp - hrow0) * 8));
         }
@@ -918,19 +1004,19 @@ chol_panel_tma_kernel(const BlockDesc* __restrict__ blocks, const int4* __restri
             // the next item's Sigma tile (its accumulator preload) -> L2 while this item's epilogue runs
             const int4 item2 = items[i0 + j + 1];
             const BlockDesc bd2 = blocks[item2.x];
-            const TpGeom q2 = tp_geom(bd2, item2, k);
+            const TpGeom q2 = tp_geom<TMR>(bd2, item2, k);
             if (q2.slice == 0 && tid < q2.prow)
                 l2_prefetch_bulk(sigma + bd2.moff + (size_t)(q2.r0 + tid) * bd2.ld + q2.pc0, (uint32_t)(q2.wk * 8));
         }
 
         if (q.nsl > 1) {
             // split-K (single-item CTAs only): partial sums to scratch, the last arriver adds them up IN SLICE ORDER
-            double* part = scratch + ((size_t)(item.w - group_base) * q.nsl) * (TM * NB);
-            double2* mine = reinterpret_cast<double2*>(part + (size_t)q.slice * (TM * NB)) + tid;
+            double* part = scratch + ((size_t)(item.w - group_base) * q.nsl) * (TMR * NB);
+            double2* mine = reinterpret_cast<double2*>(part + (size_t)q.slice * (TMR * NB)) + tid;
 #pragma unroll
             for (int f = 0; f < 2; ++f)
 #pragma unroll
-                for (int c = 0; c < 8; ++c) mine[(f * 8 + c) * CHOL_THREADS] = make_double2(acc[f][c][0], acc[f][c][1]);
+                for (int c = 0; c < 8; ++c) mine[(f * 8 + c) * NT] = make_double2(acc[f][c][0], acc[f][c][1]);
             __threadfence();
             __syncthreads();
             if (tid == 0) s_last = (atomicAdd(&counters[item.w], 1) == q.nsl - 1);
@@ -945,12 +1031,12 @@ chol_panel_tma_kernel(const BlockDesc* __restrict__ blocks, const int4* __restri
 #pragma unroll
                 for (int c = 0; c < 8; ++c) acc[f][c][0] = acc[f][c][1] = 0.0;
             for (int sl = 0; sl < q.nsl; ++sl) {
-                const double2* src2 = reinterpret_cast<const double2*>(part + (size_t)sl * (TM * NB)) + tid;
+                const double2* src2 = reinterpret_cast<const double2*>(part + (size_t)sl * (TMR * NB)) + tid;
 #pragma unroll
                 for (int f = 0; f < 2; ++f)
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
-                        const double2 v = __ldcg(src2 + (f * 8 + c) * CHOL_THREADS);
+                        const double2 v = __ldcg(src2 + (f * 8 + c) * NT);
                         acc[f][c][0] += v.x;
                         acc[f][c][1] += v.y;
                     }
@@ -979,8 +1065,9 @@ chol_panel_tma_kernel(const BlockDesc* __restrict__ blocks, const int4* __restri
                     for (int cq = 0; cq < 4; ++cq) {
                         const int c = 4 * h + cq;
                         if (c >= cp) {
-                            const double2 b = lds_f64x2(wbox + (uint32_t)(cp >> 1) * BOXB + (uint32_t)c * 1024 + lrow +
-                                                        (x0 ^ ((uint32_t)(cp & 1) << 6)));
+                            // W rows 8c.., columns 8cp..: 16x16 block (c >> 1, cp >> 1) of the image
+                            const double2 b = lds_f64x2(wbox + (uint32_t)(((c >> 1) * ((c >> 1) + 1) / 2 + (cp >> 1)) * 2048 + (c & 1) * 1024) +
+                                                        wlrow + (wx0 ^ ((uint32_t)(cp & 1) << 6)));
                             dmma884(out[0][cq][0], out[0][cq][1], acc[0][cp][0], b.x);
                             dmma884(out[1][cq][0], out[1][cq][1], acc[1][cp][0], b.x);
                             dmma884(out[0][cq][0], out[0][cq][1], acc[0][cp][1], b.y);
@@ -1060,7 +1147,7 @@ chol_panel_tma_kernel(const BlockDesc* __restrict__ blocks, const int4* __restri
 
         if (fuse_end && item.y == 0 && r0 < bd.mp && wk == NB && j == n_my - 1) {
             __syncthreads();        // T_new is in L2 for the whole CTA; shared memory is free (last item: nothing in flight)
-            diag_body(bd, item.x, k + 1, sigma, Lbuf, wbuf + wpar_next, ridge, status, reinterpret_cast<double*>(smem_al), []() {});
+            diag_body<NT>(bd, item.x, k + 1, sigma, Lbuf, wbuf + wpar_next, ridge, status, reinterpret_cast<double*>(smem_al), []() {});
         }
     }
 }
@@ -1301,19 +1388,23 @@ backsolve_cluster_kernel(const BlockDesc* __restrict__ blocks, const int32_t* __
 cudaError_t chol_configure() {
     cudaError_t e = cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DIAG);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(chol_panel_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TP);
+    e = cudaFuncSetAttribute(chol_panel_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TpCfg<2>::SMEM);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(chol_panel_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TpCfg<1>::SMEM);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CHOL);
 }
 
-// TMA panel step (see chol_panel_tma_kernel).  n_single leading items get a CTA each, the rest `tpc` consecutive items
-// per CTA; nb_total = number of blocks of the plan (W tiles per parity).
-cudaError_t launch_chol_panel_tma(const BlockDesc* blocks, const int4* items, int32_t n_items, int32_t n_single, int32_t tpc,
-                                  const int32_t* diag_items, int32_t n_diag_first, int32_t k, const CUtensorMap* lmaps,
-                                  const CUtensorMap& wmap, int32_t perm, int32_t nb_total, const double* sigma, double* L,
-                                  double* wbuf, int64_t wstride, bool fuse_end, double ridge, double* scratch,
-                                  int32_t* counters, int32_t group_base, int32_t* status, int32_t* dflag, bool pdl,
-                                  cudaStream_t st) {
+// panel CTAs that fit on one SM, by macro-tile height (the plan sizes split-K and the deferral rule with it)
+int chol_panel_ctas_per_sm(int32_t tile_rows) { return tile_rows == 64 ? TpCfg<1>::MINB : 2; }
+
+// TMA panel step (see chol_panel_tma_kernel).  tile_rows = 64 or 128 (rows per item, as the plan built the list);
+// n_single leading items get a CTA each, the rest `tpc` consecutive items per CTA; pf = L2 prefetch distance in chunks.
+cudaError_t launch_chol_panel_tma(int32_t tile_rows, const BlockDesc* blocks, const int4* items, int32_t n_items, int32_t n_single,
+                                  int32_t tpc, const int32_t* diag_items, int32_t n_diag_first, int32_t k, const CUtensorMap* lmaps,
+                                  int32_t perm, int32_t pf, const double* sigma, double* L, double* wbuf, int64_t wstride,
+                                  bool fuse_end, double ridge, double* scratch, int32_t* counters, int32_t group_base,
+                                  int32_t* status, int32_t* dflag, bool pdl, cudaStream_t st) {
     if (n_items + n_diag_first == 0) return cudaSuccess;
     const int64_t wpar = (k & 1) * wstride, wnext = ((k + 1) & 1) * wstride;
     n_single = std::min(n_single, n_items);
@@ -1321,18 +1412,24 @@ cudaError_t launch_chol_panel_tma(const BlockDesc* blocks, const int4* items, in
     const int rest = n_items - n_single;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(n_diag_first + n_single + (rest + tpc - 1) / tpc));
-    cfg.blockDim = dim3(TP_THREADS);
-    cfg.dynamicSmemBytes = SMEM_TP;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    const int32_t wrow8_cur = (int32_t)((k & 1) * (int64_t)nb_total * (NB / 8));
-    return cudaLaunchKernelEx(&cfg, chol_panel_tma_kernel, blocks, items, n_items, n_single, tpc, diag_items, n_diag_first, k,
-                              lmaps, wmap, perm, wrow8_cur, sigma, L, wbuf, wpar, wnext, ridge, scratch, counters, group_base,
-                              status, dflag, (int32_t)(fuse_end ? 1 : 0));
+    if (tile_rows == 64) {
+        cfg.blockDim = dim3(TpCfg<1>::NT);
+        cfg.dynamicSmemBytes = TpCfg<1>::SMEM;
+        return cudaLaunchKernelEx(&cfg, chol_panel_tma_kernel<1>, blocks, items, n_items, n_single, tpc, diag_items, n_diag_first, k,
+                                  lmaps, perm, pf, sigma, L, wbuf, wpar, wnext, ridge, scratch, counters, group_base, status, dflag,
+                                  (int32_t)(fuse_end ? 1 : 0));
+    }
+    cfg.blockDim = dim3(TpCfg<2>::NT);
+    cfg.dynamicSmemBytes = TpCfg<2>::SMEM;
+    return cudaLaunchKernelEx(&cfg, chol_panel_tma_kernel<2>, blocks, items, n_items, n_single, tpc, diag_items, n_diag_first, k,
+                              lmaps, perm, pf, sigma, L, wbuf, wpar, wnext, ridge, scratch, counters, group_base, status, dflag,
+                              (int32_t)(fuse_end ? 1 : 0));
 }
 
 // W_k (the inverse of the diagonal tile of panel k) lives in wbuf[(k & 1) * wstride + block * 64 * 64]: two parities,

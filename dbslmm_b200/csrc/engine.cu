@@ -78,6 +78,7 @@ constexpr int kMaxBatches = 8;
 struct Batch {
     int cls = 0;                          // size class (timing slot)
     bool big = false;                     // some member has mp > 1024: cluster back substitution
+    int32_t tile_rows = 128;              // rows per Cholesky panel item (128: 256-thread CTAs, 64: 128-thread CTAs, three per SM)
     int32_t ord_off = 0, ord_n = 0;       // members = order[ord_off, ord_off + ord_n)
     int64_t grow0 = 0, grow1 = 0;         // SNP rows of the members (contiguous only in the streaming layout)
     int32_t tile0 = 0, tile1 = 0;         // range of the one-plane Gram tile list (128 x 128 tiles)
@@ -133,7 +134,13 @@ struct dbslmm_b200_handle {
     // whose chain rivals the fit's throughput time).  Measured on an 8-GPU shard: the longest chain shrinks by 4 %, but
     // the waiting CTAs hold SM slots the bulk batches need, and the streaming fit gets slower -- off by default.
     double pdl_ratio = 0.0;
-    int defer_max_ctas = 296;                    // steps with at most this many CTAs take their diagonal tile first (see StepList)
+    int defer_max_ctas = -1;                     // steps with at most this many CTAs take their diagonal tile first (see StepList); -1: one wave of panel CTAs
+    // Panel items of 64 rows (128-thread CTAs, three per SM; DBSLMM_B200_TILE64: 2 = everywhere (default), 1 = only for the
+    // batches of bulk blocks (<= 16 panels), 0 = 128-row items, 256-thread CTAs, two per SM).  Measured on C3, one GPU:
+    // factorisation 13.7 / 13.35 / 13.0 ms for 0 / 1 / 2 -- a third independent instruction stream per SM and fewer idle
+    // warps in partially filled items outweigh the slower 128-thread diagonal-tile code even in the chain-bound classes.
+    int tile64_mode = 2;
+    int l2_pf = 0;                               // panel kernel: L2 tensor prefetch distance in 16-wide K chunks (0 = off: measured 13.0 ms without, 13.1 with 2 or 4)
     // panel step kernel: TMA/mbarrier pipeline (default) or the cp.async version (DBSLMM_B200_PANEL=legacy)
     int upload_bulk_first = 1;                   // streaming fit: bulk regions sent before the big classes (see make_batches)
     // correlation builder for blocks without missing calls: the int8-row kernel fed by the decoder (default), or the fused
@@ -144,9 +151,6 @@ struct dbslmm_b200_handle {
     bool panel_tma = true;
     int tpc_max = 4, tpc_waves = 2;              // items per CTA: at most tpc_max, and only while a step keeps >= tpc_waves waves of CTAs
     int tmap_perm = -1;                          // 1: 4-D row-permuting tensor maps, 0: plain 2-D maps (driver refused), -1: not probed yet
-    CUtensorMap wmap;                            // the W tiles (wbuf) as one tensor
-    const void* wmap_base = nullptr;
-    int64_t wmap_tiles = 0;
     // reference panel
     DevBuf bed, stats;
     PinBuf h_stats;                      // per-SNP statistics, filled asynchronously by load_bed
@@ -362,11 +366,11 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
         n_diag_max += (size_t)K;
         for (int k = 0; k < K; ++k) {
             const int wk = std::min(64, d.mp - 64 * k);
-            n_steps_tiles += (size_t)((d.nrows - (64 * k + wk) + 127) / 128);
+            n_steps_tiles += (size_t)((d.nrows - (64 * k + wk) + 63) / 64);      // 64-row items (the finer of the two shapes)
         }
     }
     // upper bound of the list part: a split-K step has at most max(#tiles, 2 n_sm) items
-    const size_t n_panel_max = n_steps_tiles + (size_t)2 * h->n_sm * kMaxBatches * (size_t)(P.max_mp / 64 + 2);
+    const size_t n_panel_max = n_steps_tiles + (size_t)3 * h->n_sm * kMaxBatches * (size_t)(P.max_mp / 64 + 2);
     const size_t lists_max = sizeof(GramTile) * (n_t1 + n_t2) + sizeof(int32_t) * ((size_t)nb + n_diag_max) + sizeof(int4) * n_panel_max +
                              sizeof(CUtensorMap) * (size_t)nb + 8 * 256;
     if (h->h_blob.ensure(o + lists_max + 256) != cudaSuccess) return fail(h, DBSLMM_B200_ERR_NOMEM, "pinned plan buffer");
@@ -464,9 +468,11 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
     diag_items.reserve(n_diag_max);
     panel_items.reserve(n_panel_max);
     int32_t n_groups = 0;
-    const int kTargetCtas = 2 * h->n_sm;              // 2 panel CTAs per SM
     for (Batch& B : P.batches) {
         const int32_t* members = P.order.data() + B.ord_off;
+        B.tile_rows = (h->panel_tma && (h->tile64_mode >= 2 || (h->tile64_mode == 1 && !B.big))) ? 64 : 128;
+        const int TR = B.tile_rows;
+        const int kTargetCtas = chol_panel_ctas_per_sm(TR) * h->n_sm;      // one wave of panel CTAs
         int kmax = 0;
         for (int i = 0; i < B.ord_n; ++i) kmax = std::max(kmax, (P.blocks[members[i]].mp + 63) / 64);
         B.steps.resize(kmax);
@@ -482,7 +488,7 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
                 const BlockDesc& d = P.blocks[members[i]];
                 if ((d.mp + 63) / 64 <= k) continue;
                 const int wk = std::min(64, d.mp - 64 * k);
-                ntiles += (d.nrows - (64 * k + wk) + 127) / 128;
+                ntiles += (d.nrows - (64 * k + wk) + TR - 1) / TR;
             }
             int nsl = 1;
             if (ntiles > 0) nsl = std::max(1, std::min({h->splitk_max, k / h->splitk_min_blocks, kTargetCtas / ntiles}));
@@ -501,7 +507,7 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
                     if (pass == 0) diag_items.push_back(b);
                     const int wk = std::min(64, d.mp - 64 * k);
                     const int below = 64 * k + wk;
-                    const int nt = (d.nrows - below + 127) / 128;
+                    const int nt = (d.nrows - below + TR - 1) / TR;
                     for (int t = (pass == 0 ? 0 : 1); t < (pass == 0 ? std::min(nt, 1) : nt); ++t) {
                         const int gid = (nsl > 1) ? n_groups++ : 0;
                         for (int sl = 0; sl < nsl; ++sl) panel_items.push_back(make_int4(b, t, sl | (nsl << 8), gid));
@@ -512,13 +518,13 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
             s.n_first = n_first;
             s.n_diag = (int32_t)diag_items.size() - s.diag_off;
             s.n_panel = (int32_t)panel_items.size() - s.panel_off;
-            batch_scratch = std::max<int64_t>(batch_scratch, (int64_t)s.n_groups * nsl * 128 * 64);
+            batch_scratch = std::max<int64_t>(batch_scratch, (int64_t)s.n_groups * nsl * TR * 64);
         }
         // A chain-bound step (the whole next step fits in one wave of CTAs) defers the next diagonal tile to the
         // next launch, where it overlaps the main loops; otherwise macro tile 0 factors it at the end of this step,
         // in the shadow of the step's later waves.
         for (int k = 0; k < kmax; ++k)
-            B.steps[k].defer = (k + 1 < kmax && B.steps[k + 1].n_panel + B.steps[k + 1].n_diag <= h->defer_max_ctas) ? 1 : 0;
+            B.steps[k].defer = (k + 1 < kmax && B.steps[k + 1].n_panel + B.steps[k + 1].n_diag <= (h->defer_max_ctas >= 0 ? h->defer_max_ctas : kTargetCtas)) ? 1 : 0;
         B.scratch_off = P.scratch_doubles;
         P.scratch_doubles += batch_scratch;
     }
@@ -675,19 +681,6 @@ int encode_lmaps(dbslmm_b200_handle* h, Plan& P) {
     P.lmaps_base = h->lbuf.p;
     return DBSLMM_B200_OK;
 }
-int encode_wmap(dbslmm_b200_handle* h, int64_t n_tiles) {
-    if (h->wmap_base == h->wbuf.p && h->wmap_tiles == n_tiles) return DBSLMM_B200_OK;
-    int rc = ensure_encoder(h);
-    if (rc != DBSLMM_B200_OK) return rc;
-    rc = probe_perm(h, h->wbuf.p);
-    if (rc != DBSLMM_B200_OK) return rc;
-    if (encode_f64_boxes(h, &h->wmap, h->wbuf.p, 64, 64 * n_tiles, h->tmap_perm == 1) != CUDA_SUCCESS)
-        return fail(h, DBSLMM_B200_ERR_CUDA, "cuTensorMapEncodeTiled failed for the W tiles");
-    h->wmap_base = h->wbuf.p;
-    h->wmap_tiles = n_tiles;
-    return DBSLMM_B200_OK;
-}
-
 }  // namespace
 
 // =============================================================================================
@@ -726,7 +719,8 @@ int dbslmm_b200_create(int device, dbslmm_b200_handle** out) {
         if (std::sscanf(e, "%d,%d", &a, &b) == 2 && a >= 1 && a <= 255 && b >= 1) { h->splitk_max = a; h->splitk_min_blocks = b; }
     }
     if (const char* e = std::getenv("DBSLMM_B200_DEFER_CTAS")) h->defer_max_ctas = std::atoi(e);
-    else h->defer_max_ctas = 2 * h->n_sm;
+    if (const char* e = std::getenv("DBSLMM_B200_TILE64")) h->tile64_mode = std::atoi(e);
+    if (const char* e = std::getenv("DBSLMM_B200_L2_PF")) h->l2_pf = std::max(0, std::atoi(e));
     if (const char* e = std::getenv("DBSLMM_B200_UPLOAD_BULK_FIRST")) h->upload_bulk_first = std::atoi(e);
     if (const char* e = std::getenv("DBSLMM_B200_GRAM")) h->gram_packed = (std::strcmp(e, "packed") == 0);
     if (const char* e = std::getenv("DBSLMM_B200_PANEL")) h->panel_tma = (std::strcmp(e, "legacy") != 0);
@@ -1098,10 +1092,8 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
     const bool tma_panel = h->panel_tma && !pcg && !quad;
     bool lmaps_dirty = false;                   // the maps in the pinned blob were (re)encoded: a cached device plan needs them again
     if (tma_panel && nb > 0) {
-        int rc = encode_wmap(h, 2 * (int64_t)std::max(nb, 1));
-        if (rc != DBSLMM_B200_OK) return rc;
         if (P.lmaps_base != h->lbuf.p) {
-            rc = encode_lmaps(h, P);
+            int rc = encode_lmaps(h, P);
             if (rc != DBSLMM_B200_OK) return rc;
             lmaps_dirty = true;
             tr.mark("tensor maps encoded");
@@ -1340,7 +1332,8 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
             const int64_t wstride = (int64_t)64 * 64 * std::max(nb, 1);
             for (int bi = 0; bi < nbatch; ++bi) {
                 const Batch& B = P.batches[bi];
-                cudaStream_t cs = h->b_stream[bi];
+                static const bool one_stream = std::getenv("DBSLMM_B200_ONE_STREAM") != nullptr;       // debugging aid
+                cudaStream_t cs = h->b_stream[one_stream ? 0 : bi];
                 // A batch whose dependency chain (steps x ~50 us) rivals the whole fit's throughput time is latency-bound:
                 // its steps are launched programmatically dependent, so the next step's CTAs are resident (and waiting)
                 // before the current step ends instead of queueing for SM slots behind lower-priority tiles afterwards.
@@ -1369,12 +1362,12 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
                         if (s.nsl == 1 && !deferred_here) {
                             n_single = fuse_end ? s.n_first : 0;
                             const int rest = s.n_panel - n_single;
-                            tpc = std::max(1, std::min(h->tpc_max, rest / std::max(1, h->tpc_waves * 2 * h->n_sm)));   // tpc_waves = 0: always tpc_max
+                            tpc = std::max(1, std::min(h->tpc_max, rest / std::max(1, h->tpc_waves * chol_panel_ctas_per_sm(B.tile_rows) * h->n_sm)));   // tpc_waves = 0: always tpc_max
                         }
-                        CU_TRY(h, launch_chol_panel_tma(d_blocks, d_panel + s.panel_off, s.n_panel, n_single, tpc,
+                        CU_TRY(h, launch_chol_panel_tma(B.tile_rows, d_blocks, d_panel + s.panel_off, s.n_panel, n_single, tpc,
                                                         d_diag + s.diag_off, deferred_here ? s.n_diag : 0, (int32_t)k,
-                                                        (const CUtensorMap*)(dblob + P.o_lmaps), h->wmap, h->tmap_perm == 1 ? 1 : 0,
-                                                        nb, (const double*)h->sigma.p, (double*)h->lbuf.p, (double*)h->wbuf.p,
+                                                        (const CUtensorMap*)(dblob + P.o_lmaps), h->tmap_perm == 1 ? 1 : 0, h->l2_pf,
+                                                        (const double*)h->sigma.p, (double*)h->lbuf.p, (double*)h->wbuf.p,
                                                         wstride, fuse_end, ridge, (double*)h->scratch.p + B.scratch_off,
                                                         (int32_t*)h->counters.p, s.group_base, d_status, (int32_t*)h->dflag.p,
                                                         pdl_batch && k > 0, cs));
@@ -1862,10 +1855,11 @@ int dbslmm_b200_get_block_sigma(dbslmm_b200_handle* h, int32_t block, double* si
     if (!h || !sigma_out) return DBSLMM_B200_ERR_ARG;
     std::vector<uint8_t> tmp;
     const BlockDesc* bd = nullptr;
-    int rc = fetch_block(h, block, h->sigma.p, sizeof(double), tmp, &bd);
+    static const bool fetch_l = std::getenv("DBSLMM_B200_DBG_FETCH_L") != nullptr;      // debugging aid: the factor instead of Sigma
+    int rc = fetch_block(h, block, fetch_l ? h->lbuf.p : h->sigma.p, sizeof(double), tmp, &bd);
     if (rc != DBSLMM_B200_OK) return rc;
     const double* s = (const double*)tmp.data();
-    const bool full = (h->last_flags & DBSLMM_B200_FLAG_FULL_SIGMA) != 0;
+    const bool full = fetch_l || (h->last_flags & DBSLMM_B200_FLAG_FULL_SIGMA) != 0;
     for (int i = 0; i < bd->m; ++i)
         for (int j = 0; j < bd->m; ++j) {
             const double v = (j <= i || full) ? s[(size_t)i * bd->ld + j] : s[(size_t)j * bd->ld + i];

@@ -64,14 +64,15 @@ cudaError_t launch_chol_panel(const BlockDesc* blocks, const int4* items, int32_
                               int32_t n_diag_first, int32_t k, const double* sigma, double* L, double* wbuf, int64_t wstride,
                               bool fuse_end, double ridge, double* scratch, int32_t* counters, int32_t group_base,
                               int32_t* status, int32_t* dflag, bool pdl, cudaStream_t st);
-// TMA/mbarrier version of the panel step (default).  lmaps: one tensor map per block over its matrix in L (device
-// array, see engine.cu encode_lmaps); wmap: the W tiles; perm: the maps permute rows inside 8-row groups (4-D form).
-cudaError_t launch_chol_panel_tma(const BlockDesc* blocks, const int4* items, int32_t n_items, int32_t n_single, int32_t tpc,
-                                  const int32_t* diag_items, int32_t n_diag_first, int32_t k, const CUtensorMap* lmaps,
-                                  const CUtensorMap& wmap, int32_t perm, int32_t nb_total, const double* sigma, double* L,
-                                  double* wbuf, int64_t wstride, bool fuse_end, double ridge, double* scratch,
-                                  int32_t* counters, int32_t group_base, int32_t* status, int32_t* dflag, bool pdl,
-                                  cudaStream_t st);
+// TMA/mbarrier version of the panel step (default).  tile_rows: rows per item of the list (128: 256-thread CTAs, two per
+// SM; 64: 128-thread CTAs, three per SM).  lmaps: one tensor map per block over its matrix in L (device array, see
+// engine.cu encode_lmaps); perm: the maps permute rows inside 8-row groups (4-D form); pf: L2 prefetch distance (chunks).
+cudaError_t launch_chol_panel_tma(int32_t tile_rows, const BlockDesc* blocks, const int4* items, int32_t n_items, int32_t n_single,
+                                  int32_t tpc, const int32_t* diag_items, int32_t n_diag_first, int32_t k, const CUtensorMap* lmaps,
+                                  int32_t perm, int32_t pf, const double* sigma, double* L, double* wbuf, int64_t wstride,
+                                  bool fuse_end, double ridge, double* scratch, int32_t* counters, int32_t group_base,
+                                  int32_t* status, int32_t* dflag, bool pdl, cudaStream_t st);
+int chol_panel_ctas_per_sm(int32_t tile_rows);
 cudaError_t launch_backsolve(const BlockDesc* blocks, const int32_t* order, int32_t n_blocks, bool big,
                              const double* L, double inv_sqrt_n, double* beta_s, double* beta_l, int32_t max_mp,
                              cudaStream_t st);

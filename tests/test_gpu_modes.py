@@ -28,6 +28,12 @@ MODES = {
     "tma_one_item_per_cta": {"DBSLMM_B200_TPC": "1"},
     "tma_plain_2d_tensor_maps": {"DBSLMM_B200_TMAP_PERM": "0", "DBSLMM_B200_TPC": "2,0"},
     "legacy_cp_async_panel_kernel": {"DBSLMM_B200_PANEL": "legacy"},
+    # macro-tile height of the TMA panel kernel: 64 rows / 128-thread CTAs everywhere (default), only for the bulk
+    # batches, or 128 rows / 256-thread CTAs everywhere; with the L2 tensor prefetch on
+    "tile64_bulk_only": {"DBSLMM_B200_TILE64": "1"},
+    "tile128_everywhere_many_items_per_cta": {"DBSLMM_B200_TILE64": "0", "DBSLMM_B200_TPC": "8,0"},
+    "tile128_diag_at_end_of_step": {"DBSLMM_B200_TILE64": "0", "DBSLMM_B200_DEFER_CTAS": "0"},
+    "tile64_l2_prefetch": {"DBSLMM_B200_L2_PF": "3"},
     # the correlation builder of blocks without missing calls: the int8-row kernel fed by the decoder (default) or the
     # experimental fused unpack + Gram from packed 2-bit rows
     "fused_unpack_gram_from_packed_rows": {"DBSLMM_B200_GRAM": "packed"},
@@ -104,3 +110,8 @@ def test_genome_wide_residuals_and_streaming_equality(engine):
         assert res < 1e-10, (b, m, res)
     rs = engine.fit(*csr, sigma_s=[sig], n_obs=n_obs, bed=w["bed"], n_ref=w["n_ref"])
     assert relmax(rs["beta_s"], r["beta_s"]) <= 1e-11 and relmax(rs["beta_l"], r["beta_l"]) <= 1e-11
+    # run-to-run determinism at full load (every reduction order is fixed): a second resident fit is bit-identical.  This
+    # is the check that exposed a ring stage handed back to the TMA producer before its shared-memory loads had returned.
+    for _ in range(2):
+        r2 = engine.fit(*csr, sigma_s=[sig], n_obs=n_obs, flags=_abi.FLAG_FULL_SIGMA)
+        assert np.array_equal(r2["beta_s"], r["beta_s"]) and np.array_equal(r2["beta_l"], r["beta_l"])

@@ -9,6 +9,14 @@ __device__ long long g_stamps[32];
 #define DIAG_STAMP(n) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_stamps[(n)] = clock64(); } while (0)
 #include "../dbslmm_b200/csrc/chol.cu"
 using namespace dbslmm;
+// the 128-thread form of the diagonal-tile code (as run inside the 64-row panel kernel)
+__global__ void __launch_bounds__(128, 3) diag128_probe_kernel(const BlockDesc* blocks, const int32_t* items, int32_t k, const double* sigma,
+                                                               double* Lbuf, double* wbuf, double ridge, int32_t* status) {
+    extern __shared__ __align__(16) double smem[];
+    const int blk = items[blockIdx.x];
+    const BlockDesc bd = blocks[blk];
+    diag_body<128>(bd, blk, k, sigma, Lbuf, wbuf, ridge, status, smem, []() {});
+}
 int main() {
     const int m = 256, mp = 256, nrows = mp + 8;
     std::vector<double> S((size_t)nrows * mp, 0.0);
@@ -27,21 +35,25 @@ int main() {
     cudaMemcpy(dI, items.data(), sizeof(int) * NBLK, cudaMemcpyHostToDevice);
     cudaMemset(dSt, 0, sizeof(int) * NBLK);
     chol_configure();
+    cudaFuncSetAttribute(diag128_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_DIAG);
+    for (int nt : {256, 128}) {
     for (int rep = 0; rep < 3; ++rep) {
-        for (int n : {1, NBLK}) {
+        for (int n : {1, NBLK, 3 * 148}) {
+            if (n > NBLK && nt == 256) continue;
             cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
             cudaEventRecord(e0);
-            launch_chol_diag(dB, dI, n, 0, dS, dL, dW, 64 * 64 * NBLK, 0.1, dSt, 0);
+            if (nt == 256) launch_chol_diag(dB, dI, n, 0, dS, dL, dW, 64 * 64 * NBLK, 0.1, dSt, 0);
+            else diag128_probe_kernel<<<std::min(n, NBLK), 128, SMEM_DIAG>>>(dB, dI, 0, dS, dL, dW, 0.1, dSt);
             cudaEventRecord(e1); cudaDeviceSynchronize();
             float ms; cudaEventElapsedTime(&ms, e0, e1);
             long long st[32]; cudaMemcpyFromSymbol(st, g_stamps, sizeof st);
-            printf("rep %d ctas %d: kernel %.2f us; stamps (clk from start):", rep, n, ms * 1e3);
+            printf("threads %d rep %d ctas %d: kernel %.2f us; stamps (clk from start):", nt, rep, std::min(n, NBLK), ms * 1e3);
             for (int i = 1; i < 24; ++i) if (st[i]) printf(" [%d]%lld", i, st[i] - st[0]);
             printf("\n");
             cudaMemset(dSt, 0, 4);
         }
     }
-    // ---- check L (lower), W^T (strict upper of the tile) and the dense W tile against a host factorisation
+    // ---- check L (lower), W^T (strict upper of the tile) and the W image against a host factorisation
     {
         std::vector<double> A(64 * 64), L(64 * 64, 0.0), W(64 * 64, 0.0);
         for (int i = 0; i < 64; ++i) for (int j = 0; j < 64; ++j) A[i * 64 + j] = S[(size_t)std::max(i, j) * mp + std::min(i, j)] + (i == j ? 0.1 : 0.0);
@@ -68,9 +80,11 @@ int main() {
         for (int i = 0; i < 64; ++i) for (int j = 0; j < 64; ++j) {
             if (j <= i) eL = fmax(eL, fabs(dl[(size_t)i * mp + j] - L[i * 64 + j]));
             else eWt = fmax(eWt, fabs(dl[(size_t)i * mp + j] - W[j * 64 + i]));
-            eW = fmax(eW, fabs(dw[i * 64 + j] - W[i * 64 + j]));
+            if ((j >> 4) <= (i >> 4)) eW = fmax(eW, fabs(dw[w_img_off(i, j)] - W[i * 64 + j]));
         }
-        printf("max abs err: L %.3e  W^T (tile upper) %.3e  W (dense) %.3e\n", eL, eWt, eW);
+        printf("threads %d max abs err: L %.3e  W^T (tile upper) %.3e  W (image) %.3e\n", nt, eL, eWt, eW);
+    }
+    cudaMemset(dL, 0, sizeof(double) * S.size() * NBLK); cudaMemset(dW, 0, sizeof(double) * 64 * 64 * NBLK * 2);
     }
     printf("cuda: %s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
