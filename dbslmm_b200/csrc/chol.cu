@@ -216,28 +216,35 @@ __device__ __forceinline__ void diag_body(const BlockDesc& bd, int blk, int k, c
     DIAG_STAMP(0);
 
     {
-        // loads are issued 16 at a time per thread, back to back (independent), then consumed
+        // 128-bit loads of the lower triangle (pairs of columns), all of a thread's loads issued back to back, then consumed
+        constexpr int PER = NB * NB / 2 / NT;           // 8 or 16 pairs per thread
+        {
+            constexpr int u0 = 0;
+            double2 tv[PER];
 #pragma unroll
-        for (int u0 = 0; u0 < NB * NB / NT; u0 += 16) {
-            double tv[16];
-#pragma unroll
-            for (int u = 0; u < 16; ++u) {
+            for (int u = 0; u < PER; ++u) {
                 const int idx = tid + (u0 + u) * NT;
-                const int a = idx >> 6, b = idx & 63;
+                const int a = idx >> 5, b = (idx & 31) * 2;
                 const bool ld_it = (a < wk) && (b <= a);
-                tv[u] = ld_it ? __ldcg(src + (size_t)(pc0 + a) * ld + pc0 + b) : 0.0;
+                tv[u] = ld_it ? __ldcg(reinterpret_cast<const double2*>(src + (size_t)(pc0 + a) * ld + pc0 + b)) : make_double2(0.0, 0.0);
             }
 #pragma unroll
-            for (int u = 0; u < 16; ++u) {
+            for (int u = 0; u < PER; ++u) {
                 const int idx = tid + (u0 + u) * NT;
-                const int a = idx >> 6, b = idx & 63;
-                double v = tv[u];
+                const int a = idx >> 5, b = (idx & 31) * 2;
+                double vx = tv[u].x, vy = (b + 1 <= a) ? tv[u].y : 0.0;      // (a, a + 1) lies above the diagonal
                 if (a == b) {
-                    if (a >= wk) v = 1.0;                                   // identity padding
-                    else if (k == 0 && pc0 + a < bd.ms) v += ridge;
+                    if (a >= wk) vx = 1.0;                                  // identity padding
+                    else if (k == 0 && pc0 + a < bd.ms) vx += ridge;
                 }
-                T[a * DT + b] = v;
+                if (a == b + 1) {
+                    if (a >= wk) vy = 1.0;
+                    else if (k == 0 && pc0 + a < bd.ms) vy += ridge;
+                }
+                T[a * DT + b] = vx;
+                T[a * DT + b + 1] = vy;
                 Wf[a * DT + b] = 0.0;
+                Wf[a * DT + b + 1] = 0.0;
             }
         }
     }
@@ -405,15 +412,20 @@ __device__ __forceinline__ void diag_body(const BlockDesc& bd, int blk, int k, c
     // ---- write back: W_kk as the shared-memory image the panel kernel of this step copies in with one bulk copy
     // (w_img_off; 16x16 blocks above the diagonal do not exist in it) ...
     double* wb = wbuf + (size_t)blk * (NB * NB);
-    for (int idx = tid; idx < NB * NB; idx += NT) {
-        const int a = idx >> 6, b = idx & 63;
-        if ((b >> 4) <= (a >> 4)) wb[w_img_off(a, b)] = (b <= a) ? Wf[a * DT + b] : 0.0;
+    for (int i2 = tid; i2 < W_IMG_DOUBLES / 2; i2 += NT) {
+        // image position (128-bit unit i2) -> element pair (a, b), (a, b + 1): the inverse of w_img_off
+        const int blk16 = i2 >> 7, rb = (blk16 >= 6) ? 3 : (blk16 >= 3) ? 2 : (blk16 >= 1) ? 1 : 0, cb = blk16 - rb * (rb + 1) / 2;
+        const int slot = (i2 >> 3) & 7, g8 = ((slot & 3) << 1) | (slot >> 2);
+        const int a = 16 * rb + 8 * ((i2 >> 6) & 1) + g8, b = 16 * cb + 2 * ((i2 & 7) ^ slot);
+        reinterpret_cast<double2*>(wb)[i2] = make_double2((b <= a) ? Wf[a * DT + b] : 0.0, (b + 1 <= a) ? Wf[a * DT + b + 1] : 0.0);
     }
     w_ready();
-    // ... and the tile itself: lower = L_kk, strict upper = W_kk^T (used by the back substitution)
-    for (int idx = tid; idx < NB * NB; idx += NT) {
-        const int a = idx >> 6, b = idx & 63;
-        if (a < wk && b < wk) Lb[(size_t)(pc0 + a) * ld + pc0 + b] = (b <= a) ? T[a * DT + b] : Wf[b * DT + a];
+    // ... and the tile itself: lower = L_kk, strict upper = W_kk^T (used by the back substitution); wk is a multiple of 8
+    for (int idx = tid; idx < NB * NB / 2; idx += NT) {
+        const int a = idx >> 5, b = (idx & 31) * 2;
+        if (a < wk && b < wk)
+            *reinterpret_cast<double2*>(Lb + (size_t)(pc0 + a) * ld + pc0 + b) =
+                make_double2((b <= a) ? T[a * DT + b] : Wf[b * DT + a], (b + 1 <= a) ? T[a * DT + b + 1] : Wf[(b + 1) * DT + a]);
     }
     DIAG_STAMP(23);
 }
@@ -855,8 +867,6 @@ chol_panel_tma_kernel(const BlockDesc* __restrict__ blocks, const int4* __restri
     const uint32_t wlrow = (uint32_t)sigp * 128u;                // the same two for the W image (always permuted)
     const uint32_t wx0 = (uint32_t)((t ^ sigp) & 7) << 4;
     const int grp = warp >> 2;
-    const int wl = grp ? 3 - (warp & 3) : (warp & 3);
-    const int wrow = 4 * grp + wl;
     uint32_t it = 0, wcount = 0;                                 // ring uses / W loads so far (all threads keep count)
     int prev_blk = -1;
 
@@ -867,6 +877,13 @@ chol_panel_tma_kernel(const BlockDesc* __restrict__ blocks, const int4* __restri
         const int pc0 = q.pc0, wk = q.wk, r0 = q.r0, prow = q.prow, ld = bd.ld;
         double* Lb = Lbuf + bd.moff;
         const double* Sb = sigma + bd.moff;
+        // 16-row slot of this warp.  The look-ahead SYRK of slot wl costs ~(wl + 1) units and warp w always runs on SM
+        // sub-partition w & 3, so the slots are mirrored -- between the two groups of a 256-thread CTA, between odd and even
+        // items of the 128-thread shape -- to spread the heavy slots over the four tensor pipes.  (A function of the ITEM:
+        // the split-K slices of one item, summed thread by thread, must all use the same mapping.)
+        const bool mirror = (NG == 2) ? (grp != 0) : (((item.x + item.y) & 1) != 0);
+        const int wl = mirror ? 3 - (warp & 3) : (warp & 3);
+        const int wrow = 4 * grp + wl;
         const bool active = (16 * wrow < prow);
         const bool load_w = (item.x != prev_blk);
         prev_blk = item.x;
