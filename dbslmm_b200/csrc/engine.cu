@@ -74,7 +74,7 @@ struct StepList {
 // (load_bed) there is one batch per size class.  When the panel streams in from host memory inside the fit
 // (fit_args.bed), batches are also the upload units: big classes first, the bulk class cut into sub-batches, so a
 // batch's decode -> Gram -> factorisation starts as soon as ITS rows have crossed PCIe.
-constexpr int kMaxBatches = 8;
+constexpr int kMaxBatches = 12;
 struct Batch {
     int cls = 0;                          // size class (timing slot)
     bool big = false;                     // some member has mp > 1024: cluster back substitution
@@ -140,9 +140,18 @@ struct dbslmm_b200_handle {
     // factorisation 13.7 / 13.35 / 13.0 ms for 0 / 1 / 2 -- a third independent instruction stream per SM and fewer idle
     // warps in partially filled items outweigh the slower 128-thread diagonal-tile code even in the chain-bound classes.
     int tile64_mode = 2;
+    // The back substitution writes the betas straight into the pinned result buffer (mapped host memory: 9 MB spread over the
+    // whole fit) instead of a device buffer that is copied back when everything is done (0.47 ms at C3, all of it exposed).
+    bool zero_copy_beta = true;
     int l2_pf = 0;                               // panel kernel: L2 tensor prefetch distance in 16-wide K chunks (0 = off: measured 13.0 ms without, 13.1 with 2 or 4)
     // panel step kernel: TMA/mbarrier pipeline (default) or the cp.async version (DBSLMM_B200_PANEL=legacy)
     int upload_bulk_first = 1;                   // streaming fit: bulk regions sent before the big classes (see make_batches)
+    // streaming fit: the bulk is cut into this many regions (upload units).  The FIRST region goes out before the plan is
+    // built and the plan blob queues behind it on the copy engine, so it should take about as long to cross PCIe as the
+    // plan takes to build: with 4 regions (138 MB each at C3) the blob arrived 4.1 ms after the call started, with 6
+    // (92 MB) it arrives at ~2.7 ms, and the first decode starts that much earlier.
+    int n_regions = 6;
+    double preplan_mb = 60.0;                    // ... and at most this much panel data is queued ahead of the plan blob
     // correlation builder for blocks without missing calls: the int8-row kernel fed by the decoder (default), or the fused
     // unpack + Gram from packed 2-bit rows (DBSLMM_B200_GRAM=packed).  Measured on C3 / C5: 1.8 / 10.8 ms against 3.9 / 34.7 ms --
     // expanding the operands in shared memory (8 unpack warps, generic-proxy stores + fence.proxy.async per K step) costs
@@ -173,6 +182,7 @@ struct dbslmm_b200_handle {
     const void* dirty_codes = nullptr;   // ... and this code buffer
     PinBuf h_blob, h_out;
     Plan plan;
+
     int32_t last_flags = 0, last_solver = 0, last_nfolds = 0;
     PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
 };
@@ -273,14 +283,14 @@ int make_batches(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, 
     std::vector<int32_t> bulk;
     for (int c = nc - 1; c >= 0; --c) {
         const bool is_bulk = (c < nc - 1) && bounds[c] <= kBulkMaxPanels;
-        if (!is_bulk && (int)P.batches.size() < kMaxBatches - 4) { add_batch(by_cls[c], c); continue; }
+        if (!is_bulk && (int)P.batches.size() < kMaxBatches - h->n_regions) { add_batch(by_cls[c], c); continue; }
         const size_t n0 = bulk.size();
         bulk.insert(bulk.end(), by_cls[c].begin(), by_cls[c].end());
         std::inplace_merge(bulk.begin(), bulk.begin() + n0, bulk.end());
     }
     int64_t tot = 0;
     for (int b : bulk) tot += P.blocks[b].m;
-    const int nsub = (bulk.size() >= 256 && tot >= 100000) ? 4 : 1;
+    const int nsub = (bulk.size() >= 256 && tot >= 100000) ? h->n_regions : 1;
     size_t i = 0;
     int64_t acc = 0;
     for (int sb = 0; sb < nsub; ++sb) {
@@ -302,6 +312,16 @@ int make_batches(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, 
     for (int i = n_big + lead; i < nbt; ++i) P.up_order.push_back(i);
     return DBSLMM_B200_OK;
 }
+
+// A list that is built in place inside the pinned plan blob (no temporary vector -- a fresh 5 MB vector per fit costs
+// more in page faults than the list costs to fill -- and no copy into the blob afterwards).
+template <class T>
+struct BlobList {
+    T* p = nullptr;
+    size_t n = 0, cap = 0;
+    void push_back(const T& v) { if (n < cap) p[n] = v; ++n; }      // overflow is detected by the caller (n > cap)
+    size_t size() const { return n; }
+};
 
 // Step 2: device layout, Gram tiles, Cholesky step lists, the pinned blob.
 // Every block gets m genotype code rows followed by m call-mask code rows; which blocks really have missing calls is
@@ -371,9 +391,15 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
     }
     // upper bound of the list part: a split-K step has at most max(#tiles, 2 n_sm) items
     const size_t n_panel_max = n_steps_tiles + (size_t)3 * h->n_sm * kMaxBatches * (size_t)(P.max_mp / 64 + 2);
-    const size_t lists_max = sizeof(GramTile) * (n_t1 + n_t2) + sizeof(int32_t) * ((size_t)nb + n_diag_max) + sizeof(int4) * n_panel_max +
-                             sizeof(CUtensorMap) * (size_t)nb + 8 * 256;
-    if (h->h_blob.ensure(o + lists_max + 256) != cudaSuccess) return fail(h, DBSLMM_B200_ERR_NOMEM, "pinned plan buffer");
+    // ... and so are the places of the lists: the two Gram tile lists and the diagonal items have exact sizes, the panel
+    // items (split-K makes their number known only afterwards) go last
+    P.o_tiles_plain = place(sizeof(GramTile) * n_t1);
+    P.o_tiles_miss = place(sizeof(GramTile) * n_t2);
+    P.o_order = place(sizeof(int32_t) * (size_t)nb);
+    P.o_diag = place(sizeof(int32_t) * n_diag_max);
+    P.o_lmaps = place(sizeof(CUtensorMap) * (size_t)nb);     // filled by encode_lmaps once the L buffer exists
+    P.o_panel = place(0);
+    if (h->h_blob.ensure(o + sizeof(int4) * n_panel_max + 512) != cudaSuccess) return fail(h, DBSLMM_B200_ERR_NOMEM, "pinned plan buffer");
     struct { uint8_t* p; uint8_t* data() const { return p; } } blob{(uint8_t*)h->h_blob.p};
     std::memcpy(blob.data() + P.o_blocks, P.blocks.data(), sizeof(BlockDesc) * (size_t)nb);
     uint32_t* rs = reinterpret_cast<uint32_t*>(blob.data() + P.o_rowsrc);
@@ -433,9 +459,11 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
     // Gram tiles in batch order, big blocks first inside a batch: the lower triangle as 128 x 128 tiles for the one-plane
     // kernel and as 64-row x 128-column tiles for the four-plane kernel (every block is in both lists; the kernels pick
     // their blocks by the device-side flag)
-    std::vector<GramTile> tiles_plain, tiles_miss;
-    tiles_plain.reserve(n_t1);
-    tiles_miss.reserve(n_t2);
+    // (built by a helper thread while this thread builds the Cholesky step lists: the two touch different fields)
+    BlobList<GramTile> tiles_plain, tiles_miss;
+    tiles_plain.p = reinterpret_cast<GramTile*>(blob.data() + P.o_tiles_plain); tiles_plain.cap = n_t1;
+    tiles_miss.p = reinterpret_cast<GramTile*>(blob.data() + P.o_tiles_miss); tiles_miss.cap = n_t2;
+    std::thread tile_thread([&]() {
     for (Batch& B : P.batches) {
         B.tile0 = (int32_t)tiles_plain.size();
         B.mtile0 = (int32_t)tiles_miss.size();
@@ -460,13 +488,14 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
     }
     P.n_tiles_plain = (int32_t)tiles_plain.size();
     P.n_tiles_miss = (int32_t)tiles_miss.size();
+    });
+    struct TileJoiner { std::thread& t; ~TileJoiner() { if (t.joinable()) t.join(); } } tile_joiner{tile_thread};
 
-    if (tr) tr->mark("  plan: gram tiles");
     // Cholesky step lists per batch
-    std::vector<int32_t> diag_items;
-    std::vector<int4> panel_items;
-    diag_items.reserve(n_diag_max);
-    panel_items.reserve(n_panel_max);
+    BlobList<int32_t> diag_items;
+    BlobList<int4> panel_items;
+    diag_items.p = reinterpret_cast<int32_t*>(blob.data() + P.o_diag); diag_items.cap = n_diag_max;
+    panel_items.p = reinterpret_cast<int4*>(blob.data() + P.o_panel); panel_items.cap = n_panel_max;
     int32_t n_groups = 0;
     for (Batch& B : P.batches) {
         const int32_t* members = P.order.data() + B.ord_off;
@@ -529,27 +558,21 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
         P.scratch_doubles += batch_scratch;
     }
 
-    if (tr) tr->mark("  plan: step lists");
-    // ---- the list part of the blob
-    P.o_tiles_plain = place(sizeof(GramTile) * tiles_plain.size());
-    P.o_tiles_miss = place(sizeof(GramTile) * tiles_miss.size());
-    P.o_order = place(sizeof(int32_t) * (size_t)nb);
-    P.o_diag = place(sizeof(int32_t) * diag_items.size());
-    P.o_panel = place(sizeof(int4) * panel_items.size());
-    P.o_lmaps = place(sizeof(CUtensorMap) * (size_t)nb);     // filled by encode_lmaps once the L buffer exists
+    tile_thread.join();
+    if (tr) tr->mark("  plan: tile + step lists");
+    // ---- the lists were written in place; the panel items close the blob
+    if (tiles_plain.size() > tiles_plain.cap || tiles_miss.size() > tiles_miss.cap || diag_items.size() > diag_items.cap ||
+        panel_items.size() > panel_items.cap)
+        return fail(h, DBSLMM_B200_ERR_NOMEM, "pinned plan buffer: list bound exceeded");
+    place(sizeof(int4) * panel_items.size());
     P.lmaps_base = nullptr;
     P.n_groups = n_groups;
     P.blob_bytes = o;
-    if (o + 256 > h->h_blob.cap) return fail(h, DBSLMM_B200_ERR_NOMEM, "pinned plan buffer: list bound exceeded");
     for (std::thread& x : fill_threads) x.join();
     fill_threads.clear();
     if (fill_bad.load()) return fail(h, DBSLMM_B200_ERR_ARG, "s_pos / l_pos out of range of the loaded .bed");
     if (tr) tr->mark("  plan: per-SNP arrays");
-    if (!tiles_plain.empty()) std::memcpy(blob.data() + P.o_tiles_plain, tiles_plain.data(), sizeof(GramTile) * tiles_plain.size());
-    if (!tiles_miss.empty()) std::memcpy(blob.data() + P.o_tiles_miss, tiles_miss.data(), sizeof(GramTile) * tiles_miss.size());
     std::memcpy(blob.data() + P.o_order, P.order.data(), sizeof(int32_t) * (size_t)nb);
-    if (!diag_items.empty()) std::memcpy(blob.data() + P.o_diag, diag_items.data(), sizeof(int32_t) * diag_items.size());
-    if (!panel_items.empty()) std::memcpy(blob.data() + P.o_panel, panel_items.data(), sizeof(int4) * panel_items.size());
     P.valid = true;
     return DBSLMM_B200_OK;
 }
@@ -721,7 +744,10 @@ int dbslmm_b200_create(int device, dbslmm_b200_handle** out) {
     if (const char* e = std::getenv("DBSLMM_B200_DEFER_CTAS")) h->defer_max_ctas = std::atoi(e);
     if (const char* e = std::getenv("DBSLMM_B200_TILE64")) h->tile64_mode = std::atoi(e);
     if (const char* e = std::getenv("DBSLMM_B200_L2_PF")) h->l2_pf = std::max(0, std::atoi(e));
+    if (const char* e = std::getenv("DBSLMM_B200_ZEROCOPY_BETA")) h->zero_copy_beta = (e[0] != '0');
     if (const char* e = std::getenv("DBSLMM_B200_UPLOAD_BULK_FIRST")) h->upload_bulk_first = std::atoi(e);
+    if (const char* e = std::getenv("DBSLMM_B200_REGIONS")) h->n_regions = std::max(1, std::min(kMaxBatches - 4, std::atoi(e)));
+    if (const char* e = std::getenv("DBSLMM_B200_PREPLAN_MB")) h->preplan_mb = std::atof(e);
     if (const char* e = std::getenv("DBSLMM_B200_GRAM")) h->gram_packed = (std::strcmp(e, "packed") == 0);
     if (const char* e = std::getenv("DBSLMM_B200_PANEL")) h->panel_tma = (std::strcmp(e, "legacy") != 0);
     if (const char* e = std::getenv("DBSLMM_B200_TPC")) {         // "max[,waves]"
@@ -1028,7 +1054,20 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
             if (rc < 0) { P.valid = false; return rc; }
             // the biggest classes go out before the plan is built (the H2D queue is in issue order: the plan blob must
             // not wait behind the whole panel, and the DMA engine should not idle while the host builds the plan)
-            if (rc == 0) { rc = upload_issue(h, P, U, a->bed, std::min(2, (int)P.batches.size()), subset); if (rc < 0) { P.valid = false; return rc; } }
+            if (rc == 0) {
+                // how many batches go out before the plan exists: the first one, and more while they stay under preplan_mb
+                int n_pre = 0;
+                double mb = 0.0;
+                for (size_t ui = 0; ui < P.up_order.size(); ++ui) {
+                    double rows = 0.0;
+                    for (const UploadPlan::Range& x : U.per_batch[P.up_order[ui]]) rows += (double)(x.second - x.first + 1);
+                    mb += rows * (double)h->pitch / 1.0e6;
+                    if (n_pre > 0 && mb > h->preplan_mb) break;
+                    ++n_pre;
+                }
+                rc = upload_issue(h, P, U, a->bed, std::min(n_pre, (int)P.batches.size()), subset);
+                if (rc < 0) { P.valid = false; return rc; }
+            }
             tr.mark("first uploads issued");
             if (rc == 1) {
                 // not streamable: plain full upload, then the resident path
@@ -1113,7 +1152,8 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
     const int32_t* d_order = (const int32_t*)(dblob + P.o_order);
     const int32_t* d_diag = (const int32_t*)(dblob + P.o_diag);
     const int4* d_panel = (const int4*)(dblob + P.o_panel);
-    double* d_beta = (double*)h->beta.p;
+    const bool zc_beta = h->zero_copy_beta && !pcg;         // (the PCG kernel reads its own betas back: device buffer)
+    double* d_beta = zc_beta ? (double*)h->h_out.p : (double*)h->beta.p;
     int32_t* d_status = (int32_t*)h->status.p;
     int32_t* d_iters = d_status + nb;
 
@@ -1444,7 +1484,7 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
 
     // ---- download
     uint8_t* hout = (uint8_t*)h->h_out.p;
-    if (n_res) CU_TRY(h, cudaMemcpyAsync(hout, d_beta, sizeof(double) * n_res, cudaMemcpyDeviceToHost, st));
+    if (n_res && !zc_beta) CU_TRY(h, cudaMemcpyAsync(hout, d_beta, sizeof(double) * n_res, cudaMemcpyDeviceToHost, st));
     CU_TRY(h, cudaMemcpyAsync(hout + sizeof(double) * n_res, d_status, sizeof(int32_t) * (size_t)(2 * nb),
                               cudaMemcpyDeviceToHost, st));
     if (d_var) CU_TRY(h, cudaMemcpyAsync(a->variance_out, d_var, sizeof(double) * (size_t)a->n_folds * nb * P.n_test,
