@@ -627,7 +627,7 @@ def main():
             traffic = tj["dram_bytes_per_fit"]
     except Exception:
         pass
-    roofline = {"bound": "tensor", "kernel": "chol_panel_tma_kernel + chol_diag_kernel (all panel steps of one fit, all folds)",
+    roofline = {"bound": "tensor", "kernel": "chol_panel_tma_kernel<1> (64-row items, 128-thread CTAs) + chol_diag_kernel (all panel steps of one fit, all folds)",
                 "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak if fp64_peak else None,
                 "traffic": traffic,
                 "traffic_note": "dram__bytes_read+write summed over all chol_* launches of one fit (ncu, profiles/chol_traffic.json); "
@@ -672,7 +672,8 @@ def main():
             "e2e": {"value": e2e_v, "unit": "blocks/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": wall_e2e / K * 1e3,
                     "how": "one dbslmm_b200_fit call per step with fit_args.bed = pinned host .bed: batched H2D of the panel "
-                           "overlapped with decode/Gram/Cholesky, plan + z H2D, beta D2H; wall clock",
+                           "overlapped with decode/Gram/Cholesky, plan + z H2D, betas written by the back substitution into pinned host memory (D2H over PCIe, "
+                           "counted in d2h_bytes_per_step) and copied to the caller's arrays; wall clock",
                     "upload_then_fit_ms_per_step": wall_two_call * 1e3},
             "resident_wall_ms_per_step": wall_resident / K * 1e3,
             "gpu_launches": int(sum(t["n_launches"] for t in tms)) + (2 * K * ((len(folds) + 2) // 3) if val else 0),
