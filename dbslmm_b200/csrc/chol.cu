@@ -867,7 +867,14 @@ chol_panel_tma_kernel(const BlockDesc* __restrict__ blocks, const int4* __restri
     const uint32_t wlrow = (uint32_t)sigp * 128u;                // the same two for the W image (always permuted)
     const uint32_t wx0 = (uint32_t)((t ^ sigp) & 7) << 4;
     const int grp = warp >> 2;
-    uint32_t it = 0, wcount = 0;                                 // ring uses / W loads so far (all threads keep count)
+    // Ring bookkeeping: chunk c of EVERY item uses stage (c + 2) % 3, so chunk 0 always lands in stage 2 -- the one stage the
+    // epilogue (whose L halves live in boxes 0..3 = stages 0 and 1 of the 64-row shape) leaves alone, which lets thread 0
+    // issue the NEXT item's first chunk while this item's TRSM / SYRK run (`pre`).  Parity bit s of pprod / pcons = uses of
+    // stage s issued by the producer / consumed by this thread so far.
+    uint32_t pprod = 0, pcons = 0, wcount = 0;                   // (wcount: W loads so far; all threads keep count)
+    const int pf_dist = pf & 0xFF;
+    const bool next_pf = (NG == 1) && ((pf >> 8) & 1);
+    bool pre = false;
     int prev_blk = -1;
 
     for (int j = 0; j < n_my; ++j) {
@@ -891,34 +898,35 @@ chol_panel_tma_kernel(const BlockDesc* __restrict__ blocks, const int4* __restri
         const CUtensorMap* lm = lmaps + item.x;
         const bool two_row_boxes = (NG == 2) && prow > NB;
 
-        // ---- producer duties of thread 0.  Chunk c of this item is ring use u = it + c: stage u % 3, and it may be
-        // written once all consumer warps have released the stage's previous use.
-        auto issue_chunk = [&](int c) {
-            const uint32_t u = it + (uint32_t)c;
-            const int s = (int)(u % TP_NST);
-            mbar_wait(&bars.empty[s], ((u / TP_NST) & 1u) ^ 1u);
-            mbar_expect_tx(&bars.full[s], (uint32_t)((two_row_boxes ? 3 : 2) * BOXB));
-            const int k0 = q.kb + c * KC;
+        // ---- producer duties of thread 0.  Chunk c goes to stage (c + 2) % 3, which may be written once all consumer
+        // warps have released the stage's previous use.  (Geometry passed in: the same code issues the next item's chunk 0.)
+        auto issue_chunk_of = [&](const CUtensorMap* lm_, int kb_, int r0_, int pc0_, bool two_, int nchunk_, int c) {
+            const int s = (c + 2) % TP_NST;
+            mbar_wait(&bars.empty[s], ((pprod >> s) & 1u) ^ 1u);
+            pprod ^= 1u << s;
+            mbar_expect_tx(&bars.full[s], (uint32_t)((two_ ? 3 : 2) * BOXB));
+            const int k0 = kb_ + c * KC;
             if (perm) {
                 const uint32_t st = sbase + (uint32_t)s * SB * BOXB;
-                tma_load_4d(st, lm, k0, 0, 0, r0 >> 3, &bars.full[s]);
-                if (two_row_boxes) tma_load_4d(st + BOXB, lm, k0, 0, 0, (r0 >> 3) + 8, &bars.full[s]);
-                tma_load_4d(st + NG * BOXB, lm, k0, 0, 0, pc0 >> 3, &bars.full[s]);
-                if (pf > 0 && c + pf < nchunk) {
-                    tma_prefetch_4d(lm, k0 + pf * KC, 0, 0, r0 >> 3);
-                    if (two_row_boxes) tma_prefetch_4d(lm, k0 + pf * KC, 0, 0, (r0 >> 3) + 8);
+                tma_load_4d(st, lm_, k0, 0, 0, r0_ >> 3, &bars.full[s]);
+                if (two_) tma_load_4d(st + BOXB, lm_, k0, 0, 0, (r0_ >> 3) + 8, &bars.full[s]);
+                tma_load_4d(st + NG * BOXB, lm_, k0, 0, 0, pc0_ >> 3, &bars.full[s]);
+                if (pf_dist > 0 && c + pf_dist < nchunk_) {
+                    tma_prefetch_4d(lm_, k0 + pf_dist * KC, 0, 0, r0_ >> 3);
+                    if (two_) tma_prefetch_4d(lm_, k0 + pf_dist * KC, 0, 0, (r0_ >> 3) + 8);
                 }
             } else {
                 uint8_t* sp = smem_al + (size_t)s * SB * BOXB;
-                tma_load_2d(sp, lm, k0, r0, &bars.full[s]);
-                if (two_row_boxes) tma_load_2d(sp + BOXB, lm, k0, r0 + NB, &bars.full[s]);
-                tma_load_2d(sp + NG * BOXB, lm, k0, pc0, &bars.full[s]);
-                if (pf > 0 && c + pf < nchunk) {
-                    tma_prefetch_2d(lm, k0 + pf * KC, r0);
-                    if (two_row_boxes) tma_prefetch_2d(lm, k0 + pf * KC, r0 + NB);
+                tma_load_2d(sp, lm_, k0, r0_, &bars.full[s]);
+                if (two_) tma_load_2d(sp + BOXB, lm_, k0, r0_ + NB, &bars.full[s]);
+                tma_load_2d(sp + NG * BOXB, lm_, k0, pc0_, &bars.full[s]);
+                if (pf_dist > 0 && c + pf_dist < nchunk_) {
+                    tma_prefetch_2d(lm_, k0 + pf_dist * KC, r0_);
+                    if (two_) tma_prefetch_2d(lm_, k0 + pf_dist * KC, r0_ + NB);
                 }
             }
         };
+        auto issue_chunk = [&](int c) { issue_chunk_of(lm, q.kb, r0, pc0, two_row_boxes, nchunk, c); };
         auto issue_w = [&]() {
             mbar_expect_tx(&bars.w_full, W_IMG_BYTES);
             bulk_g2s(wimg, wbuf + wpar + (size_t)item.x * (NB * NB), W_IMG_BYTES, &bars.w_full);
@@ -927,8 +935,9 @@ chol_panel_tma_kernel(const BlockDesc* __restrict__ blocks, const int4* __restri
             if (load_w) tensormap_acquire(lm);
             // the ring first (it gates the main loop), then W_kk (needed only by the epilogue)
             if (j > 0) mbar_wait(&bars.ring_free, (uint32_t)((j - 1) & 1));
-            if (nchunk > 0) issue_chunk(0);
+            if (nchunk > 0 && !pre) issue_chunk(0);          // (pre: already in flight since the previous item's epilogue)
             if (nchunk > 1) issue_chunk(1);
+            pre = false;
             if (load_w && !wait_w) {
                 if (j > 0) mbar_wait(&bars.w_free, (uint32_t)((j - 1) & 1));
                 issue_w();
@@ -957,13 +966,13 @@ chol_panel_tma_kernel(const BlockDesc* __restrict__ blocks, const int4* __restri
         // in a few percent of the blocks once three CTAs per SM kept that pipe busy (tools/stream_vs_resident.py,
         // tools/l_diff.py: one warp's 16 rows, last column groups of a panel).  The spin loop of the wait is a point the
         // arrive cannot be hoisted across.
+        int s = TP_NST - 1, s_prev = 0;
         for (int kc = 0; kc < nchunk; ++kc) {
-            const uint32_t u = it + (uint32_t)kc;
-            const int s = (int)(u % TP_NST);
-            mbar_wait(&bars.full[s], (u / TP_NST) & 1u);
+            mbar_wait(&bars.full[s], (pcons >> s) & 1u);
+            pcons ^= 1u << s;
             if (kc > 0) {
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&bars.empty[(int)((u - 1) % TP_NST)]);
+                if (lane == 0) mbar_arrive(&bars.empty[s_prev]);
             }
             if (tid == 0 && kc + 2 < nchunk) issue_chunk(kc + 2);
             if (active) {
@@ -994,8 +1003,9 @@ chol_panel_tma_kernel(const BlockDesc* __restrict__ blocks, const int4* __restri
                     }
                 }
             }
+            s_prev = s;
+            s = (s == TP_NST - 1) ? 0 : s + 1;
         }
-        it += (uint32_t)nchunk;
         if (wait_w && load_w && tid == 0) {
             // W_k is being produced by a diagonal CTA of THIS launch (lower blockIdx: resident or done)
             const volatile int32_t* fl = dflag + item.x;
@@ -1007,7 +1017,7 @@ chol_panel_tma_kernel(const BlockDesc* __restrict__ blocks, const int4* __restri
         __syncthreads();          // every warp is done with the ring: its boxes become the epilogue's L halves
         if (nchunk > 0) {         // the last chunk's stage (behind the barrier: see the main loop)
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bars.empty[(int)((it - 1) % TP_NST)]);
+            if (lane == 0) mbar_arrive(&bars.empty[s_prev]);
         }
 
         {
@@ -1024,6 +1034,13 @@ chol_panel_tma_kernel(const BlockDesc* __restrict__ blocks, const int4* __restri
             const TpGeom q2 = tp_geom<TMR>(bd2, item2, k);
             if (q2.slice == 0 && tid < q2.prow)
                 l2_prefetch_bulk(sigma + bd2.moff + (size_t)(q2.r0 + tid) * bd2.ld + q2.pc0, (uint32_t)(q2.wk * 8));
+            if (next_pf && tid == 0 && q2.ke > q2.kb) {
+                // ... and its first chunk into stage 2, which the epilogue does not touch: the next main loop starts warm
+                const CUtensorMap* lm2 = lmaps + item2.x;
+                if (item2.x != item.x) tensormap_acquire(lm2);
+                issue_chunk_of(lm2, q2.kb, q2.r0, q2.pc0, false, (q2.ke - q2.kb) / KC, 0);
+                pre = true;
+            }
         }
 
         if (q.nsl > 1) {

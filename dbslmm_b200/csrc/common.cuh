@@ -29,11 +29,21 @@ struct BlockDesc {
     int32_t nrows;          // matrix rows: mp + 8 (z row group) + appended test-genotype rows (variance side channel)
 };
 
-struct GramTile {           // one 128x128 output tile of a block's lower triangle
+struct GramTile {           // one 128x128 output tile of a block's lower triangle (256 x 256 in the CTA-pair list)
     int32_t blk;
     int32_t ti;             // tile row   (rows  ti*128 .. of the block)  -> "I" side
     int32_t tj;             // tile col   (cols  tj*128 ..)               -> "J" side, tj <= ti
     int32_t pad;
+};
+
+// One tile of the one-plane Gram kernels with everything the kernel needs about its block (48 bytes = three 16-byte loads):
+// a role fetches the record of tile n+1 while it works on tile n, so no dependent tile -> block -> constants chain of
+// global loads sits between two tiles.
+struct TileRec {
+    int32_t blk, ti, tj, croff;
+    int32_t goff, m, mp, ld;
+    int64_t moff;
+    int64_t pad;
 };
 
 // ----------------------------------------------------------------------------------------
@@ -89,6 +99,14 @@ __device__ __forceinline__ void tma_load_2d(void* dst_smem, const void* tmap, in
         "l"(tmap), "r"(smem_u32(bar)), "r"(x), "r"(y)
         : "memory");
 }
+// the same with an L2 eviction-priority hint (0x14F0000000000000 = evict last, 0x12F0000000000000 = evict first)
+__device__ __forceinline__ void tma_load_2d_hint(void* dst_smem, const void* tmap, int32_t x, int32_t y, uint64_t* bar, uint64_t hint) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::
+            "r"(smem_u32(dst_smem)),
+        "l"(tmap), "r"(smem_u32(bar)), "r"(x), "r"(y), "l"(hint)
+        : "memory");
+}
 // 4-D tiled TMA load (SASS UTMALDG): the FP64 panel operands of the block solver (chol.cu) -- the two middle
 // dimensions permute the rows of every 8-row group on their way into shared memory.
 __device__ __forceinline__ void tma_load_4d(uint32_t dst_smem, const void* tmap, int32_t c0, int32_t c1, int32_t c2,
@@ -141,6 +159,23 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "d"(a), "d"(b));
 }
 
+// One lane of a fully active, converged warp (the same lane every time for the same mask).  The TMA-producer and MMA-issuer
+// loops run with the WHOLE warp and guard only the issuing instructions with this: inside an `if (lane == 0)` region the
+// compiler cannot prove that the operands of UTMALDG / UTCIMMA / UTCBAR (uniform registers) are warp-uniform and wraps
+// every one of them in a vote / elect / broadcast loop (~18 SASS instructions each).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+// Exact u32 -> f64 on the FP64 pipe: 2^52 + u as a bit pattern, minus 2^52 (one DADD).  The I2F.F64 the compiler emits for
+// (double)int runs on the XU pipe at ~2 results per clock and SM on sm_100a (measured: 77 % XU-busy Gram epilogues, ncu
+// round 2) -- a 128 x 128 tile of conversions then costs more than its 64 int8 MMAs.
+__device__ __forceinline__ double u32_to_f64(uint32_t u) {
+    return __hiloint2double(0x43300000, (int)u) - 4503599627370496.0;
+}
+
 // ---- tcgen05 / TMEM ---------------------------------------------------------------------
 template <uint32_t NCOLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot_smem) {   // whole warp
@@ -171,6 +206,63 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
 }
+// ---- CTA pairs (tcgen05 cta_group::2): two CTAs of a 2-CTA cluster share one MMA of M = 256 ------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <uint32_t NCOLS>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* slot_smem) {   // whole warp, the same warp of BOTH CTAs
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_smem)),
+                 "n"(NCOLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t NCOLS>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {      // whole warp, the same warp of BOTH CTAs
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+// 2-D tiled TMA load into THIS CTA's shared memory whose completion bytes are counted on the LEADER CTA's mbarrier
+// (the barrier at the same offset in cluster rank 0: the peer bit, bit 24 of a shared-window address, cleared).
+__device__ __forceinline__ void tma_load_2d_pair(void* dst_smem, const void* tmap, int32_t x, int32_t y, uint64_t* bar, uint64_t hint) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::
+            "r"(smem_u32(dst_smem)),
+        "l"(tmap), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(x), "r"(y), "l"(hint)
+        : "memory");
+}
+// D[tmem of both CTAs] (+)= A * B over the CTA pair: M = 256 (128 rows of A per CTA), B = N/2 rows per CTA.  Leader only.
+__device__ __forceinline__ void umma_i8_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on the mbarrier at this offset in BOTH CTAs when all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+// arrive on the mbarrier at this offset in cluster rank `rank` (no cluster-scope release: what it orders here is a TMEM
+// read, fenced by tcgen05.fence::before_thread_sync; a .release.cluster would wait for every global store in flight)
+__device__ __forceinline__ void mbar_arrive_rank(uint64_t* bar, uint32_t rank) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
+        "r"(rank)
+        : "memory");
+}
+
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive 32-bit columns (SASS LDTM)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(

@@ -139,7 +139,7 @@ decode_rows_kernel(const uint8_t* __restrict__ bed, int32_t n_ref, int32_t pitch
                    int32_t buf_bytes, const uint32_t* __restrict__ row_src, const int32_t* __restrict__ row_crow,
                    const int32_t* __restrict__ row_mrow, int64_t g0, int64_t n_rows, double tau,
                    int8_t* __restrict__ codes, uint8_t* __restrict__ dirty, int32_t* __restrict__ rowN,
-                   int32_t* __restrict__ rowS, double* __restrict__ rowR, const int32_t* __restrict__ gate) {
+                   int32_t* __restrict__ rowS, double* __restrict__ rowR, double2* __restrict__ rowC, const int32_t* __restrict__ gate) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bars[kWarpsPerCta][kDecRing];
     // gate (fused-Gram pipeline): int8 rows are needed only by blocks with missing calls; *gate == 0 says there are none
@@ -248,7 +248,9 @@ decode_rows_kernel(const uint8_t* __restrict__ bed, int32_t n_ref, int32_t pitch
             const double n = (double)n_ref;
             rowN[g] = nn;
             rowS[g] = sum;
-            rowR[g] = sqrt(tau * (n - 1.0) / (n * ni * d));
+            const double rr = sqrt(tau * (n - 1.0) / (n * ni * d));
+            rowR[g] = rr;
+            rowC[g] = make_double2((double)sum, rr);      // {S_i, r_i} as one 16-byte record: the Gram epilogues stage it with cp.async
         }
         __syncwarp();
         cur = (cur + 1 == kDecRing) ? 0 : cur + 1;
@@ -268,7 +270,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32)
 pack_rows_kernel(const uint8_t* __restrict__ bed, int32_t n_ref, int32_t pitch, int32_t n_pad, int32_t buf_bytes,
                  const uint32_t* __restrict__ row_src, int64_t g0, int64_t n_rows, double tau,
                  uint32_t* __restrict__ packed, int32_t* __restrict__ rowN, int32_t* __restrict__ rowS,
-                 double* __restrict__ rowR) {
+                 double* __restrict__ rowR, double2* __restrict__ rowC) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bars[kWarpsPerCta][kDecRing];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -348,7 +350,9 @@ pack_rows_kernel(const uint8_t* __restrict__ bed, int32_t n_ref, int32_t pitch, 
             const double n = (double)n_ref;
             rowN[g] = nn;
             rowS[g] = sum;
-            rowR[g] = sqrt(tau * (n - 1.0) / (n * ni * d));
+            const double rr = sqrt(tau * (n - 1.0) / (n * ni * d));
+            rowR[g] = rr;
+            rowC[g] = make_double2((double)sum, rr);      // {S_i, r_i} as one 16-byte record: the Gram epilogues stage it with cp.async
         }
         __syncwarp();
         cur = (cur + 1 == kDecRing) ? 0 : cur + 1;
@@ -424,7 +428,7 @@ template <int RING>
 static cudaError_t launch_decode_t(const uint8_t* bed, int32_t n_ref, int32_t pitch, int32_t n_pad, int buf, int wpc,
                                    const uint32_t* row_src, const int32_t* row_crow, const int32_t* row_mrow, int64_t g0,
                                    int64_t n_rows, double tau, int8_t* codes, uint8_t* dirty, int32_t* rowN, int32_t* rowS,
-                                   double* rowR, const int32_t* gate, int n_sm, cudaStream_t st) {
+                                   double* rowR, double2* rowC, const int32_t* gate, int n_sm, cudaStream_t st) {
     const size_t smem = (size_t)wpc * RING * buf;
     cudaError_t e = cudaFuncSetAttribute(decode_rows_kernel<RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -432,14 +436,14 @@ static cudaError_t launch_decode_t(const uint8_t* bed, int32_t n_ref, int32_t pi
     const int64_t cap = (int64_t)n_sm * 8;
     if (ctas > cap) ctas = cap;
     decode_rows_kernel<RING><<<(unsigned)ctas, wpc * 32, smem, st>>>(bed, n_ref, pitch, n_pad, buf, row_src, row_crow, row_mrow, g0,
-                                                                   n_rows, tau, codes, dirty, rowN, rowS, rowR, gate);
+                                                                   n_rows, tau, codes, dirty, rowN, rowS, rowR, rowC, gate);
     return cudaGetLastError();
 }
 
 template <int RING>
 static cudaError_t launch_pack_t(const uint8_t* bed, int32_t n_ref, int32_t pitch, int32_t n_pad, int buf, int wpc,
                                  const uint32_t* row_src, int64_t g0, int64_t n_rows, double tau, uint32_t* packed,
-                                 int32_t* rowN, int32_t* rowS, double* rowR, int n_sm, cudaStream_t st) {
+                                 int32_t* rowN, int32_t* rowS, double* rowR, double2* rowC, int n_sm, cudaStream_t st) {
     const size_t smem = (size_t)wpc * RING * buf;
     cudaError_t e = cudaFuncSetAttribute(pack_rows_kernel<RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -447,26 +451,26 @@ static cudaError_t launch_pack_t(const uint8_t* bed, int32_t n_ref, int32_t pitc
     const int64_t cap = (int64_t)n_sm * 8;
     if (ctas > cap) ctas = cap;
     pack_rows_kernel<RING><<<(unsigned)ctas, wpc * 32, smem, st>>>(bed, n_ref, pitch, n_pad, buf, row_src, g0, n_rows, tau, packed,
-                                                                 rowN, rowS, rowR);
+                                                                 rowN, rowS, rowR, rowC);
     return cudaGetLastError();
 }
 // SNP rows [g0, g0 + n_rows) of the plan -> packed 2-bit rows (pitch n_pad / 4 bytes, row g at packed + g * n_pad / 16 words)
 cudaError_t launch_pack_rows(const uint8_t* bed, int32_t n_ref, int32_t n_pad, const uint32_t* row_src, int64_t g0, int64_t n_rows,
-                             double tau, uint32_t* packed, int32_t* rowN, int32_t* rowS, double* rowR, int n_sm, cudaStream_t st) {
+                             double tau, uint32_t* packed, int32_t* rowN, int32_t* rowS, double* rowR, double2* rowC, int n_sm, cudaStream_t st) {
     if (n_rows == 0) return cudaSuccess;
     const int32_t pitch = (n_ref + 3) / 4;
     const int buf = stage_bytes(pitch);
     if (stage_warps(buf, 4) == kWarpsPerCta)
-        return launch_pack_t<4>(bed, n_ref, pitch, n_pad, buf, kWarpsPerCta, row_src, g0, n_rows, tau, packed, rowN, rowS, rowR, n_sm, st);
+        return launch_pack_t<4>(bed, n_ref, pitch, n_pad, buf, kWarpsPerCta, row_src, g0, n_rows, tau, packed, rowN, rowS, rowR, rowC, n_sm, st);
     const int wpc = stage_warps(buf, 2);
     if (wpc < 1) return cudaErrorInvalidValue;
-    return launch_pack_t<2>(bed, n_ref, pitch, n_pad, buf, wpc, row_src, g0, n_rows, tau, packed, rowN, rowS, rowR, n_sm, st);
+    return launch_pack_t<2>(bed, n_ref, pitch, n_pad, buf, wpc, row_src, g0, n_rows, tau, packed, rowN, rowS, rowR, rowC, n_sm, st);
 }
 
 // SNP rows [g0, g0 + n_rows) of the plan
 cudaError_t launch_decode_rows(const uint8_t* bed, int32_t n_ref, int32_t n_pad, const uint32_t* row_src,
                                const int32_t* row_crow, const int32_t* row_mrow, int64_t g0, int64_t n_rows, double tau,
-                               int8_t* codes, uint8_t* dirty, int32_t* rowN, int32_t* rowS, double* rowR, const int32_t* gate,
+                               int8_t* codes, uint8_t* dirty, int32_t* rowN, int32_t* rowS, double* rowR, double2* rowC, const int32_t* gate,
                                int n_sm, cudaStream_t st) {
     if (n_rows == 0) return cudaSuccess;
     const int32_t pitch = (n_ref + 3) / 4;
@@ -474,10 +478,10 @@ cudaError_t launch_decode_rows(const uint8_t* bed, int32_t n_ref, int32_t n_pad,
     // four staging buffers per warp and eight warps per CTA while they fit; long rows fall back to two buffers, then
     // to fewer warps (n_ref up to decode_max_n_ref())
     if (stage_warps(buf, 4) == kWarpsPerCta)
-        return launch_decode_t<4>(bed, n_ref, pitch, n_pad, buf, kWarpsPerCta, row_src, row_crow, row_mrow, g0, n_rows, tau, codes, dirty, rowN, rowS, rowR, gate, n_sm, st);
+        return launch_decode_t<4>(bed, n_ref, pitch, n_pad, buf, kWarpsPerCta, row_src, row_crow, row_mrow, g0, n_rows, tau, codes, dirty, rowN, rowS, rowR, rowC, gate, n_sm, st);
     const int wpc = stage_warps(buf, 2);
     if (wpc < 1) return cudaErrorInvalidValue;
-    return launch_decode_t<2>(bed, n_ref, pitch, n_pad, buf, wpc, row_src, row_crow, row_mrow, g0, n_rows, tau, codes, dirty, rowN, rowS, rowR, gate, n_sm, st);
+    return launch_decode_t<2>(bed, n_ref, pitch, n_pad, buf, wpc, row_src, row_crow, row_mrow, g0, n_rows, tau, codes, dirty, rowN, rowS, rowR, rowC, gate, n_sm, st);
 }
 
 }  // namespace dbslmm

@@ -83,6 +83,7 @@ struct Batch {
     int64_t grow0 = 0, grow1 = 0;         // SNP rows of the members (contiguous only in the streaming layout)
     int32_t tile0 = 0, tile1 = 0;         // range of the one-plane Gram tile list (128 x 128 tiles)
     int32_t mtile0 = 0, mtile1 = 0;       // range of the four-plane Gram tile list (64-row x 128-column tiles)
+    int32_t ptile0 = 0, ptile1 = 0;       // range of the one-plane kernels' tile RECORD list (128 x 128 tiles, or 256 x 256 super tiles for the CTA-pair kernel)
     std::vector<StepList> steps;          // per panel step
     int64_t scratch_off = 0;              // split-K scratch region (doubles)
 };
@@ -99,12 +100,12 @@ struct Plan {
     std::vector<Batch> batches;
     bool streaming = false;                           // layout in batch order (else block-index order)
     std::vector<int32_t> up_order;                    // streaming: the order in which the batches' rows cross PCIe
-    int32_t n_tiles_plain = 0, n_tiles_miss = 0;
+    int32_t n_tiles_plain = 0, n_tiles_miss = 0, n_tiles_pair = 0;
     int64_t scratch_doubles = 0;
     int32_t n_groups = 0;                             // split-K groups (one arrival counter each)
     int32_t n_test = 0;                               // selected test individuals (variance side channel), 0 = off
     // blob layout (byte offsets inside the plan blob, identical on host and device)
-    size_t o_blocks = 0, o_rowsrc = 0, o_crow = 0, o_mrow = 0, o_z = 0, o_tiles_plain = 0, o_tiles_miss = 0, o_order = 0,
+    size_t o_blocks = 0, o_rowsrc = 0, o_crow = 0, o_mrow = 0, o_z = 0, o_tiles_plain = 0, o_tiles_miss = 0, o_tiles_pair = 0, o_order = 0,
            o_diag = 0, o_panel = 0, o_lmaps = 0, blob_bytes = 0;
     const void* lmaps_base = nullptr;                 // L buffer the per-block tensor maps in the blob were encoded for
     uint64_t fingerprint = 0;                         // of the inputs the plan was built from (FLAG_PLAN_CACHED re-use check)
@@ -143,6 +144,7 @@ struct dbslmm_b200_handle {
     // The back substitution writes the betas straight into the pinned result buffer (mapped host memory: 9 MB spread over the
     // whole fit) instead of a device buffer that is copied back when everything is done (0.47 ms at C3, all of it exposed).
     bool zero_copy_beta = true;
+    int next_pf = 1;                             // panel kernel (64-row items): the next item's first chunk is issued during the epilogue (DBSLMM_B200_NEXT_PF=0: off)
     int l2_pf = 0;                               // panel kernel: L2 tensor prefetch distance in 16-wide K chunks (0 = off: measured 13.0 ms without, 13.1 with 2 or 4)
     // panel step kernel: TMA/mbarrier pipeline (default) or the cp.async version (DBSLMM_B200_PANEL=legacy)
     int upload_bulk_first = 1;                   // streaming fit: bulk regions sent before the big classes (see make_batches)
@@ -151,12 +153,15 @@ struct dbslmm_b200_handle {
     // plan takes to build: with 4 regions (138 MB each at C3) the blob arrived 4.1 ms after the call started, with 6
     // (92 MB) it arrives at ~2.7 ms, and the first decode starts that much earlier.
     int n_regions = 6;
+    double first_region = 1.0;                   // SNP share of the FIRST bulk region relative to an equal share (< 1: a small first region crosses PCIe sooner, so the first decode / Gram / Cholesky start sooner; DBSLMM_B200_FIRST_REGION)
     double preplan_mb = 60.0;                    // ... and at most this much panel data is queued ahead of the plan blob
     // correlation builder for blocks without missing calls: the int8-row kernel fed by the decoder (default), or the fused
     // unpack + Gram from packed 2-bit rows (DBSLMM_B200_GRAM=packed).  Measured on C3 / C5: 1.8 / 10.8 ms against 3.9 / 34.7 ms --
     // expanding the operands in shared memory (8 unpack warps, generic-proxy stores + fence.proxy.async per K step) costs
     // more than the L2 traffic it saves, so the fused kernel stays an experiment.
     bool gram_packed = false;
+    int gram_hint = 0;                          // DBSLMM_B200_GRAM_HINT: tuning bits of GramArgs.hint
+    bool gram_pair = true;                      // one-plane Gram by CTA pairs (256 x 256 super tiles); DBSLMM_B200_GRAM=single: 128 x 128 tiles
     bool panel_tma = true;
     int tpc_max = 4, tpc_waves = 2;              // items per CTA: at most tpc_max, and only while a step keeps >= tpc_waves waves of CTAs
     int tmap_perm = -1;                          // 1: 4-D row-permuting tensor maps, 0: plain 2-D maps (driver refused), -1: not probed yet
@@ -170,7 +175,7 @@ struct dbslmm_b200_handle {
     int64_t n_snp = 0;
     int32_t n_ref = 0, pitch = 0, n_pad = 0;
     // workspace
-    DevBuf codes, sigma, lbuf, rowN, rowS, rowR, planblob, beta, status, intQ, intA, intN, scratch, counters, wbuf, vbed, vstats, vwork, dflag, dirty, bflags, packed;
+    DevBuf codes, sigma, lbuf, rowN, rowS, rowR, planblob, beta, status, intQ, intA, intN, scratch, counters, wbuf, vbed, vstats, vwork, dflag, dirty, bflags, packed, rowC;
     // validation panel of the scoring step, announced by dbslmm_b200_score_prefetch: uploaded in the shadow of the next fit
     const uint8_t* val_host = nullptr;
     int64_t val_n_snp = 0;
@@ -293,8 +298,10 @@ int make_batches(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, 
     const int nsub = (bulk.size() >= 256 && tot >= 100000) ? h->n_regions : 1;
     size_t i = 0;
     int64_t acc = 0;
+    // region sb ends at SNP count `target`: equal shares, except that the first region may be a fraction of a share
+    const double share0 = (nsub > 1) ? h->first_region / (double)nsub : 1.0;
     for (int sb = 0; sb < nsub; ++sb) {
-        const int64_t target = tot * (sb + 1) / nsub;
+        const int64_t target = (nsub > 1) ? (int64_t)((double)tot * (share0 + (1.0 - share0) * (double)sb / (double)(nsub - 1))) : tot;
         std::vector<int32_t> sub;
         while (i < bulk.size() && (sb == nsub - 1 || acc < target)) { acc += P.blocks[bulk[i]].m; sub.push_back(bulk[i]); ++i; }
         add_batch(sub, (sb & 1) ? 0 : 1);
@@ -376,12 +383,14 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
     P.o_crow = place(sizeof(int32_t) * (size_t)goff);
     P.o_mrow = place(sizeof(int32_t) * (size_t)goff);
     P.o_z = place(sizeof(double) * (size_t)goff);
-    size_t n_t1 = 0, n_t2 = 0, n_steps_tiles = 0, n_diag_max = 0;
+    size_t n_t1 = 0, n_t2 = 0, n_t3 = 0, n_steps_tiles = 0, n_diag_max = 0;
     for (int b = 0; b < nb; ++b) {
         const BlockDesc& d = P.blocks[b];
         const size_t nt = (size_t)(d.mp + 127) / 128, nt64 = (size_t)(d.mp + 63) / 64;
         n_t1 += nt * (nt + 1) / 2;
         n_t2 += nt64 * (nt64 / 2 + 1);
+        const size_t np = h->gram_pair ? (size_t)(d.mp + 255) / 256 : nt;
+        n_t3 += np * (np + 1) / 2;
         const int K = (d.mp + 63) / 64;
         n_diag_max += (size_t)K;
         for (int k = 0; k < K; ++k) {
@@ -393,8 +402,10 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
     const size_t n_panel_max = n_steps_tiles + (size_t)3 * h->n_sm * kMaxBatches * (size_t)(P.max_mp / 64 + 2);
     // ... and so are the places of the lists: the two Gram tile lists and the diagonal items have exact sizes, the panel
     // items (split-K makes their number known only afterwards) go last
+    if (!h->gram_packed) n_t1 = 0;            // the 128 x 128 GramTile list feeds only the packed-row kernel; the others read records
     P.o_tiles_plain = place(sizeof(GramTile) * n_t1);
     P.o_tiles_miss = place(sizeof(GramTile) * n_t2);
+    P.o_tiles_pair = place(sizeof(TileRec) * n_t3);
     P.o_order = place(sizeof(int32_t) * (size_t)nb);
     P.o_diag = place(sizeof(int32_t) * n_diag_max);
     P.o_lmaps = place(sizeof(CUtensorMap) * (size_t)nb);     // filled by encode_lmaps once the L buffer exists
@@ -461,12 +472,17 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
     // their blocks by the device-side flag)
     // (built by a helper thread while this thread builds the Cholesky step lists: the two touch different fields)
     BlobList<GramTile> tiles_plain, tiles_miss;
+    BlobList<TileRec> tiles_pair;
+    tiles_pair.p = reinterpret_cast<TileRec*>(blob.data() + P.o_tiles_pair); tiles_pair.cap = n_t3;
+    const bool want_plain = h->gram_packed;
+    const int rec_edge = h->gram_pair ? 256 : 128;
     tiles_plain.p = reinterpret_cast<GramTile*>(blob.data() + P.o_tiles_plain); tiles_plain.cap = n_t1;
     tiles_miss.p = reinterpret_cast<GramTile*>(blob.data() + P.o_tiles_miss); tiles_miss.cap = n_t2;
     std::thread tile_thread([&]() {
     for (Batch& B : P.batches) {
         B.tile0 = (int32_t)tiles_plain.size();
         B.mtile0 = (int32_t)tiles_miss.size();
+        B.ptile0 = (int32_t)tiles_pair.size();
         B.grow0 = INT64_MAX;
         B.grow1 = 0;
         for (int i = 0; i < B.ord_n; ++i) {
@@ -476,18 +492,23 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
             B.grow0 = std::min<int64_t>(B.grow0, d.goff);
             B.grow1 = std::max<int64_t>(B.grow1, (int64_t)d.goff + d.m);
             const int nt = (d.mp + 127) / 128;
-            for (int ti = 0; ti < nt; ++ti)
+            for (int ti = 0; ti < nt && want_plain; ++ti)
                 for (int tj = 0; tj <= ti; ++tj) tiles_plain.push_back({b, ti, tj, 0});
             const int nt64 = (d.mp + 63) / 64;
             for (int ti = 0; ti < nt64; ++ti)
                 for (int tj = 0; 128 * tj <= 64 * ti + 63; ++tj) tiles_miss.push_back({b, ti, tj, 0});
+            const int np = (d.mp + rec_edge - 1) / rec_edge;
+            for (int ti = 0; ti < np; ++ti)
+                for (int tj = 0; tj <= ti; ++tj) tiles_pair.push_back(TileRec{b, ti, tj, d.croff, d.goff, d.m, d.mp, d.ld, d.moff, 0});
         }
         if (B.grow0 == INT64_MAX) B.grow0 = B.grow1 = 0;
         B.tile1 = (int32_t)tiles_plain.size();
         B.mtile1 = (int32_t)tiles_miss.size();
+        B.ptile1 = (int32_t)tiles_pair.size();
     }
     P.n_tiles_plain = (int32_t)tiles_plain.size();
     P.n_tiles_miss = (int32_t)tiles_miss.size();
+    P.n_tiles_pair = (int32_t)tiles_pair.size();
     });
     struct TileJoiner { std::thread& t; ~TileJoiner() { if (t.joinable()) t.join(); } } tile_joiner{tile_thread};
 
@@ -561,7 +582,7 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
     tile_thread.join();
     if (tr) tr->mark("  plan: tile + step lists");
     // ---- the lists were written in place; the panel items close the blob
-    if (tiles_plain.size() > tiles_plain.cap || tiles_miss.size() > tiles_miss.cap || diag_items.size() > diag_items.cap ||
+    if (tiles_plain.size() > tiles_plain.cap || tiles_miss.size() > tiles_miss.cap || tiles_pair.size() > tiles_pair.cap || diag_items.size() > diag_items.cap ||
         panel_items.size() > panel_items.cap)
         return fail(h, DBSLMM_B200_ERR_NOMEM, "pinned plan buffer: list bound exceeded");
     place(sizeof(int4) * panel_items.size());
@@ -743,12 +764,18 @@ int dbslmm_b200_create(int device, dbslmm_b200_handle** out) {
     }
     if (const char* e = std::getenv("DBSLMM_B200_DEFER_CTAS")) h->defer_max_ctas = std::atoi(e);
     if (const char* e = std::getenv("DBSLMM_B200_TILE64")) h->tile64_mode = std::atoi(e);
-    if (const char* e = std::getenv("DBSLMM_B200_L2_PF")) h->l2_pf = std::max(0, std::atoi(e));
+    if (const char* e = std::getenv("DBSLMM_B200_L2_PF")) h->l2_pf = std::min(255, std::max(0, std::atoi(e)));
+    if (const char* e = std::getenv("DBSLMM_B200_NEXT_PF")) h->next_pf = std::atoi(e) != 0;
     if (const char* e = std::getenv("DBSLMM_B200_ZEROCOPY_BETA")) h->zero_copy_beta = (e[0] != '0');
     if (const char* e = std::getenv("DBSLMM_B200_UPLOAD_BULK_FIRST")) h->upload_bulk_first = std::atoi(e);
     if (const char* e = std::getenv("DBSLMM_B200_REGIONS")) h->n_regions = std::max(1, std::min(kMaxBatches - 4, std::atoi(e)));
     if (const char* e = std::getenv("DBSLMM_B200_PREPLAN_MB")) h->preplan_mb = std::atof(e);
-    if (const char* e = std::getenv("DBSLMM_B200_GRAM")) h->gram_packed = (std::strcmp(e, "packed") == 0);
+    if (const char* e = std::getenv("DBSLMM_B200_FIRST_REGION")) h->first_region = std::min(1.0, std::max(0.02, std::atof(e)));
+    if (const char* e = std::getenv("DBSLMM_B200_GRAM_HINT")) h->gram_hint = std::atoi(e);
+    if (const char* e = std::getenv("DBSLMM_B200_GRAM")) {
+        h->gram_packed = (std::strcmp(e, "packed") == 0);
+        h->gram_pair = (std::strcmp(e, "pair") == 0);
+    }
     if (const char* e = std::getenv("DBSLMM_B200_PANEL")) h->panel_tma = (std::strcmp(e, "legacy") != 0);
     if (const char* e = std::getenv("DBSLMM_B200_TPC")) {         // "max[,waves]"
         int a = 0, b = 0;
@@ -794,7 +821,7 @@ void dbslmm_b200_destroy(dbslmm_b200_handle* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     DevBuf* bufs[] = {&h->bed, &h->stats, &h->codes, &h->sigma, &h->lbuf, &h->rowN, &h->rowS, &h->rowR,
-                      &h->planblob, &h->beta, &h->status, &h->intQ, &h->intA, &h->intN, &h->scratch, &h->counters, &h->wbuf, &h->vbed, &h->vstats, &h->vwork, &h->dflag, &h->dirty, &h->bflags, &h->packed};
+                      &h->planblob, &h->beta, &h->status, &h->intQ, &h->intA, &h->intN, &h->scratch, &h->counters, &h->wbuf, &h->vbed, &h->vstats, &h->vwork, &h->dflag, &h->dirty, &h->bflags, &h->packed, &h->rowC};
     for (DevBuf* b : bufs) b->release();
     h->h_blob.release();
     h->h_out.release();
@@ -1111,6 +1138,7 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
     CU_TRY(h, h->rowN.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(P.n_snp_rows, 1)));
     CU_TRY(h, h->rowS.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(P.n_snp_rows, 1)));
     CU_TRY(h, h->rowR.ensure(sizeof(double) * (size_t)std::max<int64_t>(P.n_snp_rows, 1)));
+    CU_TRY(h, h->rowC.ensure(sizeof(double2) * (size_t)std::max<int64_t>(P.n_snp_rows, 1)));
     const size_t n_out = (size_t)(P.tot_s + P.tot_l);
     const size_t n_res = quad ? (size_t)nb : n_out * nfold;          // doubles coming back: betas of all folds, or one z'Sigma z per block
     CU_TRY(h, h->beta.ensure(sizeof(double) * std::max<size_t>(n_res, 1)));
@@ -1149,6 +1177,7 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
     const double* d_z = (const double*)(dblob + P.o_z);
     const GramTile* d_tiles_plain = (const GramTile*)(dblob + P.o_tiles_plain);
     const GramTile* d_tiles_miss = (const GramTile*)(dblob + P.o_tiles_miss);
+    const TileRec* d_recs = (const TileRec*)(dblob + P.o_tiles_pair);
     const int32_t* d_order = (const int32_t*)(dblob + P.o_order);
     const int32_t* d_diag = (const int32_t*)(dblob + P.o_diag);
     const int4* d_panel = (const int4*)(dblob + P.o_panel);
@@ -1221,6 +1250,7 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
         g.rowN = (const int32_t*)h->rowN.p;
         g.rowS = (const int32_t*)h->rowS.p;
         g.rowR = (const double*)h->rowR.p;
+        g.rowC = (const double2*)h->rowC.p;
         g.sigma = (double*)h->sigma.p;
         g.intQ = keep_int ? (int32_t*)h->intQ.p : nullptr;
         g.intA = keep_int ? (int32_t*)h->intA.p : nullptr;
@@ -1228,35 +1258,42 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
         g.full = full ? 1 : 0;
         g.light = 0;
         g.flags = d_bflags;
+        g.hint = h->gram_hint;
     }
     // One chain per batch of blocks: decode its SNP rows (both code planes where needed) -> per-block missing-call flags
     // -> one-plane Gram over the blocks without missing calls -> four-plane Gram over the others (returns at once if
     // there are none) -> z rows.  A resident fit runs ONE chain over everything.
     auto chain = [&](int64_t g0, int64_t g1, const int32_t* list, int32_t n_list, int32_t t0, int32_t t1, int32_t mt0, int32_t mt1,
-                     int32_t* any, bool light) -> int {
+                     int32_t pt0, int32_t pt1, int32_t* any, bool light) -> int {
         if (g1 <= g0) return DBSLMM_B200_OK;
         if (packed_gram)        // 2-bit rows in plan order + per-SNP statistics; int8 rows only if a block turns out to need them
             CU_TRY(h, launch_pack_rows((const uint8_t*)h->bed.p, h->n_ref, h->n_pad, d_rowsrc, g0, g1 - g0, a->tau, (uint32_t*)h->packed.p,
-                                       (int32_t*)h->rowN.p, (int32_t*)h->rowS.p, (double*)h->rowR.p, h->n_sm, st));
+                                       (int32_t*)h->rowN.p, (int32_t*)h->rowS.p, (double*)h->rowR.p, (double2*)h->rowC.p, h->n_sm, st));
         else
             CU_TRY(h, launch_decode_rows((const uint8_t*)h->bed.p, h->n_ref, h->n_pad, d_rowsrc, d_crow, d_mrow, g0, g1 - g0, a->tau,
                                          (int8_t*)h->codes.p, (uint8_t*)h->dirty.p, (int32_t*)h->rowN.p, (int32_t*)h->rowS.p,
-                                         (double*)h->rowR.p, nullptr, h->n_sm, st));
+                                         (double*)h->rowR.p, (double2*)h->rowC.p, nullptr, h->n_sm, st));
         CU_TRY(h, launch_block_flags(d_blocks, list, n_list, (const int32_t*)h->rowN.p, h->n_ref, d_bflags, any, st));
         n_launch += 2;
         g.any = any;
         g.light = light ? 1 : 0;         // 3-stage ring: a Gram CTA fits on an SM next to one Cholesky panel CTA
-        if (t1 > t0) {
+        if (t1 > t0 || pt1 > pt0) {
             g.tiles = d_tiles_plain + t0;
             g.n_tiles = t1 - t0;
             if (packed_gram) CU_TRY(h, launch_gram_packed(pmap, g, st));
-            else CU_TRY(h, launch_gram(tmap, g, st));
+            else {
+                g.tiles = nullptr;
+                g.recs = d_recs + pt0;
+                g.n_tiles = pt1 - pt0;
+                if (h->gram_pair) CU_TRY(h, launch_gram_pair(tmap, g, st));
+                else CU_TRY(h, launch_gram(tmap, g, st));
+            }
             ++n_launch;
         }
         if (packed_gram) {      // returns at once unless some block of this chain has missing calls
             CU_TRY(h, launch_decode_rows((const uint8_t*)h->bed.p, h->n_ref, h->n_pad, d_rowsrc, d_crow, d_mrow, g0, g1 - g0, a->tau,
                                          (int8_t*)h->codes.p, (uint8_t*)h->dirty.p, (int32_t*)h->rowN.p, (int32_t*)h->rowS.p,
-                                         (double*)h->rowR.p, any, h->n_sm, st));
+                                         (double*)h->rowR.p, (double2*)h->rowC.p, any, h->n_sm, st));
             ++n_launch;
         }
         if (mt1 > mt0) {
@@ -1274,11 +1311,11 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
         if (P.n_snp_rows > 0) {
             if (packed_gram)
                 CU_TRY(h, launch_pack_rows((const uint8_t*)h->bed.p, h->n_ref, h->n_pad, d_rowsrc, 0, P.n_snp_rows, a->tau, (uint32_t*)h->packed.p,
-                                           (int32_t*)h->rowN.p, (int32_t*)h->rowS.p, (double*)h->rowR.p, h->n_sm, st));
+                                           (int32_t*)h->rowN.p, (int32_t*)h->rowS.p, (double*)h->rowR.p, (double2*)h->rowC.p, h->n_sm, st));
             else
                 CU_TRY(h, launch_decode_rows((const uint8_t*)h->bed.p, h->n_ref, h->n_pad, d_rowsrc, d_crow, d_mrow, 0, P.n_snp_rows, a->tau,
                                              (int8_t*)h->codes.p, (uint8_t*)h->dirty.p, (int32_t*)h->rowN.p, (int32_t*)h->rowS.p,
-                                             (double*)h->rowR.p, nullptr, h->n_sm, st));
+                                             (double*)h->rowR.p, (double2*)h->rowC.p, nullptr, h->n_sm, st));
             ++n_launch;
         }
         CU_TRY(h, cudaEventRecord(h->ev[2], st));          // packer / decoder done
@@ -1292,10 +1329,14 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
                 CU_TRY(h, launch_gram_packed(pmap, g, st));
                 CU_TRY(h, launch_decode_rows((const uint8_t*)h->bed.p, h->n_ref, h->n_pad, d_rowsrc, d_crow, d_mrow, 0, P.n_snp_rows, a->tau,
                                              (int8_t*)h->codes.p, (uint8_t*)h->dirty.p, (int32_t*)h->rowN.p, (int32_t*)h->rowS.p,
-                                             (double*)h->rowR.p, d_any, h->n_sm, st));
+                                             (double*)h->rowR.p, (double2*)h->rowC.p, d_any, h->n_sm, st));
                 ++n_launch;
             } else {
-                CU_TRY(h, launch_gram(tmap, g, st));
+                g.tiles = nullptr;
+                g.recs = d_recs;
+                g.n_tiles = P.n_tiles_pair;
+                if (h->gram_pair) CU_TRY(h, launch_gram_pair(tmap, g, st));
+                else CU_TRY(h, launch_gram(tmap, g, st));
             }
             g.tiles = d_tiles_miss;
             g.n_tiles = P.n_tiles_miss;
@@ -1311,7 +1352,7 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
             const int bi = P.up_order[ui];                 // decode / Gram in the order the rows arrive
             const Batch& B = P.batches[bi];
             CU_TRY(h, cudaStreamWaitEvent(st, h->ev_up[bi], 0));
-            int rc = chain(B.grow0, B.grow1, d_order + B.ord_off, B.ord_n, B.tile0, B.tile1, B.mtile0, B.mtile1, d_any + 1 + bi, true);
+            int rc = chain(B.grow0, B.grow1, d_order + B.ord_off, B.ord_n, B.tile0, B.tile1, B.mtile0, B.mtile1, B.ptile0, B.ptile1, d_any + 1 + bi, true);
             if (rc != DBSLMM_B200_OK) return rc;
             CU_TRY(h, cudaEventRecord(h->ev_gram[bi], st));
         }
@@ -1406,7 +1447,7 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
                         }
                         CU_TRY(h, launch_chol_panel_tma(B.tile_rows, d_blocks, d_panel + s.panel_off, s.n_panel, n_single, tpc,
                                                         d_diag + s.diag_off, deferred_here ? s.n_diag : 0, (int32_t)k,
-                                                        (const CUtensorMap*)(dblob + P.o_lmaps), h->tmap_perm == 1 ? 1 : 0, h->l2_pf,
+                                                        (const CUtensorMap*)(dblob + P.o_lmaps), h->tmap_perm == 1 ? 1 : 0, h->l2_pf | (h->next_pf << 8),
                                                         (const double*)h->sigma.p, (double*)h->lbuf.p, (double*)h->wbuf.p,
                                                         wstride, fuse_end, ridge, (double*)h->scratch.p + B.scratch_off,
                                                         (int32_t*)h->counters.p, s.group_base, d_status, (int32_t*)h->dflag.p,

@@ -40,6 +40,73 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         : "memory");
 }
 
+// FP64 transform + stores of NV * 32 rows (i0 ...) x this warp's 32 Sigma columns (jl = this lane's column) from the raw
+// s32 accumulators v (one TMEM column per row): n Q - S_i S_j (exact) -> scale -> coalesced row stores of the lower
+// triangle.  rc[r] = {S_i, r_i} of row i0 + r; `below` = every entry of the chunk lies strictly below the diagonal.
+template <class Desc, int NV>      // Desc = BlockDesc or TileRec: m, mp, ld, moff
+__device__ __forceinline__ void store_half_tile(const GramArgs& a, const Desc& bd, const uint32_t (&v)[NV][32], const double2* rc,
+                                                bool below, int i0, int jl, double Sj, double rj) {
+    constexpr int NR = 32 * NV;
+    if (i0 >= bd.mp) return;                                  // warp-uniform: nothing of this half is inside the block
+    const double dn = (double)a.n_ref;
+    double* sig = a.sigma + bd.moff;
+    const size_t ld = (size_t)bd.ld;
+    if (below && i0 + NR <= bd.m && !a.full && a.intQ == nullptr) {
+        // interior half tile (every entry below the diagonal, every row a real SNP): straight-line code
+        double* p = sig + (size_t)i0 * ld + jl;
+        // kB rows at a time, stage by stage: the five FP64 operations of a row form one dependent chain (~10 cycles each),
+        // and left to itself ptxas walks the rows one after the other in the same registers (~100 cycles per row and warp,
+        // ncu round 2); written this way the chains of kB rows overlap
+        constexpr int kB = 8;
+#pragma unroll
+        for (int r0 = 0; r0 < NR; r0 += kB) {
+            double2 c[kB];
+            double t[kB];
+#pragma unroll
+            for (int i = 0; i < kB; ++i) c[i] = rc[r0 + i];
+#pragma unroll
+            for (int i = 0; i < kB; ++i) t[i] = u32_to_f64(v[(r0 + i) >> 5][(r0 + i) & 31]);
+#pragma unroll
+            for (int i = 0; i < kB; ++i) t[i] *= dn;
+            // n Q - S_i S_j is an exact integer below 2^53: one FMA, no rounding
+#pragma unroll
+            for (int i = 0; i < kB; ++i) t[i] = fma(-c[i].x, Sj, t[i]);
+#pragma unroll
+            for (int i = 0; i < kB; ++i) t[i] *= c[i].y;
+#pragma unroll
+            for (int i = 0; i < kB; ++i) t[i] *= rj;
+#pragma unroll
+            for (int i = 0; i < kB; ++i) {
+                if (a.hint & 2) __stcs(p + (size_t)(r0 + i) * ld, t[i]);
+                else p[(size_t)(r0 + i) * ld] = t[i];
+            }
+        }
+        return;
+    }
+    // general half tile (diagonal, last tile row, debug planes): same arithmetic, predicated stores
+    const int nreal = bd.m - i0;                           // rows r < nreal are real SNPs
+    double* p = sig + (size_t)i0 * ld + jl;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        const int il = i0 + r;
+        const double2 c = rc[r];
+        const double t = fma(-c.x, Sj, dn * u32_to_f64(v[r >> 5][r & 31]));
+        double val = t * c.y * rj;
+        if (il == jl) val += a.one_minus_tau;
+        if (r < nreal && jl <= il) {
+            p[(size_t)r * ld] = val;
+            if (a.full && jl < il) sig[(size_t)jl * ld + il] = val;
+            if (a.intQ != nullptr) {
+                a.intQ[(size_t)bd.moff + (size_t)il * ld + jl] = (int32_t)v[r >> 5][r & 31];
+                a.intQ[(size_t)bd.moff + (size_t)jl * ld + il] = (int32_t)v[r >> 5][r & 31];
+            }
+        }
+    }
+    // identity padding rows m .. mp-1 (at most 7 per block)
+    for (int il = max(bd.m, i0); il < min(bd.mp, i0 + NR); ++il)
+        if (jl <= il) sig[(size_t)il * ld + jl] = (il == jl) ? 1.0 : 0.0;
+}
+
 // FP64 epilogue of one 128 x 128 one-plane tile for one epilogue warp (TMEM lane quarter q = Sigma columns, row half):
 // tcgen05.ld -> n Q - S_i S_j (exact) -> scale -> coalesced row stores of the lower triangle.  Shared by the int8-row and the
 // packed-row kernels.  rc: this warp's 64 x {S_i, r_i} staging in shared memory.
@@ -65,7 +132,6 @@ __device__ __forceinline__ void plain_epilogue_tile(const GramArgs& a, const Gra
     mbar_wait(acc_full_bar, full_parity);
     tc_fence_after();
     const uint32_t tlane = tmem_acc + ((uint32_t)(q * 32) << 16);
-    double* sig = a.sigma + bd.moff;
     uint32_t v[2][32];
     tmem_ld32(tlane + half * 64, v[0]);
     tmem_ld32(tlane + half * 64 + 32, v[1]);
@@ -73,68 +139,55 @@ __device__ __forceinline__ void plain_epilogue_tile(const GramArgs& a, const Gra
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(acc_empty_bar);                // accumulator copied out: MMA may reuse it
-    if (i0 >= bd.mp) return;                                  // warp-uniform: nothing of this half is inside the block
-    const size_t ld = (size_t)bd.ld;
-    if (tile.ti > tile.tj && i0 + 64 <= bd.m && !a.full && a.intQ == nullptr) {
-        // interior half tile (every entry below the diagonal, every row a real SNP): straight-line code
-        double* p = sig + (size_t)i0 * ld + jl;
-#pragma unroll
-        for (int r = 0; r < 64; ++r) {
-            const double2 c = rc[r];
-            // n Q - S_i S_j is an exact integer below 2^53: one FMA, no rounding
-            const double t = fma(-c.x, Sj, dn * (double)(int32_t)v[r >> 5][r & 31]);
-            p[(size_t)r * ld] = t * c.y * rj;
-        }
-        return;
-    }
-    // general half tile (diagonal, last tile row, debug planes): same arithmetic, predicated stores
-    const int nreal = bd.m - i0;                           // rows r < nreal are real SNPs
-    double* p = sig + (size_t)i0 * ld + jl;
-#pragma unroll
-    for (int r = 0; r < 64; ++r) {
-        const int il = i0 + r;
-        const double2 c = rc[r];
-        const double t = fma(-c.x, Sj, dn * (double)(int32_t)v[r >> 5][r & 31]);
-        double val = t * c.y * rj;
-        if (il == jl) val += a.one_minus_tau;
-        if (r < nreal && jl <= il) {
-            p[(size_t)r * ld] = val;
-            if (a.full && jl < il) sig[(size_t)jl * ld + il] = val;
-            if (a.intQ != nullptr) {
-                a.intQ[(size_t)bd.moff + (size_t)il * ld + jl] = (int32_t)v[r >> 5][r & 31];
-                a.intQ[(size_t)bd.moff + (size_t)jl * ld + il] = (int32_t)v[r >> 5][r & 31];
-            }
-        }
-    }
-    // identity padding rows m .. mp-1 (at most 7 per block)
-    for (int il = max(bd.m, i0); il < min(bd.mp, i0 + 64); ++il)
-        if (jl <= il) sig[(size_t)il * ld + jl] = (il == jl) ? 1.0 : 0.0;
+    store_half_tile(a, bd, v, rc, tile.ti > tile.tj, i0, jl, Sj, rj);
 }
 
 // ------------------------------------------------------------------------------------------
-// Blocks WITHOUT missing calls (one accumulator plane): one CTA per SM walks
-// the tile list; the s32 accumulator is double-buffered in TMEM (2 x 128 columns) so the FP64
-// epilogue of tile i (8 warps) overlaps the TMA/MMA main loop of tile i+1, and a 5-stage smem
-// ring keeps more TMA requests in flight.  Same arithmetic as gram_kernel<1>.
-//   warp 0: TMA producer   warp 1: TMEM alloc + MMA issuer   warps 2-9: epilogue
-//   (TMEM lane quarter = warp % 4, column half = (warp - 2) / 4)
+// Blocks WITHOUT missing calls (one accumulator plane), two kernels of the same shape: persistent, warp-specialised,
+//   warp 0: TMA producer   warp 1: TMEM alloc + MMA issuer   warps 2-9: FP64 epilogue
+// the s32 accumulator double-buffered in TMEM so the epilogue of tile n overlaps the TMA/MMA main loop of tile n+1.
+//
+// What bounds them (ncu, round 2): not the tensor pipe, L2 or DRAM, but LATENCY between tiles.  Until session 3 every role
+// began a tile with a chain of dependent global loads (tile -> block descriptor -> per-row constants, 0.7-2 us each under
+// load) and the producer / MMA issuer ran inside `if (lane == 0)`, where each UTMALDG / UTCIMMA / UTCBAR is wrapped in a
+// vote-elect-broadcast loop (~18 SASS instructions).  Now:
+//   * the tile list holds self-contained RECORDS (TileRec, 48 B, built by the host); every role fetches the record of
+//     the NEXT tile before it starts on the current one;
+//   * the epilogue warps stage {S_i, r_i} of their rows and columns (rowC, written by the decoder) with cp.async into a
+//     double-buffered shared-memory table one tile ahead -- no register ever waits for them;
+//   * warps 0 and 1 run their loops with all 32 lanes and elect one lane per issue (elect_one in common.cuh).
+// Tiles are assigned round-robin (tile t0 + n * stride); blocks whose device-side flag says "missing calls" are skipped.
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ TileRec ld_rec(const TileRec* p) {
+    const int4* q = reinterpret_cast<const int4*>(p);
+    const int4 x = __ldg(q), y = __ldg(q + 1), z = __ldg(q + 2);
+    TileRec r;
+    r.blk = x.x; r.ti = x.y; r.tj = x.z; r.croff = x.w;
+    r.goff = y.x; r.m = y.y; r.mp = y.z; r.ld = y.w;
+    r.moff = (int64_t)(((uint64_t)(uint32_t)z.y << 32) | (uint64_t)(uint32_t)z.x);
+    r.pad = 0;
+    return r;
+}
+
 static constexpr int kPThreads = 320;
 template <int kPStages>
 struct PCfg { static constexpr int kSmem = kPStages * 2 * kTileBytes + 1024; };
 
+// 128 x 128 tiles, one CTA per SM (DBSLMM_B200_GRAM=single).
 // (min-blocks 2 only caps the registers at 102 per thread: with the 3-stage ring a Gram CTA then fits next to a
-//  Cholesky panel CTA -- 32 K registers, 110 KB shared memory -- during a streaming fit)
+//  Cholesky panel CTA during a streaming fit)
 template <int kPStages>
 __global__ void __launch_bounds__(kPThreads, 2)
 gram_persistent_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs a) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[kPStages], empty_bar[kPStages], acc_full[2], acc_empty[2];
-    __shared__ __align__(16) double2 row_consts[8][64];          // per epilogue warp: {S_i, r_i} of its 64 rows
+    __shared__ __align__(16) double2 row_consts[8][2][64 + 32];  // per epilogue warp, two tiles: {S, r} of its 64 rows, then of its 32 columns
     __shared__ uint32_t tmem_slot;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int nk = a.nk;
+    const uint64_t l2hint = (a.hint & 1) ? 0x14F0000000000000ull : 0x1000000000000000ull;      // evict last / normal
+    const int t0 = (int)blockIdx.x, tstride = (int)gridDim.x, n_tiles = a.n_tiles;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kPStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -149,34 +202,42 @@ gram_persistent_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs 
     const uint32_t tmem_base = tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (int tile_i = blockIdx.x; tile_i < a.n_tiles; tile_i += gridDim.x) {
-                const GramTile tile = a.tiles[tile_i];
-                if (a.flags[tile.blk] != 0) continue;                 // missing calls: the four-plane kernel's block
-                const BlockDesc bd = a.blocks[tile.blk];
-                const bool diag = (tile.ti == tile.tj);
-                const int32_t rowJ = bd.croff + tile.tj * kTile, rowI = bd.croff + tile.ti * kTile;
+        uint32_t it = 0;
+        int t = t0;
+        TileRec cur = ld_rec(a.recs + min(t, n_tiles - 1)), nxt = cur;
+        while (t < n_tiles) {
+            const int tn = t + tstride;
+            if (tn < n_tiles) nxt = ld_rec(a.recs + tn);
+            if (__ldg(a.flags + cur.blk) == 0) {                  // (else: missing calls, the four-plane kernel's block)
+                const bool diag = (cur.ti == cur.tj);
+                const int32_t rowJ = cur.croff + cur.tj * kTile, rowI = cur.croff + cur.ti * kTile;
                 const uint32_t bytes = (uint32_t)((diag ? 1 : 2) * kTileBytes);
                 for (int ks = 0; ks < nk; ++ks, ++it) {
                     const int s = it % kPStages;
                     const uint32_t ph = (it / kPStages) & 1u;
                     mbar_wait(&empty_bar[s], ph ^ 1u);
                     uint8_t* st = smem + (size_t)s * 2 * kTileBytes;
-                    mbar_expect_tx(&full_bar[s], bytes);
-                    tma_load_2d(st, &tmap, ks * 128, rowJ, &full_bar[s]);
-                    if (!diag) tma_load_2d(st + kTileBytes, &tmap, ks * 128, rowI, &full_bar[s]);
+                    if (elect_one()) {
+                        mbar_expect_tx(&full_bar[s], bytes);
+                        tma_load_2d_hint(st, &tmap, ks * 128, rowJ, &full_bar[s], l2hint);
+                        if (!diag) tma_load_2d_hint(st + kTileBytes, &tmap, ks * 128, rowI, &full_bar[s], l2hint);
+                    }
+                    __syncwarp();
                 }
             }
+            cur = nxt;
+            t = tn;
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_i8_idesc(kTile, kTile);
-            uint32_t it = 0, lt = 0;
-            for (int tile_i = blockIdx.x; tile_i < a.n_tiles; tile_i += gridDim.x) {
-                const GramTile tile = a.tiles[tile_i];
-                if (a.flags[tile.blk] != 0) continue;
-                const bool diag = (tile.ti == tile.tj);
+        constexpr uint32_t idesc = make_i8_idesc(kTile, kTile);
+        uint32_t it = 0, lt = 0;
+        int t = t0;
+        TileRec cur = ld_rec(a.recs + min(t, n_tiles - 1)), nxt = cur;
+        while (t < n_tiles) {
+            const int tn = t + tstride;
+            if (tn < n_tiles) nxt = ld_rec(a.recs + tn);
+            if (__ldg(a.flags + cur.blk) == 0) {
+                const bool diag = (cur.ti == cur.tj);
                 const uint32_t as = lt & 1u;
                 mbar_wait(&acc_empty[as], ((lt >> 1) & 1u) ^ 1u);      // epilogue has drained this accumulator
                 tc_fence_after();
@@ -187,32 +248,270 @@ gram_persistent_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs 
                     tc_fence_after();
                     const uint32_t st = smem_u32(smem + (size_t)s * 2 * kTileBytes);
                     const uint64_t dJ = make_sw128_kmajor_desc(st), dI = make_sw128_kmajor_desc(diag ? st : st + kTileBytes);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)
-                        umma_i8(tmem_base + as * kTile, dJ + (uint64_t)(kk * 2), dI + (uint64_t)(kk * 2), idesc,
-                                (ks > 0 || kk > 0) ? 1u : 0u);
-                    umma_commit(&empty_bar[s]);
+                        for (int kk = 0; kk < 4; ++kk)
+                            umma_i8(tmem_base + as * kTile, dJ + (uint64_t)(kk * 2), dI + (uint64_t)(kk * 2), idesc,
+                                    (ks > 0 || kk > 0) ? 1u : 0u);
+                        umma_commit(&empty_bar[s]);
+                        if (ks == nk - 1) umma_commit(&acc_full[as]);
+                    }
+                    __syncwarp();
                 }
-                umma_commit(&acc_full[as]);
                 ++lt;
             }
+            cur = nxt;
+            t = tn;
         }
     } else {
-        const int q = warp & 3, half = (warp - 2) >> 2;
-        double2* rc = row_consts[warp - 2];                      // this warp's 64 rows: {S_i, r_i}
-        uint32_t lt = 0;
-        for (int tile_i = blockIdx.x; tile_i < a.n_tiles; tile_i += gridDim.x) {
-            const GramTile tile = a.tiles[tile_i];
-            if (a.flags[tile.blk] != 0) continue;
-            const BlockDesc bd = a.blocks[tile.blk];
-            const uint32_t my_lt = lt++;                         // tiles this CTA has processed so far
-            const uint32_t as = my_lt & 1u;
-            plain_epilogue_tile(a, tile, bd, tmem_base + as * kTile, q, half, lane, rc, &acc_full[as], (my_lt >> 1) & 1u, &acc_empty[as]);
+        const int q = warp & 3, half = (warp - 2) >> 2;              // TMEM lane quarter (Sigma columns), row half
+        double2 (*rcb)[64 + 32] = row_consts[warp - 2];
+        const double dn = (double)a.n_ref;
+        // {S, r} of tile r's rows and columns -> table `buf` (zero beyond the block), asynchronously
+        auto stage = [&](int buf, const TileRec& r) {
+            const double2* src = a.rowC + r.goff;
+            const int i0 = r.ti * kTile + half * 64;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int il = i0 + 32 * hh + lane;
+                cp_async16(&rcb[buf][32 * hh + lane], src + (il < r.m ? il : 0), il < r.m);
+            }
+            const int jl = r.tj * kTile + q * 32 + lane;
+            cp_async16(&rcb[buf][64 + lane], src + (jl < r.m ? jl : 0), jl < r.m);
+        };
+        uint32_t lt = 0, n = 0;
+        int t = t0;
+        TileRec cur = ld_rec(a.recs + min(t, n_tiles - 1)), nxt = cur;
+        if (t < n_tiles) stage(0, cur);
+        cp_async_commit();
+        if (t + tstride < n_tiles) nxt = ld_rec(a.recs + t + tstride);
+        while (t < n_tiles) {
+            const int tn = t + tstride, tnn = tn + tstride;
+            TileRec nn = nxt;
+            if (tnn < n_tiles) nn = ld_rec(a.recs + tnn);
+            __syncwarp();                                        // every lane is done with the table of tile n - 1
+            if (tn < n_tiles) stage((int)((n + 1) & 1u), nxt);
+            cp_async_commit();
+            if (__ldg(a.flags + cur.blk) == 0) {
+                const uint32_t as = lt & 1u;
+                const int jl = cur.tj * kTile + q * 32 + lane;
+                const int i0 = cur.ti * kTile + half * 64;
+                cp_async_wait<1>();                              // this tile's table has landed (only the group just committed may be pending)
+                __syncwarp();
+                const double2* rc = rcb[n & 1u];
+                const double2 cj = rc[64 + lane];
+                const double Sj = cj.x, rj = cj.y * dn;
+                mbar_wait(&acc_full[as], (lt >> 1) & 1u);
+                tc_fence_after();
+                const uint32_t tlane = tmem_base + as * kTile + ((uint32_t)(q * 32) << 16);
+                uint32_t v[2][32];
+                tmem_ld32(tlane + half * 64, v[0]);
+                tmem_ld32(tlane + half * 64 + 32, v[1]);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[as]);      // accumulator copied out: MMA may reuse it
+                store_half_tile(a, cur, v, rc, cur.ti > cur.tj, i0, jl, Sj, rj);
+                ++lt;
+            }
+            cur = nxt;
+            nxt = nn;
+            t = tn;
+            ++n;
         }
+        cp_async_wait<0>();
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc<256>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------
+// CTA-pair version (default).  The two CTAs of a 2-CTA cluster (one TPC) share ONE tcgen05.mma.cta_group::2 of
+// M = N = 256 over a 256 x 256 SUPER tile of the block's lower triangle: CTA r loads 128 J rows (its half of A = its 128
+// Sigma columns, the TMEM lanes) and 128 I rows (its half of B), 32 KB per K step for FOUR 128 x 128 units instead of
+// one -- half the L2 -> SM operand traffic per unit (a quarter on diagonal super tiles, where A and the B half are the
+// same rows and only one box is loaded; 9.6 GB instead of 16.5 GB per genome-wide fit by ncu), and a quarter of the
+// per-tile pipeline turnarounds.  The upper-right unit of a diagonal super tile is computed and dropped.
+//   warp 0 (both CTAs)  TMA producer; completion bytes of both CTAs are counted on the LEADER's full barrier
+//   warp 1              TMEM allocator (both CTAs); the leader's warp issues the MMAs and commits to both CTAs
+//   warps 2-9 (both)    epilogue of this CTA's 128 columns x 256 rows (2 x 256 s32 TMEM columns, double-buffered):
+//                       lane quarter = warp % 4, row half = (warp - 2) / 4, two 64-row chunks per warp
+//   (measured and dropped: 16 epilogue warps of 64 rows each, handing the accumulator back before any FP64 work --
+//    2.6 ms against 2.2 ms on the same box: 96 registers per thread and spills)
+// ------------------------------------------------------------------------------------------
+static constexpr int kSuper = 256;
+template <int kStages>
+struct PairCfg { static constexpr int kSmem = kStages * 2 * kTileBytes + 1024; };
+
+// (kMinB = 2 only caps the registers at 102 per thread: the 3-stage version then fits next to a Cholesky panel CTA
+//  during a streaming fit, like gram_persistent_kernel<3>)
+template <int kStages, int kMinB>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPThreads, kMinB)
+gram_pair_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], acc_full[2], acc_empty[2];
+    __shared__ __align__(16) double2 row_consts[8][2][128 + 32]; // per epilogue warp, two tiles: {S, r} of its 128 rows, then of its 32 columns
+    __shared__ uint32_t tmem_slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int t0 = (int)(blockIdx.x >> 1), tstride = (int)(gridDim.x >> 1), n_tiles = a.n_tiles;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int nk = a.nk;
+    const uint64_t l2hint = (a.hint & 1) ? 0x14F0000000000000ull : 0x1000000000000000ull;      // evict last / normal
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 16); }      // 8 epilogue warps x 2 CTAs
+        mbar_fence_init();
+        tma_prefetch_desc(&tmap);
+    }
+    cluster_sync_all();                                          // both CTAs are running, all barriers exist
+    if (warp == 1) tmem_alloc_pair<512>(&tmem_slot);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 0) {
+        uint32_t it = 0;
+        int t = t0;
+        TileRec cur = ld_rec(a.recs + min(t, n_tiles - 1)), nxt = cur;
+        while (t < n_tiles) {
+            const int tn = t + tstride;
+            if (tn < n_tiles) nxt = ld_rec(a.recs + tn);
+            if (__ldg(a.flags + cur.blk) == 0) {                  // (else: missing calls, the four-plane kernel's block)
+                const bool diag = (cur.ti == cur.tj);
+                const int32_t rowJ = cur.croff + cur.tj * kSuper + (int32_t)rank * kTile;      // this CTA's Sigma columns
+                const int32_t rowI = cur.croff + cur.ti * kSuper + (int32_t)rank * kTile;      // this CTA's half of the Sigma rows
+                const uint32_t bytes = (uint32_t)((diag ? 2 : 4) * kTileBytes);                // of BOTH CTAs
+                for (int ks = 0; ks < nk; ++ks, ++it) {
+                    const int s = it % kStages;
+                    const uint32_t ph = (it / kStages) & 1u;
+                    mbar_wait(&empty_bar[s], ph ^ 1u);
+                    uint8_t* st = smem + (size_t)s * 2 * kTileBytes;
+                    if (elect_one()) {
+                        if (rank == 0) mbar_expect_tx(&full_bar[s], bytes);
+                        tma_load_2d_pair(st, &tmap, ks * 128, rowJ, &full_bar[s], l2hint);
+                        if (!diag) tma_load_2d_pair(st + kTileBytes, &tmap, ks * 128, rowI, &full_bar[s], l2hint);
+                    }
+                    __syncwarp();
+                }
+            }
+            cur = nxt;
+            t = tn;
+        }
+    } else if (warp == 1) {
+        if (rank == 0) {
+            constexpr uint32_t idesc = make_i8_idesc(kSuper, kSuper);
+            uint32_t it = 0, lt = 0;
+            int t = t0;
+            TileRec cur = ld_rec(a.recs + min(t, n_tiles - 1)), nxt = cur;
+            while (t < n_tiles) {
+                const int tn = t + tstride;
+                if (tn < n_tiles) nxt = ld_rec(a.recs + tn);
+                if (__ldg(a.flags + cur.blk) == 0) {
+                    const bool diag = (cur.ti == cur.tj);
+                    const uint32_t as = lt & 1u;
+                    mbar_wait(&acc_empty[as], ((lt >> 1) & 1u) ^ 1u);      // both CTAs' epilogues have drained this accumulator
+                    tc_fence_after();
+                    for (int ks = 0; ks < nk; ++ks, ++it) {
+                        const int s = it % kStages;
+                        const uint32_t ph = (it / kStages) & 1u;
+                        mbar_wait(&full_bar[s], ph);
+                        tc_fence_after();
+                        const uint32_t st = smem_u32(smem + (size_t)s * 2 * kTileBytes);
+                        const uint64_t dJ = make_sw128_kmajor_desc(st), dI = make_sw128_kmajor_desc(diag ? st : st + kTileBytes);
+                        if (elect_one()) {
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk)
+                                umma_i8_pair(tmem_base + as * kSuper, dJ + (uint64_t)(kk * 2), dI + (uint64_t)(kk * 2), idesc,
+                                             (ks > 0 || kk > 0) ? 1u : 0u);
+                            umma_commit_pair(&empty_bar[s]);
+                            if (ks == nk - 1) umma_commit_pair(&acc_full[as]);
+                        }
+                        __syncwarp();
+                    }
+                    ++lt;
+                }
+                cur = nxt;
+                t = tn;
+            }
+        }
+    } else {
+        const int q = warp & 3, hsel = (warp - 2) >> 2;
+        double2 (*rcb)[128 + 32] = row_consts[warp - 2];
+        const double dn = (double)a.n_ref;
+        auto stage = [&](int buf, const TileRec& r) {
+            const double2* src = a.rowC + r.goff;
+            const int ib = r.ti * kSuper + hsel * kTile;
+#pragma unroll
+            for (int hh = 0; hh < 4; ++hh) {
+                const int il = ib + 32 * hh + lane;
+                cp_async16(&rcb[buf][32 * hh + lane], src + (il < r.m ? il : 0), il < r.m);
+            }
+            const int jl = r.tj * kSuper + (int)rank * kTile + q * 32 + lane;
+            cp_async16(&rcb[buf][128 + lane], src + (jl < r.m ? jl : 0), jl < r.m);
+        };
+        uint32_t lt = 0, n = 0;
+        int t = t0;
+        TileRec cur = ld_rec(a.recs + min(t, n_tiles - 1)), nxt = cur;
+        if (t < n_tiles) stage(0, cur);
+        cp_async_commit();
+        if (t + tstride < n_tiles) nxt = ld_rec(a.recs + t + tstride);
+        while (t < n_tiles) {
+            const int tn = t + tstride, tnn = tn + tstride;
+            TileRec nn = nxt;
+            if (tnn < n_tiles) nn = ld_rec(a.recs + tnn);
+            __syncwarp();                                        // every lane is done with the table of tile n - 1
+            if (tn < n_tiles) stage((int)((n + 1) & 1u), nxt);
+            cp_async_commit();
+            if (__ldg(a.flags + cur.blk) == 0) {
+                const uint32_t as = lt & 1u;
+                const int jmin = cur.tj * kSuper + (int)rank * kTile + q * 32;      // this warp's first Sigma column
+                const int jl = jmin + lane;
+                const int ib = cur.ti * kSuper + hsel * kTile;                      // first of this warp's 128 rows
+                cp_async_wait<1>();                              // this tile's table has landed
+                __syncwarp();
+                const double2* rc = rcb[n & 1u];
+                const double2 cj = rc[128 + lane];
+                const double Sj = cj.x, rj = cj.y * dn;
+                // a 64-row chunk is needed if it reaches into the block and below (or onto) the diagonal of this warp's columns
+                const bool need0 = (ib < cur.mp) && (ib + 63 >= jmin);
+                const bool need1 = (ib + 64 < cur.mp) && (ib + 127 >= jmin);
+                mbar_wait(&acc_full[as], (lt >> 1) & 1u);
+                tc_fence_after();
+                const uint32_t tlane = tmem_base + as * kSuper + (uint32_t)(hsel * kTile) + ((uint32_t)(q * 32) << 16);
+                bool handed_back = false;
+#pragma unroll 1
+                for (int c = 0; c < 2; ++c) {                        // (not unrolled: one copy of the store code)
+                    const bool need = (c == 0) ? need0 : need1;
+                    uint32_t v[2][32];
+                    if (need) {
+                        tmem_ld32(tlane + 64 * c, v[0]);
+                        tmem_ld32(tlane + 64 * c + 32, v[1]);
+                        tmem_ld_wait();
+                    }
+                    if (!handed_back && (c == 1 || !need1)) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_rank(&acc_empty[as], 0);      // the leader's MMA issuer may reuse the accumulator
+                        handed_back = true;
+                    }
+                    if (need) store_half_tile(a, cur, v, rc + 64 * c, ib + 64 * c > jmin + 31, ib + 64 * c, jl, Sj, rj);
+                }
+                ++lt;
+            }
+            cur = nxt;
+            nxt = nn;
+            t = tn;
+            ++n;
+        }
+        cp_async_wait<0>();
+    }
+    tc_fence_before();
+    cluster_sync_all();          // the peer's shared memory, barriers and TMEM stay alive until both CTAs are done
+    if (warp == 1) tmem_dealloc_pair<512>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -409,7 +708,7 @@ gram_missing_kernel(const __grid_constant__ CUtensorMap tmapJ, const __grid_cons
     const uint32_t tmem_base = tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        {
             uint32_t it = 0;
             for (int tile_i = blockIdx.x; tile_i < a.n_tiles; tile_i += gridDim.x) {
                 const GramTile tile = a.tiles[tile_i];
@@ -420,16 +719,19 @@ gram_missing_kernel(const __grid_constant__ CUtensorMap tmapJ, const __grid_cons
                     const int s = it % kMStages;
                     mbar_wait(&empty_bar[s], ((it / kMStages) & 1u) ^ 1u);
                     uint8_t* st = smem + (size_t)s * kMStageBytes;
-                    mbar_expect_tx(&full_bar[s], (uint32_t)kMStageBytes);
-                    tma_load_2d(st, &tmapJ, ks * 128, rowJ, &full_bar[s]);
-                    tma_load_2d(st + kTileBytes, &tmapJ, ks * 128, rowJ + bd.m, &full_bar[s]);
-                    tma_load_2d(st + 2 * kTileBytes, &tmapI, ks * 128, rowI, &full_bar[s]);
-                    tma_load_2d(st + 2 * kTileBytes + kTileBytes / 2, &tmapI, ks * 128, rowI + bd.m, &full_bar[s]);
+                    if (elect_one()) {
+                        mbar_expect_tx(&full_bar[s], (uint32_t)kMStageBytes);
+                        tma_load_2d(st, &tmapJ, ks * 128, rowJ, &full_bar[s]);
+                        tma_load_2d(st + kTileBytes, &tmapJ, ks * 128, rowJ + bd.m, &full_bar[s]);
+                        tma_load_2d(st + 2 * kTileBytes, &tmapI, ks * 128, rowI, &full_bar[s]);
+                        tma_load_2d(st + 2 * kTileBytes + kTileBytes / 2, &tmapI, ks * 128, rowI + bd.m, &full_bar[s]);
+                    }
+                    __syncwarp();
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
             // The I-side genotype rows and mask rows of a stage are adjacent in shared memory (2 x 64 rows), so ONE
             // B descriptor with N = 128 covers both: g_j . [g_i | M_i] fills the Q and P1 planes in one instruction,
             // M_j . [g_i | M_i] the P2 and N planes -- two MMAs per K step instead of four, a third less operand traffic.
@@ -449,16 +751,20 @@ gram_missing_kernel(const __grid_constant__ CUtensorMap tmapJ, const __grid_cons
                     const uint32_t st = smem_u32(smem + (size_t)s * kMStageBytes);
                     const uint64_t dgJ = make_sw128_kmajor_desc(st), dmJ = make_sw128_kmajor_desc(st + kTileBytes);
                     const uint64_t dI = make_sw128_kmajor_desc(st + 2 * kTileBytes);      // [g_i (64 rows) | M_i (64 rows)]
+                    if (elect_one()) {
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        const uint32_t acc = (ks > 0 || kk > 0) ? 1u : 0u;
-                        const uint64_t adv = (uint64_t)(kk * 2);   // +32 bytes inside the 128 B swizzle atom
-                        umma_i8(tm + 0 * kTileI, dgJ + adv, dI + adv, idesc, acc);        // Q | P1 : g_j . [g_i | M_i]
-                        umma_i8(tm + 2 * kTileI, dmJ + adv, dI + adv, idesc, acc);        // P2 | N : M_j . [g_i | M_i]
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const uint32_t acc = (ks > 0 || kk > 0) ? 1u : 0u;
+                            const uint64_t adv = (uint64_t)(kk * 2);   // +32 bytes inside the 128 B swizzle atom
+                            umma_i8(tm + 0 * kTileI, dgJ + adv, dI + adv, idesc, acc);        // Q | P1 : g_j . [g_i | M_i]
+                            umma_i8(tm + 2 * kTileI, dmJ + adv, dI + adv, idesc, acc);        // P2 | N : M_j . [g_i | M_i]
+                        }
+                        umma_commit(&empty_bar[s]);
                     }
-                    umma_commit(&empty_bar[s]);
+                    __syncwarp();
                 }
-                umma_commit(&acc_full[as]);
+                if (elect_one()) umma_commit(&acc_full[as]);
+                __syncwarp();
                 ++lt;
             }
         }
@@ -503,19 +809,28 @@ gram_missing_kernel(const __grid_constant__ CUtensorMap tmapJ, const __grid_cons
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&acc_empty[as]);
                 }
+                // the values of all 16 rows first, without branches (the FP64 chains of different rows overlap), then the stores
+                double vals[16];
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    const double4 rcv = rc[c0 + r];
+                    const double Si = rcv.x, Ni = rcv.y, ri = rcv.z;
+                    const double Q = u32_to_f64(v0[r]), P1 = u32_to_f64(v1[r]);      // counts are >= 0
+                    const double P2 = u32_to_f64(v2[r]), Nn = u32_to_f64(v3[r]);
+                    // A_ij = sum g_i M_j = P2,  A_ji = sum g_j M_i = P1; every product and partial sum is an exact integer < 2^53
+                    double num = (Ni * Nj) * Q;
+                    num = fma(-(Ni * Sj), P2, num);
+                    num = fma(-(Nj * Si), P1, num);
+                    num = fma(Si * Sj, Nn, num);
+                    vals[r] = num * ri * rj;
+                }
 #pragma unroll
                 for (int r = 0; r < 16; ++r) {
                     const int il = i0 + c0 + r;
-                    const double4 rcv = rc[c0 + r];
                     if (il >= bd.mp || jl > il) continue;
                     double val;
                     if (il < bd.m) {
-                        const double Si = rcv.x, Ni = rcv.y, ri = rcv.z;
-                        const double Q = (double)(int32_t)v0[r], P1 = (double)(int32_t)v1[r];
-                        const double P2 = (double)(int32_t)v2[r], Nn = (double)(int32_t)v3[r];
-                        // A_ij = sum g_i M_j = P2,  A_ji = sum g_j M_i = P1; every product is an exact integer < 2^53
-                        const double num = Ni * Nj * Q - Ni * Sj * P2 - Nj * Si * P1 + Si * Sj * Nn;
-                        val = num * ri * rj;
+                        val = vals[r];
                         if (il == jl) val += a.one_minus_tau;
                     } else {
                         val = (il == jl) ? 1.0 : 0.0;                 // identity padding rows m..mp-1
@@ -556,6 +871,34 @@ cudaError_t launch_gram(const CUtensorMap& tmap, const GramArgs& a, cudaStream_t
         if (e != cudaSuccess) return e;
         gram_persistent_kernel<5><<<std::min(a.n_tiles, n_sm), kPThreads, PCfg<5>::kSmem, st>>>(tmap, a);
     }
+    return cudaGetLastError();
+}
+
+// One-plane CTA-pair kernel over `a.tiles` (256 x 256 super tiles; blocks whose flag is set are skipped).
+cudaError_t launch_gram_pair(const CUtensorMap& tmap, const GramArgs& a, cudaStream_t st) {
+    if (a.n_tiles == 0) return cudaSuccess;
+    static int max_pairs[2] = {0, 0};
+    const int li = a.light ? 1 : 0;
+    constexpr int kFull = 5, kLight = 3;
+    const int smem = a.light ? PairCfg<kLight>::kSmem : PairCfg<kFull>::kSmem;
+    const void* fn = a.light ? (const void*)gram_pair_kernel<kLight, 2> : (const void*)gram_pair_kernel<kFull, 1>;
+    if (max_pairs[li] == 0) {
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        int dev = 0, n_sm = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(n_sm & ~1));
+        cfg.blockDim = dim3(kPThreads);
+        cfg.dynamicSmemBytes = (size_t)smem;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, fn, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = n_sm / 2; }
+        max_pairs[li] = std::min(n, n_sm / 2);
+    }
+    const int npairs = std::min(a.n_tiles, max_pairs[li]);
+    if (a.light) gram_pair_kernel<kLight, 2><<<2 * npairs, kPThreads, smem, st>>>(tmap, a);
+    else gram_pair_kernel<kFull, 1><<<2 * npairs, kPThreads, smem, st>>>(tmap, a);
     return cudaGetLastError();
 }
 

@@ -13,12 +13,12 @@ cudaError_t launch_snp_stats(const uint8_t* bed, int64_t n_snp, int32_t n_ref, S
 // SNP rows [g0, g0 + n_rows) of the plan: genotype code rows always, mask code rows where needed (see decode.cu)
 cudaError_t launch_decode_rows(const uint8_t* bed, int32_t n_ref, int32_t n_pad, const uint32_t* row_src,
                                const int32_t* row_crow, const int32_t* row_mrow, int64_t g0, int64_t n_rows, double tau,
-                               int8_t* codes, uint8_t* dirty, int32_t* rowN, int32_t* rowS, double* rowR, const int32_t* gate,
+                               int8_t* codes, uint8_t* dirty, int32_t* rowN, int32_t* rowS, double* rowR, double2* rowC, const int32_t* gate,
                                int n_sm, cudaStream_t st);
 // the same rows as 2-bit codes in plan order with an aligned pitch (n_pad / 4 bytes) + the per-SNP statistics: the input of
 // the fused unpack + Gram kernel
 cudaError_t launch_pack_rows(const uint8_t* bed, int32_t n_ref, int32_t n_pad, const uint32_t* row_src, int64_t g0, int64_t n_rows,
-                             double tau, uint32_t* packed, int32_t* rowN, int32_t* rowS, double* rowR, int n_sm, cudaStream_t st);
+                             double tau, uint32_t* packed, int32_t* rowN, int32_t* rowS, double* rowR, double2* rowC, int n_sm, cudaStream_t st);
 int32_t decode_max_n_ref();          // largest n_ref the row-staging kernels (decoder, statistics) can take
 // flags[b] = block b has missing calls (from the decoder's counts), for the blocks in `list` (nullptr: 0..n_list-1);
 // *any |= flags
@@ -27,7 +27,7 @@ cudaError_t launch_block_flags(const BlockDesc* blocks, const int32_t* list, int
 
 // gram.cu
 struct GramArgs {
-    const GramTile* tiles;      // device
+    const GramTile* tiles;      // device (four-plane and packed-row kernels)
     int32_t n_tiles;
     const BlockDesc* blocks;    // device
     int32_t nk;                 // n_pad / 128
@@ -36,6 +36,8 @@ struct GramArgs {
     const int32_t* rowN;
     const int32_t* rowS;
     const double* rowR;
+    const double2* rowC;        // {S_i (as double), r_i} per SNP row
+    const TileRec* recs;        // self-contained tile records of the one-plane kernels (128 x 128 tiles or 256 x 256 super tiles)
     double* sigma;
     int32_t* intQ;              // optional raw planes (same offsets/ld as sigma)
     int32_t* intA;
@@ -44,8 +46,11 @@ struct GramArgs {
     int32_t light;              // persistent kernel with a 3-stage ring (97 KB: co-resident with a Cholesky panel CTA)
     const int32_t* flags;       // per block: has missing calls (device, written by block_flags_kernel)
     const int32_t* any;         // some block of this launch has missing calls
+    int32_t hint;               // tuning bits (DBSLMM_B200_GRAM_HINT): 1 = operand loads with L2 evict-last priority, 2 = streaming (evict-first) Sigma stores; measured, no effect: off
 };
 cudaError_t launch_gram(const CUtensorMap& tmap, const GramArgs& a, cudaStream_t st);
+// CTA-pair kernel: `a.tiles` = 256 x 256 super tiles of the lower triangles
+cudaError_t launch_gram_pair(const CUtensorMap& tmap, const GramArgs& a, cudaStream_t st);
 cudaError_t launch_gram_packed(const CUtensorMap& pmap, const GramArgs& a, cudaStream_t st);
 cudaError_t launch_gram_missing(const CUtensorMap& tmapJ, const CUtensorMap& tmapI, const GramArgs& a, cudaStream_t st);
 cudaError_t launch_gram_simt(const int8_t* codes, int32_t n_pad, int64_t row0, int32_t m, int32_t* q_out,

@@ -1,0 +1,15 @@
+#!/bin/bash
+# round-2 session Y: whole-warp (elect.sync) producer / MMA-issuer loops in the Gram kernels
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_streaming.py -x -q -m gpu > gpurun_out/r2y_tests.log 2>&1; echo "tests rc=$?"; tail -3 gpurun_out/r2y_tests.log
+DBSLMM_B200_GRAM=single DBSLMM_B200_GRAM_HINT=4 timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu > gpurun_out/r2y_tests_dyn.log 2>&1; echo "tests single dyn rc=$?"; tail -3 gpurun_out/r2y_tests_dyn.log
+for cfg in single:0 single:4 pair:0 pair:1; do
+  k=${cfg%%:*}; hint=${cfg##*:}
+  DBSLMM_B200_GRAM=$k DBSLMM_B200_GRAM_HINT=$hint timeout 300 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-parity > gpurun_out/r2y_${k}_${hint}.json 2> gpurun_out/r2y_${k}_${hint}.err; echo "$cfg rc=$?"; python tools/bench_brief.py gpurun_out/r2y_${k}_${hint}.json
+done
+timeout 300 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-parity --missing 0.005 > gpurun_out/r2y_missing.json 2> gpurun_out/r2y_missing.err; echo "missing rc=$?"; python tools/bench_brief.py gpurun_out/r2y_missing.json
+CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-parity"
+for cfg in single:4 pair:0; do
+  k=${cfg%%:*}; hint=${cfg##*:}
+  DBSLMM_B200_GRAM=$k DBSLMM_B200_GRAM_HINT=$hint timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active --clock-control none -k regex:'gram_p' -c 1 --csv --log-file gpurun_out/r2y_ncu_${k}_${hint}.csv $CMD > /dev/null 2>&1; echo "ncu $cfg rc=$?"; grep -v "^==" gpurun_out/r2y_ncu_${k}_${hint}.csv | cut -d, -f5,13- | tail -5
+done
