@@ -83,9 +83,40 @@ __device__ __forceinline__ void store_half_tile(const GramArgs& a, const Desc& b
         }
         return;
     }
-    // general half tile (diagonal, last tile row, debug planes): same arithmetic, predicated stores
     const int nreal = bd.m - i0;                           // rows r < nreal are real SNPs
     double* p = sig + (size_t)i0 * ld + jl;
+    if (!a.full && a.intQ == nullptr) {
+        // half tile on the diagonal or in the last tile row: the same staged arithmetic for every row (the table is zero
+        // beyond the block), then PREDICATED stores -- no branch per row
+        constexpr int kB = 8;
+#pragma unroll
+        for (int r0 = 0; r0 < NR; r0 += kB) {
+            double2 c[kB];
+            double t[kB];
+#pragma unroll
+            for (int i = 0; i < kB; ++i) c[i] = rc[r0 + i];
+#pragma unroll
+            for (int i = 0; i < kB; ++i) t[i] = u32_to_f64(v[(r0 + i) >> 5][(r0 + i) & 31]);
+#pragma unroll
+            for (int i = 0; i < kB; ++i) t[i] *= dn;
+#pragma unroll
+            for (int i = 0; i < kB; ++i) t[i] = fma(-c[i].x, Sj, t[i]);
+#pragma unroll
+            for (int i = 0; i < kB; ++i) t[i] *= c[i].y;
+#pragma unroll
+            for (int i = 0; i < kB; ++i) t[i] *= rj;
+#pragma unroll
+            for (int i = 0; i < kB; ++i) {
+                const int il = i0 + r0 + i;
+                const double val = (il == jl) ? t[i] + a.one_minus_tau : t[i];
+                if (r0 + i < nreal && jl <= il) p[(size_t)(r0 + i) * ld] = val;
+            }
+        }
+        for (int il = max(bd.m, i0); il < min(bd.mp, i0 + NR); ++il)      // identity padding rows m .. mp-1 (at most 7 per block)
+            if (jl <= il) sig[(size_t)il * ld + jl] = (il == jl) ? 1.0 : 0.0;
+        return;
+    }
+    // debug planes / upper triangle on request: same arithmetic, row by row
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
         const int il = i0 + r;
@@ -176,11 +207,13 @@ struct PCfg { static constexpr int kSmem = kPStages * 2 * kTileBytes + 1024; };
 // 128 x 128 tiles, one CTA per SM (DBSLMM_B200_GRAM=single).
 // (min-blocks 2 only caps the registers at 102 per thread: with the 3-stage ring a Gram CTA then fits next to a
 //  Cholesky panel CTA during a streaming fit)
-template <int kPStages>
-__global__ void __launch_bounds__(kPThreads, 2)
+// kAcc accumulator buffers of 128 TMEM columns (4 = all 512 columns: the MMA issuer runs up to three tiles ahead of the
+// epilogue and practically never waits for an accumulator to be handed back)
+template <int kPStages, int kMinB, int kAcc>
+__global__ void __launch_bounds__(kPThreads, kMinB)
 gram_persistent_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[kPStages], empty_bar[kPStages], acc_full[2], acc_empty[2];
+    __shared__ __align__(8) uint64_t full_bar[kPStages], empty_bar[kPStages], acc_full[kAcc], acc_empty[kAcc];
     __shared__ __align__(16) double2 row_consts[8][2][64 + 32];  // per epilogue warp, two tiles: {S, r} of its 64 rows, then of its 32 columns
     __shared__ uint32_t tmem_slot;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -191,11 +224,11 @@ gram_persistent_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs 
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kPStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
+        for (int b = 0; b < kAcc; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
         mbar_fence_init();
         tma_prefetch_desc(&tmap);
     }
-    if (warp == 1) tmem_alloc<256>(&tmem_slot);
+    if (warp == 1) tmem_alloc<128 * kAcc>(&tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -238,8 +271,8 @@ gram_persistent_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs 
             if (tn < n_tiles) nxt = ld_rec(a.recs + tn);
             if (__ldg(a.flags + cur.blk) == 0) {
                 const bool diag = (cur.ti == cur.tj);
-                const uint32_t as = lt & 1u;
-                mbar_wait(&acc_empty[as], ((lt >> 1) & 1u) ^ 1u);      // epilogue has drained this accumulator
+                const uint32_t as = lt % kAcc;
+                mbar_wait(&acc_empty[as], ((lt / kAcc) & 1u) ^ 1u);    // epilogue has drained this accumulator
                 tc_fence_after();
                 for (int ks = 0; ks < nk; ++ks, ++it) {
                     const int s = it % kPStages;
@@ -293,7 +326,7 @@ gram_persistent_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs 
             if (tn < n_tiles) stage((int)((n + 1) & 1u), nxt);
             cp_async_commit();
             if (__ldg(a.flags + cur.blk) == 0) {
-                const uint32_t as = lt & 1u;
+                const uint32_t as = lt % kAcc;
                 const int jl = cur.tj * kTile + q * 32 + lane;
                 const int i0 = cur.ti * kTile + half * 64;
                 cp_async_wait<1>();                              // this tile's table has landed (only the group just committed may be pending)
@@ -301,7 +334,7 @@ gram_persistent_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs 
                 const double2* rc = rcb[n & 1u];
                 const double2 cj = rc[64 + lane];
                 const double Sj = cj.x, rj = cj.y * dn;
-                mbar_wait(&acc_full[as], (lt >> 1) & 1u);
+                mbar_wait(&acc_full[as], (lt / kAcc) & 1u);
                 tc_fence_after();
                 const uint32_t tlane = tmem_base + as * kTile + ((uint32_t)(q * 32) << 16);
                 uint32_t v[2][32];
@@ -323,35 +356,38 @@ gram_persistent_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs 
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc<256>(tmem_base);
+    if (warp == 1) tmem_dealloc<128 * kAcc>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------
-// CTA-pair version (default).  The two CTAs of a 2-CTA cluster (one TPC) share ONE tcgen05.mma.cta_group::2 of
-// M = N = 256 over a 256 x 256 SUPER tile of the block's lower triangle: CTA r loads 128 J rows (its half of A = its 128
-// Sigma columns, the TMEM lanes) and 128 I rows (its half of B), 32 KB per K step for FOUR 128 x 128 units instead of
-// one -- half the L2 -> SM operand traffic per unit (a quarter on diagonal super tiles, where A and the B half are the
-// same rows and only one box is loaded; 9.6 GB instead of 16.5 GB per genome-wide fit by ncu), and a quarter of the
-// per-tile pipeline turnarounds.  The upper-right unit of a diagonal super tile is computed and dropped.
+// CTA-pair version (DBSLMM_B200_GRAM=pair).  The 128 x 128-tile kernel above moves 32 KB of operands from L2 per
+// 128-sample K step and tile -- 17 GB per genome-wide fit, 11.5 TB/s: once its epilogue was out of the way (session 3) it
+// ran at the L2 -> SM limit of the chip (~12 TB/s).  Here the two CTAs of a 2-CTA cluster (one TPC) work on a 256 x 256
+// SUPER tile of the block's lower triangle with tcgen05.mma.cta_group::2: CTA r loads 128 J rows (its half of A = its 128
+// Sigma columns, the TMEM lanes) and 2 x 64 I rows (its halves of the two B operands), 32 KB per K step for FOUR 128 x 128
+// units instead of one -- half the operand traffic per unit.  The super tile is computed as TWO MMAs of M = 256, N = 128
+// (I rows 0..127 and 128..255) into separate 128-column accumulators, four of which fill TMEM: every epilogue warp then
+// owns 64 rows x 32 columns of a unit, copies them out with two tcgen05.ld and hands the accumulator back BEFORE its FP64
+// work, exactly like the one-CTA kernel (a 256-column accumulator forced each warp through 64 rows of arithmetic before
+// the hand-over, and the MMA issuer waited for it half of the time).  The upper-right unit of a diagonal super tile is
+// computed and dropped; a last I half beyond the block is not computed at all.
 //   warp 0 (both CTAs)  TMA producer; completion bytes of both CTAs are counted on the LEADER's full barrier
 //   warp 1              TMEM allocator (both CTAs); the leader's warp issues the MMAs and commits to both CTAs
-//   warps 2-9 (both)    epilogue of this CTA's 128 columns x 256 rows (2 x 256 s32 TMEM columns, double-buffered):
-//                       lane quarter = warp % 4, row half = (warp - 2) / 4, two 64-row chunks per warp
-//   (measured and dropped: 16 epilogue warps of 64 rows each, handing the accumulator back before any FP64 work --
-//    2.6 ms against 2.2 ms on the same box: 96 registers per thread and spills)
+//   warps 2-9 (both)    epilogue: lane quarter = warp % 4, 64-row half of the unit = (warp - 2) / 4
 // ------------------------------------------------------------------------------------------
 static constexpr int kSuper = 256;
+static constexpr int kPairAcc = 4;                               // accumulator buffers (128 TMEM columns each)
 template <int kStages>
 struct PairCfg { static constexpr int kSmem = kStages * 2 * kTileBytes + 1024; };
 
 // (kMinB = 2 only caps the registers at 102 per thread: the 3-stage version then fits next to a Cholesky panel CTA
-//  during a streaming fit, like gram_persistent_kernel<3>)
+//  during a streaming fit, like the one-CTA kernel's)
 template <int kStages, int kMinB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPThreads, kMinB)
-gram_pair_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs a) {
+gram_pair_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap64, const GramArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], acc_full[2], acc_empty[2];
-    __shared__ __align__(16) double2 row_consts[8][2][128 + 32]; // per epilogue warp, two tiles: {S, r} of its 128 rows, then of its 32 columns
+    __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], acc_full[kPairAcc], acc_empty[kPairAcc];
+    __shared__ __align__(16) double2 row_consts[8][2][128 + 32]; // per epilogue warp, two super tiles: {S, r} of its 2 x 64 rows, then of its 32 columns
     __shared__ uint32_t tmem_slot;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -362,16 +398,19 @@ gram_pair_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs a) {
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 16); }      // 8 epilogue warps x 2 CTAs
+        for (int b = 0; b < kPairAcc; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 16); }      // 8 epilogue warps x 2 CTAs
         mbar_fence_init();
         tma_prefetch_desc(&tmap);
+        tma_prefetch_desc(&tmap64);
     }
     cluster_sync_all();                                          // both CTAs are running, all barriers exist
-    if (warp == 1) tmem_alloc_pair<512>(&tmem_slot);
+    if (warp == 1) tmem_alloc_pair<128 * kPairAcc>(&tmem_slot);
     tc_fence_before();
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
+    // units of a super tile: the I rows 256 ti .. +127 always, 256 ti + 128 .. +255 if they reach into the block
+    auto two_units = [](const TileRec& r) { return r.ti * kSuper + kTile < r.mp; };
 
     if (warp == 0) {
         uint32_t it = 0;
@@ -381,10 +420,10 @@ gram_pair_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs a) {
             const int tn = t + tstride;
             if (tn < n_tiles) nxt = ld_rec(a.recs + tn);
             if (__ldg(a.flags + cur.blk) == 0) {                  // (else: missing calls, the four-plane kernel's block)
-                const bool diag = (cur.ti == cur.tj);
-                const int32_t rowJ = cur.croff + cur.tj * kSuper + (int32_t)rank * kTile;      // this CTA's Sigma columns
-                const int32_t rowI = cur.croff + cur.ti * kSuper + (int32_t)rank * kTile;      // this CTA's half of the Sigma rows
-                const uint32_t bytes = (uint32_t)((diag ? 2 : 4) * kTileBytes);                // of BOTH CTAs
+                const bool two = two_units(cur);
+                const int32_t rowJ = cur.croff + cur.tj * kSuper + (int32_t)rank * kTile;      // this CTA's Sigma columns (A)
+                const int32_t rowI = cur.croff + cur.ti * kSuper + (int32_t)rank * 64;         // its half of the first 128 Sigma rows (B0); B1 = + 128
+                const uint32_t bytes = (uint32_t)((two ? 4 : 3) * kTileBytes);                 // of BOTH CTAs
                 for (int ks = 0; ks < nk; ++ks, ++it) {
                     const int s = it % kStages;
                     const uint32_t ph = (it / kStages) & 1u;
@@ -393,7 +432,8 @@ gram_pair_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs a) {
                     if (elect_one()) {
                         if (rank == 0) mbar_expect_tx(&full_bar[s], bytes);
                         tma_load_2d_pair(st, &tmap, ks * 128, rowJ, &full_bar[s], l2hint);
-                        if (!diag) tma_load_2d_pair(st + kTileBytes, &tmap, ks * 128, rowI, &full_bar[s], l2hint);
+                        tma_load_2d_pair(st + kTileBytes, &tmap64, ks * 128, rowI, &full_bar[s], l2hint);
+                        if (two) tma_load_2d_pair(st + kTileBytes + kTileBytes / 2, &tmap64, ks * 128, rowI + kTile, &full_bar[s], l2hint);
                     }
                     __syncwarp();
                 }
@@ -403,17 +443,18 @@ gram_pair_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs a) {
         }
     } else if (warp == 1) {
         if (rank == 0) {
-            constexpr uint32_t idesc = make_i8_idesc(kSuper, kSuper);
-            uint32_t it = 0, lt = 0;
+            constexpr uint32_t idesc = make_i8_idesc(kSuper, kTile);
+            uint32_t it = 0, ut = 0;                              // ring uses, units issued so far
             int t = t0;
             TileRec cur = ld_rec(a.recs + min(t, n_tiles - 1)), nxt = cur;
             while (t < n_tiles) {
                 const int tn = t + tstride;
                 if (tn < n_tiles) nxt = ld_rec(a.recs + tn);
                 if (__ldg(a.flags + cur.blk) == 0) {
-                    const bool diag = (cur.ti == cur.tj);
-                    const uint32_t as = lt & 1u;
-                    mbar_wait(&acc_empty[as], ((lt >> 1) & 1u) ^ 1u);      // both CTAs' epilogues have drained this accumulator
+                    const bool two = two_units(cur);
+                    const uint32_t a0 = ut % kPairAcc, a1 = (ut + 1) % kPairAcc;
+                    mbar_wait(&acc_empty[a0], ((ut / kPairAcc) & 1u) ^ 1u);          // both CTAs' epilogues have drained these accumulators
+                    if (two) mbar_wait(&acc_empty[a1], (((ut + 1) / kPairAcc) & 1u) ^ 1u);
                     tc_fence_after();
                     for (int ks = 0; ks < nk; ++ks, ++it) {
                         const int s = it % kStages;
@@ -421,39 +462,45 @@ gram_pair_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs a) {
                         mbar_wait(&full_bar[s], ph);
                         tc_fence_after();
                         const uint32_t st = smem_u32(smem + (size_t)s * 2 * kTileBytes);
-                        const uint64_t dJ = make_sw128_kmajor_desc(st), dI = make_sw128_kmajor_desc(diag ? st : st + kTileBytes);
+                        const uint64_t dJ = make_sw128_kmajor_desc(st), dI0 = make_sw128_kmajor_desc(st + kTileBytes),
+                                       dI1 = make_sw128_kmajor_desc(st + kTileBytes + kTileBytes / 2);
                         if (elect_one()) {
 #pragma unroll
-                            for (int kk = 0; kk < 4; ++kk)
-                                umma_i8_pair(tmem_base + as * kSuper, dJ + (uint64_t)(kk * 2), dI + (uint64_t)(kk * 2), idesc,
-                                             (ks > 0 || kk > 0) ? 1u : 0u);
+                            for (int kk = 0; kk < 4; ++kk) {
+                                const uint32_t acc = (ks > 0 || kk > 0) ? 1u : 0u;
+                                umma_i8_pair(tmem_base + a0 * kTile, dJ + (uint64_t)(kk * 2), dI0 + (uint64_t)(kk * 2), idesc, acc);
+                                if (two) umma_i8_pair(tmem_base + a1 * kTile, dJ + (uint64_t)(kk * 2), dI1 + (uint64_t)(kk * 2), idesc, acc);
+                            }
                             umma_commit_pair(&empty_bar[s]);
-                            if (ks == nk - 1) umma_commit_pair(&acc_full[as]);
+                            if (ks == nk - 1) {
+                                umma_commit_pair(&acc_full[a0]);
+                                if (two) umma_commit_pair(&acc_full[a1]);
+                            }
                         }
                         __syncwarp();
                     }
-                    ++lt;
+                    ut += two ? 2u : 1u;
                 }
                 cur = nxt;
                 t = tn;
             }
         }
     } else {
-        const int q = warp & 3, hsel = (warp - 2) >> 2;
+        const int q = warp & 3, half = (warp - 2) >> 2;              // TMEM lane quarter (Sigma columns), 64-row half of a unit
         double2 (*rcb)[128 + 32] = row_consts[warp - 2];
         const double dn = (double)a.n_ref;
+        // {S, r} of this warp's rows (64 of unit 0, then 64 of unit 1) and columns of super tile r -> table `buf`
         auto stage = [&](int buf, const TileRec& r) {
             const double2* src = a.rowC + r.goff;
-            const int ib = r.ti * kSuper + hsel * kTile;
 #pragma unroll
             for (int hh = 0; hh < 4; ++hh) {
-                const int il = ib + 32 * hh + lane;
+                const int il = r.ti * kSuper + (hh >> 1) * kTile + half * 64 + 32 * (hh & 1) + lane;
                 cp_async16(&rcb[buf][32 * hh + lane], src + (il < r.m ? il : 0), il < r.m);
             }
             const int jl = r.tj * kSuper + (int)rank * kTile + q * 32 + lane;
             cp_async16(&rcb[buf][128 + lane], src + (jl < r.m ? jl : 0), jl < r.m);
         };
-        uint32_t lt = 0, n = 0;
+        uint32_t ut = 0, n = 0;
         int t = t0;
         TileRec cur = ld_rec(a.recs + min(t, n_tiles - 1)), nxt = cur;
         if (t < n_tiles) stage(0, cur);
@@ -467,40 +514,34 @@ gram_pair_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs a) {
             if (tn < n_tiles) stage((int)((n + 1) & 1u), nxt);
             cp_async_commit();
             if (__ldg(a.flags + cur.blk) == 0) {
-                const uint32_t as = lt & 1u;
                 const int jmin = cur.tj * kSuper + (int)rank * kTile + q * 32;      // this warp's first Sigma column
                 const int jl = jmin + lane;
-                const int ib = cur.ti * kSuper + hsel * kTile;                      // first of this warp's 128 rows
                 cp_async_wait<1>();                              // this tile's table has landed
                 __syncwarp();
                 const double2* rc = rcb[n & 1u];
                 const double2 cj = rc[128 + lane];
                 const double Sj = cj.x, rj = cj.y * dn;
-                // a 64-row chunk is needed if it reaches into the block and below (or onto) the diagonal of this warp's columns
-                const bool need0 = (ib < cur.mp) && (ib + 63 >= jmin);
-                const bool need1 = (ib + 64 < cur.mp) && (ib + 127 >= jmin);
-                mbar_wait(&acc_full[as], (lt >> 1) & 1u);
-                tc_fence_after();
-                const uint32_t tlane = tmem_base + as * kSuper + (uint32_t)(hsel * kTile) + ((uint32_t)(q * 32) << 16);
-                bool handed_back = false;
+                const int nu = two_units(cur) ? 2 : 1;
 #pragma unroll 1
-                for (int c = 0; c < 2; ++c) {                        // (not unrolled: one copy of the store code)
-                    const bool need = (c == 0) ? need0 : need1;
+                for (int u = 0; u < nu; ++u, ++ut) {                 // (not unrolled: one copy of the store code)
+                    const uint32_t as = ut % kPairAcc;
+                    const int i0 = cur.ti * kSuper + u * kTile + half * 64;          // first of this warp's 64 rows of the unit
+                    // needed if the rows reach into the block and below (or onto) the diagonal of this warp's columns
+                    const bool need = (i0 < cur.mp) && (i0 + 63 >= jmin);
+                    mbar_wait(&acc_full[as], (ut / kPairAcc) & 1u);
+                    tc_fence_after();
+                    const uint32_t tlane = tmem_base + as * kTile + (uint32_t)(half * 64) + ((uint32_t)(q * 32) << 16);
                     uint32_t v[2][32];
                     if (need) {
-                        tmem_ld32(tlane + 64 * c, v[0]);
-                        tmem_ld32(tlane + 64 * c + 32, v[1]);
+                        tmem_ld32(tlane, v[0]);
+                        tmem_ld32(tlane + 32, v[1]);
                         tmem_ld_wait();
                     }
-                    if (!handed_back && (c == 1 || !need1)) {
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive_rank(&acc_empty[as], 0);      // the leader's MMA issuer may reuse the accumulator
-                        handed_back = true;
-                    }
-                    if (need) store_half_tile(a, cur, v, rc + 64 * c, ib + 64 * c > jmin + 31, ib + 64 * c, jl, Sj, rj);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_rank(&acc_empty[as], 0);          // copied out: the leader's MMA issuer may reuse the accumulator
+                    if (need) store_half_tile(a, cur, v, rc + 64 * u, i0 > jmin + 31, i0, jl, Sj, rj);
                 }
-                ++lt;
             }
             cur = nxt;
             nxt = nn;
@@ -511,7 +552,7 @@ gram_pair_kernel(const __grid_constant__ CUtensorMap tmap, const GramArgs a) {
     }
     tc_fence_before();
     cluster_sync_all();          // the peer's shared memory, barriers and TMEM stay alive until both CTAs are done
-    if (warp == 1) tmem_dealloc_pair<512>(tmem_base);
+    if (warp == 1) tmem_dealloc_pair<128 * kPairAcc>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -863,19 +904,19 @@ cudaError_t launch_gram(const CUtensorMap& tmap, const GramArgs& a, cudaStream_t
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     if (a.light) {
-        e = cudaFuncSetAttribute(gram_persistent_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg<3>::kSmem);
+        e = cudaFuncSetAttribute(gram_persistent_kernel<3, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg<3>::kSmem);
         if (e != cudaSuccess) return e;
-        gram_persistent_kernel<3><<<std::min(a.n_tiles, n_sm), kPThreads, PCfg<3>::kSmem, st>>>(tmap, a);
+        gram_persistent_kernel<3, 2, 4><<<std::min(a.n_tiles, n_sm), kPThreads, PCfg<3>::kSmem, st>>>(tmap, a);
     } else {
-        e = cudaFuncSetAttribute(gram_persistent_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg<5>::kSmem);
+        e = cudaFuncSetAttribute(gram_persistent_kernel<5, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg<5>::kSmem);
         if (e != cudaSuccess) return e;
-        gram_persistent_kernel<5><<<std::min(a.n_tiles, n_sm), kPThreads, PCfg<5>::kSmem, st>>>(tmap, a);
+        gram_persistent_kernel<5, 1, 4><<<std::min(a.n_tiles, n_sm), kPThreads, PCfg<5>::kSmem, st>>>(tmap, a);
     }
     return cudaGetLastError();
 }
 
 // One-plane CTA-pair kernel over `a.tiles` (256 x 256 super tiles; blocks whose flag is set are skipped).
-cudaError_t launch_gram_pair(const CUtensorMap& tmap, const GramArgs& a, cudaStream_t st) {
+cudaError_t launch_gram_pair(const CUtensorMap& tmap, const CUtensorMap& tmap64, const GramArgs& a, cudaStream_t st) {
     if (a.n_tiles == 0) return cudaSuccess;
     static int max_pairs[2] = {0, 0};
     const int li = a.light ? 1 : 0;
@@ -897,8 +938,8 @@ cudaError_t launch_gram_pair(const CUtensorMap& tmap, const GramArgs& a, cudaStr
         max_pairs[li] = std::min(n, n_sm / 2);
     }
     const int npairs = std::min(a.n_tiles, max_pairs[li]);
-    if (a.light) gram_pair_kernel<kLight, 2><<<2 * npairs, kPThreads, smem, st>>>(tmap, a);
-    else gram_pair_kernel<kFull, 1><<<2 * npairs, kPThreads, smem, st>>>(tmap, a);
+    if (a.light) gram_pair_kernel<kLight, 2><<<2 * npairs, kPThreads, smem, st>>>(tmap, tmap64, a);
+    else gram_pair_kernel<kFull, 1><<<2 * npairs, kPThreads, smem, st>>>(tmap, tmap64, a);
     return cudaGetLastError();
 }
 

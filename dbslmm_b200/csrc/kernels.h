@@ -50,7 +50,7 @@ struct GramArgs {
 };
 cudaError_t launch_gram(const CUtensorMap& tmap, const GramArgs& a, cudaStream_t st);
 // CTA-pair kernel: `a.tiles` = 256 x 256 super tiles of the lower triangles
-cudaError_t launch_gram_pair(const CUtensorMap& tmap, const GramArgs& a, cudaStream_t st);
+cudaError_t launch_gram_pair(const CUtensorMap& tmap, const CUtensorMap& tmap64, const GramArgs& a, cudaStream_t st);
 cudaError_t launch_gram_packed(const CUtensorMap& pmap, const GramArgs& a, cudaStream_t st);
 cudaError_t launch_gram_missing(const CUtensorMap& tmapJ, const CUtensorMap& tmapI, const GramArgs& a, cudaStream_t st);
 cudaError_t launch_gram_simt(const int8_t* codes, int32_t n_pad, int64_t row0, int32_t m, int32_t* q_out,

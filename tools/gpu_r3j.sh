@@ -1,0 +1,9 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_streaming.py -x -q -m gpu 2>&1 | tail -2
+DBSLMM_B200_GRAM=single timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_streaming.py -x -q -m gpu 2>&1 | tail -2
+for k in single pair single; do
+  DBSLMM_B200_GRAM=$k timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-parity > gpurun_out/r3j_$k.json 2>/dev/null; python tools/bench_brief.py gpurun_out/r3j_$k.json
+done
+CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-parity"
+DBSLMM_B200_GRAM=single timeout 600 ncu --set full --clock-control none --import-source on -k regex:gram_persistent -c 1 -o gpurun_out/r3j_gram_single $CMD > gpurun_out/r3j_ncu.log 2>&1; echo "ncu rc=$?"
