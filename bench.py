@@ -641,6 +641,10 @@ def main():
     dec_all_gbs = float(tms[-1]["decode_bytes"]) / (dec_ms * 1e-3) / 1e9 if dec_ms > 0 else 0.0
     gram_pops = float(tms[-1]["gram_ops"]) / (gram_ms * 1e-3) / 1e15 if gram_ms > 0 else 0.0
     sigma_bytes = float(np.sum((w["sizes"].astype(np.float64)) ** 2)) * 4.0     # lower triangle, 8 B
+    # operand bytes the one-plane kernel pulls from L2 per fit: a 128 x 128 tile loads two [128 rows x n_pad] int8 strips
+    # (one on the diagonal)
+    _nt = np.ceil(np.ceil(w["sizes"] / 8.0) * 8.0 / 128.0)
+    gram_l2_bytes = float(np.sum(_nt + _nt * (_nt - 1.0))) * 128.0 * float(((n_ref + 127) // 128) * 128)
     other = {"decode": {"bound": "hbm", "achieved": dec_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": dec_gbs / hbm_peak,
                         "bytes": ".bed rows read (algorithmic, SURVEY 8d)", "with_int8_codes_written_GBs": dec_all_gbs,
                         "with_int8_codes_written_frac": dec_all_gbs / hbm_peak, "peak_source": hbm_src, "ms": dec_ms},
@@ -649,6 +653,8 @@ def main():
                       "peak_source": "torch._int_mm (cuBLASLt IGEMM s8 x s8 -> s32) 8192^3 measured in this run (MEASURED_PEAKS.json has no int8 figure)",
                       "sigma_write_GBs": sigma_bytes / (gram_ms * 1e-3) / 1e9 if world == 1 and gram_ms > 0 else None,
                       "sigma_write_frac_of_hbm": sigma_bytes / (gram_ms * 1e-3) / 1e9 / hbm_peak if world == 1 and gram_ms > 0 else None,
+                      "operand_l2_GBs": gram_l2_bytes / (gram_ms * 1e-3) / 1e9 if world == 1 and gram_ms > 0 and args.missing == 0 else None,
+                      "operand_l2_note": "128 x 128 tiles pull 32 KB of int8 operands per 128-sample K step and tile from L2 (TMA); ncu l1tex__m_xbar2l1tex_read_bytes agrees (profiles/r03_gram_single_full.txt).  No ceiling is claimed: the same kernel sustains 15.8 TB/s at C5 (157 K steps per tile) against 10.8 TB/s at C3 (16 K steps per tile)",
                       "ms": gram_ms},
              "solve_total_ms": avg("solve_ms"), "h2d_ms": avg("h2d_ms"), "d2h_ms": avg("d2h_ms"),
              "chol_class_ms": [float(np.mean([t["class_ms"][c] for t in tms])) for c in range(4)]}
