@@ -908,9 +908,9 @@ cudaError_t launch_gram(const CUtensorMap& tmap, const GramArgs& a, cudaStream_t
         if (e != cudaSuccess) return e;
         gram_persistent_kernel<3, 2, 4><<<std::min(a.n_tiles, n_sm), kPThreads, PCfg<3>::kSmem, st>>>(tmap, a);
     } else {
-        e = cudaFuncSetAttribute(gram_persistent_kernel<5, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg<5>::kSmem);
+        e = cudaFuncSetAttribute(gram_persistent_kernel<6, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg<6>::kSmem);
         if (e != cudaSuccess) return e;
-        gram_persistent_kernel<5, 1, 4><<<std::min(a.n_tiles, n_sm), kPThreads, PCfg<5>::kSmem, st>>>(tmap, a);
+        gram_persistent_kernel<6, 1, 4><<<std::min(a.n_tiles, n_sm), kPThreads, PCfg<6>::kSmem, st>>>(tmap, a);
     }
     return cudaGetLastError();
 }

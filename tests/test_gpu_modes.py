@@ -37,6 +37,12 @@ MODES = {
     # the correlation builder of blocks without missing calls: the int8-row kernel fed by the decoder (default) or the
     # experimental fused unpack + Gram from packed 2-bit rows
     "fused_unpack_gram_from_packed_rows": {"DBSLMM_B200_GRAM": "packed"},
+    # ... or by CTA pairs (tcgen05 cta_group::2, 256 x 256 super tiles as two N = 128 MMAs), with and without the L2 hints
+    "gram_by_cta_pairs": {"DBSLMM_B200_GRAM": "pair"},
+    "gram_by_cta_pairs_l2_hints": {"DBSLMM_B200_GRAM": "pair", "DBSLMM_B200_GRAM_HINT": "3"},
+    "gram_single_cta_l2_hints": {"DBSLMM_B200_GRAM": "single", "DBSLMM_B200_GRAM_HINT": "3"},
+    # the panel kernel without the next item's first chunk issued during the epilogue
+    "no_next_item_prefetch": {"DBSLMM_B200_NEXT_PF": "0", "DBSLMM_B200_TPC": "8,0"},
 }
 KEYS = sorted({k for m in MODES.values() for k in m})
 

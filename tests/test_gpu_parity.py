@@ -116,6 +116,45 @@ def test_fused_unpack_gram_is_bit_exact():
         eng.close()
 
 
+@pytest.mark.parametrize("variant", ["single", "pair"])
+def test_one_plane_gram_variants_are_bit_exact(variant):
+    """Both one-plane correlation builders -- 128 x 128 tiles by one CTA (default) and 256 x 256 super tiles by a CTA pair
+    (tcgen05 cta_group::2) -- give the integer Gram bit for bit and Sigma / betas as the oracle, on block sizes around the
+    tile edges (1 .. 3 super tiles per side, last tile rows of 1, 127, 128 and 129 SNPs), resident and streaming."""
+    sizes, n_ref = [129, 256, 1, 385, 640, 511, 257], 500
+    w = synth.make_workload(321, sizes, n_ref, missing_rate=0.0, frac_large=0.02)
+    os.environ["DBSLMM_B200_GRAM"] = variant
+    try:
+        eng = _abi.Engine(0)
+    finally:
+        os.environ.pop("DBSLMM_B200_GRAM", None)
+    try:
+        csr = (w["s_off"], w["s_pos"], w["s_z"], w["l_off"], w["l_pos"], w["l_z"])
+        bs, bl, _, _ = O.est(w["bed"], n_ref, 10_000, 1e-4, *csr, threads=4, mode=O.MODE_EXACT)
+        for streaming in (False, True):
+            if streaming:
+                r = eng.fit(*csr, sigma_s=[1e-4], n_obs=10_000, flags=_abi.FLAG_KEEP_INT_GRAM, bed=w["bed"], n_ref=n_ref)
+            else:
+                eng.load_bed(w["bed"], n_ref)
+                r = eng.fit(*csr, sigma_s=[1e-4], n_obs=10_000, flags=_abi.FLAG_KEEP_INT_GRAM)
+            assert r["n_bad"] == 0 and r["timing"]["n_blocks_missing"] == 0
+            for b, m in enumerate(w["block_sizes"]):
+                Q, A, N = eng.block_gram(b, m)
+                Qo, Ao, No = O.gram_int(w["bed"], n_ref, block_pos(w, b))
+                assert np.array_equal(Q, Qo) and np.array_equal(A, Ao) and np.array_equal(N, No)
+            assert relmax(r["beta_s"][0], bs) <= 1e-10 and relmax(r["beta_l"][0], bl) <= 1e-10
+        # the production path (no debug planes: the straight-line and the predicated epilogue paths instead of the
+        # row-by-row one) must give the same Sigma and betas
+        r2 = eng.fit(*csr, sigma_s=[1e-4], n_obs=10_000)
+        assert r2["n_bad"] == 0
+        assert relmax(r2["beta_s"][0], bs) <= 1e-10 and relmax(r2["beta_l"][0], bl) <= 1e-10
+        for b, m in enumerate(w["block_sizes"]):
+            S = eng.block_sigma(b, m)
+            assert np.abs(S - O.sigma(w["bed"], n_ref, block_pos(w, b))).max() <= 1e-13, (variant, b)
+    finally:
+        eng.close()
+
+
 @pytest.mark.parametrize("mode", ["dbslmm", "lmm"])
 def test_beta_vs_exact_oracle(case, engine, mode):
     _, w = case
