@@ -9,6 +9,10 @@
 // batches and overlaps all of that; with fit_args.quadform_out the solve is replaced by the
 // `valid` tool's quadratic form.  No CPU arithmetic on the data path: without a CUDA device every
 // entry point fails.
+#include <nvtx3/nvToolsExt.h>
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -224,11 +228,14 @@ inline void par_memcpy(void* dst, const void* src, size_t bytes) {
 }
 
 // DBSLMM_B200_TRACE=1: host-side wall-clock marks of one fit on stderr (tuning aid)
+// Phase marks of a fit: NVTX markers always (free without a profiler attached; they line the phases up with the kernels in
+// an Nsight timeline), wall-clock lines on stderr with DBSLMM_B200_TRACE=1.
 struct Trace {
     bool on;
     std::chrono::steady_clock::time_point t0;
     Trace() : on(std::getenv("DBSLMM_B200_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
     void mark(const char* what) const {
+        nvtxMarkA(what);
         if (on) std::fprintf(stderr, "[dbslmm_b200 trace] %-28s %8.3f ms\n", what,
                              std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
     }
@@ -322,11 +329,39 @@ int make_batches(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, 
 
 // A list that is built in place inside the pinned plan blob (no temporary vector -- a fresh 5 MB vector per fit costs
 // more in page faults than the list costs to fill -- and no copy into the blob afterwards).
+// Non-temporal stores for the O(#SNPs) part of the pinned plan blob.  The blob is written by several host threads and read
+// once, by the GPU's copy engine: with ordinary stores its lines sit dirty in the caches of whichever cores ran the fill
+// threads, and the H2D copy then crawls at 13-17 GB/s instead of 54 (measured: tools/h2d_probe.py, 28 MB written by one
+// thread 0.55 ms, by eight threads 2.2-3.0 ms; in the streaming fit the blob arrived 1.6 ms after the first panel region).
+#if defined(__x86_64__)
+inline void nt_store(uint32_t* p, uint32_t v) { _mm_stream_si32(reinterpret_cast<int*>(p), (int)v); }
+inline void nt_store(int32_t* p, int32_t v) { _mm_stream_si32(reinterpret_cast<int*>(p), v); }
+inline void nt_store(double* p, double v) { long long b; std::memcpy(&b, &v, 8); _mm_stream_si64(reinterpret_cast<long long*>(p), b); }
+template <class T>
+inline void nt_copy(T* dst, const T& v) {          // records of the plan lists: 4 bytes or a multiple of 16 (16-byte aligned)
+    if constexpr (sizeof(T) % 16 == 0) {
+        const __m128i* src = reinterpret_cast<const __m128i*>(&v);
+        for (size_t i = 0; i < sizeof(T) / 16; ++i) _mm_stream_si128(reinterpret_cast<__m128i*>(dst) + i, _mm_loadu_si128(src + i));
+    } else {
+        static_assert(sizeof(T) == 4, "plan list records are 4 bytes or a multiple of 16");
+        int b; std::memcpy(&b, &v, 4); _mm_stream_si32(reinterpret_cast<int*>(dst), b);
+    }
+}
+inline void nt_fence() { _mm_sfence(); }
+#else
+template <class T>
+inline void nt_copy(T* dst, const T& v) { *dst = v; }
+inline void nt_store(uint32_t* p, uint32_t v) { *p = v; }
+inline void nt_store(int32_t* p, int32_t v) { *p = v; }
+inline void nt_store(double* p, double v) { *p = v; }
+inline void nt_fence() {}
+#endif
+
 template <class T>
 struct BlobList {
     T* p = nullptr;
     size_t n = 0, cap = 0;
-    void push_back(const T& v) { if (n < cap) p[n] = v; ++n; }      // overflow is detected by the caller (n > cap)
+    void push_back(const T& v) { if (n < cap) nt_copy(&p[n], v); ++n; }      // (non-temporal, see nt_store) overflow is detected by the caller (n > cap)
     size_t size() const { return n; }
 };
 
@@ -423,7 +458,7 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
     // per-SNP rows (source .bed row, SNP-row index, z-score): the only O(#SNPs) part of the plan, filled by a few
     // host threads, each owning a contiguous range of blocks; the .bed row range check rides along
     {
-        const int nthr = (int)std::max<int64_t>(1, std::min<int64_t>({8, (int64_t)std::thread::hardware_concurrency(), goff / 65536}));
+        const int nthr = (int)std::max<int64_t>(1, std::min<int64_t>({12, (int64_t)std::thread::hardware_concurrency() - 2, goff / 65536}));
         auto fill = [&, rs, rcr, rmr, z](int b0, int b1) {
             int oob = 0;
             for (int b = b0; b < b1; ++b) {
@@ -437,7 +472,7 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
                 for (int j = 0; j < d.ms; ++j) {
                     const int32_t p = sp[j];
                     oob |= (p < 0) | (p >= n_snp);
-                    rsb[j] = (uint32_t)p; rcb[j] = d.croff + j; rmb[j] = d.croff + d.m + j; zb[j] = sz[j];
+                    nt_store(rsb + j, (uint32_t)p); nt_store(rcb + j, d.croff + j); nt_store(rmb + j, d.croff + d.m + j); nt_store(zb + j, sz[j]);
                 }
                 if (d.m > d.ms) {
                     const int32_t* lp = a->l_pos + a->l_off[b];
@@ -445,10 +480,11 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
                     for (int j = d.ms; j < d.m; ++j) {
                         const int32_t p = lp[j - d.ms];
                         oob |= (p < 0) | (p >= n_snp);
-                        rsb[j] = (uint32_t)p; rcb[j] = d.croff + j; rmb[j] = d.croff + d.m + j; zb[j] = lz[j - d.ms];
+                        nt_store(rsb + j, (uint32_t)p); nt_store(rcb + j, d.croff + j); nt_store(rmb + j, d.croff + d.m + j); nt_store(zb + j, lz[j - d.ms]);
                     }
                 }
             }
+            nt_fence();
             if (oob) fill_bad.store(1);
         };
         if (nthr == 1) fill(0, nb);
@@ -506,6 +542,7 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
         B.mtile1 = (int32_t)tiles_miss.size();
         B.ptile1 = (int32_t)tiles_pair.size();
     }
+    nt_fence();
     P.n_tiles_plain = (int32_t)tiles_plain.size();
     P.n_tiles_miss = (int32_t)tiles_miss.size();
     P.n_tiles_pair = (int32_t)tiles_pair.size();
@@ -579,6 +616,7 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
         P.scratch_doubles += batch_scratch;
     }
 
+    nt_fence();
     tile_thread.join();
     if (tr) tr->mark("  plan: tile + step lists");
     // ---- the lists were written in place; the panel items close the blob
@@ -1196,6 +1234,8 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
             if (d.m > d.ms) std::memcpy(z + d.goff + d.ms, a->l_z + a->l_off[b], sizeof(double) * (size_t)(d.m - d.ms));
         }
     }
+    cudaEvent_t tr_blob = nullptr, tr_blob0 = nullptr, tr_dec[kMaxBatches] = {}, tr_start[kMaxBatches] = {};      // DBSLMM_B200_TRACE only
+    int tr_chain = 0;
     CU_TRY(h, cudaEventRecord(h->ev[0], st));
     // ---- upload
     if (!reuse) {
@@ -1204,9 +1244,11 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
         } else {
             // The plan blob travels on the UPLOAD stream, between the first batches and the rest of the panel: copies
             // of one stream run in issue order, whereas a copy on another stream may sit behind the whole panel.
+            if (tr.on) { cudaEventCreate(&tr_blob0); cudaEventRecord(tr_blob0, h->up_stream); }
             if (P.blob_bytes) CU_TRY(h, cudaMemcpyAsync(dblob, h->h_blob.p, P.blob_bytes, cudaMemcpyHostToDevice, h->up_stream));
             CU_TRY(h, cudaEventRecord(h->ev_blob, h->up_stream));
             CU_TRY(h, cudaStreamWaitEvent(st, h->ev_blob, 0));
+            if (tr.on) { cudaEventCreate(&tr_blob); cudaEventRecord(tr_blob, h->up_stream); }
             int rc = upload_issue(h, P, U, a->bed, nbatch, subset);
             if (rc < 0) return rc;
             tr.mark("all uploads issued");
@@ -1266,6 +1308,7 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
     auto chain = [&](int64_t g0, int64_t g1, const int32_t* list, int32_t n_list, int32_t t0, int32_t t1, int32_t mt0, int32_t mt1,
                      int32_t pt0, int32_t pt1, int32_t* any, bool light) -> int {
         if (g1 <= g0) return DBSLMM_B200_OK;
+        if (tr.on && streaming && tr_chain < kMaxBatches) { cudaEventCreate(&tr_start[tr_chain]); cudaEventRecord(tr_start[tr_chain], st); }
         if (packed_gram)        // 2-bit rows in plan order + per-SNP statistics; int8 rows only if a block turns out to need them
             CU_TRY(h, launch_pack_rows((const uint8_t*)h->bed.p, h->n_ref, h->n_pad, d_rowsrc, g0, g1 - g0, a->tau, (uint32_t*)h->packed.p,
                                        (int32_t*)h->rowN.p, (int32_t*)h->rowS.p, (double*)h->rowR.p, (double2*)h->rowC.p, h->n_sm, st));
@@ -1273,6 +1316,7 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
             CU_TRY(h, launch_decode_rows((const uint8_t*)h->bed.p, h->n_ref, h->n_pad, d_rowsrc, d_crow, d_mrow, g0, g1 - g0, a->tau,
                                          (int8_t*)h->codes.p, (uint8_t*)h->dirty.p, (int32_t*)h->rowN.p, (int32_t*)h->rowS.p,
                                          (double*)h->rowR.p, (double2*)h->rowC.p, nullptr, h->n_sm, st));
+        if (tr.on && streaming && tr_chain < kMaxBatches) { cudaEventCreate(&tr_dec[tr_chain]); cudaEventRecord(tr_dec[tr_chain], st); ++tr_chain; }
         CU_TRY(h, launch_block_flags(d_blocks, list, n_list, (const int32_t*)h->rowN.p, h->n_ref, d_bflags, any, st));
         n_launch += 2;
         g.any = any;
@@ -1546,6 +1590,20 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
     CU_TRY(h, cudaStreamSynchronize(st));
     tr.mark("device done");
     if (tr.on && streaming && !pcg) {
+        if (tr_blob && tr_blob0) {
+            float b = 0.f, b0 = 0.f;
+            cudaEventElapsedTime(&b, h->ev[0], tr_blob);
+            cudaEventElapsedTime(&b0, h->ev[0], tr_blob0);
+            std::fprintf(stderr, "[dbslmm_b200 trace] plan blob (%.1f MB): copy starts %.2f, on the device at %.2f (device ms after fit start)\n", (double)P.blob_bytes / 1e6, b0, b);
+            cudaEventDestroy(tr_blob); cudaEventDestroy(tr_blob0);
+        }
+        for (int c = 0; c < tr_chain; ++c) {
+            float s0 = 0.f, d0 = 0.f;
+            cudaEventElapsedTime(&s0, h->ev[0], tr_start[c]);
+            cudaEventElapsedTime(&d0, h->ev[0], tr_dec[c]);
+            std::fprintf(stderr, "[dbslmm_b200 trace] chain %d (batch %d): starts %.2f  decoded %.2f\n", c, P.up_order[c], s0, d0);
+            cudaEventDestroy(tr_start[c]); cudaEventDestroy(tr_dec[c]);
+        }
         for (int bi = 0; bi < nbatch; ++bi) {
             float u = 0.f, g2 = 0.f, c = 0.f, j = 0.f;
             cudaEventElapsedTime(&u, h->ev[0], h->ev_up[bi]);
@@ -1623,6 +1681,7 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
 extern "C" {
 
 int dbslmm_b200_fit(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a) {
+    struct Range { Range() { nvtxRangePushA("dbslmm_b200_fit"); } ~Range() { nvtxRangePop(); } } nvtx_range;
     if (!h || !a) return DBSLMM_B200_ERR_ARG;
     if (!a->bed && h->n_snp == 0) return fail(h, DBSLMM_B200_ERR_STATE, "fit before load_bed (and no fit_args.bed)");
     if (a->bed && (a->bed_n_snp <= 0 || a->bed_n_ref <= 1)) return fail(h, DBSLMM_B200_ERR_ARG, "fit: bad bed_n_snp / bed_n_ref");
