@@ -484,4 +484,19 @@ cudaError_t launch_decode_rows(const uint8_t* bed, int32_t n_ref, int32_t n_pad,
     return launch_decode_t<2>(bed, n_ref, pitch, n_pad, buf, wpc, row_src, row_crow, row_mrow, g0, n_rows, tau, codes, dirty, rowN, rowS, rowR, rowC, gate, n_sm, st);
 }
 
+// Code row and mask row of every SNP row (the decoder's scatter maps): a function of the block layout, so they are written
+// here instead of travelling with the plan blob (8 bytes per SNP less to build on the host and to push across PCIe).
+__global__ void fill_rowmaps_kernel(const BlockDesc* __restrict__ blocks, int32_t* __restrict__ row_crow, int32_t* __restrict__ row_mrow) {
+    const BlockDesc bd = blocks[blockIdx.x];
+    for (int j = threadIdx.x; j < bd.m; j += blockDim.x) {
+        row_crow[bd.goff + j] = bd.croff + j;
+        row_mrow[bd.goff + j] = bd.croff + bd.m + j;
+    }
+}
+cudaError_t launch_fill_rowmaps(const BlockDesc* blocks, int32_t n_blocks, int32_t* row_crow, int32_t* row_mrow, cudaStream_t st) {
+    if (n_blocks == 0) return cudaSuccess;
+    fill_rowmaps_kernel<<<n_blocks, 256, 0, st>>>(blocks, row_crow, row_mrow);
+    return cudaGetLastError();
+}
+
 }  // namespace dbslmm

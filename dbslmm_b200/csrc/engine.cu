@@ -29,6 +29,7 @@
 #include "../../include/dbslmm_b200.h"
 #include "common.cuh"
 #include "kernels.h"
+#include "hostpool.hpp"
 
 using namespace dbslmm;
 
@@ -179,7 +180,7 @@ struct dbslmm_b200_handle {
     int64_t n_snp = 0;
     int32_t n_ref = 0, pitch = 0, n_pad = 0;
     // workspace
-    DevBuf codes, sigma, lbuf, rowN, rowS, rowR, planblob, beta, status, intQ, intA, intN, scratch, counters, wbuf, vbed, vstats, vwork, dflag, dirty, bflags, packed, rowC;
+    DevBuf codes, sigma, lbuf, rowN, rowS, rowR, planblob, beta, status, intQ, intA, intN, scratch, counters, wbuf, vbed, vstats, vwork, dflag, dirty, bflags, packed, rowC, rowmap;
     // validation panel of the scoring step, announced by dbslmm_b200_score_prefetch: uploaded in the shadow of the next fit
     const uint8_t* val_host = nullptr;
     int64_t val_n_snp = 0;
@@ -190,6 +191,7 @@ struct dbslmm_b200_handle {
     int32_t dirty_n_ref = 0;             // ... for this panel width (another width = another default mask pattern)
     const void* dirty_codes = nullptr;   // ... and this code buffer
     PinBuf h_blob, h_out;
+    HostPool pool;                              // host worker threads (plan building, tensor maps, row-range scan)
     Plan plan;
 
     int32_t last_flags = 0, last_solver = 0, last_nfolds = 0;
@@ -334,11 +336,13 @@ int make_batches(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, 
 // threads, and the H2D copy then crawls at 13-17 GB/s instead of 54 (measured: tools/h2d_probe.py, 28 MB written by one
 // thread 0.55 ms, by eight threads 2.2-3.0 ms; in the streaming fit the blob arrived 1.6 ms after the first panel region).
 #if defined(__x86_64__)
-inline void nt_store(uint32_t* p, uint32_t v) { _mm_stream_si32(reinterpret_cast<int*>(p), (int)v); }
-inline void nt_store(int32_t* p, int32_t v) { _mm_stream_si32(reinterpret_cast<int*>(p), v); }
-inline void nt_store(double* p, double v) { long long b; std::memcpy(&b, &v, 8); _mm_stream_si64(reinterpret_cast<long long*>(p), b); }
+static bool g_nt = std::getenv("DBSLMM_B200_NT") == nullptr || std::atoi(std::getenv("DBSLMM_B200_NT")) != 0;      // DBSLMM_B200_NT=0: ordinary stores
+inline void nt_store(uint32_t* p, uint32_t v) { if (g_nt) _mm_stream_si32(reinterpret_cast<int*>(p), (int)v); else *p = v; }
+inline void nt_store(int32_t* p, int32_t v) { if (g_nt) _mm_stream_si32(reinterpret_cast<int*>(p), v); else *p = v; }
+inline void nt_store(double* p, double v) { if (!g_nt) { *p = v; return; } long long b; std::memcpy(&b, &v, 8); _mm_stream_si64(reinterpret_cast<long long*>(p), b); }
 template <class T>
 inline void nt_copy(T* dst, const T& v) {          // records of the plan lists: 4 bytes or a multiple of 16 (16-byte aligned)
+    if (!g_nt) { *dst = v; return; }
     if constexpr (sizeof(T) % 16 == 0) {
         const __m128i* src = reinterpret_cast<const __m128i*>(&v);
         for (size_t i = 0; i < sizeof(T) / 16; ++i) _mm_stream_si128(reinterpret_cast<__m128i*>(dst) + i, _mm_loadu_si128(src + i));
@@ -415,8 +419,7 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
     auto place = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
     P.o_blocks = place(sizeof(BlockDesc) * (size_t)nb);
     P.o_rowsrc = place(sizeof(uint32_t) * (size_t)goff);
-    P.o_crow = place(sizeof(int32_t) * (size_t)goff);
-    P.o_mrow = place(sizeof(int32_t) * (size_t)goff);
+    P.o_crow = P.o_mrow = 0;      // (the code-row / mask-row maps are a function of the layout: written on the device, fill_rowmaps)
     P.o_z = place(sizeof(double) * (size_t)goff);
     size_t n_t1 = 0, n_t2 = 0, n_t3 = 0, n_steps_tiles = 0, n_diag_max = 0;
     for (int b = 0; b < nb; ++b) {
@@ -449,30 +452,28 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
     struct { uint8_t* p; uint8_t* data() const { return p; } } blob{(uint8_t*)h->h_blob.p};
     std::memcpy(blob.data() + P.o_blocks, P.blocks.data(), sizeof(BlockDesc) * (size_t)nb);
     uint32_t* rs = reinterpret_cast<uint32_t*>(blob.data() + P.o_rowsrc);
-    int32_t* rcr = reinterpret_cast<int32_t*>(blob.data() + P.o_crow);
-    int32_t* rmr = reinterpret_cast<int32_t*>(blob.data() + P.o_mrow);
     double* z = reinterpret_cast<double*>(blob.data() + P.o_z);
-    std::vector<std::thread> fill_threads;
+    // every helper task below references this frame: the guard waits for all of them on every way out
+    TaskGroup g_fill, g_tiles, g_lists;
+    struct PoolGuard { HostPool& p; TaskGroup& a; TaskGroup& b; TaskGroup& c; ~PoolGuard() { p.wait(a); p.wait(b); p.wait(c); } } pool_guard{h->pool, g_fill, g_tiles, g_lists};
     std::atomic<int> fill_bad{0};
-    struct Joiner { std::vector<std::thread>& t; ~Joiner() { for (std::thread& x : t) if (x.joinable()) x.join(); } } joiner{fill_threads};
     // per-SNP rows (source .bed row, SNP-row index, z-score): the only O(#SNPs) part of the plan, filled by a few
     // host threads, each owning a contiguous range of blocks; the .bed row range check rides along
     {
-        const int nthr = (int)std::max<int64_t>(1, std::min<int64_t>({12, (int64_t)std::thread::hardware_concurrency() - 2, goff / 65536}));
-        auto fill = [&, rs, rcr, rmr, z](int b0, int b1) {
+        static const int fill_max = std::getenv("DBSLMM_B200_FILL_THREADS") ? std::max(1, std::atoi(std::getenv("DBSLMM_B200_FILL_THREADS"))) : 6;       // (the pool also runs the two tile-list tasks and one step-list task per batch)
+        const int nthr = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)fill_max, (int64_t)std::thread::hardware_concurrency(), goff / 65536}));
+        auto fill = [&, rs, z](int b0, int b1) {
             int oob = 0;
             for (int b = b0; b < b1; ++b) {
                 const BlockDesc& d = P.blocks[b];
                 const int32_t* sp = a->s_pos + a->s_off[b];
                 const double* sz = a->s_z + a->s_off[b];
                 uint32_t* rsb = rs + d.goff;
-                int32_t* rcb = rcr + d.goff;
-                int32_t* rmb = rmr + d.goff;
                 double* zb = z + d.goff;
                 for (int j = 0; j < d.ms; ++j) {
                     const int32_t p = sp[j];
                     oob |= (p < 0) | (p >= n_snp);
-                    nt_store(rsb + j, (uint32_t)p); nt_store(rcb + j, d.croff + j); nt_store(rmb + j, d.croff + d.m + j); nt_store(zb + j, sz[j]);
+                    nt_store(rsb + j, (uint32_t)p); nt_store(zb + j, sz[j]);
                 }
                 if (d.m > d.ms) {
                     const int32_t* lp = a->l_pos + a->l_off[b];
@@ -480,7 +481,7 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
                     for (int j = d.ms; j < d.m; ++j) {
                         const int32_t p = lp[j - d.ms];
                         oob |= (p < 0) | (p >= n_snp);
-                        nt_store(rsb + j, (uint32_t)p); nt_store(rcb + j, d.croff + j); nt_store(rmb + j, d.croff + d.m + j); nt_store(zb + j, lz[j - d.ms]);
+                        nt_store(rsb + j, (uint32_t)p); nt_store(zb + j, lz[j - d.ms]);
                     }
                 }
             }
@@ -489,7 +490,6 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
         };
         if (nthr == 1) fill(0, nb);
         else {
-            std::vector<std::thread>& th = fill_threads;
             int b0 = 0;
             for (int t = 0; t < nthr; ++t) {
                 // cut at equal SNP counts (block-index order; goff is monotone only in the resident layout, so count)
@@ -497,7 +497,7 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
                 int64_t acc = 0;
                 const int64_t share = (goff + nthr - 1) / nthr;
                 while (b1 < nb && (t == nthr - 1 || acc < share)) acc += P.blocks[b1++].m;
-                th.emplace_back(fill, b0, b1);
+                h->pool.submit(g_fill, [fill, b0, b1]() { fill(b0, b1); });      // (by value: `fill` leaves scope before the tasks run)
                 b0 = b1;
             }
         }
@@ -514,10 +514,27 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
     const int rec_edge = h->gram_pair ? 256 : 128;
     tiles_plain.p = reinterpret_cast<GramTile*>(blob.data() + P.o_tiles_plain); tiles_plain.cap = n_t1;
     tiles_miss.p = reinterpret_cast<GramTile*>(blob.data() + P.o_tiles_miss); tiles_miss.cap = n_t2;
-    std::thread tile_thread([&]() {
+    // (two helper threads -- the four-plane list is the longest -- while this thread builds the Cholesky step lists: the three
+    //  touch different fields)
+    h->pool.submit(g_tiles, [&]() {
+        for (Batch& B : P.batches) {
+            B.mtile0 = (int32_t)tiles_miss.size();
+            for (int i = 0; i < B.ord_n; ++i) {
+                const int b = P.order[B.ord_off + i];
+                const BlockDesc& d = P.blocks[b];
+                if (d.m == 0) continue;
+                const int nt64 = (d.mp + 63) / 64;
+                for (int ti = 0; ti < nt64; ++ti)
+                    for (int tj = 0; 128 * tj <= 64 * ti + 63; ++tj) tiles_miss.push_back({b, ti, tj, 0});
+            }
+            B.mtile1 = (int32_t)tiles_miss.size();
+        }
+        nt_fence();
+        P.n_tiles_miss = (int32_t)tiles_miss.size();
+    });
+    h->pool.submit(g_tiles, [&]() {
     for (Batch& B : P.batches) {
         B.tile0 = (int32_t)tiles_plain.size();
-        B.mtile0 = (int32_t)tiles_miss.size();
         B.ptile0 = (int32_t)tiles_pair.size();
         B.grow0 = INT64_MAX;
         B.grow1 = 0;
@@ -530,31 +547,29 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
             const int nt = (d.mp + 127) / 128;
             for (int ti = 0; ti < nt && want_plain; ++ti)
                 for (int tj = 0; tj <= ti; ++tj) tiles_plain.push_back({b, ti, tj, 0});
-            const int nt64 = (d.mp + 63) / 64;
-            for (int ti = 0; ti < nt64; ++ti)
-                for (int tj = 0; 128 * tj <= 64 * ti + 63; ++tj) tiles_miss.push_back({b, ti, tj, 0});
             const int np = (d.mp + rec_edge - 1) / rec_edge;
             for (int ti = 0; ti < np; ++ti)
                 for (int tj = 0; tj <= ti; ++tj) tiles_pair.push_back(TileRec{b, ti, tj, d.croff, d.goff, d.m, d.mp, d.ld, d.moff, 0});
         }
         if (B.grow0 == INT64_MAX) B.grow0 = B.grow1 = 0;
         B.tile1 = (int32_t)tiles_plain.size();
-        B.mtile1 = (int32_t)tiles_miss.size();
         B.ptile1 = (int32_t)tiles_pair.size();
     }
     nt_fence();
     P.n_tiles_plain = (int32_t)tiles_plain.size();
-    P.n_tiles_miss = (int32_t)tiles_miss.size();
     P.n_tiles_pair = (int32_t)tiles_pair.size();
     });
-    struct TileJoiner { std::thread& t; ~TileJoiner() { if (t.joinable()) t.join(); } } tile_joiner{tile_thread};
 
     // Cholesky step lists per batch
     BlobList<int32_t> diag_items;
     BlobList<int4> panel_items;
     diag_items.p = reinterpret_cast<int32_t*>(blob.data() + P.o_diag); diag_items.cap = n_diag_max;
     panel_items.p = reinterpret_cast<int4*>(blob.data() + P.o_panel); panel_items.cap = n_panel_max;
+    // Two passes.  Pass 1 (serial, arithmetic only): per batch and step the split-K factor and the list sizes, hence the
+    // place of every step's items; pass 2 (one host thread per batch): the items themselves -- 120 k non-temporal 16-byte
+    // stores at C3, 0.65 ms on one thread, and on the critical path of a streaming fit.
     int32_t n_groups = 0;
+    size_t n_diag_tot = 0, n_panel_tot = 0;
     for (Batch& B : P.batches) {
         const int32_t* members = P.order.data() + B.ord_off;
         B.tile_rows = (h->panel_tma && (h->tile64_mode >= 2 || (h->tile64_mode == 1 && !B.big))) ? 64 : 128;
@@ -566,45 +581,31 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
         int64_t batch_scratch = 0;
         for (int k = 0; k < kmax; ++k) {
             StepList& s = B.steps[k];
-            s.diag_off = (int32_t)diag_items.size();
-            s.panel_off = (int32_t)panel_items.size();
+            s.diag_off = (int32_t)n_diag_tot;
+            s.panel_off = (int32_t)n_panel_tot;
             // macro tiles of this step, then the split-K factor: when a step has few tiles but a long K
             // loop (late panels of big blocks), slice K so the step still fills the GPU
-            int ntiles = 0;
+            int ntiles = 0, nactive = 0, ndiag = 0;
             for (int i = 0; i < B.ord_n; ++i) {
                 const BlockDesc& d = P.blocks[members[i]];
                 if ((d.mp + 63) / 64 <= k) continue;
                 const int wk = std::min(64, d.mp - 64 * k);
-                ntiles += (d.nrows - (64 * k + wk) + TR - 1) / TR;
+                const int nt = (d.nrows - (64 * k + wk) + TR - 1) / TR;
+                ntiles += nt;
+                nactive += (nt > 0);
+                ++ndiag;
             }
             int nsl = 1;
             if (ntiles > 0) nsl = std::max(1, std::min({h->splitk_max, k / h->splitk_min_blocks, kTargetCtas / ntiles}));
             s.nsl = nsl;
             s.group_base = n_groups;
-            // macro tile 0 of every block goes first: its CTA also factors the next diagonal tile (fused), so it
-            // should start in the first wave of the launch
-            int32_t n_first = 0;
-            for (int pass = 0; pass < 2; ++pass) {
-                if (pass == 1) n_first = (int32_t)panel_items.size() - s.panel_off;
-                for (int i = 0; i < B.ord_n; ++i) {
-                    const int b = members[i];
-                    const BlockDesc& d = P.blocks[b];
-                    const int K = (d.mp + 63) / 64;
-                    if (K <= k) continue;
-                    if (pass == 0) diag_items.push_back(b);
-                    const int wk = std::min(64, d.mp - 64 * k);
-                    const int below = 64 * k + wk;
-                    const int nt = (d.nrows - below + TR - 1) / TR;
-                    for (int t = (pass == 0 ? 0 : 1); t < (pass == 0 ? std::min(nt, 1) : nt); ++t) {
-                        const int gid = (nsl > 1) ? n_groups++ : 0;
-                        for (int sl = 0; sl < nsl; ++sl) panel_items.push_back(make_int4(b, t, sl | (nsl << 8), gid));
-                    }
-                }
-            }
-            s.n_groups = n_groups - s.group_base;
-            s.n_first = n_first;
-            s.n_diag = (int32_t)diag_items.size() - s.diag_off;
-            s.n_panel = (int32_t)panel_items.size() - s.panel_off;
+            s.n_groups = (nsl > 1) ? ntiles : 0;
+            n_groups += s.n_groups;
+            s.n_first = nactive * nsl;                 // macro tile 0 of every block, all its slices
+            s.n_diag = ndiag;
+            s.n_panel = ntiles * nsl;
+            n_diag_tot += (size_t)s.n_diag;
+            n_panel_tot += (size_t)s.n_panel;
             batch_scratch = std::max<int64_t>(batch_scratch, (int64_t)s.n_groups * nsl * TR * 64);
         }
         // A chain-bound step (the whole next step fits in one wave of CTAs) defers the next diagonal tile to the
@@ -615,9 +616,46 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
         B.scratch_off = P.scratch_doubles;
         P.scratch_doubles += batch_scratch;
     }
+    diag_items.n = n_diag_tot;
+    panel_items.n = n_panel_tot;
+    if (n_diag_tot <= diag_items.cap && n_panel_tot <= panel_items.cap) {
+        auto fill_batch = [&](const Batch& B) {
+            const int32_t* members = P.order.data() + B.ord_off;
+            const int TR = B.tile_rows;
+            for (size_t k = 0; k < B.steps.size(); ++k) {
+                const StepList& s = B.steps[k];
+                int32_t* dg = diag_items.p + s.diag_off;
+                int4* pn = panel_items.p + s.panel_off;
+                const int nsl = s.nsl;
+                int32_t gid_next = s.group_base;
+                // macro tile 0 of every block goes first: its CTA also factors the next diagonal tile (fused), so it
+                // should start in the first wave of the launch
+                for (int pass = 0; pass < 2; ++pass) {
+                    for (int i = 0; i < B.ord_n; ++i) {
+                        const int b = members[i];
+                        const BlockDesc& d = P.blocks[b];
+                        if ((d.mp + 63) / 64 <= (int)k) continue;
+                        if (pass == 0) nt_copy(dg++, (int32_t)b);
+                        const int wk = std::min(64, d.mp - 64 * (int)k);
+                        const int nt = (d.nrows - (64 * (int)k + wk) + TR - 1) / TR;
+                        for (int t = (pass == 0 ? 0 : 1); t < (pass == 0 ? std::min(nt, 1) : nt); ++t) {
+                            const int gid = (nsl > 1) ? gid_next++ : 0;
+                            for (int sl = 0; sl < nsl; ++sl) nt_copy(pn++, make_int4(b, t, sl | (nsl << 8), gid));
+                        }
+                    }
+                }
+            }
+            nt_fence();
+        };
+        for (size_t bi = 0; bi < P.batches.size(); ++bi) {
+            const Batch* Bp = &P.batches[bi];
+            h->pool.submit(g_lists, [&fill_batch, Bp]() { fill_batch(*Bp); });
+        }
+        h->pool.wait(g_lists);             // (this thread works the queue too)
+    }
 
     nt_fence();
-    tile_thread.join();
+    h->pool.wait(g_tiles);
     if (tr) tr->mark("  plan: tile + step lists");
     // ---- the lists were written in place; the panel items close the blob
     if (tiles_plain.size() > tiles_plain.cap || tiles_miss.size() > tiles_miss.cap || tiles_pair.size() > tiles_pair.cap || diag_items.size() > diag_items.cap ||
@@ -627,8 +665,7 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
     P.lmaps_base = nullptr;
     P.n_groups = n_groups;
     P.blob_bytes = o;
-    for (std::thread& x : fill_threads) x.join();
-    fill_threads.clear();
+    h->pool.wait(g_fill);
     if (fill_bad.load()) return fail(h, DBSLMM_B200_ERR_ARG, "s_pos / l_pos out of range of the loaded .bed");
     if (tr) tr->mark("  plan: per-SNP arrays");
     std::memcpy(blob.data() + P.o_order, P.order.data(), sizeof(int32_t) * (size_t)nb);
@@ -751,12 +788,15 @@ int encode_lmaps(dbslmm_b200_handle* h, Plan& P) {
             if (r != CUDA_SUCCESS) bad.store((int)r);
         }
     };
-    const int nthr = (int)std::max<int64_t>(1, std::min<int64_t>({8, (int64_t)std::thread::hardware_concurrency(), (int64_t)nb / 128}));
+    const int nthr = (int)std::max<int64_t>(1, std::min<int64_t>({8, (int64_t)h->pool.size() + 1, (int64_t)nb / 128}));
     if (nthr == 1) work(0, nb);
     else {
-        std::vector<std::thread> th;
-        for (int t = 0; t < nthr; ++t) th.emplace_back(work, (int)((int64_t)nb * t / nthr), (int)((int64_t)nb * (t + 1) / nthr));
-        for (std::thread& x : th) x.join();
+        TaskGroup g;
+        for (int t = 0; t < nthr; ++t) {
+            const int b0 = (int)((int64_t)nb * t / nthr), b1 = (int)((int64_t)nb * (t + 1) / nthr);
+            h->pool.submit(g, [&work, b0, b1]() { work(b0, b1); });
+        }
+        h->pool.wait(g);
     }
     if (bad.load() && nthr > 1) { bad.store(0); work(0, nb); }      // once more on the calling thread
     if (bad.load()) return fail(h, DBSLMM_B200_ERR_CUDA, "cuTensorMapEncodeTiled failed for a block matrix (CUresult " + std::to_string(bad.load()) + ")");
@@ -794,6 +834,12 @@ int dbslmm_b200_create(int device, dbslmm_b200_handle** out) {
     if (!h) return DBSLMM_B200_ERR_NOMEM;
     h->device = device;
     h->n_sm = prop.multiProcessorCount;
+    {
+        // host workers: leave two hardware threads to the caller; DBSLMM_B200_HOST_THREADS overrides (0 = no pool: every helper task runs inline)
+        int n = (int)std::thread::hardware_concurrency() - 2;
+        if (const char* e = std::getenv("DBSLMM_B200_HOST_THREADS")) n = std::atoi(e);
+        h->pool.start(std::max(0, std::min(n, 14)));
+    }
     if (const char* e = std::getenv("DBSLMM_B200_FUSE_DIAG")) h->fuse_diag = (e[0] != '0');   // tuning switches
     if (const char* e = std::getenv("DBSLMM_B200_STREAM_BED")) h->stream_bed = (e[0] != '0');
     if (const char* e = std::getenv("DBSLMM_B200_SPLITK")) {      // "max,min_blocks"
@@ -859,7 +905,7 @@ void dbslmm_b200_destroy(dbslmm_b200_handle* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     DevBuf* bufs[] = {&h->bed, &h->stats, &h->codes, &h->sigma, &h->lbuf, &h->rowN, &h->rowS, &h->rowR,
-                      &h->planblob, &h->beta, &h->status, &h->intQ, &h->intA, &h->intN, &h->scratch, &h->counters, &h->wbuf, &h->vbed, &h->vstats, &h->vwork, &h->dflag, &h->dirty, &h->bflags, &h->packed, &h->rowC};
+                      &h->planblob, &h->beta, &h->status, &h->intQ, &h->intA, &h->intN, &h->scratch, &h->counters, &h->wbuf, &h->vbed, &h->vstats, &h->vwork, &h->dflag, &h->dirty, &h->bflags, &h->packed, &h->rowC, &h->rowmap};
     for (DevBuf* b : bufs) b->release();
     h->h_blob.release();
     h->h_out.release();
@@ -1005,12 +1051,15 @@ int upload_prepare(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, const P
             }
         };
         const int64_t tot = P.tot_s + P.tot_l;
-        const int nthr = (int)std::max<int64_t>(1, std::min<int64_t>({4, (int64_t)std::thread::hardware_concurrency(), tot / 131072}));
+        const int nthr = (int)std::max<int64_t>(1, std::min<int64_t>({8, (int64_t)h->pool.size() + 1, tot / 131072}));
         if (nthr == 1) scan(0, nb);
         else {
-            std::vector<std::thread> th;
-            for (int t = 0; t < nthr; ++t) th.emplace_back(scan, (int)((int64_t)nb * t / nthr), (int)((int64_t)nb * (t + 1) / nthr));
-            for (std::thread& x : th) x.join();
+            TaskGroup g;
+            for (int t = 0; t < nthr; ++t) {
+                const int b0 = (int)((int64_t)nb * t / nthr), b1 = (int)((int64_t)nb * (t + 1) / nthr);
+                h->pool.submit(g, [&scan, b0, b1]() { scan(b0, b1); });
+            }
+            h->pool.wait(g);
         }
         if (bad.load()) return fail(h, DBSLMM_B200_ERR_ARG, "fit: SNP row out of range of the .bed");
     }
@@ -1177,6 +1226,7 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
     CU_TRY(h, h->rowS.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(P.n_snp_rows, 1)));
     CU_TRY(h, h->rowR.ensure(sizeof(double) * (size_t)std::max<int64_t>(P.n_snp_rows, 1)));
     CU_TRY(h, h->rowC.ensure(sizeof(double2) * (size_t)std::max<int64_t>(P.n_snp_rows, 1)));
+    CU_TRY(h, h->rowmap.ensure(2 * sizeof(int32_t) * (size_t)std::max<int64_t>(P.n_snp_rows, 1)));
     const size_t n_out = (size_t)(P.tot_s + P.tot_l);
     const size_t n_res = quad ? (size_t)nb : n_out * nfold;          // doubles coming back: betas of all folds, or one z'Sigma z per block
     CU_TRY(h, h->beta.ensure(sizeof(double) * std::max<size_t>(n_res, 1)));
@@ -1208,8 +1258,8 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
     uint8_t* dblob = (uint8_t*)h->planblob.p;   // (re-pointed below if the plan has to be rebuilt)
     const BlockDesc* d_blocks = (const BlockDesc*)(dblob + P.o_blocks);
     const uint32_t* d_rowsrc = (const uint32_t*)(dblob + P.o_rowsrc);
-    const int32_t* d_crow = (const int32_t*)(dblob + P.o_crow);
-    const int32_t* d_mrow = (const int32_t*)(dblob + P.o_mrow);
+    const int32_t* d_crow = (const int32_t*)h->rowmap.p;                       // [n_snp_rows] code row, then [n_snp_rows] mask row
+    const int32_t* d_mrow = d_crow + std::max<int64_t>(P.n_snp_rows, 1);
     int32_t* d_bflags = (int32_t*)h->bflags.p;               // [nb] per-block flag, then one "any" word per batch
     int32_t* d_any = d_bflags + std::max(nb, 1);
     const double* d_z = (const double*)(dblob + P.o_z);
@@ -1259,6 +1309,11 @@ int fit_impl(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, bool streamin
                                       cudaMemcpyHostToDevice, st));
         CU_TRY(h, cudaMemcpyAsync(dblob + P.o_z, (uint8_t*)h->h_blob.p + P.o_z, sizeof(double) * (size_t)P.n_snp_rows,
                                   cudaMemcpyHostToDevice, st));
+    }
+    if (!reuse && nb > 0 && P.n_snp_rows > 0) {
+        // code-row / mask-row of every SNP row from the block descriptors (the stream already waits for the blob)
+        CU_TRY(h, launch_fill_rowmaps(d_blocks, nb, (int32_t*)h->rowmap.p, (int32_t*)h->rowmap.p + P.n_snp_rows, st));
+        ++n_launch;
     }
     { int rc = issue_val_upload(h); if (rc != DBSLMM_B200_OK) return rc; }     // an announced validation panel follows the fit's own copies
     CU_TRY(h, cudaMemsetAsync(d_status, 0, sizeof(int32_t) * (size_t)std::max(2 * nb, 1), st));

@@ -19,6 +19,8 @@ cudaError_t launch_decode_rows(const uint8_t* bed, int32_t n_ref, int32_t n_pad,
 // the fused unpack + Gram kernel
 cudaError_t launch_pack_rows(const uint8_t* bed, int32_t n_ref, int32_t n_pad, const uint32_t* row_src, int64_t g0, int64_t n_rows,
                              double tau, uint32_t* packed, int32_t* rowN, int32_t* rowS, double* rowR, double2* rowC, int n_sm, cudaStream_t st);
+// row_crow[g] / row_mrow[g] of every SNP row of every block: croff + j and croff + m + j
+cudaError_t launch_fill_rowmaps(const BlockDesc* blocks, int32_t n_blocks, int32_t* row_crow, int32_t* row_mrow, cudaStream_t st);
 int32_t decode_max_n_ref();          // largest n_ref the row-staging kernels (decoder, statistics) can take
 // flags[b] = block b has missing calls (from the decoder's counts), for the blocks in `list` (nullptr: 0..n_list-1);
 // *any |= flags
