@@ -158,7 +158,7 @@ struct dbslmm_b200_handle {
     // plan takes to build: with 4 regions (138 MB each at C3) the blob arrived 4.1 ms after the call started, with 6
     // (92 MB) it arrives at ~2.7 ms, and the first decode starts that much earlier.
     int n_regions = 6;
-    double first_region = 1.0;                   // SNP share of the FIRST bulk region relative to an equal share (< 1: a small first region crosses PCIe sooner, so the first decode / Gram / Cholesky start sooner; DBSLMM_B200_FIRST_REGION)
+    double first_region = 0.3;                   // SNP share of the FIRST bulk region relative to an equal share (< 1: a small first region crosses PCIe sooner, so the first decode / Gram / Cholesky start sooner; DBSLMM_B200_FIRST_REGION)
     double preplan_mb = 60.0;                    // ... and at most this much panel data is queued ahead of the plan blob
     // correlation builder for blocks without missing calls: the int8-row kernel fed by the decoder (default), or the fused
     // unpack + Gram from packed 2-bit rows (DBSLMM_B200_GRAM=packed).  Measured on C3 / C5: 1.8 / 10.8 ms against 3.9 / 34.7 ms --
@@ -460,7 +460,7 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
     // per-SNP rows (source .bed row, SNP-row index, z-score): the only O(#SNPs) part of the plan, filled by a few
     // host threads, each owning a contiguous range of blocks; the .bed row range check rides along
     {
-        static const int fill_max = std::getenv("DBSLMM_B200_FILL_THREADS") ? std::max(1, std::atoi(std::getenv("DBSLMM_B200_FILL_THREADS"))) : 6;       // (the pool also runs the two tile-list tasks and one step-list task per batch)
+        static const int fill_max = std::getenv("DBSLMM_B200_FILL_THREADS") ? std::max(1, std::atoi(std::getenv("DBSLMM_B200_FILL_THREADS"))) : 12;      // (the pool also runs two tile-list tasks and one step-list task per batch)
         const int nthr = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)fill_max, (int64_t)std::thread::hardware_concurrency(), goff / 65536}));
         auto fill = [&, rs, z](int b0, int b1) {
             int oob = 0;
@@ -514,51 +514,71 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
     const int rec_edge = h->gram_pair ? 256 : 128;
     tiles_plain.p = reinterpret_cast<GramTile*>(blob.data() + P.o_tiles_plain); tiles_plain.cap = n_t1;
     tiles_miss.p = reinterpret_cast<GramTile*>(blob.data() + P.o_tiles_miss); tiles_miss.cap = n_t2;
-    // (two helper threads -- the four-plane list is the longest -- while this thread builds the Cholesky step lists: the three
-    //  touch different fields)
-    h->pool.submit(g_tiles, [&]() {
+    // The places of every batch's tiles follow from block sizes alone (serial, arithmetic only); the entries themselves are
+    // written by one pool task per batch and list while this thread builds the Cholesky step lists.
+    {
+        size_t c_plain = 0, c_miss = 0, c_rec = 0;
         for (Batch& B : P.batches) {
-            B.mtile0 = (int32_t)tiles_miss.size();
+            B.tile0 = (int32_t)c_plain;
+            B.mtile0 = (int32_t)c_miss;
+            B.ptile0 = (int32_t)c_rec;
+            B.grow0 = INT64_MAX;
+            B.grow1 = 0;
             for (int i = 0; i < B.ord_n; ++i) {
-                const int b = P.order[B.ord_off + i];
-                const BlockDesc& d = P.blocks[b];
+                const BlockDesc& d = P.blocks[P.order[B.ord_off + i]];
                 if (d.m == 0) continue;
-                const int nt64 = (d.mp + 63) / 64;
-                for (int ti = 0; ti < nt64; ++ti)
-                    for (int tj = 0; 128 * tj <= 64 * ti + 63; ++tj) tiles_miss.push_back({b, ti, tj, 0});
+                B.grow0 = std::min<int64_t>(B.grow0, d.goff);
+                B.grow1 = std::max<int64_t>(B.grow1, (int64_t)d.goff + d.m);
+                const size_t nt = (size_t)(d.mp + 127) / 128, nt64 = (size_t)(d.mp + 63) / 64, np = (size_t)(d.mp + rec_edge - 1) / rec_edge;
+                if (want_plain) c_plain += nt * (nt + 1) / 2;
+                for (size_t ti = 0; ti < nt64; ++ti) c_miss += (64 * ti + 63) / 128 + 1;
+                c_rec += np * (np + 1) / 2;
             }
-            B.mtile1 = (int32_t)tiles_miss.size();
+            if (B.grow0 == INT64_MAX) B.grow0 = B.grow1 = 0;
+            B.tile1 = (int32_t)c_plain;
+            B.mtile1 = (int32_t)c_miss;
+            B.ptile1 = (int32_t)c_rec;
         }
-        nt_fence();
-        P.n_tiles_miss = (int32_t)tiles_miss.size();
-    });
-    h->pool.submit(g_tiles, [&]() {
-    for (Batch& B : P.batches) {
-        B.tile0 = (int32_t)tiles_plain.size();
-        B.ptile0 = (int32_t)tiles_pair.size();
-        B.grow0 = INT64_MAX;
-        B.grow1 = 0;
-        for (int i = 0; i < B.ord_n; ++i) {
-            const int b = P.order[B.ord_off + i];
-            const BlockDesc& d = P.blocks[b];
-            if (d.m == 0) continue;
-            B.grow0 = std::min<int64_t>(B.grow0, d.goff);
-            B.grow1 = std::max<int64_t>(B.grow1, (int64_t)d.goff + d.m);
-            const int nt = (d.mp + 127) / 128;
-            for (int ti = 0; ti < nt && want_plain; ++ti)
-                for (int tj = 0; tj <= ti; ++tj) tiles_plain.push_back({b, ti, tj, 0});
-            const int np = (d.mp + rec_edge - 1) / rec_edge;
-            for (int ti = 0; ti < np; ++ti)
-                for (int tj = 0; tj <= ti; ++tj) tiles_pair.push_back(TileRec{b, ti, tj, d.croff, d.goff, d.m, d.mp, d.ld, d.moff, 0});
-        }
-        if (B.grow0 == INT64_MAX) B.grow0 = B.grow1 = 0;
-        B.tile1 = (int32_t)tiles_plain.size();
-        B.ptile1 = (int32_t)tiles_pair.size();
+        tiles_plain.n = c_plain;
+        tiles_miss.n = c_miss;
+        tiles_pair.n = c_rec;
+        P.n_tiles_plain = (int32_t)c_plain;
+        P.n_tiles_miss = (int32_t)c_miss;
+        P.n_tiles_pair = (int32_t)c_rec;
     }
-    nt_fence();
-    P.n_tiles_plain = (int32_t)tiles_plain.size();
-    P.n_tiles_pair = (int32_t)tiles_pair.size();
-    });
+    if (tiles_plain.n <= tiles_plain.cap && tiles_miss.n <= tiles_miss.cap && tiles_pair.n <= tiles_pair.cap) {
+        for (size_t bi = 0; bi < P.batches.size(); ++bi) {
+            const Batch* Bp = &P.batches[bi];
+            h->pool.submit(g_tiles, [&P, &tiles_miss, Bp]() {
+                GramTile* out = tiles_miss.p + Bp->mtile0;
+                for (int i = 0; i < Bp->ord_n; ++i) {
+                    const int b = P.order[Bp->ord_off + i];
+                    const BlockDesc& d = P.blocks[b];
+                    if (d.m == 0) continue;
+                    const int nt64 = (d.mp + 63) / 64;
+                    for (int ti = 0; ti < nt64; ++ti)
+                        for (int tj = 0; 128 * tj <= 64 * ti + 63; ++tj) nt_copy(out++, GramTile{b, ti, tj, 0});
+                }
+                nt_fence();
+            });
+            h->pool.submit(g_tiles, [&P, &tiles_plain, &tiles_pair, Bp, want_plain, rec_edge]() {
+                GramTile* outp = tiles_plain.p + Bp->tile0;
+                TileRec* outr = tiles_pair.p + Bp->ptile0;
+                for (int i = 0; i < Bp->ord_n; ++i) {
+                    const int b = P.order[Bp->ord_off + i];
+                    const BlockDesc& d = P.blocks[b];
+                    if (d.m == 0) continue;
+                    const int nt = (d.mp + 127) / 128;
+                    for (int ti = 0; ti < nt && want_plain; ++ti)
+                        for (int tj = 0; tj <= ti; ++tj) nt_copy(outp++, GramTile{b, ti, tj, 0});
+                    const int np = (d.mp + rec_edge - 1) / rec_edge;
+                    for (int ti = 0; ti < np; ++ti)
+                        for (int tj = 0; tj <= ti; ++tj) nt_copy(outr++, TileRec{b, ti, tj, d.croff, d.goff, d.m, d.mp, d.ld, d.moff, 0});
+                }
+                nt_fence();
+            });
+        }
+    }
 
     // Cholesky step lists per batch
     BlobList<int32_t> diag_items;
@@ -618,6 +638,7 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
     }
     diag_items.n = n_diag_tot;
     panel_items.n = n_panel_tot;
+    if (tr) tr->mark("  plan: step sizes");
     if (n_diag_tot <= diag_items.cap && n_panel_tot <= panel_items.cap) {
         auto fill_batch = [&](const Batch& B) {
             const int32_t* members = P.order.data() + B.ord_off;
@@ -653,6 +674,7 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
         }
         h->pool.wait(g_lists);             // (this thread works the queue too)
     }
+    if (tr) tr->mark("  plan: step lists");
 
     nt_fence();
     h->pool.wait(g_tiles);
