@@ -191,7 +191,6 @@ struct dbslmm_b200_handle {
     int32_t dirty_n_ref = 0;             // ... for this panel width (another width = another default mask pattern)
     const void* dirty_codes = nullptr;   // ... and this code buffer
     PinBuf h_blob, h_out;
-    HostPool pool;                              // host worker threads (plan building, tensor maps, row-range scan)
     Plan plan;
 
     int32_t last_flags = 0, last_solver = 0, last_nfolds = 0;
@@ -230,6 +229,12 @@ inline void par_memcpy(void* dst, const void* src, size_t bytes) {
 }
 
 // DBSLMM_B200_TRACE=1: host-side wall-clock marks of one fit on stderr (tuning aid)
+// The process-wide pool of host worker threads (hostpool.hpp): plan building, tensor maps, the row-range scan.
+HostPool& host_pool() {
+    static HostPool pool;
+    return pool;
+}
+
 // Phase marks of a fit: NVTX markers always (free without a profiler attached; they line the phases up with the kernels in
 // an Nsight timeline), wall-clock lines on stderr with DBSLMM_B200_TRACE=1.
 struct Trace {
@@ -455,7 +460,7 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
     double* z = reinterpret_cast<double*>(blob.data() + P.o_z);
     // every helper task below references this frame: the guard waits for all of them on every way out
     TaskGroup g_fill, g_tiles, g_lists;
-    struct PoolGuard { HostPool& p; TaskGroup& a; TaskGroup& b; TaskGroup& c; ~PoolGuard() { p.wait(a); p.wait(b); p.wait(c); } } pool_guard{h->pool, g_fill, g_tiles, g_lists};
+    struct PoolGuard { HostPool& p; TaskGroup& a; TaskGroup& b; TaskGroup& c; ~PoolGuard() { p.wait(a); p.wait(b); p.wait(c); } } pool_guard{host_pool(), g_fill, g_tiles, g_lists};
     std::atomic<int> fill_bad{0};
     // per-SNP rows (source .bed row, SNP-row index, z-score): the only O(#SNPs) part of the plan, filled by a few
     // host threads, each owning a contiguous range of blocks; the .bed row range check rides along
@@ -497,7 +502,7 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
                 int64_t acc = 0;
                 const int64_t share = (goff + nthr - 1) / nthr;
                 while (b1 < nb && (t == nthr - 1 || acc < share)) acc += P.blocks[b1++].m;
-                h->pool.submit(g_fill, [fill, b0, b1]() { fill(b0, b1); });      // (by value: `fill` leaves scope before the tasks run)
+                host_pool().submit(g_fill, [fill, b0, b1]() { fill(b0, b1); });      // (by value: `fill` leaves scope before the tasks run)
                 b0 = b1;
             }
         }
@@ -549,7 +554,7 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
     if (tiles_plain.n <= tiles_plain.cap && tiles_miss.n <= tiles_miss.cap && tiles_pair.n <= tiles_pair.cap) {
         for (size_t bi = 0; bi < P.batches.size(); ++bi) {
             const Batch* Bp = &P.batches[bi];
-            h->pool.submit(g_tiles, [&P, &tiles_miss, Bp]() {
+            host_pool().submit(g_tiles, [&P, &tiles_miss, Bp]() {
                 GramTile* out = tiles_miss.p + Bp->mtile0;
                 for (int i = 0; i < Bp->ord_n; ++i) {
                     const int b = P.order[Bp->ord_off + i];
@@ -561,7 +566,7 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
                 }
                 nt_fence();
             });
-            h->pool.submit(g_tiles, [&P, &tiles_plain, &tiles_pair, Bp, want_plain, rec_edge]() {
+            host_pool().submit(g_tiles, [&P, &tiles_plain, &tiles_pair, Bp, want_plain, rec_edge]() {
                 GramTile* outp = tiles_plain.p + Bp->tile0;
                 TileRec* outr = tiles_pair.p + Bp->ptile0;
                 for (int i = 0; i < Bp->ord_n; ++i) {
@@ -670,14 +675,14 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
         };
         for (size_t bi = 0; bi < P.batches.size(); ++bi) {
             const Batch* Bp = &P.batches[bi];
-            h->pool.submit(g_lists, [&fill_batch, Bp]() { fill_batch(*Bp); });
+            host_pool().submit(g_lists, [&fill_batch, Bp]() { fill_batch(*Bp); });
         }
-        h->pool.wait(g_lists);             // (this thread works the queue too)
+        host_pool().wait(g_lists);             // (this thread works the queue too)
     }
     if (tr) tr->mark("  plan: step lists");
 
     nt_fence();
-    h->pool.wait(g_tiles);
+    host_pool().wait(g_tiles);
     if (tr) tr->mark("  plan: tile + step lists");
     // ---- the lists were written in place; the panel items close the blob
     if (tiles_plain.size() > tiles_plain.cap || tiles_miss.size() > tiles_miss.cap || tiles_pair.size() > tiles_pair.cap || diag_items.size() > diag_items.cap ||
@@ -687,7 +692,7 @@ int build_plan(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, co
     P.lmaps_base = nullptr;
     P.n_groups = n_groups;
     P.blob_bytes = o;
-    h->pool.wait(g_fill);
+    host_pool().wait(g_fill);
     if (fill_bad.load()) return fail(h, DBSLMM_B200_ERR_ARG, "s_pos / l_pos out of range of the loaded .bed");
     if (tr) tr->mark("  plan: per-SNP arrays");
     std::memcpy(blob.data() + P.o_order, P.order.data(), sizeof(int32_t) * (size_t)nb);
@@ -810,15 +815,15 @@ int encode_lmaps(dbslmm_b200_handle* h, Plan& P) {
             if (r != CUDA_SUCCESS) bad.store((int)r);
         }
     };
-    const int nthr = (int)std::max<int64_t>(1, std::min<int64_t>({8, (int64_t)h->pool.size() + 1, (int64_t)nb / 128}));
+    const int nthr = (int)std::max<int64_t>(1, std::min<int64_t>({8, (int64_t)host_pool().size() + 1, (int64_t)nb / 128}));
     if (nthr == 1) work(0, nb);
     else {
         TaskGroup g;
         for (int t = 0; t < nthr; ++t) {
             const int b0 = (int)((int64_t)nb * t / nthr), b1 = (int)((int64_t)nb * (t + 1) / nthr);
-            h->pool.submit(g, [&work, b0, b1]() { work(b0, b1); });
+            host_pool().submit(g, [&work, b0, b1]() { work(b0, b1); });
         }
-        h->pool.wait(g);
+        host_pool().wait(g);
     }
     if (bad.load() && nthr > 1) { bad.store(0); work(0, nb); }      // once more on the calling thread
     if (bad.load()) return fail(h, DBSLMM_B200_ERR_CUDA, "cuTensorMapEncodeTiled failed for a block matrix (CUresult " + std::to_string(bad.load()) + ")");
@@ -857,10 +862,13 @@ int dbslmm_b200_create(int device, dbslmm_b200_handle** out) {
     h->device = device;
     h->n_sm = prop.multiProcessorCount;
     {
-        // host workers: leave two hardware threads to the caller; DBSLMM_B200_HOST_THREADS overrides (0 = no pool: every helper task runs inline)
+        // host workers, ONE pool per process (all handles of a --gpus N command line share it): leave two hardware threads
+        // to the caller; under a one-process-per-GPU launcher (LOCAL_WORLD_SIZE set) a process takes its share of the
+        // machine; DBSLMM_B200_HOST_THREADS overrides (0 = no pool: every helper task runs inline)
         int n = (int)std::thread::hardware_concurrency() - 2;
+        if (const char* e = std::getenv("LOCAL_WORLD_SIZE")) { const int lws = std::max(1, std::atoi(e)); n = (int)std::thread::hardware_concurrency() / lws - 1; }
         if (const char* e = std::getenv("DBSLMM_B200_HOST_THREADS")) n = std::atoi(e);
-        h->pool.start(std::max(0, std::min(n, 14)));
+        host_pool().start(std::max(0, std::min(n, 14)));
     }
     if (const char* e = std::getenv("DBSLMM_B200_FUSE_DIAG")) h->fuse_diag = (e[0] != '0');   // tuning switches
     if (const char* e = std::getenv("DBSLMM_B200_STREAM_BED")) h->stream_bed = (e[0] != '0');
@@ -1073,15 +1081,15 @@ int upload_prepare(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, const P
             }
         };
         const int64_t tot = P.tot_s + P.tot_l;
-        const int nthr = (int)std::max<int64_t>(1, std::min<int64_t>({8, (int64_t)h->pool.size() + 1, tot / 131072}));
+        const int nthr = (int)std::max<int64_t>(1, std::min<int64_t>({8, (int64_t)host_pool().size() + 1, tot / 131072}));
         if (nthr == 1) scan(0, nb);
         else {
             TaskGroup g;
             for (int t = 0; t < nthr; ++t) {
                 const int b0 = (int)((int64_t)nb * t / nthr), b1 = (int)((int64_t)nb * (t + 1) / nthr);
-                h->pool.submit(g, [&scan, b0, b1]() { scan(b0, b1); });
+                host_pool().submit(g, [&scan, b0, b1]() { scan(b0, b1); });
             }
-            h->pool.wait(g);
+            host_pool().wait(g);
         }
         if (bad.load()) return fail(h, DBSLMM_B200_ERR_ARG, "fit: SNP row out of range of the .bed");
     }
