@@ -554,7 +554,11 @@ __device__ __forceinline__ void panel_body(const BlockDesc& bd, const int4 item,
         // W_k comes from a diagonal CTA of this launch (lower blockIdx, so it is resident or done): acquire, then load
         if (tid == 0) {
             const volatile int32_t* f = dflag + item.x;
-            while (*f < k + 1) __nanosleep(40);
+            uint32_t spins = 0;                 // bounded like the TMA kernel's wait (see there)
+            while (*f < k + 1) {
+                __nanosleep(40);
+                if (++spins > (1u << 27)) { atomicOr(&status[item.x], 4); break; }
+            }
             __threadfence();
         }
         __syncthreads();
@@ -1009,7 +1013,13 @@ chol_panel_tma_kernel(const BlockDesc* __restrict__ blocks, const int4* __restri
         if (wait_w && load_w && tid == 0) {
             // W_k is being produced by a diagonal CTA of THIS launch (lower blockIdx: resident or done)
             const volatile int32_t* fl = dflag + item.x;
-            while (*fl < k + 1) __nanosleep(40);
+            // bounded: the diagonal CTAs have lower block indices and are dispatched first, so the flag comes within tens of
+            // microseconds; if it has not come after ~5 s something is broken, and a flagged block beats a hung device
+            uint32_t spins = 0;
+            while (*fl < k + 1) {
+                __nanosleep(40);
+                if (++spins > (1u << 27)) { atomicOr(&status[item.x], 4); break; }      // DBSLMM_B200_BLK_SYNC_TIMEOUT
+            }
             __threadfence();
             fence_proxy_async();
             issue_w();

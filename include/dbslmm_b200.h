@@ -46,6 +46,8 @@ extern "C" {
 #define DBSLMM_B200_BLK_NOT_SPD     1   /* Cholesky pivot <= 0 or NaN (monomorphic SNP => NaN column,
                                            the reference poisons the whole block the same way)      */
 #define DBSLMM_B200_BLK_PCG_MAXITER 2   /* PCG hit maxiter ("Matrix is Singular", dbslmmfit.cpp:664) */
+#define DBSLMM_B200_BLK_SYNC_TIMEOUT 4  /* an in-launch wait of the block solver gave up after ~5 s (never observed; the block's
+                                           betas are invalid) */
 
 /* solver selection */
 #define DBSLMM_B200_SOLVER_CHOLESKY 0   /* exact: batched FP64 Cholesky of the bordered block system  */
