@@ -12,11 +12,16 @@
 // the reference.  Blocks without missing calls need only Q
 // (A_ij = S_i, N_ij = n): one accumulator plane; blocks with missing calls use four.
 //
-// Kernel shape (both kernels are persistent, one CTA per SM walking a tile list, warp-specialised):
+// Kernel shape (all kernels are persistent, walking a tile list, warp-specialised; details at each kernel):
 //   warp 0   TMA producer: int8 code tiles [rows x 128 B], SWIZZLE_128B, multi-stage ring
-//   warp 1   TMEM allocator + single-thread tcgen05.mma.kind::i8 issuer (s32 accumulators double-buffered in TMEM)
-//   warps 2-9 epilogue: tcgen05.ld -> FP64 transform -> coalesced stores of the LOWER tile, overlapping the next
-//            tile's main loop.
+//   warp 1   TMEM allocator + tcgen05.mma.kind::i8 issuer (whole-warp loop, one elected lane issues; s32 accumulators in
+//            TMEM: four of 128 columns in the one-plane kernels, two sets of four planes in the four-plane kernel)
+//   warps 2-9 epilogue: tcgen05.ld -> FP64 transform -> coalesced stores of the LOWER tile, overlapping the next tiles'
+//            main loops.
+//   gram_persistent_kernel  one plane, 128 x 128 tiles, one CTA per SM (default)
+//   gram_pair_kernel        one plane, 256 x 256 super tiles by CTA pairs (tcgen05 cta_group::2; DBSLMM_B200_GRAM=pair)
+//   gram_packed_kernel      one plane from packed 2-bit rows, unpacked in shared memory (DBSLMM_B200_GRAM=packed)
+//   gram_missing_kernel     four planes (blocks with missing calls)
 // The A operand is the J (column) side and the B operand the I (row) side, so a TMEM lane
 // holds one Sigma column and consecutive lanes store consecutive addresses of one Sigma row.
 // Which kernel owns a block is decided ON THE DEVICE: block_flags_kernel (decode.cu) sets flags[b] from the counts the
@@ -896,7 +901,7 @@ gram_missing_kernel(const __grid_constant__ CUtensorMap tmapJ, const __grid_cons
     if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
-// One-plane kernel over `a.tiles` (128 x 128 tiles; blocks whose flag is set are skipped).
+// One-plane kernel over `a.recs` (128 x 128 tile records; blocks whose flag is set are skipped).
 cudaError_t launch_gram(const CUtensorMap& tmap, const GramArgs& a, cudaStream_t st) {
     if (a.n_tiles == 0) return cudaSuccess;
     cudaError_t e;
@@ -915,7 +920,7 @@ cudaError_t launch_gram(const CUtensorMap& tmap, const GramArgs& a, cudaStream_t
     return cudaGetLastError();
 }
 
-// One-plane CTA-pair kernel over `a.tiles` (256 x 256 super tiles; blocks whose flag is set are skipped).
+// One-plane CTA-pair kernel over `a.recs` (256 x 256 super-tile records; blocks whose flag is set are skipped).
 cudaError_t launch_gram_pair(const CUtensorMap& tmap, const CUtensorMap& tmap64, const GramArgs& a, cudaStream_t st) {
     if (a.n_tiles == 0) return cudaSuccess;
     static int max_pairs[2] = {0, 0};
