@@ -80,6 +80,11 @@ struct StepList {
 // (fit_args.bed), batches are also the upload units: big classes first, the bulk class cut into sub-batches, so a
 // batch's decode -> Gram -> factorisation starts as soon as ITS rows have crossed PCIe.
 constexpr int kMaxBatches = 12;
+// Rough device rates for the upload-order rule of the streaming fit (make_batches) and nothing else -- measured on C3
+// (DESIGN.md 4): a panel step of a chain-bound block ~45 us, the bulk factorisation ~23 Tflop/s, the Gram ~1.2 Pop/s.
+constexpr double kChainStepUs = 45.0;
+constexpr double kBulkFlopPerUs = 23.0e6;
+constexpr double kGramOpsPerUs = 1.2e9;
 struct Batch {
     int cls = 0;                          // size class (timing slot)
     bool big = false;                     // some member has mp > 1024: cluster back substitution
@@ -104,6 +109,7 @@ struct Plan {
     std::vector<int32_t> order;                       // concatenated batch member lists (big classes first)
     std::vector<Batch> batches;
     bool streaming = false;                           // layout in batch order (else block-index order)
+    bool chain_bound = false;                         // the big classes' dependency chains outlast the bulk's throughput time (make_batches)
     std::vector<int32_t> up_order;                    // streaming: the order in which the batches' rows cross PCIe
     int32_t n_tiles_plain = 0, n_tiles_miss = 0, n_tiles_pair = 0;
     int64_t scratch_doubles = 0;
@@ -153,11 +159,13 @@ struct dbslmm_b200_handle {
     int l2_pf = 0;                               // panel kernel: L2 tensor prefetch distance in 16-wide K chunks (0 = off: measured 13.0 ms without, 13.1 with 2 or 4)
     // panel step kernel: TMA/mbarrier pipeline (default) or the cp.async version (DBSLMM_B200_PANEL=legacy)
     int upload_bulk_first = 1;                   // streaming fit: bulk regions sent before the big classes (see make_batches)
+    bool upload_auto = true;                     // ... only when the fit is throughput-bound and the first region is small (make_batches); an explicit DBSLMM_B200_UPLOAD_BULK_FIRST switches the rule off
     // streaming fit: the bulk is cut into this many regions (upload units).  The FIRST region goes out before the plan is
     // built and the plan blob queues behind it on the copy engine, so it should take about as long to cross PCIe as the
     // plan takes to build: with 4 regions (138 MB each at C3) the blob arrived 4.1 ms after the call started, with 6
     // (92 MB) it arrives at ~2.7 ms, and the first decode starts that much earlier.
     int n_regions = 6;
+    int region_min_blocks = 256;                 // ... when the bulk has at least this many blocks (and 100,000 SNPs), else it is ONE region (DBSLMM_B200_REGION_MIN_BLOCKS)
     double first_region = 0.3;                   // SNP share of the FIRST bulk region relative to an equal share (< 1: a small first region crosses PCIe sooner, so the first decode / Gram / Cholesky start sooner; DBSLMM_B200_FIRST_REGION)
     double preplan_mb = 60.0;                    // ... and at most this much panel data is queued ahead of the plan blob
     // correlation builder for blocks without missing calls: the int8-row kernel fed by the decoder (default), or the fused
@@ -264,6 +272,7 @@ int make_batches(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, 
     const std::vector<int>& bounds = h->cls_bounds;
     const int nc = (int)bounds.size() + 1;
     std::vector<std::vector<int32_t>> by_cls((size_t)nc);
+    double chain_us = 0.0, bulk_us = 0.0;
     for (int b = 0; b < nb; ++b) {
         const int ms = a->s_off[b + 1] - a->s_off[b];
         const int ml = a->l_off ? a->l_off[b + 1] - a->l_off[b] : 0;
@@ -277,7 +286,16 @@ int make_batches(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, 
         int c = 0;
         while (c < nc - 1 && K > bounds[c]) ++c;
         by_cls[c].push_back(b);          // m == 0 blocks land in class 0: no tiles, no steps, they only exist
+        const double m = (double)d.m;
+        if (K > kBulkMaxPanels) chain_us = std::max(chain_us, kChainStepUs * (double)(K + 1));
+        else bulk_us += (m * m * m / 3.0 + 2.0 * m * m) / kBulkFlopPerUs + (double)h->n_pad * m * (m + 1.0) / kGramOpsPerUs;
     }
+    // CHAIN-bound fit (typically one rank's shard of a multi-GPU run: a 3,000-SNP block is 47 serial panel steps next to a
+    // bulk of a millisecond or two): the big classes' dependency chains are the critical path, the bulk runs in their shadow.
+    // (Measured and dropped: padding the bulk batches' shared-memory request so that only two of their CTAs fit on an SM and
+    // the third slot stays free for the chains' CTAs -- the bulk slowed down as expected, 1.92 -> 2.09 ms, but a chain step
+    // stayed at 61 us against 42 us alone: the chains do not wait for CTA slots, they share the SMs' FP64 pipes.)
+    P.chain_bound = chain_us > bulk_us;
     P.order.reserve(nb);
     auto add_batch = [&](std::vector<int32_t>& sub, int cls) {
         if (sub.empty()) return;
@@ -309,7 +327,7 @@ int make_batches(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, 
     }
     int64_t tot = 0;
     for (int b : bulk) tot += P.blocks[b].m;
-    const int nsub = (bulk.size() >= 256 && tot >= 100000) ? h->n_regions : 1;
+    const int nsub = ((int)bulk.size() >= h->region_min_blocks && tot >= 100000) ? h->n_regions : 1;
     size_t i = 0;
     int64_t acc = 0;
     // region sb ends at SNP count `target`: equal shares, except that the first region may be a fraction of a share
@@ -327,7 +345,16 @@ int make_batches(dbslmm_b200_handle* h, const dbslmm_b200_fit_args* a, Plan& P, 
     const int nbt = (int)P.batches.size();
     int n_big = 0;
     while (n_big < nbt && P.batches[n_big].cls > 1) ++n_big;          // bulk regions carry class 0 / 1
-    const int lead = std::max(0, std::min(h->upload_bulk_first, nbt - n_big));
+    int lead = std::max(0, std::min(h->upload_bulk_first, nbt - n_big));
+    if (h->upload_auto && lead > 0 && n_big > 0) {
+        // ... unless the fit is chain-bound (above) or the first bulk region is too big to send ahead of the plan blob (few
+        // bulk blocks are ONE region): everything queued on the copy engine ahead of the big classes -- and ahead of the plan
+        // blob, which follows the pre-plan uploads -- then delays the whole fit (rank 0 of 8 at C3: 5.1-5.7 -> 4.5-4.8 ms per call, profiles/r05u_shard_upload_order.txt).
+        double first_mb = 0.0;
+        for (int j = 0; j < P.batches[n_big].ord_n; ++j)
+            first_mb += (double)P.blocks[P.order[P.batches[n_big].ord_off + j]].m * (double)h->pitch / 1.0e6;
+        if (P.chain_bound || first_mb > h->preplan_mb) lead = 0;
+    }
     for (int i = 0; i < lead; ++i) P.up_order.push_back(n_big + i);
     for (int i = 0; i < n_big; ++i) P.up_order.push_back(i);
     for (int i = n_big + lead; i < nbt; ++i) P.up_order.push_back(i);
@@ -881,9 +908,10 @@ int dbslmm_b200_create(int device, dbslmm_b200_handle** out) {
     if (const char* e = std::getenv("DBSLMM_B200_L2_PF")) h->l2_pf = std::min(255, std::max(0, std::atoi(e)));
     if (const char* e = std::getenv("DBSLMM_B200_NEXT_PF")) h->next_pf = std::atoi(e) != 0;
     if (const char* e = std::getenv("DBSLMM_B200_ZEROCOPY_BETA")) h->zero_copy_beta = (e[0] != '0');
-    if (const char* e = std::getenv("DBSLMM_B200_UPLOAD_BULK_FIRST")) h->upload_bulk_first = std::atoi(e);
+    if (const char* e = std::getenv("DBSLMM_B200_UPLOAD_BULK_FIRST")) { h->upload_bulk_first = std::atoi(e); h->upload_auto = false; }
     if (const char* e = std::getenv("DBSLMM_B200_REGIONS")) h->n_regions = std::max(1, std::min(kMaxBatches - 4, std::atoi(e)));
     if (const char* e = std::getenv("DBSLMM_B200_PREPLAN_MB")) h->preplan_mb = std::atof(e);
+    if (const char* e = std::getenv("DBSLMM_B200_REGION_MIN_BLOCKS")) h->region_min_blocks = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("DBSLMM_B200_FIRST_REGION")) h->first_region = std::min(1.0, std::max(0.02, std::atof(e)));
     if (const char* e = std::getenv("DBSLMM_B200_GRAM_HINT")) h->gram_hint = std::atoi(e);
     if (const char* e = std::getenv("DBSLMM_B200_GRAM")) {

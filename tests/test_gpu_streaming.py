@@ -1,6 +1,8 @@
 """Streaming fit: the reference panel travels with dbslmm_b200_fit (fit_args.bed), as DBSLMMFIT::est receives its
 bed_str (reference scr/dbslmmfit.hpp:38-67); the upload is cut into batches and overlaps the fit.  Results must be
 IDENTICAL (same kernels, same arithmetic, only a different schedule and device layout) to load_bed + fit."""
+import functools
+
 import numpy as np
 import pytest
 
@@ -54,6 +56,42 @@ def test_streaming_many_blocks_sub_batches(engine):
     rr = engine.fit(*csr, **kw)
     # (sub-batches may pick another split-K factor than the whole class: same arithmetic, different summation order)
     assert relmax(rs["beta_s"], rr["beta_s"]) <= 1e-12 and relmax(rs["beta_l"], rr["beta_l"]) <= 1e-12
+
+
+@functools.lru_cache(maxsize=1)
+def _order_case():
+    """>= 256 bulk blocks and >= 100k SNPs (the bulk is cut into regions) next to three big blocks; betas of the exact oracle."""
+    rng = np.random.default_rng(12)
+    sizes = [int(x) for x in rng.integers(300, 440, size=285)] + [1300, 2100, 1100]
+    w = synth.make_workload(98, sizes, 400, missing_rate=0.0, frac_large=0.01)
+    bs, bl, _, _ = O.est(w["bed"], 400, 50_000, 2e-4, *csr_of(w), threads=4, mode=O.MODE_EXACT)
+    return w, bs, bl
+
+
+@pytest.mark.parametrize("order", ["0", "1", None])
+def test_streaming_upload_order_does_not_change_the_result(engine, order, monkeypatch):
+    """The big classes go out first when their dependency chains outlast the bulk (one rank's shard of a multi-GPU run, and
+    this workload), a bulk region first when the fit is throughput-bound (the whole genome); DBSLMM_B200_UPLOAD_BULK_FIRST
+    forces either.  Same batches, same kernels: the betas do not depend on it."""
+    w, bs, bl = _order_case()
+    csr = csr_of(w)
+    kw = dict(sigma_s=[2e-4], n_obs=50_000)
+    if order is None:
+        monkeypatch.delenv("DBSLMM_B200_UPLOAD_BULK_FIRST", raising=False)
+    else:
+        monkeypatch.setenv("DBSLMM_B200_UPLOAD_BULK_FIRST", order)
+    eng = _abi.Engine(0)                     # the switches are read when a handle is created
+    try:
+        rs = eng.fit(*csr, bed=w["bed"], n_ref=400, **kw)
+        assert rs["n_bad"] == 0
+        rs2 = eng.fit(*csr, bed=w["bed"], n_ref=400, **kw)
+        assert np.array_equal(rs["beta_s"], rs2["beta_s"]) and np.array_equal(rs["beta_l"], rs2["beta_l"])
+    finally:
+        eng.close()
+    engine.load_bed(w["bed"], 400)
+    rr = engine.fit(*csr, **kw)
+    assert relmax(rs["beta_s"], rr["beta_s"]) <= 1e-12 and relmax(rs["beta_l"], rr["beta_l"]) <= 1e-12
+    assert relmax(rs["beta_s"][0], bs) <= 1e-10 and relmax(rs["beta_l"][0], bl) <= 1e-10
 
 
 def test_streaming_subset_of_rows_and_unordered_blocks(engine):
