@@ -141,7 +141,10 @@ DBSLMM_B200_API const char* dbslmm_b200_last_error(const dbslmm_b200_handle* h);
  * dbslmm_b200_fit planning -- overlaps it), so `bed` must stay valid and unchanged until the
  * next dbslmm_b200_snp_stats / dbslmm_b200_fit / dbslmm_b200_load_bed / dbslmm_b200_destroy
  * on this handle has returned.  (fit_args.bed, by contrast, is no longer needed once that
- * fit call returns.) */
+ * fit call returns.)
+ * Limit: n_ref <= 409,344 individuals (the decoder stages two whole .bed rows of ceil(n_ref/4) bytes per warp in 200 KB
+ * of shared memory; the reference, which reads byte by byte, has none).  Larger panels are refused with
+ * DBSLMM_B200_ERR_ARG and a message naming the limit, here and in dbslmm_b200_fit(fit_args.bed). */
 DBSLMM_B200_API int  dbslmm_b200_load_bed(dbslmm_b200_handle* h, const uint8_t* bed, int64_t n_snp, int32_t n_ref);
 
 /* MAF pre-pass product (dtpr.cpp:93-102, 361-362): maf after mean imputation; optional
